@@ -1,0 +1,161 @@
+/* include/stemk.h -- C ABI of the B200 stem-kernel / string-kernel Gram-matrix builder.
+ *
+ * This is the drop-in boundary for ONE path of keio-bioinformatics/stem_kernel: evaluating a
+ * kernel functor over many sequence pairs.  In the reference that path is entered through
+ *
+ *     value_type Kernel::operator()(const Data&, const Data&) const
+ *         stem_kernel_lite/stem_kernel.h:18, string_kernel.h:20, def_kernel.h:21,45,72,100,130,156,184
+ *         string_kernel/string_kernel.h:19 (naive kernel on std::string)
+ *
+ * called one pair at a time from the Calc* functors of common/kernel_matrix.cpp (lines 50, 95,
+ * 104, 159, 168, 176) on behalf of the four KernelMatrix entry points
+ *
+ *     calculate(train, kernel, normalize, n_th)                 kernel_matrix.h:67-69   -> stemk_gram
+ *     calculate(test, train, kernel, norm_test, normalize,n_th) kernel_matrix.h:71-74   -> stemk_cross
+ *     calculate(row, example, train, sv_index, kernel, ...)     kernel_matrix.h:76-82   -> stemk_cross (1 row)
+ *     diagonal(diag, train, sv_index, kernel, n_th)             kernel_matrix.h:94-97   -> stemk_diag
+ *
+ * A reference maintainer binds these entry points from a KernelMatrix specialisation (see
+ * INTEGRATION.md); stem_kernel_b200/host/ holds a C++ mirror of the reference's kernel classes and
+ * KernelMatrix built on them.
+ *
+ * Conventions: plain pointers and sizes only; all host buffers are owned by the caller and may be
+ * freed as soon as the call returns; device buffers are owned by the context / set.  Every function
+ * returns STEMK_OK (0) or a negative error code; stemk_last_error() gives the message.  There is no
+ * CPU fallback: without a CUDA device every compute entry point fails with STEMK_ERR_CUDA.
+ * All arithmetic is IEEE fp64 on the device (the reference's ValueType is double,
+ * stem_kernel.cpp:103, string_kernel.cpp:139).
+ */
+#ifndef STEMK_H_
+#define STEMK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STEMK_OK 0
+#define STEMK_ERR_ARG (-1)    /* bad argument / inconsistent descriptor */
+#define STEMK_ERR_CUDA (-2)   /* CUDA runtime error or no device */
+#define STEMK_ERR_NOMEM (-3)
+#define STEMK_ERR_STATE (-4)  /* set does not carry what the kernel needs (e.g. no DAG for a stem kernel) */
+
+/* Kernel selection = the reference's kernel classes (stem_kernel_lite/def_kernel.h, main.cpp:180-215). */
+typedef enum {
+  STEMK_SI_STEM = 0,      /* SiStemKernel:     stem DAG kernel, match/mismatch node score (def_kernel.h:12)   */
+  STEMK_SU_STEM = 1,      /* SuStemKernel:     stem DAG kernel, exp(beta*RIBOSUM) node score (def_kernel.h:36) */
+  STEMK_SI_STEM_STR = 2,  /* SiStemStrKernel = SiStem + StringKernel(gap,match,mismatch) (def_kernel.h:59)   */
+  STEMK_SU_STEM_STR = 3,  /* SuStemStrKernel = SuStem + StringKernel(gap,alpha)          (def_kernel.h:87)   */
+  STEMK_LSU_STEM = 4,     /* beta*log(SuStem)                                            (def_kernel.h:114)  */
+  STEMK_LSU_STR = 5,      /* alpha*log(StringKernel(gap,alpha))                          (def_kernel.h:140)  */
+  STEMK_LSU_STEM_STR = 6, /* sum of the two above                                        (def_kernel.h:166)  */
+  STEMK_STR_SUBST = 7,    /* lite StringKernel(gap, alpha)             (stem_kernel_lite/string_kernel.cpp:11) */
+  STEMK_STR_SIMPLE = 8,   /* lite StringKernel(gap, match, mismatch)   (stem_kernel_lite/string_kernel.cpp:24) */
+  STEMK_STR_NAIVE = 9     /* exact-match gap-weighted kernel on raw characters (string_kernel/string_kernel.cpp:11) */
+} stemk_kind;
+
+typedef struct {
+  int32_t kind;        /* stemk_kind */
+  uint32_t len_band;   /* --length-band; 0 = no band (stem_kernel.cpp:46-48) */
+  double loop_gap;     /* -g  (stem) */
+  double beta;         /* -b  (stem, RIBOSUM weight) */
+  double stack;        /* -s  (stem, --no-ribosum match) */
+  double covar;        /* -v  (stem, --no-ribosum mismatch) */
+  double gap;          /* -G  (string); STR_NAIVE: the float-parsed -g of string_kernel/main.cpp:40, widened */
+  double alpha;        /* -a  (string, RIBOSUM weight) */
+  double match;        /* --match    (string, --no-ribosum) */
+  double mismatch;     /* --mismatch (string, --no-ribosum) */
+} stemk_params;
+
+/* A set of sequence records, flattened: the fields of the reference's MData
+ * (stem_kernel_lite/data.h:33-37; DAG::Node / DAG::Edge, dag.h:17-157) as concatenated arrays.
+ * Node order inside a record must be the reference's (children before parents, data.cpp:193-244).
+ * A record with zero nodes is legal (no pair reached the threshold: k_stem = 0). */
+typedef struct {
+  uint32_t n_seqs;
+  /* DAG: per-record node ranges, then CSR over all nodes */
+  const uint32_t* node_off;     /* [n_seqs+1] */
+  const uint32_t* node_first;   /* [n_nodes] 0-based column of the 5' base */
+  const uint32_t* node_last;    /* [n_nodes] first==last marks a leaf */
+  const float* node_weight;     /* [n_nodes] */
+  const uint32_t* edge_off;     /* [n_nodes+1] */
+  const uint32_t* edge_to;      /* [n_edges] child, as an index LOCAL to its record */
+  const uint32_t* edge_gaps;    /* [n_edges] */
+  const float* edge_weight;     /* [n_edges] */
+  const uint32_t* bpf_off;      /* [n_nodes+1] */
+  const uint8_t* bpf_a;         /* [n_bpf] */
+  const uint8_t* bpf_b;         /* [n_bpf] */
+  const float* bpf_freq;        /* [n_bpf] */
+  const uint32_t* root_off;     /* [n_seqs+1] */
+  const uint32_t* root;         /* [n_roots] local node indices */
+  /* sequence profile */
+  const uint32_t* col_off;      /* [n_seqs+1] */
+  const float* profile;         /* [n_cols*5]  A,C,G,U,GAP per column (common/profile.h:15-16) */
+  const float* n_rows;          /* [n_seqs]    ProfileSequence::n_seqs() */
+  const uint32_t* weight_off;   /* [n_seqs+1]  empty range = record has no weight vector */
+  const float* col_weight;      /* [n_weights] MData::weight (data.cpp:437-453) */
+  const uint8_t* text;          /* [n_cols] raw characters of the first row (STEMK_STR_NAIVE); may be NULL */
+} stemk_seqset_desc;
+
+typedef struct stemk_ctx stemk_ctx;
+typedef struct stemk_set stemk_set;
+
+/* library / device */
+const char* stemk_version(void);
+int stemk_device_count(void);
+
+/* context: one CUDA device + one kernel object (immutable, like the reference's kernel classes) */
+int stemk_create(stemk_ctx** ctx, const stemk_params* params, int device);
+void stemk_destroy(stemk_ctx* ctx);
+const char* stemk_last_error(const stemk_ctx* ctx); /* ctx may be NULL: last creation error */
+
+/* upload a flattened set (copied; derived per-record tables are built here) */
+int stemk_upload(stemk_ctx* ctx, const stemk_seqset_desc* desc, stemk_set** set);
+void stemk_set_free(stemk_ctx* ctx, stemk_set* set);
+uint32_t stemk_set_size(const stemk_set* set);
+
+/* KernelMatrix::calculate(train, kernel, normalize) -- kernel_matrix.cpp:485-575.
+ * out: n*n row-major, both triangles.  normalize: K_ij /= sqrt(K_ii K_jj), K_ii = 1. */
+int stemk_gram(stemk_ctx* ctx, const stemk_set* train, int normalize, double* out);
+
+/* KernelMatrix::calculate(test, train, ...) and the static one-row calculate -- kernel_matrix.cpp:635-754.
+ * out: n_test*n_train row-major.  sv_index (may be NULL, n_sv = 0): only those train columns are
+ * computed, the others are left untouched in out.  self_out (may be NULL): k(test_i, test_i).
+ * normalize != 0: out_ij /= sqrt(self_i * k(train_j,train_j)) as kernel_matrix.cpp:735-748
+ * (train diagonals are computed internally). */
+int stemk_cross(stemk_ctx* ctx, const stemk_set* test, const stemk_set* train, const uint32_t* sv_index,
+                uint32_t n_sv, int normalize, double* out, double* self_out);
+
+/* KernelMatrix::diagonal -- kernel_matrix.cpp:578-633.  out: n; with sv_index only those entries are written. */
+int stemk_diag(stemk_ctx* ctx, const stemk_set* train, const uint32_t* sv_index, uint32_t n_sv, double* out);
+
+/* Arbitrary pair list: out[k] = kernel(x[xi[k]], y[yi[k]]).  The three calls above are built on it;
+ * multi-GPU drivers use it for their tile of the matrix. */
+int stemk_pairs(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, size_t n_pairs, const uint32_t* xi,
+                const uint32_t* yi, double* out);
+
+/* Same, asynchronous on `stream` (a cudaStream_t, or NULL) with DEVICE index/result buffers.
+ * xi/yi must stay valid until the stream reaches the end of the call's work. */
+int stemk_pairs_device(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, size_t n_pairs,
+                       const uint32_t* d_xi, const uint32_t* d_yi, double* d_out, void* stream);
+
+/* Work model of SURVEY 8(d), per pair: DP cells and algorithmic flops
+ * (stem: 2*U_match + 3*U_bf + 3*U_skip; string: 9, 7 or 4(+3 per match) per cell). Host only. */
+int stemk_pair_cost(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, size_t n_pairs, const uint32_t* xi,
+                    const uint32_t* yi, double* cells, double* flops);
+
+/* Launch accounting for benchmarks: kernels launched / device ms (CUDA events on the library's own
+ * stream) spent inside them since the last reset. */
+void stemk_stats_reset(stemk_ctx* ctx);
+void stemk_stats_get(const stemk_ctx* ctx, uint64_t* launches, double* stem_ms, double* string_ms);
+
+/* FP64 FMA micro-benchmark on the context's device: returns sustained Tflop/s (the roofline
+ * denominator, since MEASURED_PEAKS.json carries no fp64 entry). */
+int stemk_fp64_peak(stemk_ctx* ctx, double seconds, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STEMK_H_ */
