@@ -1,0 +1,23 @@
+/* oracle/stemk_oracle.h -- TEST INFRASTRUCTURE, NOT PRODUCT CODE (see stemk_oracle.c). */
+#ifndef STEMK_ORACLE_H_
+#define STEMK_ORACLE_H_
+#include "../include/stemk.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+double oracle_pair(const stemk_params* p, const stemk_seqset_desc* X, uint32_t xi, const stemk_seqset_desc* Y,
+                   uint32_t yi);
+void oracle_pairs(const stemk_params* p, const stemk_seqset_desc* X, const stemk_seqset_desc* Y, size_t n_pairs,
+                  const uint32_t* xi, const uint32_t* yi, double* out);
+void oracle_gram(const stemk_params* p, const stemk_seqset_desc* S, int normalize, double* out);
+void oracle_diag(const stemk_params* p, const stemk_seqset_desc* S, const uint32_t* sv_index, uint32_t n_sv,
+                 double* out);
+void oracle_cross(const stemk_params* p, const stemk_seqset_desc* T, const stemk_seqset_desc* S,
+                  const uint32_t* sv_index, uint32_t n_sv, int normalize, double* out, double* self_out);
+long oracle_print(const double* m, size_t rows, size_t cols, const int* labels, char* buf, long cap);
+void oracle_pair_cost(const stemk_params* p, const stemk_seqset_desc* X, uint32_t xi, const stemk_seqset_desc* Y,
+                      uint32_t yi, double* cells, double* flops);
+#ifdef __cplusplus
+}
+#endif
+#endif

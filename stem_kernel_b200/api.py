@@ -1,0 +1,267 @@
+"""Python mirror of the reference's kernel classes and KernelMatrix, over the C ABI (include/stemk.h).
+
+    SuStemKernel / SiStemKernel / SuStemStrKernel / ...   stem_kernel_lite/def_kernel.h:12-192
+    StringKernel                                           stem_kernel_lite/string_kernel.h:8-30
+    NaiveStringKernel                                      string_kernel/string_kernel.h:8-22
+    KernelMatrix.calculate / calculate_test / diagonal / print
+                                                           common/kernel_matrix.h:67-107, .cpp:485-770
+
+A kernel object is immutable (like the reference's); KernelMatrix owns an n x n (or n_test x n_train)
+numpy matrix and the labels, and prints LIBSVM "precomputed kernel" text.  All arithmetic happens in the
+CUDA library; this module only marshals arrays."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from .hostlib import MData, SeqSet
+
+
+class StemkError(RuntimeError):
+    pass
+
+
+class Context:
+    """stemk_ctx: one device + one kernel object."""
+
+    def __init__(self, params, device=0):
+        self.params = params
+        self.h = C.c_void_p()
+        rc = L.lib().stemk_create(C.byref(self.h), C.byref(params), device)
+        if rc != L.OK:
+            raise StemkError(f"stemk_create failed ({rc}): {L.lib().stemk_last_error(None).decode()}")
+        self.device = device
+
+    def _check(self, rc):
+        if rc != L.OK:
+            raise StemkError(f"stemk error {rc}: {L.lib().stemk_last_error(self.h).decode()}")
+
+    def close(self):
+        if self.h:
+            L.lib().stemk_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload(self, mdatas):
+        return DeviceSet(self, mdatas)
+
+    # ---- KernelMatrix entry points
+    def gram(self, dset, normalize=False):
+        n = len(dset)
+        out = np.zeros((n, n))
+        self._check(L.lib().stemk_gram(self.h, dset.h, int(normalize), out.ctypes.data))
+        return out
+
+    def cross(self, test, train, sv_index=None, normalize=False, want_self=True, init=0.0):
+        out = np.full((len(test), len(train)), init, dtype=np.float64)
+        selfv = np.zeros(len(test))
+        sv = np.ascontiguousarray(sv_index if sv_index is not None else [], dtype=np.uint32)
+        self._check(L.lib().stemk_cross(self.h, test.h, train.h, sv.ctypes.data if len(sv) else None, len(sv),
+                                        int(normalize), out.ctypes.data, selfv.ctypes.data if want_self else None))
+        return out, selfv
+
+    def diag(self, train, sv_index=None, init=0.0):
+        out = np.full(len(train), init, dtype=np.float64)
+        sv = np.ascontiguousarray(sv_index if sv_index is not None else [], dtype=np.uint32)
+        self._check(L.lib().stemk_diag(self.h, train.h, sv.ctypes.data if len(sv) else None, len(sv), out.ctypes.data))
+        return out
+
+    def pairs(self, x, y, xi, yi):
+        xi = np.ascontiguousarray(xi, dtype=np.uint32)
+        yi = np.ascontiguousarray(yi, dtype=np.uint32)
+        out = np.zeros(len(xi))
+        self._check(L.lib().stemk_pairs(self.h, x.h, y.h, len(xi), xi.ctypes.data, yi.ctypes.data, out.ctypes.data))
+        return out
+
+    def pairs_device(self, x, y, n_pairs, d_xi, d_yi, d_out, stream=None):
+        """Device pointers (ints, e.g. torch.Tensor.data_ptr()); asynchronous on `stream` (cudaStream_t as int)."""
+        self._check(L.lib().stemk_pairs_device(self.h, x.h, y.h, n_pairs, d_xi, d_yi, d_out, stream))
+
+    def pair_cost(self, x, y, xi, yi):
+        xi = np.ascontiguousarray(xi, dtype=np.uint32)
+        yi = np.ascontiguousarray(yi, dtype=np.uint32)
+        cells, flops = np.zeros(len(xi)), np.zeros(len(xi))
+        self._check(L.lib().stemk_pair_cost(self.h, x.h, y.h, len(xi), xi.ctypes.data, yi.ctypes.data,
+                                            cells.ctypes.data, flops.ctypes.data))
+        return cells, flops
+
+    def stats_reset(self):
+        L.lib().stemk_stats_reset(self.h)
+
+    def stats(self):
+        n, a, b = C.c_uint64(), C.c_double(), C.c_double()
+        L.lib().stemk_stats_get(self.h, C.byref(n), C.byref(a), C.byref(b))
+        return dict(launches=n.value, stem_ms=a.value, string_ms=b.value)
+
+    def fp64_peak(self, seconds=0.5):
+        t = C.c_double()
+        self._check(L.lib().stemk_fp64_peak(self.h, seconds, C.byref(t)))
+        return t.value
+
+
+class DeviceSet:
+    """stemk_set: a flattened, compiled and uploaded list of MData records."""
+
+    def __init__(self, ctx, mdatas):
+        self.ctx = ctx
+        self.h = C.c_void_p()
+        if isinstance(mdatas, SeqSet):
+            flat = mdatas
+        else:
+            flat = SeqSet(mdatas)
+        desc = flat.desc()
+        ctx._check(L.lib().stemk_upload(ctx.h, C.byref(desc), C.byref(self.h)))
+        self.n = len(flat)
+
+    def __len__(self):
+        return self.n
+
+    def free(self):
+        if self.h and self.ctx.h:
+            L.lib().stemk_set_free(self.ctx.h, self.h)
+        self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+# ---------------------------------------------------------------- kernel classes (def_kernel.h)
+class _Kernel:
+    kind = None
+
+    def __init__(self, device=0, **kw):
+        self.params = L.make_params(self.kind, **kw)
+        self.ctx = Context(self.params, device)
+
+    def __call__(self, x, y):
+        """value_type operator()(const Data&, const Data&) const -- one pair (x, y are MData)."""
+        sx, sy = self.ctx.upload([x]), self.ctx.upload([y])
+        return float(self.ctx.pairs(sx, sy, [0], [0])[0])
+
+
+class SiStemKernel(_Kernel):
+    kind = L.SI_STEM
+
+    def __init__(self, loop_gap=0.2, stack=1.3, covar=0.8, len_band=10, device=0):
+        super().__init__(device, loop_gap=loop_gap, stack=stack, covar=covar, len_band=len_band)
+
+
+class SuStemKernel(_Kernel):
+    kind = L.SU_STEM
+
+    def __init__(self, loop_gap=0.2, beta=0.3, len_band=10, device=0):
+        super().__init__(device, loop_gap=loop_gap, beta=beta, len_band=len_band)
+
+
+class SiStemStrKernel(_Kernel):
+    kind = L.SI_STEM_STR
+
+    def __init__(self, loop_gap=0.2, stack=1.3, covar=0.8, gap=0.8, match=1.0, mismatch=0.8, len_band=10, device=0):
+        super().__init__(device, loop_gap=loop_gap, stack=stack, covar=covar, gap=gap, match=match, mismatch=mismatch,
+                         len_band=len_band)
+
+
+class SuStemStrKernel(_Kernel):
+    kind = L.SU_STEM_STR
+
+    def __init__(self, alpha=0.2, beta=0.3, loop_gap=0.2, gap=0.8, len_band=10, device=0):
+        super().__init__(device, alpha=alpha, beta=beta, loop_gap=loop_gap, gap=gap, len_band=len_band)
+
+
+class LSuStemKernel(_Kernel):
+    kind = L.LSU_STEM
+
+    def __init__(self, loop_gap=0.2, beta=0.3, len_band=10, device=0):
+        super().__init__(device, loop_gap=loop_gap, beta=beta, len_band=len_band)
+
+
+class LSuStrKernel(_Kernel):
+    kind = L.LSU_STR
+
+    def __init__(self, gap=0.8, alpha=0.2, device=0):
+        super().__init__(device, gap=gap, alpha=alpha)
+
+
+class LSuStemStrKernel(_Kernel):
+    kind = L.LSU_STEM_STR
+
+    def __init__(self, alpha=0.2, beta=0.3, loop_gap=0.2, gap=0.8, len_band=10, device=0):
+        super().__init__(device, alpha=alpha, beta=beta, loop_gap=loop_gap, gap=gap, len_band=len_band)
+
+
+class StringKernel(_Kernel):
+    """Lite string kernel: StringKernel(gap, alpha) or StringKernel(gap, match, mismatch)."""
+
+    def __init__(self, gap=0.8, alpha=None, match=None, mismatch=None, device=0):
+        if alpha is not None:
+            self.kind = L.STR_SUBST
+            super().__init__(device, gap=gap, alpha=alpha)
+        else:
+            self.kind = L.STR_SIMPLE
+            super().__init__(device, gap=gap, match=1.0 if match is None else match,
+                             mismatch=0.8 if mismatch is None else mismatch)
+
+
+class NaiveStringKernel(_Kernel):
+    """string_kernel/ binary: the gap is parsed as a float and widened (string_kernel/main.cpp:26,40,93)."""
+    kind = L.STR_NAIVE
+
+    def __init__(self, gap=1.0, device=0):
+        super().__init__(device, gap=float(np.float32(gap)))
+
+
+# ---------------------------------------------------------------- KernelMatrix (kernel_matrix.h)
+class KernelMatrix:
+    def __init__(self):
+        self.matrix = np.zeros((0, 0))
+        self.labels = []
+        self.self_ = np.zeros(0)
+
+    def calculate(self, train, kernel, normalize=False, n_th=1):
+        """calculate(train, kernel, normalize, n_th): train = list of (label, MData).  n_th is accepted for
+        signature compatibility; the work is scheduled over the GPU's CTAs instead of host threads."""
+        dset = kernel.ctx.upload([d for _, d in train])
+        self.matrix = kernel.ctx.gram(dset, normalize)
+        self.labels = [lab for lab, _ in train]
+        return self
+
+    def calculate_test(self, test, train, kernel, norm_test=False, normalize=False, n_th=1, sv_index=None):
+        """calculate(test, train, kernel, norm_test, normalize, n_th) (+ the sv_index of the row variant)."""
+        dtest = kernel.ctx.upload([d for _, d in test])
+        dtrain = kernel.ctx.upload([d for _, d in train])
+        self.matrix, selfv = kernel.ctx.cross(dtest, dtrain, sv_index, normalize, want_self=norm_test or normalize)
+        self.self_ = selfv
+        self.labels = [lab for lab, _ in test]
+        return self
+
+    @staticmethod
+    def diagonal(train, kernel, sv_index=None, n_th=1):
+        dtrain = kernel.ctx.upload([d for _, d in train])
+        return kernel.ctx.diag(dtrain, sv_index)
+
+    def print(self, out):
+        """KernelMatrix::print (kernel_matrix.cpp:756-770): `label 0:<row> 1:v 2:v ... ` per line,
+        values with the C++ stream default of 6 significant digits."""
+        out.write(format_matrix(self.matrix, self.labels))
+
+
+def format_matrix(m, labels):
+    lines = []
+    for i in range(m.shape[0]):
+        parts = [f"{labels[i]} 0:{i + 1} "]
+        parts.extend(f"{j + 1}:{_g6(m[i, j])} " for j in range(m.shape[1]))
+        lines.append("".join(parts) + "\n")
+    return "".join(lines)
+
+
+def _g6(v):
+    s = "%g" % v
+    return s

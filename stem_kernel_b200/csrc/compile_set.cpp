@@ -1,0 +1,236 @@
+// stem_kernel_b200/csrc/compile_set.cpp -- host side of stemk_upload(): turns the flattened MData
+// records of a stemk_seqset_desc into the per-record tables the CUDA kernels read (RecDev /
+// SetView in stemk_internal.h).  Pure host C++ (no CUDA), O(nodes + edges + columns) per record.
+//
+// What is folded in here, and which reference lines it comes from:
+//   a      = g*g*node_weight                         node_score(xx,i), score_table.h:26-29
+//   ce     = g^gaps * edge_weight, g^k by repeated multiplication like SimpleEdgeScore::initialize
+//            (score_table.cpp:61-77) so the powers are the reference's bit for bit
+//   el,ql  = what the leaf rows/columns of the reference's G0 table contribute: G0(leaf,leaf)=1,
+//            G0(i,leaf)=a_i*ql_i, G0(leaf,j)=0 for non-leaf j   (stem_kernel.cpp:39-42,62-77)
+//   paths  = number of root->node paths; sum_roots K0 == sum_ij paths_x(i) paths_y(j) MATCH(i,j)
+//            because the K recursion (stem_kernel.cpp:56,65,75) only counts paths
+//   levels = longest-path layering of the non-leaf nodes (rows of one level are independent)
+#include <algorithm>
+#include <cmath>
+#include <thread>
+
+#include "ribosum85_60.inc"
+#include "stemk_internal.h"
+
+namespace stemk {
+
+void make_tables(const stemk_params& p, KernelTables* t) {
+  const bool stem_simple = p.kind == STEMK_SI_STEM || p.kind == STEMK_SI_STEM_STR;
+  const bool str_simple = p.kind == STEMK_SI_STEM_STR || p.kind == STEMK_STR_SIMPLE;
+  for (int ab = 0; ab < 16; ++ab)
+    for (int cd = 0; cd < 16; ++cd)
+      t->pair_tab[ab * 16 + cd] =
+          stem_simple ? (ab == cd ? p.stack : p.covar) : std::exp(kRibosumPair[ab * 16 + cd] * p.beta);
+  for (int a = 0; a < 4; ++a)
+    for (int b = 0; b < 4; ++b)
+      t->subst[a * 4 + b] = str_simple ? (a == b ? p.match : p.mismatch) : std::exp(kRibosumSingle[a * 4 + b] * p.alpha);
+}
+
+namespace {
+
+struct RecOut {  // one record's share, appended to the CompiledSet in record order afterwards
+  RecDev hdr;
+  std::vector<double> a, el, ql, paths, gapt, bfreq, ce, bfq, cw;
+  std::vector<uint32_t> len, coff, cidx, lev_off, boff;
+  std::vector<uint8_t> bcode, bab, ccode, text;
+  std::vector<float> prof;
+  std::vector<uint32_t> deg_all;
+  uint32_t n_all = 0, e_all = 0, max_rows = 0;
+  std::string err;
+};
+
+void compile_record(const stemk_seqset_desc& s, uint32_t r, double g, RecOut* o) {
+  const uint32_t n0 = s.node_off[r], n = s.node_off[r + 1] - n0;
+  const uint32_t* first = s.node_first + n0;
+  const uint32_t* last = s.node_last + n0;
+  const float* w = s.node_weight + n0;
+  const uint32_t* eoff = s.edge_off + n0;
+  const uint32_t* boff = s.bpf_off + n0;
+  const uint32_t c0 = s.col_off[r], L = s.col_off[r + 1] - c0;
+  const float* prof = s.profile + (size_t)5 * c0;
+  const float nrows = s.n_rows[r];
+  RecDev& h = o->hdr;
+  h = RecDev();
+  h.L = L;
+  h.n_rows = nrows;
+  o->n_all = n;
+  o->e_all = n ? eoff[n] - eoff[0] : 0;
+
+  // ---- columns
+  o->ccode.resize(L); o->cw.resize(L); o->prof.resize((size_t)4 * L); o->text.resize(L);
+  const uint32_t w0 = s.weight_off[r], nw = s.weight_off[r + 1] - w0;
+  if (nw != 0 && nw != L) { o->err = "weight vector length differs from the sequence length"; return; }
+  bool simple_cols = true;
+  for (uint32_t c = 0; c < L; ++c) {
+    const float* p = prof + 5 * c;
+    int ones = 0, zeros = 0, which = 0;
+    for (int k = 0; k < 4; ++k) {
+      if (p[k] == 1.0f) { ++ones; which = k; }
+      if (p[k] == 0.0f) ++zeros;
+      o->prof[4 * c + k] = p[k];
+    }
+    uint8_t code = 5;
+    if (ones == 1 && zeros == 3) code = (uint8_t)which;
+    else if (zeros == 4) code = 4;
+    if (code == 5) simple_cols = false;
+    o->ccode[c] = code;
+    o->cw[c] = nw ? (double)s.col_weight[w0 + c] : 1.0;
+    o->text[c] = s.text ? s.text[c0 + c] : 0;
+  }
+  h.flags = (nw ? REC_HAS_WEIGHT : 0u) | (simple_cols ? REC_SIMPLE_COLS : 0u);
+
+  // ---- DAG
+  if (n == 0) {
+    h.N = 0; h.nlev = 0; h.flags |= REC_SIMPLE_BPF;
+    o->coff.assign(1, 0); o->lev_off.assign(1, 0); o->boff.assign(1, 0);
+    return;
+  }
+  uint32_t max_gaps = 0;
+  for (uint32_t u = 0; u < n; ++u) {
+    if (eoff[u + 1] < eoff[u]) { o->err = "edge offsets not monotone"; return; }
+    for (uint32_t e = eoff[u]; e < eoff[u + 1]; ++e) {
+      if (s.edge_to[e] >= u) { o->err = "DAG nodes must list children before parents"; return; }
+      max_gaps = std::max(max_gaps, s.edge_gaps[e]);
+    }
+  }
+  std::vector<double> gpow(max_gaps + 1);
+  gpow[0] = 1.0;
+  for (uint32_t k = 1; k <= max_gaps; ++k) gpow[k] = gpow[k - 1] * g;
+
+  std::vector<char> leaf(n);
+  std::vector<uint32_t> level(n, 0), newidx(n, 0xffffffffu);
+  std::vector<double> px(n), ql(n), el(n), av(n), pl(n), paths(n, 0.0);
+  uint32_t nlev = 0;
+  for (uint32_t u = 0; u < n; ++u) {
+    leaf[u] = eoff[u] == eoff[u + 1];
+    if (leaf[u]) { px[u] = 1.0; pl[u] = 1.0; continue; }
+    av[u] = g * g * (double)w[u];
+    double q = 0.0, e_leaf = 0.0, p_l = 0.0;
+    uint32_t lv = 0;
+    for (uint32_t e = eoff[u]; e < eoff[u + 1]; ++e) {
+      const uint32_t c = s.edge_to[e];
+      const double ce = gpow[s.edge_gaps[e]] * (double)s.edge_weight[e];
+      q += ce * px[c];
+      p_l += pl[c];
+      if (leaf[c]) e_leaf += ce; else lv = std::max(lv, level[c] + 1);
+    }
+    ql[u] = q; el[u] = e_leaf; px[u] = av[u] * q; pl[u] = p_l; level[u] = lv;
+    nlev = std::max(nlev, lv + 1);
+  }
+  // root -> node path counts (parents come after children in the record, so walk backwards)
+  double plr = 0.0;
+  uint32_t lr = 0;
+  for (uint32_t k = s.root_off[r]; k < s.root_off[r + 1]; ++k) {
+    const uint32_t u = s.root[k];
+    if (u >= n) { o->err = "root index out of range"; return; }
+    paths[u] += 1.0;
+    plr += pl[u];
+    if (leaf[u]) ++lr;
+  }
+  for (uint32_t u = n; u-- > 0;)
+    for (uint32_t e = eoff[u]; e < eoff[u + 1]; ++e) paths[s.edge_to[e]] += paths[u];
+  h.plr = plr; h.lr = lr;
+
+  // ---- level order
+  std::vector<uint32_t> order;
+  order.reserve(n);
+  o->lev_off.assign(nlev + 1, 0);
+  for (uint32_t u = 0; u < n; ++u) if (!leaf[u]) ++o->lev_off[level[u] + 1];
+  for (uint32_t l = 0; l < nlev; ++l) {
+    o->max_rows = std::max(o->max_rows, o->lev_off[l + 1]);
+    o->lev_off[l + 1] += o->lev_off[l];
+  }
+  {
+    std::vector<uint32_t> fill(o->lev_off.begin(), o->lev_off.end() - 1);
+    order.assign(o->lev_off[nlev], 0);
+    for (uint32_t u = 0; u < n; ++u) if (!leaf[u]) { newidx[u] = fill[level[u]]; order[fill[level[u]]++] = u; }
+  }
+  const uint32_t N = (uint32_t)order.size();
+  h.N = N; h.nlev = nlev;
+  o->a.resize(N); o->el.resize(N); o->ql.resize(N); o->paths.resize(N); o->gapt.resize(N); o->bfreq.resize(N);
+  o->len.resize(N); o->bcode.resize(N); o->coff.assign(N + 1, 0); o->boff.assign(N + 1, 0);
+  bool simple_bpf = true;
+  for (uint32_t k = 0; k < N; ++k) {
+    const uint32_t u = order[k];
+    o->a[k] = av[u]; o->el[k] = el[u]; o->ql[k] = ql[u]; o->paths[k] = paths[u];
+    if (first[u] >= L) { o->err = "node position outside the sequence"; return; }
+    o->gapt[k] = (double)prof[5 * first[u] + 4] / (double)nrows;
+    o->len[k] = last[u] - first[u];
+    o->deg_all.push_back(eoff[u + 1] - eoff[u]);
+    for (uint32_t e = eoff[u]; e < eoff[u + 1]; ++e) {
+      const uint32_t c = s.edge_to[e];
+      if (leaf[c]) continue;
+      o->cidx.push_back(newidx[c]);
+      o->ce.push_back(gpow[s.edge_gaps[e]] * (double)s.edge_weight[e]);
+    }
+    o->coff[k + 1] = (uint32_t)o->cidx.size();
+    const uint32_t nb = boff[u + 1] - boff[u];
+    for (uint32_t b = boff[u]; b < boff[u + 1]; ++b) {
+      if (s.bpf_a[b] > 3 || s.bpf_b[b] > 3) { o->err = "base code out of range in a base-pair profile"; return; }
+      o->bab.push_back((uint8_t)(s.bpf_a[b] * 4 + s.bpf_b[b]));
+      o->bfq.push_back((double)s.bpf_freq[b]);
+    }
+    o->boff[k + 1] = (uint32_t)o->bab.size();
+    if (nb == 1) { o->bcode[k] = o->bab.back(); o->bfreq[k] = o->bfq.back(); }
+    else { o->bcode[k] = 0xFF; o->bfreq[k] = 0.0; simple_bpf = false; }
+  }
+  if (simple_bpf) h.flags |= REC_SIMPLE_BPF;
+}
+
+template <class T>
+void append(std::vector<T>& dst, const std::vector<T>& src) { dst.insert(dst.end(), src.begin(), src.end()); }
+
+}  // namespace
+
+std::string compile_set(const stemk_seqset_desc& s, double g, int n_threads, CompiledSet* out) {
+  const uint32_t n = s.n_seqs;
+  std::vector<RecOut> recs(n);
+  if (n_threads < 1) n_threads = 1;
+  n_threads = std::min<int>(n_threads, std::max<uint32_t>(1, n / 16));
+  if (n_threads <= 1) {
+    for (uint32_t r = 0; r < n; ++r) compile_record(s, r, g, &recs[r]);
+  } else {
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; ++t)
+      th.push_back(std::thread([&, t]() { for (uint32_t r = t; r < n; r += n_threads) compile_record(s, r, g, &recs[r]); }));
+    for (auto& x : th) x.join();
+  }
+  CompiledSet& c = *out;
+  c = CompiledSet();
+  c.rec.resize(n);
+  for (uint32_t r = 0; r < n; ++r) {
+    RecOut& o = recs[r];
+    if (!o.err.empty()) return "record " + std::to_string(r) + ": " + o.err;
+    RecDev h = o.hdr;
+    h.node0 = (uint32_t)c.a.size();
+    h.coff0 = (uint32_t)c.coff.size();
+    h.lev0 = (uint32_t)c.lev_off.size();
+    h.boff0 = (uint32_t)c.boff.size();
+    h.col0 = (uint32_t)c.ccode.size();
+    // child / profile offsets become absolute so the kernels index cidx/ce/bab/bfq directly
+    const uint32_t e0 = (uint32_t)c.cidx.size(), b0 = (uint32_t)c.bab.size();
+    for (auto& v : o.coff) v += e0;
+    for (auto& v : o.boff) v += b0;
+    append(c.a, o.a); append(c.el, o.el); append(c.ql, o.ql); append(c.paths, o.paths); append(c.gapt, o.gapt);
+    append(c.bfreq, o.bfreq); append(c.len, o.len); append(c.bcode, o.bcode); append(c.coff, o.coff);
+    append(c.cidx, o.cidx); append(c.ce, o.ce); append(c.lev_off, o.lev_off); append(c.boff, o.boff);
+    append(c.bab, o.bab); append(c.bfq, o.bfq); append(c.ccode, o.ccode); append(c.cw, o.cw);
+    append(c.prof, o.prof); append(c.text, o.text); append(c.deg_all, o.deg_all);
+    c.rec[r] = h;
+    c.n_nodes_all.push_back(o.n_all);
+    c.n_edges_all.push_back(o.e_all);
+    c.max_level_rows.push_back(o.max_rows);
+    if (o.n_all) c.has_dag = true;
+    c.max_N = std::max(c.max_N, h.N);
+    c.max_L = std::max(c.max_L, h.L);
+  }
+  return "";
+}
+
+}  // namespace stemk

@@ -1,0 +1,51 @@
+// stem_kernel_b200/csrc/kernels.cuh -- launch descriptors shared by the .cu files.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "stemk_internal.h"
+
+namespace stemk {
+
+struct StemLaunch {
+  SetView X, Y;
+  const uint32_t* xi;  // device pair list: out[k] = k_stem(X[xi[k]], Y[yi[k]])
+  const uint32_t* yi;
+  unsigned long long n_pairs;
+  double* out;
+  unsigned long long* counter;  // work queue head (zeroed before launch)
+  double* scratch;              // per-CTA slab holding the G0 rows of the pair in flight
+  unsigned long long scratch_stride;  // doubles per CTA
+  const double* pair_tab;       // 256 doubles
+  uint32_t len_band;
+  uint32_t rb;                  // rows per row block
+  uint32_t ny_cap;              // largest Ny of this launch (shared-memory carve-up)
+};
+
+struct StringLaunch {
+  SetView X, Y;
+  const uint32_t* xi;
+  const uint32_t* yi;
+  unsigned long long n_pairs;
+  double* out;
+  unsigned long long* counter;
+  double* carry;                // per-warp column carries for sequences wider than one tile
+  unsigned long long carry_stride;  // doubles per warp
+  const double* subst;          // 16 doubles
+  double gap;
+  int naive;                    // exact-match kernel on raw characters
+};
+
+// host-callable launchers (defined in the .cu files); all asynchronous on `stream`
+size_t stem_smem_bytes(uint32_t rb, uint32_t ny_cap);
+cudaError_t launch_stem(const StemLaunch& p, int grid, size_t smem, cudaStream_t stream);
+int stem_max_ctas_per_sm(size_t smem);
+cudaError_t launch_string(const StringLaunch& p, int cw, int grid, cudaStream_t stream);
+int string_warps_per_cta();
+cudaError_t launch_combine(int kind, double alpha, double beta, const double* stem, const double* str, double* out,
+                           unsigned long long n, cudaStream_t stream);
+cudaError_t launch_scatter_square(const double* vals, const uint32_t* xi, const uint32_t* yi, unsigned long long n_pairs,
+                                  double* matrix, uint32_t n, cudaStream_t stream);
+cudaError_t launch_normalize_square(double* matrix, uint32_t n, cudaStream_t stream);
+cudaError_t launch_fp64_peak(double* sink, int grid, int block, int iters, cudaStream_t stream);
+
+}  // namespace stemk

@@ -1,0 +1,504 @@
+// stem_kernel_b200/csrc/stemk_api.cu -- implementation of the C ABI in include/stemk.h.
+//
+// A context owns one CUDA device, one stream, the kernel constants and growable device scratch;
+// a set owns the device copy of a compiled record set.  The Gram / cross / diagonal entry points
+// (KernelMatrix::calculate / diagonal, common/kernel_matrix.cpp:485-754) are thin drivers over one
+// pair-list evaluator.  There is deliberately no CPU path: without a device every entry point
+// returns STEMK_ERR_CUDA.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace stemk;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= bytes) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; bytes = 0;
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e == cudaSuccess) bytes = n;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+};
+
+}  // namespace
+
+struct stemk_set {
+  CompiledSet host;   // kept for the work model and the scheduler
+  DevBuf blob;        // every array of the view in one allocation
+  SetView view;       // device pointers
+  int device = 0;
+};
+
+struct stemk_ctx {
+  int device = 0;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+  stemk_params params;
+  KernelTables tables;
+  cudaStream_t stream = nullptr;
+  double* d_pair_tab = nullptr;
+  double* d_subst = nullptr;
+  unsigned long long* d_counter = nullptr;
+  DevBuf scratch, carry, tmp_stem, tmp_str, idx_x, idx_y, vals, matrix;
+  std::string err;
+  // stats
+  uint64_t launches = 0;
+  double stem_ms = 0, string_ms = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace {
+
+int fail(stemk_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg; else g_create_error = msg;
+  return code;
+}
+int cuda_fail(stemk_ctx* c, cudaError_t e, const char* where) {
+  return fail(c, STEMK_ERR_CUDA, std::string(where) + ": " + cudaGetErrorString(e));
+}
+#define CU(call)                                                     \
+  do {                                                               \
+    cudaError_t e_ = (call);                                         \
+    if (e_ != cudaSuccess) return cuda_fail(ctx, e_, #call);         \
+  } while (0)
+
+template <class T>
+size_t place(size_t& off, const std::vector<T>& v) {
+  off = (off + 255) & ~size_t(255);
+  size_t at = off;
+  off += v.size() * sizeof(T);
+  return at;
+}
+
+// rows per block and shared memory for a launch whose widest y has ny_cap non-leaf nodes
+void stem_config(const stemk_ctx* ctx, uint32_t ny_cap, uint32_t* rb, size_t* smem) {
+  const size_t budget2 = (size_t)100 * 1024;  // two CTAs per SM
+  const size_t budget1 = std::min<size_t>(ctx->smem_optin, (size_t)220 * 1024);
+  uint32_t best = 0;
+  for (uint32_t r : {32u, 24u, 16u}) if (stem_smem_bytes(r, ny_cap) <= budget2) { best = r; break; }
+  if (!best) for (uint32_t r : {32u, 24u, 16u, 12u, 8u, 4u, 2u, 1u}) if (stem_smem_bytes(r, ny_cap) <= budget1) { best = r; break; }
+  *rb = best;
+  *smem = best ? stem_smem_bytes(best, ny_cap) : 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* stemk_version(void) { return "stemk-b200 0.1 (sm_100a)"; }
+
+int stemk_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+const char* stemk_last_error(const stemk_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int stemk_create(stemk_ctx** out, const stemk_params* params, int device) {
+  stemk_ctx* ctx = nullptr;
+  if (!out || !params) return fail(nullptr, STEMK_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (params->kind < STEMK_SI_STEM || params->kind > STEMK_STR_NAIVE) return fail(nullptr, STEMK_ERR_ARG, "unknown kernel kind");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(nullptr, STEMK_ERR_CUDA, "no CUDA device: this library has no CPU path");
+  }
+  if (device < 0 || device >= n) return fail(nullptr, STEMK_ERR_ARG, "device index out of range");
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaSetDevice");
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaGetDeviceProperties");
+  stemk_ctx* c = new stemk_ctx;
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  c->smem_optin = prop.sharedMemPerBlockOptin;
+  c->params = *params;
+  make_tables(*params, &c->tables);
+  bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaMalloc((void**)&c->d_pair_tab, sizeof(double) * 256) == cudaSuccess &&
+            cudaMalloc((void**)&c->d_subst, sizeof(double) * 16) == cudaSuccess &&
+            cudaMalloc((void**)&c->d_counter, sizeof(unsigned long long)) == cudaSuccess &&
+            cudaMemcpy(c->d_pair_tab, c->tables.pair_tab, sizeof(double) * 256, cudaMemcpyHostToDevice) == cudaSuccess &&
+            cudaMemcpy(c->d_subst, c->tables.subst, sizeof(double) * 16, cudaMemcpyHostToDevice) == cudaSuccess &&
+            cudaEventCreate(&c->ev0) == cudaSuccess && cudaEventCreate(&c->ev1) == cudaSuccess;
+  if (!ok) {
+    e = cudaGetLastError();
+    stemk_destroy(c);
+    return cuda_fail(nullptr, e, "context allocation");
+  }
+  *out = c;
+  return STEMK_OK;
+}
+
+void stemk_destroy(stemk_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  for (DevBuf* b : {&c->scratch, &c->carry, &c->tmp_stem, &c->tmp_str, &c->idx_x, &c->idx_y, &c->vals, &c->matrix}) b->release();
+  if (c->d_pair_tab) cudaFree(c->d_pair_tab);
+  if (c->d_subst) cudaFree(c->d_subst);
+  if (c->d_counter) cudaFree(c->d_counter);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int stemk_upload(stemk_ctx* ctx, const stemk_seqset_desc* desc, stemk_set** out) {
+  if (!ctx || !desc || !out) return fail(ctx, STEMK_ERR_ARG, "null argument");
+  *out = nullptr;
+  CU(cudaSetDevice(ctx->device));
+  stemk_set* s = new stemk_set;
+  s->device = ctx->device;
+  const int n_threads = (int)std::min<unsigned>(16, std::max(1u, std::thread::hardware_concurrency()));
+  std::string err = compile_set(*desc, ctx->params.loop_gap, n_threads, &s->host);
+  if (!err.empty()) { delete s; return fail(ctx, STEMK_ERR_ARG, err); }
+  const CompiledSet& h = s->host;
+  size_t off = 0;
+  const size_t o_rec = place(off, h.rec), o_a = place(off, h.a), o_el = place(off, h.el), o_ql = place(off, h.ql),
+               o_paths = place(off, h.paths), o_gapt = place(off, h.gapt), o_bfreq = place(off, h.bfreq),
+               o_len = place(off, h.len), o_bcode = place(off, h.bcode), o_coff = place(off, h.coff),
+               o_cidx = place(off, h.cidx), o_ce = place(off, h.ce), o_lev = place(off, h.lev_off),
+               o_boff = place(off, h.boff), o_bab = place(off, h.bab), o_bfq = place(off, h.bfq),
+               o_ccode = place(off, h.ccode), o_cw = place(off, h.cw), o_prof = place(off, h.prof),
+               o_text = place(off, h.text);
+  off = (off + 255) & ~size_t(255);
+  std::vector<char> stage(off, 0);
+  auto put = [&](size_t at, const auto& v) { if (!v.empty()) std::memcpy(stage.data() + at, v.data(), v.size() * sizeof(v[0])); };
+  put(o_rec, h.rec); put(o_a, h.a); put(o_el, h.el); put(o_ql, h.ql); put(o_paths, h.paths); put(o_gapt, h.gapt);
+  put(o_bfreq, h.bfreq); put(o_len, h.len); put(o_bcode, h.bcode); put(o_coff, h.coff); put(o_cidx, h.cidx);
+  put(o_ce, h.ce); put(o_lev, h.lev_off); put(o_boff, h.boff); put(o_bab, h.bab); put(o_bfq, h.bfq);
+  put(o_ccode, h.ccode); put(o_cw, h.cw); put(o_prof, h.prof); put(o_text, h.text);
+  cudaError_t e = s->blob.reserve(std::max<size_t>(off, 256));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(s->blob.p, stage.data(), off, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) { s->blob.release(); delete s; return cuda_fail(ctx, e, "set upload"); }
+  char* b = static_cast<char*>(s->blob.p);
+  SetView& v = s->view;
+  v.n_recs = (uint32_t)h.rec.size();
+  v.rec = (const RecDev*)(b + o_rec); v.a = (const double*)(b + o_a); v.el = (const double*)(b + o_el);
+  v.ql = (const double*)(b + o_ql); v.paths = (const double*)(b + o_paths); v.gapt = (const double*)(b + o_gapt);
+  v.bfreq = (const double*)(b + o_bfreq); v.len = (const uint32_t*)(b + o_len); v.bcode = (const uint8_t*)(b + o_bcode);
+  v.coff = (const uint32_t*)(b + o_coff); v.cidx = (const uint32_t*)(b + o_cidx); v.ce = (const double*)(b + o_ce);
+  v.lev_off = (const uint32_t*)(b + o_lev); v.boff = (const uint32_t*)(b + o_boff); v.bab = (const uint8_t*)(b + o_bab);
+  v.bfq = (const double*)(b + o_bfq); v.ccode = (const uint8_t*)(b + o_ccode); v.cw = (const double*)(b + o_cw);
+  v.prof = (const float*)(b + o_prof); v.text = (const uint8_t*)(b + o_text);
+  *out = s;
+  return STEMK_OK;
+}
+
+void stemk_set_free(stemk_ctx* ctx, stemk_set* s) {
+  if (!s) return;
+  if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+  s->blob.release();
+  delete s;
+}
+
+uint32_t stemk_set_size(const stemk_set* s) { return s ? (uint32_t)s->host.rec.size() : 0; }
+
+// -------------------------------------------------------------------------- pair evaluator
+int stemk_pairs_device(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, size_t n_pairs, const uint32_t* d_xi,
+                       const uint32_t* d_yi, double* d_out, void* stream_) {
+  if (!ctx || !x || !y) return fail(ctx, STEMK_ERR_ARG, "null argument");
+  if (n_pairs == 0) return STEMK_OK;
+  if (!d_xi || !d_yi || !d_out) return fail(ctx, STEMK_ERR_ARG, "null buffer");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = stream_ ? (cudaStream_t)stream_ : ctx->stream;
+  const int kind = ctx->params.kind;
+  const bool has_stem = kind_has_stem(kind), has_str = kind_has_string(kind);
+  const bool combine = (has_stem && has_str) || kind == STEMK_LSU_STEM || kind == STEMK_LSU_STR;
+  double* stem_out = d_out;
+  double* str_out = d_out;
+  if (combine) {
+    if (has_stem) { CU(ctx->tmp_stem.reserve(n_pairs * sizeof(double))); stem_out = (double*)ctx->tmp_stem.p; }
+    if (has_str) { CU(ctx->tmp_str.reserve(n_pairs * sizeof(double))); str_out = (double*)ctx->tmp_str.p; }
+  }
+
+  if (has_stem) {
+    const uint32_t ny_cap = std::max(1u, y->host.max_N), nx_cap = std::max(1u, x->host.max_N);
+    uint32_t rb; size_t smem;
+    stem_config(ctx, ny_cap, &rb, &smem);
+    if (!rb) return fail(ctx, STEMK_ERR_NOMEM, "a record has too many DAG nodes for the shared-memory row block");
+    int per_sm = stem_max_ctas_per_sm(smem);
+    if (per_sm < 1) return fail(ctx, STEMK_ERR_CUDA, "stem kernel does not fit on an SM");
+    per_sm = std::min(per_sm, 4);
+    const int grid = (int)std::min<size_t>(n_pairs, (size_t)ctx->sm_count * per_sm);
+    const unsigned long long stride = (unsigned long long)nx_cap * ((ny_cap + 1u) & ~1u);
+    CU(ctx->scratch.reserve(sizeof(double) * stride * grid));
+    CU(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), st));
+    StemLaunch L;
+    L.X = x->view; L.Y = y->view; L.xi = d_xi; L.yi = d_yi; L.n_pairs = n_pairs; L.out = stem_out;
+    L.counter = ctx->d_counter; L.scratch = (double*)ctx->scratch.p; L.scratch_stride = stride;
+    L.pair_tab = ctx->d_pair_tab; L.len_band = ctx->params.len_band; L.rb = rb; L.ny_cap = ny_cap;
+    CU(cudaEventRecord(ctx->ev0, st));
+    CU(launch_stem(L, grid, smem, st));
+    CU(cudaEventRecord(ctx->ev1, st));
+    ctx->launches += 1;
+    // stats need the elapsed time; callers that want overlap use the *_device entry once per batch
+    CU(cudaEventSynchronize(ctx->ev1));
+    float ms = 0; CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1)); ctx->stem_ms += ms;
+  }
+  if (has_str) {
+    const uint32_t ly_cap = std::max(1u, y->host.max_L), lx_cap = std::max(1u, x->host.max_L);
+    const int cw = ly_cap <= 128 ? 4 : (ly_cap <= 256 ? 8 : 12);
+    const int wpc = string_warps_per_cta();
+    const size_t want = (n_pairs + wpc - 1) / wpc;
+    const int grid = (int)std::min<size_t>(want, (size_t)ctx->sm_count * 12);
+    const unsigned long long cstride = 2ull * (lx_cap + 2);
+    CU(ctx->carry.reserve(sizeof(double) * cstride * grid * wpc));
+    CU(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), st));
+    StringLaunch L;
+    L.X = x->view; L.Y = y->view; L.xi = d_xi; L.yi = d_yi; L.n_pairs = n_pairs; L.out = str_out;
+    L.counter = ctx->d_counter; L.carry = (double*)ctx->carry.p; L.carry_stride = cstride; L.subst = ctx->d_subst;
+    L.gap = ctx->params.gap; L.naive = kind == STEMK_STR_NAIVE;
+    CU(cudaEventRecord(ctx->ev0, st));
+    CU(launch_string(L, cw, grid, st));
+    CU(cudaEventRecord(ctx->ev1, st));
+    ctx->launches += 1;
+    CU(cudaEventSynchronize(ctx->ev1));
+    float ms = 0; CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1)); ctx->string_ms += ms;
+  }
+  if (combine) {
+    CU(launch_combine(kind, ctx->params.alpha, ctx->params.beta, has_stem ? stem_out : nullptr,
+                      has_str ? str_out : nullptr, d_out, n_pairs, st));
+    ctx->launches += 1;
+  }
+  return STEMK_OK;
+}
+
+int stemk_pairs(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, size_t n_pairs, const uint32_t* xi,
+                const uint32_t* yi, double* out) {
+  if (!ctx || !x || !y) return fail(ctx, STEMK_ERR_ARG, "null argument");
+  if (n_pairs == 0) return STEMK_OK;
+  if (!xi || !yi || !out) return fail(ctx, STEMK_ERR_ARG, "null buffer");
+  for (size_t k = 0; k < n_pairs; ++k)
+    if (xi[k] >= x->host.rec.size() || yi[k] >= y->host.rec.size()) return fail(ctx, STEMK_ERR_ARG, "pair index out of range");
+  CU(cudaSetDevice(ctx->device));
+  CU(ctx->idx_x.reserve(n_pairs * sizeof(uint32_t)));
+  CU(ctx->idx_y.reserve(n_pairs * sizeof(uint32_t)));
+  CU(ctx->vals.reserve(n_pairs * sizeof(double)));
+  CU(cudaMemcpyAsync(ctx->idx_x.p, xi, n_pairs * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->idx_y.p, yi, n_pairs * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  int rc = stemk_pairs_device(ctx, x, y, n_pairs, (const uint32_t*)ctx->idx_x.p, (const uint32_t*)ctx->idx_y.p,
+                              (double*)ctx->vals.p, ctx->stream);
+  if (rc != STEMK_OK) return rc;
+  CU(cudaMemcpyAsync(out, ctx->vals.p, n_pairs * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return STEMK_OK;
+}
+
+// -------------------------------------------------------------------------- Gram drivers
+// Rough per-pair cost used only to order the work queue (largest first).
+static inline double sched_cost(const stemk_ctx* ctx, const CompiledSet& a, uint32_t i, const CompiledSet& b, uint32_t j) {
+  double c = 0;
+  if (kind_has_stem(ctx->params.kind)) c += (double)a.n_nodes_all[i] * b.n_edges_all[j] + (double)a.n_edges_all[i] * b.n_nodes_all[j];
+  if (kind_has_string(ctx->params.kind)) c += (double)a.rec[i].L * b.rec[j].L;
+  return c;
+}
+
+int stemk_gram(stemk_ctx* ctx, const stemk_set* train, int normalize, double* out) {
+  if (!ctx || !train || !out) return fail(ctx, STEMK_ERR_ARG, "null argument");
+  const uint32_t n = (uint32_t)train->host.rec.size();
+  if (n == 0) return STEMK_OK;
+  CU(cudaSetDevice(ctx->device));
+  // records sorted by size, big first: the queue then hands out the expensive pairs first
+  std::vector<uint32_t> perm(n);
+  std::iota(perm.begin(), perm.end(), 0u);
+  std::vector<double> size_key(n);
+  for (uint32_t i = 0; i < n; ++i) size_key[i] = sched_cost(ctx, train->host, i, train->host, i);
+  std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) { return size_key[a] > size_key[b]; });
+  const size_t n_pairs = (size_t)n * (n + 1) / 2;
+  std::vector<uint32_t> xi(n_pairs), yi(n_pairs);
+  size_t k = 0;
+  for (uint32_t p = 0; p < n; ++p)
+    for (uint32_t q = p; q < n; ++q, ++k) {
+      // the reference evaluates kernel_(train[i], train[j]) with i <= j (kernel_matrix.cpp:47-50);
+      // the stem kernel is not symmetric in its arguments, so the roles must be kept
+      const uint32_t a = perm[p], b = perm[q];
+      xi[k] = std::min(a, b); yi[k] = std::max(a, b);
+    }
+  CU(ctx->idx_x.reserve(n_pairs * sizeof(uint32_t)));
+  CU(ctx->idx_y.reserve(n_pairs * sizeof(uint32_t)));
+  CU(ctx->vals.reserve(n_pairs * sizeof(double)));
+  CU(ctx->matrix.reserve((size_t)n * n * sizeof(double)));
+  CU(cudaMemcpyAsync(ctx->idx_x.p, xi.data(), n_pairs * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->idx_y.p, yi.data(), n_pairs * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  int rc = stemk_pairs_device(ctx, train, train, n_pairs, (const uint32_t*)ctx->idx_x.p, (const uint32_t*)ctx->idx_y.p,
+                              (double*)ctx->vals.p, ctx->stream);
+  if (rc != STEMK_OK) return rc;
+  CU(launch_scatter_square((const double*)ctx->vals.p, (const uint32_t*)ctx->idx_x.p, (const uint32_t*)ctx->idx_y.p,
+                           n_pairs, (double*)ctx->matrix.p, n, ctx->stream));
+  ctx->launches += 1;
+  if (normalize) { CU(launch_normalize_square((double*)ctx->matrix.p, n, ctx->stream)); ctx->launches += 2; }
+  CU(cudaMemcpyAsync(out, ctx->matrix.p, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return STEMK_OK;
+}
+
+int stemk_diag(stemk_ctx* ctx, const stemk_set* train, const uint32_t* sv_index, uint32_t n_sv, double* out) {
+  if (!ctx || !train || !out) return fail(ctx, STEMK_ERR_ARG, "null argument");
+  const uint32_t n = (uint32_t)train->host.rec.size();
+  std::vector<uint32_t> idx;
+  if (n_sv == 0) { idx.resize(n); std::iota(idx.begin(), idx.end(), 0u); }
+  else {
+    if (!sv_index) return fail(ctx, STEMK_ERR_ARG, "null sv_index");
+    idx.assign(sv_index, sv_index + n_sv);
+  }
+  std::vector<double> v(idx.size());
+  int rc = stemk_pairs(ctx, train, train, idx.size(), idx.data(), idx.data(), v.data());
+  if (rc != STEMK_OK) return rc;
+  for (size_t k = 0; k < idx.size(); ++k) out[idx[k]] = v[k];
+  return STEMK_OK;
+}
+
+int stemk_cross(stemk_ctx* ctx, const stemk_set* test, const stemk_set* train, const uint32_t* sv_index, uint32_t n_sv,
+                int normalize, double* out, double* self_out) {
+  if (!ctx || !test || !train || !out) return fail(ctx, STEMK_ERR_ARG, "null argument");
+  const uint32_t nt = (uint32_t)test->host.rec.size(), ns = (uint32_t)train->host.rec.size();
+  std::vector<uint32_t> cols;
+  if (n_sv == 0) { cols.resize(ns); std::iota(cols.begin(), cols.end(), 0u); }
+  else {
+    if (!sv_index) return fail(ctx, STEMK_ERR_ARG, "null sv_index");
+    cols.assign(sv_index, sv_index + n_sv);
+    for (uint32_t c : cols) if (c >= ns) return fail(ctx, STEMK_ERR_ARG, "sv_index out of range");
+  }
+  // rows k(train_x, test_i): the train record is the FIRST argument (kernel_matrix.cpp:159,168)
+  const size_t n_pairs = (size_t)nt * cols.size();
+  std::vector<uint32_t> xi(n_pairs), yi(n_pairs);
+  // order: big test records first, big train records first inside each
+  std::vector<uint32_t> tperm(nt), cperm(cols.size());
+  std::iota(tperm.begin(), tperm.end(), 0u);
+  std::iota(cperm.begin(), cperm.end(), 0u);
+  std::stable_sort(tperm.begin(), tperm.end(), [&](uint32_t a, uint32_t b) {
+    return sched_cost(ctx, test->host, a, test->host, a) > sched_cost(ctx, test->host, b, test->host, b); });
+  std::stable_sort(cperm.begin(), cperm.end(), [&](uint32_t a, uint32_t b) {
+    return sched_cost(ctx, train->host, cols[a], train->host, cols[a]) > sched_cost(ctx, train->host, cols[b], train->host, cols[b]); });
+  size_t k = 0;
+  for (uint32_t t : tperm) for (uint32_t c : cperm) { xi[k] = cols[c]; yi[k] = t; ++k; }
+  std::vector<double> v(n_pairs);
+  int rc = stemk_pairs(ctx, train, test, n_pairs, xi.data(), yi.data(), v.data());
+  if (rc != STEMK_OK) return rc;
+  for (k = 0; k < n_pairs; ++k) out[(size_t)yi[k] * ns + xi[k]] = v[k];
+  std::vector<double> selfv;
+  if (self_out || normalize) {
+    std::vector<uint32_t> id(nt);
+    std::iota(id.begin(), id.end(), 0u);
+    selfv.resize(nt);
+    rc = stemk_pairs(ctx, test, test, nt, id.data(), id.data(), selfv.data());
+    if (rc != STEMK_OK) return rc;
+    if (self_out) std::memcpy(self_out, selfv.data(), nt * sizeof(double));
+  }
+  if (normalize) {
+    // kernel_matrix.cpp:735-748 over every column; columns outside sv_index keep a zero diagonal
+    // exactly like App::predict's diag vector (framework.h:188-189,282-286), i.e. they turn into NaN/inf
+    std::vector<double> diag(ns, 0.0);
+    rc = stemk_diag(ctx, train, n_sv ? cols.data() : nullptr, n_sv ? (uint32_t)cols.size() : 0, diag.data());
+    if (rc != STEMK_OK) return rc;
+    for (uint32_t i = 0; i < nt; ++i)
+      for (uint32_t j = 0; j < ns; ++j) out[(size_t)i * ns + j] /= std::sqrt(selfv[i] * diag[j]);
+  }
+  return STEMK_OK;
+}
+
+// -------------------------------------------------------------------------- work model
+int stemk_pair_cost(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, size_t n_pairs, const uint32_t* xi,
+                    const uint32_t* yi, double* cells, double* flops) {
+  if (!ctx || !x || !y || !xi || !yi) return fail(ctx, STEMK_ERR_ARG, "null argument");
+  const int kind = ctx->params.kind;
+  const bool has_stem = kind_has_stem(kind), has_str = kind_has_string(kind) && kind != STEMK_STR_NAIVE;
+  const CompiledSet& A = x->host;
+  const CompiledSet& B = y->host;
+  for (size_t k = 0; k < n_pairs; ++k) {
+    const uint32_t i = xi[k], j = yi[k];
+    if (i >= A.rec.size() || j >= B.rec.size()) return fail(ctx, STEMK_ERR_ARG, "pair index out of range");
+    const RecDev& rx = A.rec[i];
+    const RecDev& ry = B.rec[j];
+    double c = 0, f = 0;
+    if (has_stem) {
+      // U_match / U_bf over in-band non-leaf node pairs, with the reference's full degrees (leaf edges included)
+      double um = 0, ub = 0;
+      for (uint32_t a = 0; a < rx.N; ++a) {
+        const double dx = A.deg_all[rx.node0 + a];
+        const double bx = A.boff[rx.boff0 + a + 1] - A.boff[rx.boff0 + a];
+        const uint32_t la = A.len[rx.node0 + a];
+        for (uint32_t b = 0; b < ry.N; ++b) {
+          const uint32_t lb = B.len[ry.node0 + b];
+          const uint32_t dl = la > lb ? la - lb : lb - la;
+          if (ctx->params.len_band != 0 && dl > ctx->params.len_band) continue;
+          const double dy = B.deg_all[ry.node0 + b];
+          um += dx * dy;
+          ub += bx * (double)(B.boff[ry.boff0 + b + 1] - B.boff[ry.boff0 + b]);
+        }
+      }
+      c += (double)A.n_nodes_all[i] * B.n_nodes_all[j];
+      f += 2 * um + 3 * ub + 3 * ((double)A.n_nodes_all[i] * B.n_edges_all[j] + (double)A.n_edges_all[i] * B.n_nodes_all[j]);
+    }
+    if (has_str) {
+      const bool w = (rx.flags & REC_HAS_WEIGHT) && (ry.flags & REC_HAS_WEIGHT);
+      if (!has_stem) c += (double)rx.L * ry.L;
+      f += (w ? 9.0 : 7.0) * rx.L * ry.L;
+    }
+    if (kind == STEMK_STR_NAIVE) {
+      double m = 0;
+      const uint8_t* tx = A.text.data() + rx.col0;
+      const uint8_t* ty = B.text.data() + ry.col0;
+      uint32_t cnt_x[256] = {0};
+      for (uint32_t a = 0; a < rx.L; ++a) ++cnt_x[tx[a]];
+      for (uint32_t b = 0; b < ry.L; ++b) m += cnt_x[ty[b]];
+      c += (double)rx.L * ry.L;
+      f += 4.0 * rx.L * ry.L + 3.0 * m;
+    }
+    if (cells) cells[k] = c;
+    if (flops) flops[k] = f;
+  }
+  return STEMK_OK;
+}
+
+void stemk_stats_reset(stemk_ctx* ctx) { if (ctx) { ctx->launches = 0; ctx->stem_ms = ctx->string_ms = 0; } }
+void stemk_stats_get(const stemk_ctx* ctx, uint64_t* launches, double* stem_ms, double* string_ms) {
+  if (!ctx) return;
+  if (launches) *launches = ctx->launches;
+  if (stem_ms) *stem_ms = ctx->stem_ms;
+  if (string_ms) *string_ms = ctx->string_ms;
+}
+
+int stemk_fp64_peak(stemk_ctx* ctx, double seconds, double* tflops) {
+  if (!ctx || !tflops) return fail(ctx, STEMK_ERR_ARG, "null argument");
+  CU(cudaSetDevice(ctx->device));
+  double* sink = nullptr;
+  CU(cudaMalloc((void**)&sink, sizeof(double)));
+  const int block = 256, grid = ctx->sm_count * 8, iters = 1 << 16;
+  const double flop_per_launch = 2.0 * 8.0 * iters * (double)block * grid;
+  double best = 0, spent = 0;
+  for (int rep = 0; rep < 1000 && (rep < 3 || spent < seconds); ++rep) {
+    cudaEventRecord(ctx->ev0, ctx->stream);
+    cudaError_t e = launch_fp64_peak(sink, grid, block, iters, ctx->stream);
+    cudaEventRecord(ctx->ev1, ctx->stream);
+    if (e != cudaSuccess || cudaEventSynchronize(ctx->ev1) != cudaSuccess) { cudaFree(sink); return cuda_fail(ctx, cudaGetLastError(), "fp64 probe"); }
+    float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    spent += ms * 1e-3;
+    if (rep > 0) best = std::max(best, flop_per_launch / (ms * 1e-3) / 1e12);
+  }
+  cudaFree(sink);
+  *tflops = best;
+  return STEMK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,99 @@
+// stem_kernel_b200/csrc/stemk_internal.h -- internal structures shared by the host-side set
+// compiler (compile_set.cpp), the CUDA kernels and the C ABI (stemk_api.cu).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/stemk.h"
+
+namespace stemk {
+
+// ------------------------------------------------------------------------------------------
+// Compiled record.  The stem DP only ever needs values on (non-leaf x non-leaf) node pairs: a
+// leaf row/column of the reference's tables is a constant (DESIGN.md "restated
+// recurrence").  So each record is compiled, once per upload, into its non-leaf nodes renumbered
+// level by level (level = longest path to a hairpin-closing pair), with per-node constants that
+// fold the leaf rows/columns in.  All of it depends only on the record and the loop gap g.
+// ------------------------------------------------------------------------------------------
+struct RecDev {
+  uint32_t N;       // non-leaf nodes
+  uint32_t nlev;    // levels
+  uint32_t node0;   // offset of this record in the per-node arrays
+  uint32_t coff0;   // offset of its N+1 child offsets in `coff`
+  uint32_t lev0;    // offset of its nlev+1 level offsets in `lev_off`
+  uint32_t boff0;   // offset of its N+1 base-pair-profile offsets in `boff`
+  uint32_t L;       // columns
+  uint32_t col0;    // offset in the per-column arrays
+  uint32_t lr;      // roots that are leaves (0 for DAGs made by the front end)
+  uint32_t flags;   // REC_*
+  double plr;       // sum over roots of #paths root -> any leaf
+  double n_rows;    // ProfileSequence::n_seqs()
+};
+enum { REC_HAS_WEIGHT = 1u, REC_SIMPLE_COLS = 2u, REC_SIMPLE_BPF = 4u };
+
+// Pointers into one device (or host) allocation holding a compiled set.
+struct SetView {
+  uint32_t n_recs;
+  const RecDev* rec;
+  // per non-leaf node (index node0 + k, k in level order)
+  const double* a;       // g*g*weight                       score_table.h:26-29
+  const double* el;      // sum over leaf children of g^gaps*w
+  const double* ql;      // value of sum_children e * G0(child, leaf column); constant per node
+  const double* paths;   // number of root->node paths (replaces the K tables)
+  const double* gapt;    // gap count at the node's first column / n_rows   score_table.cpp:189-197
+  const double* bfreq;   // base-pair frequency when the node has a single (a,b) entry
+  const uint32_t* len;   // last - first
+  const uint8_t* bcode;  // a*4+b for a single-entry profile, 0xFF otherwise
+  // children (non-leaf only), CSR local to the record
+  const uint32_t* coff;  // [sum(N+1)]
+  const uint32_t* cidx;  // child, in the record's level numbering
+  const double* ce;      // g^gaps * edge weight
+  const uint32_t* lev_off;
+  // general base-pair profiles (alignments / IUPAC)
+  const uint32_t* boff;  // [sum(N+1)]
+  const uint8_t* bab;    // a*4+b
+  const double* bfq;
+  // per column
+  const uint8_t* ccode;  // 0..3 one-hot base, 4 all-zero column (gap/unknown), 5 general profile
+  const double* cw;      // column weight (1 when the record has none)
+  const float* prof;     // 4 floats per column (A,C,G,U)
+  const uint8_t* text;   // raw characters
+};
+
+// Host-side result of compiling a descriptor: one byte blob + the view's offsets.
+struct CompiledSet {
+  std::vector<RecDev> rec;
+  std::vector<double> a, el, ql, paths, gapt, bfreq, ce, bfq, cw;
+  std::vector<uint32_t> len, coff, cidx, lev_off, boff;
+  std::vector<uint8_t> bcode, bab, ccode, text;
+  std::vector<float> prof;
+  // host-only statistics for the work model and the scheduler
+  std::vector<uint32_t> n_nodes_all;  // nodes incl. leaves (reference's #V)
+  std::vector<uint32_t> n_edges_all;  // edges incl. leaf edges (reference's #E)
+  std::vector<uint32_t> max_level_rows;
+  std::vector<uint32_t> deg_all;      // per non-leaf node (level order): out-degree incl. leaf edges
+  bool has_dag = false;
+  uint32_t max_N = 0, max_L = 0;
+};
+
+// Builds the compiled form of every record of `desc` under loop gap `g`.  Returns "" or an error.
+std::string compile_set(const stemk_seqset_desc& desc, double g, int n_threads, CompiledSet* out);
+
+// Kernel constants derived from stemk_params on the host with libm (same exp() the reference calls).
+struct KernelTables {
+  double pair_tab[256];  // exp(beta*ribosum_p) or stack/covar   score_table.cpp:118-134 / :14-41
+  double subst[16];      // exp(alpha*ribosum_s) or match/mismatch   string_kernel.cpp:11-34
+};
+void make_tables(const stemk_params& p, KernelTables* t);
+
+inline bool kind_has_stem(int k) {
+  return k == STEMK_SI_STEM || k == STEMK_SU_STEM || k == STEMK_SI_STEM_STR || k == STEMK_SU_STEM_STR ||
+         k == STEMK_LSU_STEM || k == STEMK_LSU_STEM_STR;
+}
+inline bool kind_has_string(int k) {
+  return k == STEMK_SI_STEM_STR || k == STEMK_SU_STEM_STR || k == STEMK_LSU_STR || k == STEMK_LSU_STEM_STR ||
+         k == STEMK_STR_SUBST || k == STEMK_STR_SIMPLE || k == STEMK_STR_NAIVE;
+}
+
+}  // namespace stemk
