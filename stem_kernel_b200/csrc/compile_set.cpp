@@ -87,7 +87,7 @@ void compile_record(const stemk_seqset_desc& s, uint32_t r, double g, RecOut* o)
 
   // ---- DAG
   if (n == 0) {
-    h.N = 0; h.nlev = 0; h.flags |= REC_SIMPLE_BPF;
+    h.N = 0; h.nlev = 0; h.flags |= REC_SIMPLE_BPF | REC_LEN_MONOTONE;
     o->coff.assign(1, 0); o->lev_off.assign(1, 0); o->boff.assign(1, 0);
     return;
   }
@@ -155,7 +155,7 @@ void compile_record(const stemk_seqset_desc& s, uint32_t r, double g, RecOut* o)
   h.N = N; h.nlev = nlev;
   o->a.resize(N); o->el.resize(N); o->ql.resize(N); o->paths.resize(N); o->gapt.resize(N); o->bfreq.resize(N);
   o->len.resize(N); o->bcode.resize(N); o->coff.assign(N + 1, 0); o->boff.assign(N + 1, 0);
-  bool simple_bpf = true;
+  bool simple_bpf = true, len_mono = true;
   for (uint32_t k = 0; k < N; ++k) {
     const uint32_t u = order[k];
     o->a[k] = av[u]; o->el[k] = el[u]; o->ql[k] = ql[u]; o->paths[k] = paths[u];
@@ -166,6 +166,7 @@ void compile_record(const stemk_seqset_desc& s, uint32_t r, double g, RecOut* o)
     for (uint32_t e = eoff[u]; e < eoff[u + 1]; ++e) {
       const uint32_t c = s.edge_to[e];
       if (leaf[c]) continue;
+      if (last[c] - first[c] >= last[u] - first[u]) len_mono = false;
       o->cidx.push_back(newidx[c]);
       o->ce.push_back(gpow[s.edge_gaps[e]] * (double)s.edge_weight[e]);
     }
@@ -181,6 +182,7 @@ void compile_record(const stemk_seqset_desc& s, uint32_t r, double g, RecOut* o)
     else { o->bcode[k] = 0xFF; o->bfreq[k] = 0.0; simple_bpf = false; }
   }
   if (simple_bpf) h.flags |= REC_SIMPLE_BPF;
+  if (len_mono) h.flags |= REC_LEN_MONOTONE;
 }
 
 template <class T>
@@ -229,6 +231,8 @@ std::string compile_set(const stemk_seqset_desc& s, double g, int n_threads, Com
     if (o.n_all) c.has_dag = true;
     c.max_N = std::max(c.max_N, h.N);
     c.max_L = std::max(c.max_L, h.L);
+    c.max_E = std::max(c.max_E, (uint32_t)o.cidx.size());
+    c.max_nlev = std::max(c.max_nlev, h.nlev);
   }
   return "";
 }

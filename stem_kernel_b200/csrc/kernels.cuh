@@ -18,7 +18,9 @@ struct StemLaunch {
   const double* pair_tab;       // 256 doubles
   uint32_t len_band;
   uint32_t rb;                  // rows per row block
-  uint32_t ny_cap;              // largest Ny of this launch (shared-memory carve-up)
+  uint32_t ny_cap;              // largest Ny / Ey / level count over the y set (shared-memory carve-up)
+  uint32_t ey_cap;
+  uint32_t lev_cap;
 };
 
 struct StringLaunch {
@@ -36,7 +38,7 @@ struct StringLaunch {
 };
 
 // host-callable launchers (defined in the .cu files); all asynchronous on `stream`
-size_t stem_smem_bytes(uint32_t rb, uint32_t ny_cap);
+size_t stem_smem_bytes(uint32_t rb, uint32_t ny_cap, uint32_t ey_cap, uint32_t lev_cap);
 cudaError_t launch_stem(const StemLaunch& p, int grid, size_t smem, cudaStream_t stream);
 int stem_max_ctas_per_sm(size_t smem);
 cudaError_t launch_string(const StringLaunch& p, int cw, int grid, cudaStream_t stream);

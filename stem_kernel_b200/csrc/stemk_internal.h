@@ -30,7 +30,8 @@ struct RecDev {
   double plr;       // sum over roots of #paths root -> any leaf
   double n_rows;    // ProfileSequence::n_seqs()
 };
-enum { REC_HAS_WEIGHT = 1u, REC_SIMPLE_COLS = 2u, REC_SIMPLE_BPF = 4u };
+enum { REC_HAS_WEIGHT = 1u, REC_SIMPLE_COLS = 2u, REC_SIMPLE_BPF = 4u,
+       REC_LEN_MONOTONE = 8u };  // every non-leaf child is strictly shorter than its parent (true for front-end DAGs)
 
 // Pointers into one device (or host) allocation holding a compiled set.
 struct SetView {
@@ -74,7 +75,7 @@ struct CompiledSet {
   std::vector<uint32_t> max_level_rows;
   std::vector<uint32_t> deg_all;      // per non-leaf node (level order): out-degree incl. leaf edges
   bool has_dag = false;
-  uint32_t max_N = 0, max_L = 0;
+  uint32_t max_N = 0, max_L = 0, max_E = 0, max_nlev = 0;  // non-leaf nodes / columns / non-leaf edges / levels
 };
 
 // Builds the compiled form of every record of `desc` under loop gap `g`.  Returns "" or an error.
