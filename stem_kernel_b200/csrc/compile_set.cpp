@@ -147,9 +147,17 @@ void compile_record(const stemk_seqset_desc& s, uint32_t r, double g, RecOut* o)
     o->lev_off[l + 1] += o->lev_off[l];
   }
   {
-    std::vector<uint32_t> fill(o->lev_off.begin(), o->lev_off.end() - 1);
-    order.assign(o->lev_off[nlev], 0);
-    for (uint32_t u = 0; u < n; ++u) if (!leaf[u]) { newidx[u] = fill[level[u]]; order[fill[level[u]]++] = u; }
+    // inside a level, nodes with many inner pairs first: lanes of a warp then see similar trip counts
+    std::vector<uint32_t> nl_deg(n, 0);
+    for (uint32_t u = 0; u < n; ++u)
+      for (uint32_t e = eoff[u]; e < eoff[u + 1]; ++e) if (!leaf[s.edge_to[e]]) ++nl_deg[u];
+    order.clear();
+    for (uint32_t u = 0; u < n; ++u) if (!leaf[u]) order.push_back(u);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+      if (level[a] != level[b]) return level[a] < level[b];
+      return nl_deg[a] > nl_deg[b];
+    });
+    for (uint32_t k = 0; k < order.size(); ++k) newidx[order[k]] = k;
   }
   const uint32_t N = (uint32_t)order.size();
   h.N = N; h.nlev = nlev;

@@ -17,7 +17,8 @@ struct StemLaunch {
   unsigned long long scratch_stride;  // doubles per CTA
   const double* pair_tab;       // 256 doubles
   uint32_t len_band;
-  uint32_t rb;                  // rows per row block
+  uint32_t nslots;              // warps of a CTA that own a (Q row, G1 row) pair in shared memory
+  uint32_t nx_cap;              // largest Nx over the x set (row flags)
   uint32_t ny_cap;              // largest Ny / Ey / level count over the y set (shared-memory carve-up)
   uint32_t ey_cap;
   uint32_t lev_cap;
@@ -38,7 +39,8 @@ struct StringLaunch {
 };
 
 // host-callable launchers (defined in the .cu files); all asynchronous on `stream`
-size_t stem_smem_bytes(uint32_t rb, uint32_t ny_cap, uint32_t ey_cap, uint32_t lev_cap);
+size_t stem_smem_bytes(uint32_t nslots, uint32_t nx_cap, uint32_t ny_cap, uint32_t ey_cap, uint32_t lev_cap);
+int stem_warps_per_cta();
 cudaError_t launch_stem(const StemLaunch& p, int grid, size_t smem, cudaStream_t stream);
 int stem_max_ctas_per_sm(size_t smem);
 cudaError_t launch_string(const StringLaunch& p, int cw, int grid, cudaStream_t stream);

@@ -17,17 +17,18 @@
 // With a length band, G1(i,j) is identically 0 when len_j + band < len_i (MATCH is out of band for
 // j and for every descendant of j, which are all shorter), so those cells are skipped.
 //
-// Mapping.  The y record (DAG in CSR form, per-node constants) is staged in shared memory once per
-// pair.  Rows of one x-level are independent and are processed in blocks of up to RB rows:
-//   phase A  threads <-> columns j : Q rows of the block from earlier G0 rows -- coalesced reads of the
-//            per-CTA G0 slab in global memory (L2-resident), the block's x edges staged in shared
-//            memory so that the loads of one thread are independent and can be in flight together
-//   phase B  y-level by y-level, threads <-> cells (row, node of the level) with rows fastest, so the
-//            lanes of a warp share a node (same child list, no degree divergence) and read
-//            consecutive shared-memory words of the node-major Q / G1 tiles ([node][RB|1])
-//   phase C  threads <-> columns : finished G0 rows written back coalesced
-// One CTA barrier per y-level and three per row block.  Shared memory is addressed through 32-bit
-// byte offsets from one base so that every access is an LDS/STS with a register+immediate address.
+// Mapping: dataflow over rows.  The y record (DAG in CSR form, per-node constants) is staged in shared
+// memory once per pair.  Each of the CTA's warps then repeatedly takes the next row i of x (rows are
+// numbered level by level, so every child of a row has a smaller number), waits on shared-memory flags
+// until the rows of i's inner pairs are finished, and processes the row on its own:
+//   A  lanes <-> columns: Q(i,:) from the finished G0 rows (coalesced L2 reads of the per-CTA G0 slab;
+//      the row's edge list sits in lane registers and is broadcast by shuffles)
+//   B  y-level by y-level, lanes <-> nodes of the level: R, S gathered from the warp's private Q / G1
+//      rows in shared memory; only __syncwarp between levels
+//   C  lanes <-> columns: the finished G0 row is written back, fenced, and the row's flag is raised
+// There is no CTA-wide barrier inside a pair: warps sit at different rows, levels and phases, which is
+// what hides the shared-memory and L2 latency of this pointer-chasing recursion.  Shared memory is
+// addressed through 32-bit byte offsets from one base (LDS/STS with register+immediate addresses).
 #include <cstdio>
 
 #include "kernels.cuh"
@@ -38,11 +39,10 @@ namespace {
 
 constexpr int kStemThreads = 512;
 constexpr int kStemWarps = kStemThreads / 32;
-constexpr uint32_t kXEdgeCap = 768;  // x edges staged per row block
 
-struct __align__(16) EdgeRec {   // one staged DAG edge
+struct __align__(16) EdgeRec {   // one staged y edge
   double ce;                     // g^gaps * edge weight
-  uint32_t off;                  // x edges: element offset of the child's G0 row; y edges: byte offset of the child's tile row
+  uint32_t off;                  // byte offset of the child inside a Q / G1 row
   uint32_t pad;
 };
 struct __align__(16) NodeInt {   // integer part of a staged y node
@@ -53,14 +53,15 @@ struct __align__(16) NodeInt {   // integer part of a staged y node
 
 // byte offsets of the shared-memory carve-up; everything 16-byte aligned
 struct StemLayout {
-  uint32_t tab, red, yA, yB, yG, yI, yE, yLev, xA, xB, xG, xI, xE, xOff, Q, G1, total;
+  uint32_t tab, red, yA, yB, yG, yI, yE, yLev, done, rows, row_bytes, nslots, total;
 };
 
-__host__ __device__ inline StemLayout stem_layout(uint32_t rb, uint32_t ny_cap, uint32_t ey_cap, uint32_t lev_cap) {
+// nslots warps get a private (Q row, G1 row) pair; the rest of the CTA's warps stay idle for that launch
+__host__ __device__ inline StemLayout stem_layout(uint32_t nslots, uint32_t nx_cap, uint32_t ny_cap, uint32_t ey_cap,
+                                                  uint32_t lev_cap) {
   StemLayout L;
   uint32_t off = 0;
   auto take = [&](uint32_t bytes) { uint32_t at = off; off += (bytes + 15u) & ~15u; return at; };
-  const uint32_t rbp = rb | 1u;
   L.tab = take(8 * 256);
   L.red = take(8 * kStemWarps);
   L.yA = take(16 * ny_cap);        // double2 {a, el}
@@ -69,14 +70,10 @@ __host__ __device__ inline StemLayout stem_layout(uint32_t rb, uint32_t ny_cap, 
   L.yI = take(16 * ny_cap);        // NodeInt
   L.yE = take(16 * ey_cap);        // EdgeRec
   L.yLev = take(4 * (lev_cap + 1));
-  L.xA = take(16 * rb);            // double2 {a, ql}
-  L.xB = take(16 * rb);            // double2 {paths, bfreq}
-  L.xG = take(8 * rb);             // gapt
-  L.xI = take(8 * rb);             // uint2 {len, bcode}
-  L.xE = take(16 * kXEdgeCap);     // EdgeRec
-  L.xOff = take(4 * (rb + 1));
-  L.Q = take(8 * ny_cap * rbp);    // [node][rbp]
-  L.G1 = take(8 * ny_cap * rbp);
+  L.done = take(4 * nx_cap);       // row-finished flags
+  L.row_bytes = (8u * ny_cap + 15u) & ~15u;
+  L.nslots = nslots;
+  L.rows = take(2u * L.row_bytes * nslots);  // per slot: Q row then G1 row
   L.total = off;
   return L;
 }
@@ -103,23 +100,29 @@ __device__ __noinline__ double node_match_general(const uint32_t* __restrict__ x
   return v;
 }
 
+__device__ __forceinline__ uint32_t ld_flag(const unsigned char* sm, uint32_t byteoff) {
+  return *reinterpret_cast<const volatile uint32_t*>(sm + byteoff);
+}
+
 __global__ void __launch_bounds__(kStemThreads, 1) stem_pairs_kernel(const StemLaunch P) {
   extern __shared__ __align__(16) unsigned char sm[];
   __shared__ unsigned long long s_pair;
-  const StemLayout L = stem_layout(P.rb, P.ny_cap, P.ey_cap, P.lev_cap);
+  __shared__ uint32_t s_next_row;
+  const StemLayout L = stem_layout(P.nslots, P.nx_cap, P.ny_cap, P.ey_cap, P.lev_cap);
 #define SM(T, byteoff) (*reinterpret_cast<T*>(sm + (byteoff)))
 
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-  const uint32_t RB = P.rb, RBP = P.rb | 1u;
   const uint32_t band = P.len_band;
   for (uint32_t t = tid; t < 256; t += kStemThreads) SM(double, L.tab + 8 * t) = P.pair_tab[t];
   double* __restrict__ G0 = P.scratch + (size_t)blockIdx.x * P.scratch_stride;
   const SetView& X = P.X;
   const SetView& Y = P.Y;
+  const uint32_t qrow = L.rows + 2u * L.row_bytes * warp;  // this warp's Q row; its G1 row follows
+  const uint32_t g1row = qrow + L.row_bytes;
 
   for (;;) {
     __syncthreads();  // previous pair fully retired (also orders the tab fill on the first trip)
-    if (tid == 0) s_pair = atomicAdd(P.counter, 1ull);
+    if (tid == 0) { s_pair = atomicAdd(P.counter, 1ull); s_next_row = 0; }
     __syncthreads();
     const unsigned long long k = s_pair;
     if (k >= P.n_pairs) break;
@@ -135,7 +138,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_pairs_kernel(const StemL
     const uint32_t ye0 = Y.coff[ry.coff0];  // first edge of y in the global edge arrays
     const uint32_t Ey = Y.coff[ry.coff0 + Ny] - ye0;
 
-    // ---- stage the y record
+    // ---- stage the y record, clear the row flags
     for (uint32_t j = tid; j < Ny; j += kStemThreads) {
       const uint32_t g = ry.node0 + j;
       SM(double2, L.yA + 16 * j) = make_double2(Y.a[g], Y.el[g]);
@@ -147,161 +150,130 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_pairs_kernel(const StemL
     }
     for (uint32_t e = tid; e < Ey; e += kStemThreads) {
       EdgeRec er;
-      er.ce = Y.ce[ye0 + e]; er.off = Y.cidx[ye0 + e] * RBP * 8u; er.pad = 0;
+      er.ce = Y.ce[ye0 + e]; er.off = Y.cidx[ye0 + e] * 8u; er.pad = 0;
       SM(EdgeRec, L.yE + 16 * e) = er;
     }
     for (uint32_t l = tid; l <= ry.nlev; l += kStemThreads) SM(uint32_t, L.yLev + 4 * l) = Y.lev_off[ry.lev0 + l];
+    for (uint32_t i = tid; i < Nx; i += kStemThreads) SM(uint32_t, L.done + 4 * i) = 0u;
+    __syncthreads();
+
     const uint32_t* __restrict__ xcoff = X.coff + rx.coff0;
-    const uint32_t* __restrict__ xlev = X.lev_off + rx.lev0;
     const bool simple_bpf = (rx.flags & REC_SIMPLE_BPF) && (ry.flags & REC_SIMPLE_BPF);
     const bool skip_short = band != 0u && (ry.flags & REC_LEN_MONOTONE);  // zero-G1 shortcut is valid
     double acc = 0.0;
 
-    for (uint32_t lx = 0; lx < rx.nlev; ++lx) {
-      const uint32_t lev_end = xlev[lx + 1];
-      uint32_t row0 = xlev[lx];
-      while (row0 < lev_end) {
-        // rows of this block: at most RB, and at most kXEdgeCap staged edges
-        uint32_t nrows = min(RB, lev_end - row0);
-        const uint32_t xe0 = xcoff[row0];
-        while (nrows > 1 && xcoff[row0 + nrows] - xe0 > kXEdgeCap) --nrows;
-        const uint32_t nedge_all = xcoff[row0 + nrows] - xe0;
-        const bool staged = nedge_all <= kXEdgeCap;  // false only for a single row wider than the staging area
+    if (warp < L.nslots) {
+      for (;;) {
+        uint32_t i = 0;
+        if (lane == 0) i = atomicAdd(&s_next_row, 1u);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= Nx) break;
+        const uint32_t gx = rx.node0 + i;
+        const uint32_t e0 = xcoff[i], e1 = xcoff[i + 1];
+        const double xa = X.a[gx], xql = X.ql[gx], xpath = X.paths[gx], xbf = X.bfreq[gx], xgap = X.gapt[gx];
+        const uint32_t xl = X.len[gx], xbc = X.bcode[gx];
 
-        __syncthreads();  // previous block is done with Q/G1 and the x staging area
-        for (uint32_t r = tid; r < nrows; r += kStemThreads) {
-          const uint32_t g = rx.node0 + row0 + r;
-          SM(double2, L.xA + 16 * r) = make_double2(X.a[g], X.ql[g]);
-          SM(double2, L.xB + 16 * r) = make_double2(X.paths[g], X.bfreq[g]);
-          SM(double, L.xG + 8 * r) = X.gapt[g];
-          SM(uint2, L.xI + 8 * r) = make_uint2(X.len[g], X.bcode[g]);
-        }
-        for (uint32_t r = tid; r <= nrows; r += kStemThreads) SM(uint32_t, L.xOff + 4 * r) = xcoff[row0 + r] - xe0;
-        if (staged)
-          for (uint32_t e = tid; e < nedge_all; e += kStemThreads) {
-            EdgeRec er;
-            er.ce = X.ce[xe0 + e]; er.off = X.cidx[xe0 + e] * NYS; er.pad = 0;
-            SM(EdgeRec, L.xE + 16 * e) = er;
+        // ---- phase A: Q(i,:) = sum over inner pairs c of e * G0(c,:)
+        for (uint32_t eb = e0; eb < e1 || eb == e0; eb += 32u) {
+          // up to 32 edges of the row live in lane registers
+          const uint32_t ne = min(32u, e1 - eb);
+          double ce_l = 0.0;
+          uint32_t off_l = 0u;
+          if (lane < ne) {
+            const uint32_t c = X.cidx[eb + lane];
+            ce_l = X.ce[eb + lane];
+            off_l = c * NYS;
+            while (ld_flag(sm, L.done + 4u * c) == 0u) __nanosleep(40);  // wait until that row is finished
           }
-        __syncthreads();
-
-        // ---- phase A: Q(block rows, all columns), one column per thread, loads of a row unrolled
-        if (lx == 0) {
-          for (uint32_t t = tid; t < Ny * RBP; t += kStemThreads) SM(double, L.Q + 8 * t) = 0.0;  // hairpin rows: no inner pair
-        } else if (staged) {
-          for (uint32_t j = tid; j < Ny; j += kStemThreads) {
-            const double* __restrict__ g0c = G0 + j;
-            uint32_t e = 0;
-            for (uint32_t r = 0; r < nrows; ++r) {
-              const uint32_t e1 = SM(uint32_t, L.xOff + 4 * (r + 1));
-              double q0 = 0.0, q1 = 0.0;
-#pragma unroll 1
-              for (; e + 3 < e1; e += 4) {
-                const EdgeRec a = SM(EdgeRec, L.xE + 16 * e), b = SM(EdgeRec, L.xE + 16 * e + 16),
-                              c = SM(EdgeRec, L.xE + 16 * e + 32), d = SM(EdgeRec, L.xE + 16 * e + 48);
-                const double va = g0c[a.off], vb = g0c[b.off], vc = g0c[c.off], vd = g0c[d.off];
-                q0 = fma(a.ce, va, q0); q1 = fma(b.ce, vb, q1); q0 = fma(c.ce, vc, q0); q1 = fma(d.ce, vd, q1);
-              }
-#pragma unroll 1
-              for (; e < e1; ++e) {
-                const EdgeRec a = SM(EdgeRec, L.xE + 16 * e);
-                q0 = fma(a.ce, g0c[a.off], q0);
-              }
-              SM(double, L.Q + 8 * (j * RBP + r)) = q0 + q1;
+          __syncwarp();
+          __threadfence_block();  // acquire: the G0 rows behind the flags just seen
+          for (uint32_t jb = 0; jb < Ny; jb += 64u) {  // uniform trip count: the shuffles below need every lane
+            const uint32_t j = jb + lane;
+            const bool one = j < Ny, two = j + 32u < Ny;
+            double q0 = (one && eb != e0) ? SM(double, qrow + 8u * j) : 0.0;
+            double q1 = (two && eb != e0) ? SM(double, qrow + 8u * (j + 32u)) : 0.0;
+#pragma unroll 4
+            for (uint32_t t = 0; t < ne; ++t) {
+              const double ce = __shfl_sync(0xffffffffu, ce_l, t);
+              const uint32_t off = __shfl_sync(0xffffffffu, off_l, t);
+              if (one) q0 = fma(ce, __ldcg(G0 + off + j), q0);
+              if (two) q1 = fma(ce, __ldcg(G0 + off + j + 32u), q1);
             }
+            if (one) SM(double, qrow + 8u * j) = q0;
+            if (two) SM(double, qrow + 8u * (j + 32u)) = q1;
           }
-        } else {
-          for (uint32_t j = tid; j < Ny; j += kStemThreads) {
-            double q = 0.0;
-            for (uint32_t e = xe0; e < xcoff[row0 + 1]; ++e) q = fma(X.ce[e], G0[(size_t)X.cidx[e] * NYS + j], q);
-            SM(double, L.Q + 8 * (j * RBP)) = q;
-          }
+          if (e1 == e0) break;
         }
-        __syncthreads();
+        __syncwarp();
 
-        // ---- phase B: sweep the y DAG level by level; cells = (row, node), rows fastest.
-        // (r, jj) of this thread's first cell and the step to its next cell (tid + kStemThreads)
-        const uint32_t jj_first = tid / nrows, r_first = tid - jj_first * nrows;
-        const uint32_t jj_step = kStemThreads / nrows, r_step = kStemThreads - jj_step * nrows;
+        // ---- phase B: sweep the y DAG level by level, lanes <-> nodes of the level
+        double racc = 0.0;
+        uint32_t jbeg = SM(uint32_t, L.yLev);
         for (uint32_t ly = 0; ly < ry.nlev; ++ly) {
-          const uint32_t j0 = SM(uint32_t, L.yLev + 4 * ly);
-          const uint32_t nj = SM(uint32_t, L.yLev + 4 * ly + 4) - j0;
-          uint32_t jj = jj_first, r = r_first;
-          while (jj < nj) {
-            const uint32_t j = j0 + jj;
-            const NodeInt ni = SM(NodeInt, L.yI + 16 * j);
-            const uint2 xi = SM(uint2, L.xI + 8 * r);
-            const uint32_t cell_off = 8u * (j * RBP + r);
-            // G1 == 0 for every node shorter than len_i - band (see header); nothing to do for the cell
-            if (skip_short && ni.len + band < xi.x) {
-              SM(double, L.G1 + cell_off) = 0.0;
-            } else {
-              const uint32_t dl = xi.x > ni.len ? xi.x - ni.len : ni.len - xi.x;
-              const bool in_band = (band == 0u) || (dl <= band);
-              const double2 yA = SM(double2, L.yA + 16 * j);                   // {a_y, el_y}
-              double S0 = 0.0, S1 = 0.0;
-              double m = 0.0;
-              const uint32_t g1r = L.G1 + 8u * r, qr = L.Q + 8u * r;
-              uint32_t e = L.yE + 16u * ni.e0;
-              const uint32_t eend = L.yE + 16u * ni.e1;
-              if (in_band) {
-                const double2 xA = SM(double2, L.xA + 16 * r);                 // {a_x, ql_x}
-                const double2 xB = SM(double2, L.xB + 16 * r);                 // {paths_x, bfreq_x}
-                const double2 yB = SM(double2, L.yB + 16 * j);                 // {paths_y, bfreq_y}
-                double vs;
-                if (simple_bpf) vs = SM(double, L.tab + 8u * (xi.y * 16u + ni.bcode)) * xB.y * yB.y;
-                else vs = node_match_general(X.boff + rx.boff0 + row0 + r, X.bab, X.bfq, Y.boff + ry.boff0 + j, Y.bab, Y.bfq,
-                                             reinterpret_cast<const double*>(sm + L.tab));
-                vs = fma(yA.x, SM(double, L.xG + 8 * r), vs);
-                vs = fma(xA.x, SM(double, L.yG + 8 * j), vs);
-                double R0 = 0.0, R1 = 0.0;
-#pragma unroll 1
-                for (; e + 16u < eend; e += 32u) {
-                  const EdgeRec a = SM(EdgeRec, e), b = SM(EdgeRec, e + 16u);
-                  S0 = fma(a.ce, SM(double, g1r + a.off), S0); R0 = fma(a.ce, SM(double, qr + a.off), R0);
-                  S1 = fma(b.ce, SM(double, g1r + b.off), S1); R1 = fma(b.ce, SM(double, qr + b.off), R1);
-                }
-                if (e < eend) {
-                  const EdgeRec a = SM(EdgeRec, e);
-                  S0 = fma(a.ce, SM(double, g1r + a.off), S0); R0 = fma(a.ce, SM(double, qr + a.off), R0);
-                }
-                const double R = fma(yA.y, xA.y, R0 + R1);
-                m = vs * R;
-                acc = fma(xB.x * yB.x, m, acc);
-              } else {
-#pragma unroll 1
-                for (; e + 16u < eend; e += 32u) {
-                  const EdgeRec a = SM(EdgeRec, e), b = SM(EdgeRec, e + 16u);
-                  S0 = fma(a.ce, SM(double, g1r + a.off), S0);
-                  S1 = fma(b.ce, SM(double, g1r + b.off), S1);
-                }
-                if (e < eend) {
-                  const EdgeRec a = SM(EdgeRec, e);
-                  S0 = fma(a.ce, SM(double, g1r + a.off), S0);
-                }
-              }
-              SM(double, L.G1 + cell_off) = fma(yA.x, S0 + S1, m);
+          const uint32_t jend = SM(uint32_t, L.yLev + 4u * ly + 4u);
+          for (uint32_t j = jbeg + lane; j < jend; j += 32u) {
+            const NodeInt ni = SM(NodeInt, L.yI + 16u * j);
+            if (skip_short && ni.len + band < xl) {  // G1 == 0 here and below (see header)
+              SM(double, g1row + 8u * j) = 0.0;
+              continue;
             }
-            jj += jj_step; r += r_step;
-            if (r >= nrows) { r -= nrows; ++jj; }
+            const uint32_t dl = xl > ni.len ? xl - ni.len : ni.len - xl;
+            const bool in_band = (band == 0u) || (dl <= band);
+            const double2 yA = SM(double2, L.yA + 16u * j);  // {a_y, el_y}
+            double S0 = 0.0, S1 = 0.0, m = 0.0;
+            uint32_t e = L.yE + 16u * ni.e0;
+            const uint32_t eend = L.yE + 16u * ni.e1;
+            if (in_band) {
+              const double2 yB = SM(double2, L.yB + 16u * j);  // {paths_y, bfreq_y}
+              double vs;
+              if (simple_bpf) vs = SM(double, L.tab + 8u * (xbc * 16u + ni.bcode)) * xbf * yB.y;
+              else vs = node_match_general(X.boff + rx.boff0 + i, X.bab, X.bfq, Y.boff + ry.boff0 + j, Y.bab, Y.bfq,
+                                           reinterpret_cast<const double*>(sm + L.tab));
+              vs = fma(yA.x, xgap, vs);
+              vs = fma(xa, SM(double, L.yG + 8u * j), vs);
+              double R0 = 0.0, R1 = 0.0;
+#pragma unroll 1
+              for (; e + 16u < eend; e += 32u) {
+                const EdgeRec a = SM(EdgeRec, e), b = SM(EdgeRec, e + 16u);
+                S0 = fma(a.ce, SM(double, g1row + a.off), S0); R0 = fma(a.ce, SM(double, qrow + a.off), R0);
+                S1 = fma(b.ce, SM(double, g1row + b.off), S1); R1 = fma(b.ce, SM(double, qrow + b.off), R1);
+              }
+              if (e < eend) {
+                const EdgeRec a = SM(EdgeRec, e);
+                S0 = fma(a.ce, SM(double, g1row + a.off), S0); R0 = fma(a.ce, SM(double, qrow + a.off), R0);
+              }
+              m = vs * fma(yA.y, xql, R0 + R1);
+              racc = fma(yB.x, m, racc);
+            } else {
+#pragma unroll 1
+              for (; e + 16u < eend; e += 32u) {
+                const EdgeRec a = SM(EdgeRec, e), b = SM(EdgeRec, e + 16u);
+                S0 = fma(a.ce, SM(double, g1row + a.off), S0);
+                S1 = fma(b.ce, SM(double, g1row + b.off), S1);
+              }
+              if (e < eend) {
+                const EdgeRec a = SM(EdgeRec, e);
+                S0 = fma(a.ce, SM(double, g1row + a.off), S0);
+              }
+            }
+            SM(double, g1row + 8u * j) = fma(yA.x, S0 + S1, m);
           }
-          __syncthreads();
+          jbeg = jend;
+          __syncwarp();
         }
+        acc = fma(xpath, racc, acc);
 
-        // ---- phase C: finished rows, G0(i,:) = G1 + a_x * Q, coalesced over columns
-        for (uint32_t j = tid; j < Ny; j += kStemThreads) {
-          for (uint32_t r = 0; r < nrows; ++r) {
-            const uint32_t o = 8u * (j * RBP + r);
-            G0[(size_t)(row0 + r) * NYS + j] = fma(SM(double2, L.xA + 16 * r).x, SM(double, L.Q + o), SM(double, L.G1 + o));
-          }
-        }
-        row0 += nrows;
+        // ---- phase C: finished row G0(i,:) = G1 + a_x * Q, then publish it
+        double* __restrict__ g0row = G0 + (size_t)i * NYS;
+        for (uint32_t j = lane; j < Ny; j += 32u) g0row[j] = fma(xa, SM(double, qrow + 8u * j), SM(double, g1row + 8u * j));
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) *reinterpret_cast<volatile uint32_t*>(sm + L.done + 4u * i) = 1u;
       }
     }
 
     // ---- block reduction of the path-weighted MATCH sum
     acc = warp_sum(acc);
-    __syncthreads();
     if (lane == 0) SM(double, L.red + 8 * warp) = acc;
     __syncthreads();
     if (tid == 0) {
@@ -315,9 +287,10 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_pairs_kernel(const StemL
 
 }  // namespace
 
-size_t stem_smem_bytes(uint32_t rb, uint32_t ny_cap, uint32_t ey_cap, uint32_t lev_cap) {
-  return stem_layout(rb, ny_cap, ey_cap, lev_cap).total;
+size_t stem_smem_bytes(uint32_t nslots, uint32_t nx_cap, uint32_t ny_cap, uint32_t ey_cap, uint32_t lev_cap) {
+  return stem_layout(nslots, nx_cap, ny_cap, ey_cap, lev_cap).total;
 }
+int stem_warps_per_cta() { return kStemWarps; }
 
 int stem_max_ctas_per_sm(size_t smem) {
   int n = 0;

@@ -85,16 +85,14 @@ size_t place(size_t& off, const std::vector<T>& v) {
   return at;
 }
 
-// rows per block and shared memory for a launch over the y set `ys`
-void stem_config(const stemk_ctx* ctx, const CompiledSet& ys, uint32_t* rb, size_t* smem) {
-  const uint32_t ny = std::max(1u, ys.max_N), ey = std::max(1u, ys.max_E), lv = std::max(1u, ys.max_nlev);
-  const size_t budget2 = (size_t)108 * 1024;  // two CTAs per SM
-  const size_t budget1 = std::min<size_t>(ctx->smem_optin, (size_t)224 * 1024);
+// number of row slots (warps with private Q/G1 rows) and shared memory for a launch of x set against y set
+void stem_config(const stemk_ctx* ctx, const CompiledSet& xs, const CompiledSet& ys, uint32_t* nslots, size_t* smem) {
+  const uint32_t nx = std::max(1u, xs.max_N), ny = std::max(1u, ys.max_N), ey = std::max(1u, ys.max_E), lv = std::max(1u, ys.max_nlev);
+  const size_t budget = std::min<size_t>(ctx->smem_optin, (size_t)226 * 1024);
   uint32_t best = 0;
-  for (uint32_t r = 32; r >= 16; r -= 4) if (stem_smem_bytes(r, ny, ey, lv) <= budget2) { best = r; break; }
-  if (!best) for (uint32_t r = 32; r >= 1; --r) if (stem_smem_bytes(r, ny, ey, lv) <= budget1) { best = r; break; }
-  *rb = best;
-  *smem = best ? stem_smem_bytes(best, ny, ey, lv) : 0;
+  for (uint32_t w = (uint32_t)stem_warps_per_cta(); w >= 1; --w) if (stem_smem_bytes(w, nx, ny, ey, lv) <= budget) { best = w; break; }
+  *nslots = best;
+  *smem = best ? stem_smem_bytes(best, nx, ny, ey, lv) : 0;
 }
 
 }  // namespace
@@ -234,9 +232,9 @@ int stemk_pairs_device(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, s
 
   if (has_stem) {
     const uint32_t ny_cap = std::max(1u, y->host.max_N), nx_cap = std::max(1u, x->host.max_N);
-    uint32_t rb; size_t smem;
-    stem_config(ctx, y->host, &rb, &smem);
-    if (!rb) return fail(ctx, STEMK_ERR_NOMEM, "a record has too many DAG nodes for the shared-memory row block");
+    uint32_t nslots; size_t smem;
+    stem_config(ctx, x->host, y->host, &nslots, &smem);
+    if (!nslots) return fail(ctx, STEMK_ERR_NOMEM, "a record has too many DAG nodes to stage in shared memory");
     int per_sm = stem_max_ctas_per_sm(smem);
     if (per_sm < 1) return fail(ctx, STEMK_ERR_CUDA, "stem kernel does not fit on an SM");
     per_sm = std::min(per_sm, 4);
@@ -247,7 +245,7 @@ int stemk_pairs_device(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, s
     StemLaunch L;
     L.X = x->view; L.Y = y->view; L.xi = d_xi; L.yi = d_yi; L.n_pairs = n_pairs; L.out = stem_out;
     L.counter = ctx->d_counter; L.scratch = (double*)ctx->scratch.p; L.scratch_stride = stride;
-    L.pair_tab = ctx->d_pair_tab; L.len_band = ctx->params.len_band; L.rb = rb; L.ny_cap = ny_cap; L.ey_cap = std::max(1u, y->host.max_E); L.lev_cap = std::max(1u, y->host.max_nlev);
+    L.pair_tab = ctx->d_pair_tab; L.len_band = ctx->params.len_band; L.nslots = nslots; L.nx_cap = nx_cap; L.ny_cap = ny_cap; L.ey_cap = std::max(1u, y->host.max_E); L.lev_cap = std::max(1u, y->host.max_nlev);
     CU(cudaEventRecord(ctx->ev0, st));
     CU(launch_stem(L, grid, smem, st));
     CU(cudaEventRecord(ctx->ev1, st));
