@@ -141,6 +141,12 @@ int stemk_pairs(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, size_t n
 int stemk_pairs_device(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, size_t n_pairs,
                        const uint32_t* d_xi, const uint32_t* d_yi, double* d_out, void* stream);
 
+/* Rank-0 half of a distributed KernelMatrix::calculate (kernel_matrix.cpp:504-526 gathers the ranks' values,
+ * :560-571 normalises): scatter n_pairs gathered values into the n*n DEVICE matrix, mirroring (i,j) to (j,i),
+ * then optionally K_ij /= sqrt(K_ii K_jj), K_ii = 1.  Asynchronous on `stream`. */
+int stemk_assemble_device(stemk_ctx* ctx, size_t n_pairs, const uint32_t* d_xi, const uint32_t* d_yi,
+                          const double* d_vals, uint32_t n, int normalize, double* d_matrix, void* stream);
+
 /* Work model of SURVEY 8(d), per pair: DP cells and algorithmic flops
  * (stem: 2*U_match + 3*U_bf + 3*U_skip; string: 9, 7 or 4(+3 per match) per cell). Host only. */
 int stemk_pair_cost(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, size_t n_pairs, const uint32_t* xi,
@@ -149,7 +155,7 @@ int stemk_pair_cost(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, size
 /* Launch accounting for benchmarks: kernels launched / device ms (CUDA events on the library's own
  * stream) spent inside them since the last reset. */
 void stemk_stats_reset(stemk_ctx* ctx);
-void stemk_stats_get(const stemk_ctx* ctx, uint64_t* launches, double* stem_ms, double* string_ms);
+void stemk_stats_get(stemk_ctx* ctx, uint64_t* launches, double* stem_ms, double* string_ms);
 
 /* FP64 FMA micro-benchmark on the context's device: returns sustained Tflop/s (the roofline
  * denominator, since MEASURED_PEAKS.json carries no fp64 entry). */

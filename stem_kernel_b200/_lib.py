@@ -33,7 +33,7 @@ def make_params(kind, loop_gap=0.2, beta=0.3, stack=1.3, covar=0.8, gap=0.8, alp
 
 EXPORTS = ["stemk_version", "stemk_device_count", "stemk_create", "stemk_destroy", "stemk_last_error", "stemk_upload",
            "stemk_set_free", "stemk_set_size", "stemk_gram", "stemk_cross", "stemk_diag", "stemk_pairs",
-           "stemk_pairs_device", "stemk_pair_cost", "stemk_stats_reset", "stemk_stats_get", "stemk_fp64_peak"]
+           "stemk_pairs_device", "stemk_assemble_device", "stemk_pair_cost", "stemk_stats_reset", "stemk_stats_get", "stemk_fp64_peak"]
 
 _lib = None
 
@@ -61,6 +61,7 @@ def lib():
         L.stemk_diag.argtypes = [vp, vp, vp, u32, vp]
         L.stemk_pairs.argtypes = [vp, vp, vp, sz, vp, vp, vp]
         L.stemk_pairs_device.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp]
+        L.stemk_assemble_device.argtypes = [vp, sz, vp, vp, vp, u32, C.c_int, vp, vp]
         L.stemk_pair_cost.argtypes = [vp, vp, vp, sz, vp, vp, vp, vp]
         L.stemk_stats_reset.argtypes = [vp]
         L.stemk_stats_get.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_double)]

@@ -82,6 +82,11 @@ class Context:
         """Device pointers (ints, e.g. torch.Tensor.data_ptr()); asynchronous on `stream` (cudaStream_t as int)."""
         self._check(L.lib().stemk_pairs_device(self.h, x.h, y.h, n_pairs, d_xi, d_yi, d_out, stream))
 
+    def assemble_device(self, n_pairs, d_xi, d_yi, d_vals, n, normalize, d_matrix, stream=None):
+        """Scatter gathered pair values into the n x n device matrix (+ mirror, + normalisation)."""
+        self._check(L.lib().stemk_assemble_device(self.h, n_pairs, d_xi, d_yi, d_vals, n, int(normalize), d_matrix,
+                                                  stream))
+
     def pair_cost(self, x, y, xi, yi):
         xi = np.ascontiguousarray(xi, dtype=np.uint32)
         yi = np.ascontiguousarray(yi, dtype=np.uint32)

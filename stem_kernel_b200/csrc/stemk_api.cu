@@ -60,9 +60,35 @@ struct stemk_ctx {
   uint64_t launches = 0;
   double stem_ms = 0, string_ms = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // launch timings are resolved lazily (stemk_stats_get) so that the launch path never blocks the host
+  struct Timed { cudaEvent_t a, b; int which; };
+  std::vector<Timed> pending, free_events;
 };
 
 namespace {
+
+// event pair around one kernel launch; `which` 0 = stem, 1 = string
+stemk_ctx::Timed timed_begin(stemk_ctx* c, int which, cudaStream_t st) {
+  stemk_ctx::Timed t{nullptr, nullptr, which};
+  if (!c->free_events.empty()) { t = c->free_events.back(); c->free_events.pop_back(); t.which = which; }
+  else { cudaEventCreate(&t.a); cudaEventCreate(&t.b); }
+  cudaEventRecord(t.a, st);
+  return t;
+}
+void timed_resolve(stemk_ctx* c) {
+  for (auto& t : c->pending) {
+    float ms = 0;
+    if (cudaEventSynchronize(t.b) == cudaSuccess && cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess)
+      (t.which == 0 ? c->stem_ms : c->string_ms) += ms;
+    c->free_events.push_back(t);
+  }
+  c->pending.clear();
+}
+void timed_end(stemk_ctx* c, stemk_ctx::Timed t, cudaStream_t st) {
+  cudaEventRecord(t.b, st);
+  c->pending.push_back(t);
+  if (c->pending.size() >= 256) timed_resolve(c);
+}
 
 int fail(stemk_ctx* c, int code, const std::string& msg) {
   if (c) c->err = msg; else g_create_error = msg;
@@ -154,6 +180,8 @@ void stemk_destroy(stemk_ctx* c) {
   if (c->d_pair_tab) cudaFree(c->d_pair_tab);
   if (c->d_subst) cudaFree(c->d_subst);
   if (c->d_counter) cudaFree(c->d_counter);
+  timed_resolve(c);
+  for (auto& t : c->free_events) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -246,13 +274,11 @@ int stemk_pairs_device(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, s
     L.X = x->view; L.Y = y->view; L.xi = d_xi; L.yi = d_yi; L.n_pairs = n_pairs; L.out = stem_out;
     L.counter = ctx->d_counter; L.scratch = (double*)ctx->scratch.p; L.scratch_stride = stride;
     L.pair_tab = ctx->d_pair_tab; L.len_band = ctx->params.len_band; L.nslots = nslots; L.nx_cap = nx_cap; L.ny_cap = ny_cap; L.ey_cap = std::max(1u, y->host.max_E); L.lev_cap = std::max(1u, y->host.max_nlev);
-    CU(cudaEventRecord(ctx->ev0, st));
-    CU(launch_stem(L, grid, smem, st));
-    CU(cudaEventRecord(ctx->ev1, st));
+    stemk_ctx::Timed tm = timed_begin(ctx, 0, st);
+    cudaError_t le = launch_stem(L, grid, smem, st);
+    timed_end(ctx, tm, st);
+    CU(le);
     ctx->launches += 1;
-    // stats need the elapsed time; callers that want overlap use the *_device entry once per batch
-    CU(cudaEventSynchronize(ctx->ev1));
-    float ms = 0; CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1)); ctx->stem_ms += ms;
   }
   if (has_str) {
     const uint32_t ly_cap = std::max(1u, y->host.max_L), lx_cap = std::max(1u, x->host.max_L);
@@ -267,12 +293,11 @@ int stemk_pairs_device(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, s
     L.X = x->view; L.Y = y->view; L.xi = d_xi; L.yi = d_yi; L.n_pairs = n_pairs; L.out = str_out;
     L.counter = ctx->d_counter; L.carry = (double*)ctx->carry.p; L.carry_stride = cstride; L.subst = ctx->d_subst;
     L.gap = ctx->params.gap; L.naive = kind == STEMK_STR_NAIVE;
-    CU(cudaEventRecord(ctx->ev0, st));
-    CU(launch_string(L, cw, grid, st));
-    CU(cudaEventRecord(ctx->ev1, st));
+    stemk_ctx::Timed tm = timed_begin(ctx, 1, st);
+    cudaError_t le = launch_string(L, cw, grid, st);
+    timed_end(ctx, tm, st);
+    CU(le);
     ctx->launches += 1;
-    CU(cudaEventSynchronize(ctx->ev1));
-    float ms = 0; CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1)); ctx->string_ms += ms;
   }
   if (combine) {
     CU(launch_combine(kind, ctx->params.alpha, ctx->params.beta, has_stem ? stem_out : nullptr,
@@ -342,12 +367,24 @@ int stemk_gram(stemk_ctx* ctx, const stemk_set* train, int normalize, double* ou
   int rc = stemk_pairs_device(ctx, train, train, n_pairs, (const uint32_t*)ctx->idx_x.p, (const uint32_t*)ctx->idx_y.p,
                               (double*)ctx->vals.p, ctx->stream);
   if (rc != STEMK_OK) return rc;
-  CU(launch_scatter_square((const double*)ctx->vals.p, (const uint32_t*)ctx->idx_x.p, (const uint32_t*)ctx->idx_y.p,
-                           n_pairs, (double*)ctx->matrix.p, n, ctx->stream));
-  ctx->launches += 1;
-  if (normalize) { CU(launch_normalize_square((double*)ctx->matrix.p, n, ctx->stream)); ctx->launches += 2; }
+  rc = stemk_assemble_device(ctx, n_pairs, (const uint32_t*)ctx->idx_x.p, (const uint32_t*)ctx->idx_y.p,
+                             (const double*)ctx->vals.p, n, normalize, (double*)ctx->matrix.p, ctx->stream);
+  if (rc != STEMK_OK) return rc;
   CU(cudaMemcpyAsync(out, ctx->matrix.p, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  return STEMK_OK;
+}
+
+int stemk_assemble_device(stemk_ctx* ctx, size_t n_pairs, const uint32_t* d_xi, const uint32_t* d_yi,
+                          const double* d_vals, uint32_t n, int normalize, double* d_matrix, void* stream_) {
+  if (!ctx) return fail(ctx, STEMK_ERR_ARG, "null argument");
+  if (n == 0) return STEMK_OK;
+  if (!d_matrix || (n_pairs && (!d_xi || !d_yi || !d_vals))) return fail(ctx, STEMK_ERR_ARG, "null buffer");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = stream_ ? (cudaStream_t)stream_ : ctx->stream;
+  CU(launch_scatter_square(d_vals, d_xi, d_yi, n_pairs, d_matrix, n, st));
+  ctx->launches += 1;
+  if (normalize) { CU(launch_normalize_square(d_matrix, n, st)); ctx->launches += 2; }
   return STEMK_OK;
 }
 
@@ -470,9 +507,10 @@ int stemk_pair_cost(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, size
   return STEMK_OK;
 }
 
-void stemk_stats_reset(stemk_ctx* ctx) { if (ctx) { ctx->launches = 0; ctx->stem_ms = ctx->string_ms = 0; } }
-void stemk_stats_get(const stemk_ctx* ctx, uint64_t* launches, double* stem_ms, double* string_ms) {
+void stemk_stats_reset(stemk_ctx* ctx) { if (ctx) { timed_resolve(ctx); ctx->launches = 0; ctx->stem_ms = ctx->string_ms = 0; } }
+void stemk_stats_get(stemk_ctx* ctx, uint64_t* launches, double* stem_ms, double* string_ms) {
   if (!ctx) return;
+  timed_resolve(ctx);
   if (launches) *launches = ctx->launches;
   if (stem_ms) *stem_ms = ctx->stem_ms;
   if (string_ms) *string_ms = ctx->string_ms;

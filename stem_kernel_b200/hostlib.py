@@ -166,6 +166,7 @@ class SeqSet:
     def desc(self):
         d = SeqSetDesc()
         lib().stemk_host_set_desc(self.h, C.byref(d))
+        d._owner = self  # the descriptor points into this set's arrays: keep them alive with it
         return d
 
     def __del__(self):

@@ -1,0 +1,101 @@
+"""Generates tests/golden/*.npz from the UNMODIFIED reference compiled under oracle/_ref (run in the build
+container, where /root/reference exists:  python tests/make_golden.py).  The reference ships no golden vectors
+of its own, so these files pin the oracle and the CUDA path to the reference's own outputs:
+
+  golden_pairs.npz     inputs (rows + sparse base-pair lists) of 17 records and, for every lite kernel class
+                       x {len_band 10, 0}: the reference's Gram matrix; normalised Gram, rectangular
+                       test x train matrix, sv_index row, diagonal and the printed text for SuStemStrKernel
+  golden_mdata.npz     the reference constructor's MData (DAG, profiles, weights) for each record
+  golden_naive.npz     string_kernel/ (naive) Gram on 8 raw strings, gap parsed as float
+  golden_svm.npz       40-record C1 Gram (reference) and the vendored LIBSVM's 5-fold CV targets on it
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import refbind as R  # noqa: E402
+from stem_kernel_b200 import synth  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+TH = 0.01
+
+
+def golden_records():
+    recs = synth.make_config(1, 6) + synth.make_config(3, 3)
+    recs += [synth.alignment_like(7, i, n_rows=(i % 4) + 1) for i in range(6)]
+    z = np.zeros(0, dtype=np.int64)
+    # no pair reaches the threshold: empty DAG, k_stem = 0 (stem_kernel.cpp:88-93 sums over no roots)
+    recs.append(dict(rows=["acguacguacguacguacgu"], bp=[(z, z, np.zeros(0))], label=1))
+    # a single isolated hairpin: one stem of 3 stacked pairs
+    recs.append(dict(rows=["gggaaaaccc"], bp=[(np.array([1, 2, 3]), np.array([10, 9, 8]), np.array([0.9, 0.8, 0.7]))],
+                     label=-1))
+    return recs
+
+
+def pack_records(recs):
+    rows = json.dumps([r["rows"] for r in recs])
+    labels = np.array([r["label"] for r in recs], dtype=np.int32)
+    bi, bj, bp, off = [], [], [], [0]
+    for r in recs:
+        for (a, b, p) in r["bp"]:
+            bi.append(np.asarray(a, dtype=np.uint32)); bj.append(np.asarray(b, dtype=np.uint32))
+            bp.append(np.asarray(p, dtype=np.float64)); off.append(off[-1] + len(a))
+    return dict(rows_json=np.array(rows), labels=labels, bp_i=np.concatenate(bi), bp_j=np.concatenate(bj),
+                bp_p=np.concatenate(bp), bp_off=np.array(off, dtype=np.int64))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    recs = golden_records()
+    ref = [R.RefMData.build(r["rows"], r["bp"], TH) for r in recs]
+    out = pack_records(recs)
+    for kind in range(9):
+        for band in (10, 0):
+            k = R.RefKernel(kind, len_band=band)
+            out[f"gram_k{kind}_b{band}"] = k.gram(ref)[0]
+    k = R.RefKernel(R.SU_STEM_STR)
+    labels = [r["label"] for r in recs]
+    gn, _, text = k.gram(ref, normalize=True, labels=labels, want_text=True)
+    out["gram_norm_k3_b10"] = gn
+    out["gram_norm_text_k3_b10"] = np.array(text)
+    test, train = ref[:5], ref[5:]
+    m, selfv, _ = k.cross(test, train, norm_test=True, normalize=False)
+    out["cross_k3"] = m; out["cross_self_k3"] = selfv
+    m, selfv, _ = k.cross(test, train, norm_test=True, normalize=True)
+    out["cross_norm_k3"] = m
+    sv = np.array([1, 4, 7], dtype=np.uint32)
+    row, s, _ = k.row(ref[2], train, sv_index=sv, init=-1.0)
+    out["row_sv_index"] = sv; out["row_sv_k3"] = row; out["row_sv_self_k3"] = np.array(s)
+    out["diag_k3"] = k.diag(train)[0]
+    out["diag_sv_k3"] = k.diag(train, sv_index=sv, init=-1.0)[0]
+    np.savez_compressed(os.path.join(OUT, "golden_pairs.npz"), **out)
+
+    md = {}
+    for i, d in enumerate(ref):
+        for key, v in d.dump().items():
+            md[f"r{i}_{key}"] = np.asarray(v)
+    np.savez_compressed(os.path.join(OUT, "golden_mdata.npz"), **md)
+
+    seqs = [r["rows"][0] for r in synth.make_config(2, 6)] + ["ACGUacgu", "gattaca"]
+    gaps = [np.float32(0.8), np.float32(1.0)]
+    nv = dict(seqs_json=np.array(json.dumps(seqs)), gaps=np.array(gaps, dtype=np.float32))
+    for gi, g in enumerate(gaps):
+        nv[f"gram_g{gi}"] = R.naive_gram(float(g), seqs)[0]
+    np.savez_compressed(os.path.join(OUT, "golden_naive.npz"), **nv)
+
+    recs1 = synth.make_config(1, 40)
+    ref1 = [R.RefMData.build(r["rows"], r["bp"], TH) for r in recs1]
+    K = R.RefKernel(R.SU_STEM_STR).gram(ref1, normalize=True)[0]
+    y = np.array([r["label"] for r in recs1], dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, "golden_svm.npz"), gram=K, y=y, cv_target=R.svm_cv(K, y, 1.0, 5, 1))
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()
