@@ -106,7 +106,11 @@ typedef struct stemk_set stemk_set;
 const char* stemk_version(void);
 int stemk_device_count(void);
 
-/* context: one CUDA device + one kernel object (immutable, like the reference's kernel classes) */
+/* context: one CUDA device + one kernel object (immutable, like the reference's kernel classes).
+ * device = STEMK_DEVICE_NONE makes a host-only context: stemk_upload compiles the records and stemk_set_stats /
+ * stemk_pair_cost (schedulers, work model) work, every entry point that computes a kernel value fails with
+ * STEMK_ERR_CUDA. */
+#define STEMK_DEVICE_NONE (-1)
 int stemk_create(stemk_ctx** ctx, const stemk_params* params, int device);
 void stemk_destroy(stemk_ctx* ctx);
 const char* stemk_last_error(const stemk_ctx* ctx); /* ctx may be NULL: last creation error */
@@ -115,6 +119,11 @@ const char* stemk_last_error(const stemk_ctx* ctx); /* ctx may be NULL: last cre
 int stemk_upload(stemk_ctx* ctx, const stemk_seqset_desc* desc, stemk_set** set);
 void stemk_set_free(stemk_ctx* ctx, stemk_set* set);
 uint32_t stemk_set_size(const stemk_set* set);
+/* Per-record sizes for cost models / schedulers: #V and #E of the DAG (leaves and leaf edges included, as the
+ * reference counts them) and the number of columns.  Any of the three output arrays [n] may be NULL. */
+void stemk_set_stats(const stemk_set* set, uint32_t* n_nodes, uint32_t* n_edges, uint32_t* length);
+/* Bytes of device memory the uploaded set occupies (= host->device bytes copied by stemk_upload). */
+uint64_t stemk_set_device_bytes(const stemk_set* set);
 
 /* KernelMatrix::calculate(train, kernel, normalize) -- kernel_matrix.cpp:485-575.
  * out: n*n row-major, both triangles.  normalize: K_ij /= sqrt(K_ii K_jj), K_ii = 1. */

@@ -32,7 +32,7 @@ def make_params(kind, loop_gap=0.2, beta=0.3, stack=1.3, covar=0.8, gap=0.8, alp
 
 
 EXPORTS = ["stemk_version", "stemk_device_count", "stemk_create", "stemk_destroy", "stemk_last_error", "stemk_upload",
-           "stemk_set_free", "stemk_set_size", "stemk_gram", "stemk_cross", "stemk_diag", "stemk_pairs",
+           "stemk_set_free", "stemk_set_size", "stemk_set_stats", "stemk_set_device_bytes", "stemk_gram", "stemk_cross", "stemk_diag", "stemk_pairs",
            "stemk_pairs_device", "stemk_assemble_device", "stemk_pair_cost", "stemk_stats_reset", "stemk_stats_get", "stemk_fp64_peak"]
 
 _lib = None
@@ -56,6 +56,9 @@ def lib():
         L.stemk_set_free.argtypes = [vp, vp]
         L.stemk_set_size.restype = u32
         L.stemk_set_size.argtypes = [vp]
+        L.stemk_set_stats.argtypes = [vp, vp, vp, vp]
+        L.stemk_set_device_bytes.restype = C.c_uint64
+        L.stemk_set_device_bytes.argtypes = [vp]
         L.stemk_gram.argtypes = [vp, vp, C.c_int, vp]
         L.stemk_cross.argtypes = [vp, vp, vp, vp, u32, C.c_int, vp, vp]
         L.stemk_diag.argtypes = [vp, vp, vp, u32, vp]

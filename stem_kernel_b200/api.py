@@ -126,6 +126,15 @@ class DeviceSet:
     def __len__(self):
         return self.n
 
+    def stats(self):
+        """Per-record (#V, #E, L) as the reference counts them (leaves and leaf edges included)."""
+        v, e, l = (np.zeros(self.n, dtype=np.uint32) for _ in range(3))
+        L.lib().stemk_set_stats(self.h, v.ctypes.data, e.ctypes.data, l.ctypes.data)
+        return v, e, l
+
+    def device_bytes(self):
+        return int(L.lib().stemk_set_device_bytes(self.h))
+
     def free(self):
         if self.h and self.ctx.h:
             L.lib().stemk_set_free(self.ctx.h, self.h)

@@ -41,6 +41,7 @@ struct RecOut {  // one record's share, appended to the CompiledSet in record or
   std::vector<uint8_t> bcode, bab, ccode, text;
   std::vector<float> prof;
   std::vector<uint32_t> deg_all;
+  std::vector<double> pd, pb;  // work-model prefix sums over node length
   uint32_t n_all = 0, e_all = 0, max_rows = 0;
   std::string err;
 };
@@ -191,6 +192,14 @@ void compile_record(const stemk_seqset_desc& s, uint32_t r, double g, RecOut* o)
   }
   if (simple_bpf) h.flags |= REC_SIMPLE_BPF;
   if (len_mono) h.flags |= REC_LEN_MONOTONE;
+  uint32_t max_len = 0;
+  for (uint32_t k = 0; k < N; ++k) max_len = std::max(max_len, o->len[k]);
+  o->pd.assign(max_len + 2, 0.0); o->pb.assign(max_len + 2, 0.0);
+  for (uint32_t k = 0; k < N; ++k) {
+    o->pd[o->len[k] + 1] += o->deg_all[k];
+    o->pb[o->len[k] + 1] += o->boff[k + 1] - o->boff[k];
+  }
+  for (uint32_t l = 1; l < max_len + 2; ++l) { o->pd[l] += o->pd[l - 1]; o->pb[l] += o->pb[l - 1]; }
 }
 
 template <class T>
@@ -232,6 +241,9 @@ std::string compile_set(const stemk_seqset_desc& s, double g, int n_threads, Com
     append(c.cidx, o.cidx); append(c.ce, o.ce); append(c.lev_off, o.lev_off); append(c.boff, o.boff);
     append(c.bab, o.bab); append(c.bfq, o.bfq); append(c.ccode, o.ccode); append(c.cw, o.cw);
     append(c.prof, o.prof); append(c.text, o.text); append(c.deg_all, o.deg_all);
+    if (o.pd.empty()) { o.pd.assign(1, 0.0); o.pb.assign(1, 0.0); }
+    c.cost_off.push_back(c.cost_pd.size());
+    append(c.cost_pd, o.pd); append(c.cost_pb, o.pb);
     c.rec[r] = h;
     c.n_nodes_all.push_back(o.n_all);
     c.n_edges_all.push_back(o.e_all);
@@ -242,6 +254,7 @@ std::string compile_set(const stemk_seqset_desc& s, double g, int n_threads, Com
     c.max_E = std::max(c.max_E, (uint32_t)o.cidx.size());
     c.max_nlev = std::max(c.max_nlev, h.nlev);
   }
+  c.cost_off.push_back(c.cost_pd.size());
   return "";
 }
 

@@ -97,6 +97,9 @@ int fail(stemk_ctx* c, int code, const std::string& msg) {
 int cuda_fail(stemk_ctx* c, cudaError_t e, const char* where) {
   return fail(c, STEMK_ERR_CUDA, std::string(where) + ": " + cudaGetErrorString(e));
 }
+int no_device(stemk_ctx* c) {
+  return fail(c, STEMK_ERR_CUDA, "host-only context: kernel values are computed on a CUDA device only (no CPU path)");
+}
 #define CU(call)                                                     \
   do {                                                               \
     cudaError_t e_ = (call);                                         \
@@ -140,6 +143,15 @@ int stemk_create(stemk_ctx** out, const stemk_params* params, int device) {
   if (!out || !params) return fail(nullptr, STEMK_ERR_ARG, "null argument");
   *out = nullptr;
   if (params->kind < STEMK_SI_STEM || params->kind > STEMK_STR_NAIVE) return fail(nullptr, STEMK_ERR_ARG, "unknown kernel kind");
+  if (device == STEMK_DEVICE_NONE) {
+    // host-only context: record compilation and the work model, nothing that computes a kernel value
+    stemk_ctx* c = new stemk_ctx;
+    c->device = STEMK_DEVICE_NONE;
+    c->params = *params;
+    make_tables(*params, &c->tables);
+    *out = c;
+    return STEMK_OK;
+  }
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess || n == 0) {
@@ -174,6 +186,7 @@ int stemk_create(stemk_ctx** out, const stemk_params* params, int device) {
 
 void stemk_destroy(stemk_ctx* c) {
   if (!c) return;
+  if (c->device == STEMK_DEVICE_NONE) { delete c; return; }
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (DevBuf* b : {&c->scratch, &c->carry, &c->tmp_stem, &c->tmp_str, &c->idx_x, &c->idx_y, &c->vals, &c->matrix}) b->release();
@@ -191,13 +204,14 @@ void stemk_destroy(stemk_ctx* c) {
 int stemk_upload(stemk_ctx* ctx, const stemk_seqset_desc* desc, stemk_set** out) {
   if (!ctx || !desc || !out) return fail(ctx, STEMK_ERR_ARG, "null argument");
   *out = nullptr;
-  CU(cudaSetDevice(ctx->device));
+  if (ctx->device != STEMK_DEVICE_NONE) CU(cudaSetDevice(ctx->device));
   stemk_set* s = new stemk_set;
   s->device = ctx->device;
   const int n_threads = (int)std::min<unsigned>(16, std::max(1u, std::thread::hardware_concurrency()));
   std::string err = compile_set(*desc, ctx->params.loop_gap, n_threads, &s->host);
   if (!err.empty()) { delete s; return fail(ctx, STEMK_ERR_ARG, err); }
   const CompiledSet& h = s->host;
+  if (ctx->device == STEMK_DEVICE_NONE) { *out = s; return STEMK_OK; }
   size_t off = 0;
   const size_t o_rec = place(off, h.rec), o_a = place(off, h.a), o_el = place(off, h.el), o_ql = place(off, h.ql),
                o_paths = place(off, h.paths), o_gapt = place(off, h.gapt), o_bfreq = place(off, h.bfreq),
@@ -233,17 +247,29 @@ int stemk_upload(stemk_ctx* ctx, const stemk_seqset_desc* desc, stemk_set** out)
 
 void stemk_set_free(stemk_ctx* ctx, stemk_set* s) {
   if (!s) return;
-  if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+  if (ctx && ctx->device != STEMK_DEVICE_NONE) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
   s->blob.release();
   delete s;
 }
 
 uint32_t stemk_set_size(const stemk_set* s) { return s ? (uint32_t)s->host.rec.size() : 0; }
 
+void stemk_set_stats(const stemk_set* s, uint32_t* n_nodes, uint32_t* n_edges, uint32_t* length) {
+  if (!s) return;
+  for (size_t i = 0; i < s->host.rec.size(); ++i) {
+    if (n_nodes) n_nodes[i] = s->host.n_nodes_all[i];
+    if (n_edges) n_edges[i] = s->host.n_edges_all[i];
+    if (length) length[i] = s->host.rec[i].L;
+  }
+}
+
+uint64_t stemk_set_device_bytes(const stemk_set* s) { return s ? (uint64_t)s->blob.bytes : 0; }
+
 // -------------------------------------------------------------------------- pair evaluator
 int stemk_pairs_device(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, size_t n_pairs, const uint32_t* d_xi,
                        const uint32_t* d_yi, double* d_out, void* stream_) {
   if (!ctx || !x || !y) return fail(ctx, STEMK_ERR_ARG, "null argument");
+  if (ctx->device == STEMK_DEVICE_NONE) return no_device(ctx);
   if (n_pairs == 0) return STEMK_OK;
   if (!d_xi || !d_yi || !d_out) return fail(ctx, STEMK_ERR_ARG, "null buffer");
   CU(cudaSetDevice(ctx->device));
@@ -310,6 +336,7 @@ int stemk_pairs_device(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, s
 int stemk_pairs(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, size_t n_pairs, const uint32_t* xi,
                 const uint32_t* yi, double* out) {
   if (!ctx || !x || !y) return fail(ctx, STEMK_ERR_ARG, "null argument");
+  if (ctx->device == STEMK_DEVICE_NONE) return no_device(ctx);
   if (n_pairs == 0) return STEMK_OK;
   if (!xi || !yi || !out) return fail(ctx, STEMK_ERR_ARG, "null buffer");
   for (size_t k = 0; k < n_pairs; ++k)
@@ -340,6 +367,7 @@ static inline double sched_cost(const stemk_ctx* ctx, const CompiledSet& a, uint
 int stemk_gram(stemk_ctx* ctx, const stemk_set* train, int normalize, double* out) {
   if (!ctx || !train || !out) return fail(ctx, STEMK_ERR_ARG, "null argument");
   const uint32_t n = (uint32_t)train->host.rec.size();
+  if (ctx->device == STEMK_DEVICE_NONE) return no_device(ctx);
   if (n == 0) return STEMK_OK;
   CU(cudaSetDevice(ctx->device));
   // records sorted by size, big first: the queue then hands out the expensive pairs first
@@ -378,6 +406,7 @@ int stemk_gram(stemk_ctx* ctx, const stemk_set* train, int normalize, double* ou
 int stemk_assemble_device(stemk_ctx* ctx, size_t n_pairs, const uint32_t* d_xi, const uint32_t* d_yi,
                           const double* d_vals, uint32_t n, int normalize, double* d_matrix, void* stream_) {
   if (!ctx) return fail(ctx, STEMK_ERR_ARG, "null argument");
+  if (ctx->device == STEMK_DEVICE_NONE) return no_device(ctx);
   if (n == 0) return STEMK_OK;
   if (!d_matrix || (n_pairs && (!d_xi || !d_yi || !d_vals))) return fail(ctx, STEMK_ERR_ARG, "null buffer");
   CU(cudaSetDevice(ctx->device));
@@ -461,27 +490,28 @@ int stemk_pair_cost(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, size
   const bool has_stem = kind_has_stem(kind), has_str = kind_has_string(kind) && kind != STEMK_STR_NAIVE;
   const CompiledSet& A = x->host;
   const CompiledSet& B = y->host;
-  for (size_t k = 0; k < n_pairs; ++k) {
+  for (size_t k = 0; k < n_pairs; ++k)
+    if (xi[k] >= A.rec.size() || yi[k] >= B.rec.size()) return fail(ctx, STEMK_ERR_ARG, "pair index out of range");
+  const uint32_t band = ctx->params.len_band;
+  auto one = [&](size_t k) {
     const uint32_t i = xi[k], j = yi[k];
-    if (i >= A.rec.size() || j >= B.rec.size()) return fail(ctx, STEMK_ERR_ARG, "pair index out of range");
     const RecDev& rx = A.rec[i];
     const RecDev& ry = B.rec[j];
     double c = 0, f = 0;
     if (has_stem) {
-      // U_match / U_bf over in-band non-leaf node pairs, with the reference's full degrees (leaf edges included)
+      // U_match / U_bf over in-band non-leaf node pairs, with the reference's full degrees (leaf edges included):
+      // per x node, the y nodes with |len - len_x| <= band come from y's prefix sums over node length
       double um = 0, ub = 0;
+      const double* pd = B.cost_pd.data() + B.cost_off[j];
+      const double* pb = B.cost_pb.data() + B.cost_off[j];
+      const uint32_t ny_len = (uint32_t)(B.cost_off[j + 1] - B.cost_off[j]) - 1;  // prefix arrays cover len < ny_len
       for (uint32_t a = 0; a < rx.N; ++a) {
-        const double dx = A.deg_all[rx.node0 + a];
-        const double bx = A.boff[rx.boff0 + a + 1] - A.boff[rx.boff0 + a];
         const uint32_t la = A.len[rx.node0 + a];
-        for (uint32_t b = 0; b < ry.N; ++b) {
-          const uint32_t lb = B.len[ry.node0 + b];
-          const uint32_t dl = la > lb ? la - lb : lb - la;
-          if (ctx->params.len_band != 0 && dl > ctx->params.len_band) continue;
-          const double dy = B.deg_all[ry.node0 + b];
-          um += dx * dy;
-          ub += bx * (double)(B.boff[ry.boff0 + b + 1] - B.boff[ry.boff0 + b]);
-        }
+        uint32_t lo = 0, hi = ny_len;  // [lo, hi) in node length
+        if (band != 0) { lo = la > band ? la - band : 0; hi = std::min<uint64_t>(ny_len, (uint64_t)la + band + 1); }
+        if (lo >= hi) continue;
+        um += (double)A.deg_all[rx.node0 + a] * (pd[hi] - pd[lo]);
+        ub += (double)(A.boff[rx.boff0 + a + 1] - A.boff[rx.boff0 + a]) * (pb[hi] - pb[lo]);
       }
       c += (double)A.n_nodes_all[i] * B.n_nodes_all[j];
       f += 2 * um + 3 * ub + 3 * ((double)A.n_nodes_all[i] * B.n_edges_all[j] + (double)A.n_edges_all[i] * B.n_nodes_all[j]);
@@ -503,14 +533,21 @@ int stemk_pair_cost(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, size
     }
     if (cells) cells[k] = c;
     if (flops) flops[k] = f;
+  };
+  const unsigned nt = n_pairs < 4096 ? 1u : std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
+  if (nt <= 1) { for (size_t k = 0; k < n_pairs; ++k) one(k); }
+  else {
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t) th.emplace_back([&, t]() { for (size_t k = t; k < n_pairs; k += nt) one(k); });
+    for (auto& w : th) w.join();
   }
   return STEMK_OK;
 }
 
-void stemk_stats_reset(stemk_ctx* ctx) { if (ctx) { timed_resolve(ctx); ctx->launches = 0; ctx->stem_ms = ctx->string_ms = 0; } }
+void stemk_stats_reset(stemk_ctx* ctx) { if (ctx) { if (ctx->device != STEMK_DEVICE_NONE) timed_resolve(ctx); ctx->launches = 0; ctx->stem_ms = ctx->string_ms = 0; } }
 void stemk_stats_get(stemk_ctx* ctx, uint64_t* launches, double* stem_ms, double* string_ms) {
   if (!ctx) return;
-  timed_resolve(ctx);
+  if (ctx->device != STEMK_DEVICE_NONE) timed_resolve(ctx);
   if (launches) *launches = ctx->launches;
   if (stem_ms) *stem_ms = ctx->stem_ms;
   if (string_ms) *string_ms = ctx->string_ms;
@@ -518,6 +555,7 @@ void stemk_stats_get(stemk_ctx* ctx, uint64_t* launches, double* stem_ms, double
 
 int stemk_fp64_peak(stemk_ctx* ctx, double seconds, double* tflops) {
   if (!ctx || !tflops) return fail(ctx, STEMK_ERR_ARG, "null argument");
+  if (ctx->device == STEMK_DEVICE_NONE) return no_device(ctx);
   CU(cudaSetDevice(ctx->device));
   double* sink = nullptr;
   CU(cudaMalloc((void**)&sink, sizeof(double)));

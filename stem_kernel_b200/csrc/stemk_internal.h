@@ -74,6 +74,10 @@ struct CompiledSet {
   std::vector<uint32_t> n_edges_all;  // edges incl. leaf edges (reference's #E)
   std::vector<uint32_t> max_level_rows;
   std::vector<uint32_t> deg_all;      // per non-leaf node (level order): out-degree incl. leaf edges
+  // work model: per record, prefix sums over node length of the out-degrees and of the base-pair-profile sizes
+  // (cost_pd[cost_off[r] + k] = sum of deg over the record's non-leaf nodes with len < k), cost_off has n+1 entries
+  std::vector<uint64_t> cost_off;
+  std::vector<double> cost_pd, cost_pb;
   bool has_dag = false;
   uint32_t max_N = 0, max_L = 0, max_E = 0, max_nlev = 0;  // non-leaf nodes / columns / non-leaf edges / levels
 };

@@ -1,0 +1,163 @@
+"""Gram matrices over several GPUs of one box: one process per GPU, the pair list dealt out by cost, one gather.
+
+Replaces the reference's MPI path (common/kernel_matrix.cpp:186-262 CalcTrainMatrix with `cnt % size == rank`,
+:495-526 Ssend/Recv of each rank's values to rank 0, :560-571 normalisation on the gathered matrix):
+
+  * every rank holds the whole flattened record set in its own HBM (<= 2 GB for 10k records);
+  * the n(n+1)/2 pairs (or n_test*n_train for the rectangular matrix) are put into ONE global order -- records
+    sorted by a size key, biggest first, pairs nested (p, q>=p) -- and rank r owns pairs r, r+W, r+2W, ...
+    Neighbouring pairs of that order cost nearly the same (same x record, y records adjacent in size), so the
+    strided deal is balanced to well under a percent of the stem work model and every rank still runs its own
+    expensive pairs first, which is what keeps the tail of its device-side work queue short;
+  * the data path has exactly one exchange: a gather of ceil(P/W) doubles per rank to rank 0 (NCCL over NVLink
+    on the GPUs, gloo in the CPU tests).  Rank 0 un-deals (a transpose), scatters into the n x n matrix with the
+    mirror, and normalises -- all on its device through the C ABI (stemk_assemble_device).
+
+The arithmetic is injected (`compute`, `assemble`): GpuBackend binds them to the C ABI; the CPU tests bind them to
+the oracle so that the dealing / gather / un-deal logic is exercised with world_size 2 over gloo.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+# ----------------------------------------------------------------------------------------------- pair orders
+def size_order(keys):
+    """Record indices, biggest key first (stable), as the single-GPU driver orders them (stemk_api.cu)."""
+    keys = np.asarray(keys, dtype=np.float64)
+    return np.argsort(-keys, kind="stable").astype(np.uint32)
+
+
+def square_pairs(keys):
+    """All pairs i<=j of a square Gram matrix in the global work order.  The reference evaluates
+    kernel_(x_i, x_j) with i <= j (kernel_matrix.cpp:47-50), so x = min index, y = max index."""
+    perm = size_order(keys)
+    n = len(perm)
+    p, q = np.triu_indices(n)
+    a, b = perm[p], perm[q]
+    return np.minimum(a, b).astype(np.uint32), np.maximum(a, b).astype(np.uint32)
+
+
+def cross_pairs(test_keys, train_keys, cols=None):
+    """Pairs of the rectangular matrix: x = train record (FIRST argument, kernel_matrix.cpp:159,168), y = test."""
+    cols = np.arange(len(train_keys), dtype=np.uint32) if cols is None else np.asarray(cols, dtype=np.uint32)
+    tperm = size_order(test_keys)
+    cperm = cols[size_order(np.asarray(train_keys)[cols])]
+    yi = np.repeat(tperm, len(cperm)).astype(np.uint32)
+    xi = np.tile(cperm, len(tperm)).astype(np.uint32)
+    return xi, yi
+
+
+def deal(n_pairs, rank, world):
+    """Global positions owned by `rank`: r, r+W, ...  Every rank gets ceil or floor of P/W pairs."""
+    return np.arange(rank, n_pairs, world, dtype=np.int64)
+
+
+def slab(n_pairs, world):
+    """Length of the per-rank gather buffer (ranks with one pair fewer pad with a zero)."""
+    return (n_pairs + world - 1) // world
+
+
+def undeal(gathered, n_pairs):
+    """[W, slab] gathered values -> values in global pair order (position k = t*W + r sits at [r, t])."""
+    return gathered.t().reshape(-1)[:n_pairs].contiguous()
+
+
+def stem_cost_proxy(v, e, length, xi, yi, stem=True, string=False):
+    """Work model used for balance reports: U_skip = Vx*Ey + Ex*Vy and Lx*Ly string cells."""
+    v, e, length = (np.asarray(a, dtype=np.float64) for a in (v, e, length))
+    c = np.zeros(len(xi))
+    if stem:
+        c += v[xi] * e[yi] + e[xi] * v[yi]
+    if string:
+        c += length[xi] * length[yi]
+    return c
+
+
+def imbalance(cost, world):
+    """max over ranks of the dealt cost / mean; 1.0 is perfect."""
+    per = np.array([cost[r::world].sum() for r in range(world)])
+    return float(per.max() / per.mean()) if per.mean() > 0 else 1.0
+
+
+# ----------------------------------------------------------------------------------------------- driver
+class ShardedGram:
+    """Square Gram matrix of one record set over `world` ranks.
+
+    compute(xi, yi) -> 1-D float64 tensor (this rank's values, on `device`)
+    assemble(xi_all, yi_all, vals_all, n, normalize) -> n x n tensor (rank 0 only)
+    xi/yi are torch uint32-as-int32 tensors on `device` holding record indices.
+    """
+
+    def __init__(self, keys, rank, world, device, compute, assemble, group=None):
+        self.rank, self.world, self.device, self.group = rank, world, device, group
+        self.compute, self.assemble = compute, assemble
+        self.n = len(keys)
+        xi, yi = square_pairs(keys)
+        self.n_pairs = len(xi)
+        mine = deal(self.n_pairs, rank, world)
+        self.n_mine = len(mine)
+        as_dev = lambda a: torch.from_numpy(a.view(np.int32).copy()).to(device)
+        self.xi_mine, self.yi_mine = as_dev(xi[mine]), as_dev(yi[mine])
+        self.slab = slab(self.n_pairs, world)
+        self.send = torch.zeros(self.slab, dtype=torch.float64, device=device)
+        if rank == 0:
+            self.xi_all, self.yi_all = as_dev(xi), as_dev(yi)
+            self.recv = torch.zeros((world, self.slab), dtype=torch.float64, device=device)
+        self.xi_host, self.yi_host = xi, yi
+
+    def run(self, normalize=False):
+        """One Gram matrix.  Returns the n x n tensor on rank 0, None elsewhere."""
+        vals = self.compute(self.xi_mine, self.yi_mine)
+        self.send[: self.n_mine].copy_(vals)
+        if self.world > 1:
+            if self.rank == 0:
+                dist.gather(self.send, list(self.recv.unbind(0)), dst=0, group=self.group)
+            else:
+                dist.gather(self.send, None, dst=0, group=self.group)
+        else:
+            self.recv[0].copy_(self.send)
+        if self.rank != 0:
+            return None
+        return self.assemble(self.xi_all, self.yi_all, undeal(self.recv, self.n_pairs), self.n, normalize)
+
+
+class GpuBackend:
+    """compute / assemble bound to the C ABI on this rank's GPU, asynchronous on torch's current stream.
+    Run ShardedGram.run() under `with torch.cuda.stream(backend.stream)`: the library treats a NULL stream as
+    "my own stream", which is not ordered against torch's legacy default stream."""
+
+    def __init__(self, ctx, dset, device):
+        self.ctx, self.dset, self.device = ctx, dset, device
+        self.matrix = None
+        self.stream = torch.cuda.Stream(device)
+
+    def _stream(self):
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        if not s:
+            raise RuntimeError("run under a non-default torch stream (GpuBackend.stream)")
+        return s
+
+    def compute(self, xi, yi):
+        out = torch.empty(xi.numel(), dtype=torch.float64, device=self.device)
+        self.ctx.pairs_device(self.dset, self.dset, xi.numel(), xi.data_ptr(), yi.data_ptr(), out.data_ptr(),
+                              self._stream())
+        return out
+
+    def assemble(self, xi, yi, vals, n, normalize):
+        if self.matrix is None or self.matrix.shape[0] != n:
+            self.matrix = torch.empty((n, n), dtype=torch.float64, device=self.device)
+        self.ctx.assemble_device(xi.numel(), xi.data_ptr(), yi.data_ptr(), vals.data_ptr(), n, normalize,
+                                 self.matrix.data_ptr(), self._stream())
+        return self.matrix
+
+
+def record_keys(dset, stem=True, string=False):
+    """Per-record size key of the work order (cost of the record against itself)."""
+    v, e, length = dset.stats()
+    k = np.zeros(len(v))
+    if stem:
+        k += 2.0 * v.astype(np.float64) * e
+    if string:
+        k += length.astype(np.float64) ** 2
+    return k

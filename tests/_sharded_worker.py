@@ -1,0 +1,56 @@
+"""One rank of the world_size-2 gloo test of stem_kernel_b200/sharded.py (launched by test_sharded.py).
+The arithmetic is the oracle (allowed: this is a test); what is under test is dealing, gather and un-deal."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from conftest import TH, load_golden_records  # noqa: E402
+from oracle import oraclebind as O  # noqa: E402
+from stem_kernel_b200 import _lib as L  # noqa: E402
+from stem_kernel_b200 import hostlib, sharded  # noqa: E402
+
+
+def main():
+    rank, world, port, out = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3], sys.argv[4]
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    recs, _ = load_golden_records()
+    md = [hostlib.MData.from_record(r, TH) for r in recs]
+    flat = hostlib.SeqSet(md)
+    desc = flat.desc()
+    p = O.Params.from_buffer_copy(L.make_params(L.SU_STEM_STR))
+    sizes = [m.sizes() for m in md]
+    keys = [2.0 * s["n_nodes"] * s["n_edges"] + s["length"] ** 2 for s in sizes]
+
+    def compute(xi, yi):
+        return torch.from_numpy(O.pairs(p, desc, desc, xi.numpy().view(np.uint32), yi.numpy().view(np.uint32)))
+
+    def assemble(xi, yi, vals, n, normalize):
+        m = np.zeros((n, n))
+        a, b = xi.numpy().view(np.uint32), yi.numpy().view(np.uint32)
+        m[a, b] = vals.numpy()
+        m[b, a] = vals.numpy()
+        if normalize:
+            d = np.diag(m).copy()
+            with np.errstate(divide="ignore", invalid="ignore"):
+                m = m / np.sqrt(np.outer(d, d))
+            np.fill_diagonal(m, 1.0)
+        return torch.from_numpy(m)
+
+    sg = sharded.ShardedGram(keys, rank, world, torch.device("cpu"), compute, assemble)
+    res = sg.run(normalize=True)
+    assert (res is None) == (rank != 0)
+    if rank == 0:
+        np.save(out, res.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
