@@ -222,7 +222,7 @@ def test_config2_full_size_string_kernel_properties():
 
 def test_config3_stem_kernel_properties_and_sampled_parity():
     """C3 records (150-300 nt): 400 of them -> 80 200 pairs; sampled entries against the oracle; composition
-    is exactly additive (AddKernel, conv_kernel.h:49-52); the record order does not change any entry."""
+    is exactly additive (AddKernel, conv_kernel.h:49-52); behaviour under a permutation of the records."""
     recs = synth.make_config(3, 400)
     md = hostlib.build_many(recs, TH)
     flat = hostlib.SeqSet(md)
@@ -237,11 +237,18 @@ def test_config3_stem_kernel_properties_and_sampled_parity():
     xi, yi = rng.integers(0, 400, 120), rng.integers(0, 400, 120)
     lo, hi = np.minimum(xi, yi), np.maximum(xi, yi)
     assert relerr(gs[lo, hi], O.pairs(oparams(ps), flat.desc(), flat.desc(), lo, hi)) < TOL
+    # The stem kernel is NOT symmetric in its arguments (a leaf row of the reference's tables is 0, a leaf column
+    # is not: stem_kernel.cpp:39-42,62-77), and KernelMatrix evaluates kernel_(x_i, x_j) with i <= j
+    # (kernel_matrix.cpp:47-50).  Under a permutation of the records, entries whose argument order is preserved
+    # must not change at all; entries whose order flips must equal the oracle with the arguments flipped.
     perm = rng.permutation(400)
     gp = cs.gram(cs.upload([md[i] for i in perm]))
-    # the reference evaluates k(x_i, x_j) for i <= j: a permutation can swap the argument roles, which changes
-    # the summation order only
-    assert relerr(gp, gs[np.ix_(perm, perm)]) < 1e-12
+    a, b = np.triu_indices(400)
+    kept = perm[a] <= perm[b]
+    assert np.array_equal(gp[a[kept], b[kept]], gs[perm[a[kept]], perm[b[kept]]])
+    fl = np.nonzero(~kept)[0][:: max(1, (~kept).sum() // 60)]
+    want = O.pairs(oparams(ps), flat.desc(), flat.desc(), perm[a[fl]], perm[b[fl]])
+    assert relerr(gp[a[fl], b[fl]], want) < TOL
 
 
 @pytest.mark.skipif(not os.path.exists(os.path.join(R.REF_DIR, "libstemk_ref_svm.so")), reason="oracle/_ref not shipped")
