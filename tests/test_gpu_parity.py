@@ -240,12 +240,13 @@ def test_config3_stem_kernel_properties_and_sampled_parity():
     # The stem kernel is NOT symmetric in its arguments (a leaf row of the reference's tables is 0, a leaf column
     # is not: stem_kernel.cpp:39-42,62-77), and KernelMatrix evaluates kernel_(x_i, x_j) with i <= j
     # (kernel_matrix.cpp:47-50).  Under a permutation of the records, entries whose argument order is preserved
-    # must not change at all; entries whose order flips must equal the oracle with the arguments flipped.
+    # must not change (beyond the last bits: warps pick up rows dynamically, so the final sum's order may
+    # differ between launches); entries whose order flips must equal the oracle with the arguments flipped.
     perm = rng.permutation(400)
     gp = cs.gram(cs.upload([md[i] for i in perm]))
     a, b = np.triu_indices(400)
     kept = perm[a] <= perm[b]
-    assert np.array_equal(gp[a[kept], b[kept]], gs[perm[a[kept]], perm[b[kept]]])
+    assert relerr(gp[a[kept], b[kept]], gs[perm[a[kept]], perm[b[kept]]]) < 1e-13
     fl = np.nonzero(~kept)[0][:: max(1, (~kept).sum() // 60)]
     want = O.pairs(oparams(ps), flat.desc(), flat.desc(), perm[a[fl]], perm[b[fl]])
     assert relerr(gp[a[fl], b[fl]], want) < TOL
