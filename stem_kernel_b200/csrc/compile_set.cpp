@@ -41,6 +41,10 @@ struct RecOut {  // one record's share, appended to the CompiledSet in record or
   std::vector<uint8_t> bcode, bab, ccode, text;
   std::vector<float> prof;
   std::vector<uint32_t> deg_all;
+  std::vector<double> up, dn, s2;
+  std::vector<NodeI> nodei;
+  std::vector<uint16_t> c16;
+  std::vector<uint32_t> blk;
   std::vector<double> pd, pb;  // work-model prefix sums over node length
   uint32_t n_all = 0, e_all = 0, max_rows = 0;
   std::string err;
@@ -194,6 +198,55 @@ void compile_record(const stemk_seqset_desc& s, uint32_t r, double g, RecOut* o)
   if (len_mono) h.flags |= REC_LEN_MONOTONE;
   uint32_t max_len = 0;
   for (uint32_t k = 0; k < N; ++k) max_len = std::max(max_len, o->len[k]);
+
+  // ---- separable fast path.  A stem edge has gaps = len_p - len_c - 2 (dag.h:25-26), so
+  // e(p,c) = g^gaps = g^(len_p-2-B) * g^(B-len_c) for any reference B: rows can be stored pre-scaled by
+  // up = g^(B-len) and a parent just ADDS its children and multiplies once by s2 = g^(len-2-B).  B = half the
+  // longest pair keeps every factor within g^(+-max_len/2).  Eligible records: every non-leaf edge has weight 1
+  // and exactly that gap count, single-entry base-pair profiles, no gap columns under a node, and powers that
+  // stay far from the fp64 range limits.  Everything else runs on the general kernel.
+  {
+    const uint32_t B = max_len / 2;
+    const uint32_t span = std::max(B, max_len - B) + 2;
+    bool fast = simple_bpf && len_mono && N > 0 && N <= kFastMaxN && max_len < 65535u;
+    for (uint32_t k = 0; k < N && fast; ++k) if (o->gapt[k] != 0.0) fast = false;
+    for (uint32_t k = 0; k < N && fast; ++k) {
+      const uint32_t u = order[k];
+      for (uint32_t e = eoff[u]; e < eoff[u + 1]; ++e) {
+        const uint32_t c = s.edge_to[e];
+        if (leaf[c]) continue;
+        const uint32_t lp = last[u] - first[u], lc = last[c] - first[c];
+        if (s.edge_weight[e] != 1.0f || lc + 2 > lp || s.edge_gaps[e] != lp - lc - 2) { fast = false; break; }
+      }
+    }
+    std::vector<double> pos(span + 1), neg(span + 1);
+    pos[0] = neg[0] = 1.0;
+    const double ginv = 1.0 / g;
+    for (uint32_t k = 1; k <= span; ++k) { pos[k] = pos[k - 1] * g; neg[k] = neg[k - 1] * ginv; }
+    auto in_range = [](double v) { return std::isfinite(v) && std::fabs(v) > 1e-140 && std::fabs(v) < 1e140; };
+    if (!in_range(pos[span]) || !in_range(neg[span])) fast = false;
+    auto pw = [&](long k) { return k >= 0 ? pos[(size_t)k] : neg[(size_t)(-k)]; };
+    o->up.resize(N); o->dn.resize(N); o->s2.resize(N); o->nodei.resize(N);
+    for (uint32_t k = 0; k < N; ++k) {
+      const long l = (long)o->len[k];
+      o->up[k] = fast ? pw((long)B - l) : 0.0;
+      o->dn[k] = fast ? pw(l - (long)B) : 0.0;
+      o->s2[k] = fast ? pw(l - 2 - (long)B) : 0.0;
+      NodeI ni;
+      ni.e4_bcode = ((uint32_t)o->c16.size() << 8) | o->bcode[k];
+      const uint32_t c0 = o->coff[k], c1 = o->coff[k + 1];
+      for (uint32_t e = c0; e < c1; ++e) o->c16.push_back((uint16_t)o->cidx[e]);
+      while (o->c16.size() % 4) o->c16.push_back((uint16_t)N);   // dummy column: reads 0.0
+      ni.deg4 = (uint16_t)((o->c16.size() - (ni.e4_bcode >> 8)) / 4);
+      ni.len = (uint16_t)o->len[k];
+      o->nodei[k] = ni;
+      if ((o->c16.size() >> 24) != 0) fast = false;
+    }
+    for (uint32_t l = 0; l < nlev; ++l)
+      for (uint32_t r = o->lev_off[l]; r < o->lev_off[l + 1]; r += kFastRows)
+        o->blk.push_back(r | (std::min(kFastRows, o->lev_off[l + 1] - r) << 16));
+    if (fast) h.flags |= REC_FAST;
+  }
   o->pd.assign(max_len + 2, 0.0); o->pb.assign(max_len + 2, 0.0);
   for (uint32_t k = 0; k < N; ++k) {
     o->pd[o->len[k] + 1] += o->deg_all[k];
@@ -232,6 +285,13 @@ std::string compile_set(const stemk_seqset_desc& s, double g, int n_threads, Com
     h.lev0 = (uint32_t)c.lev_off.size();
     h.boff0 = (uint32_t)c.boff.size();
     h.col0 = (uint32_t)c.ccode.size();
+    h.c16_0 = (uint32_t)c.c16.size(); h.e4 = (uint32_t)o.c16.size();
+    h.blk0 = (uint32_t)c.blk.size(); h.nblk = (uint32_t)o.blk.size();
+    append(c.up, o.up); append(c.dn, o.dn); append(c.s2, o.s2); append(c.nodei, o.nodei);
+    append(c.c16, o.c16); append(c.blk, o.blk);
+    if (h.flags & REC_FAST) {
+      c.max_E4 = std::max(c.max_E4, h.e4); c.max_fastN = std::max(c.max_fastN, h.N); ++c.n_fast;
+    }
     // child / profile offsets become absolute so the kernels index cidx/ce/bab/bfq directly
     const uint32_t e0 = (uint32_t)c.cidx.size(), b0 = (uint32_t)c.bab.size();
     for (auto& v : o.coff) v += e0;

@@ -22,6 +22,41 @@ struct StemLaunch {
   uint32_t ny_cap;              // largest Ny / Ey / level count over the y set (shared-memory carve-up)
   uint32_t ey_cap;
   uint32_t lev_cap;
+  const uint32_t* order;                 // optional: pair numbers to run (bucket 0 of the classifier); NULL = 0..n_pairs-1
+  const unsigned long long* n_items_dev; // with `order`: how many of them (device memory)
+};
+
+constexpr int kMaxFastBuckets = 8;
+
+// fast (separable) stem kernel: runs the pairs order[start[bucket] .. + count[bucket])
+struct StemFastLaunch {
+  SetView X, Y;
+  const uint32_t* xi;
+  const uint32_t* yi;
+  double* out;
+  const uint32_t* order;
+  const unsigned long long* start;   // [n_buckets] device
+  const unsigned long long* count;   // [n_buckets] device
+  unsigned long long* counter;       // this bucket's work-queue head (zeroed by the classifier)
+  int bucket;
+  double* scratch;                   // per-CTA slab of pre-scaled G0 rows
+  unsigned long long scratch_stride; // doubles per CTA
+  const double* pair_tab;
+  uint32_t len_band, nx_cap, ny_cap, e4_cap, lev_cap;
+};
+
+struct StemClassify {
+  SetView X, Y;
+  const uint32_t* xi;
+  const uint32_t* yi;
+  unsigned long long n_pairs;
+  double* out;                       // trivial pairs (an empty DAG on either side) are finished by the classifier
+  unsigned long long* count;         // [n_buckets]
+  unsigned long long* start;         // [n_buckets]
+  uint32_t* order;                   // [n_pairs]
+  uint32_t caps[kMaxFastBuckets];    // staged-record size limit of fast bucket b (bucket number 1+b)
+  int n_caps;
+  int allow_fast;
 };
 
 struct StringLaunch {
@@ -43,6 +78,10 @@ size_t stem_smem_bytes(uint32_t nslots, uint32_t nx_cap, uint32_t ny_cap, uint32
 int stem_warps_per_cta();
 cudaError_t launch_stem(const StemLaunch& p, int grid, size_t smem, cudaStream_t stream);
 int stem_max_ctas_per_sm(size_t smem);
+size_t stem_fast_smem_bytes(uint32_t nwarps, uint32_t nx_cap, uint32_t ny_cap, uint32_t e4_cap, uint32_t lev_cap);
+int stem_fast_ctas_per_sm(int nwarps, size_t smem);
+cudaError_t launch_stem_fast(const StemFastLaunch& p, int grid, int nwarps, size_t smem, cudaStream_t stream);
+cudaError_t launch_classify(const StemClassify& c, int n_buckets, unsigned long long* counters, cudaStream_t stream);
 cudaError_t launch_string(const StringLaunch& p, int cw, int grid, cudaStream_t stream);
 int string_warps_per_cta();
 cudaError_t launch_combine(int kind, double alpha, double beta, const double* stem, const double* str, double* out,

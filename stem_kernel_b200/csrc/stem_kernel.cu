@@ -113,6 +113,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_pairs_kernel(const StemL
 
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const uint32_t band = P.len_band;
+  const unsigned long long n_items = P.order ? *P.n_items_dev : P.n_pairs;
   for (uint32_t t = tid; t < 256; t += kStemThreads) SM(double, L.tab + 8 * t) = P.pair_tab[t];
   double* __restrict__ G0 = P.scratch + (size_t)blockIdx.x * P.scratch_stride;
   const SetView& X = P.X;
@@ -124,8 +125,8 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_pairs_kernel(const StemL
     __syncthreads();  // previous pair fully retired (also orders the tab fill on the first trip)
     if (tid == 0) { s_pair = atomicAdd(P.counter, 1ull); s_next_row = 0; }
     __syncthreads();
-    const unsigned long long k = s_pair;
-    if (k >= P.n_pairs) break;
+    if (s_pair >= n_items) break;
+    const unsigned long long k = P.order ? (unsigned long long)P.order[s_pair] : s_pair;
     const RecDev rx = X.rec[P.xi[k]];
     const RecDev ry = Y.rec[P.yi[k]];
     const uint32_t Nx = rx.N, Ny = ry.N;

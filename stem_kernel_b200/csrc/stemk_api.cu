@@ -7,6 +7,7 @@
 // returns STEMK_ERR_CUDA.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -54,7 +55,9 @@ struct stemk_ctx {
   double* d_pair_tab = nullptr;
   double* d_subst = nullptr;
   unsigned long long* d_counter = nullptr;
-  DevBuf scratch, carry, tmp_stem, tmp_str, idx_x, idx_y, vals, matrix;
+  DevBuf scratch, carry, tmp_stem, tmp_str, idx_x, idx_y, vals, matrix, order;
+  unsigned long long* d_bucket = nullptr;  // count[16] | start[16] | queue heads[16]
+  int use_fast = 1;                        // STEMK_FAST=0 in the environment forces the general stem kernel
   std::string err;
   // stats
   uint64_t launches = 0;
@@ -168,10 +171,12 @@ int stemk_create(stemk_ctx** out, const stemk_params* params, int device) {
   c->smem_optin = prop.sharedMemPerBlockOptin;
   c->params = *params;
   make_tables(*params, &c->tables);
+  if (const char* f = std::getenv("STEMK_FAST")) c->use_fast = std::atoi(f);
   bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaMalloc((void**)&c->d_pair_tab, sizeof(double) * 256) == cudaSuccess &&
             cudaMalloc((void**)&c->d_subst, sizeof(double) * 16) == cudaSuccess &&
             cudaMalloc((void**)&c->d_counter, sizeof(unsigned long long)) == cudaSuccess &&
+            cudaMalloc((void**)&c->d_bucket, sizeof(unsigned long long) * 48) == cudaSuccess &&
             cudaMemcpy(c->d_pair_tab, c->tables.pair_tab, sizeof(double) * 256, cudaMemcpyHostToDevice) == cudaSuccess &&
             cudaMemcpy(c->d_subst, c->tables.subst, sizeof(double) * 16, cudaMemcpyHostToDevice) == cudaSuccess &&
             cudaEventCreate(&c->ev0) == cudaSuccess && cudaEventCreate(&c->ev1) == cudaSuccess;
@@ -189,10 +194,11 @@ void stemk_destroy(stemk_ctx* c) {
   if (c->device == STEMK_DEVICE_NONE) { delete c; return; }
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  for (DevBuf* b : {&c->scratch, &c->carry, &c->tmp_stem, &c->tmp_str, &c->idx_x, &c->idx_y, &c->vals, &c->matrix}) b->release();
+  for (DevBuf* b : {&c->scratch, &c->carry, &c->tmp_stem, &c->tmp_str, &c->idx_x, &c->idx_y, &c->vals, &c->matrix, &c->order}) b->release();
   if (c->d_pair_tab) cudaFree(c->d_pair_tab);
   if (c->d_subst) cudaFree(c->d_subst);
   if (c->d_counter) cudaFree(c->d_counter);
+  if (c->d_bucket) cudaFree(c->d_bucket);
   timed_resolve(c);
   for (auto& t : c->free_events) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
   if (c->ev0) cudaEventDestroy(c->ev0);
@@ -219,7 +225,8 @@ int stemk_upload(stemk_ctx* ctx, const stemk_seqset_desc* desc, stemk_set** out)
                o_cidx = place(off, h.cidx), o_ce = place(off, h.ce), o_lev = place(off, h.lev_off),
                o_boff = place(off, h.boff), o_bab = place(off, h.bab), o_bfq = place(off, h.bfq),
                o_ccode = place(off, h.ccode), o_cw = place(off, h.cw), o_prof = place(off, h.prof),
-               o_text = place(off, h.text);
+               o_text = place(off, h.text), o_up = place(off, h.up), o_dn = place(off, h.dn), o_s2 = place(off, h.s2),
+               o_nodei = place(off, h.nodei), o_c16 = place(off, h.c16), o_blk = place(off, h.blk);
   off = (off + 255) & ~size_t(255);
   std::vector<char> stage(off, 0);
   auto put = [&](size_t at, const auto& v) { if (!v.empty()) std::memcpy(stage.data() + at, v.data(), v.size() * sizeof(v[0])); };
@@ -227,6 +234,7 @@ int stemk_upload(stemk_ctx* ctx, const stemk_seqset_desc* desc, stemk_set** out)
   put(o_bfreq, h.bfreq); put(o_len, h.len); put(o_bcode, h.bcode); put(o_coff, h.coff); put(o_cidx, h.cidx);
   put(o_ce, h.ce); put(o_lev, h.lev_off); put(o_boff, h.boff); put(o_bab, h.bab); put(o_bfq, h.bfq);
   put(o_ccode, h.ccode); put(o_cw, h.cw); put(o_prof, h.prof); put(o_text, h.text);
+  put(o_up, h.up); put(o_dn, h.dn); put(o_s2, h.s2); put(o_nodei, h.nodei); put(o_c16, h.c16); put(o_blk, h.blk);
   cudaError_t e = s->blob.reserve(std::max<size_t>(off, 256));
   if (e == cudaSuccess) e = cudaMemcpyAsync(s->blob.p, stage.data(), off, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
@@ -241,6 +249,8 @@ int stemk_upload(stemk_ctx* ctx, const stemk_seqset_desc* desc, stemk_set** out)
   v.lev_off = (const uint32_t*)(b + o_lev); v.boff = (const uint32_t*)(b + o_boff); v.bab = (const uint8_t*)(b + o_bab);
   v.bfq = (const double*)(b + o_bfq); v.ccode = (const uint8_t*)(b + o_ccode); v.cw = (const double*)(b + o_cw);
   v.prof = (const float*)(b + o_prof); v.text = (const uint8_t*)(b + o_text);
+  v.up = (const double*)(b + o_up); v.dn = (const double*)(b + o_dn); v.s2 = (const double*)(b + o_s2);
+  v.nodei = (const NodeI*)(b + o_nodei); v.c16 = (const uint16_t*)(b + o_c16); v.blk = (const uint32_t*)(b + o_blk);
   *out = s;
   return STEMK_OK;
 }
@@ -285,26 +295,85 @@ int stemk_pairs_device(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, s
   }
 
   if (has_stem) {
-    const uint32_t ny_cap = std::max(1u, y->host.max_N), nx_cap = std::max(1u, x->host.max_N);
-    uint32_t nslots; size_t smem;
-    stem_config(ctx, x->host, y->host, &nslots, &smem);
-    if (!nslots) return fail(ctx, STEMK_ERR_NOMEM, "a record has too many DAG nodes to stage in shared memory");
-    int per_sm = stem_max_ctas_per_sm(smem);
-    if (per_sm < 1) return fail(ctx, STEMK_ERR_CUDA, "stem kernel does not fit on an SM");
-    per_sm = std::min(per_sm, 4);
-    const int grid = (int)std::min<size_t>(n_pairs, (size_t)ctx->sm_count * per_sm);
-    const unsigned long long stride = (unsigned long long)nx_cap * ((ny_cap + 1u) & ~1u);
-    CU(ctx->scratch.reserve(sizeof(double) * stride * grid));
-    CU(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), st));
-    StemLaunch L;
-    L.X = x->view; L.Y = y->view; L.xi = d_xi; L.yi = d_yi; L.n_pairs = n_pairs; L.out = stem_out;
-    L.counter = ctx->d_counter; L.scratch = (double*)ctx->scratch.p; L.scratch_stride = stride;
-    L.pair_tab = ctx->d_pair_tab; L.len_band = ctx->params.len_band; L.nslots = nslots; L.nx_cap = nx_cap; L.ny_cap = ny_cap; L.ey_cap = std::max(1u, y->host.max_E); L.lev_cap = std::max(1u, y->host.max_nlev);
-    stemk_ctx::Timed tm = timed_begin(ctx, 0, st);
-    cudaError_t le = launch_stem(L, grid, smem, st);
-    timed_end(ctx, tm, st);
-    CU(le);
-    ctx->launches += 1;
+    const uint32_t nx_cap = std::max(1u, x->host.max_N);
+    const uint32_t lev_cap = std::max(1u, y->host.max_nlev);
+    if (n_pairs > 0xffffffffull) return fail(ctx, STEMK_ERR_ARG, "more than 2^32 pairs in one call");
+    // ---- classify: trivial pairs are finished, the others go to the general kernel (bucket 0) or to the fast
+    // kernel's size buckets (1..), each bucket keeping the caller's pair order
+    static const uint32_t kCaps[kMaxFastBuckets] = {256, 320, 384, 448, 512, 640, 768, kFastMaxN};
+    const bool any_fast = ctx->use_fast && x->host.n_fast > 0 && y->host.n_fast > 0;
+    StemClassify C;
+    C.X = x->view; C.Y = y->view; C.xi = d_xi; C.yi = d_yi; C.n_pairs = n_pairs; C.out = stem_out;
+    C.count = ctx->d_bucket; C.start = ctx->d_bucket + 16;
+    unsigned long long* heads = ctx->d_bucket + 32;
+    C.n_caps = 0; C.allow_fast = any_fast;
+    if (any_fast)
+      for (int b = 0; b < kMaxFastBuckets; ++b) {
+        C.caps[C.n_caps++] = kCaps[b];
+        if (kCaps[b] >= y->host.max_fastN) break;
+      }
+    CU(ctx->order.reserve(n_pairs * sizeof(uint32_t)));
+    C.order = (uint32_t*)ctx->order.p;
+    const int n_buckets = 1 + C.n_caps;
+    CU(launch_classify(C, n_buckets, heads, st));
+    ctx->launches += 3;
+
+    // ---- general kernel: needed unless every record with a DAG is fast-eligible
+    auto n_dag = [](const CompiledSet& h) { uint32_t n = 0; for (const RecDev& r : h.rec) n += r.N > 0; return n; };
+    const bool need_general = !any_fast || x->host.n_fast < n_dag(x->host) || y->host.n_fast < n_dag(y->host);
+    if (need_general) {
+      const uint32_t ny_cap = std::max(1u, y->host.max_N);
+      uint32_t nslots; size_t smem;
+      stem_config(ctx, x->host, y->host, &nslots, &smem);
+      if (!nslots) return fail(ctx, STEMK_ERR_NOMEM, "a record has too many DAG nodes to stage in shared memory");
+      int per_sm = stem_max_ctas_per_sm(smem);
+      if (per_sm < 1) return fail(ctx, STEMK_ERR_CUDA, "stem kernel does not fit on an SM");
+      per_sm = std::min(per_sm, 4);
+      const int grid = (int)std::min<size_t>(n_pairs, (size_t)ctx->sm_count * per_sm);
+      const unsigned long long stride = (unsigned long long)nx_cap * ((ny_cap + 1u) & ~1u);
+      CU(ctx->scratch.reserve(sizeof(double) * stride * grid));
+      StemLaunch L;
+      L.X = x->view; L.Y = y->view; L.xi = d_xi; L.yi = d_yi; L.n_pairs = n_pairs; L.out = stem_out;
+      L.counter = heads + 0; L.scratch = (double*)ctx->scratch.p; L.scratch_stride = stride;
+      L.pair_tab = ctx->d_pair_tab; L.len_band = ctx->params.len_band; L.nslots = nslots; L.nx_cap = nx_cap; L.ny_cap = ny_cap;
+      L.ey_cap = std::max(1u, y->host.max_E); L.lev_cap = lev_cap;
+      L.order = C.order; L.n_items_dev = C.count + 0;
+      stemk_ctx::Timed tm = timed_begin(ctx, 0, st);
+      cudaError_t le = launch_stem(L, grid, smem, st);
+      timed_end(ctx, tm, st);
+      CU(le);
+      ctx->launches += 1;
+    }
+    // ---- fast kernel, one launch per size bucket (shared memory and CTAs per SM sized for the bucket)
+    for (int b = 0; b < C.n_caps; ++b) {
+      const uint32_t ny_cap = std::min(C.caps[b], std::max(1u, y->host.max_fastN));
+      const uint32_t e4_cap = std::max(4u, y->host.max_E4);
+      const size_t budget = std::min<size_t>(ctx->smem_optin, (size_t)227 * 1024);
+      int best_w = 0, best_ctas = 0; size_t best_smem = 0;
+      for (int ctas = 4; ctas >= 1; --ctas) {
+        const size_t per_cta = std::min(budget, ((size_t)228 * 1024) / ctas - 1024);
+        int w = 0;
+        for (int t = 8; t >= 2; --t) if (stem_fast_smem_bytes(t, nx_cap, ny_cap, e4_cap, lev_cap) <= per_cta) { w = t; break; }
+        if (w && ctas * w > best_ctas * best_w) { best_w = w; best_ctas = ctas; best_smem = stem_fast_smem_bytes(w, nx_cap, ny_cap, e4_cap, lev_cap); }
+      }
+      if (!best_w) return fail(ctx, STEMK_ERR_NOMEM, "fast stem kernel: record does not fit in shared memory");
+      int per_sm = stem_fast_ctas_per_sm(best_w, best_smem);
+      if (per_sm < 1) return fail(ctx, STEMK_ERR_CUDA, "fast stem kernel does not fit on an SM");
+      per_sm = std::min(per_sm, best_ctas);
+      const int grid = (int)std::min<size_t>(n_pairs, (size_t)ctx->sm_count * per_sm);
+      const unsigned long long stride = (unsigned long long)nx_cap * ((ny_cap + 1u) & ~1u);
+      CU(ctx->scratch.reserve(sizeof(double) * stride * grid));
+      StemFastLaunch F;
+      F.X = x->view; F.Y = y->view; F.xi = d_xi; F.yi = d_yi; F.out = stem_out; F.order = C.order;
+      F.start = C.start; F.count = C.count; F.counter = heads + 1 + b; F.bucket = 1 + b;
+      F.scratch = (double*)ctx->scratch.p; F.scratch_stride = stride; F.pair_tab = ctx->d_pair_tab;
+      F.len_band = ctx->params.len_band; F.nx_cap = nx_cap; F.ny_cap = ny_cap; F.e4_cap = e4_cap; F.lev_cap = lev_cap;
+      stemk_ctx::Timed tm = timed_begin(ctx, 0, st);
+      cudaError_t le = launch_stem_fast(F, grid, best_w, best_smem, st);
+      timed_end(ctx, tm, st);
+      CU(le);
+      ctx->launches += 1;
+    }
   }
   if (has_str) {
     const uint32_t ly_cap = std::max(1u, y->host.max_L), lx_cap = std::max(1u, x->host.max_L);

@@ -29,9 +29,23 @@ struct RecDev {
   uint32_t flags;   // REC_*
   double plr;       // sum over roots of #paths root -> any leaf
   double n_rows;    // ProfileSequence::n_seqs()
+  // fast-path (separable gap factors) extras
+  uint32_t c16_0;   // offset of the record's padded 16-bit child lists in `c16`
+  uint32_t e4;      // entries of those lists (every node's list padded to a multiple of 4 with index N)
+  uint32_t blk0;    // offset of its row blocks in `blk`
+  uint32_t nblk;    // row blocks (<= kFastRows rows of one level each)
 };
 enum { REC_HAS_WEIGHT = 1u, REC_SIMPLE_COLS = 2u, REC_SIMPLE_BPF = 4u,
-       REC_LEN_MONOTONE = 8u };  // every non-leaf child is strictly shorter than its parent (true for front-end DAGs)
+       REC_LEN_MONOTONE = 8u,  // every non-leaf child is strictly shorter than its parent (true for front-end DAGs)
+       REC_FAST = 16u };       // eligible for the separable fast kernel (see compile_set.cpp)
+constexpr uint32_t kFastRows = 2;     // rows a warp of the fast stem kernel sweeps in lockstep
+constexpr uint32_t kFastMaxN = 1024;  // largest staged record (non-leaf nodes) of the fast stem kernel
+
+struct NodeI {        // integer part of a node for the fast kernel (8 bytes)
+  uint32_t e4_bcode;  // (offset of its padded child list inside the record, in entries) << 8 | bcode
+  uint16_t deg4;      // padded list length / 4
+  uint16_t len;       // last - first
+};
 
 // Pointers into one device (or host) allocation holding a compiled set.
 struct SetView {
@@ -51,6 +65,13 @@ struct SetView {
   const uint32_t* cidx;  // child, in the record's level numbering
   const double* ce;      // g^gaps * edge weight
   const uint32_t* lev_off;
+  // separable fast path: e(j,c) = g^(len_j - len_c - 2) = s2[j] * up[c]; dn = 1/up (as its own power)
+  const double* up;      // g^(B - len)   B = the record's reference length (half its longest pair)
+  const double* dn;      // g^(len - B)
+  const double* s2;      // g^(len - 2 - B)
+  const NodeI* nodei;
+  const uint16_t* c16;   // padded child lists, record-local node numbers, N = the all-zero dummy column
+  const uint32_t* blk;   // row blocks: first row | count << 16
   // general base-pair profiles (alignments / IUPAC)
   const uint32_t* boff;  // [sum(N+1)]
   const uint8_t* bab;    // a*4+b
@@ -69,6 +90,11 @@ struct CompiledSet {
   std::vector<uint32_t> len, coff, cidx, lev_off, boff;
   std::vector<uint8_t> bcode, bab, ccode, text;
   std::vector<float> prof;
+  std::vector<double> up, dn, s2;
+  std::vector<NodeI> nodei;
+  std::vector<uint16_t> c16;
+  std::vector<uint32_t> blk;
+  uint32_t max_E4 = 0, max_fastN = 0, n_fast = 0;  // over fast-eligible records
   // host-only statistics for the work model and the scheduler
   std::vector<uint32_t> n_nodes_all;  // nodes incl. leaves (reference's #V)
   std::vector<uint32_t> n_edges_all;  // edges incl. leaf edges (reference's #E)

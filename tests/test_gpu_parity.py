@@ -32,7 +32,13 @@ def _gpu():
 # ------------------------------------------------------------------ (1) golden vectors of the reference
 @pytest.mark.parametrize("kind", range(9))
 @pytest.mark.parametrize("band", [10, 0])
-def test_golden_gram(golden, kind, band):
+@pytest.mark.parametrize("fast", ["1", "0"])
+def test_golden_gram(golden, kind, band, fast, monkeypatch):
+    """fast=1: single-sequence records take the separable fast stem kernel, alignments the general one;
+    fast=0 forces the general kernel for every pair (STEMK_FAST is read when the context is created)."""
+    if fast == "0" and kind in (L.STR_SUBST, L.STR_SIMPLE, L.LSU_STR):
+        pytest.skip("no stem part")
+    monkeypatch.setenv("STEMK_FAST", fast)
     ctx = api.Context(L.make_params(kind, len_band=band))
     got = ctx.gram(ctx.upload(golden["flat"]))
     assert relerr(got, golden["z"][f"gram_k{kind}_b{band}"]) < TOL
@@ -98,6 +104,38 @@ def test_oracle_fresh_inputs_nondefault_params(kind):
     ds = ctx.upload(flat)
     for normalize in (False, True):
         assert relerr(ctx.gram(ds, normalize), O.gram(oparams(p), flat.desc(), normalize)) < TOL
+
+
+@pytest.mark.parametrize("g", [0.9, 0.05, 0.001])
+def test_loop_gap_range(g):
+    """Large and tiny loop gaps: the separable fast path rescales rows by g^(+-len/2); when those powers leave its
+    safe range (g = 0.001 on 300 nt) the records must fall back to the general kernel, not lose accuracy."""
+    recs = synth.make_config(3, 6, offset=1300) + synth.make_config(1, 4, offset=1300)
+    flat = hostlib.SeqSet([hostlib.MData.from_record(r, TH) for r in recs])
+    for band in (10, 0):
+        p = L.make_params(L.SU_STEM, loop_gap=g, len_band=band)
+        ctx = api.Context(p)
+        assert relerr(ctx.gram(ctx.upload(flat)), O.gram(oparams(p), flat.desc(), False)) < TOL
+
+
+def test_fast_and_general_kernels_agree_and_fast_is_deterministic(monkeypatch):
+    recs = synth.make_config(3, 40, offset=2100)
+    md = hostlib.build_many(recs, TH)
+    p = L.make_params(L.SU_STEM)
+    monkeypatch.setenv("STEMK_FAST", "0")
+    cg = api.Context(p)
+    g_general = cg.gram(cg.upload(md))
+    monkeypatch.setenv("STEMK_FAST", "1")
+    cf = api.Context(p)
+    ds = cf.upload(md)
+    g_fast = cf.gram(ds)
+    assert relerr(g_fast, g_general) < 1e-11
+    assert np.array_equal(g_fast, cf.gram(ds))          # fixed-order reduction: bit-reproducible
+    perm = np.random.default_rng(0).permutation(40)
+    gp = cf.gram(cf.upload([md[i] for i in perm]))
+    a, b = np.triu_indices(40)
+    kept = perm[a] <= perm[b]
+    assert np.array_equal(gp[a[kept], b[kept]], g_fast[perm[a[kept]], perm[b[kept]]])
 
 
 def test_threshold_changes_dag_density():
