@@ -27,6 +27,7 @@ struct StemLaunch {
 };
 
 constexpr int kMaxFastBuckets = 8;
+constexpr uint32_t kFastGroup = 2;  // == kGroup of stem_fast.cu
 
 // fast (separable) stem kernel: runs the pairs order[start[bucket] .. + count[bucket])
 struct StemFastLaunch {
@@ -39,8 +40,8 @@ struct StemFastLaunch {
   const unsigned long long* count;   // [n_buckets] device
   unsigned long long* counter;       // this bucket's work-queue head (zeroed by the classifier)
   int bucket;
-  double* scratch;                   // per-CTA slab of pre-scaled G0 rows
-  unsigned long long scratch_stride; // doubles per CTA
+  double* scratch;                   // per-CTA slabs of pre-scaled G0 rows (one per pair of a group)
+  unsigned long long scratch_stride; // doubles per CTA (all slabs of the group)
   const double* pair_tab;
   uint32_t len_band, nx_cap, ny_cap, e4_cap, lev_cap;
 };

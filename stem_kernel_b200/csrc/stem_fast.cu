@@ -12,9 +12,11 @@
 // No FMA operand has to be fetched per edge any more, child lists are padded to multiples of four (index N is an
 // all-zero dummy column), so the inner loop is one 8-byte index load + four 8-byte gathers + four adds.
 //
-// Mapping.  One CTA per pair, several CTAs per SM (launches are bucketed by the size of the staged record so that
-// shared memory is sized for the bucket, not for the largest record of the set).  The y record is staged in shared
-// memory.  Warps pull row BLOCKS of the x record -- up to kFastRows rows of one DAG level, precomputed per record --
+// Mapping.  One persistent CTA per SM; launches are bucketed by the size of the staged record so that shared memory
+// is sized for the bucket, not for the largest record of the set.  A CTA takes a GROUP of up to kGroup consecutive
+// queue positions that share their y record (callers order pair lists y-major), stages that record in shared memory
+// once and runs the group's pairs concurrently: a DAG level of one x record has ~14 rows, too few to keep the CTA's
+// warps busy on its own.  Warps pull row BLOCKS of the x records -- up to kFastRows rows of one DAG level, precomputed per record --
 // from a shared-memory queue, wait on per-row flags until the rows of the block's inner pairs are published, and
 // run the block alone:
 //   A  per row, lanes <-> columns: sum of the finished pre-scaled G0 rows (coalesced L2 reads of the per-CTA slab)
@@ -28,6 +30,8 @@
 namespace stemk {
 
 namespace {
+
+constexpr uint32_t kGroup = 2;  // pairs sharing one staged y record that a CTA runs concurrently
 
 struct FastLayout {
   uint32_t tab, yD0, yD1, yD2, yD3, yI, yC, yLev, done, rowacc, rows, row_bytes, total;
@@ -47,8 +51,8 @@ __host__ __device__ inline FastLayout fast_layout(uint32_t nwarps, uint32_t nx_c
   L.yI = take(8 * ny_cap);    // NodeI
   L.yC = take(2 * e4_cap);    // child lists
   L.yLev = take(4 * (lev_cap + 1));
-  L.done = take(4 * nx_cap);
-  L.rowacc = take(8 * nx_cap);
+  L.done = take(4 * nx_cap * kGroup);    // per pair of the group
+  L.rowacc = take(8 * nx_cap * kGroup);
   L.row_bytes = (8u * (ny_cap + 1u) + 15u) & ~15u;  // + the dummy column
   L.rows = take(2u * kFastRows * L.row_bytes * nwarps);
   L.total = off;
@@ -65,10 +69,17 @@ __device__ __forceinline__ uint32_t ld_flag_f(const unsigned char* sm, uint32_t 
   return *reinterpret_cast<const volatile uint32_t*>(sm + byteoff);
 }
 
-__global__ void __launch_bounds__(256, 2) stem_fast_kernel(const StemFastLaunch P) {
+struct PairSlot {        // one pair of the group in flight
+  uint32_t k;            // pair number (index into xi / yi / out)
+  uint32_t N, node0, coff0, blk0, nblk;
+  double plr;
+};
+
+__global__ void __launch_bounds__(512, 1) stem_fast_kernel(const StemFastLaunch P) {
   extern __shared__ __align__(16) unsigned char sm[];
-  __shared__ unsigned long long s_pair;
-  __shared__ uint32_t s_next_blk;
+  __shared__ unsigned long long s_item;
+  __shared__ uint32_t s_next_blk, s_g, s_maxblk;
+  __shared__ PairSlot s_slot[kGroup];
   const uint32_t nwarps = blockDim.x >> 5;
   const FastLayout L = fast_layout(nwarps, P.nx_cap, P.ny_cap, P.e4_cap, P.lev_cap);
 #define SM(T, byteoff) (*reinterpret_cast<T*>(sm + (byteoff)))
@@ -76,91 +87,131 @@ __global__ void __launch_bounds__(256, 2) stem_fast_kernel(const StemFastLaunch 
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const uint32_t band = P.len_band;
   for (uint32_t t = tid; t < 256; t += blockDim.x) SM(double, L.tab + 8 * t) = P.pair_tab[t];
-  double* __restrict__ G0 = P.scratch + (size_t)blockIdx.x * P.scratch_stride;
+  double* __restrict__ slab = P.scratch + (size_t)blockIdx.x * P.scratch_stride;
+  const unsigned long long slot_stride = P.scratch_stride / kGroup;
   const SetView& X = P.X;
   const SetView& Y = P.Y;
   const unsigned long long n_items = P.count[P.bucket];
   const uint32_t* __restrict__ order = P.order + P.start[P.bucket];
   // this warp's rows: [r][HQ | H]
   const uint32_t wrows = L.rows + 2u * kFastRows * L.row_bytes * warp;
+  unsigned long long item = 0, item_end = 0;  // the CTA's current run of queue positions
 
   for (;;) {
-    __syncthreads();  // previous pair fully retired (also orders the tab fill on the first trip)
-    if (tid == 0) { s_pair = atomicAdd(P.counter, 1ull); s_next_blk = 0; }
+    __syncthreads();  // previous group fully retired (also orders the tab fill on the first trip)
+    if (tid == 0) {
+      // take kGroup queue positions at a time; a group = the leading positions that share their y record
+      if (item >= item_end) { item = atomicAdd(P.counter, (unsigned long long)kGroup); item_end = item + kGroup; }
+      if (item_end > n_items) item_end = n_items;
+      uint32_t g = 0;
+      if (item < item_end) {
+        const uint32_t y0 = P.yi[order[item]];
+        uint32_t maxblk = 0;
+        while (item + g < item_end && g < kGroup && P.yi[order[item + g]] == y0) {
+          const uint32_t k = order[item + g];
+          const RecDev rx = X.rec[P.xi[k]];
+          PairSlot ps;
+          ps.k = k; ps.N = rx.N; ps.node0 = rx.node0; ps.coff0 = rx.coff0; ps.blk0 = rx.blk0; ps.nblk = rx.nblk; ps.plr = rx.plr;
+          s_slot[g] = ps;
+          maxblk = max(maxblk, rx.nblk);
+          ++g;
+        }
+        s_maxblk = maxblk;
+        s_item = item;
+        item += g;
+      }
+      s_g = g;
+      s_next_blk = 0;
+    }
     __syncthreads();
-    if (s_pair >= n_items) break;
-    const uint32_t k = order[s_pair];
-    const RecDev rx = X.rec[P.xi[k]];
-    const RecDev ry = Y.rec[P.yi[k]];
-    const uint32_t Nx = rx.N, Ny = ry.N;
-    const uint32_t NYS = (Ny + 1u) & ~1u;  // row stride of the G0 slab
+    const uint32_t g = s_g;
+    if (g == 0) break;
+    const RecDev ry = Y.rec[P.yi[order[s_item]]];
+    const uint32_t Ny = ry.N;
+    const uint32_t NYS = (Ny + 1u) & ~1u;  // row stride of the G0 slabs
+    const uint32_t n_tickets = g * s_maxblk;
 
     // ---- stage the y record, clear the row flags
     for (uint32_t j = tid; j < Ny; j += blockDim.x) {
-      const uint32_t g = ry.node0 + j;
-      SM(double2, L.yD0 + 16 * j) = make_double2(Y.a[g], Y.el[g]);
-      SM(double2, L.yD1 + 16 * j) = make_double2(Y.s2[g], Y.up[g]);
-      SM(double2, L.yD2 + 16 * j) = make_double2(Y.paths[g], Y.bfreq[g]);
-      SM(double, L.yD3 + 8 * j) = Y.dn[g];
-      SM(NodeI, L.yI + 8 * j) = Y.nodei[g];
+      const uint32_t gy = ry.node0 + j;
+      SM(double2, L.yD0 + 16 * j) = make_double2(Y.a[gy], Y.el[gy]);
+      SM(double2, L.yD1 + 16 * j) = make_double2(Y.s2[gy], Y.up[gy]);
+      SM(double2, L.yD2 + 16 * j) = make_double2(Y.paths[gy], Y.bfreq[gy]);
+      SM(double, L.yD3 + 8 * j) = Y.dn[gy];
+      SM(NodeI, L.yI + 8 * j) = Y.nodei[gy];
     }
     {
       const uint2* __restrict__ src = reinterpret_cast<const uint2*>(Y.c16 + ry.c16_0);  // c16_0 is a multiple of 4
       for (uint32_t e = tid; e < ry.e4 / 4u; e += blockDim.x) SM(uint2, L.yC + 8 * e) = src[e];
     }
     for (uint32_t l = tid; l <= ry.nlev; l += blockDim.x) SM(uint32_t, L.yLev + 4 * l) = Y.lev_off[ry.lev0 + l];
-    for (uint32_t i = tid; i < Nx; i += blockDim.x) SM(uint32_t, L.done + 4 * i) = 0u;
+    for (uint32_t i = tid; i < g * P.nx_cap; i += blockDim.x) SM(uint32_t, L.done + 4 * i) = 0u;
     // the dummy column of every row of this warp
     if (lane < 2u * kFastRows) SM(double, wrows + L.row_bytes * lane + 8u * Ny) = 0.0;
     __syncthreads();
 
-    const uint32_t* __restrict__ xcoff = X.coff + rx.coff0;
-    const uint32_t* __restrict__ xblk = X.blk + rx.blk0;
-
     for (;;) {
-      uint32_t b = 0;
-      if (lane == 0) b = atomicAdd(&s_next_blk, 1u);
-      b = __shfl_sync(0xffffffffu, b, 0);
-      if (b >= rx.nblk) break;
-      const uint32_t blk = xblk[b];
+      // tickets interleave the pairs of the group block by block; a pair's own blocks keep their order, which is
+      // all the dependencies need (a block only waits for earlier blocks of the same pair)
+      uint32_t t = 0;
+      if (lane == 0) t = atomicAdd(&s_next_blk, 1u);
+      t = __shfl_sync(0xffffffffu, t, 0);
+      if (t >= n_tickets) break;
+      const uint32_t sl = t % g, b = t / g;
+      const PairSlot ps = s_slot[sl];
+      if (b >= ps.nblk) continue;
+      const uint32_t blk = X.blk[ps.blk0 + b];
       const uint32_t i0 = blk & 0xffffu, cnt = blk >> 16;  // cnt in 1..kFastRows
+      const uint32_t* __restrict__ xcoff = X.coff + ps.coff0;
+      double* __restrict__ G0 = slab + sl * slot_stride;
+      const uint32_t done = L.done + 4u * sl * P.nx_cap;
 
       // ---- phase A: HQ(r,:) = up_y * s2_x(i) * sum over inner pairs c of G0s(c,:)
       for (uint32_t r = 0; r < cnt; ++r) {
         const uint32_t i = i0 + r;
         const uint32_t hq = wrows + 2u * L.row_bytes * r;
         const uint32_t e0 = xcoff[i], e1 = xcoff[i + 1];
-        const double xs2 = X.s2[rx.node0 + i];
+        const double xs2 = X.s2[ps.node0 + i];
         for (uint32_t eb = e0; eb < e1 || eb == e0; eb += 32u) {
           const uint32_t ne = min(32u, e1 - eb);
+          const bool last = eb + 32u >= e1;
           uint32_t off_l = 0u;
           if (lane < ne) {
             const uint32_t c = X.cidx[eb + lane];
             off_l = c * NYS;
-            while (ld_flag_f(sm, L.done + 4u * c) == 0u) __nanosleep(32);  // wait until that row is published
+            while (ld_flag_f(sm, done + 4u * c) == 0u) __nanosleep(32);  // wait until that row is published
           }
           __syncwarp();
           __threadfence_block();  // acquire: the G0 rows behind the flags just seen
-          for (uint32_t jb = 0; jb < Ny; jb += 64u) {  // uniform trip count: the shuffles below need every lane
+          for (uint32_t jb = 0; jb < Ny; jb += 128u) {  // uniform trip count: the shuffles below need every lane
             const uint32_t j = jb + lane;
-            const bool one = j < Ny, two = j + 32u < Ny;
-            double q0 = (one && eb != e0) ? SM(double, hq + 8u * j) : 0.0;
-            double q1 = (two && eb != e0) ? SM(double, hq + 8u * (j + 32u)) : 0.0;
+            const bool v0 = j < Ny, v1 = j + 32u < Ny, v2 = j + 64u < Ny, v3 = j + 96u < Ny;
+            const bool more = eb != e0;
+            double q0 = (v0 && more) ? SM(double, hq + 8u * j) : 0.0;
+            double q1 = (v1 && more) ? SM(double, hq + 8u * (j + 32u)) : 0.0;
+            double q2 = (v2 && more) ? SM(double, hq + 8u * (j + 64u)) : 0.0;
+            double q3 = (v3 && more) ? SM(double, hq + 8u * (j + 96u)) : 0.0;
 #pragma unroll 4
-            for (uint32_t t = 0; t < ne; ++t) {
-              const uint32_t off = __shfl_sync(0xffffffffu, off_l, t);
-              if (one) q0 += __ldcg(G0 + off + j);
-              if (two) q1 += __ldcg(G0 + off + j + 32u);
+            for (uint32_t tt = 0; tt < ne; ++tt) {
+              const double* __restrict__ src = G0 + __shfl_sync(0xffffffffu, off_l, tt) + j;
+              if (v0) q0 += __ldcg(src);
+              if (v1) q1 += __ldcg(src + 32);
+              if (v2) q2 += __ldcg(src + 64);
+              if (v3) q3 += __ldcg(src + 96);
             }
-            if (one) SM(double, hq + 8u * j) = q0;
-            if (two) SM(double, hq + 8u * (j + 32u)) = q1;
+            if (last) {  // scale: HQ = up_y(j) * (s2_x * sum)
+              if (v0) q0 = SM(double2, L.yD1 + 16u * j).y * (xs2 * q0);
+              if (v1) q1 = SM(double2, L.yD1 + 16u * (j + 32u)).y * (xs2 * q1);
+              if (v2) q2 = SM(double2, L.yD1 + 16u * (j + 64u)).y * (xs2 * q2);
+              if (v3) q3 = SM(double2, L.yD1 + 16u * (j + 96u)).y * (xs2 * q3);
+            }
+            if (v0) SM(double, hq + 8u * j) = q0;
+            if (v1) SM(double, hq + 8u * (j + 32u)) = q1;
+            if (v2) SM(double, hq + 8u * (j + 64u)) = q2;
+            if (v3) SM(double, hq + 8u * (j + 96u)) = q3;
           }
           if (e1 == e0) break;
         }
-        __syncwarp();
-        // scale: HQ = up_y(j) * (s2_x * sum)
-        for (uint32_t j = lane; j < Ny; j += 32u)
-          SM(double, hq + 8u * j) = SM(double2, L.yD1 + 16u * j).y * (xs2 * SM(double, hq + 8u * j));
       }
       __syncwarp();
 
@@ -168,7 +219,7 @@ __global__ void __launch_bounds__(256, 2) stem_fast_kernel(const StemFastLaunch 
       const uint32_t r = (cnt == 2u) ? (lane >> 4) : 0u;
       const uint32_t slot = (cnt == 2u) ? (lane & 15u) : lane;
       const uint32_t nslot = (cnt == 2u) ? 16u : 32u;
-      const uint32_t gx = rx.node0 + i0 + r;
+      const uint32_t gx = ps.node0 + i0 + r;
       const double xql = X.ql[gx], xbf = X.bfreq[gx];
       const uint32_t xl = X.len[gx], xbc = X.bcode[gx];
       const uint32_t hqrow = wrows + 2u * L.row_bytes * r, hrow = hqrow + L.row_bytes;
@@ -222,36 +273,38 @@ __global__ void __launch_bounds__(256, 2) stem_fast_kernel(const StemFastLaunch 
         __syncwarp();
       }
       // per-row path-weighted MATCH sum (lanes of one row are contiguous: reduce inside the half / full warp)
+      const uint32_t racc_at = L.rowacc + 8u * (sl * P.nx_cap + i0 + r);
       if (cnt == 2u) {
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) racc += __shfl_xor_sync(0xffffffffu, racc, o);
-        if ((lane & 15u) == 0u) SM(double, L.rowacc + 8u * (i0 + r)) = X.paths[gx] * racc;
+        if ((lane & 15u) == 0u) SM(double, racc_at) = X.paths[gx] * racc;
       } else {
         racc = warp_sum_all(racc);
-        if (lane == 0u) SM(double, L.rowacc + 8u * i0) = X.paths[gx] * racc;
+        if (lane == 0u) SM(double, racc_at) = X.paths[gx] * racc;
       }
 
       // ---- phase C: finished rows G0s(i,:) = up_x(i) * dn_y * (H + a_x*HQ), then publish them
       for (uint32_t rr = 0; rr < cnt; ++rr) {
         const uint32_t i = i0 + rr;
         const uint32_t hq2 = wrows + 2u * L.row_bytes * rr, h2 = hq2 + L.row_bytes;
-        const double xa2 = X.a[rx.node0 + i], xup = X.up[rx.node0 + i];
+        const double xa2 = X.a[ps.node0 + i], xup = X.up[ps.node0 + i];
         double* __restrict__ g0row = G0 + (size_t)i * NYS;
         for (uint32_t j = lane; j < Ny; j += 32u)
           g0row[j] = xup * (SM(double, L.yD3 + 8u * j) * fma(xa2, SM(double, hq2 + 8u * j), SM(double, h2 + 8u * j)));
       }
       __threadfence_block();
       __syncwarp();
-      if (lane < cnt) *reinterpret_cast<volatile uint32_t*>(sm + L.done + 4u * (i0 + lane)) = 1u;
+      if (lane < cnt) *reinterpret_cast<volatile uint32_t*>(sm + done + 4u * (i0 + lane)) = 1u;
     }
 
-    // ---- fixed-order sum of the per-row slots
+    // ---- fixed-order sum of the per-row slots, one warp per pair of the group
     __syncthreads();
-    if (warp == 0) {
+    if (warp < g) {
+      const PairSlot ps = s_slot[warp];
       double t = 0.0;
-      for (uint32_t i = lane; i < Nx; i += 32u) t += SM(double, L.rowacc + 8u * i);
+      for (uint32_t i = lane; i < ps.N; i += 32u) t += SM(double, L.rowacc + 8u * (warp * P.nx_cap + i));
       t = warp_sum_all(t);
-      if (lane == 0) P.out[k] = t + rx.plr * (double)ry.lr;
+      if (lane == 0) P.out[ps.k] = t + ps.plr * (double)ry.lr;
     }
   }
 #undef SM

@@ -349,19 +349,15 @@ int stemk_pairs_device(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, s
       const uint32_t ny_cap = std::min(C.caps[b], std::max(1u, y->host.max_fastN));
       const uint32_t e4_cap = std::max(4u, y->host.max_E4);
       const size_t budget = std::min<size_t>(ctx->smem_optin, (size_t)227 * 1024);
-      int best_w = 0, best_ctas = 0; size_t best_smem = 0;
-      for (int ctas = 4; ctas >= 1; --ctas) {
-        const size_t per_cta = std::min(budget, ((size_t)228 * 1024) / ctas - 1024);
-        int w = 0;
-        for (int t = 8; t >= 2; --t) if (stem_fast_smem_bytes(t, nx_cap, ny_cap, e4_cap, lev_cap) <= per_cta) { w = t; break; }
-        if (w && ctas * w > best_ctas * best_w) { best_w = w; best_ctas = ctas; best_smem = stem_fast_smem_bytes(w, nx_cap, ny_cap, e4_cap, lev_cap); }
-      }
+      // one CTA per SM with as many warps as the bucket's rows leave room for
+      int best_w = 0; size_t best_smem = 0;
+      for (int t = 16; t >= 2; --t) if (stem_fast_smem_bytes(t, nx_cap, ny_cap, e4_cap, lev_cap) <= budget) { best_w = t; break; }
       if (!best_w) return fail(ctx, STEMK_ERR_NOMEM, "fast stem kernel: record does not fit in shared memory");
-      int per_sm = stem_fast_ctas_per_sm(best_w, best_smem);
+      best_smem = stem_fast_smem_bytes(best_w, nx_cap, ny_cap, e4_cap, lev_cap);
+      const int per_sm = stem_fast_ctas_per_sm(best_w, best_smem);
       if (per_sm < 1) return fail(ctx, STEMK_ERR_CUDA, "fast stem kernel does not fit on an SM");
-      per_sm = std::min(per_sm, best_ctas);
-      const int grid = (int)std::min<size_t>(n_pairs, (size_t)ctx->sm_count * per_sm);
-      const unsigned long long stride = (unsigned long long)nx_cap * ((ny_cap + 1u) & ~1u);
+      const int grid = (int)std::min<size_t>((n_pairs + kFastGroup - 1) / kFastGroup, (size_t)ctx->sm_count);
+      const unsigned long long stride = (unsigned long long)kFastGroup * nx_cap * ((ny_cap + 1u) & ~1u);
       CU(ctx->scratch.reserve(sizeof(double) * stride * grid));
       StemFastLaunch F;
       F.X = x->view; F.Y = y->view; F.xi = d_xi; F.yi = d_yi; F.out = stem_out; F.order = C.order;
@@ -447,14 +443,19 @@ int stemk_gram(stemk_ctx* ctx, const stemk_set* train, int normalize, double* ou
   std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) { return size_key[a] > size_key[b]; });
   const size_t n_pairs = (size_t)n * (n + 1) / 2;
   std::vector<uint32_t> xi(n_pairs), yi(n_pairs);
+  // y-major work order: for every record b (big first) all partners a <= b (big first).  The reference evaluates
+  // kernel_(train[i], train[j]) with i <= j (kernel_matrix.cpp:47-50) and the stem kernel is not symmetric in
+  // its arguments, so x = the smaller ORIGINAL index.  Consecutive pairs share their y record, which the stem
+  // kernel stages once per group of pairs.
   size_t k = 0;
-  for (uint32_t p = 0; p < n; ++p)
-    for (uint32_t q = p; q < n; ++q, ++k) {
-      // the reference evaluates kernel_(train[i], train[j]) with i <= j (kernel_matrix.cpp:47-50);
-      // the stem kernel is not symmetric in its arguments, so the roles must be kept
-      const uint32_t a = perm[p], b = perm[q];
-      xi[k] = std::min(a, b); yi[k] = std::max(a, b);
+  for (uint32_t q = 0; q < n; ++q) {
+    const uint32_t b = perm[q];
+    for (uint32_t p = 0; p < n; ++p) {
+      const uint32_t a = perm[p];
+      if (a > b) continue;
+      xi[k] = a; yi[k] = b; ++k;
     }
+  }
   CU(ctx->idx_x.reserve(n_pairs * sizeof(uint32_t)));
   CU(ctx->idx_y.reserve(n_pairs * sizeof(uint32_t)));
   CU(ctx->vals.reserve(n_pairs * sizeof(double)));

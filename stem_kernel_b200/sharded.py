@@ -5,8 +5,8 @@ Replaces the reference's MPI path (common/kernel_matrix.cpp:186-262 CalcTrainMat
 
   * every rank holds the whole flattened record set in its own HBM (<= 2 GB for 10k records, SURVEY 5.8);
   * the n(n+1)/2 pairs (or n_test*n_train for the rectangular matrix) are put into ONE global order -- records
-    sorted by a size key, biggest first, pairs nested (p, q>=p) -- and rank r owns pairs r, r+W, r+2W, ...
-    Neighbouring pairs of that order cost nearly the same (same x record, y records adjacent in size), so the
+    sorted by a size key, biggest first, pairs y-major (for each y all its partners) -- and rank r owns pairs
+    r, r+W, r+2W, ...  Neighbouring pairs of that order cost nearly the same (same y, x adjacent in size), so the
     strided deal is balanced to well under a percent of the stem work model and every rank still runs its own
     expensive pairs first, which is what keeps the tail of its device-side work queue short;
   * the data path has exactly one exchange: a gather of ceil(P/W) doubles per rank to rank 0 (NCCL over NVLink
@@ -29,13 +29,23 @@ def size_order(keys):
 
 
 def square_pairs(keys):
-    """All pairs i<=j of a square Gram matrix in the global work order.  The reference evaluates
-    kernel_(x_i, x_j) with i <= j (kernel_matrix.cpp:47-50), so x = min index, y = max index."""
+    """All pairs i<=j of a square Gram matrix in the global work order: y-major -- for every record b (biggest
+    first) all partners a <= b (biggest first).  The reference evaluates kernel_(x_i, x_j) with i <= j
+    (kernel_matrix.cpp:47-50) and the stem kernel is not symmetric, so x = the smaller ORIGINAL index.
+    Consecutive pairs share their y record (the stem kernel stages it once per group of pairs)."""
     perm = size_order(keys)
     n = len(perm)
-    p, q = np.triu_indices(n)
-    a, b = perm[p], perm[q]
-    return np.minimum(a, b).astype(np.uint32), np.maximum(a, b).astype(np.uint32)
+    xs, ys = [], []
+    step = max(1, (1 << 24) // max(n, 1))           # rows of the n x n candidate grid per chunk
+    for q0 in range(0, n, step):
+        b = perm[q0:q0 + step]
+        keep = perm[None, :] <= b[:, None]
+        ys.append(np.repeat(b, keep.sum(axis=1)))
+        xs.append(np.broadcast_to(perm[None, :], keep.shape)[keep])
+    if not xs:
+        z = np.zeros(0, dtype=np.uint32)
+        return z, z
+    return np.concatenate(xs).astype(np.uint32), np.concatenate(ys).astype(np.uint32)
 
 
 def cross_pairs(test_keys, train_keys, cols=None):

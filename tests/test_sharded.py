@@ -21,6 +21,7 @@ def test_square_pairs_cover_upper_triangle_once():
     order = sharded.size_order(keys)
     assert list(order) == [2, 3, 0, 5, 1, 4]                 # biggest first, stable
     assert (int(xi[0]), int(yi[0])) == (2, 2) and (int(xi[-1]), int(yi[-1])) == (4, 4)
+    assert list(yi[:3]) == [2, 2, 2] and list(xi[:3]) == [2, 0, 1]        # y-major; partners big first
 
 
 def test_cross_pairs_roles_and_sv_subset():
