@@ -27,10 +27,7 @@ struct StemLaunch {
 };
 
 constexpr int kMaxFastBuckets = 8;
-#ifndef STEMK_GROUP
-#define STEMK_GROUP 2
-#endif
-constexpr uint32_t kFastGroup = STEMK_GROUP;  // == kGroup of stem_fast.cu
+constexpr uint32_t kFastGroup = 2;  // == kGroup of stem_fast.cu
 
 // fast (separable) stem kernel: runs the pairs order[start[bucket] .. + count[bucket])
 struct StemFastLaunch {
@@ -82,9 +79,9 @@ size_t stem_smem_bytes(uint32_t nslots, uint32_t nx_cap, uint32_t ny_cap, uint32
 int stem_warps_per_cta();
 cudaError_t launch_stem(const StemLaunch& p, int grid, size_t smem, cudaStream_t stream);
 int stem_max_ctas_per_sm(size_t smem);
-size_t stem_fast_smem_bytes(uint32_t nteams, uint32_t nx_cap, uint32_t ny_cap, uint32_t e4_cap, uint32_t lev_cap);
-int stem_fast_ctas_per_sm(int nteams, size_t smem);
-cudaError_t launch_stem_fast(const StemFastLaunch& p, int grid, int nteams, size_t smem, cudaStream_t stream);
+size_t stem_fast_smem_bytes(uint32_t nwarps, uint32_t nx_cap, uint32_t ny_cap, uint32_t e4_cap, uint32_t lev_cap);
+int stem_fast_ctas_per_sm(int nwarps, size_t smem);
+cudaError_t launch_stem_fast(const StemFastLaunch& p, int grid, int nwarps, size_t smem, cudaStream_t stream);
 cudaError_t launch_classify(const StemClassify& c, int n_buckets, unsigned long long* counters, cudaStream_t stream);
 cudaError_t launch_string(const StringLaunch& p, int cw, int grid, cudaStream_t stream);
 int string_warps_per_cta();

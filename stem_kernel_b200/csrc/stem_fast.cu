@@ -31,19 +31,14 @@ namespace stemk {
 
 namespace {
 
-#ifndef STEMK_GROUP
-#define STEMK_GROUP 2
-#endif
-constexpr uint32_t kGroup = STEMK_GROUP;  // pairs sharing one staged y record that a CTA runs concurrently
-constexpr uint32_t kTeamWarps = 4;        // warps that sweep one row block together
-constexpr uint32_t kTeamThreads = 32 * kTeamWarps;
+constexpr uint32_t kGroup = 2;  // pairs sharing one staged y record that a CTA runs concurrently
 
 struct FastLayout {
-  uint32_t tab, yD0, yD1, yD2, yD3, yI, yC, yLev, done, rowacc, red, rows, row_stride, team_bytes, total;
+  uint32_t tab, yD0, yD1, yD2, yD3, yI, yC, yLev, done, rowacc, rows, row_bytes, total;
 };
 
-// nteams teams of kTeamWarps warps, each with kFastRows x (HQ row, H row)
-__host__ __device__ inline FastLayout fast_layout(uint32_t nteams, uint32_t nx_cap, uint32_t ny_cap, uint32_t e4_cap,
+// nwarps warps, each with kFastRows x (HQ row, H row)
+__host__ __device__ inline FastLayout fast_layout(uint32_t nwarps, uint32_t nx_cap, uint32_t ny_cap, uint32_t e4_cap,
                                                   uint32_t lev_cap) {
   FastLayout L;
   uint32_t off = 0;
@@ -58,13 +53,8 @@ __host__ __device__ inline FastLayout fast_layout(uint32_t nteams, uint32_t nx_c
   L.yLev = take(4 * (lev_cap + 1));
   L.done = take(4 * nx_cap * kGroup);    // per pair of the group
   L.rowacc = take(8 * nx_cap * kGroup);
-  L.red = take(8 * kTeamWarps * kFastRows * nteams);
-  // row stride == 8 (mod 128): the same column of the block's 8 rows falls into 8 different bank pairs
-  L.row_stride = ((8u * (ny_cap + 1u) + 127u) & ~127u) + 8u;
-  if (L.row_stride >= 8u * (ny_cap + 1u) + 128u) L.row_stride -= 128u;
-  if (L.row_stride < 8u * (ny_cap + 1u)) L.row_stride += 128u;
-  L.team_bytes = (2u * kFastRows * L.row_stride + 15u) & ~15u;
-  L.rows = take(L.team_bytes * nteams);
+  L.row_bytes = (8u * (ny_cap + 1u) + 15u) & ~15u;  // + the dummy column
+  L.rows = take(2u * kFastRows * L.row_bytes * nwarps);
   L.total = off;
   return L;
 }
@@ -79,10 +69,6 @@ __device__ __forceinline__ uint32_t ld_flag_f(const unsigned char* sm, uint32_t 
   return *reinterpret_cast<const volatile uint32_t*>(sm + byteoff);
 }
 
-__device__ __forceinline__ void team_sync(uint32_t team) {  // named barrier 1 + team, kTeamThreads threads
-  asm volatile("bar.sync %0, %1;" ::"r"(1u + team), "r"(kTeamThreads) : "memory");
-}
-
 struct PairSlot {        // one pair of the group in flight
   uint32_t k;            // pair number (index into xi / yi / out)
   uint32_t N, node0, coff0, blk0, nblk;
@@ -93,14 +79,12 @@ __global__ void __launch_bounds__(512, 1) stem_fast_kernel(const StemFastLaunch 
   extern __shared__ __align__(16) unsigned char sm[];
   __shared__ unsigned long long s_item;
   __shared__ uint32_t s_next_blk, s_g, s_maxblk;
-  __shared__ uint32_t s_ticket[4];
   __shared__ PairSlot s_slot[kGroup];
-  const uint32_t nteams = blockDim.x / kTeamThreads;
-  const FastLayout L = fast_layout(nteams, P.nx_cap, P.ny_cap, P.e4_cap, P.lev_cap);
+  const uint32_t nwarps = blockDim.x >> 5;
+  const FastLayout L = fast_layout(nwarps, P.nx_cap, P.ny_cap, P.e4_cap, P.lev_cap);
 #define SM(T, byteoff) (*reinterpret_cast<T*>(sm + (byteoff)))
 
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-  const uint32_t team = warp / kTeamWarps, tw = warp % kTeamWarps;  // team and warp inside the team
   const uint32_t band = P.len_band;
   for (uint32_t t = tid; t < 256; t += blockDim.x) SM(double, L.tab + 8 * t) = P.pair_tab[t];
   double* __restrict__ slab = P.scratch + (size_t)blockIdx.x * P.scratch_stride;
@@ -109,10 +93,8 @@ __global__ void __launch_bounds__(512, 1) stem_fast_kernel(const StemFastLaunch 
   const SetView& Y = P.Y;
   const unsigned long long n_items = P.count[P.bucket];
   const uint32_t* __restrict__ order = P.order + P.start[P.bucket];
-  // this team's rows: HQ rows 0..7 then H rows 0..7
-  const uint32_t trows = L.rows + L.team_bytes * team;
-  const uint32_t RS = L.row_stride;
-  const uint32_t tred = L.red + 8u * kTeamWarps * kFastRows * team;
+  // this warp's rows: [r][HQ | H]
+  const uint32_t wrows = L.rows + 2u * kFastRows * L.row_bytes * warp;
   unsigned long long item = 0, item_end = 0;  // the CTA's current run of queue positions
 
   for (;;) {
@@ -164,30 +146,30 @@ __global__ void __launch_bounds__(512, 1) stem_fast_kernel(const StemFastLaunch 
     }
     for (uint32_t l = tid; l <= ry.nlev; l += blockDim.x) SM(uint32_t, L.yLev + 4 * l) = Y.lev_off[ry.lev0 + l];
     for (uint32_t i = tid; i < g * P.nx_cap; i += blockDim.x) SM(uint32_t, L.done + 4 * i) = 0u;
-    // the dummy column of every row of this team
-    if (tw == 0 && lane < 2u * kFastRows) SM(double, trows + RS * lane + 8u * Ny) = 0.0;
+    // the dummy column of every row of this warp
+    if (lane < 2u * kFastRows) SM(double, wrows + L.row_bytes * lane + 8u * Ny) = 0.0;
     __syncthreads();
 
     for (;;) {
       // tickets interleave the pairs of the group block by block; a pair's own blocks keep their order, which is
       // all the dependencies need (a block only waits for earlier blocks of the same pair)
-      if (tw == 0 && lane == 0) s_ticket[team] = atomicAdd(&s_next_blk, 1u);
-      team_sync(team);
-      const uint32_t t = s_ticket[team];
+      uint32_t t = 0;
+      if (lane == 0) t = atomicAdd(&s_next_blk, 1u);
+      t = __shfl_sync(0xffffffffu, t, 0);
       if (t >= n_tickets) break;
       const uint32_t sl = t % g, b = t / g;
       const PairSlot ps = s_slot[sl];
-      if (b >= ps.nblk) { team_sync(team); continue; }   // (the barrier keeps s_ticket from being overwritten early)
+      if (b >= ps.nblk) continue;
       const uint32_t blk = X.blk[ps.blk0 + b];
       const uint32_t i0 = blk & 0xffffu, cnt = blk >> 16;  // cnt in 1..kFastRows
       const uint32_t* __restrict__ xcoff = X.coff + ps.coff0;
       double* __restrict__ G0 = slab + sl * slot_stride;
       const uint32_t done = L.done + 4u * sl * P.nx_cap;
 
-      // ---- phase A: HQ(r,:) = up_y * s2_x(i) * sum over inner pairs c of G0s(c,:); rows dealt to the team's warps
-      for (uint32_t r = tw; r < cnt; r += kTeamWarps) {
+      // ---- phase A: HQ(r,:) = up_y * s2_x(i) * sum over inner pairs c of G0s(c,:)
+      for (uint32_t r = 0; r < cnt; ++r) {
         const uint32_t i = i0 + r;
-        const uint32_t hq = trows + RS * r;
+        const uint32_t hq = wrows + 2u * L.row_bytes * r;
         const uint32_t e0 = xcoff[i], e1 = xcoff[i + 1];
         const double xs2 = X.s2[ps.node0 + i];
         for (uint32_t eb = e0; eb < e1 || eb == e0; eb += 32u) {
@@ -231,24 +213,21 @@ __global__ void __launch_bounds__(512, 1) stem_fast_kernel(const StemFastLaunch 
           if (e1 == e0) break;
         }
       }
-      team_sync(team);
+      __syncwarp();
 
-      // ---- phase B: sweep the y DAG level by level; lane <-> (row r of the block) x (node slot); the team's
-      // 4 warps x (32 / rows) slots cover up to 16..128 nodes of a level per step
-      const uint32_t rsh = cnt > 4u ? 3u : (cnt > 2u ? 2u : (cnt > 1u ? 1u : 0u));  // rows rounded up to 1,2,4,8
-      const uint32_t r = lane & ((1u << rsh) - 1u);
-      const uint32_t spw = 32u >> rsh;                    // node slots per warp
-      const uint32_t slot = tw * spw + (lane >> rsh), nslot = kTeamWarps * spw;
-      const bool live = r < cnt;
-      const uint32_t gx = ps.node0 + i0 + (live ? r : 0u);
+      // ---- phase B: sweep the y DAG level by level; lanes <-> (row r, node slot s)
+      const uint32_t r = (cnt == 2u) ? (lane >> 4) : 0u;
+      const uint32_t slot = (cnt == 2u) ? (lane & 15u) : lane;
+      const uint32_t nslot = (cnt == 2u) ? 16u : 32u;
+      const uint32_t gx = ps.node0 + i0 + r;
       const double xql = X.ql[gx], xbf = X.bfreq[gx];
       const uint32_t xl = X.len[gx], xbc = X.bcode[gx];
-      const uint32_t hqrow = trows + RS * r, hrow = hqrow + RS * kFastRows;
+      const uint32_t hqrow = wrows + 2u * L.row_bytes * r, hrow = hqrow + L.row_bytes;
       double racc = 0.0;
       uint32_t jbeg = SM(uint32_t, L.yLev);
       for (uint32_t ly = 0; ly < ry.nlev; ++ly) {
         const uint32_t jend = SM(uint32_t, L.yLev + 4u * ly + 4u);
-        if (live) for (uint32_t j = jbeg + slot; j < jend; j += nslot) {
+        for (uint32_t j = jbeg + slot; j < jend; j += nslot) {
           const NodeI ni = SM(NodeI, L.yI + 8u * j);
           const uint32_t yl = ni.len;
           if (band != 0u && yl + band < xl) {  // G1 == 0 here and below (length-monotone DAG)
@@ -291,32 +270,31 @@ __global__ void __launch_bounds__(512, 1) stem_fast_kernel(const StemFastLaunch 
           SM(double, hrow + 8u * j) = d1.y * g1;
         }
         jbeg = jend;
-        team_sync(team);
+        __syncwarp();
       }
-      // per-row path-weighted MATCH sum: slots of a warp by shuffles (fixed pattern), then the team's warps in order
-      for (uint32_t o = 16u; o >= (1u << rsh) && o > 0u; o >>= 1) racc += __shfl_xor_sync(0xffffffffu, racc, o);
-      if (lane < (1u << rsh)) SM(double, tred + 8u * (tw * kFastRows + lane)) = racc;
-      team_sync(team);
-      if (tw == 0 && lane < cnt) {
-        double t4 = 0.0;
+      // per-row path-weighted MATCH sum (lanes of one row are contiguous: reduce inside the half / full warp)
+      const uint32_t racc_at = L.rowacc + 8u * (sl * P.nx_cap + i0 + r);
+      if (cnt == 2u) {
 #pragma unroll
-        for (uint32_t w = 0; w < kTeamWarps; ++w) t4 += SM(double, tred + 8u * (w * kFastRows + lane));
-        SM(double, L.rowacc + 8u * (sl * P.nx_cap + i0 + lane)) = X.paths[ps.node0 + i0 + lane] * t4;
+        for (int o = 8; o > 0; o >>= 1) racc += __shfl_xor_sync(0xffffffffu, racc, o);
+        if ((lane & 15u) == 0u) SM(double, racc_at) = X.paths[gx] * racc;
+      } else {
+        racc = warp_sum_all(racc);
+        if (lane == 0u) SM(double, racc_at) = X.paths[gx] * racc;
       }
 
       // ---- phase C: finished rows G0s(i,:) = up_x(i) * dn_y * (H + a_x*HQ), then publish them
-      for (uint32_t rr = tw; rr < cnt; rr += kTeamWarps) {
+      for (uint32_t rr = 0; rr < cnt; ++rr) {
         const uint32_t i = i0 + rr;
-        const uint32_t hq2 = trows + RS * rr, h2 = hq2 + RS * kFastRows;
+        const uint32_t hq2 = wrows + 2u * L.row_bytes * rr, h2 = hq2 + L.row_bytes;
         const double xa2 = X.a[ps.node0 + i], xup = X.up[ps.node0 + i];
         double* __restrict__ g0row = G0 + (size_t)i * NYS;
         for (uint32_t j = lane; j < Ny; j += 32u)
           g0row[j] = xup * (SM(double, L.yD3 + 8u * j) * fma(xa2, SM(double, hq2 + 8u * j), SM(double, h2 + 8u * j)));
-        __threadfence_block();
-        __syncwarp();
-        if (lane == 0) *reinterpret_cast<volatile uint32_t*>(sm + done + 4u * i) = 1u;
       }
-      team_sync(team);  // the rows (and s_ticket) are free again
+      __threadfence_block();
+      __syncwarp();
+      if (lane < cnt) *reinterpret_cast<volatile uint32_t*>(sm + done + 4u * (i0 + lane)) = 1u;
     }
 
     // ---- fixed-order sum of the per-row slots, one warp per pair of the group
@@ -387,24 +365,24 @@ __global__ void bucket_fill_stable_kernel(const StemClassify C) {
 
 }  // namespace
 
-size_t stem_fast_smem_bytes(uint32_t nteams, uint32_t nx_cap, uint32_t ny_cap, uint32_t e4_cap, uint32_t lev_cap) {
-  return fast_layout(nteams, nx_cap, ny_cap, e4_cap, lev_cap).total;
+size_t stem_fast_smem_bytes(uint32_t nwarps, uint32_t nx_cap, uint32_t ny_cap, uint32_t e4_cap, uint32_t lev_cap) {
+  return fast_layout(nwarps, nx_cap, ny_cap, e4_cap, lev_cap).total;
 }
 
-cudaError_t launch_stem_fast(const StemFastLaunch& p, int grid, int nteams, size_t smem, cudaStream_t stream) {
+cudaError_t launch_stem_fast(const StemFastLaunch& p, int grid, int nwarps, size_t smem, cudaStream_t stream) {
   cudaError_t e = cudaFuncSetAttribute(stem_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  stem_fast_kernel<<<grid, nteams * (int)kTeamThreads, smem, stream>>>(p);
+  stem_fast_kernel<<<grid, nwarps * 32, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
-int stem_fast_ctas_per_sm(int nteams, size_t smem) {
+int stem_fast_ctas_per_sm(int nwarps, size_t smem) {
   int n = 0;
   if (cudaFuncSetAttribute(stem_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, stem_fast_kernel, nteams * (int)kTeamThreads, smem) != cudaSuccess) {
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, stem_fast_kernel, nwarps * 32, smem) != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }
