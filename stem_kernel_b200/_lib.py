@@ -8,7 +8,7 @@ import os
 from .hostlib import SeqSetDesc
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-CUDA_SO = os.path.join(_HERE, "csrc", "libstemk_b200.so")
+CUDA_SO = os.environ.get("STEMK_SO") or os.path.join(_HERE, "csrc", "libstemk_b200.so")   # STEMK_SO: tuning builds
 
 OK, ERR_ARG, ERR_CUDA, ERR_NOMEM, ERR_STATE = 0, -1, -2, -3, -4
 

@@ -27,7 +27,10 @@ struct StemLaunch {
 };
 
 constexpr int kMaxFastBuckets = 8;
-constexpr uint32_t kFastGroup = 2;  // == kGroup of stem_fast.cu
+#ifndef STEMK_GROUP
+#define STEMK_GROUP 3
+#endif
+constexpr uint32_t kFastGroup = STEMK_GROUP;  // == kGroup of stem_fast.cu
 
 // fast (separable) stem kernel: runs the pairs order[start[bucket] .. + count[bucket])
 struct StemFastLaunch {

@@ -31,7 +31,10 @@ namespace stemk {
 
 namespace {
 
-constexpr uint32_t kGroup = 2;  // pairs sharing one staged y record that a CTA runs concurrently
+#ifndef STEMK_GROUP
+#define STEMK_GROUP 3
+#endif
+constexpr uint32_t kGroup = STEMK_GROUP;  // pairs sharing one staged y record that a CTA runs concurrently
 
 struct FastLayout {
   uint32_t tab, yD0, yD1, yD2, yD3, yI, yC, yLev, done, rowacc, rows, row_bytes, total;
@@ -224,11 +227,38 @@ __global__ void __launch_bounds__(512, 1) stem_fast_kernel(const StemFastLaunch 
       const uint32_t xl = X.len[gx], xbc = X.bcode[gx];
       const uint32_t hqrow = wrows + 2u * L.row_bytes * r, hrow = hqrow + L.row_bytes;
       double racc = 0.0;
-      uint32_t jbeg = SM(uint32_t, L.yLev);
+      // The sweep is a chain of dependent shared-memory round trips per level (node record -> child list ->
+      // gathers -> store), and a block's latency is what bounds the kernel.  So the static part of the NEXT node
+      // this lane will own (node record, constants, first eight children) is fetched while the current level is
+      // still in flight: only gathers -> adds -> store remain on the critical path of a level.
+      uint32_t plv = 0, pj = SM(uint32_t, L.yLev) + slot;   // prefetch cursor: level, node
+      NodeI pni; pni.e4_bcode = 0; pni.deg4 = 0; pni.len = 0;
+      uint2 pc0 = make_uint2(0u, 0u), pc1 = pc0;
+      double2 pd0 = make_double2(0.0, 0.0), pd1 = pd0;
+      const uint32_t dummy2 = Ny | (Ny << 16);
+      auto fetch = [&]() {
+        while (plv < ry.nlev && pj >= SM(uint32_t, L.yLev + 4u * plv + 4u)) {
+          ++plv;
+          if (plv < ry.nlev) pj = SM(uint32_t, L.yLev + 4u * plv) + slot;
+        }
+        if (plv < ry.nlev) {
+          pni = SM(NodeI, L.yI + 8u * pj);
+          pd0 = SM(double2, L.yD0 + 16u * pj);  // {a_y, el_y}
+          pd1 = SM(double2, L.yD1 + 16u * pj);  // {s2_y, up_y}
+          const uint32_t e = L.yC + 2u * (pni.e4_bcode >> 8);
+          pc0 = SM(uint2, e);
+          pc1 = pni.deg4 > 1u ? SM(uint2, e + 8u) : make_uint2(dummy2, dummy2);
+        }
+      };
+      fetch();
       for (uint32_t ly = 0; ly < ry.nlev; ++ly) {
-        const uint32_t jend = SM(uint32_t, L.yLev + 4u * ly + 4u);
-        for (uint32_t j = jbeg + slot; j < jend; j += nslot) {
-          const NodeI ni = SM(NodeI, L.yI + 8u * j);
+        while (plv == ly) {
+          const NodeI ni = pni;
+          const uint2 c0 = pc0, c1 = pc1;
+          const double2 d0 = pd0, d1 = pd1;
+          const uint32_t j = pj;
+          pj += nslot;
+          fetch();   // next node of this lane (static data only: no hazard with this level's stores)
           const uint32_t yl = ni.len;
           if (band != 0u && yl + band < xl) {  // G1 == 0 here and below (length-monotone DAG)
             SM(double, hrow + 8u * j) = 0.0;
@@ -236,40 +266,41 @@ __global__ void __launch_bounds__(512, 1) stem_fast_kernel(const StemFastLaunch 
           }
           const uint32_t dl = xl > yl ? xl - yl : yl - xl;
           const bool in_band = (band == 0u) || (dl <= band);
-          const double2 d0 = SM(double2, L.yD0 + 16u * j);  // {a_y, el_y}
-          const double2 d1 = SM(double2, L.yD1 + 16u * j);  // {s2_y, up_y}
-          uint32_t e = L.yC + 2u * (ni.e4_bcode >> 8);
-          const uint32_t eend = e + 8u * ni.deg4;
-          double S0 = 0.0, S1 = 0.0, m = 0.0;
+          const uint32_t o0 = (c0.x & 0xffffu) * 8u, o1 = (c0.x >> 16) * 8u, o2 = (c0.y & 0xffffu) * 8u, o3 = (c0.y >> 16) * 8u;
+          const uint32_t o4 = (c1.x & 0xffffu) * 8u, o5 = (c1.x >> 16) * 8u, o6 = (c1.y & 0xffffu) * 8u, o7 = (c1.y >> 16) * 8u;
+          // all eight gathers in flight at once (lists shorter than 8 point at the all-zero dummy column)
+          const double h0 = SM(double, hrow + o0), h1 = SM(double, hrow + o1), h2 = SM(double, hrow + o2), h3 = SM(double, hrow + o3);
+          const double h4 = SM(double, hrow + o4), h5 = SM(double, hrow + o5), h6 = SM(double, hrow + o6), h7 = SM(double, hrow + o7);
+          double S = ((h0 + h1) + (h2 + h3)) + ((h4 + h5) + (h6 + h7));
+          double m = 0.0;
+          uint32_t e = L.yC + 2u * (ni.e4_bcode >> 8) + 16u;
+          const uint32_t eend = e - 16u + 8u * ni.deg4;
           if (in_band) {
-            double R0 = 0.0, R1 = 0.0;
+            const double q0 = SM(double, hqrow + o0), q1 = SM(double, hqrow + o1), q2 = SM(double, hqrow + o2), q3 = SM(double, hqrow + o3);
+            const double q4 = SM(double, hqrow + o4), q5 = SM(double, hqrow + o5), q6 = SM(double, hqrow + o6), q7 = SM(double, hqrow + o7);
+            double R = ((q0 + q1) + (q2 + q3)) + ((q4 + q5) + (q6 + q7));
 #pragma unroll 1
-            for (; e < eend; e += 8u) {
+            for (; e < eend; e += 8u) {   // more than eight inner pairs: rare
               const uint2 c4 = SM(uint2, e);
-              const uint32_t o0 = (c4.x & 0xffffu) * 8u, o1 = (c4.x >> 16) * 8u, o2 = (c4.y & 0xffffu) * 8u, o3 = (c4.y >> 16) * 8u;
-              S0 += SM(double, hrow + o0); R0 += SM(double, hqrow + o0);
-              S1 += SM(double, hrow + o1); R1 += SM(double, hqrow + o1);
-              S0 += SM(double, hrow + o2); R0 += SM(double, hqrow + o2);
-              S1 += SM(double, hrow + o3); R1 += SM(double, hqrow + o3);
+              const uint32_t p0 = (c4.x & 0xffffu) * 8u, p1 = (c4.x >> 16) * 8u, p2 = (c4.y & 0xffffu) * 8u, p3 = (c4.y >> 16) * 8u;
+              S += (SM(double, hrow + p0) + SM(double, hrow + p1)) + (SM(double, hrow + p2) + SM(double, hrow + p3));
+              R += (SM(double, hqrow + p0) + SM(double, hqrow + p1)) + (SM(double, hqrow + p2) + SM(double, hqrow + p3));
             }
             const double2 d2 = SM(double2, L.yD2 + 16u * j);  // {paths_y, bfreq_y}
             const double vs = SM(double, L.tab + 8u * (xbc * 16u + (ni.e4_bcode & 0xffu))) * xbf * d2.y;
-            m = vs * fma(d0.y, xql, d1.x * (R0 + R1));
+            m = vs * fma(d0.y, xql, d1.x * R);
             racc = fma(d2.x, m, racc);
           } else {
 #pragma unroll 1
             for (; e < eend; e += 8u) {
               const uint2 c4 = SM(uint2, e);
-              S0 += SM(double, hrow + (c4.x & 0xffffu) * 8u);
-              S1 += SM(double, hrow + (c4.x >> 16) * 8u);
-              S0 += SM(double, hrow + (c4.y & 0xffffu) * 8u);
-              S1 += SM(double, hrow + (c4.y >> 16) * 8u);
+              const uint32_t p0 = (c4.x & 0xffffu) * 8u, p1 = (c4.x >> 16) * 8u, p2 = (c4.y & 0xffffu) * 8u, p3 = (c4.y >> 16) * 8u;
+              S += (SM(double, hrow + p0) + SM(double, hrow + p1)) + (SM(double, hrow + p2) + SM(double, hrow + p3));
             }
           }
-          const double g1 = fma(d0.x, d1.x * (S0 + S1), m);
+          const double g1 = fma(d0.x, d1.x * S, m);
           SM(double, hrow + 8u * j) = d1.y * g1;
         }
-        jbeg = jend;
         __syncwarp();
       }
       // per-row path-weighted MATCH sum (lanes of one row are contiguous: reduce inside the half / full warp)
