@@ -235,8 +235,8 @@ void compile_record(const stemk_seqset_desc& s, uint32_t r, double g, RecOut* o)
       NodeI ni;
       ni.e4_bcode = ((uint32_t)o->c16.size() << 8) | o->bcode[k];
       const uint32_t c0 = o->coff[k], c1 = o->coff[k + 1];
-      for (uint32_t e = c0; e < c1; ++e) o->c16.push_back((uint16_t)o->cidx[e]);
-      while (o->c16.size() % 4) o->c16.push_back((uint16_t)N);   // dummy column: reads 0.0
+      for (uint32_t e = c0; e < c1; ++e) o->c16.push_back((uint16_t)(8u * o->cidx[e]));   // byte offsets into a row
+      while (o->c16.size() % 4) o->c16.push_back((uint16_t)(8u * N));   // dummy column: reads 0.0
       ni.deg4 = (uint16_t)((o->c16.size() - (ni.e4_bcode >> 8)) / 4);
       ni.len = (uint16_t)o->len[k];
       o->nodei[k] = ni;

@@ -68,9 +68,27 @@ __device__ __forceinline__ double warp_sum_all(double v) {
   return v;
 }
 
-__device__ __forceinline__ uint32_t ld_flag_f(const unsigned char* sm, uint32_t byteoff) {
-  return *reinterpret_cast<const volatile uint32_t*>(sm + byteoff);
+__device__ __forceinline__ uint32_t ld_flag_f(uint32_t addr) {
+  uint32_t v; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v;
 }
+
+// Shared-memory accessors on raw 32-bit shared addresses.  Going through generic pointers makes the compiler rebuild
+// the shared window base (S2R SR_CgaCtaId + LEA) next to the accesses of the inner loops; these keep it to one
+// cvta per kernel.  All of them are volatile: they keep their program order around __syncwarp / __syncthreads.
+__device__ __forceinline__ double lds_f64(uint32_t a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
+__device__ __forceinline__ double2 lds_v2f64(uint32_t a) { double2 v; asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint2 lds_v2u32(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ NodeI lds_nodei(uint32_t a) {
+  const uint2 v = lds_v2u32(a);
+  NodeI n; n.e4_bcode = v.x; n.deg4 = (uint16_t)(v.y & 0xffffu); n.len = (uint16_t)(v.y >> 16);
+  return n;
+}
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ void sts_v2f64(uint32_t a, double2 v) { asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v.x), "d"(v.y) : "memory"); }
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_v2u32(uint32_t a, uint2 v) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(v.x), "r"(v.y) : "memory"); }
+__device__ __forceinline__ void sts_nodei(uint32_t a, NodeI n) { sts_v2u32(a, make_uint2(n.e4_bcode, (uint32_t)n.deg4 | ((uint32_t)n.len << 16))); }
 
 struct PairSlot {        // one pair of the group in flight
   uint32_t k;            // pair number (index into xi / yi / out)
@@ -85,11 +103,11 @@ __global__ void __launch_bounds__(512, 1) stem_fast_kernel(const StemFastLaunch 
   __shared__ PairSlot s_slot[kGroup];
   const uint32_t nwarps = blockDim.x >> 5;
   const FastLayout L = fast_layout(nwarps, P.nx_cap, P.ny_cap, P.e4_cap, P.lev_cap);
-#define SM(T, byteoff) (*reinterpret_cast<T*>(sm + (byteoff)))
+  const uint32_t sb = (uint32_t)__cvta_generic_to_shared(sm);  // raw 32-bit shared addresses: LDS/STS [reg+imm]
 
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const uint32_t band = P.len_band;
-  for (uint32_t t = tid; t < 256; t += blockDim.x) SM(double, L.tab + 8 * t) = P.pair_tab[t];
+  for (uint32_t t = tid; t < 256; t += blockDim.x) sts_f64(sb + (L.tab + 8 * t), P.pair_tab[t]);
   double* __restrict__ slab = P.scratch + (size_t)blockIdx.x * P.scratch_stride;
   const unsigned long long slot_stride = P.scratch_stride / kGroup;
   const SetView& X = P.X;
@@ -137,20 +155,20 @@ __global__ void __launch_bounds__(512, 1) stem_fast_kernel(const StemFastLaunch 
     // ---- stage the y record, clear the row flags
     for (uint32_t j = tid; j < Ny; j += blockDim.x) {
       const uint32_t gy = ry.node0 + j;
-      SM(double2, L.yD0 + 16 * j) = make_double2(Y.a[gy], Y.el[gy]);
-      SM(double2, L.yD1 + 16 * j) = make_double2(Y.s2[gy], Y.up[gy]);
-      SM(double2, L.yD2 + 16 * j) = make_double2(Y.paths[gy], Y.bfreq[gy]);
-      SM(double, L.yD3 + 8 * j) = Y.dn[gy];
-      SM(NodeI, L.yI + 8 * j) = Y.nodei[gy];
+      sts_v2f64(sb + (L.yD0 + 16 * j), make_double2(Y.a[gy], Y.el[gy]));
+      sts_v2f64(sb + (L.yD1 + 16 * j), make_double2(Y.s2[gy], Y.up[gy]));
+      sts_v2f64(sb + (L.yD2 + 16 * j), make_double2(Y.paths[gy], Y.bfreq[gy]));
+      sts_f64(sb + (L.yD3 + 8 * j), Y.dn[gy]);
+      sts_nodei(sb + (L.yI + 8 * j), Y.nodei[gy]);
     }
     {
       const uint2* __restrict__ src = reinterpret_cast<const uint2*>(Y.c16 + ry.c16_0);  // c16_0 is a multiple of 4
-      for (uint32_t e = tid; e < ry.e4 / 4u; e += blockDim.x) SM(uint2, L.yC + 8 * e) = src[e];
+      for (uint32_t e = tid; e < ry.e4 / 4u; e += blockDim.x) sts_v2u32(sb + (L.yC + 8 * e), src[e]);
     }
-    for (uint32_t l = tid; l <= ry.nlev; l += blockDim.x) SM(uint32_t, L.yLev + 4 * l) = Y.lev_off[ry.lev0 + l];
-    for (uint32_t i = tid; i < g * P.nx_cap; i += blockDim.x) SM(uint32_t, L.done + 4 * i) = 0u;
+    for (uint32_t l = tid; l <= ry.nlev; l += blockDim.x) sts_u32(sb + (L.yLev + 4 * l), Y.lev_off[ry.lev0 + l]);
+    for (uint32_t i = tid; i < g * P.nx_cap; i += blockDim.x) sts_u32(sb + (L.done + 4 * i), 0u);
     // the dummy column of every row of this warp
-    if (lane < 2u * kFastRows) SM(double, wrows + L.row_bytes * lane + 8u * Ny) = 0.0;
+    if (lane < 2u * kFastRows) sts_f64(sb + (wrows + L.row_bytes * lane + 8u * Ny), 0.0);
     __syncthreads();
 
     for (;;) {
@@ -182,7 +200,9 @@ __global__ void __launch_bounds__(512, 1) stem_fast_kernel(const StemFastLaunch 
           if (lane < ne) {
             const uint32_t c = X.cidx[eb + lane];
             off_l = c * NYS;
-            while (ld_flag_f(sm, done + 4u * c) == 0u) __nanosleep(32);  // wait until that row is published
+            #ifndef ABL_NO_WAIT
+            while (ld_flag_f(sb + done + 4u * c) == 0u) __nanosleep(32);
+#endif  // wait until that row is published
           }
           __syncwarp();
           __threadfence_block();  // acquire: the G0 rows behind the flags just seen
@@ -190,28 +210,32 @@ __global__ void __launch_bounds__(512, 1) stem_fast_kernel(const StemFastLaunch 
             const uint32_t j = jb + lane;
             const bool v0 = j < Ny, v1 = j + 32u < Ny, v2 = j + 64u < Ny, v3 = j + 96u < Ny;
             const bool more = eb != e0;
-            double q0 = (v0 && more) ? SM(double, hq + 8u * j) : 0.0;
-            double q1 = (v1 && more) ? SM(double, hq + 8u * (j + 32u)) : 0.0;
-            double q2 = (v2 && more) ? SM(double, hq + 8u * (j + 64u)) : 0.0;
-            double q3 = (v3 && more) ? SM(double, hq + 8u * (j + 96u)) : 0.0;
+            double q0 = (v0 && more) ? lds_f64(sb + (hq + 8u * j)) : 0.0;
+            double q1 = (v1 && more) ? lds_f64(sb + (hq + 8u * (j + 32u))) : 0.0;
+            double q2 = (v2 && more) ? lds_f64(sb + (hq + 8u * (j + 64u))) : 0.0;
+            double q3 = (v3 && more) ? lds_f64(sb + (hq + 8u * (j + 96u))) : 0.0;
 #pragma unroll 4
             for (uint32_t tt = 0; tt < ne; ++tt) {
               const double* __restrict__ src = G0 + __shfl_sync(0xffffffffu, off_l, tt) + j;
+#ifndef ABL_NO_A
               if (v0) q0 += __ldcg(src);
               if (v1) q1 += __ldcg(src + 32);
               if (v2) q2 += __ldcg(src + 64);
               if (v3) q3 += __ldcg(src + 96);
+#else
+              q0 += (double)(size_t)src * 1e-300;
+#endif
             }
             if (last) {  // scale: HQ = up_y(j) * (s2_x * sum)
-              if (v0) q0 = SM(double2, L.yD1 + 16u * j).y * (xs2 * q0);
-              if (v1) q1 = SM(double2, L.yD1 + 16u * (j + 32u)).y * (xs2 * q1);
-              if (v2) q2 = SM(double2, L.yD1 + 16u * (j + 64u)).y * (xs2 * q2);
-              if (v3) q3 = SM(double2, L.yD1 + 16u * (j + 96u)).y * (xs2 * q3);
+              if (v0) q0 = lds_v2f64(sb + (L.yD1 + 16u * j)).y * (xs2 * q0);
+              if (v1) q1 = lds_v2f64(sb + (L.yD1 + 16u * (j + 32u))).y * (xs2 * q1);
+              if (v2) q2 = lds_v2f64(sb + (L.yD1 + 16u * (j + 64u))).y * (xs2 * q2);
+              if (v3) q3 = lds_v2f64(sb + (L.yD1 + 16u * (j + 96u))).y * (xs2 * q3);
             }
-            if (v0) SM(double, hq + 8u * j) = q0;
-            if (v1) SM(double, hq + 8u * (j + 32u)) = q1;
-            if (v2) SM(double, hq + 8u * (j + 64u)) = q2;
-            if (v3) SM(double, hq + 8u * (j + 96u)) = q3;
+            if (v0) sts_f64(sb + (hq + 8u * j), q0);
+            if (v1) sts_f64(sb + (hq + 8u * (j + 32u)), q1);
+            if (v2) sts_f64(sb + (hq + 8u * (j + 64u)), q2);
+            if (v3) sts_f64(sb + (hq + 8u * (j + 96u)), q3);
           }
           if (e1 == e0) break;
         }
@@ -227,80 +251,56 @@ __global__ void __launch_bounds__(512, 1) stem_fast_kernel(const StemFastLaunch 
       const uint32_t xl = X.len[gx], xbc = X.bcode[gx];
       const uint32_t hqrow = wrows + 2u * L.row_bytes * r, hrow = hqrow + L.row_bytes;
       double racc = 0.0;
-      // The sweep is a chain of dependent shared-memory round trips per level (node record -> child list ->
-      // gathers -> store), and a block's latency is what bounds the kernel.  So the static part of the NEXT node
-      // this lane will own (node record, constants, first eight children) is fetched while the current level is
-      // still in flight: only gathers -> adds -> store remain on the critical path of a level.
-      uint32_t plv = 0, pj = SM(uint32_t, L.yLev) + slot;   // prefetch cursor: level, node
-      NodeI pni; pni.e4_bcode = 0; pni.deg4 = 0; pni.len = 0;
-      uint2 pc0 = make_uint2(0u, 0u), pc1 = pc0;
-      double2 pd0 = make_double2(0.0, 0.0), pd1 = pd0;
-      const uint32_t dummy2 = Ny | (Ny << 16);
-      auto fetch = [&]() {
-        while (plv < ry.nlev && pj >= SM(uint32_t, L.yLev + 4u * plv + 4u)) {
-          ++plv;
-          if (plv < ry.nlev) pj = SM(uint32_t, L.yLev + 4u * plv) + slot;
-        }
-        if (plv < ry.nlev) {
-          pni = SM(NodeI, L.yI + 8u * pj);
-          pd0 = SM(double2, L.yD0 + 16u * pj);  // {a_y, el_y}
-          pd1 = SM(double2, L.yD1 + 16u * pj);  // {s2_y, up_y}
-          const uint32_t e = L.yC + 2u * (pni.e4_bcode >> 8);
-          pc0 = SM(uint2, e);
-          pc1 = pni.deg4 > 1u ? SM(uint2, e + 8u) : make_uint2(dummy2, dummy2);
-        }
-      };
-      fetch();
+      uint32_t jbeg = lds_u32(sb + (L.yLev));
+#ifdef ABL_NO_B
+      for (uint32_t ly = 0; ly < 1; ++ly) {
+#else
       for (uint32_t ly = 0; ly < ry.nlev; ++ly) {
-        while (plv == ly) {
-          const NodeI ni = pni;
-          const uint2 c0 = pc0, c1 = pc1;
-          const double2 d0 = pd0, d1 = pd1;
-          const uint32_t j = pj;
-          pj += nslot;
-          fetch();   // next node of this lane (static data only: no hazard with this level's stores)
+#endif
+        const uint32_t jend = lds_u32(sb + (L.yLev + 4u * ly + 4u));
+        for (uint32_t j = jbeg + slot; j < jend; j += nslot) {
+          const NodeI ni = lds_nodei(sb + (L.yI + 8u * j));
           const uint32_t yl = ni.len;
           if (band != 0u && yl + band < xl) {  // G1 == 0 here and below (length-monotone DAG)
-            SM(double, hrow + 8u * j) = 0.0;
+            sts_f64(sb + (hrow + 8u * j), 0.0);
             continue;
           }
           const uint32_t dl = xl > yl ? xl - yl : yl - xl;
           const bool in_band = (band == 0u) || (dl <= band);
-          const uint32_t o0 = (c0.x & 0xffffu) * 8u, o1 = (c0.x >> 16) * 8u, o2 = (c0.y & 0xffffu) * 8u, o3 = (c0.y >> 16) * 8u;
-          const uint32_t o4 = (c1.x & 0xffffu) * 8u, o5 = (c1.x >> 16) * 8u, o6 = (c1.y & 0xffffu) * 8u, o7 = (c1.y >> 16) * 8u;
-          // all eight gathers in flight at once (lists shorter than 8 point at the all-zero dummy column)
-          const double h0 = SM(double, hrow + o0), h1 = SM(double, hrow + o1), h2 = SM(double, hrow + o2), h3 = SM(double, hrow + o3);
-          const double h4 = SM(double, hrow + o4), h5 = SM(double, hrow + o5), h6 = SM(double, hrow + o6), h7 = SM(double, hrow + o7);
-          double S = ((h0 + h1) + (h2 + h3)) + ((h4 + h5) + (h6 + h7));
-          double m = 0.0;
-          uint32_t e = L.yC + 2u * (ni.e4_bcode >> 8) + 16u;
-          const uint32_t eend = e - 16u + 8u * ni.deg4;
+          const double2 d0 = lds_v2f64(sb + (L.yD0 + 16u * j));  // {a_y, el_y}
+          const double2 d1 = lds_v2f64(sb + (L.yD1 + 16u * j));  // {s2_y, up_y}
+          uint32_t e = L.yC + 2u * (ni.e4_bcode >> 8);
+          const uint32_t eend = e + 8u * ni.deg4;
+          double S0 = 0.0, S1 = 0.0, m = 0.0;
           if (in_band) {
-            const double q0 = SM(double, hqrow + o0), q1 = SM(double, hqrow + o1), q2 = SM(double, hqrow + o2), q3 = SM(double, hqrow + o3);
-            const double q4 = SM(double, hqrow + o4), q5 = SM(double, hqrow + o5), q6 = SM(double, hqrow + o6), q7 = SM(double, hqrow + o7);
-            double R = ((q0 + q1) + (q2 + q3)) + ((q4 + q5) + (q6 + q7));
+            double R0 = 0.0, R1 = 0.0;
 #pragma unroll 1
-            for (; e < eend; e += 8u) {   // more than eight inner pairs: rare
-              const uint2 c4 = SM(uint2, e);
-              const uint32_t p0 = (c4.x & 0xffffu) * 8u, p1 = (c4.x >> 16) * 8u, p2 = (c4.y & 0xffffu) * 8u, p3 = (c4.y >> 16) * 8u;
-              S += (SM(double, hrow + p0) + SM(double, hrow + p1)) + (SM(double, hrow + p2) + SM(double, hrow + p3));
-              R += (SM(double, hqrow + p0) + SM(double, hqrow + p1)) + (SM(double, hqrow + p2) + SM(double, hqrow + p3));
+            for (; e < eend; e += 8u) {
+              const uint2 c4 = lds_v2u32(sb + (e));
+              const uint32_t o0 = c4.x & 0xffffu, o1 = c4.x >> 16, o2 = c4.y & 0xffffu, o3 = c4.y >> 16;
+              S0 += lds_f64(sb + (hrow + o0)); R0 += lds_f64(sb + (hqrow + o0));
+              S1 += lds_f64(sb + (hrow + o1)); R1 += lds_f64(sb + (hqrow + o1));
+              S0 += lds_f64(sb + (hrow + o2)); R0 += lds_f64(sb + (hqrow + o2));
+              S1 += lds_f64(sb + (hrow + o3)); R1 += lds_f64(sb + (hqrow + o3));
             }
-            const double2 d2 = SM(double2, L.yD2 + 16u * j);  // {paths_y, bfreq_y}
-            const double vs = SM(double, L.tab + 8u * (xbc * 16u + (ni.e4_bcode & 0xffu))) * xbf * d2.y;
-            m = vs * fma(d0.y, xql, d1.x * R);
+            const double2 d2 = lds_v2f64(sb + (L.yD2 + 16u * j));  // {paths_y, bfreq_y}
+            const double vs = lds_f64(sb + (L.tab + 8u * (xbc * 16u + (ni.e4_bcode & 0xffu)))) * xbf * d2.y;
+            m = vs * fma(d0.y, xql, d1.x * (R0 + R1));
             racc = fma(d2.x, m, racc);
           } else {
 #pragma unroll 1
             for (; e < eend; e += 8u) {
-              const uint2 c4 = SM(uint2, e);
-              const uint32_t p0 = (c4.x & 0xffffu) * 8u, p1 = (c4.x >> 16) * 8u, p2 = (c4.y & 0xffffu) * 8u, p3 = (c4.y >> 16) * 8u;
-              S += (SM(double, hrow + p0) + SM(double, hrow + p1)) + (SM(double, hrow + p2) + SM(double, hrow + p3));
+              const uint2 c4 = lds_v2u32(sb + (e));
+              S0 += lds_f64(sb + hrow + (c4.x & 0xffffu));
+              S1 += lds_f64(sb + hrow + (c4.x >> 16));
+              S0 += lds_f64(sb + hrow + (c4.y & 0xffffu));
+              S1 += lds_f64(sb + hrow + (c4.y >> 16));
             }
           }
-          const double g1 = fma(d0.x, d1.x * S, m);
-          SM(double, hrow + 8u * j) = d1.y * g1;
+          const double g1 = fma(d0.x, d1.x * (S0 + S1), m);
+          sts_f64(sb + (hrow + 8u * j), d1.y * g1);
         }
+        jbeg = jend;
         __syncwarp();
       }
       // per-row path-weighted MATCH sum (lanes of one row are contiguous: reduce inside the half / full warp)
@@ -308,10 +308,10 @@ __global__ void __launch_bounds__(512, 1) stem_fast_kernel(const StemFastLaunch 
       if (cnt == 2u) {
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) racc += __shfl_xor_sync(0xffffffffu, racc, o);
-        if ((lane & 15u) == 0u) SM(double, racc_at) = X.paths[gx] * racc;
+        if ((lane & 15u) == 0u) sts_f64(sb + (racc_at), X.paths[gx] * racc);
       } else {
         racc = warp_sum_all(racc);
-        if (lane == 0u) SM(double, racc_at) = X.paths[gx] * racc;
+        if (lane == 0u) sts_f64(sb + (racc_at), X.paths[gx] * racc);
       }
 
       // ---- phase C: finished rows G0s(i,:) = up_x(i) * dn_y * (H + a_x*HQ), then publish them
@@ -320,12 +320,16 @@ __global__ void __launch_bounds__(512, 1) stem_fast_kernel(const StemFastLaunch 
         const uint32_t hq2 = wrows + 2u * L.row_bytes * rr, h2 = hq2 + L.row_bytes;
         const double xa2 = X.a[ps.node0 + i], xup = X.up[ps.node0 + i];
         double* __restrict__ g0row = G0 + (size_t)i * NYS;
+#ifdef ABL_NO_C
+        for (uint32_t j = lane; j < 32u; j += 32u)
+#else
         for (uint32_t j = lane; j < Ny; j += 32u)
-          g0row[j] = xup * (SM(double, L.yD3 + 8u * j) * fma(xa2, SM(double, hq2 + 8u * j), SM(double, h2 + 8u * j)));
+#endif
+          g0row[j] = xup * (lds_f64(sb + (L.yD3 + 8u * j)) * fma(xa2, lds_f64(sb + (hq2 + 8u * j)), lds_f64(sb + (h2 + 8u * j))));
       }
       __threadfence_block();
       __syncwarp();
-      if (lane < cnt) *reinterpret_cast<volatile uint32_t*>(sm + done + 4u * (i0 + lane)) = 1u;
+      if (lane < cnt) asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(sb + done + 4u * (i0 + lane)), "r"(1u) : "memory");
     }
 
     // ---- fixed-order sum of the per-row slots, one warp per pair of the group
@@ -333,12 +337,11 @@ __global__ void __launch_bounds__(512, 1) stem_fast_kernel(const StemFastLaunch 
     if (warp < g) {
       const PairSlot ps = s_slot[warp];
       double t = 0.0;
-      for (uint32_t i = lane; i < ps.N; i += 32u) t += SM(double, L.rowacc + 8u * (warp * P.nx_cap + i));
+      for (uint32_t i = lane; i < ps.N; i += 32u) t += lds_f64(sb + (L.rowacc + 8u * (warp * P.nx_cap + i)));
       t = warp_sum_all(t);
       if (lane == 0) P.out[ps.k] = t + ps.plr * (double)ry.lr;
     }
   }
-#undef SM
 }
 
 // ---- pair classification: which kernel / size bucket runs a pair -----------------------------------------

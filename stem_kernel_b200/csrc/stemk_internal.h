@@ -70,7 +70,7 @@ struct SetView {
   const double* dn;      // g^(len - B)
   const double* s2;      // g^(len - 2 - B)
   const NodeI* nodei;
-  const uint16_t* c16;   // padded child lists, record-local node numbers, N = the all-zero dummy column
+  const uint16_t* c16;   // padded child lists as byte offsets into a row (8 * record-local node number), 8N = the all-zero dummy column
   const uint32_t* blk;   // row blocks: first row | count << 16
   // general base-pair profiles (alignments / IUPAC)
   const uint32_t* boff;  // [sum(N+1)]
