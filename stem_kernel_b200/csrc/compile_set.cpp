@@ -309,6 +309,8 @@ std::string compile_set(const stemk_seqset_desc& s, double g, int n_threads, Com
     c.n_edges_all.push_back(o.e_all);
     c.max_level_rows.push_back(o.max_rows);
     if (o.n_all) c.has_dag = true;
+    if (h.flags & REC_HAS_WEIGHT) ++c.n_weighted;
+    if (h.flags & REC_SIMPLE_COLS) ++c.n_simple_cols;
     c.max_N = std::max(c.max_N, h.N);
     c.max_L = std::max(c.max_L, h.L);
     c.max_E = std::max(c.max_E, (uint32_t)o.cidx.size());

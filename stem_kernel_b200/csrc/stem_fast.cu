@@ -206,6 +206,15 @@ __global__ void __launch_bounds__(512, 1) stem_fast_kernel(const StemFastLaunch 
           }
           __syncwarp();
           __threadfence_block();  // acquire: the G0 rows behind the flags just seen
+#ifndef STEMK_NO_PREFETCH
+          // The slabs of all CTAs together are several times the L2, so about half of these rows come from
+          // DRAM: ask for every 128-byte line of every child row at once instead of discovering the misses
+          // sixteen loads at a time.
+          for (uint32_t tt = 0; tt < ne; ++tt) {
+            const double* __restrict__ src = G0 + __shfl_sync(0xffffffffu, off_l, tt);
+            for (uint32_t ln = lane * 16u; ln < Ny; ln += 512u) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + ln));
+          }
+#endif
           for (uint32_t jb = 0; jb < Ny; jb += 128u) {  // uniform trip count: the shuffles below need every lane
             const uint32_t j = jb + lane;
             const bool v0 = j < Ny, v1 = j + 32u < Ny, v2 = j + 64u < Ny, v3 = j + 96u < Ny;

@@ -95,6 +95,7 @@ struct CompiledSet {
   std::vector<uint16_t> c16;
   std::vector<uint32_t> blk;
   uint32_t max_E4 = 0, max_fastN = 0, n_fast = 0;  // over fast-eligible records
+  uint32_t n_weighted = 0, n_simple_cols = 0;      // records with per-column weights / with one-hot-or-gap columns only
   // host-only statistics for the work model and the scheduler
   std::vector<uint32_t> n_nodes_all;  // nodes incl. leaves (reference's #V)
   std::vector<uint32_t> n_edges_all;  // edges incl. leaf edges (reference's #E)

@@ -1,4 +1,4 @@
-// stem_kernel_b200/csrc/string_kernel.cu -- gap-weighted string kernels, one warp per pair.
+// stem_kernel_b200/csrc/string_kernel.cu -- gap-weighted string kernels, a group of lanes per pair.
 //
 // Replaces StringKernel<V,D>::operator() of stem_kernel_lite/string_kernel.cpp:66-132 (profile
 // columns, RIBOSUM or match/mismatch substitution, optional per-column weights) and the naive
@@ -8,10 +8,12 @@
 //     v       = G0(i-1,j-1) * wx(i) * wy(j) * s(x_i,y_j)         (naive: G0(i-1,j-1)*g^2 if x_i==y_j else 0)
 //     G1(i,j) = v + g * G1(i,j-1)          G0(i,j) = G1(i,j) + g * G0(i-1,j)
 //     K0(Lx,Ly) = 1 + sum_ij v(i,j)        (the K tables of the reference only add the v's up)
-// Mapping: a lane owns CW consecutive columns and keeps their G0 in registers; lane l works on
-// row s-l at step s (skewed wavefront), the two values crossing a lane boundary travel by one
-// shuffle pair per step.  Sequences wider than 32*CW columns are swept tile by tile with the last
-// column of a tile carried through a small per-warp global buffer.
+// Mapping: TP lanes share a pair; a lane owns CW consecutive columns and keeps their G0 in registers; lane l of
+// the group works on row s-l at step s (skewed wavefront), the two values crossing a lane boundary travel by one
+// shuffle pair per step.  Few lanes with many columns each (4 x 25 for 100-nt sequences) keep the wavefront's
+// fill/drain and the shuffles small against the cells, and a warp runs 32/TP pairs side by side.  Sequences wider
+// than TP*CW columns are swept tile by tile with the last column of a tile carried through a small per-group
+// global buffer.
 #include "kernels.cuh"
 
 namespace stemk {
@@ -22,7 +24,7 @@ constexpr int kStrWarps = 4;
 
 // string_kernel.cpp:46-64: expectation of the substitution score over two profile columns,
 // with the reference's float accumulation of the normaliser
-__device__ __forceinline__ double subst_general(const double* __restrict__ st, const float* __restrict__ x,
+__device__ __noinline__ double subst_general(const double* __restrict__ st, const float* __restrict__ x,
                                                 const float* __restrict__ y) {
   double v_c = 0.0;
   float n = 0.0f;
@@ -39,73 +41,90 @@ __device__ __forceinline__ double subst_general(const double* __restrict__ st, c
   return n == 0.0f ? 1.0 : v_c / (double)n;
 }
 
-template <int CW>
-__global__ void __launch_bounds__(kStrWarps * 32) string_pairs_kernel(const StringLaunch P) {
-  __shared__ double st[16];
-  if (threadIdx.x < 16) st[threadIdx.x] = P.subst[threadIdx.x];
+// CW columns per lane, TP lanes per pair (a power of two): a warp runs 32/TP pairs side by side.
+// MODE: 0 one-hot / gap columns, no weights; 1 the same with per-column weights on every pair; 2 exact-match kernel
+// on raw characters; 3 anything (profile columns, weights decided per pair).
+enum { STR_PLAIN = 0, STR_WEIGHTED = 1, STR_NAIVE_MODE = 2, STR_GENERAL = 3 };
+
+template <int CW, int TP, int MODE>
+__global__ void __launch_bounds__(kStrWarps * 32, 3) string_pairs_kernel(const StringLaunch P) {
+  constexpr int GPW = 32 / TP;           // pairs (lane groups) per warp
+  __shared__ double st5[25];             // substitution scores with a fifth code: an all-gap column scores 1
+  extern __shared__ double gpow[];       // gap^k by repeated multiplication, k = 0..P.pow_cap (string_kernel.cpp:85-92)
+  if (threadIdx.x < 25) {
+    const int a = threadIdx.x / 5, b = threadIdx.x % 5;
+    st5[threadIdx.x] = (a < 4 && b < 4) ? P.subst[a * 4 + b] : 1.0;
+  }
+  if (threadIdx.x == 32) {
+    double p = 1.0;
+    for (uint32_t k = 0; k <= P.pow_cap; ++k) { gpow[k] = p; p *= P.gap; }
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const unsigned warp_global = blockIdx.x * kStrWarps + (threadIdx.x >> 5);
-  double* __restrict__ carry_g1 = P.carry + (size_t)warp_global * P.carry_stride;
+  const int sub = lane % TP, grp = lane / TP;
+  const unsigned group_global = (blockIdx.x * kStrWarps + (threadIdx.x >> 5)) * GPW + grp;
+  double* __restrict__ carry_g1 = P.carry + (size_t)group_global * P.carry_stride;
   double* __restrict__ carry_g0 = carry_g1 + P.carry_stride / 2;
   const SetView& X = P.X;
   const SetView& Y = P.Y;
   const double gap = P.gap, g2 = P.gap * P.gap;
 
   for (;;) {
-    unsigned long long k = 0;
-    if (lane == 0) k = atomicAdd(P.counter, 1ull);
-    k = __shfl_sync(0xffffffffu, k, 0);
-    if (k >= P.n_pairs) break;
-    const RecDev rx = X.rec[P.xi[k]];
-    const RecDev ry = Y.rec[P.yi[k]];
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(P.counter, (unsigned long long)GPW);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= P.n_pairs) break;
+    const unsigned long long k = base + grp;
+    const bool valid = k < P.n_pairs;
+    RecDev rx, ry;
+    rx.L = ry.L = 0; rx.flags = ry.flags = 0; rx.col0 = ry.col0 = 0;
+    if (valid) { rx = X.rec[P.xi[k]]; ry = Y.rec[P.yi[k]]; }
     const int Lx = (int)rx.L, Ly = (int)ry.L;
-    if (Lx == 0 || Ly == 0) {
-      if (lane == 0) P.out[k] = 1.0;
-      continue;
-    }
-    const bool use_w = (rx.flags & REC_HAS_WEIGHT) && (ry.flags & REC_HAS_WEIGHT) && !P.naive;
-    const uint8_t* __restrict__ xcode = (P.naive ? X.text : X.ccode) + rx.col0;
-    const uint8_t* __restrict__ ycode = (P.naive ? Y.text : Y.ccode) + ry.col0;
+    const bool use_w = MODE == STR_WEIGHTED || (MODE == STR_GENERAL && (rx.flags & REC_HAS_WEIGHT) && (ry.flags & REC_HAS_WEIGHT));
+    const uint8_t* __restrict__ xcode = (MODE == STR_NAIVE_MODE ? X.text : X.ccode) + rx.col0;
+    const uint8_t* __restrict__ ycode = (MODE == STR_NAIVE_MODE ? Y.text : Y.ccode) + ry.col0;
     const double* __restrict__ xw = X.cw + rx.col0;
     const double* __restrict__ yw = Y.cw + ry.col0;
     const float* __restrict__ xprof = X.prof + (size_t)4 * rx.col0;
     const float* __restrict__ yprof = Y.prof + (size_t)4 * ry.col0;
     double acc = 0.0;
 
-    const int ntiles = (Ly + 32 * CW - 1) / (32 * CW);
-    for (int tile = 0; tile < ntiles; ++tile) {
-      const int jb = tile * 32 * CW + lane * CW;  // 0-based index of this lane's first column
-      // top boundary G0(0,j) = g^j by repeated multiplication (string_kernel.cpp:85-88)
-      double g0[CW], wy[CW];
-      int yc[CW];
-      {
-        double p = 1.0;
-        for (int t = 0; t < jb; ++t) p *= gap;
+    // the groups of a warp run in lockstep: trip counts are the warp's maxima
+    int nsteps = Lx + TP - 1, ntiles = (Ly + TP * CW - 1) / (TP * CW);
+    if (Lx == 0 || Ly == 0) { nsteps = 0; ntiles = 0; }
+    int nsteps_w = nsteps, ntiles_w = ntiles;
 #pragma unroll
-        for (int c = 0; c < CW; ++c) {
-          p *= gap;  // g^(jb+c+1): column index is 1-based in the table
-          g0[c] = p;
-          const int j = jb + c;
-          yc[c] = j < Ly ? (int)ycode[j] : 4;
-          wy[c] = (j < Ly && use_w) ? yw[j] : 1.0;
-        }
+    for (int o = 16; o > 0; o >>= 1) {
+      nsteps_w = max(nsteps_w, __shfl_xor_sync(0xffffffffu, nsteps_w, o));
+      ntiles_w = max(ntiles_w, __shfl_xor_sync(0xffffffffu, ntiles_w, o));
+    }
+
+    for (int tile = 0; tile < ntiles_w; ++tile) {
+      const bool tile_on = tile < ntiles;
+      const int jb = tile * TP * CW + sub * CW;  // 0-based index of this lane's first column
+      // top boundary G0(0,j) = g^j; columns past the end of y behave like all-zero columns that are never summed
+      double g0[CW];
+      double wy[(MODE == STR_WEIGHTED || MODE == STR_GENERAL) ? CW : 1];
+      int yc[CW];
+#pragma unroll
+      for (int c = 0; c < CW; ++c) {
+        const int j = jb + c;
+        const bool in = tile_on && j < Ly;
+        g0[c] = in ? gpow[j + 1] : 0.0;   // column index is 1-based in the table
+        yc[c] = in ? (int)ycode[j] : 4;
+        if (MODE == STR_WEIGHTED || MODE == STR_GENERAL) wy[c] = (in && use_w) ? yw[j] : 1.0;
       }
       // value a lane hands to its right neighbour after finishing a row
       double send_g1 = 0.0, send_diag = 0.0;
-      // left boundary for lane 0: column 0 (tile 0) or the carried column (later tiles)
-      double left_pow = 1.0;  // g^(i-1), only meaningful for tile 0 / lane 0
-      const int nsteps = Lx + 31;
-      for (int s = 0; s < nsteps; ++s) {
-        double in_g1 = __shfl_up_sync(0xffffffffu, send_g1, 1);
-        double in_diag = __shfl_up_sync(0xffffffffu, send_diag, 1);
-        const int i = s - lane;  // 0-based row of x
-        if (i < 0 || i >= Lx) continue;
-        if (lane == 0) {
+      for (int s = 0; s < nsteps_w; ++s) {
+        double in_g1 = __shfl_up_sync(0xffffffffu, send_g1, 1, TP);
+        double in_diag = __shfl_up_sync(0xffffffffu, send_diag, 1, TP);
+        const int i = s - sub;  // 0-based row of x
+        if (!tile_on || i < 0 || i >= Lx) continue;
+        if (sub == 0) {
           if (tile == 0) {
             in_g1 = 0.0;        // G1(i,0) = 0
-            in_diag = left_pow; // G0(i-1,0) = g^(i-1)
-            left_pow *= gap;
+            in_diag = gpow[i];  // G0(i-1,0) = g^(i-1): i is the 0-based row
           } else {
             in_g1 = carry_g1[i + 1];
             in_diag = carry_g0[i];
@@ -119,15 +138,15 @@ __global__ void __launch_bounds__(kStrWarps * 32) string_pairs_kernel(const Stri
           const double old = g0[c];
           if (jb + c < Ly) {
             double v;
-            if (P.naive) {
+            if (MODE == STR_NAIVE_MODE) {
               v = (xc == yc[c]) ? diag * g2 : 0.0;
             } else {
               v = diag;
-              if (use_w) v = v * wx * wy[c];
+              if (MODE == STR_WEIGHTED) v = v * wx * wy[c];
+              if (MODE == STR_GENERAL && use_w) v = v * wx * wy[c];
               double sc;
-              if (xc < 4 && yc[c] < 4) sc = st[xc * 4 + yc[c]];
-              else if (xc == 4 || yc[c] == 4) sc = 1.0;
-              else sc = subst_general(st, xprof + 4 * i, yprof + 4 * (jb + c));
+              if (MODE != STR_GENERAL || (xc < 5 && yc[c] < 5)) sc = st5[xc * 5 + yc[c]];
+              else sc = subst_general(P.subst, xprof + 4 * i, yprof + 4 * (jb + c));
               v *= sc;
             }
             acc += v;
@@ -139,24 +158,20 @@ __global__ void __launch_bounds__(kStrWarps * 32) string_pairs_kernel(const Stri
         send_g1 = g1;
         send_diag = diag;
         // the lane that owns the tile's last column leaves it behind for the next tile
-        if (lane == 31 && tile + 1 < ntiles) {
+        if (sub == TP - 1 && tile + 1 < ntiles) {
           carry_g1[i + 1] = g1;
           carry_g0[i + 1] = g0[CW - 1];
         }
       }
-      if (tile + 1 < ntiles) {
+      if (tile + 1 < ntiles_w) {
         // G0(0, last column of this tile) for the next tile's first diagonal
-        if (lane == 31) {
-          double p = 1.0;
-          for (int t = 0; t < jb + CW; ++t) p *= gap;
-          carry_g0[0] = p;
-        }
+        if (sub == TP - 1 && tile + 1 < ntiles) carry_g0[0] = gpow[jb + CW];
         __syncwarp();
       }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
-    if (lane == 0) P.out[k] = 1.0 + acc;
+    for (int o = TP / 2; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, TP);
+    if (sub == 0 && valid) P.out[k] = 1.0 + acc;
   }
 }
 
@@ -206,13 +221,36 @@ __global__ void normalize_square_kernel(double* __restrict__ m, const double* __
 
 int string_warps_per_cta() { return kStrWarps; }
 
-cudaError_t launch_string(const StringLaunch& p, int cw, int grid, cudaStream_t stream) {
-  switch (cw) {
-    case 4: string_pairs_kernel<4><<<grid, kStrWarps * 32, 0, stream>>>(p); break;
-    case 8: string_pairs_kernel<8><<<grid, kStrWarps * 32, 0, stream>>>(p); break;
-    default: string_pairs_kernel<12><<<grid, kStrWarps * 32, 0, stream>>>(p); break;
+// (columns per lane, lanes per pair) the kernel is instantiated for; capacity of one tile = cw * tp columns
+static const int kStrShapes[][2] = {{13, 4}, {19, 4}, {13, 8}, {19, 8}, {13, 16}, {19, 16}, {13, 32}, {19, 32}};
+
+void string_shape_for(uint32_t ly_cap, int* cw, int* tp) {
+  for (const auto& sh : kStrShapes)
+    if ((uint32_t)(sh[0] * sh[1]) >= ly_cap) { *cw = sh[0]; *tp = sh[1]; return; }
+  *cw = 19; *tp = 32;   // wider sequences are swept tile by tile
+}
+
+template <int CW, int TP>
+static cudaError_t launch_string_mode(const StringLaunch& p, int mode, int grid, size_t smem, cudaStream_t stream) {
+#define STR_MODE(M_)                                                                                                  \
+  if (mode == M_) {                                                                                                   \
+    cudaError_t e = cudaFuncSetAttribute(string_pairs_kernel<CW, TP, M_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e != cudaSuccess) return e;                                                                                   \
+    string_pairs_kernel<CW, TP, M_><<<grid, kStrWarps * 32, smem, stream>>>(p);                                       \
+    return cudaGetLastError();                                                                                        \
   }
-  return cudaGetLastError();
+  STR_MODE(STR_PLAIN) STR_MODE(STR_WEIGHTED) STR_MODE(STR_NAIVE_MODE) STR_MODE(STR_GENERAL)
+#undef STR_MODE
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_string(const StringLaunch& p, int cw, int tp, int mode, int grid, cudaStream_t stream) {
+  const size_t smem = sizeof(double) * ((size_t)p.pow_cap + 1);
+#define STR_CASE(CW_, TP_) if (cw == CW_ && tp == TP_) return launch_string_mode<CW_, TP_>(p, mode, grid, smem, stream);
+  STR_CASE(13, 4) STR_CASE(19, 4) STR_CASE(13, 8) STR_CASE(19, 8) STR_CASE(13, 16) STR_CASE(19, 16) STR_CASE(13, 32)
+  STR_CASE(19, 32)
+#undef STR_CASE
+  return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_combine(int kind, double alpha, double beta, const double* stem, const double* str, double* out,
