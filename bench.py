@@ -293,6 +293,32 @@ def run_b200(args, rank, world, local_rank):
             dist.destroy_process_group()
         return
 
+    # secondary workload, N=1 only: BASELINE.json configs[1] (C2: gap-weighted string kernel, 2 000 x 100 nt)
+    secondary = None
+    if world == 1 and not args.records:
+        recs2 = synth.make_config(2)
+        md2 = [hostlib.MData.seq_only(r["rows"]) for r in recs2]
+        ctx2 = api.Context(L.make_params(L.STR_SUBST), device=local_rank)
+        ds2 = ctx2.upload(md2)
+        n2 = len(md2)
+        for _ in range(3):
+            ctx2.gram(ds2)
+        ctx2.stats_reset()
+        t0 = time.perf_counter()
+        reps = 5
+        for _ in range(reps):
+            ctx2.gram(ds2, normalize=True)
+        wall = (time.perf_counter() - t0) / reps
+        st2 = ctx2.stats()
+        p2 = n2 * (n2 + 1) // 2
+        kms = st2["string_ms"] / reps
+        secondary = {"workload": "C2: lite StringKernel(gap 0.8, alpha 0.2) Gram matrix, 2000 random sequences of 100 nt",
+                     "pairs": p2, "kernel_ms": kms, "kernel_pairs_per_s": p2 / (kms * 1e-3),
+                     "kernel_gcups": p2 * 1e4 / (kms * 1e-3) / 1e9,
+                     "kernel_alg_tflops": 7.0 * p2 * 1e4 / (kms * 1e-3) / 1e12,
+                     "e2e_pairs_per_s": p2 / wall, "e2e_note": "stemk_gram with host buffers (pair lists H2D, 32 MB matrix D2H)"}
+        ctx2.close()
+
     cpu = None
     if world == 1:
         try:
@@ -338,6 +364,7 @@ def run_b200(args, rank, world, local_rank):
                      "hbm_sanity": {"set_bytes": int(set_bytes), "peak_gbs": hbm_peak,
                                     "note": "compulsory HBM traffic is << 1 B/flop on this path (SURVEY 8(d))"}},
         "cpu_baseline": cpu,
+        "secondary": secondary,
         "clocks": clocks.summary(),
     }
     print(json.dumps(line), flush=True)

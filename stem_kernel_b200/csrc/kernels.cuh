@@ -28,9 +28,13 @@ struct StemLaunch {
 
 constexpr int kMaxFastBuckets = 8;
 #ifndef STEMK_GROUP
-#define STEMK_GROUP 3
+#define STEMK_GROUP 4
 #endif
 constexpr uint32_t kFastGroup = STEMK_GROUP;  // == kGroup of stem_fast.cu
+#ifndef STEMK_MAXWARPS
+#define STEMK_MAXWARPS 24
+#endif
+constexpr int kFastMaxWarps = STEMK_MAXWARPS;  // warps per CTA of the fast stem kernel (its launch bound)
 
 // fast (separable) stem kernel: runs the pairs order[start[bucket] .. + count[bucket])
 struct StemFastLaunch {

@@ -32,7 +32,7 @@ namespace stemk {
 namespace {
 
 #ifndef STEMK_GROUP
-#define STEMK_GROUP 3
+#define STEMK_GROUP 4
 #endif
 constexpr uint32_t kGroup = STEMK_GROUP;  // pairs sharing one staged y record that a CTA runs concurrently
 
@@ -96,7 +96,7 @@ struct PairSlot {        // one pair of the group in flight
   double plr;
 };
 
-__global__ void __launch_bounds__(512, 1) stem_fast_kernel(const StemFastLaunch P) {
+__global__ void __launch_bounds__(32 * kFastMaxWarps, 1) stem_fast_kernel(const StemFastLaunch P) {
   extern __shared__ __align__(16) unsigned char sm[];
   __shared__ unsigned long long s_item;
   __shared__ uint32_t s_next_blk, s_g, s_maxblk;
@@ -252,9 +252,12 @@ __global__ void __launch_bounds__(512, 1) stem_fast_kernel(const StemFastLaunch 
       __syncwarp();
 
       // ---- phase B: sweep the y DAG level by level; lanes <-> (row r, node slot s)
-      const uint32_t r = (cnt == 2u) ? (lane >> 4) : 0u;
-      const uint32_t slot = (cnt == 2u) ? (lane & 15u) : lane;
-      const uint32_t nslot = (cnt == 2u) ? 16u : 32u;
+      // rows of the block rounded up to 1, 2, 4: lane = row * nslot + slot
+      const uint32_t rsh = cnt > 2u ? 2u : (cnt > 1u ? 1u : 0u);
+      const uint32_t nslot = 32u >> rsh;
+      const uint32_t r_raw = lane / nslot, slot = lane % nslot;
+      const bool live = r_raw < cnt;
+      const uint32_t r = live ? r_raw : 0u;
       const uint32_t gx = ps.node0 + i0 + r;
       const double xql = X.ql[gx], xbf = X.bfreq[gx];
       const uint32_t xl = X.len[gx], xbc = X.bcode[gx];
@@ -267,7 +270,7 @@ __global__ void __launch_bounds__(512, 1) stem_fast_kernel(const StemFastLaunch 
       for (uint32_t ly = 0; ly < ry.nlev; ++ly) {
 #endif
         const uint32_t jend = lds_u32(sb + (L.yLev + 4u * ly + 4u));
-        for (uint32_t j = jbeg + slot; j < jend; j += nslot) {
+        for (uint32_t j = jbeg + slot; live && j < jend; j += nslot) {
           const NodeI ni = lds_nodei(sb + (L.yI + 8u * j));
           const uint32_t yl = ni.len;
           if (band != 0u && yl + band < xl) {  // G1 == 0 here and below (length-monotone DAG)
@@ -314,14 +317,8 @@ __global__ void __launch_bounds__(512, 1) stem_fast_kernel(const StemFastLaunch 
       }
       // per-row path-weighted MATCH sum (lanes of one row are contiguous: reduce inside the half / full warp)
       const uint32_t racc_at = L.rowacc + 8u * (sl * P.nx_cap + i0 + r);
-      if (cnt == 2u) {
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) racc += __shfl_xor_sync(0xffffffffu, racc, o);
-        if ((lane & 15u) == 0u) sts_f64(sb + (racc_at), X.paths[gx] * racc);
-      } else {
-        racc = warp_sum_all(racc);
-        if (lane == 0u) sts_f64(sb + (racc_at), X.paths[gx] * racc);
-      }
+      for (uint32_t o = nslot >> 1; o > 0u; o >>= 1) racc += __shfl_xor_sync(0xffffffffu, racc, o);
+      if (slot == 0u && live) sts_f64(sb + (racc_at), X.paths[gx] * racc);
 
       // ---- phase C: finished rows G0s(i,:) = up_x(i) * dn_y * (H + a_x*HQ), then publish them
       for (uint32_t rr = 0; rr < cnt; ++rr) {

@@ -351,7 +351,7 @@ int stemk_pairs_device(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, s
       const size_t budget = std::min<size_t>(ctx->smem_optin, (size_t)227 * 1024);
       // one CTA per SM with as many warps as the bucket's rows leave room for
       int best_w = 0; size_t best_smem = 0;
-      for (int t = 16; t >= 2; --t) if (stem_fast_smem_bytes(t, nx_cap, ny_cap, e4_cap, lev_cap) <= budget) { best_w = t; break; }
+      for (int t = kFastMaxWarps; t >= 2; --t) if (stem_fast_smem_bytes(t, nx_cap, ny_cap, e4_cap, lev_cap) <= budget) { best_w = t; break; }
       if (!best_w) return fail(ctx, STEMK_ERR_NOMEM, "fast stem kernel: record does not fit in shared memory");
       best_smem = stem_fast_smem_bytes(best_w, nx_cap, ny_cap, e4_cap, lev_cap);
       const int per_sm = stem_fast_ctas_per_sm(best_w, best_smem);

@@ -38,7 +38,10 @@ struct RecDev {
 enum { REC_HAS_WEIGHT = 1u, REC_SIMPLE_COLS = 2u, REC_SIMPLE_BPF = 4u,
        REC_LEN_MONOTONE = 8u,  // every non-leaf child is strictly shorter than its parent (true for front-end DAGs)
        REC_FAST = 16u };       // eligible for the separable fast kernel (see compile_set.cpp)
-constexpr uint32_t kFastRows = 2;     // rows a warp of the fast stem kernel sweeps in lockstep
+#ifndef STEMK_ROWS
+#define STEMK_ROWS 1
+#endif
+constexpr uint32_t kFastRows = STEMK_ROWS;  // rows (1, 2 or 4) a warp of the fast stem kernel sweeps in lockstep
 constexpr uint32_t kFastMaxN = 1024;  // largest staged record (non-leaf nodes) of the fast stem kernel
 
 struct NodeI {        // integer part of a node for the fast kernel (8 bytes)
