@@ -13,6 +13,9 @@
 //   levels = longest-path layering of the non-leaf nodes (rows of one level are independent)
 #include <algorithm>
 #include <cmath>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <thread>
 
 #include "ribosum85_60.inc"
@@ -262,6 +265,8 @@ void append(std::vector<T>& dst, const std::vector<T>& src) { dst.insert(dst.end
 
 std::string compile_set(const stemk_seqset_desc& s, double g, int n_threads, CompiledSet* out) {
   const uint32_t n = s.n_seqs;
+  const bool timing = std::getenv("STEMK_TIMING") != nullptr;
+  auto t0 = std::chrono::steady_clock::now();
   std::vector<RecOut> recs(n);
   if (n_threads < 1) n_threads = 1;
   n_threads = std::min<int>(n_threads, std::max<uint32_t>(1, n / 16));
@@ -273,9 +278,23 @@ std::string compile_set(const stemk_seqset_desc& s, double g, int n_threads, Com
       th.push_back(std::thread([&, t]() { for (uint32_t r = t; r < n; r += n_threads) compile_record(s, r, g, &recs[r]); }));
     for (auto& x : th) x.join();
   }
+  auto t1 = std::chrono::steady_clock::now();
   CompiledSet& c = *out;
   c = CompiledSet();
   c.rec.resize(n);
+  {  // one allocation per array instead of growth by doubling
+    size_t nn = 0, ne = 0, nl = 0, nb = 0, nc = 0, n16 = 0, nblk = 0, ncost = 0;
+    for (const RecOut& o : recs) {
+      nn += o.a.size(); ne += o.cidx.size(); nl += o.lev_off.size(); nb += o.bab.size(); nc += o.ccode.size();
+      n16 += o.c16.size(); nblk += o.blk.size(); ncost += std::max<size_t>(1, o.pd.size());
+    }
+    for (auto* v : {&c.a, &c.el, &c.ql, &c.paths, &c.gapt, &c.bfreq, &c.up, &c.dn, &c.s2}) v->reserve(nn);
+    c.len.reserve(nn); c.bcode.reserve(nn); c.nodei.reserve(nn); c.deg_all.reserve(nn);
+    c.coff.reserve(nn + n); c.boff.reserve(nn + n); c.cidx.reserve(ne); c.ce.reserve(ne); c.lev_off.reserve(nl);
+    c.bab.reserve(nb); c.bfq.reserve(nb); c.ccode.reserve(nc); c.cw.reserve(nc); c.text.reserve(nc);
+    c.prof.reserve(4 * nc); c.c16.reserve(n16); c.blk.reserve(nblk); c.cost_pd.reserve(ncost); c.cost_pb.reserve(ncost);
+    c.cost_off.reserve(n + 1); c.n_nodes_all.reserve(n); c.n_edges_all.reserve(n); c.max_level_rows.reserve(n);
+  }
   for (uint32_t r = 0; r < n; ++r) {
     RecOut& o = recs[r];
     if (!o.err.empty()) return "record " + std::to_string(r) + ": " + o.err;
@@ -317,6 +336,12 @@ std::string compile_set(const stemk_seqset_desc& s, double g, int n_threads, Com
     c.max_nlev = std::max(c.max_nlev, h.nlev);
   }
   c.cost_off.push_back(c.cost_pd.size());
+  if (timing) {
+    auto t2 = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "compile_set: %u records, per-record %.1f ms (%d threads), merge %.1f ms\n", n,
+                 std::chrono::duration<double, std::milli>(t1 - t0).count(), n_threads,
+                 std::chrono::duration<double, std::milli>(t2 - t1).count());
+  }
   return "";
 }
 

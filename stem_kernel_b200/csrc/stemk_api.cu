@@ -228,15 +228,17 @@ int stemk_upload(stemk_ctx* ctx, const stemk_seqset_desc* desc, stemk_set** out)
                o_text = place(off, h.text), o_up = place(off, h.up), o_dn = place(off, h.dn), o_s2 = place(off, h.s2),
                o_nodei = place(off, h.nodei), o_c16 = place(off, h.c16), o_blk = place(off, h.blk);
   off = (off + 255) & ~size_t(255);
-  std::vector<char> stage(off, 0);
-  auto put = [&](size_t at, const auto& v) { if (!v.empty()) std::memcpy(stage.data() + at, v.data(), v.size() * sizeof(v[0])); };
+  cudaError_t e = s->blob.reserve(std::max<size_t>(off, 256));
+  // every array goes straight from its host vector to its place in the blob (no staging copy)
+  auto put = [&](size_t at, const auto& v) {
+    if (e == cudaSuccess && !v.empty())
+      e = cudaMemcpyAsync(static_cast<char*>(s->blob.p) + at, v.data(), v.size() * sizeof(v[0]), cudaMemcpyHostToDevice, ctx->stream);
+  };
   put(o_rec, h.rec); put(o_a, h.a); put(o_el, h.el); put(o_ql, h.ql); put(o_paths, h.paths); put(o_gapt, h.gapt);
   put(o_bfreq, h.bfreq); put(o_len, h.len); put(o_bcode, h.bcode); put(o_coff, h.coff); put(o_cidx, h.cidx);
   put(o_ce, h.ce); put(o_lev, h.lev_off); put(o_boff, h.boff); put(o_bab, h.bab); put(o_bfq, h.bfq);
   put(o_ccode, h.ccode); put(o_cw, h.cw); put(o_prof, h.prof); put(o_text, h.text);
   put(o_up, h.up); put(o_dn, h.dn); put(o_s2, h.s2); put(o_nodei, h.nodei); put(o_c16, h.c16); put(o_blk, h.blk);
-  cudaError_t e = s->blob.reserve(std::max<size_t>(off, 256));
-  if (e == cudaSuccess) e = cudaMemcpyAsync(s->blob.p, stage.data(), off, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) { s->blob.release(); delete s; return cuda_fail(ctx, e, "set upload"); }
   char* b = static_cast<char*>(s->blob.p);
