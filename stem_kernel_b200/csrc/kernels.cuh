@@ -28,7 +28,7 @@ struct StemLaunch {
 
 constexpr int kMaxFastBuckets = 8;
 #ifndef STEMK_GROUP
-#define STEMK_GROUP 4
+#define STEMK_GROUP 6
 #endif
 constexpr uint32_t kFastGroup = STEMK_GROUP;  // == kGroup of stem_fast.cu
 #ifndef STEMK_MAXWARPS
@@ -49,6 +49,7 @@ struct StemFastLaunch {
   int bucket;
   double* scratch;                   // per-CTA slabs of pre-scaled G0 rows (one per pair of a group)
   unsigned long long scratch_stride; // doubles per CTA (all slabs of the group)
+  double* rowacc;                    // per CTA: kFastGroup x nx_cap per-row result slots
   const double* pair_tab;
   uint32_t len_band, nx_cap, ny_cap, e4_cap, lev_cap;
 };

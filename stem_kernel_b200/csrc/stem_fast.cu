@@ -32,12 +32,12 @@ namespace stemk {
 namespace {
 
 #ifndef STEMK_GROUP
-#define STEMK_GROUP 4
+#define STEMK_GROUP 6
 #endif
 constexpr uint32_t kGroup = STEMK_GROUP;  // pairs sharing one staged y record that a CTA runs concurrently
 
 struct FastLayout {
-  uint32_t tab, yD0, yD1, yD2, yD3, yI, yC, yLev, done, rowacc, rows, row_bytes, total;
+  uint32_t tab, yD0, yD1, yD2, yD3, yI, yC, yLev, done, rows, row_bytes, total;
 };
 
 // nwarps warps, each with kFastRows x (HQ row, H row)
@@ -54,8 +54,7 @@ __host__ __device__ inline FastLayout fast_layout(uint32_t nwarps, uint32_t nx_c
   L.yI = take(8 * ny_cap);    // NodeI
   L.yC = take(2 * e4_cap);    // child lists
   L.yLev = take(4 * (lev_cap + 1));
-  L.done = take(4 * nx_cap * kGroup);    // per pair of the group
-  L.rowacc = take(8 * nx_cap * kGroup);
+  L.done = take(nx_cap * kGroup);        // one byte per row, per pair of the group
   L.row_bytes = (8u * (ny_cap + 1u) + 15u) & ~15u;  // + the dummy column
   L.rows = take(2u * kFastRows * L.row_bytes * nwarps);
   L.total = off;
@@ -69,7 +68,7 @@ __device__ __forceinline__ double warp_sum_all(double v) {
 }
 
 __device__ __forceinline__ uint32_t ld_flag_f(uint32_t addr) {
-  uint32_t v; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v;
+  uint32_t v; asm volatile("ld.volatile.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v;
 }
 
 // Shared-memory accessors on raw 32-bit shared addresses.  Going through generic pointers makes the compiler rebuild
@@ -166,7 +165,7 @@ __global__ void __launch_bounds__(32 * kFastMaxWarps, 1) stem_fast_kernel(const 
       for (uint32_t e = tid; e < ry.e4 / 4u; e += blockDim.x) sts_v2u32(sb + (L.yC + 8 * e), src[e]);
     }
     for (uint32_t l = tid; l <= ry.nlev; l += blockDim.x) sts_u32(sb + (L.yLev + 4 * l), Y.lev_off[ry.lev0 + l]);
-    for (uint32_t i = tid; i < g * P.nx_cap; i += blockDim.x) sts_u32(sb + (L.done + 4 * i), 0u);
+    for (uint32_t i = tid; i < (g * P.nx_cap + 3u) / 4u; i += blockDim.x) sts_u32(sb + (L.done + 4 * i), 0u);
     // the dummy column of every row of this warp
     if (lane < 2u * kFastRows) sts_f64(sb + (wrows + L.row_bytes * lane + 8u * Ny), 0.0);
     __syncthreads();
@@ -185,7 +184,8 @@ __global__ void __launch_bounds__(32 * kFastMaxWarps, 1) stem_fast_kernel(const 
       const uint32_t i0 = blk & 0xffffu, cnt = blk >> 16;  // cnt in 1..kFastRows
       const uint32_t* __restrict__ xcoff = X.coff + ps.coff0;
       double* __restrict__ G0 = slab + sl * slot_stride;
-      const uint32_t done = L.done + 4u * sl * P.nx_cap;
+      const uint32_t done = L.done + sl * P.nx_cap;
+      double* __restrict__ rowacc = P.rowacc + ((size_t)blockIdx.x * kGroup + sl) * P.nx_cap;
 
       // ---- phase A: HQ(r,:) = up_y * s2_x(i) * sum over inner pairs c of G0s(c,:)
       for (uint32_t r = 0; r < cnt; ++r) {
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(32 * kFastMaxWarps, 1) stem_fast_kernel(const 
             const uint32_t c = X.cidx[eb + lane];
             off_l = c * NYS;
             #ifndef ABL_NO_WAIT
-            while (ld_flag_f(sb + done + 4u * c) == 0u) __nanosleep(32);
+            while (ld_flag_f(sb + done + c) == 0u) __nanosleep(32);
 #endif  // wait until that row is published
           }
           __syncwarp();
@@ -316,9 +316,9 @@ __global__ void __launch_bounds__(32 * kFastMaxWarps, 1) stem_fast_kernel(const 
         __syncwarp();
       }
       // per-row path-weighted MATCH sum (lanes of one row are contiguous: reduce inside the half / full warp)
-      const uint32_t racc_at = L.rowacc + 8u * (sl * P.nx_cap + i0 + r);
+
       for (uint32_t o = nslot >> 1; o > 0u; o >>= 1) racc += __shfl_xor_sync(0xffffffffu, racc, o);
-      if (slot == 0u && live) sts_f64(sb + (racc_at), X.paths[gx] * racc);
+      if (slot == 0u && live) rowacc[i0 + r] = X.paths[gx] * racc;   // per-row slot in global scratch (L2)
 
       // ---- phase C: finished rows G0s(i,:) = up_x(i) * dn_y * (H + a_x*HQ), then publish them
       for (uint32_t rr = 0; rr < cnt; ++rr) {
@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(32 * kFastMaxWarps, 1) stem_fast_kernel(const 
       }
       __threadfence_block();
       __syncwarp();
-      if (lane < cnt) asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(sb + done + 4u * (i0 + lane)), "r"(1u) : "memory");
+      if (lane < cnt) asm volatile("st.volatile.shared.u8 [%0], %1;" ::"r"(sb + done + i0 + lane), "r"(1u) : "memory");
     }
 
     // ---- fixed-order sum of the per-row slots, one warp per pair of the group
@@ -343,7 +343,8 @@ __global__ void __launch_bounds__(32 * kFastMaxWarps, 1) stem_fast_kernel(const 
     if (warp < g) {
       const PairSlot ps = s_slot[warp];
       double t = 0.0;
-      for (uint32_t i = lane; i < ps.N; i += 32u) t += lds_f64(sb + (L.rowacc + 8u * (warp * P.nx_cap + i)));
+      const double* __restrict__ ra = P.rowacc + ((size_t)blockIdx.x * kGroup + warp) * P.nx_cap;
+      for (uint32_t i = lane; i < ps.N; i += 32u) t += __ldcg(ra + i);
       t = warp_sum_all(t);
       if (lane == 0) P.out[ps.k] = t + ps.plr * (double)ry.lr;
     }

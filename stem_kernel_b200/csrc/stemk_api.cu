@@ -55,7 +55,7 @@ struct stemk_ctx {
   double* d_pair_tab = nullptr;
   double* d_subst = nullptr;
   unsigned long long* d_counter = nullptr;
-  DevBuf scratch, carry, tmp_stem, tmp_str, idx_x, idx_y, vals, matrix, order;
+  DevBuf scratch, carry, tmp_stem, tmp_str, idx_x, idx_y, vals, matrix, order, rowacc;
   unsigned long long* d_bucket = nullptr;  // count[16] | start[16] | queue heads[16]
   int use_fast = 1;                        // STEMK_FAST=0 in the environment forces the general stem kernel
   std::string err;
@@ -194,7 +194,7 @@ void stemk_destroy(stemk_ctx* c) {
   if (c->device == STEMK_DEVICE_NONE) { delete c; return; }
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  for (DevBuf* b : {&c->scratch, &c->carry, &c->tmp_stem, &c->tmp_str, &c->idx_x, &c->idx_y, &c->vals, &c->matrix, &c->order}) b->release();
+  for (DevBuf* b : {&c->scratch, &c->carry, &c->tmp_stem, &c->tmp_str, &c->idx_x, &c->idx_y, &c->vals, &c->matrix, &c->order, &c->rowacc}) b->release();
   if (c->d_pair_tab) cudaFree(c->d_pair_tab);
   if (c->d_subst) cudaFree(c->d_subst);
   if (c->d_counter) cudaFree(c->d_counter);
@@ -361,10 +361,11 @@ int stemk_pairs_device(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, s
       const int grid = (int)std::min<size_t>((n_pairs + kFastGroup - 1) / kFastGroup, (size_t)ctx->sm_count);
       const unsigned long long stride = (unsigned long long)kFastGroup * nx_cap * ((ny_cap + 1u) & ~1u);
       CU(ctx->scratch.reserve(sizeof(double) * stride * grid));
+      CU(ctx->rowacc.reserve(sizeof(double) * (size_t)kFastGroup * nx_cap * grid));
       StemFastLaunch F;
       F.X = x->view; F.Y = y->view; F.xi = d_xi; F.yi = d_yi; F.out = stem_out; F.order = C.order;
       F.start = C.start; F.count = C.count; F.counter = heads + 1 + b; F.bucket = 1 + b;
-      F.scratch = (double*)ctx->scratch.p; F.scratch_stride = stride; F.pair_tab = ctx->d_pair_tab;
+      F.scratch = (double*)ctx->scratch.p; F.scratch_stride = stride; F.rowacc = (double*)ctx->rowacc.p; F.pair_tab = ctx->d_pair_tab;
       F.len_band = ctx->params.len_band; F.nx_cap = nx_cap; F.ny_cap = ny_cap; F.e4_cap = e4_cap; F.lev_cap = lev_cap;
       stemk_ctx::Timed tm = timed_begin(ctx, 0, st);
       cudaError_t le = launch_stem_fast(F, grid, best_w, best_smem, st);
