@@ -46,20 +46,32 @@ __device__ __noinline__ double subst_general(const double* __restrict__ st, cons
 // on raw characters; 3 anything (profile columns, weights decided per pair).
 enum { STR_PLAIN = 0, STR_WEIGHTED = 1, STR_NAIVE_MODE = 2, STR_GENERAL = 3 };
 
+__device__ __forceinline__ double lds_f64_raw(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+
 template <int CW, int TP, int MODE>
 __global__ void __launch_bounds__(kStrWarps * 32, 3) string_pairs_kernel(const StringLaunch P) {
   constexpr int GPW = 32 / TP;           // pairs (lane groups) per warp
-  __shared__ double st5[25];             // substitution scores with a fifth code: an all-gap column scores 1
+  constexpr bool kGeneral = MODE == STR_GENERAL;
+  constexpr bool kHasW = MODE == STR_WEIGHTED || MODE == STR_GENERAL;
+  // score table, 5 rows (x code: 4 bases, all-gap column) of 8 entries (y code: 4 bases, all-gap column = 1,
+  // padding column = 0): a column past the end of y scores 0 against everything, so the inner loop needs no
+  // bounds predicate -- values only ever flow to the right, a padding column cannot reach a real one
+  __shared__ __align__(16) double st8[5 * 8];
   extern __shared__ double gpow[];       // gap^k by repeated multiplication, k = 0..P.pow_cap (string_kernel.cpp:85-92)
-  if (threadIdx.x < 25) {
-    const int a = threadIdx.x / 5, b = threadIdx.x % 5;
-    st5[threadIdx.x] = (a < 4 && b < 4) ? P.subst[a * 4 + b] : 1.0;
+  if (threadIdx.x < 40) {
+    const int a = threadIdx.x / 8, b = threadIdx.x % 8;
+    st8[threadIdx.x] = b >= 5 ? 0.0 : ((a < 4 && b < 4) ? P.subst[a * 4 + b] : 1.0);
   }
   if (threadIdx.x == 32) {
     double p = 1.0;
     for (uint32_t k = 0; k <= P.pow_cap; ++k) { gpow[k] = p; p *= P.gap; }
   }
   __syncthreads();
+  const uint32_t st_base = (uint32_t)__cvta_generic_to_shared(st8);
   const int lane = threadIdx.x & 31;
   const int sub = lane % TP, grp = lane / TP;
   const unsigned group_global = (blockIdx.x * kStrWarps + (threadIdx.x >> 5)) * GPW + grp;
@@ -80,7 +92,7 @@ __global__ void __launch_bounds__(kStrWarps * 32, 3) string_pairs_kernel(const S
     rx.L = ry.L = 0; rx.flags = ry.flags = 0; rx.col0 = ry.col0 = 0;
     if (valid) { rx = X.rec[P.xi[k]]; ry = Y.rec[P.yi[k]]; }
     const int Lx = (int)rx.L, Ly = (int)ry.L;
-    const bool use_w = MODE == STR_WEIGHTED || (MODE == STR_GENERAL && (rx.flags & REC_HAS_WEIGHT) && (ry.flags & REC_HAS_WEIGHT));
+    const bool use_w = MODE == STR_WEIGHTED || (kGeneral && (rx.flags & REC_HAS_WEIGHT) && (ry.flags & REC_HAS_WEIGHT));
     const uint8_t* __restrict__ xcode = (MODE == STR_NAIVE_MODE ? X.text : X.ccode) + rx.col0;
     const uint8_t* __restrict__ ycode = (MODE == STR_NAIVE_MODE ? Y.text : Y.ccode) + ry.col0;
     const double* __restrict__ xw = X.cw + rx.col0;
@@ -102,25 +114,33 @@ __global__ void __launch_bounds__(kStrWarps * 32, 3) string_pairs_kernel(const S
     for (int tile = 0; tile < ntiles_w; ++tile) {
       const bool tile_on = tile < ntiles;
       const int jb = tile * TP * CW + sub * CW;  // 0-based index of this lane's first column
-      // top boundary G0(0,j) = g^j; columns past the end of y behave like all-zero columns that are never summed
-      double g0[CW];
-      double wy[(MODE == STR_WEIGHTED || MODE == STR_GENERAL) ? CW : 1];
-      int yc[CW];
+      // top boundary G0(0,j) = g^j
+      double ga[CW], gb[CW];                 // G0 of the lane's columns, ping-pong between consecutive steps
+      double wy[kHasW ? CW : 1];
+      int yc[CW];                            // plain / weighted: byte offset of the column's score inside a table row
 #pragma unroll
       for (int c = 0; c < CW; ++c) {
         const int j = jb + c;
         const bool in = tile_on && j < Ly;
-        g0[c] = in ? gpow[j + 1] : 0.0;   // column index is 1-based in the table
-        yc[c] = in ? (int)ycode[j] : 4;
-        if (MODE == STR_WEIGHTED || MODE == STR_GENERAL) wy[c] = (in && use_w) ? yw[j] : 1.0;
+        ga[c] = in ? gpow[j + 1] : 0.0;   // column index is 1-based in the table
+        gb[c] = 0.0;
+        if (MODE == STR_NAIVE_MODE) yc[c] = in ? (int)ycode[j] : 0x100;          // matches no character
+        else if (kGeneral) yc[c] = in ? (int)ycode[j] : 4;
+        else yc[c] = in ? 8 * (int)ycode[j] : 8 * 5;                             // padding column: score 0
+        if (kHasW) wy[c] = (in && use_w) ? yw[j] : 1.0;
       }
       // value a lane hands to its right neighbour after finishing a row
       double send_g1 = 0.0, send_diag = 0.0;
-      for (int s = 0; s < nsteps_w; ++s) {
+
+      auto step = [&](int s, double (&gi)[CW], double (&go)[CW]) {
         double in_g1 = __shfl_up_sync(0xffffffffu, send_g1, 1, TP);
         double in_diag = __shfl_up_sync(0xffffffffu, send_diag, 1, TP);
         const int i = s - sub;  // 0-based row of x
-        if (!tile_on || i < 0 || i >= Lx) continue;
+        if (!tile_on || i < 0 || i >= Lx) {
+#pragma unroll
+          for (int c = 0; c < CW; ++c) go[c] = gi[c];
+          return;
+        }
         if (sub == 0) {
           if (tile == 0) {
             in_g1 = 0.0;        // G1(i,0) = 0
@@ -132,27 +152,32 @@ __global__ void __launch_bounds__(kStrWarps * 32, 3) string_pairs_kernel(const S
         }
         const int xc = (int)xcode[i];
         const double wx = use_w ? xw[i] : 1.0;
+        const uint32_t xrow = st_base + 64u * (uint32_t)xc;
         double diag = in_diag, g1 = in_g1;
 #pragma unroll
         for (int c = 0; c < CW; ++c) {
-          const double old = g0[c];
-          if (jb + c < Ly) {
-            double v;
-            if (MODE == STR_NAIVE_MODE) {
-              v = (xc == yc[c]) ? diag * g2 : 0.0;
-            } else {
+          const double old = gi[c];
+          double v;
+          if (MODE == STR_NAIVE_MODE) {
+            v = (xc == yc[c]) ? diag * g2 : 0.0;
+          } else if (!kGeneral) {
+            v = diag;
+            if (MODE == STR_WEIGHTED) v = v * wx * wy[c];
+            v *= lds_f64_raw(xrow + (uint32_t)yc[c]);
+          } else {
+            v = 0.0;
+            if (jb + c < Ly) {
               v = diag;
-              if (MODE == STR_WEIGHTED) v = v * wx * wy[c];
-              if (MODE == STR_GENERAL && use_w) v = v * wx * wy[c];
+              if (use_w) v = v * wx * wy[c];
               double sc;
-              if (MODE != STR_GENERAL || (xc < 5 && yc[c] < 5)) sc = st5[xc * 5 + yc[c]];
+              if (xc < 5 && yc[c] < 5) sc = st8[xc * 8 + yc[c]];
               else sc = subst_general(P.subst, xprof + 4 * i, yprof + 4 * (jb + c));
               v *= sc;
             }
-            acc += v;
-            g1 = fma(g1, gap, v);
-            g0[c] = fma(old, gap, g1);
           }
+          acc += v;
+          g1 = fma(g1, gap, v);
+          go[c] = fma(old, gap, g1);
           diag = old;
         }
         send_g1 = g1;
@@ -160,8 +185,12 @@ __global__ void __launch_bounds__(kStrWarps * 32, 3) string_pairs_kernel(const S
         // the lane that owns the tile's last column leaves it behind for the next tile
         if (sub == TP - 1 && tile + 1 < ntiles) {
           carry_g1[i + 1] = g1;
-          carry_g0[i + 1] = g0[CW - 1];
+          carry_g0[i + 1] = go[CW - 1];
         }
+      };
+      for (int s = 0; s < nsteps_w; s += 2) {
+        step(s, ga, gb);
+        if (s + 1 < nsteps_w) step(s + 1, gb, ga);
       }
       if (tile + 1 < ntiles_w) {
         // G0(0, last column of this tile) for the next tile's first diagonal
