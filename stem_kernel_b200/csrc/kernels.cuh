@@ -92,7 +92,7 @@ size_t stem_fast_smem_bytes(uint32_t nwarps, uint32_t nx_cap, uint32_t ny_cap, u
 int stem_fast_ctas_per_sm(int nwarps, size_t smem);
 cudaError_t launch_stem_fast(const StemFastLaunch& p, int grid, int nwarps, size_t smem, cudaStream_t stream);
 cudaError_t launch_classify(const StemClassify& c, int n_buckets, unsigned long long* counters, cudaStream_t stream);
-void string_shape_for(uint32_t ly_cap, int* cw, int* tp);
+void string_shape_for(uint32_t ly_cap, int mode, int* cw, int* tp);
 // mode: 0 plain one-hot columns, 1 weighted, 2 naive characters, 3 general (see string_kernel.cu)
 cudaError_t launch_string(const StringLaunch& p, int cw, int tp, int mode, int grid, cudaStream_t stream);
 int string_warps_per_cta();

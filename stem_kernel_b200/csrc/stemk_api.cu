@@ -376,8 +376,14 @@ int stemk_pairs_device(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, s
   }
   if (has_str) {
     const uint32_t ly_cap = std::max(1u, y->host.max_L), lx_cap = std::max(1u, x->host.max_L);
+    // specialised kernels when the whole launch is uniform, the general one otherwise
+    const size_t nxr = x->host.rec.size(), nyr = y->host.rec.size();
+    const bool simple = x->host.n_simple_cols == nxr && y->host.n_simple_cols == nyr;
+    const bool all_w = x->host.n_weighted == nxr && y->host.n_weighted == nyr;
+    const bool none_w = x->host.n_weighted == 0 || y->host.n_weighted == 0;
+    const int mode = kind == STEMK_STR_NAIVE ? 2 : (!simple ? 3 : (all_w ? 1 : (none_w ? 0 : 3)));
     int cw, tp;
-    string_shape_for(ly_cap, &cw, &tp);
+    string_shape_for(ly_cap, mode, &cw, &tp);
     const int wpc = string_warps_per_cta();
     const int gpw = 32 / tp;                                   // pairs per warp
     const size_t want = (n_pairs + (size_t)wpc * gpw - 1) / ((size_t)wpc * gpw);
@@ -390,12 +396,6 @@ int stemk_pairs_device(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, s
     L.counter = ctx->d_counter; L.carry = (double*)ctx->carry.p; L.carry_stride = cstride; L.subst = ctx->d_subst;
     L.gap = ctx->params.gap; L.naive = kind == STEMK_STR_NAIVE; L.pow_cap = std::max(lx_cap, ly_cap) + 1;
     stemk_ctx::Timed tm = timed_begin(ctx, 1, st);
-    // specialised kernels when the whole launch is uniform, the general one otherwise
-    const size_t nxr = x->host.rec.size(), nyr = y->host.rec.size();
-    const bool simple = x->host.n_simple_cols == nxr && y->host.n_simple_cols == nyr;
-    const bool all_w = x->host.n_weighted == nxr && y->host.n_weighted == nyr;
-    const bool none_w = x->host.n_weighted == 0 || y->host.n_weighted == 0;
-    const int mode = kind == STEMK_STR_NAIVE ? 2 : (!simple ? 3 : (all_w ? 1 : (none_w ? 0 : 3)));
     cudaError_t le = launch_string(L, cw, tp, mode, grid, st);
     timed_end(ctx, tm, st);
     CU(le);

@@ -250,35 +250,44 @@ __global__ void normalize_square_kernel(double* __restrict__ m, const double* __
 
 int string_warps_per_cta() { return kStrWarps; }
 
-// (columns per lane, lanes per pair) the kernel is instantiated for; capacity of one tile = cw * tp columns
-static const int kStrShapes[][2] = {{13, 4}, {19, 4}, {13, 8}, {19, 8}, {13, 16}, {19, 16}, {13, 32}, {19, 32}};
+// (columns per lane, lanes per pair) the kernel is instantiated for; capacity of one tile = cw * tp columns.
+// 25 columns per lane only for the modes without per-column weights (the weighted ones would spill registers).
+static const int kStrShapesLight[][2] = {{13, 4}, {19, 4}, {25, 4}, {19, 8}, {25, 8}, {19, 16}, {25, 16}, {19, 32}, {25, 32}};
+static const int kStrShapesHeavy[][2] = {{13, 4}, {19, 4}, {13, 8}, {19, 8}, {13, 16}, {19, 16}, {13, 32}, {19, 32}};
 
-void string_shape_for(uint32_t ly_cap, int* cw, int* tp) {
-  for (const auto& sh : kStrShapes)
-    if ((uint32_t)(sh[0] * sh[1]) >= ly_cap) { *cw = sh[0]; *tp = sh[1]; return; }
-  *cw = 19; *tp = 32;   // wider sequences are swept tile by tile
+void string_shape_for(uint32_t ly_cap, int mode, int* cw, int* tp) {
+  const bool light = mode == STR_PLAIN || mode == STR_NAIVE_MODE;
+  if (light) {
+    for (const auto& sh : kStrShapesLight) if ((uint32_t)(sh[0] * sh[1]) >= ly_cap) { *cw = sh[0]; *tp = sh[1]; return; }
+    *cw = 25; *tp = 32;   // wider sequences are swept tile by tile
+  } else {
+    for (const auto& sh : kStrShapesHeavy) if ((uint32_t)(sh[0] * sh[1]) >= ly_cap) { *cw = sh[0]; *tp = sh[1]; return; }
+    *cw = 19; *tp = 32;
+  }
 }
 
-template <int CW, int TP>
-static cudaError_t launch_string_mode(const StringLaunch& p, int mode, int grid, size_t smem, cudaStream_t stream) {
-#define STR_MODE(M_)                                                                                                  \
-  if (mode == M_) {                                                                                                   \
-    cudaError_t e = cudaFuncSetAttribute(string_pairs_kernel<CW, TP, M_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    if (e != cudaSuccess) return e;                                                                                   \
-    string_pairs_kernel<CW, TP, M_><<<grid, kStrWarps * 32, smem, stream>>>(p);                                       \
-    return cudaGetLastError();                                                                                        \
-  }
-  STR_MODE(STR_PLAIN) STR_MODE(STR_WEIGHTED) STR_MODE(STR_NAIVE_MODE) STR_MODE(STR_GENERAL)
-#undef STR_MODE
-  return cudaErrorInvalidValue;
+template <int CW, int TP, int M_>
+static cudaError_t launch_string_one(const StringLaunch& p, int grid, size_t smem, cudaStream_t stream) {
+  cudaError_t e = cudaFuncSetAttribute(string_pairs_kernel<CW, TP, M_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  string_pairs_kernel<CW, TP, M_><<<grid, kStrWarps * 32, smem, stream>>>(p);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_string(const StringLaunch& p, int cw, int tp, int mode, int grid, cudaStream_t stream) {
   const size_t smem = sizeof(double) * ((size_t)p.pow_cap + 1);
-#define STR_CASE(CW_, TP_) if (cw == CW_ && tp == TP_) return launch_string_mode<CW_, TP_>(p, mode, grid, smem, stream);
-  STR_CASE(13, 4) STR_CASE(19, 4) STR_CASE(13, 8) STR_CASE(19, 8) STR_CASE(13, 16) STR_CASE(19, 16) STR_CASE(13, 32)
-  STR_CASE(19, 32)
-#undef STR_CASE
+#define STR_LIGHT(CW_, TP_)                                                                                  \
+  if (cw == CW_ && tp == TP_ && mode == STR_PLAIN) return launch_string_one<CW_, TP_, STR_PLAIN>(p, grid, smem, stream); \
+  if (cw == CW_ && tp == TP_ && mode == STR_NAIVE_MODE) return launch_string_one<CW_, TP_, STR_NAIVE_MODE>(p, grid, smem, stream);
+#define STR_HEAVY(CW_, TP_)                                                                                  \
+  if (cw == CW_ && tp == TP_ && mode == STR_WEIGHTED) return launch_string_one<CW_, TP_, STR_WEIGHTED>(p, grid, smem, stream); \
+  if (cw == CW_ && tp == TP_ && mode == STR_GENERAL) return launch_string_one<CW_, TP_, STR_GENERAL>(p, grid, smem, stream);
+  STR_LIGHT(13, 4) STR_LIGHT(19, 4) STR_LIGHT(25, 4) STR_LIGHT(19, 8) STR_LIGHT(25, 8) STR_LIGHT(19, 16) STR_LIGHT(25, 16)
+  STR_LIGHT(19, 32) STR_LIGHT(25, 32)
+  STR_HEAVY(13, 4) STR_HEAVY(19, 4) STR_HEAVY(13, 8) STR_HEAVY(19, 8) STR_HEAVY(13, 16) STR_HEAVY(19, 16) STR_HEAVY(13, 32)
+  STR_HEAVY(19, 32)
+#undef STR_LIGHT
+#undef STR_HEAVY
   return cudaErrorInvalidValue;
 }
 
