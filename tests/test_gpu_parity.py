@@ -308,6 +308,53 @@ def test_config1_libsvm_cross_validation_is_identical():
     assert relerr(got[:40, :40], z["gram"]) < TOL
 
 
+def test_rectangular_matrix_with_sv_subset_at_moderate_size():
+    """KernelMatrix::calculate(test, train) / the one-row variant with an sv_index (kernel_matrix.cpp:635-754):
+    60 test x 150 train C3 records, 40 support-vector columns, normalised; sampled entries against the oracle,
+    columns outside sv_index untouched, NaN pattern of the normalisation as in App::predict."""
+    train = hostlib.build_many(synth.make_config(3, 150, offset=3000), TH)
+    test = hostlib.build_many(synth.make_config(3, 60, offset=5000), TH)
+    ftrain, ftest = hostlib.SeqSet(train), hostlib.SeqSet(test)
+    p = L.make_params(L.SU_STEM_STR)
+    ctx = api.Context(p)
+    dtrain, dtest = ctx.upload(ftrain), ctx.upload(ftest)
+    rng = np.random.default_rng(9)
+    sv = np.sort(rng.choice(150, 40, replace=False)).astype(np.uint32)
+    m, selfv = ctx.cross(dtest, dtrain, sv_index=sv, init=-7.0)
+    others = np.setdiff1d(np.arange(150), sv)
+    assert np.all(m[:, others] == -7.0)
+    ti, ci = rng.integers(0, 60, 150), sv[rng.integers(0, 40, 150)]
+    want = O.pairs(oparams(p), ftrain.desc(), ftest.desc(), ci, ti)       # train record is the first argument
+    assert relerr(m[ti, ci], want) < TOL
+    assert relerr(selfv[:10], O.pairs(oparams(p), ftest.desc(), ftest.desc(), np.arange(10), np.arange(10))) < TOL
+    full, _ = ctx.cross(dtest, dtrain)
+    assert relerr(full[:, sv], m[:, sv]) == 0.0
+    mn, _ = ctx.cross(dtest, dtrain, normalize=True)
+    d = ctx.diag(dtrain)
+    assert relerr(mn, full / np.sqrt(np.outer(selfv, d))) < 1e-15 * 8
+
+
+@pytest.mark.parametrize("case", ["all_weighted", "none_weighted", "mixed", "gap_columns", "wide_weighted"])
+def test_string_kernel_launch_modes(case):
+    """The string kernel is specialised per launch (plain / weighted / general): every mode against the oracle."""
+    recs = synth.make_config(1, 6, offset=7000)
+    if case == "all_weighted":
+        md = [hostlib.MData.from_record(r, TH) for r in recs]
+    elif case == "none_weighted":
+        md = [hostlib.MData.seq_only(r["rows"]) for r in recs]
+    elif case == "mixed":
+        md = [hostlib.MData.from_record(r, TH) if i % 2 else hostlib.MData.seq_only(r["rows"]) for i, r in enumerate(recs)]
+    elif case == "gap_columns":   # a one-row record with '-' columns: one-hot-or-gap columns, score 1 on the gaps
+        md = [hostlib.MData.seq_only([r["rows"][0][:20] + "--" + r["rows"][0][20:40] + "-" + r["rows"][0][40:]]) for r in recs]
+    else:
+        md = hostlib.build_many(synth.make_config(3, 5, offset=7100), TH)     # 150-300 columns, weighted
+    flat = hostlib.SeqSet(md)
+    for kind in (L.STR_SUBST, L.STR_SIMPLE):
+        p = L.make_params(kind)
+        ctx = api.Context(p)
+        assert relerr(ctx.gram(ctx.upload(flat)), O.gram(oparams(p), flat.desc(), False)) < TOL
+
+
 def test_sharded_driver_single_rank_equals_gram():
     import torch
     from stem_kernel_b200 import sharded
