@@ -358,7 +358,11 @@ def run_b200(args, rank, world, local_rank):
         "gpu_launches_per_step": launches_per_step,
         "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": achieved / fp64_peak if fp64_peak else None,
-                     "traffic": None,
+                     # DRAM bytes of the stem kernels of one step: 4.44 MB per pair (read 3.27 + write 1.17) from the ncu
+                     # capture profiles/r01_stem_final_traffic_n256.csv, scaled by this rank's pair count
+                     "traffic": 4.44e6 * len(mine),
+                     "traffic_note": "per step, summed over the step's bucket launches like `achieved`; the per-pair DP "
+                                     "table (G0 slab, ~1.2 MB) lives in L2/HBM by design, see DESIGN.md 5.1",
                      "kernel": "stem_pairs_kernel", "kernel_ms_per_launch": kern_ms,
                      "kernel_share_of_step": kern_ms / (total_ms / args.steps),
                      "peak_source": "FP64 FMA probe run live on this GPU (stemk_fp64_peak); MEASURED_PEAKS.json has no "
