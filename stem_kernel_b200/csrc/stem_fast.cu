@@ -47,8 +47,8 @@ __host__ __device__ inline FastLayout fast_layout(uint32_t nwarps, uint32_t nx_c
   uint32_t off = 0;
   auto take = [&](uint32_t bytes) { uint32_t at = off; off += (bytes + 15u) & ~15u; return at; };
   L.tab = take(8 * 256);
-  L.yD0 = take(16 * ny_cap);  // {a, el}
-  L.yD1 = take(16 * ny_cap);  // {s2, up}
+  L.yD0 = take(16 * ny_cap);  // {s2, el}     (MATCH cells only)
+  L.yD1 = take(16 * ny_cap);  // {up*a*s2, up}
   L.yD2 = take(16 * ny_cap);  // {paths, bfreq}
   L.yD3 = take(8 * ny_cap);   // dn
   L.yI = take(8 * ny_cap);    // NodeI
@@ -154,8 +154,9 @@ __global__ void __launch_bounds__(32 * kFastMaxWarps, 1) stem_fast_kernel(const 
     // ---- stage the y record, clear the row flags
     for (uint32_t j = tid; j < Ny; j += blockDim.x) {
       const uint32_t gy = ry.node0 + j;
-      sts_v2f64(sb + (L.yD0 + 16 * j), make_double2(Y.a[gy], Y.el[gy]));
-      sts_v2f64(sb + (L.yD1 + 16 * j), make_double2(Y.s2[gy], Y.up[gy]));
+      const double ys2 = Y.s2[gy], yup = Y.up[gy];
+      sts_v2f64(sb + (L.yD0 + 16 * j), make_double2(ys2, Y.el[gy]));
+      sts_v2f64(sb + (L.yD1 + 16 * j), make_double2(yup * (Y.a[gy] * ys2), yup));   // H = up*a*s2 * sum(H children) (+ up*M)
       sts_v2f64(sb + (L.yD2 + 16 * j), make_double2(Y.paths[gy], Y.bfreq[gy]));
       sts_f64(sb + (L.yD3 + 8 * j), Y.dn[gy]);
       sts_nodei(sb + (L.yI + 8 * j), Y.nodei[gy]);
@@ -252,16 +253,19 @@ __global__ void __launch_bounds__(32 * kFastMaxWarps, 1) stem_fast_kernel(const 
       __syncwarp();
 
       // ---- phase B: sweep the y DAG level by level; lanes <-> (row r, node slot s)
-      // rows of the block rounded up to 1, 2, 4: lane = row * nslot + slot
-      const uint32_t rsh = cnt > 2u ? 2u : (cnt > 1u ? 1u : 0u);
+      // rows of the block rounded up to 1, 2, 4: lane = row * nslot + slot (all compile-time for one row per warp)
+      const uint32_t rsh = kFastRows == 1u ? 0u : (cnt > 2u ? 2u : (cnt > 1u ? 1u : 0u));
       const uint32_t nslot = 32u >> rsh;
-      const uint32_t r_raw = lane / nslot, slot = lane % nslot;
-      const bool live = r_raw < cnt;
+      const uint32_t r_raw = lane >> (5u - rsh), slot = lane & (nslot - 1u);
+      const bool live = kFastRows == 1u ? true : r_raw < cnt;
       const uint32_t r = live ? r_raw : 0u;
       const uint32_t gx = ps.node0 + i0 + r;
       const double xql = X.ql[gx], xbf = X.bfreq[gx];
       const uint32_t xl = X.len[gx], xbc = X.bcode[gx];
       const uint32_t hqrow = wrows + 2u * L.row_bytes * r, hrow = hqrow + L.row_bytes;
+      // MATCH needs |len_x - len_y| <= band; below the window G1 is identically 0 (length-monotone DAG)
+      const uint32_t len_lo = (band != 0u && xl > band) ? xl - band : 0u;
+      const uint32_t len_hi = band != 0u ? xl + band : 0xffffffffu;
       double racc = 0.0;
       uint32_t jbeg = lds_u32(sb + (L.yLev));
 #ifdef ABL_NO_B
@@ -273,14 +277,12 @@ __global__ void __launch_bounds__(32 * kFastMaxWarps, 1) stem_fast_kernel(const 
         for (uint32_t j = jbeg + slot; live && j < jend; j += nslot) {
           const NodeI ni = lds_nodei(sb + (L.yI + 8u * j));
           const uint32_t yl = ni.len;
-          if (band != 0u && yl + band < xl) {  // G1 == 0 here and below (length-monotone DAG)
+          if (yl < len_lo) {  // G1 == 0 here and below
             sts_f64(sb + (hrow + 8u * j), 0.0);
             continue;
           }
-          const uint32_t dl = xl > yl ? xl - yl : yl - xl;
-          const bool in_band = (band == 0u) || (dl <= band);
-          const double2 d0 = lds_v2f64(sb + (L.yD0 + 16u * j));  // {a_y, el_y}
-          const double2 d1 = lds_v2f64(sb + (L.yD1 + 16u * j));  // {s2_y, up_y}
+          const bool in_band = yl <= len_hi;
+          const double2 d1 = lds_v2f64(sb + (L.yD1 + 16u * j));  // {up*a*s2, up}
           uint32_t e = L.yC + 2u * (ni.e4_bcode >> 8);
           const uint32_t eend = e + 8u * ni.deg4;
           double S0 = 0.0, S1 = 0.0, m = 0.0;
@@ -295,9 +297,10 @@ __global__ void __launch_bounds__(32 * kFastMaxWarps, 1) stem_fast_kernel(const 
               S0 += lds_f64(sb + (hrow + o2)); R0 += lds_f64(sb + (hqrow + o2));
               S1 += lds_f64(sb + (hrow + o3)); R1 += lds_f64(sb + (hqrow + o3));
             }
+            const double2 d0 = lds_v2f64(sb + (L.yD0 + 16u * j));  // {s2_y, el_y}
             const double2 d2 = lds_v2f64(sb + (L.yD2 + 16u * j));  // {paths_y, bfreq_y}
             const double vs = lds_f64(sb + (L.tab + 8u * (xbc * 16u + (ni.e4_bcode & 0xffu)))) * xbf * d2.y;
-            m = vs * fma(d0.y, xql, d1.x * (R0 + R1));
+            m = vs * fma(d0.y, xql, d0.x * (R0 + R1));
             racc = fma(d2.x, m, racc);
           } else {
 #pragma unroll 1
@@ -309,8 +312,7 @@ __global__ void __launch_bounds__(32 * kFastMaxWarps, 1) stem_fast_kernel(const 
               S1 += lds_f64(sb + hrow + (c4.y >> 16));
             }
           }
-          const double g1 = fma(d0.x, d1.x * (S0 + S1), m);
-          sts_f64(sb + (hrow + 8u * j), d1.y * g1);
+          sts_f64(sb + (hrow + 8u * j), fma(d1.x, S0 + S1, d1.y * m));   // up_y * (M + a_y*s2_y*sum)
         }
         jbeg = jend;
         __syncwarp();
