@@ -336,6 +336,17 @@ std::string compile_set(const stemk_seqset_desc& s, double g, int n_threads, Com
     c.max_nlev = std::max(c.max_nlev, h.nlev);
   }
   c.cost_off.push_back(c.cost_pd.size());
+  // packed row records (absolute child ranges, so built after the merge)
+  c.xnode.resize(c.a.size());
+  for (uint32_t r = 0; r < n; ++r) {
+    const RecDev& h = c.rec[r];
+    for (uint32_t k = 0; k < h.N; ++k) {
+      const uint32_t gk = h.node0 + k;
+      XNode& xn = c.xnode[gk];
+      xn.s2 = c.s2[gk]; xn.a = c.a[gk]; xn.up = c.up[gk]; xn.ql = c.ql[gk]; xn.bfreq = c.bfreq[gk]; xn.paths = c.paths[gk];
+      xn.e0 = c.coff[h.coff0 + k]; xn.e1 = c.coff[h.coff0 + k + 1]; xn.len = c.len[gk]; xn.bcode = c.bcode[gk];
+    }
+  }
   if (timing) {
     auto t2 = std::chrono::steady_clock::now();
     std::fprintf(stderr, "compile_set: %u records, per-record %.1f ms (%d threads), merge %.1f ms\n", n,

@@ -181,9 +181,8 @@ __global__ void __launch_bounds__(32 * kFastMaxWarps, 1) stem_fast_kernel(const 
       const uint32_t sl = t % g, b = t / g;
       const PairSlot ps = s_slot[sl];
       if (b >= ps.nblk) continue;
-      const uint32_t blk = X.blk[ps.blk0 + b];
+      const uint32_t blk = kFastRows == 1u ? (b | (1u << 16)) : X.blk[ps.blk0 + b];   // one row per block: block b = row b
       const uint32_t i0 = blk & 0xffffu, cnt = blk >> 16;  // cnt in 1..kFastRows
-      const uint32_t* __restrict__ xcoff = X.coff + ps.coff0;
       double* __restrict__ G0 = slab + sl * slot_stride;
       const uint32_t done = L.done + sl * P.nx_cap;
       double* __restrict__ rowacc = P.rowacc + ((size_t)blockIdx.x * kGroup + sl) * P.nx_cap;
@@ -192,8 +191,10 @@ __global__ void __launch_bounds__(32 * kFastMaxWarps, 1) stem_fast_kernel(const 
       for (uint32_t r = 0; r < cnt; ++r) {
         const uint32_t i = i0 + r;
         const uint32_t hq = wrows + 2u * L.row_bytes * r;
-        const uint32_t e0 = xcoff[i], e1 = xcoff[i + 1];
-        const double xs2 = X.s2[ps.node0 + i];
+        const XNode* __restrict__ xn = X.xnode + ps.node0 + i;   // one 64-byte line, the same address for every lane
+        const uint4 xi4 = __ldg(reinterpret_cast<const uint4*>(xn) + 3);
+        const uint32_t e0 = xi4.x, e1 = xi4.y;
+        const double xs2 = __ldg(&xn->s2);
         for (uint32_t eb = e0; eb < e1 || eb == e0; eb += 32u) {
           const uint32_t ne = min(32u, e1 - eb);
           const bool last = eb + 32u >= e1;
@@ -260,8 +261,11 @@ __global__ void __launch_bounds__(32 * kFastMaxWarps, 1) stem_fast_kernel(const 
       const bool live = kFastRows == 1u ? true : r_raw < cnt;
       const uint32_t r = live ? r_raw : 0u;
       const uint32_t gx = ps.node0 + i0 + r;
-      const double xql = X.ql[gx], xbf = X.bfreq[gx];
-      const uint32_t xl = X.len[gx], xbc = X.bcode[gx];
+      const XNode* __restrict__ xr = X.xnode + gx;
+      const double2 x12 = __ldg(reinterpret_cast<const double2*>(xr) + 1), x22 = __ldg(reinterpret_cast<const double2*>(xr) + 2);
+      const uint4 xr4 = __ldg(reinterpret_cast<const uint4*>(xr) + 3);
+      const double xql = x12.y, xbf = x22.x, xpaths = x22.y;
+      const uint32_t xl = xr4.z, xbc = xr4.w;
       const uint32_t hqrow = wrows + 2u * L.row_bytes * r, hrow = hqrow + L.row_bytes;
       // MATCH needs |len_x - len_y| <= band; below the window G1 is identically 0 (length-monotone DAG)
       const uint32_t len_lo = (band != 0u && xl > band) ? xl - band : 0u;
@@ -320,13 +324,14 @@ __global__ void __launch_bounds__(32 * kFastMaxWarps, 1) stem_fast_kernel(const 
       // per-row path-weighted MATCH sum (lanes of one row are contiguous: reduce inside the half / full warp)
 
       for (uint32_t o = nslot >> 1; o > 0u; o >>= 1) racc += __shfl_xor_sync(0xffffffffu, racc, o);
-      if (slot == 0u && live) rowacc[i0 + r] = X.paths[gx] * racc;   // per-row slot in global scratch (L2)
+      if (slot == 0u && live) rowacc[i0 + r] = xpaths * racc;   // per-row slot in global scratch (L2)
 
       // ---- phase C: finished rows G0s(i,:) = up_x(i) * dn_y * (H + a_x*HQ), then publish them
       for (uint32_t rr = 0; rr < cnt; ++rr) {
         const uint32_t i = i0 + rr;
         const uint32_t hq2 = wrows + 2u * L.row_bytes * rr, h2 = hq2 + L.row_bytes;
-        const double xa2 = X.a[ps.node0 + i], xup = X.up[ps.node0 + i];
+        const XNode* __restrict__ xc = X.xnode + ps.node0 + i;
+        const double xa2 = __ldg(&xc->a), xup = __ldg(&xc->up);
         double* __restrict__ g0row = G0 + (size_t)i * NYS;
 #ifdef ABL_NO_C
         for (uint32_t j = lane; j < 32u; j += 32u)

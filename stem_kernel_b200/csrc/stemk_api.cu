@@ -226,7 +226,7 @@ int stemk_upload(stemk_ctx* ctx, const stemk_seqset_desc* desc, stemk_set** out)
                o_boff = place(off, h.boff), o_bab = place(off, h.bab), o_bfq = place(off, h.bfq),
                o_ccode = place(off, h.ccode), o_cw = place(off, h.cw), o_prof = place(off, h.prof),
                o_text = place(off, h.text), o_up = place(off, h.up), o_dn = place(off, h.dn), o_s2 = place(off, h.s2),
-               o_nodei = place(off, h.nodei), o_c16 = place(off, h.c16), o_blk = place(off, h.blk);
+               o_nodei = place(off, h.nodei), o_c16 = place(off, h.c16), o_blk = place(off, h.blk), o_xnode = place(off, h.xnode);
   off = (off + 255) & ~size_t(255);
   cudaError_t e = s->blob.reserve(std::max<size_t>(off, 256));
   // every array goes straight from its host vector to its place in the blob (no staging copy)
@@ -238,7 +238,7 @@ int stemk_upload(stemk_ctx* ctx, const stemk_seqset_desc* desc, stemk_set** out)
   put(o_bfreq, h.bfreq); put(o_len, h.len); put(o_bcode, h.bcode); put(o_coff, h.coff); put(o_cidx, h.cidx);
   put(o_ce, h.ce); put(o_lev, h.lev_off); put(o_boff, h.boff); put(o_bab, h.bab); put(o_bfq, h.bfq);
   put(o_ccode, h.ccode); put(o_cw, h.cw); put(o_prof, h.prof); put(o_text, h.text);
-  put(o_up, h.up); put(o_dn, h.dn); put(o_s2, h.s2); put(o_nodei, h.nodei); put(o_c16, h.c16); put(o_blk, h.blk);
+  put(o_up, h.up); put(o_dn, h.dn); put(o_s2, h.s2); put(o_nodei, h.nodei); put(o_c16, h.c16); put(o_blk, h.blk); put(o_xnode, h.xnode);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) { s->blob.release(); delete s; return cuda_fail(ctx, e, "set upload"); }
   char* b = static_cast<char*>(s->blob.p);
@@ -252,7 +252,7 @@ int stemk_upload(stemk_ctx* ctx, const stemk_seqset_desc* desc, stemk_set** out)
   v.bfq = (const double*)(b + o_bfq); v.ccode = (const uint8_t*)(b + o_ccode); v.cw = (const double*)(b + o_cw);
   v.prof = (const float*)(b + o_prof); v.text = (const uint8_t*)(b + o_text);
   v.up = (const double*)(b + o_up); v.dn = (const double*)(b + o_dn); v.s2 = (const double*)(b + o_s2);
-  v.nodei = (const NodeI*)(b + o_nodei); v.c16 = (const uint16_t*)(b + o_c16); v.blk = (const uint32_t*)(b + o_blk);
+  v.nodei = (const NodeI*)(b + o_nodei); v.c16 = (const uint16_t*)(b + o_c16); v.blk = (const uint32_t*)(b + o_blk); v.xnode = (const XNode*)(b + o_xnode);
   *out = s;
   return STEMK_OK;
 }

@@ -44,6 +44,14 @@ enum { REC_HAS_WEIGHT = 1u, REC_SIMPLE_COLS = 2u, REC_SIMPLE_BPF = 4u,
 constexpr uint32_t kFastRows = STEMK_ROWS;  // rows (1, 2 or 4) a warp of the fast stem kernel sweeps in lockstep
 constexpr uint32_t kFastMaxN = 1024;  // largest staged record (non-leaf nodes) of the fast stem kernel
 
+struct __attribute__((aligned(16))) XNode {   // everything the fast kernel needs about a ROW node, one 64-byte line
+  double s2, a;         // g^(len-2-B), g*g*weight
+  double up, ql;        // g^(B-len), sum_children e*G0(child, leaf column)
+  double bfreq, paths;  // base-pair frequency, root->node paths
+  uint32_t e0, e1;      // its non-leaf children in cidx (absolute)
+  uint32_t len, bcode;
+};
+
 struct NodeI {        // integer part of a node for the fast kernel (8 bytes)
   uint32_t e4_bcode;  // (offset of its padded child list inside the record, in entries) << 8 | bcode
   uint16_t deg4;      // padded list length / 4
@@ -73,6 +81,7 @@ struct SetView {
   const double* dn;      // g^(len - B)
   const double* s2;      // g^(len - 2 - B)
   const NodeI* nodei;
+  const XNode* xnode;
   const uint16_t* c16;   // padded child lists as byte offsets into a row (8 * record-local node number), 8N = the all-zero dummy column
   const uint32_t* blk;   // row blocks: first row | count << 16
   // general base-pair profiles (alignments / IUPAC)
@@ -95,6 +104,7 @@ struct CompiledSet {
   std::vector<float> prof;
   std::vector<double> up, dn, s2;
   std::vector<NodeI> nodei;
+  std::vector<XNode> xnode;
   std::vector<uint16_t> c16;
   std::vector<uint32_t> blk;
   uint32_t max_E4 = 0, max_fastN = 0, n_fast = 0;  // over fast-eligible records

@@ -308,6 +308,31 @@ def test_config1_libsvm_cross_validation_is_identical():
     assert relerr(got[:40, :40], z["gram"]) < TOL
 
 
+def test_long_records_take_the_general_kernel_next_to_fast_ones():
+    """500-nt records: pairs up to ~490 nt apart push the fast path's gap powers g^(+-len/2) out of its safe range
+    and the DAGs are big (~1000 nodes), so these records must run on the general kernel while the 150-300 nt
+    records of the same set keep the fast one -- both inside one stemk_gram call."""
+    recs = [synth.ncrna_like(424242, i, lmin=500, lmax=500) for i in range(3)] + synth.make_config(3, 4, offset=8800)
+    md = [hostlib.MData.from_record(r, TH) for r in recs]
+    assert max(m.sizes()["n_nodes"] for m in md[:3]) > 700
+    flat = hostlib.SeqSet(md)
+    for kind in (L.SU_STEM, L.SU_STEM_STR):
+        p = L.make_params(kind)
+        ctx = api.Context(p)
+        got = ctx.gram(ctx.upload(flat))
+        assert relerr(got, O.gram(oparams(p), flat.desc(), False)) < TOL
+
+
+def test_record_too_large_for_shared_memory_is_an_error_not_a_wrong_answer():
+    recs = [synth.ncrna_like(77, 0, lmin=1500, lmax=1500)]
+    md = [hostlib.MData.from_record(r, 0.001) for r in recs]      # low threshold: every background pair is a node
+    if md[0].sizes()["n_nodes"] < 2500:
+        pytest.skip("record not large enough to exceed the staging limit")
+    ctx = api.Context(L.make_params(L.SU_STEM))
+    with pytest.raises(api.StemkError, match="shared memory"):
+        ctx.gram(ctx.upload(md))
+
+
 def test_rectangular_matrix_with_sv_subset_at_moderate_size():
     """KernelMatrix::calculate(test, train) / the one-row variant with an sv_index (kernel_matrix.cpp:635-754):
     60 test x 150 train C3 records, 40 support-vector columns, normalised; sampled entries against the oracle,
