@@ -338,12 +338,15 @@ std::string compile_set(const stemk_seqset_desc& s, double g, int n_threads, Com
   c.cost_off.push_back(c.cost_pd.size());
   // packed row records (absolute child ranges, so built after the merge)
   c.xnode.resize(c.a.size());
+  c.yband.resize(c.a.size());
   for (uint32_t r = 0; r < n; ++r) {
     const RecDev& h = c.rec[r];
     for (uint32_t k = 0; k < h.N; ++k) {
       const uint32_t gk = h.node0 + k;
       XNode& xn = c.xnode[gk];
       xn.s2 = c.s2[gk]; xn.a = c.a[gk]; xn.up = c.up[gk]; xn.ql = c.ql[gk]; xn.bfreq = c.bfreq[gk]; xn.paths = c.paths[gk];
+      NodeB& nb = c.yband[gk];
+      nb.s2 = c.s2[gk]; nb.el = c.el[gk]; nb.paths = c.paths[gk]; nb.bfreq = c.bfreq[gk];
       xn.e0 = c.coff[h.coff0 + k]; xn.e1 = c.coff[h.coff0 + k + 1]; xn.len = c.len[gk]; xn.bcode = c.bcode[gk];
     }
   }

@@ -58,6 +58,8 @@ struct stemk_ctx {
   DevBuf scratch, carry, tmp_stem, tmp_str, idx_x, idx_y, vals, matrix, order, rowacc;
   unsigned long long* d_bucket = nullptr;  // count[16] | start[16] | queue heads[16]
   int use_fast = 1;                        // STEMK_FAST=0 in the environment forces the general stem kernel
+  int use_rows = 1;                        // STEMK_ROWSK=0: the one-row-per-warp fast kernel instead of the row-block kernel
+  int rows_warps = 32;                     // STEMK_ROWS_WARPS: warps per CTA of the row-block kernel
   std::string err;
   // stats
   uint64_t launches = 0;
@@ -172,6 +174,8 @@ int stemk_create(stemk_ctx** out, const stemk_params* params, int device) {
   c->params = *params;
   make_tables(*params, &c->tables);
   if (const char* f = std::getenv("STEMK_FAST")) c->use_fast = std::atoi(f);
+  if (const char* f = std::getenv("STEMK_ROWSK")) c->use_rows = std::atoi(f);
+  if (const char* f = std::getenv("STEMK_ROWS_WARPS")) c->rows_warps = std::max(1, std::min(32, std::atoi(f)));
   bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaMalloc((void**)&c->d_pair_tab, sizeof(double) * 256) == cudaSuccess &&
             cudaMalloc((void**)&c->d_subst, sizeof(double) * 16) == cudaSuccess &&
@@ -226,7 +230,7 @@ int stemk_upload(stemk_ctx* ctx, const stemk_seqset_desc* desc, stemk_set** out)
                o_boff = place(off, h.boff), o_bab = place(off, h.bab), o_bfq = place(off, h.bfq),
                o_ccode = place(off, h.ccode), o_cw = place(off, h.cw), o_prof = place(off, h.prof),
                o_text = place(off, h.text), o_up = place(off, h.up), o_dn = place(off, h.dn), o_s2 = place(off, h.s2),
-               o_nodei = place(off, h.nodei), o_c16 = place(off, h.c16), o_blk = place(off, h.blk), o_xnode = place(off, h.xnode);
+               o_nodei = place(off, h.nodei), o_c16 = place(off, h.c16), o_blk = place(off, h.blk), o_xnode = place(off, h.xnode), o_yband = place(off, h.yband);
   off = (off + 255) & ~size_t(255);
   cudaError_t e = s->blob.reserve(std::max<size_t>(off, 256));
   // every array goes straight from its host vector to its place in the blob (no staging copy)
@@ -238,7 +242,7 @@ int stemk_upload(stemk_ctx* ctx, const stemk_seqset_desc* desc, stemk_set** out)
   put(o_bfreq, h.bfreq); put(o_len, h.len); put(o_bcode, h.bcode); put(o_coff, h.coff); put(o_cidx, h.cidx);
   put(o_ce, h.ce); put(o_lev, h.lev_off); put(o_boff, h.boff); put(o_bab, h.bab); put(o_bfq, h.bfq);
   put(o_ccode, h.ccode); put(o_cw, h.cw); put(o_prof, h.prof); put(o_text, h.text);
-  put(o_up, h.up); put(o_dn, h.dn); put(o_s2, h.s2); put(o_nodei, h.nodei); put(o_c16, h.c16); put(o_blk, h.blk); put(o_xnode, h.xnode);
+  put(o_up, h.up); put(o_dn, h.dn); put(o_s2, h.s2); put(o_nodei, h.nodei); put(o_c16, h.c16); put(o_blk, h.blk); put(o_xnode, h.xnode); put(o_yband, h.yband);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) { s->blob.release(); delete s; return cuda_fail(ctx, e, "set upload"); }
   char* b = static_cast<char*>(s->blob.p);
@@ -252,7 +256,7 @@ int stemk_upload(stemk_ctx* ctx, const stemk_seqset_desc* desc, stemk_set** out)
   v.bfq = (const double*)(b + o_bfq); v.ccode = (const uint8_t*)(b + o_ccode); v.cw = (const double*)(b + o_cw);
   v.prof = (const float*)(b + o_prof); v.text = (const uint8_t*)(b + o_text);
   v.up = (const double*)(b + o_up); v.dn = (const double*)(b + o_dn); v.s2 = (const double*)(b + o_s2);
-  v.nodei = (const NodeI*)(b + o_nodei); v.c16 = (const uint16_t*)(b + o_c16); v.blk = (const uint32_t*)(b + o_blk); v.xnode = (const XNode*)(b + o_xnode);
+  v.nodei = (const NodeI*)(b + o_nodei); v.c16 = (const uint16_t*)(b + o_c16); v.blk = (const uint32_t*)(b + o_blk); v.xnode = (const XNode*)(b + o_xnode); v.yband = (const NodeB*)(b + o_yband);
   *out = s;
   return STEMK_OK;
 }
@@ -302,7 +306,12 @@ int stemk_pairs_device(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, s
     if (n_pairs > 0xffffffffull) return fail(ctx, STEMK_ERR_ARG, "more than 2^32 pairs in one call");
     // ---- classify: trivial pairs are finished, the others go to the general kernel (bucket 0) or to the fast
     // kernel's size buckets (1..), each bucket keeping the caller's pair order
-    static const uint32_t kCaps[kMaxFastBuckets] = {256, 320, 384, 448, 512, 640, 768, kFastMaxN};
+    static const uint32_t kCapsFast[kMaxFastBuckets] = {256, 320, 384, 448, 512, 640, 768, kFastMaxN};
+    // row-block kernel: the staged record decides how many rows (32 / 16 / 8) fit next to it in shared memory
+    static const uint32_t kCapsRows[kMaxFastBuckets] = {384, 704, kFastMaxN, 0, 0, 0, 0, 0};
+    static const uint32_t kRowsOf[3] = {32, 16, 8};
+    const bool rows_mode = ctx->use_rows != 0;
+    const uint32_t* kCaps = rows_mode ? kCapsRows : kCapsFast;
     const bool any_fast = ctx->use_fast && x->host.n_fast > 0 && y->host.n_fast > 0;
     StemClassify C;
     C.X = x->view; C.Y = y->view; C.xi = d_xi; C.yi = d_yi; C.n_pairs = n_pairs; C.out = stem_out;
@@ -310,7 +319,7 @@ int stemk_pairs_device(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, s
     unsigned long long* heads = ctx->d_bucket + 32;
     C.n_caps = 0; C.allow_fast = any_fast;
     if (any_fast)
-      for (int b = 0; b < kMaxFastBuckets; ++b) {
+      for (int b = 0; b < kMaxFastBuckets && kCaps[b] != 0; ++b) {
         C.caps[C.n_caps++] = kCaps[b];
         if (kCaps[b] >= y->host.max_fastN) break;
       }
@@ -346,8 +355,39 @@ int stemk_pairs_device(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, s
       CU(le);
       ctx->launches += 1;
     }
+    // ---- row-block kernel, one launch per rows-per-block class
+    for (int b = 0; rows_mode && b < C.n_caps; ++b) {
+      const uint32_t ny_cap = std::min(C.caps[b], std::max(1u, y->host.max_fastN));
+      const uint32_t lo = b ? C.caps[b - 1] : 0u;
+      uint32_t e4_cap = 4;
+      bool any = false;
+      for (const RecDev& r : y->host.rec)
+        if ((r.flags & REC_FAST) && r.N > lo && r.N <= C.caps[b]) { e4_cap = std::max(e4_cap, r.e4); any = true; }
+      if (!any) continue;
+      const uint32_t xlev_cap = std::max(1u, x->host.max_nlev);
+      const size_t smem = stem_rows_smem_bytes(kRowsOf[b], ny_cap, e4_cap, lev_cap, xlev_cap);
+      const size_t budget = std::min<size_t>(ctx->smem_optin, (size_t)227 * 1024);
+      if (smem > budget) return fail(ctx, STEMK_ERR_NOMEM, "row-block stem kernel: record does not fit in shared memory");
+      const int grid = (int)std::min<size_t>((n_pairs + kFastGroup - 1) / kFastGroup, (size_t)ctx->sm_count);
+      const unsigned long long stride = (unsigned long long)kFastGroup * nx_cap * ((ny_cap + 3u) & ~3u);
+      const unsigned long long ra_stride = (unsigned long long)kFastGroup * nx_cap + 1024u;
+      CU(ctx->scratch.reserve(sizeof(double) * stride * grid));
+      CU(ctx->rowacc.reserve(sizeof(double) * ra_stride * grid));
+      StemRowsLaunch F;
+      F.X = x->view; F.Y = y->view; F.xi = d_xi; F.yi = d_yi; F.out = stem_out; F.order = C.order;
+      F.start = C.start; F.count = C.count; F.counter = heads + 1 + b; F.bucket = 1 + b;
+      F.scratch = (double*)ctx->scratch.p; F.scratch_stride = stride; F.rowacc = (double*)ctx->rowacc.p;
+      F.rowacc_stride = ra_stride; F.pair_tab = ctx->d_pair_tab;
+      F.len_band = ctx->params.len_band; F.nx_cap = nx_cap; F.ny_cap = ny_cap; F.e4_cap = e4_cap;
+      F.ylev_cap = lev_cap; F.xlev_cap = xlev_cap;
+      stemk_ctx::Timed tm = timed_begin(ctx, 0, st);
+      cudaError_t le = launch_stem_rows(F, kRowsOf[b], grid, ctx->rows_warps, smem, st);
+      timed_end(ctx, tm, st);
+      CU(le);
+      ctx->launches += 1;
+    }
     // ---- fast kernel, one launch per size bucket (shared memory and CTAs per SM sized for the bucket)
-    for (int b = 0; b < C.n_caps; ++b) {
+    for (int b = 0; !rows_mode && b < C.n_caps; ++b) {
       const uint32_t ny_cap = std::min(C.caps[b], std::max(1u, y->host.max_fastN));
       const uint32_t e4_cap = std::max(4u, y->host.max_E4);
       const size_t budget = std::min<size_t>(ctx->smem_optin, (size_t)227 * 1024);

@@ -52,6 +52,11 @@ struct __attribute__((aligned(16))) XNode {   // everything the fast kernel need
   uint32_t len, bcode;
 };
 
+struct __attribute__((aligned(16))) NodeB {   // what a MATCH cell needs about a COLUMN node (row-block kernel), 32 bytes
+  double s2, el;        // g^(len-2-B), sum over leaf children of the edge factor
+  double paths, bfreq;  // root->node paths, base-pair frequency
+};
+
 struct NodeI {        // integer part of a node for the fast kernel (8 bytes)
   uint32_t e4_bcode;  // (offset of its padded child list inside the record, in entries) << 8 | bcode
   uint16_t deg4;      // padded list length / 4
@@ -82,6 +87,7 @@ struct SetView {
   const double* s2;      // g^(len - 2 - B)
   const NodeI* nodei;
   const XNode* xnode;
+  const NodeB* yband;
   const uint16_t* c16;   // padded child lists as byte offsets into a row (8 * record-local node number), 8N = the all-zero dummy column
   const uint32_t* blk;   // row blocks: first row | count << 16
   // general base-pair profiles (alignments / IUPAC)
@@ -105,6 +111,7 @@ struct CompiledSet {
   std::vector<double> up, dn, s2;
   std::vector<NodeI> nodei;
   std::vector<XNode> xnode;
+  std::vector<NodeB> yband;
   std::vector<uint16_t> c16;
   std::vector<uint32_t> blk;
   uint32_t max_E4 = 0, max_fastN = 0, n_fast = 0;  // over fast-eligible records
