@@ -71,7 +71,9 @@ struct StemRowsLaunch {
   unsigned long long rowacc_stride;  // doubles per CTA
   const double* pair_tab;
   uint32_t len_band, nx_cap, ny_cap, e4_cap, ylev_cap, xlev_cap;
+  uint32_t team_warps;               // warps of a team (a team sweeps one row block)
 };
+constexpr int kRowsMaxThreads = 768;  // launch bound of the row-block kernel (85 registers per thread)
 
 struct StemClassify {
   SetView X, Y;
@@ -110,8 +112,9 @@ int stem_max_ctas_per_sm(size_t smem);
 size_t stem_fast_smem_bytes(uint32_t nwarps, uint32_t nx_cap, uint32_t ny_cap, uint32_t e4_cap, uint32_t lev_cap);
 int stem_fast_ctas_per_sm(int nwarps, size_t smem);
 cudaError_t launch_stem_fast(const StemFastLaunch& p, int grid, int nwarps, size_t smem, cudaStream_t stream);
-size_t stem_rows_smem_bytes(uint32_t rows, uint32_t ny_cap, uint32_t e4_cap, uint32_t ylev_cap, uint32_t xlev_cap);
-cudaError_t launch_stem_rows(const StemRowsLaunch& p, uint32_t rows, int grid, int nwarps, size_t smem, cudaStream_t stream);
+size_t stem_rows_smem_bytes(uint32_t rows, uint32_t nteams, uint32_t team_warps, uint32_t nx_cap, uint32_t ny_cap,
+                            uint32_t e4_cap, uint32_t ylev_cap, uint32_t xlev_cap);
+cudaError_t launch_stem_rows(const StemRowsLaunch& p, uint32_t rows, int grid, int nteams, size_t smem, cudaStream_t stream);
 cudaError_t launch_classify(const StemClassify& c, int n_buckets, unsigned long long* counters, cudaStream_t stream);
 void string_shape_for(uint32_t ly_cap, int mode, int* cw, int* tp);
 // mode: 0 plain one-hot columns, 1 weighted, 2 naive characters, 3 general (see string_kernel.cu)

@@ -7,6 +7,7 @@
 // returns STEMK_ERR_CUDA.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
@@ -59,7 +60,7 @@ struct stemk_ctx {
   unsigned long long* d_bucket = nullptr;  // count[16] | start[16] | queue heads[16]
   int use_fast = 1;                        // STEMK_FAST=0 in the environment forces the general stem kernel
   int use_rows = 1;                        // STEMK_ROWSK=0: the one-row-per-warp fast kernel instead of the row-block kernel
-  int rows_warps = 32;                     // STEMK_ROWS_WARPS: warps per CTA of the row-block kernel
+  int rows_tw = 4, rows_r = 0, rows_nt = 0; // STEMK_ROWS_TW / _R / _NT: warps per team, forced rows per block, team limit
   std::string err;
   // stats
   uint64_t launches = 0;
@@ -175,7 +176,9 @@ int stemk_create(stemk_ctx** out, const stemk_params* params, int device) {
   make_tables(*params, &c->tables);
   if (const char* f = std::getenv("STEMK_FAST")) c->use_fast = std::atoi(f);
   if (const char* f = std::getenv("STEMK_ROWSK")) c->use_rows = std::atoi(f);
-  if (const char* f = std::getenv("STEMK_ROWS_WARPS")) c->rows_warps = std::max(1, std::min(32, std::atoi(f)));
+  if (const char* f = std::getenv("STEMK_ROWS_TW")) c->rows_tw = std::max(1, std::min(8, std::atoi(f)));
+  if (const char* f = std::getenv("STEMK_ROWS_R")) c->rows_r = std::atoi(f);
+  if (const char* f = std::getenv("STEMK_ROWS_NT")) c->rows_nt = std::atoi(f);
   bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaMalloc((void**)&c->d_pair_tab, sizeof(double) * 256) == cudaSuccess &&
             cudaMalloc((void**)&c->d_subst, sizeof(double) * 16) == cudaSuccess &&
@@ -306,12 +309,8 @@ int stemk_pairs_device(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, s
     if (n_pairs > 0xffffffffull) return fail(ctx, STEMK_ERR_ARG, "more than 2^32 pairs in one call");
     // ---- classify: trivial pairs are finished, the others go to the general kernel (bucket 0) or to the fast
     // kernel's size buckets (1..), each bucket keeping the caller's pair order
-    static const uint32_t kCapsFast[kMaxFastBuckets] = {256, 320, 384, 448, 512, 640, 768, kFastMaxN};
-    // row-block kernel: the staged record decides how many rows (32 / 16 / 8) fit next to it in shared memory
-    static const uint32_t kCapsRows[kMaxFastBuckets] = {384, 704, kFastMaxN, 0, 0, 0, 0, 0};
-    static const uint32_t kRowsOf[3] = {32, 16, 8};
+    static const uint32_t kCaps[kMaxFastBuckets] = {256, 320, 384, 448, 512, 640, 768, kFastMaxN};
     const bool rows_mode = ctx->use_rows != 0;
-    const uint32_t* kCaps = rows_mode ? kCapsRows : kCapsFast;
     const bool any_fast = ctx->use_fast && x->host.n_fast > 0 && y->host.n_fast > 0;
     StemClassify C;
     C.X = x->view; C.Y = y->view; C.xi = d_xi; C.yi = d_yi; C.n_pairs = n_pairs; C.out = stem_out;
@@ -319,7 +318,7 @@ int stemk_pairs_device(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, s
     unsigned long long* heads = ctx->d_bucket + 32;
     C.n_caps = 0; C.allow_fast = any_fast;
     if (any_fast)
-      for (int b = 0; b < kMaxFastBuckets && kCaps[b] != 0; ++b) {
+      for (int b = 0; b < kMaxFastBuckets; ++b) {
         C.caps[C.n_caps++] = kCaps[b];
         if (kCaps[b] >= y->host.max_fastN) break;
       }
@@ -355,7 +354,7 @@ int stemk_pairs_device(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, s
       CU(le);
       ctx->launches += 1;
     }
-    // ---- row-block kernel, one launch per rows-per-block class
+    // ---- row-block kernel, one launch per size bucket: as many teams as fit next to the staged record
     for (int b = 0; rows_mode && b < C.n_caps; ++b) {
       const uint32_t ny_cap = std::min(C.caps[b], std::max(1u, y->host.max_fastN));
       const uint32_t lo = b ? C.caps[b - 1] : 0u;
@@ -365,12 +364,23 @@ int stemk_pairs_device(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, s
         if ((r.flags & REC_FAST) && r.N > lo && r.N <= C.caps[b]) { e4_cap = std::max(e4_cap, r.e4); any = true; }
       if (!any) continue;
       const uint32_t xlev_cap = std::max(1u, x->host.max_nlev);
-      const size_t smem = stem_rows_smem_bytes(kRowsOf[b], ny_cap, e4_cap, lev_cap, xlev_cap);
-      const size_t budget = std::min<size_t>(ctx->smem_optin, (size_t)227 * 1024);
-      if (smem > budget) return fail(ctx, STEMK_ERR_NOMEM, "row-block stem kernel: record does not fit in shared memory");
+      const size_t budget = std::min<size_t>(ctx->smem_optin, (size_t)227 * 1024) - 512;   // static shared memory
+      const uint32_t tw = (uint32_t)ctx->rows_tw;
+      auto teams_for = [&](uint32_t R) {
+        uint32_t nt = 0;
+        const uint32_t lim = std::min<uint32_t>(15u, (uint32_t)kRowsMaxThreads / (32u * tw));
+        while (nt < lim && stem_rows_smem_bytes(R, nt + 1, tw, nx_cap, ny_cap, e4_cap, lev_cap, xlev_cap) <= budget) ++nt;
+        if (ctx->rows_nt > 0) nt = std::min<uint32_t>(nt, (uint32_t)ctx->rows_nt);
+        return nt;
+      };
+      uint32_t R = 8, nt = teams_for(8);
+      if (ctx->rows_r == 4 || ctx->rows_r == 8 || ctx->rows_r == 16) { R = (uint32_t)ctx->rows_r; nt = teams_for(R); }
+      else if (nt < 2) { R = 4; nt = teams_for(4); }
+      if (nt < 1) return fail(ctx, STEMK_ERR_NOMEM, "row-block stem kernel: record does not fit in shared memory");
+      const size_t smem = stem_rows_smem_bytes(R, nt, tw, nx_cap, ny_cap, e4_cap, lev_cap, xlev_cap);
       const int grid = (int)std::min<size_t>((n_pairs + kFastGroup - 1) / kFastGroup, (size_t)ctx->sm_count);
       const unsigned long long stride = (unsigned long long)kFastGroup * nx_cap * ((ny_cap + 3u) & ~3u);
-      const unsigned long long ra_stride = (unsigned long long)kFastGroup * nx_cap + 1024u;
+      const unsigned long long ra_stride = (unsigned long long)kFastGroup * nx_cap;
       CU(ctx->scratch.reserve(sizeof(double) * stride * grid));
       CU(ctx->rowacc.reserve(sizeof(double) * ra_stride * grid));
       StemRowsLaunch F;
@@ -379,9 +389,10 @@ int stemk_pairs_device(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, s
       F.scratch = (double*)ctx->scratch.p; F.scratch_stride = stride; F.rowacc = (double*)ctx->rowacc.p;
       F.rowacc_stride = ra_stride; F.pair_tab = ctx->d_pair_tab;
       F.len_band = ctx->params.len_band; F.nx_cap = nx_cap; F.ny_cap = ny_cap; F.e4_cap = e4_cap;
-      F.ylev_cap = lev_cap; F.xlev_cap = xlev_cap;
+      F.ylev_cap = lev_cap; F.xlev_cap = xlev_cap; F.team_warps = tw;
+      if (std::getenv("STEMK_TIMING")) std::fprintf(stderr, "rows bucket %d: cap %u R %u teams %u smem %zu\n", b, ny_cap, R, nt, smem);
       stemk_ctx::Timed tm = timed_begin(ctx, 0, st);
-      cudaError_t le = launch_stem_rows(F, kRowsOf[b], grid, ctx->rows_warps, smem, st);
+      cudaError_t le = launch_stem_rows(F, R, grid, (int)nt, smem, st);
       timed_end(ctx, tm, st);
       CU(le);
       ctx->launches += 1;
