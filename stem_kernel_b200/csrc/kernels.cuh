@@ -72,8 +72,9 @@ struct StemRowsLaunch {
   const double* pair_tab;
   uint32_t len_band, nx_cap, ny_cap, e4_cap, ylev_cap, xlev_cap;
   uint32_t team_warps;               // warps of a team (a team sweeps one row block)
+  unsigned long long* prof;          // optional (ROWS_PROF builds): per-phase cycle counters, 16 per launch
 };
-constexpr int kRowsMaxThreads = 768;  // launch bound of the row-block kernel (85 registers per thread)
+constexpr int kRowsMaxThreads = 512;  // launch bound of the row-block kernel (128 registers per thread)
 
 struct StemClassify {
   SetView X, Y;

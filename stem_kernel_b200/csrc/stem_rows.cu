@@ -36,7 +36,7 @@ namespace {
 constexpr uint32_t kG = kFastGroup;
 
 struct RowsLayout {
-  uint32_t tab, yI, yD1, yB, yDn, yC, yLev, cnt, start, pref, blk, done, teams, team_bytes, part, H, HQ, total;
+  uint32_t tab, yN, yB, yDn, yC, yLev, cnt, start, pref, blk, done, teams, team_bytes, part, H, HQ, total;
 };
 
 // Tile pitch R+1 doubles: lanes <-> rows at a fixed column is contiguous, lanes <-> columns at a fixed row strides
@@ -48,11 +48,10 @@ __host__ __device__ inline RowsLayout rows_layout(uint32_t R, uint32_t nteams, u
   uint32_t off = 0;
   auto take = [&](uint32_t bytes) { uint32_t at = off; off += (bytes + 15u) & ~15u; return at; };
   L.tab = take(8 * 256);
-  L.yI = take(8 * ny_cap);      // {child list offset << 8 | bcode, deg | len << 16}
-  L.yD1 = take(16 * ny_cap);    // {up*a*s2, up}
+  L.yN = take(32 * ny_cap);     // {rest of the child list << 8 | bcode, deg | len << 16, first four children, up*a*s2, up}
   L.yB = take(32 * ny_cap);     // {s2, el, paths, bfreq}   (MATCH cells only)
   L.yDn = take(8 * ny_cap);     // dn
-  L.yC = take(2 * e4_cap);      // child lists: 8 * child number (16 bit), padded with 8*N (the zero row)
+  L.yC = take(2 * e4_cap);      // child lists as tile offsets (pitch * child number, 16 bit), padded with the zero row
   L.yLev = take(4 * (ylev_cap + 1));
   L.cnt = take(2 * kG * xlev_cap);     // per (round, pair): rows of the pair's level
   L.start = take(2 * kG * xlev_cap);   // ... first row
@@ -93,11 +92,20 @@ struct RowSlot {         // one pair of the group in flight
   double plr;
 };
 
-struct NodePre {         // what a lane needs about its next y node, fetched ahead of the level barrier
-  uint2 ni;              // {child list offset << 8 | bcode, deg | len << 16}
+struct NodePre {         // what a lane needs about its next y node (one 32-byte record), fetched a level ahead
+  uint4 ni;              // {child list offset << 8 | bcode, deg | len << 16, children 0-1, children 2-3 (tile offsets)}
   double2 d1;            // {up*a*s2, up}
-  uint2 c4;              // its first four children
 };
+__device__ __forceinline__ uint4 lds_v4u32(uint32_t a) { uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_v4u32(uint32_t a, uint4 v) { asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
+
+#ifdef ROWS_PROF
+#define PROF_T(var) const long long var = clock64()
+#define PROF_ADD(k, a, b) do { if (tw == 0 && lane == 0) prof_acc[k] += (unsigned long long)((b) - (a)); } while (0)
+#else
+#define PROF_T(var)
+#define PROF_ADD(k, a, b)
+#endif
 
 template <int RSH>
 __global__ void __launch_bounds__(kRowsMaxThreads, 1) stem_rows_kernel(const StemRowsLaunch P) {
@@ -131,7 +139,14 @@ __global__ void __launch_bounds__(kRowsMaxThreads, 1) stem_rows_kernel(const Ste
   const uint32_t tbase = sb + L.teams + L.team_bytes * team;   // this team's area: partial sums | H tile | HQ tile
   const uint32_t tH = tbase + L.H, tHQ = tbase + L.HQ;
 
+#ifdef ROWS_PROF
+  unsigned long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  unsigned long long prof_acc2[2] = {0, 0};
+  unsigned long long prof_acc3[3] = {0, 0, 0};
+  const long long prof_k0 = clock64();
+#endif
   for (;;) {
+    PROF_T(pg0);
     __syncthreads();
     if (tid == 0) {
       if (item >= item_end) { item = atomicAdd(P.counter, (unsigned long long)kG); item_end = item + kG; }
@@ -169,18 +184,21 @@ __global__ void __launch_bounds__(kRowsMaxThreads, 1) stem_rows_kernel(const Ste
       const uint32_t gy = ry.node0 + j;
       const NodeB nb = Y.yband[gy];
       const double yup = Y.up[gy];
-      sts_v2f64(sb + (L.yD1 + 16 * j), make_double2(yup * (Y.a[gy] * nb.s2), yup));
       sts_v2f64(sb + (L.yB + 32 * j), make_double2(nb.s2, nb.el));
       sts_v2f64(sb + (L.yB + 32 * j + 16), make_double2(nb.paths, nb.bfreq));
       sts_f64(sb + (L.yDn + 8 * j), Y.dn[gy]);
       const NodeI ni = Y.nodei[gy];
       const uint32_t deg = Y.coff[ry.coff0 + j + 1] - Y.coff[ry.coff0 + j];
-      sts_v2u32(sb + (L.yI + 8 * j), make_uint2(ni.e4_bcode, deg | ((uint32_t)ni.len << 16)));
+      // first four children as tile offsets (c16 holds 8 * child; the padding entries 8 * N are the zero row)
+      uint2 c4 = make_uint2(0u, 0u);
+      if (deg > 0u) c4 = *reinterpret_cast<const uint2*>(Y.c16 + ry.c16_0 + (ni.e4_bcode >> 8));
+      const uint32_t zero2 = (8u * Ny * RP) | ((8u * Ny * RP) << 16);
+      const uint32_t c01 = deg > 0u ? ((c4.x & 0xffffu) * RP) | (((c4.x >> 16) * RP) << 16) : zero2;
+      const uint32_t c23 = deg > 2u ? ((c4.y & 0xffffu) * RP) | (((c4.y >> 16) * RP) << 16) : zero2;
+      sts_v4u32(sb + (L.yN + 32 * j), make_uint4(ni.e4_bcode, deg | ((uint32_t)ni.len << 16), c01, c23));
+      sts_v2f64(sb + (L.yN + 32 * j + 16), make_double2(yup * (Y.a[gy] * nb.s2), yup));
     }
-    {
-      const uint2* __restrict__ src = reinterpret_cast<const uint2*>(Y.c16 + ry.c16_0);
-      for (uint32_t e = tid; e < ry.e4 / 4u; e += blockDim.x) sts_v2u32(sb + (L.yC + 8 * e), src[e]);
-    }
+    for (uint32_t e = tid; e < ry.e4; e += blockDim.x) sts_u16(sb + (L.yC + 2 * e), (uint32_t)Y.c16[ry.c16_0 + e] * RP);
     for (uint32_t l = tid; l <= ry.nlev; l += blockDim.x) sts_u32(sb + (L.yLev + 4 * l), Y.lev_off[ry.lev0 + l]);
     for (uint32_t i = tid; i < (g * P.nx_cap + 3u) / 4u; i += blockDim.x) sts_u32(sb + (L.done + 4 * i), 0u);
     for (uint32_t t = tid; t < maxlev * g; t += blockDim.x) {
@@ -215,8 +233,11 @@ __global__ void __launch_bounds__(kRowsMaxThreads, 1) stem_rows_kernel(const Ste
     }
     __syncthreads();
     const uint32_t nblocks = s_nblocks;
+    PROF_T(pg1);
+    PROF_ADD(0, pg0, pg1);   // group setup
 
     for (;;) {
+      PROF_T(pt0);
       if (tw == 0 && lane == 0) s_tk[team] = atomicAdd(&s_ticket, 1u);
       team_sync(bar_id, TT);
       const uint32_t t = *reinterpret_cast<volatile uint32_t*>(&s_tk[team]);
@@ -227,6 +248,8 @@ __global__ void __launch_bounds__(kRowsMaxThreads, 1) stem_rows_kernel(const Ste
       double* __restrict__ G0 = slab + sl * slot_stride;
       const uint32_t done = sb + L.done + sl * P.nx_cap;
 
+      PROF_T(pa0);
+      PROF_ADD(1, pt0, pa0);   // ticket
       // ---- phase A: HQ(:, r) = up_y * s2_x(i) * sum over inner pairs c of G0s(c, :)
       for (uint32_t r = tw; r < cnt; r += TW) {
         const XNode* __restrict__ xn = X.xnode + ps.node0 + row0 + r;
@@ -238,40 +261,77 @@ __global__ void __launch_bounds__(kRowsMaxThreads, 1) stem_rows_kernel(const Ste
           const uint32_t ne = min(32u, e1 - eb);
           const bool first = eb == e0, last = eb + 32u >= e1;
           uint32_t off_l = 0u;
+          PROF_T(px0);
+          uint32_t cc = 0;
+          if (lane < ne) cc = __ldg(X.cidx + eb + lane);
+#ifdef ROWS_PROF
+          const long long px1 = clock64() + (cc & 0u);
+#endif
           if (lane < ne) {
-            const uint32_t c = __ldg(X.cidx + eb + lane);
+            const uint32_t c = cc;
             off_l = c * NYS;
             while (ld_flag(done + c) == 0u) __nanosleep(32);   // wait until that row is published
           }
           __syncwarp();
           __threadfence_block();   // acquire: the G0 rows behind the flags just seen
-          for (uint32_t jb = 0; jb < Ny; jb += 256u) {
+#ifdef ROWS_PROF
+          const long long px2 = clock64();
+          if (tw == 0 && lane == 0) { prof_acc3[1] += (unsigned long long)(px2 - px0); }
+#endif
+          for (uint32_t jb = 0; jb < Ny; jb += 128u) {
             const uint32_t j = jb + lane;
-            double qv[8];
+            const bool p0 = j < Ny, p1 = j + 32u < Ny, p2 = j + 64u < Ny, p3 = j + 96u < Ny;
+            double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
+            if (!first) {
+              if (p0) q0 = lds_f64(hq + ROWB * j);
+              if (p1) q1 = lds_f64(hq + ROWB * (j + 32u));
+              if (p2) q2 = lds_f64(hq + ROWB * (j + 64u));
+              if (p3) q3 = lds_f64(hq + ROWB * (j + 96u));
+            }
+            // eight inner pairs at a time: 32 independent 8-byte loads per lane in flight, then the adds
+            for (uint32_t t0 = 0; t0 < ne; t0 += 8u) {
+              PROF_T(pv0);
+              double v[8][4];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) qv[u] = (!first && j + 32u * u < Ny) ? lds_f64(hq + ROWB * (j + 32u * u)) : 0.0;
-#pragma unroll 2
-            for (uint32_t tt = 0; tt < ne; ++tt) {
-              const double* __restrict__ src = G0 + __shfl_sync(0xffffffffu, off_l, tt) + j;
-#pragma unroll
-              for (int u = 0; u < 8; ++u) if (j + 32u * u < Ny) {
+              for (uint32_t t = 0; t < 8u; ++t) {
+                const uint32_t off = __shfl_sync(0xffffffffu, off_l, (t0 + t) & 31u);
+                const double* __restrict__ src = G0 + off + j;
+                const bool pt = t0 + t < ne;
 #ifndef ROWS_ABL_NO_A
-                qv[u] += __ldcg(src + 32 * u);
+                v[t][0] = (pt && p0) ? __ldcg(src) : 0.0;
+                v[t][1] = (pt && p1) ? __ldcg(src + 32) : 0.0;
+                v[t][2] = (pt && p2) ? __ldcg(src + 64) : 0.0;
+                v[t][3] = (pt && p3) ? __ldcg(src + 96) : 0.0;
 #else
-                qv[u] += (double)(size_t)src * 1e-300;
+                v[t][0] = v[t][1] = v[t][2] = v[t][3] = (double)(size_t)src * 1e-300;
 #endif
               }
-            }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const uint32_t jj = j + 32u * u;
-              if (jj < Ny) sts_f64(hq + ROWB * jj, last ? lds_v2f64(sb + (L.yD1 + 16u * jj)).y * (xs2 * qv[u]) : qv[u]);
+              for (uint32_t t = 0; t < 8u; ++t) { q0 += v[t][0]; q1 += v[t][1]; q2 += v[t][2]; q3 += v[t][3]; }
+#ifdef ROWS_PROF
+              const long long pv1 = clock64() + ((long long)(q0 + q1 + q2 + q3 == 12345.678) & 0);
+              if (tw == 0 && lane == 0) { prof_acc3[0] += (unsigned long long)(pv1 - pv0); prof_acc3[2] += 1; }
+#endif
             }
+            if (last) {
+              if (p0) q0 = lds_f64(sb + (L.yN + 32u * j + 24u)) * (xs2 * q0);
+              if (p1) q1 = lds_f64(sb + (L.yN + 32u * (j + 32u) + 24u)) * (xs2 * q1);
+              if (p2) q2 = lds_f64(sb + (L.yN + 32u * (j + 64u) + 24u)) * (xs2 * q2);
+              if (p3) q3 = lds_f64(sb + (L.yN + 32u * (j + 96u) + 24u)) * (xs2 * q3);
+            }
+            if (p0) sts_f64(hq + ROWB * j, q0);
+            if (p1) sts_f64(hq + ROWB * (j + 32u), q1);
+            if (p2) sts_f64(hq + ROWB * (j + 64u), q2);
+            if (p3) sts_f64(hq + ROWB * (j + 96u), q3);
           }
           if (e1 == e0) break;
         }
       }
+      PROF_T(pa1);
       team_sync(bar_id, TT);
+      PROF_T(pb0);
+      PROF_ADD(2, pa0, pa1);   // phase A (this warp)
+      PROF_ADD(3, pa1, pb0);   // wait for the team's other warps
 
       // ---- phase B: sweep the y DAG level by level; lanes <-> (node slot, row of the block), warps <-> more slots
       const bool valid = rr < cnt;
@@ -286,90 +346,100 @@ __global__ void __launch_bounds__(kRowsMaxThreads, 1) stem_rows_kernel(const Ste
       // MATCH needs |len_x - len_y| <= band; below the window G1 is identically 0 (length-monotone DAG)
       const uint32_t len_lo = !valid ? 0xffffu : ((band != 0u && xl > band) ? xl - band : 0u);
       const uint32_t len_hi = band != 0u ? xl + band : 0xffffffffu;
-      const uint32_t hbase = tH + 8u * rr, hqbase = tHQ + 8u * rr;
+      const uint32_t hbase = tH + 8u * rr;
       const uint32_t tabrow = sb + L.tab + 8u * 16u * xbc;
       const uint32_t slot_id = tw * NS + q, step = TW * NS;
       double racc = 0.0;
+      const uint32_t hq_off = tHQ - tH;
       auto fetch = [&](uint32_t j, uint32_t jend) {
         NodePre n;
-        n.ni = make_uint2(0u, 0u); n.d1 = make_double2(0.0, 0.0); n.c4 = make_uint2(0u, 0u);
+        n.ni = make_uint4(0u, 0u, 0u, 0u); n.d1 = make_double2(0.0, 0.0);
         if (j < jend) {
-          n.ni = lds_v2u32(sb + (L.yI + 8u * j));
-          n.d1 = lds_v2f64(sb + (L.yD1 + 16u * j));
-          n.c4 = lds_v2u32(sb + L.yC + 2u * (n.ni.x >> 8));
+          n.ni = lds_v4u32(sb + (L.yN + 32u * j));
+          n.d1 = lds_v2f64(sb + (L.yN + 32u * j + 16u));
         }
         return n;
       };
+      // One node per slot for this lane's row: gathers, MATCH term, store.  Control flow is warp-uniform (votes):
+      // rows below their window compute an exact 0 from zeros, slots without a node compute on a zero record and
+      // do not store, the MATCH part runs for every lane when any lane of the warp is in band.
+      auto node = [&](const NodePre& n, uint32_t j, bool act) {
+        const uint32_t yl = n.ni.y >> 16, deg = act ? (n.ni.y & 0xffffu) : 0u;
+        const bool live = act && yl >= len_lo;
+        if (!__any_sync(0xffffffffu, live)) {  // G1 == 0 here and below for every row of the warp
+          if (act && valid) sts_f64(hbase + ROWB * j, 0.0);
+          return;
+        }
+        const bool in_band = live && yl <= len_hi;
+        const bool any_band = __any_sync(0xffffffffu, in_band);
+        const uint32_t a0 = hbase + (n.ni.z & 0xffffu), a1 = hbase + (n.ni.z >> 16);
+        const uint32_t a2 = hbase + (n.ni.w & 0xffffu), a3 = hbase + (n.ni.w >> 16);
+        double S0 = lds_f64(a0), S1 = lds_f64(a1), S2 = lds_f64(a2), S3 = lds_f64(a3);
+        double R0 = 0.0, R1 = 0.0, R2 = 0.0, R3 = 0.0;
+        if (any_band) { R0 = lds_f64(a0 + hq_off); R1 = lds_f64(a1 + hq_off); R2 = lds_f64(a2 + hq_off); R3 = lds_f64(a3 + hq_off); }
+        const uint32_t maxdeg = __reduce_max_sync(0xffffffffu, deg);
+        if (maxdeg > 4u) {   // lists are padded to multiples of four with the zero row: whole groups of four
+          const uint32_t e0 = sb + L.yC + 2u * (n.ni.x >> 8);
+#pragma unroll 1
+          for (uint32_t gq = 4u; gq < maxdeg; gq += 4u) {
+            if (gq < deg) {
+              const uint2 c = lds_v2u32(e0 + 2u * gq);
+              const uint32_t o0 = hbase + (c.x & 0xffffu), o1 = hbase + (c.x >> 16);
+              const uint32_t o2 = hbase + (c.y & 0xffffu), o3 = hbase + (c.y >> 16);
+              const double h0 = lds_f64(o0), h1 = lds_f64(o1), h2 = lds_f64(o2), h3 = lds_f64(o3);
+              if (any_band) {
+                const double r0 = lds_f64(o0 + hq_off), r1 = lds_f64(o1 + hq_off), r2 = lds_f64(o2 + hq_off), r3 = lds_f64(o3 + hq_off);
+                R0 += r0; R1 += r1; R2 += r2; R3 += r3;
+              }
+              S0 += h0; S1 += h1; S2 += h2; S3 += h3;
+            }
+          }
+        }
+        double m = 0.0;
+        if (any_band) {
+          const double2 b0v = lds_v2f64(sb + (L.yB + 32u * j));        // {s2_y, el_y}
+          const double2 b1v = lds_v2f64(sb + (L.yB + 32u * j + 16u));  // {paths_y, bfreq_y}
+          const double vs = lds_f64(tabrow + 8u * (n.ni.x & 0xffu)) * xbf * b1v.y;
+          m = in_band ? vs * fma(b0v.y, xql, b0v.x * ((R0 + R1) + (R2 + R3))) : 0.0;
+          if (in_band) racc = fma(b1v.x, m, racc);
+        }
+        if (act) sts_f64(hbase + ROWB * j, fma(n.d1.x, (S0 + S1) + (S2 + S3), n.d1.y * m));   // up_y * (M + a_y*s2_y*sum)
+      };
       uint32_t jbeg = lds_u32(sb + L.yLev);
       uint32_t jend = lds_u32(sb + (L.yLev + 4u));
+      uint32_t jend2 = lds_u32(sb + (L.yLev + 4u * min(2u, ry.nlev)));
       NodePre nx = fetch(jbeg + slot_id, jend);
 #ifdef ROWS_ABL_NO_B
       for (uint32_t ly = 0; ly < 1; ++ly) {
 #else
       for (uint32_t ly = 0; ly < ry.nlev; ++ly) {
 #endif
-        for (uint32_t j = jbeg + slot_id; j < jend; j += step) {
-          const NodePre n = nx;
-          if (j + step < jend) nx = fetch(j + step, jend);
-          const uint32_t yl = n.ni.y >> 16, deg = n.ni.y & 0xffffu;
-          if (yl < len_lo) {  // G1 == 0 here and below
-            if (valid) sts_f64(hbase + ROWB * j, 0.0);
-            continue;
-          }
-          const bool in_band = yl <= len_hi;
-          double S0 = 0.0, S1 = 0.0, m = 0.0;
-          uint32_t e = sb + L.yC + 2u * (n.ni.x >> 8) + 8u;   // past the four prefetched children
-          const uint32_t eend = e - 8u + 2u * deg;
-          if (in_band) {
-            double R0 = 0.0, R1 = 0.0;
-            if (deg > 0u) {
-              const uint32_t o0 = (n.c4.x & 0xffffu) * RP, o1 = (n.c4.x >> 16) * RP;
-              S0 += lds_f64(hbase + o0); R0 += lds_f64(hqbase + o0);
-              S1 += lds_f64(hbase + o1); R1 += lds_f64(hqbase + o1);
-            }
-            if (deg > 2u) {
-              const uint32_t o0 = (n.c4.y & 0xffffu) * RP, o1 = (n.c4.y >> 16) * RP;
-              S0 += lds_f64(hbase + o0); R0 += lds_f64(hqbase + o0);
-              S1 += lds_f64(hbase + o1); R1 += lds_f64(hqbase + o1);
-            }
-            for (; e < eend; e += 4u) {
-              const uint32_t c2 = lds_u32(e);
-              const uint32_t o0 = (c2 & 0xffffu) * RP, o1 = (c2 >> 16) * RP;
-              S0 += lds_f64(hbase + o0); R0 += lds_f64(hqbase + o0);
-              S1 += lds_f64(hbase + o1); R1 += lds_f64(hqbase + o1);
-            }
-            const double2 b0v = lds_v2f64(sb + (L.yB + 32u * j));        // {s2_y, el_y}
-            const double2 b1v = lds_v2f64(sb + (L.yB + 32u * j + 16u));  // {paths_y, bfreq_y}
-            const double vs = lds_f64(tabrow + 8u * (n.ni.x & 0xffu)) * xbf * b1v.y;
-            m = vs * fma(b0v.y, xql, b0v.x * (R0 + R1));
-            racc = fma(b1v.x, m, racc);
-          } else {
-            if (deg > 0u) {
-              S0 += lds_f64(hbase + (n.c4.x & 0xffffu) * RP);
-              S1 += lds_f64(hbase + (n.c4.x >> 16) * RP);
-            }
-            if (deg > 2u) {
-              S0 += lds_f64(hbase + (n.c4.y & 0xffffu) * RP);
-              S1 += lds_f64(hbase + (n.c4.y >> 16) * RP);
-            }
-            for (; e < eend; e += 4u) {
-              const uint32_t c2 = lds_u32(e);
-              S0 += lds_f64(hbase + (c2 & 0xffffu) * RP);
-              S1 += lds_f64(hbase + (c2 >> 16) * RP);
-            }
-          }
-          sts_f64(hbase + ROWB * j, fma(n.d1.x, S0 + S1, n.d1.y * m));   // up_y * (M + a_y*s2_y*sum)
+        // this level's first node is in registers; the next level's record is requested before the gathers
+        PROF_T(pl0);
+        const NodePre cur = nx;
+        nx = fetch(jend + slot_id, jend2);
+        const uint32_t jend3 = lds_u32(sb + (L.yLev + 4u * min(ly + 3u, ry.nlev)));
+        // warp-uniform trip count: the warp's first slot decides, slots past the level's end run inactive
+        uint32_t jw = jbeg + tw * NS;
+        if (jw < jend) {
+          node(cur, jw + q, jw + q < jend);
+          for (jw += step; jw < jend; jw += step) node(fetch(jw + q, jend), jw + q, jw + q < jend);   // wide levels
         }
-        jbeg = jend;
-        if (ly + 1u < ry.nlev) {   // next level's node record and first children, fetched ahead of the barrier
-          jend = lds_u32(sb + (L.yLev + 4u * ly + 8u));
-          nx = fetch(jbeg + slot_id, jend);
-        } else {
-          sts_f64(tbase + 8u * (tw * 32u + lane), racc);
-        }
+        jbeg = jend; jend = jend2; jend2 = jend3;
+        if (ly + 1u == ry.nlev) sts_f64(tbase + 8u * (tw * 32u + lane), racc);
+        PROF_T(pl1);
         team_sync(bar_id, TT);
+        PROF_T(pl2);
+#ifdef ROWS_PROF
+        if (tw == 0 && lane == 0) { prof_acc2[0] += (unsigned long long)(pl1 - pl0); prof_acc2[1] += (unsigned long long)(pl2 - pl1); }
+#endif
       }
 
+      PROF_T(pc0);
+      PROF_ADD(4, pb0, pc0);   // phase B
+#ifdef ROWS_PROF
+      if (tw == 0 && lane == 0) { prof_acc[6] += 1; prof_acc[7] += ry.nlev; }
+#endif
       // ---- phase C: finished rows G0s(i,:) = up_x(i) * dn_y * (H + a_x*HQ) to the slab; row sums; publish
       for (uint32_t r = tw; r < cnt; r += TW) {
         const uint32_t i = row0 + r;
@@ -391,6 +461,8 @@ __global__ void __launch_bounds__(kRowsMaxThreads, 1) stem_rows_kernel(const Ste
         __syncwarp();
         if (lane == 0) asm volatile("st.volatile.shared.u8 [%0], %1;" ::"r"(done + i), "r"(1u) : "memory");
       }
+      PROF_T(pc1);
+      PROF_ADD(5, pc0, pc1);   // phase C
     }
 
     // ---- fixed-order sum of the per-row slots, one warp per pair of the group
@@ -405,7 +477,22 @@ __global__ void __launch_bounds__(kRowsMaxThreads, 1) stem_rows_kernel(const Ste
       if (lane == 0) P.out[ps.k] = t + ps.plr * (double)ry.lr;
     }
   }
+#ifdef ROWS_PROF
+  if (P.prof != nullptr && tw == 0 && lane == 0) {
+    for (int k = 0; k < 8; ++k) atomicAdd(P.prof + k, prof_acc[k]);
+    atomicAdd(P.prof + 8, (unsigned long long)(clock64() - prof_k0));
+    atomicAdd(P.prof + 9, 1ull);
+    atomicAdd(P.prof + 10, prof_acc2[0]);
+    atomicAdd(P.prof + 11, prof_acc2[1]);
+    atomicAdd(P.prof + 12, prof_acc3[0]);
+    atomicAdd(P.prof + 13, prof_acc3[1]);
+    atomicAdd(P.prof + 14, prof_acc3[2]);
+  }
+#endif
 }
+
+#undef PROF_T
+#undef PROF_ADD
 
 template <int RSH>
 cudaError_t launch_rows_t(const StemRowsLaunch& p, int grid, int nthreads, size_t smem, cudaStream_t stream) {

@@ -368,6 +368,7 @@ int stemk_pairs_device(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, s
       const uint32_t tw = (uint32_t)ctx->rows_tw;
       auto teams_for = [&](uint32_t R) {
         uint32_t nt = 0;
+        if ((ny_cap + 1u) * 8u * (R + 1u) > 65535u) return 0u;   // tile offsets are 16 bit
         const uint32_t lim = std::min<uint32_t>(15u, (uint32_t)kRowsMaxThreads / (32u * tw));
         while (nt < lim && stem_rows_smem_bytes(R, nt + 1, tw, nx_cap, ny_cap, e4_cap, lev_cap, xlev_cap) <= budget) ++nt;
         if (ctx->rows_nt > 0) nt = std::min<uint32_t>(nt, (uint32_t)ctx->rows_nt);
@@ -390,12 +391,30 @@ int stemk_pairs_device(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, s
       F.rowacc_stride = ra_stride; F.pair_tab = ctx->d_pair_tab;
       F.len_band = ctx->params.len_band; F.nx_cap = nx_cap; F.ny_cap = ny_cap; F.e4_cap = e4_cap;
       F.ylev_cap = lev_cap; F.xlev_cap = xlev_cap; F.team_warps = tw;
+      F.prof = nullptr;
+      static unsigned long long* d_prof = nullptr;
+      const bool prof = std::getenv("STEMK_PROF") != nullptr;
+      if (prof) {
+        if (!d_prof) cudaMalloc((void**)&d_prof, 16 * sizeof(unsigned long long));
+        cudaMemsetAsync(d_prof, 0, 16 * sizeof(unsigned long long), st);
+        F.prof = d_prof;
+      }
       if (std::getenv("STEMK_TIMING")) std::fprintf(stderr, "rows bucket %d: cap %u R %u teams %u smem %zu\n", b, ny_cap, R, nt, smem);
       stemk_ctx::Timed tm = timed_begin(ctx, 0, st);
       cudaError_t le = launch_stem_rows(F, R, grid, (int)nt, smem, st);
       timed_end(ctx, tm, st);
       CU(le);
       ctx->launches += 1;
+      if (prof) {
+        unsigned long long h[16];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost);
+        const double nb = h[6] ? (double)h[6] : 1.0, nt_ = h[9] ? (double)h[9] : 1.0;
+        std::fprintf(stderr, "prof cap %u R %u teams %u: blocks %llu levels/block %.1f | per block: ticket %.0f A %.0f Await %.0f B %.0f C %.0f | "
+                     "per team: setup %.0f total %.0f cycles | per level (warp 0): work %.0f barrier %.0f | per A load batch: %.0f cycles; flags+fence/batch %.0f (batches %llu)\n", ny_cap, R, nt, h[6], h[7] / nb, h[1] / nb, h[2] / nb, h[3] / nb, h[4] / nb,
+                     h[5] / nb, h[0] / nt_, h[8] / nt_, h[10] / (double)(h[7] ? h[7] : 1), h[11] / (double)(h[7] ? h[7] : 1),
+                     h[12] / (double)(h[14] ? h[14] : 1), h[13] / (double)(h[14] ? h[14] : 1), h[14]);
+      }
     }
     // ---- fast kernel, one launch per size bucket (shared memory and CTAs per SM sized for the bucket)
     for (int b = 0; !rows_mode && b < C.n_caps; ++b) {
