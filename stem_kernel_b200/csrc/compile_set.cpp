@@ -155,7 +155,7 @@ void compile_record(const stemk_seqset_desc& s, uint32_t r, double g, RecOut* o)
     o->lev_off[l + 1] += o->lev_off[l];
   }
   {
-    // inside a level: by length (the row blocks / node slots of a warp then share their band window), then by degree
+    // inside a level, nodes with many inner pairs first: lanes of a warp then see similar trip counts
     std::vector<uint32_t> nl_deg(n, 0);
     for (uint32_t u = 0; u < n; ++u)
       for (uint32_t e = eoff[u]; e < eoff[u + 1]; ++e) if (!leaf[s.edge_to[e]]) ++nl_deg[u];
@@ -163,8 +163,6 @@ void compile_record(const stemk_seqset_desc& s, uint32_t r, double g, RecOut* o)
     for (uint32_t u = 0; u < n; ++u) if (!leaf[u]) order.push_back(u);
     std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
       if (level[a] != level[b]) return level[a] < level[b];
-      const uint32_t la = last[a] - first[a], lb = last[b] - first[b];
-      if (la != lb) return la < lb;   // neighbours of a level have similar lengths: their band windows coincide
       return nl_deg[a] > nl_deg[b];
     });
     for (uint32_t k = 0; k < order.size(); ++k) newidx[order[k]] = k;

@@ -138,11 +138,19 @@ __global__ void __launch_bounds__(kRowsMaxThreads, 1) stem_rows_kernel(const Ste
   const uint32_t rr = lane & (R - 1u), q = lane >> RSH;   // phase B: this lane's row of the block, node slot
   const uint32_t tbase = sb + L.teams + L.team_bytes * team;   // this team's area: partial sums | H tile | HQ tile
   const uint32_t tH = tbase + L.H, tHQ = tbase + L.HQ;
+  __shared__ __align__(8) unsigned long long s_mbar[16];   // one transaction barrier per team (phase A's bulk copies)
+  const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&s_mbar[team]);
+  uint32_t mphase = 0;
+  if (tw == 0 && lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
 
 #ifdef ROWS_PROF
   unsigned long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   unsigned long long prof_acc2[2] = {0, 0};
   unsigned long long prof_acc3[3] = {0, 0, 0};
+  unsigned long long prof_acc4[2] = {0, 0};
   const long long prof_k0 = clock64();
 #endif
   for (;;) {
@@ -251,69 +259,86 @@ __global__ void __launch_bounds__(kRowsMaxThreads, 1) stem_rows_kernel(const Ste
       PROF_T(pa0);
       PROF_ADD(1, pt0, pa0);   // ticket
       // ---- phase A: HQ(:, r) = up_y * s2_x(i) * sum over inner pairs c of G0s(c, :)
-      for (uint32_t r = tw; r < cnt; r += TW) {
-        const XNode* __restrict__ xn = X.xnode + ps.node0 + row0 + r;
-        const uint4 xi4 = __ldg(reinterpret_cast<const uint4*>(xn) + 3);
-        const uint32_t e0 = xi4.x, e1 = xi4.y;
-        const double xs2 = __ldg(&xn->s2);
-        const uint32_t hq = tHQ + 8u * r;
-        for (uint32_t eb = e0; eb < e1 || eb == e0; eb += 32u) {
-          const uint32_t ne = min(32u, e1 - eb);
-          const bool first = eb == e0, last = eb + 32u >= e1;
-          uint32_t off_l = 0u;
-          PROF_T(px0);
-          uint32_t cc = 0;
-          if (lane < ne) cc = __ldg(X.cidx + eb + lane);
-#ifdef ROWS_PROF
-          const long long px1 = clock64() + (cc & 0u);
-#endif
-          if (lane < ne) {
-            const uint32_t c = cc;
-            off_l = c * NYS;
+      // The finished rows of the inner pairs are fetched by TMA bulk copies (one 8*NYS-byte copy per (row, inner pair)
+      // edge, issued by the lanes of the team's first warp, completion on the team's mbarrier) into the team's H
+      // tile, which is free until phase B; a warp's own loads cannot do this: a warp sustains only ~2-4 B/clk of
+      // global loads however many it keeps in flight (scripts/micro/rowsum.cu).
+      uint32_t e0r = 0, degr = 0;
+      if (lane < cnt) {
+        const uint4 xi4 = __ldg(reinterpret_cast<const uint4*>(X.xnode + ps.node0 + row0 + lane) + 3);
+        e0r = xi4.x; degr = xi4.y - xi4.x;
+      }
+      uint32_t pre = degr;   // inclusive prefix of the rows' inner-pair counts over lanes 0..R-1
+#pragma unroll
+      for (uint32_t o = 1; o < R; o <<= 1) { const uint32_t t2 = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += t2; }
+      const uint32_t etot = __shfl_sync(0xffffffffu, pre, R - 1u);
+      const uint32_t row_bytes = 8u * NYS;
+      const uint32_t kst = min(32u, (ROWB * (P.ny_cap + 1u)) / row_bytes);   // rows the H tile can stage
+      for (uint32_t r = tw; r < cnt; r += TW)   // rows whose inner pairs are all hairpin loops: Q == 0
+        if (__shfl_sync(0xffffffffu, degr, r) == 0u)
+          for (uint32_t j = lane; j < Ny; j += 32u) sts_f64(tHQ + 8u * r + ROWB * j, 0.0);
+      for (uint32_t b0 = 0; b0 < etot; b0 += kst) {
+        const uint32_t nb = min(kst, etot - b0);
+        team_sync(bar_id, TT);   // the staging rows are free (previous batch summed, previous block's phase C done)
+        PROF_T(px0);
+        if (tw == 0) {
+          const uint32_t x = b0 + lane;
+          uint32_t row = 0;
+#pragma unroll
+          for (uint32_t r = 0; r < R; ++r) row += (x >= __shfl_sync(0xffffffffu, pre, r)) ? 1u : 0u;
+          row = min(row, R - 1u);
+          const uint32_t e0x = __shfl_sync(0xffffffffu, e0r, row), exx = __shfl_sync(0xffffffffu, pre - degr, row);
+          uint32_t c = 0;
+          if (lane < nb) {
+            c = __ldg(X.cidx + e0x + (x - exx));
             while (ld_flag(done + c) == 0u) __nanosleep(32);   // wait until that row is published
           }
           __syncwarp();
           __threadfence_block();   // acquire: the G0 rows behind the flags just seen
+          asm volatile("fence.proxy.async;" ::: "memory");   // ... and hand them (and the staging rows) to the async proxy
+          if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(nb * row_bytes) : "memory");
+          __syncwarp();
+          if (lane < nb)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(tH + lane * row_bytes), "l"(G0 + (size_t)c * NYS), "r"(row_bytes), "r"(mbar) : "memory");
+        }
+        {
+          uint32_t ok = 0;
+          while (!ok)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(ok) : "r"(mbar), "r"(mphase) : "memory");
+          mphase ^= 1u;
+        }
 #ifdef ROWS_PROF
-          const long long px2 = clock64();
-          if (tw == 0 && lane == 0) { prof_acc3[1] += (unsigned long long)(px2 - px0); }
+        const long long px1 = clock64();
+        if (tw == 0 && lane == 0) { prof_acc3[0] += (unsigned long long)(px1 - px0); prof_acc3[2] += 1; }
 #endif
-          for (uint32_t jb = 0; jb < Ny; jb += 128u) {
+        for (uint32_t r = tw; r < cnt; r += TW) {   // a warp owns the rows r = tw, tw + TW, ...
+          const uint32_t pin = __shfl_sync(0xffffffffu, pre, r), dg = __shfl_sync(0xffffffffu, degr, r);
+          const uint32_t ex = pin - dg, lo = max(ex, b0), hi = min(pin, b0 + nb);
+          if (lo >= hi) continue;
+          const double xs2 = __ldg(&(X.xnode + ps.node0 + row0 + r)->s2);
+          const uint32_t hq = tHQ + 8u * r;
+          const bool cont = lo > ex, fin = hi == pin;
+          for (uint32_t jb = 0; jb < Ny; jb += 128u) {   // four columns per lane: four independent sums
             const uint32_t j = jb + lane;
             const bool p0 = j < Ny, p1 = j + 32u < Ny, p2 = j + 64u < Ny, p3 = j + 96u < Ny;
             double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
-            if (!first) {
+            if (cont) {
               if (p0) q0 = lds_f64(hq + ROWB * j);
               if (p1) q1 = lds_f64(hq + ROWB * (j + 32u));
               if (p2) q2 = lds_f64(hq + ROWB * (j + 64u));
               if (p3) q3 = lds_f64(hq + ROWB * (j + 96u));
             }
-            // eight inner pairs at a time: 32 independent 8-byte loads per lane in flight, then the adds
-            for (uint32_t t0 = 0; t0 < ne; t0 += 8u) {
-              PROF_T(pv0);
-              double v[8][4];
-#pragma unroll
-              for (uint32_t t = 0; t < 8u; ++t) {
-                const uint32_t off = __shfl_sync(0xffffffffu, off_l, (t0 + t) & 31u);
-                const double* __restrict__ src = G0 + off + j;
-                const bool pt = t0 + t < ne;
 #ifndef ROWS_ABL_NO_A
-                v[t][0] = (pt && p0) ? __ldcg(src) : 0.0;
-                v[t][1] = (pt && p1) ? __ldcg(src + 32) : 0.0;
-                v[t][2] = (pt && p2) ? __ldcg(src + 64) : 0.0;
-                v[t][3] = (pt && p3) ? __ldcg(src + 96) : 0.0;
-#else
-                v[t][0] = v[t][1] = v[t][2] = v[t][3] = (double)(size_t)src * 1e-300;
-#endif
-              }
-#pragma unroll
-              for (uint32_t t = 0; t < 8u; ++t) { q0 += v[t][0]; q1 += v[t][1]; q2 += v[t][2]; q3 += v[t][3]; }
-#ifdef ROWS_PROF
-              const long long pv1 = clock64() + ((long long)(q0 + q1 + q2 + q3 == 12345.678) & 0);
-              if (tw == 0 && lane == 0) { prof_acc3[0] += (unsigned long long)(pv1 - pv0); prof_acc3[2] += 1; }
-#endif
+            uint32_t src = tH + (lo - b0) * row_bytes + 8u * j;
+            for (uint32_t x = lo; x < hi; ++x, src += row_bytes) {
+              const double v0 = p0 ? lds_f64(src) : 0.0, v1 = p1 ? lds_f64(src + 256u) : 0.0;
+              const double v2 = p2 ? lds_f64(src + 512u) : 0.0, v3 = p3 ? lds_f64(src + 768u) : 0.0;
+              q0 += v0; q1 += v1; q2 += v2; q3 += v3;
             }
-            if (last) {
+#endif
+            if (fin) {
               if (p0) q0 = lds_f64(sb + (L.yN + 32u * j + 24u)) * (xs2 * q0);
               if (p1) q1 = lds_f64(sb + (L.yN + 32u * (j + 32u) + 24u)) * (xs2 * q1);
               if (p2) q2 = lds_f64(sb + (L.yN + 32u * (j + 64u) + 24u)) * (xs2 * q2);
@@ -324,8 +349,14 @@ __global__ void __launch_bounds__(kRowsMaxThreads, 1) stem_rows_kernel(const Ste
             if (p2) sts_f64(hq + ROWB * (j + 64u), q2);
             if (p3) sts_f64(hq + ROWB * (j + 96u), q3);
           }
-          if (e1 == e0) break;
         }
+#ifdef ROWS_PROF
+        { const long long px2 = clock64(); if (tw == 0 && lane == 0) prof_acc3[1] += (unsigned long long)(px2 - px1); }
+#endif
+      }
+      if (etot != 0u) {   // the staged rows ran over the H tile's zero row: put it back once everybody has summed
+        team_sync(bar_id, TT);
+        if (tw == 0 && lane < R) sts_f64(tH + ROWB * Ny + 8u * lane, 0.0);
       }
       PROF_T(pa1);
       team_sync(bar_id, TT);
@@ -351,88 +382,100 @@ __global__ void __launch_bounds__(kRowsMaxThreads, 1) stem_rows_kernel(const Ste
       const uint32_t slot_id = tw * NS + q, step = TW * NS;
       double racc = 0.0;
       const uint32_t hq_off = tHQ - tH;
-      auto fetch = [&](uint32_t j, uint32_t jend) {
-        NodePre n;
-        n.ni = make_uint4(0u, 0u, 0u, 0u); n.d1 = make_double2(0.0, 0.0);
-        if (j < jend) {
-          n.ni = lds_v4u32(sb + (L.yN + 32u * j));
-          n.d1 = lds_v2f64(sb + (L.yN + 32u * j + 16u));
-        }
-        return n;
-      };
-      // One node per slot for this lane's row: gathers, MATCH term, store.  Control flow is warp-uniform (votes):
-      // rows below their window compute an exact 0 from zeros, slots without a node compute on a zero record and
-      // do not store, the MATCH part runs for every lane when any lane of the warp is in band.
-      auto node = [&](const NodePre& n, uint32_t j, bool act) {
-        const uint32_t yl = n.ni.y >> 16, deg = act ? (n.ni.y & 0xffffu) : 0u;
-        const bool live = act && yl >= len_lo;
-        if (!__any_sync(0xffffffffu, live)) {  // G1 == 0 here and below for every row of the warp
-          if (act && valid) sts_f64(hbase + ROWB * j, 0.0);
-          return;
-        }
-        const bool in_band = live && yl <= len_hi;
-        const bool any_band = __any_sync(0xffffffffu, in_band);
-        const uint32_t a0 = hbase + (n.ni.z & 0xffffu), a1 = hbase + (n.ni.z >> 16);
-        const uint32_t a2 = hbase + (n.ni.w & 0xffffu), a3 = hbase + (n.ni.w >> 16);
-        double S0 = lds_f64(a0), S1 = lds_f64(a1), S2 = lds_f64(a2), S3 = lds_f64(a3);
-        double R0 = 0.0, R1 = 0.0, R2 = 0.0, R3 = 0.0;
-        if (any_band) { R0 = lds_f64(a0 + hq_off); R1 = lds_f64(a1 + hq_off); R2 = lds_f64(a2 + hq_off); R3 = lds_f64(a3 + hq_off); }
-        const uint32_t maxdeg = __reduce_max_sync(0xffffffffu, deg);
-        if (maxdeg > 4u) {   // lists are padded to multiples of four with the zero row: whole groups of four
-          const uint32_t e0 = sb + L.yC + 2u * (n.ni.x >> 8);
-#pragma unroll 1
-          for (uint32_t gq = 4u; gq < maxdeg; gq += 4u) {
-            if (gq < deg) {
-              const uint2 c = lds_v2u32(e0 + 2u * gq);
-              const uint32_t o0 = hbase + (c.x & 0xffffu), o1 = hbase + (c.x >> 16);
-              const uint32_t o2 = hbase + (c.y & 0xffffu), o3 = hbase + (c.y >> 16);
-              const double h0 = lds_f64(o0), h1 = lds_f64(o1), h2 = lds_f64(o2), h3 = lds_f64(o3);
-              if (any_band) {
-                const double r0 = lds_f64(o0 + hq_off), r1 = lds_f64(o1 + hq_off), r2 = lds_f64(o2 + hq_off), r3 = lds_f64(o3 + hq_off);
-                R0 += r0; R1 += r1; R2 += r2; R3 += r3;
-              }
-              S0 += h0; S1 += h1; S2 += h2; S3 += h3;
-            }
-          }
-        }
-        double m = 0.0;
-        if (any_band) {
-          const double2 b0v = lds_v2f64(sb + (L.yB + 32u * j));        // {s2_y, el_y}
-          const double2 b1v = lds_v2f64(sb + (L.yB + 32u * j + 16u));  // {paths_y, bfreq_y}
-          const double vs = lds_f64(tabrow + 8u * (n.ni.x & 0xffu)) * xbf * b1v.y;
-          m = in_band ? vs * fma(b0v.y, xql, b0v.x * ((R0 + R1) + (R2 + R3))) : 0.0;
-          if (in_band) racc = fma(b1v.x, m, racc);
-        }
-        if (act) sts_f64(hbase + ROWB * j, fma(n.d1.x, (S0 + S1) + (S2 + S3), n.d1.y * m));   // up_y * (M + a_y*s2_y*sum)
-      };
+      const uint32_t yN0 = sb + L.yN, yB0 = sb + L.yB, yC0 = sb + L.yC;
+      // One step = one node per slot for this lane's row.  The step is kept as short as possible -- a warp alone on
+      // its scheduler runs dependent code at ~5 cycles per instruction, so the level time is the instruction count:
+      //   votes (everything below every row's window / some lane in band / some list longer than four) keep the
+      //   control flow warp-uniform; rows below their window compute an exact 0 from zeros; slots past the level's
+      //   end compute on a zero record and do not store.
       uint32_t jbeg = lds_u32(sb + L.yLev);
       uint32_t jend = lds_u32(sb + (L.yLev + 4u));
-      uint32_t jend2 = lds_u32(sb + (L.yLev + 4u * min(2u, ry.nlev)));
-      NodePre nx = fetch(jbeg + slot_id, jend);
+      uint4 ni = make_uint4(0u, 0u, 0u, 0u);
+      double2 d1 = make_double2(0.0, 0.0);
+      if (jbeg + slot_id < jend) { ni = lds_v4u32(yN0 + 32u * (jbeg + slot_id)); d1 = lds_v2f64(yN0 + 32u * (jbeg + slot_id) + 16u); }
 #ifdef ROWS_ABL_NO_B
       for (uint32_t ly = 0; ly < 1; ++ly) {
 #else
       for (uint32_t ly = 0; ly < ry.nlev; ++ly) {
 #endif
-        // this level's first node is in registers; the next level's record is requested before the gathers
-        PROF_T(pl0);
-        const NodePre cur = nx;
-        nx = fetch(jend + slot_id, jend2);
-        const uint32_t jend3 = lds_u32(sb + (L.yLev + 4u * min(ly + 3u, ry.nlev)));
-        // warp-uniform trip count: the warp's first slot decides, slots past the level's end run inactive
-        uint32_t jw = jbeg + tw * NS;
-        if (jw < jend) {
-          node(cur, jw + q, jw + q < jend);
-          for (jw += step; jw < jend; jw += step) node(fetch(jw + q, jend), jw + q, jw + q < jend);   // wide levels
-        }
-        jbeg = jend; jend = jend2; jend2 = jend3;
-        if (ly + 1u == ry.nlev) sts_f64(tbase + 8u * (tw * 32u + lane), racc);
-        PROF_T(pl1);
-        team_sync(bar_id, TT);
-        PROF_T(pl2);
+        for (uint32_t jw = jbeg + tw * NS; jw < jend;) {   // warp-uniform trip count (wide levels take several steps)
+          const uint32_t j = jw + q;
+          const bool act = j < jend;
+          const uint32_t yl = ni.y >> 16, deg = ni.y & 0xffffu;
+          const bool live = act && yl >= len_lo;
 #ifdef ROWS_PROF
-        if (tw == 0 && lane == 0) { prof_acc2[0] += (unsigned long long)(pl1 - pl0); prof_acc2[1] += (unsigned long long)(pl2 - pl1); }
+          const long long ps0 = clock64() + (long long)(ni.y & 0u);
+          long long ps1 = ps0, ps2 = ps0;
 #endif
+          if (__any_sync(0xffffffffu, live)) {
+            const bool in_band = live && yl <= len_hi;
+            const bool any_band = __any_sync(0xffffffffu, in_band);
+            const uint32_t a0 = hbase + (ni.z & 0xffffu), a1 = hbase + (ni.z >> 16);
+            const uint32_t a2 = hbase + (ni.w & 0xffffu), a3 = hbase + (ni.w >> 16);
+#ifdef ROWS_PROF
+            ps1 = clock64() + (long long)(a0 & 0u);
+#endif
+            double S0 = lds_f64(a0), S1 = lds_f64(a1), S2 = lds_f64(a2), S3 = lds_f64(a3);
+            double R0 = 0.0, R1 = 0.0, R2 = 0.0, R3 = 0.0, s2y = 0.0, ely = 0.0, pathsy = 0.0, vs = 0.0;
+            if (any_band) {
+              R0 = lds_f64(a0 + hq_off); R1 = lds_f64(a1 + hq_off); R2 = lds_f64(a2 + hq_off); R3 = lds_f64(a3 + hq_off);
+              if (act) {
+                const double2 b0v = lds_v2f64(yB0 + 32u * j);        // {s2_y, el_y}
+                const double2 b1v = lds_v2f64(yB0 + 32u * j + 16u);  // {paths_y, bfreq_y}
+                s2y = b0v.x; ely = b0v.y; pathsy = b1v.x;
+                vs = lds_f64(tabrow + 8u * (ni.x & 0xffu)) * xbf * b1v.y;
+              }
+            }
+            if (__any_sync(0xffffffffu, deg > 4u)) {   // lists are padded to multiples of four with the zero row
+              const uint32_t cl = yC0 + 2u * (ni.x >> 8);
+              uint32_t gq = 4u;
+#pragma unroll 1
+              do {
+                if (gq < deg) {
+                  const uint2 c = lds_v2u32(cl + 2u * gq);
+                  const uint32_t o0 = hbase + (c.x & 0xffffu), o1 = hbase + (c.x >> 16);
+                  const uint32_t o2 = hbase + (c.y & 0xffffu), o3 = hbase + (c.y >> 16);
+                  const double h0 = lds_f64(o0), h1 = lds_f64(o1), h2 = lds_f64(o2), h3 = lds_f64(o3);
+                  if (any_band) {
+                    const double r0 = lds_f64(o0 + hq_off), r1 = lds_f64(o1 + hq_off), r2 = lds_f64(o2 + hq_off), r3 = lds_f64(o3 + hq_off);
+                    R0 += r0; R1 += r1; R2 += r2; R3 += r3;
+                  }
+                  S0 += h0; S1 += h1; S2 += h2; S3 += h3;
+                }
+                gq += 4u;
+              } while (__any_sync(0xffffffffu, gq < deg));
+            }
+            double h = d1.x * ((S0 + S1) + (S2 + S3));   // up_y * a_y*s2_y * sum
+#ifdef ROWS_PROF
+            ps2 = clock64() + (long long)(h == 1.2345e-300);
+#endif
+            if (any_band) {
+              const double m = in_band ? vs * fma(ely, xql, s2y * ((R0 + R1) + (R2 + R3))) : 0.0;
+              h = fma(d1.y, m, h);                       // + up_y * M
+              if (in_band) racc = fma(pathsy, m, racc);
+            }
+            if (act) sts_f64(hbase + ROWB * j, h);
+          } else if (act) {
+            sts_f64(hbase + ROWB * j, 0.0);   // G1 == 0 here and below for every row of the warp
+          }
+#ifdef ROWS_PROF
+          { const long long ps3 = clock64();
+            if (tw == 0 && lane == 0) { prof_acc2[0] += (unsigned long long)(ps1 - ps0); prof_acc2[1] += (unsigned long long)(ps2 - ps1);
+                                        prof_acc3[0] += 0; prof_acc4[0] += (unsigned long long)(ps3 - ps2); prof_acc4[1] += 1; } }
+#endif
+          jw += step;
+          if (jw < jend) {   // wide level: the next step's record, unpipelined
+            ni = make_uint4(0u, 0u, 0u, 0u);
+            if (jw + q < jend) { ni = lds_v4u32(yN0 + 32u * (jw + q)); d1 = lds_v2f64(yN0 + 32u * (jw + q) + 16u); }
+          }
+        }
+        // the next level's record is requested ahead of the barrier
+        jbeg = jend;
+        jend = lds_u32(sb + (L.yLev + 4u * min(ly + 2u, ry.nlev)));
+        ni = make_uint4(0u, 0u, 0u, 0u);
+        if (jbeg + slot_id < jend) { ni = lds_v4u32(yN0 + 32u * (jbeg + slot_id)); d1 = lds_v2f64(yN0 + 32u * (jbeg + slot_id) + 16u); }
+        if (ly + 1u == ry.nlev) sts_f64(tbase + 8u * (tw * 32u + lane), racc);
+        team_sync(bar_id, TT);
       }
 
       PROF_T(pc0);
@@ -487,6 +530,11 @@ __global__ void __launch_bounds__(kRowsMaxThreads, 1) stem_rows_kernel(const Ste
     atomicAdd(P.prof + 12, prof_acc3[0]);
     atomicAdd(P.prof + 13, prof_acc3[1]);
     atomicAdd(P.prof + 14, prof_acc3[2]);
+    atomicAdd(P.prof + 15, prof_acc4[0]);
+    atomicAdd(P.prof + 7, 0ull);
+    atomicAdd(P.prof + 6, 0ull);
+    P.prof[16 + 0] = 0;
+    atomicAdd(P.prof + 17, prof_acc4[1]);
   }
 #endif
 }

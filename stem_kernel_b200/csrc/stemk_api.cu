@@ -7,6 +7,7 @@
 // returns STEMK_ERR_CUDA.
 #include <algorithm>
 #include <cmath>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -59,7 +60,7 @@ struct stemk_ctx {
   DevBuf scratch, carry, tmp_stem, tmp_str, idx_x, idx_y, vals, matrix, order, rowacc;
   unsigned long long* d_bucket = nullptr;  // count[16] | start[16] | queue heads[16]
   int use_fast = 1;                        // STEMK_FAST=0 in the environment forces the general stem kernel
-  int use_rows = 1;                        // STEMK_ROWSK=0: the one-row-per-warp fast kernel instead of the row-block kernel
+  int use_rows = 0;                        // STEMK_ROWSK=1: the experimental row-block kernel (stem_rows.cu) instead of the one-row-per-warp fast kernel
   int rows_tw = 4, rows_r = 0, rows_nt = 0; // STEMK_ROWS_TW / _R / _NT: warps per team, forced rows per block, team limit
   std::string err;
   // stats
@@ -395,8 +396,8 @@ int stemk_pairs_device(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, s
       static unsigned long long* d_prof = nullptr;
       const bool prof = std::getenv("STEMK_PROF") != nullptr;
       if (prof) {
-        if (!d_prof) cudaMalloc((void**)&d_prof, 16 * sizeof(unsigned long long));
-        cudaMemsetAsync(d_prof, 0, 16 * sizeof(unsigned long long), st);
+        if (!d_prof) cudaMalloc((void**)&d_prof, 32 * sizeof(unsigned long long));
+        cudaMemsetAsync(d_prof, 0, 32 * sizeof(unsigned long long), st);
         F.prof = d_prof;
       }
       if (std::getenv("STEMK_TIMING")) std::fprintf(stderr, "rows bucket %d: cap %u R %u teams %u smem %zu\n", b, ny_cap, R, nt, smem);
@@ -406,13 +407,13 @@ int stemk_pairs_device(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, s
       CU(le);
       ctx->launches += 1;
       if (prof) {
-        unsigned long long h[16];
+        unsigned long long h[32];
         cudaStreamSynchronize(st);
         cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost);
         const double nb = h[6] ? (double)h[6] : 1.0, nt_ = h[9] ? (double)h[9] : 1.0;
         std::fprintf(stderr, "prof cap %u R %u teams %u: blocks %llu levels/block %.1f | per block: ticket %.0f A %.0f Await %.0f B %.0f C %.0f | "
-                     "per team: setup %.0f total %.0f cycles | per level (warp 0): work %.0f barrier %.0f | per A load batch: %.0f cycles; flags+fence/batch %.0f (batches %llu)\n", ny_cap, R, nt, h[6], h[7] / nb, h[1] / nb, h[2] / nb, h[3] / nb, h[4] / nb,
-                     h[5] / nb, h[0] / nt_, h[8] / nt_, h[10] / (double)(h[7] ? h[7] : 1), h[11] / (double)(h[7] ? h[7] : 1),
+                     "per team: setup %.0f total %.0f cycles | per step (warp 0): votes+addr %.0f gathers+sum %.0f rest %.0f (steps/block %.1f) | per A batch: flags+TMA %.0f sum %.0f cycles (batches %llu)\n", ny_cap, R, nt, h[6], h[7] / nb, h[1] / nb, h[2] / nb, h[3] / nb, h[4] / nb,
+                     h[5] / nb, h[0] / nt_, h[8] / nt_, h[10] / (double)(h[17] ? h[17] : 1), h[11] / (double)(h[17] ? h[17] : 1), h[15] / (double)(h[17] ? h[17] : 1), h[17] / nb,
                      h[12] / (double)(h[14] ? h[14] : 1), h[13] / (double)(h[14] ? h[14] : 1), h[14]);
       }
     }
@@ -516,6 +517,11 @@ int stemk_gram(stemk_ctx* ctx, const stemk_set* train, int normalize, double* ou
   if (ctx->device == STEMK_DEVICE_NONE) return no_device(ctx);
   if (n == 0) return STEMK_OK;
   CU(cudaSetDevice(ctx->device));
+  const bool timing = std::getenv("STEMK_TIMING") != nullptr;
+  auto now = []() { return std::chrono::steady_clock::now(); };
+  auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double, std::milli>(b - a).count(); };
+  const auto tg0 = now();
   // records sorted by size, big first: the queue then hands out the expensive pairs first
   std::vector<uint32_t> perm(n);
   std::iota(perm.begin(), perm.end(), 0u);
@@ -537,6 +543,7 @@ int stemk_gram(stemk_ctx* ctx, const stemk_set* train, int normalize, double* ou
       xi[k] = a; yi[k] = b; ++k;
     }
   }
+  const auto tg1 = now();
   CU(ctx->idx_x.reserve(n_pairs * sizeof(uint32_t)));
   CU(ctx->idx_y.reserve(n_pairs * sizeof(uint32_t)));
   CU(ctx->vals.reserve(n_pairs * sizeof(double)));
@@ -549,8 +556,14 @@ int stemk_gram(stemk_ctx* ctx, const stemk_set* train, int normalize, double* ou
   rc = stemk_assemble_device(ctx, n_pairs, (const uint32_t*)ctx->idx_x.p, (const uint32_t*)ctx->idx_y.p,
                              (const double*)ctx->vals.p, n, normalize, (double*)ctx->matrix.p, ctx->stream);
   if (rc != STEMK_OK) return rc;
+  const auto tg2 = now();
+  if (timing) CU(cudaStreamSynchronize(ctx->stream));
+  const auto tg3 = now();
   CU(cudaMemcpyAsync(out, ctx->matrix.p, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  if (timing)
+    std::fprintf(stderr, "stemk_gram: %u records: pair list %.1f ms, enqueue %.1f ms, device %.1f ms, D2H %.1f ms\n", n, ms(tg0, tg1),
+                 ms(tg1, tg2), ms(tg2, tg3), ms(tg3, now()));
   return STEMK_OK;
 }
 
