@@ -170,6 +170,18 @@ void stemk_stats_get(stemk_ctx* ctx, uint64_t* launches, double* stem_ms, double
  * denominator, since MEASURED_PEAKS.json carries no fp64 entry). */
 int stemk_fp64_peak(stemk_ctx* ctx, double seconds, double* tflops);
 
+/* Text of kernel-matrix rows in the reference's output format -- KernelMatrix::print (kernel_matrix.cpp:756-770)
+ * and Output::kernel_output (framework.cpp:190-204): one line "<label> 0:<cnt> 1:<v> 2:<v> ... \n" per row, every
+ * value printed like operator<<(std::ostream&, double) with default flags ("%g").  m: n_rows x n_cols with row
+ * stride ld (doubles); labels: n_rows C strings; the row counter of row r is first_cnt + r (1-based in the
+ * reference).  Host code only (no device needed), rows are formatted by n_threads threads (<= 0: all cores).
+ * Returns the number of bytes of the text and writes it (without a terminating NUL) when it fits into cap. */
+size_t stemk_format_rows(const double* m, uint32_t n_rows, uint32_t n_cols, size_t ld, const char* const* labels,
+                         uint32_t first_cnt, int n_threads, char* out, size_t cap);
+
+/* Text of the norm file (Output::norm_output, framework.cpp:218-228): one "%g" value per line. */
+size_t stemk_format_values(const double* v, size_t n, char* out, size_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -267,6 +267,76 @@ class KernelMatrix:
         out.write(format_matrix(self.matrix, self.labels))
 
 
+def format_rows(m, labels, first_cnt=1, n_threads=0):
+    """Native (threaded) writer of kernel-matrix rows in the reference's text format: bytes of
+    "<label> 0:<cnt> 1:<v> ... \\n" lines (KernelMatrix::print, kernel_matrix.cpp:756-770; Output::kernel_output,
+    framework.cpp:190-204).  Byte-identical to format_matrix() below, which stays as the independent check."""
+    import ctypes as C
+    m = np.ascontiguousarray(m, dtype=np.float64)
+    if m.ndim == 1:
+        m = m[None, :]
+    n_rows, n_cols = m.shape
+    if n_rows == 0:
+        return b""
+    lab = (C.c_char_p * n_rows)(*[str(x).encode() for x in labels])
+    cap = n_rows * (64 + 26 * n_cols)
+    buf = C.create_string_buffer(cap)
+    n = L.lib().stemk_format_rows(m.ctypes.data, n_rows, n_cols, n_cols, lab, first_cnt, n_threads, buf, cap)
+    if n > cap:
+        buf = C.create_string_buffer(n)
+        n = L.lib().stemk_format_rows(m.ctypes.data, n_rows, n_cols, n_cols, lab, first_cnt, n_threads, buf, n)
+    return buf.raw[:n]
+
+
+def format_values(v):
+    """One "%g" value per line (the norm file, Output::norm_output, framework.cpp:218-228)."""
+    import ctypes as C
+    v = np.ascontiguousarray(v, dtype=np.float64)
+    cap = 32 * max(1, len(v))
+    buf = C.create_string_buffer(cap)
+    n = L.lib().stemk_format_values(v.ctypes.data, len(v), buf, cap)
+    return buf.raw[:n]
+
+
+def stream_predict(ctx, train, test_batches, out, norm_out=None, sv_index=None, normalize=False, train_diag=None):
+    """Streaming mirror of App::predict + Output (common/framework.h:167-306, framework.cpp:141-234): for every batch
+    (labels, uploaded test set) of `test_batches` the rows k(test_i, train_j) are computed on the device
+    (stemk_cross), normalised like framework.h:279-283 (`vec[j] /= sqrt(diag[j]*self)`), written to the binary file
+    object `out` in the reference's text format and, if given, the self terms to `norm_out`.  The text of batch b is
+    formatted by the native threaded writer while the device computes batch b+1.  Yields (labels, rows, self) per
+    batch so that a caller can feed the unchanged CPU svm_predict.  Returns nothing else: the matrix is never held
+    in memory as a whole."""
+    import threading
+    norm = normalize or norm_out is not None
+    diag = None
+    if normalize:
+        diag = np.asarray(train_diag) if train_diag is not None else ctx.diag(train, sv_index)
+    cnt = 1
+    pending = None
+
+    def flush(job):
+        labels, rows, selfv, first = job
+        out.write(format_rows(rows, labels, first))
+        if norm_out is not None:
+            norm_out.write(format_values(selfv))
+
+    for labels, test in test_batches:
+        rows, selfv = ctx.cross(test, train, sv_index, normalize=False, want_self=norm)
+        if normalize:
+            rows = rows / np.sqrt(diag[None, :] * selfv[:, None])
+        if pending is not None:
+            pending[0].join()
+            yield pending[1]
+        job = (list(labels), rows, selfv, cnt)
+        th = threading.Thread(target=flush, args=(job,))
+        th.start()
+        pending = (th, (job[0], rows, selfv))
+        cnt += len(job[0])
+    if pending is not None:
+        pending[0].join()
+        yield pending[1]
+
+
 def format_matrix(m, labels):
     lines = []
     for i in range(m.shape[0]):
@@ -277,5 +347,6 @@ def format_matrix(m, labels):
 
 
 def _g6(v):
-    s = "%g" % v
-    return s
+    if v != v:   # glibc (and with it libstdc++'s operator<<) spells a NaN with the sign bit set "-nan"; x86 0/0 is one
+        return "-nan" if np.signbit(v) else "nan"
+    return "%g" % v

@@ -7,6 +7,7 @@
 // returns STEMK_ERR_CUDA.
 #include <algorithm>
 #include <cmath>
+#include <charconv>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -715,6 +716,70 @@ void stemk_stats_get(stemk_ctx* ctx, uint64_t* launches, double* stem_ms, double
   if (launches) *launches = ctx->launches;
   if (stem_ms) *stem_ms = ctx->stem_ms;
   if (string_ms) *string_ms = ctx->string_ms;
+}
+
+namespace {
+// operator<<(std::ostream&, double) with default flags == printf("%g"): std::to_chars(general, precision 6) produces
+// the same digits (it is specified as printf's %.6g in the C locale); non-finite values go through snprintf so
+// that the spelling ("nan", "-nan", "inf") is glibc's.
+inline char* put_g(char* p, double v) {
+  if (!std::isfinite(v)) return p + std::snprintf(p, 32, "%g", v);
+  auto r = std::to_chars(p, p + 32, v, std::chars_format::general, 6);
+  return r.ptr;
+}
+inline char* put_u(char* p, uint32_t v) { return std::to_chars(p, p + 12, v).ptr; }
+}  // namespace
+
+size_t stemk_format_rows(const double* m, uint32_t n_rows, uint32_t n_cols, size_t ld, const char* const* labels,
+                         uint32_t first_cnt, int n_threads, char* out, size_t cap) {
+  if (!m || !labels || n_rows == 0) return 0;
+  if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+  n_threads = (int)std::min<uint32_t>((uint32_t)n_threads, n_rows);
+  std::vector<std::string> lines(n_rows);
+  auto work = [&](int t) {
+    std::vector<char> buf;
+    for (uint32_t r = (uint32_t)t; r < n_rows; r += (uint32_t)n_threads) {
+      const size_t ll = std::strlen(labels[r]);
+      buf.resize(ll + 32 + (size_t)n_cols * 48);
+      char* p = buf.data();
+      std::memcpy(p, labels[r], ll); p += ll;
+      *p++ = ' '; *p++ = '0'; *p++ = ':';
+      p = put_u(p, first_cnt + r);
+      *p++ = ' ';
+      const double* row = m + (size_t)r * ld;
+      for (uint32_t j = 0; j < n_cols; ++j) {
+        p = put_u(p, j + 1);
+        *p++ = ':';
+        p = put_g(p, row[j]);
+        *p++ = ' ';
+      }
+      *p++ = '\n';
+      lines[r].assign(buf.data(), (size_t)(p - buf.data()));
+    }
+  };
+  if (n_threads == 1) work(0);
+  else {
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; ++t) th.emplace_back(work, t);
+    for (auto& x : th) x.join();
+  }
+  size_t total = 0;
+  for (const auto& l : lines) total += l.size();
+  if (out && total <= cap) {
+    char* p = out;
+    for (const auto& l : lines) { std::memcpy(p, l.data(), l.size()); p += l.size(); }
+  }
+  return total;
+}
+
+size_t stemk_format_values(const double* v, size_t n, char* out, size_t cap) {
+  if (!v) return 0;
+  std::string s;
+  s.reserve(n * 14);
+  char b[40];
+  for (size_t i = 0; i < n; ++i) { char* e = put_g(b, v[i]); *e++ = '\n'; s.append(b, (size_t)(e - b)); }
+  if (out && s.size() <= cap) std::memcpy(out, s.data(), s.size());
+  return s.size();
 }
 
 int stemk_fp64_peak(stemk_ctx* ctx, double seconds, double* tflops) {

@@ -394,3 +394,31 @@ def test_sharded_driver_single_rank_equals_gram():
         m = sg.run(normalize=True)
     be.stream.synchronize()
     assert np.array_equal(m.cpu().numpy(), ctx.gram(ds, normalize=True), equal_nan=True)
+
+
+def test_stream_predict_writes_the_reference_text():
+    """Streaming predict + writer (SURVEY 8(f) rank 2; App::predict / Output, common/framework.h:167-306,
+    framework.cpp:141-234): test rows computed batch by batch, normalised like framework.h:279-283, written by the
+    native threaded writer.  The files must be byte-identical to formatting the one-shot normalised cross matrix
+    with the Python mirror of KernelMatrix::print / Output::kernel_output, whatever the batch size."""
+    import io
+    train = hostlib.build_many(synth.make_config(1, 40, offset=100), TH)
+    test_recs = synth.make_config(1, 23, offset=900)
+    test = hostlib.build_many(test_recs, TH)
+    ctx = api.Context(L.make_params(L.SU_STEM_STR))
+    dtrain = ctx.upload(hostlib.SeqSet(train))
+    labels = ["+1" if i % 3 else "-1" for i in range(len(test))]
+    want_m, want_self = ctx.cross(ctx.upload(hostlib.SeqSet(test)), dtrain, normalize=True)
+    want = api.format_matrix(want_m, labels).encode()
+    want_norm = "".join(api._g6(v) + "\n" for v in want_self).encode()
+    for bs in (1, 5, 23):
+        def batches():
+            for b in range(0, len(test), bs):
+                yield labels[b:b + bs], ctx.upload(hostlib.SeqSet(test[b:b + bs]))
+        out, nout = io.BytesIO(), io.BytesIO()
+        seen = 0
+        for lab, rows, selfv in api.stream_predict(ctx, dtrain, batches(), out, norm_out=nout, normalize=True):
+            assert rows.shape == (len(lab), len(train)) and np.array_equal(rows, want_m[seen:seen + len(lab)])
+            seen += len(lab)
+        assert seen == len(test)
+        assert out.getvalue() == want and nout.getvalue() == want_norm
