@@ -132,6 +132,98 @@ class ShardedGram:
         return self.assemble(self.xi_all, self.yi_all, undeal(self.recv, self.n_pairs), self.n, normalize)
 
 
+class ShardedCross:
+    """Rectangular test x train matrix over `world` ranks: KernelMatrix::calculate(test, train, ...) and the
+    one-row variant behind App::predict (common/kernel_matrix.cpp:635-754, MPI path :264-369; BASELINE config 5:
+    5k test x 10k train feeding svm_predict).  Three pair lists are dealt round-robin like the square case --
+    the n_test x n_cols kernel rows (x = train record, the FIRST argument, kernel_matrix.cpp:159,168), the n_test
+    self terms k(t,t) and, for the normalisation, the n_cols train diagonals (KernelMatrix::diagonal,
+    :578-633) -- their values travel to rank 0 in ONE gather, and rank 0 scatters, then divides by
+    sqrt(self_i * diag_j) as kernel_matrix.cpp:735-748 / framework.h:279-283 do (columns outside sv_index keep the
+    caller's `init` value and a zero diagonal, i.e. they become NaN / inf exactly like the reference's rows).
+
+    compute(which_x, which_y, xi, yi) -> 1-D float64 tensor on `device`; which_* is "train" or "test".
+    """
+
+    def __init__(self, test_keys, train_keys, rank, world, device, compute, cols=None, group=None):
+        self.rank, self.world, self.device, self.group, self.compute = rank, world, device, group, compute
+        self.n_test, self.n_train = len(test_keys), len(train_keys)
+        self.cols = np.arange(self.n_train, dtype=np.uint32) if cols is None else np.asarray(cols, dtype=np.uint32)
+        xi, yi = cross_pairs(test_keys, train_keys, self.cols)
+        tid = size_order(test_keys)
+        cid = self.cols[size_order(np.asarray(train_keys)[self.cols])]
+        # (which_x, which_y, xi, yi) of the three lists; every list is dealt on its own
+        self.lists = [("train", "test", xi, yi), ("test", "test", tid, tid), ("train", "train", cid, cid)]
+        self.slabs = [slab(len(l[2]), world) for l in self.lists]
+        as_dev = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int32).copy()).to(device)
+        self.mine = []
+        for _, _, a, b in self.lists:
+            m = deal(len(a), rank, world)
+            self.mine.append((as_dev(a[m]), as_dev(b[m]), len(m)))
+        self.send = torch.zeros(sum(self.slabs), dtype=torch.float64, device=device)
+        if rank == 0:
+            self.recv = torch.zeros((world, sum(self.slabs)), dtype=torch.float64, device=device)
+            self.idx = [(torch.from_numpy(a.astype(np.int64)).to(device), torch.from_numpy(b.astype(np.int64)).to(device))
+                        for _, _, a, b in self.lists]
+
+    @property
+    def n_pairs(self):
+        return sum(len(l[2]) for l in self.lists)
+
+    def run(self, normalize=False, init=0.0):
+        """Returns (matrix [n_test, n_train], self [n_test]) on rank 0, (None, None) elsewhere."""
+        off = 0
+        for k, (wx, wy, _, _) in enumerate(self.lists):
+            a, b, n = self.mine[k]
+            if n and (k < 2 or normalize):
+                self.send[off:off + n].copy_(self.compute(wx, wy, a, b))
+            off += self.slabs[k]
+        if self.world > 1:
+            if self.rank == 0:
+                dist.gather(self.send, list(self.recv.unbind(0)), dst=0, group=self.group)
+            else:
+                dist.gather(self.send, None, dst=0, group=self.group)
+        else:
+            self.recv[0].copy_(self.send)
+        if self.rank != 0:
+            return None, None
+        vals, off = [], 0
+        for k, (_, _, a, _) in enumerate(self.lists):
+            vals.append(undeal(self.recv[:, off:off + self.slabs[k]], len(a)))
+            off += self.slabs[k]
+        m = torch.full((self.n_test, self.n_train), float(init), dtype=torch.float64, device=self.device)
+        m[self.idx[0][1], self.idx[0][0]] = vals[0]                     # row = test record (y), column = train record (x)
+        selfv = torch.zeros(self.n_test, dtype=torch.float64, device=self.device)
+        selfv[self.idx[1][0]] = vals[1]
+        if normalize:
+            diag = torch.zeros(self.n_train, dtype=torch.float64, device=self.device)
+            diag[self.idx[2][0]] = vals[2]
+            if m.device.type == "cpu":   # torch's CPU sqrt / division are vectorised and not always correctly rounded
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    m = torch.from_numpy(m.numpy() / np.sqrt(selfv.numpy()[:, None] * diag.numpy()[None, :]))
+            else:
+                m = m / torch.sqrt(selfv[:, None] * diag[None, :])
+        return m, selfv
+
+
+class GpuCrossBackend:
+    """compute(which_x, which_y, xi, yi) of ShardedCross bound to the C ABI (train and test sets uploaded on this
+    rank's GPU).  Same stream rule as GpuBackend."""
+
+    def __init__(self, ctx, dtrain, dtest, device):
+        self.ctx, self.sets, self.device = ctx, {"train": dtrain, "test": dtest}, device
+        self.stream = torch.cuda.Stream(device)
+
+    def compute(self, which_x, which_y, xi, yi):
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        if not s:
+            raise RuntimeError("run under a non-default torch stream (GpuCrossBackend.stream)")
+        out = torch.empty(xi.numel(), dtype=torch.float64, device=self.device)
+        self.ctx.pairs_device(self.sets[which_x], self.sets[which_y], xi.numel(), xi.data_ptr(), yi.data_ptr(),
+                              out.data_ptr(), s)
+        return out
+
+
 class GpuBackend:
     """compute / assemble bound to the C ABI on this rank's GPU, asynchronous on torch's current stream.
     Run ShardedGram.run() under `with torch.cuda.stream(backend.stream)`: the library treats a NULL stream as

@@ -43,6 +43,24 @@ def main():
             np.fill_diagonal(m, 1.0)
         return torch.from_numpy(m)
 
+    if len(sys.argv) > 5 and sys.argv[5] == "cross":
+        # rectangular: the first 11 golden records are the training set, the rest the test set, 7 sv columns
+        n_tr = 11
+        ftr, fte = hostlib.SeqSet(md[:n_tr]), hostlib.SeqSet(md[n_tr:])
+        descs = {"train": ftr.desc(), "test": fte.desc()}
+        cols = np.array([0, 2, 3, 5, 7, 8, 10], dtype=np.uint32)
+
+        def compute_sets(wx, wy, xi, yi):
+            return torch.from_numpy(O.pairs(p, descs[wx], descs[wy], xi.numpy().view(np.uint32), yi.numpy().view(np.uint32)))
+
+        sc = sharded.ShardedCross(keys[n_tr:], keys[:n_tr], rank, world, torch.device("cpu"), compute_sets, cols=cols)
+        m, selfv = sc.run(normalize=True, init=-3.0)
+        assert (m is None) == (rank != 0)
+        if rank == 0:
+            np.save(out, np.concatenate([m.numpy(), selfv.numpy()[:, None]], axis=1))
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     sg = sharded.ShardedGram(keys, rank, world, torch.device("cpu"), compute, assemble)
     res = sg.run(normalize=True)
     assert (res is None) == (rank != 0)

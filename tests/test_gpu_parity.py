@@ -430,3 +430,38 @@ def test_stream_predict_writes_the_reference_text():
         assert nout.getvalue() == "".join(api._g6(v) + "\n" for v in np.concatenate(got_self)).encode()
         if bs == len(test):
             assert out.getvalue() == want and nout.getvalue() == want_norm
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(R.REF_DIR, "libstemk_ref_svm.so")), reason="oracle/_ref not shipped")
+def test_sharded_cross_feeds_identical_svm_predictions():
+    """BASELINE config 5 at test size: rectangular test x train matrix through the multi-GPU driver's rectangular path
+    (ShardedCross with world 1: pair lists, self terms, train diagonals, one buffer, scatter, normalisation) against
+    the oracle and against stemk_cross; the vendored LIBSVM trained on the normalised train Gram predicts the same
+    labels from the GPU rows as from the oracle's rows (north_star: identical downstream predictions)."""
+    import torch
+    from stem_kernel_b200 import sharded
+    rtrain, rtest = synth.make_config(1, 60, offset=300), synth.make_config(1, 25, offset=700)
+    train, test = hostlib.build_many(rtrain, TH), hostlib.build_many(rtest, TH)
+    ftrain, ftest = hostlib.SeqSet(train), hostlib.SeqSet(test)
+    p = L.make_params(L.SU_STEM_STR)
+    ctx = api.Context(p)
+    dtrain, dtest = ctx.upload(ftrain), ctx.upload(ftest)
+    dev = torch.device("cuda", 0)
+    be = sharded.GpuCrossBackend(ctx, dtrain, dtest, dev)
+    sc = sharded.ShardedCross(sharded.record_keys(dtest, string=True), sharded.record_keys(dtrain, string=True), 0, 1, dev,
+                              be.compute)
+    assert sc.n_pairs == 25 * 60 + 25 + 60
+    with torch.cuda.stream(be.stream):
+        m, selfv = sc.run(normalize=True)
+    be.stream.synchronize()
+    got, got_self = m.cpu().numpy(), selfv.cpu().numpy()
+    want, want_self = O.cross(oparams(p), ftest.desc(), ftrain.desc(), normalize=True)
+    assert relerr(got, want) < TOL and relerr(got_self, want_self) < TOL
+    one, one_self = ctx.cross(dtest, dtrain, normalize=True)
+    np.testing.assert_allclose(got, one, rtol=1e-12, atol=0)
+    np.testing.assert_allclose(got_self, one_self, rtol=1e-12, atol=0)
+    ktrain = ctx.gram(dtrain, normalize=True)
+    y = np.array([r["label"] for r in rtrain], dtype=np.float64)
+    pred_gpu = R.svm_train_predict(ktrain, y, got)
+    pred_ref = R.svm_train_predict(O.gram(oparams(p), ftrain.desc(), True), y, want)
+    assert np.array_equal(pred_gpu, pred_ref) and set(np.unique(pred_gpu)) <= {-1.0, 1.0}

@@ -75,3 +75,29 @@ def test_world_size_2_gloo_matches_golden(tmp_path, golden):
     assert all(p.returncode == 0 for p in procs), "\n".join(logs)
     got = np.load(out)
     assert np.array_equal(got, golden["z"]["gram_norm_k3_b10"], equal_nan=True)
+
+
+def test_world_size_2_gloo_rectangular_matches_the_oracle(tmp_path):
+    """ShardedCross (test x train with an sv subset, self terms, train diagonals, one gather) against the oracle's
+    one-process cross matrix: bit-identical values, untouched columns outside sv_index turned into the same
+    non-finite pattern by the normalisation."""
+    from conftest import TH, load_golden_records
+    from oracle import oraclebind as O
+    from stem_kernel_b200 import _lib as L, hostlib
+    port, out = _free_port(), str(tmp_path / "cross.npy")
+    worker = os.path.join(ROOT, "tests", "_sharded_worker.py")
+    procs = [subprocess.Popen([sys.executable, worker, str(r), "2", str(port), out, "cross"], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT) for r in range(2)]
+    logs = [p.communicate(timeout=240)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(logs)
+    got = np.load(out)
+    recs, _ = load_golden_records()
+    md = [hostlib.MData.from_record(r, TH) for r in recs]
+    ftr, fte = hostlib.SeqSet(md[:11]), hostlib.SeqSet(md[11:])
+    p = O.Params.from_buffer_copy(L.make_params(L.SU_STEM_STR))
+    cols = np.array([0, 2, 3, 5, 7, 8, 10], dtype=np.uint32)
+    want, want_self = O.cross(p, fte.desc(), ftr.desc(), sv_index=cols, normalize=True, init=-3.0)
+    assert got.shape == (len(md) - 11, 12)
+    assert np.array_equal(got[:, :11], want, equal_nan=True) and np.array_equal(got[:, 11], want_self)
+    others = np.setdiff1d(np.arange(11), cols)
+    assert not np.isfinite(got[:, others]).any()
