@@ -32,7 +32,7 @@ constexpr int kMaxFastBuckets = 8;
 #endif
 constexpr uint32_t kFastGroup = STEMK_GROUP;  // == kGroup of stem_fast.cu
 #ifndef STEMK_MAXWARPS
-#define STEMK_MAXWARPS 24
+#define STEMK_MAXWARPS 28
 #endif
 constexpr int kFastMaxWarps = STEMK_MAXWARPS;  // warps per CTA of the fast stem kernel (its launch bound)
 
