@@ -170,6 +170,35 @@ void stemk_stats_get(stemk_ctx* ctx, uint64_t* launches, double* stem_ms, double
  * denominator, since MEASURED_PEAKS.json carries no fp64 entry). */
 int stemk_fp64_peak(stemk_ctx* ctx, double seconds, double* tflops);
 
+/* ---- BPLA / local-alignment kernels: bpla_kernel/bpla_kernel.cpp:64-175 -------------------
+ * BPLAKernel<double, MData>::operator() -- the local-alignment kernel with (or, no_bp, without) base-pairing
+ * profiles, in its sum-over-alignments form (local_alignment_exp, :64-118) or, sw, its Smith-Waterman form
+ * (local_alignment_max, :120-157).  A record is the reference's `Data` (bpla_kernel/data.h:30-53) flattened: per
+ * column the 5 profile counts [A,C,G,U,GAP] of ProfileSequence (common/profile.h) and the three base-pairing
+ * profiles p_left / p_right / p_unpair as data.cpp:19-46 leaves them (square roots, float).  score: the 4 x 4
+ * substitution table (bpla_kernel/main.cpp:20-26 holds the default).  Parameter defaults: main.cpp:69-73. */
+typedef struct stemk_bpla_params {
+  int32_t no_bp;      /* --noBP: LAScore instead of BPLAScore (bpla_kernel.cpp:16-62) */
+  int32_t sw;         /* --SW */
+  double gap, ext;    /* -8, -0.75 */
+  double alpha, beta; /* 4.5, 0.11 */
+  double score[16];   /* [a*4+b] */
+} stemk_bpla_params;
+
+typedef struct stemk_bpla_set {
+  uint32_t n_seqs;
+  const uint32_t* col_off;   /* [n+1] */
+  const float* profile;      /* 5 per column */
+  const float* p_left;       /* per column; may be NULL when no_bp */
+  const float* p_right;
+  const float* p_unpair;
+} stemk_bpla_set;
+
+/* out[k] = k_bpla(x[xi[k]], y[yi[k]]) on the context's device (host buffers; the two sets are copied to the
+ * device by the call).  The context's own kernel kind is irrelevant here.  No CPU path. */
+int stemk_bpla_pairs(stemk_ctx* ctx, const stemk_bpla_params* params, const stemk_bpla_set* x, const stemk_bpla_set* y,
+                     size_t n_pairs, const uint32_t* xi, const uint32_t* yi, double* out);
+
 /* Text of kernel-matrix rows in the reference's output format -- KernelMatrix::print (kernel_matrix.cpp:756-770)
  * and Output::kernel_output (framework.cpp:190-204): one line "<label> 0:<cnt> 1:<v> 2:<v> ... \n" per row, every
  * value printed like operator<<(std::ostream&, double) with default flags ("%g").  m: n_rows x n_cols with row

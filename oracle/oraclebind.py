@@ -36,6 +36,7 @@ def lib():
         L.oracle_print.restype = C.c_long
         L.oracle_print.argtypes = [vp, C.c_size_t, C.c_size_t, vp, vp, C.c_long]
         L.oracle_pair_cost.argtypes = [vp, vp, C.c_uint32, vp, C.c_uint32, vp, vp]
+        L.oracle_bpla_pairs.argtypes = [vp, vp, vp, C.c_size_t, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -92,3 +93,13 @@ def pair_cost(params, dx, xi, dy, yi):
     c, f = C.c_double(), C.c_double()
     lib().oracle_pair_cost(_p(params), _p(dx), xi, _p(dy), yi, C.byref(c), C.byref(f))
     return c.value, f.value
+
+
+def bpla_pairs(params, x, y, xi, yi):
+    """Restated BPLA kernel; params / x / y: stem_kernel_b200.bpla.BplaParams / BplaSet (same C structs)."""
+    xi = np.ascontiguousarray(xi, dtype=np.uint32)
+    yi = np.ascontiguousarray(yi, dtype=np.uint32)
+    out = np.zeros(len(xi))
+    cx, cy = x.c(), y.c()
+    lib().oracle_bpla_pairs(_p(params), _p(cx), _p(cy), len(xi), xi.ctypes.data, yi.ctypes.data, out.ctypes.data)
+    return out

@@ -265,3 +265,35 @@ def svm_train_predict(Ktrain, y, Ktest, C_=1.0):
                                         Ktest.ctypes.data, pred.ctypes.data)
     assert rc == 0
     return pred
+
+
+# ---- the reference BPLA kernel (bpla_kernel/bpla_kernel.cpp behind oracle/ref_harness_bpla.cpp) ----
+def bpla_pairs(params, x, y, xi, yi):
+    """params / x / y: stem_kernel_b200.bpla.BplaParams / BplaSet; the reference's own Data objects are rebuilt from
+    the rows and the three base-pairing profiles."""
+    Lb = _lib("libstemk_ref_bpla.so")
+    xi = np.ascontiguousarray(xi, dtype=np.uint32)
+    yi = np.ascontiguousarray(yi, dtype=np.uint32)
+    out = np.zeros(len(xi))
+
+    def rows_of(s):
+        off = np.zeros(len(s) + 1, dtype=np.uint32)
+        flat = []
+        for k, r in enumerate(s.rows):
+            flat.extend(r)
+            off[k + 1] = len(flat)
+        return off, (C.c_char_p * max(1, len(flat)))(*[t.encode() for t in flat])
+
+    ox, rx = rows_of(x)
+    oy, ry = rows_of(y)
+    table = np.array(list(params.score), dtype=np.float64)
+    vp = C.c_void_p
+    Lb.refbpla_pairs.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, vp,
+                                 C.c_int, vp, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, C.c_size_t, vp, vp, vp]
+    rc = Lb.refbpla_pairs(params.no_bp, params.sw, params.gap, params.ext, params.alpha, params.beta, table.ctypes.data,
+                          len(x), ox.ctypes.data, rx, x.col_off.ctypes.data, x.p_left.ctypes.data, x.p_right.ctypes.data,
+                          x.p_unpair.ctypes.data, len(y), oy.ctypes.data, ry, y.col_off.ctypes.data, y.p_left.ctypes.data,
+                          y.p_right.ctypes.data, y.p_unpair.ctypes.data, len(xi), xi.ctypes.data, yi.ctypes.data,
+                          out.ctypes.data)
+    assert rc == 0
+    return out

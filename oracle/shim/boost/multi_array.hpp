@@ -1,6 +1,6 @@
 // Shim: the subset of boost::multi_array the reference touches -- construction
 // from boost::extents[a][b]..., zero-initialised row-major storage, chained
-// operator[], resize(extents), size() of the leading dimension and ::element.
+// operator[], resize(extents), size() of the leading dimension, data(), num_elements() and ::element.
 #pragma once
 #include <cstddef>
 #include <vector>
@@ -39,6 +39,9 @@ class multi_array {
   explicit multi_array(const shim_detail::ext_gen<N>& e) { reshape(e); data_.assign(total(), T()); }
   void resize(const shim_detail::ext_gen<N>& e) { reshape(e); data_.assign(total(), T()); }
   std::size_t size() const { return dim_[0]; }
+  T* data() { return data_.data(); }
+  const T* data() const { return data_.data(); }
+  std::size_t num_elements() const { return data_.size(); }
   shim_detail::view<T, N> whole() { return shim_detail::view<T, N>{data_.data(), dim_, stride_}; }
   shim_detail::view<const T, N> whole() const { return shim_detail::view<const T, N>{data_.data(), dim_, stride_}; }
   auto operator[](std::size_t i) -> decltype(this->whole()[i]) { return whole()[i]; }

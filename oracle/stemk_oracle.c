@@ -398,3 +398,70 @@ void oracle_pair_cost(const stemk_params* p, const stemk_seqset_desc* X, uint32_
   }
   *cells = c; *flops = f;
 }
+
+/* ------------------------------------------------------------------------------------------------------------
+ * BPLA / local-alignment kernel -- restatement of bpla_kernel/bpla_kernel.cpp, statement order and the float /
+ * double mix of the reference kept (LAScore :16-45: `n` is a float, the products x*y are float, the table term
+ * is double; BPLAScore :47-62: the pairing terms are float products summed in float, alpha is double;
+ * local_alignment_exp :64-118; local_alignment_max :120-157; dispatch :160-175). */
+static double bpla_la_score(const double* tab, const float* x, const float* y) {
+  double v = 0.0;
+  float n = 0;
+  for (int k = 0; k != 4; ++k) {
+    if (x[k] == 0) continue;
+    for (int l = 0; l != 4; ++l) {
+      if (y[l] == 0) continue;
+      n += x[k] * y[l];
+      v += tab[k * 4 + l] * x[k] * y[l];
+    }
+  }
+  return n == 0 ? 0.0 : v / n;
+}
+
+static double bpla_score(const stemk_bpla_params* p, const stemk_bpla_set* X, size_t cx, const stemk_bpla_set* Y, size_t cy) {
+  const double la = bpla_la_score(p->score, X->profile + 5 * cx, Y->profile + 5 * cy);
+  if (p->no_bp) return la;
+  return p->alpha * (X->p_right[cx] * Y->p_right[cy] + X->p_left[cx] * Y->p_left[cy]) + X->p_unpair[cx] * Y->p_unpair[cy] * la;
+}
+
+static double bpla_pair(const stemk_bpla_params* p, const stemk_bpla_set* X, uint32_t xr, const stemk_bpla_set* Y, uint32_t yr) {
+  const size_t x0 = X->col_off[xr], lx = X->col_off[xr + 1] - x0, y0 = Y->col_off[yr], ly = Y->col_off[yr + 1] - y0;
+  const size_t w = ly + 1;
+  double* M = calloc(5 * (lx + 1) * w, sizeof(double));
+  double *Xt = M + (lx + 1) * w, *Yt = Xt + (lx + 1) * w, *X2 = Yt + (lx + 1) * w, *Y2 = X2 + (lx + 1) * w;
+  double res;
+  if (!p->sw) {
+    const double beta_gap = exp(p->beta * p->gap), beta_ext = exp(p->beta * p->ext);
+    for (size_t i = 1; i != lx + 1; ++i)
+      for (size_t j = 1; j != ly + 1; ++j) {
+        M[i * w + j] = exp(p->beta * bpla_score(p, X, x0 + i - 1, Y, y0 + j - 1)) *
+                       (1 + Xt[(i - 1) * w + j - 1] + Yt[(i - 1) * w + j - 1] + M[(i - 1) * w + j - 1]);
+        Xt[i * w + j] = beta_gap * M[(i - 1) * w + j] + beta_ext * Xt[(i - 1) * w + j];
+        Yt[i * w + j] = beta_gap * (M[i * w + j - 1] + Xt[i * w + j - 1]) + beta_ext * Yt[i * w + j - 1];
+        X2[i * w + j] = M[(i - 1) * w + j] + X2[(i - 1) * w + j];
+        Y2[i * w + j] = M[i * w + j - 1] + X2[i * w + j - 1] + Y2[i * w + j - 1];
+      }
+    res = 1 + X2[lx * w + ly] + Y2[lx * w + ly] + M[lx * w + ly];
+  } else {
+    double mmax = 0;
+    for (size_t i = 1; i != lx + 1; ++i)
+      for (size_t j = 1; j != ly + 1; ++j) {
+        double m = fmax(0.0, M[(i - 1) * w + j - 1]);
+        m = fmax(m, Xt[(i - 1) * w + j - 1]);
+        m = fmax(m, Yt[(i - 1) * w + j - 1]);
+        m += bpla_score(p, X, x0 + i - 1, Y, y0 + j - 1);
+        M[i * w + j] = m;
+        mmax = fmax(mmax, m);
+        Xt[i * w + j] = fmax(M[(i - 1) * w + j] + p->gap, Xt[(i - 1) * w + j] + p->ext);
+        Yt[i * w + j] = fmax(fmax(M[i * w + j - 1] + p->gap, Xt[i * w + j - 1] + p->gap), Yt[i * w + j - 1] + p->ext);
+      }
+    res = mmax;
+  }
+  free(M);
+  return res;
+}
+
+void oracle_bpla_pairs(const stemk_bpla_params* p, const stemk_bpla_set* X, const stemk_bpla_set* Y, size_t n_pairs,
+                       const uint32_t* xi, const uint32_t* yi, double* out) {
+  for (size_t k = 0; k < n_pairs; ++k) out[k] = bpla_pair(p, X, xi[k], Y, yi[k]);
+}

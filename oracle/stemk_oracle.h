@@ -17,6 +17,9 @@ void oracle_cross(const stemk_params* p, const stemk_seqset_desc* T, const stemk
 long oracle_print(const double* m, size_t rows, size_t cols, const int* labels, char* buf, long cap);
 void oracle_pair_cost(const stemk_params* p, const stemk_seqset_desc* X, uint32_t xi, const stemk_seqset_desc* Y,
                       uint32_t yi, double* cells, double* flops);
+/* BPLA / local-alignment kernel, bpla_kernel/bpla_kernel.cpp:16-175 */
+void oracle_bpla_pairs(const stemk_bpla_params* p, const stemk_bpla_set* X, const stemk_bpla_set* Y, size_t n_pairs,
+                       const uint32_t* xi, const uint32_t* yi, double* out);
 #ifdef __cplusplus
 }
 #endif

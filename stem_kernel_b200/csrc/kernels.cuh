@@ -126,6 +126,10 @@ cudaError_t launch_combine(int kind, double alpha, double beta, const double* st
 cudaError_t launch_scatter_square(const double* vals, const uint32_t* xi, const uint32_t* yi, unsigned long long n_pairs,
                                   double* matrix, uint32_t n, cudaStream_t stream);
 cudaError_t launch_normalize_square(double* matrix, uint32_t n, cudaStream_t stream);
+// BPLA / local-alignment kernels (bpla.cu): host buffers in, host buffer out, synchronous on `stream`
+cudaError_t run_bpla(const stemk_bpla_params& p, const stemk_bpla_set& x, const stemk_bpla_set& y, size_t n_pairs,
+                     const uint32_t* xi, const uint32_t* yi, double* out, int sm_count, size_t smem_optin,
+                     cudaStream_t stream, std::string* err);
 cudaError_t launch_fp64_peak(double* sink, int grid, int block, int iters, cudaStream_t stream);
 
 }  // namespace stemk

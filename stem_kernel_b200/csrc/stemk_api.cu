@@ -718,6 +718,27 @@ void stemk_stats_get(stemk_ctx* ctx, uint64_t* launches, double* stem_ms, double
   if (string_ms) *string_ms = ctx->string_ms;
 }
 
+int stemk_bpla_pairs(stemk_ctx* ctx, const stemk_bpla_params* params, const stemk_bpla_set* x, const stemk_bpla_set* y,
+                     size_t n_pairs, const uint32_t* xi, const uint32_t* yi, double* out) {
+  if (!ctx || !params || !x || !y) return fail(ctx, STEMK_ERR_ARG, "null argument");
+  if (ctx->device == STEMK_DEVICE_NONE) return no_device(ctx);
+  if (n_pairs == 0) return STEMK_OK;
+  if (!xi || !yi || !out) return fail(ctx, STEMK_ERR_ARG, "null buffer");
+  for (const stemk_bpla_set* s : {x, y}) {
+    if (s->n_seqs && (!s->col_off || !s->profile)) return fail(ctx, STEMK_ERR_ARG, "null set array");
+    if (!params->no_bp && s->n_seqs && (!s->p_left || !s->p_right || !s->p_unpair))
+      return fail(ctx, STEMK_ERR_ARG, "base-pairing profiles missing (p_left / p_right / p_unpair)");
+  }
+  for (size_t k = 0; k < n_pairs; ++k)
+    if (xi[k] >= x->n_seqs || yi[k] >= y->n_seqs) return fail(ctx, STEMK_ERR_ARG, "pair index out of range");
+  CU(cudaSetDevice(ctx->device));
+  std::string err;
+  cudaError_t e = run_bpla(*params, *x, *y, n_pairs, xi, yi, out, ctx->sm_count, ctx->smem_optin, ctx->stream, &err);
+  if (e != cudaSuccess) return err.empty() ? cuda_fail(ctx, e, "BPLA kernel") : fail(ctx, STEMK_ERR_NOMEM, err);
+  ctx->launches += 1;
+  return STEMK_OK;
+}
+
 namespace {
 // operator<<(std::ostream&, double) with default flags == printf("%g"): std::to_chars(general, precision 6) produces
 // the same digits (it is specified as printf's %.6g in the C locale); non-finite values go through snprintf so

@@ -8,6 +8,9 @@ of its own, so these files pin the oracle and the CUDA path to 
   golden_mdata.npz     the reference constructor's MData (DAG, profiles, weights) for each record
   golden_naive.npz     string_kernel/ (naive) Gram on 8 raw strings, gap parsed as float
   golden_svm.npz       40-record C1 Gram (reference) and the vendored LIBSVM's 5-fold CV targets on it
+  golden_bpla.npz      bpla_kernel/ (BPLA / local-alignment kernels): 12 records (single sequences, alignments,
+                       IUPAC, gaps, a length-1 and a 70-column record), their base-pairing profiles, and the
+                       reference's upper-triangle values for {BP, noBP} x {sum form, Smith-Waterman}
 """
 import json
 import os
@@ -34,6 +37,21 @@ def golden_records():
     # a single isolated hairpin: one stem of 3 stacked pairs
     recs.append(dict(rows=["gggaaaaccc"], bp=[(np.array([1, 2, 3]), np.array([10, 9, 8]), np.array([0.9, 0.8, 0.7]))],
                      label=-1))
+    return recs
+
+
+def bpla_records():
+    """Records of the BPLA golden file: C1-like single sequences with profiles from their base-pair lists, alignments
+    with IUPAC codes and gaps and hand-made profiles, a length-1 record and a 70-column record (three 32-column chunks)."""
+    from stem_kernel_b200 import bpla
+    recs = [dict(rows=r["rows"], bp=r["bp"]) for r in synth.make_config(1, 5)]
+    rng = np.random.default_rng(20260018)
+    for rows in (["GGGAAACCC--A", "GCGAANCCCUUA"], ["acgu-ryacgu", "acguaNNacgu", "ac-uacgacgu"], ["a"], ["".join(rng.choice(list("acgu"), 70))],
+                 ["gggg", "cccc"], ["u" * 33], ["acgu" * 8 + "n"]):
+        n = len(rows[0])
+        a, b = rng.uniform(0, 0.6, n), rng.uniform(0, 0.4, n)
+        recs.append(dict(rows=rows, p_left=np.sqrt(a).astype(np.float32), p_right=np.sqrt(b).astype(np.float32),
+                         p_unpair=np.sqrt(np.maximum(0, 1 - a - b)).astype(np.float32)))
     return recs
 
 
@@ -99,3 +117,17 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+    # ---- BPLA / local-alignment kernels (bpla_kernel/bpla_kernel.cpp via oracle/ref_harness_bpla.cpp)
+    from stem_kernel_b200 import bpla  # noqa: E402
+    brecs = bpla_records()
+    bs = bpla.BplaSet(brecs)
+    xi, yi = np.triu_indices(len(bs))
+    g = dict(rows_json=json.dumps([r["rows"] for r in brecs]), col_off=bs.col_off, p_left=bs.p_left, p_right=bs.p_right,
+             p_unpair=bs.p_unpair, xi=xi.astype(np.uint32), yi=yi.astype(np.uint32))
+    for no_bp in (0, 1):
+        for sw in (0, 1):
+            g[f"k_nobp{no_bp}_sw{sw}"] = R.bpla_pairs(bpla.make_params(no_bp=no_bp, sw=sw), bs, bs, xi, yi)
+    g["k_custom"] = R.bpla_pairs(bpla.make_params(gap=-3.0, ext=-0.25, alpha=2.0, beta=0.3, score=np.arange(16.0).reshape(4, 4) / 4 - 1),
+                                 bs, bs, xi, yi)
+    np.savez_compressed(os.path.join(OUT, "golden_bpla.npz"), **g)
