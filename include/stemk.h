@@ -199,6 +199,33 @@ typedef struct stemk_bpla_set {
 int stemk_bpla_pairs(stemk_ctx* ctx, const stemk_bpla_params* params, const stemk_bpla_set* x, const stemk_bpla_set* y,
                      size_t n_pairs, const uint32_t* xi, const uint32_t* yi, double* out);
 
+/* ---- naive stem kernel: stem_kernel/stem_kernel.cpp:282-351 (full_dp) --------------------
+ * StemKernel<double, BPMat>::operator() of the stem_kernel/ program with band 0 and no alignment constraint: the
+ * O(Lx^2 Ly^2) dynamic program over all pairs of base pairs (i,j) x (k,l) on the raw (lower-case) sequences.
+ * bp_mode 0: canonical pairs from the text, NormalBasePair / WobbleBasePair (:353-392; use_gu selects g-u pairs);
+ * bp_mode 1: prob(i,j) read from a dense row-major L x L float table per sequence (the role of the
+ * ViennaRNA-backed BPMatrix class, :394-420).  Parameter defaults: stem_kernel/main.cpp:46-64 (gap 0.8, stack 1,
+ * loop 3, subst 0.5).  The banded / alignment-constrained partial_dp (:113-280) is not provided. */
+typedef struct stemk_nstem_params {
+  int32_t bp_mode;
+  int32_t use_gu;
+  uint32_t loop;
+  float bp_bound;      /* a pair counts when prob > bp_bound */
+  double gap, stack, subst;
+} stemk_nstem_params;
+
+typedef struct stemk_nstem_set {
+  uint32_t n_seqs;
+  const uint32_t* off;     /* [n+1] character offsets into text */
+  const char* text;
+  const uint64_t* bp_off;  /* [n] offset of each sequence's L x L table in bp (bp_mode 1) */
+  const float* bp;
+} stemk_nstem_set;
+
+/* out[k] = k_stem_naive(x[xi[k]], y[yi[k]]) on the context's device (host buffers).  No CPU path. */
+int stemk_nstem_pairs(stemk_ctx* ctx, const stemk_nstem_params* params, const stemk_nstem_set* x, const stemk_nstem_set* y,
+                      size_t n_pairs, const uint32_t* xi, const uint32_t* yi, double* out);
+
 /* Text of kernel-matrix rows in the reference's output format -- KernelMatrix::print (kernel_matrix.cpp:756-770)
  * and Output::kernel_output (framework.cpp:190-204): one line "<label> 0:<cnt> 1:<v> 2:<v> ... \n" per row, every
  * value printed like operator<<(std::ostream&, double) with default flags ("%g").  m: n_rows x n_cols with row

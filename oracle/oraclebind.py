@@ -37,6 +37,7 @@ def lib():
         L.oracle_print.argtypes = [vp, C.c_size_t, C.c_size_t, vp, vp, C.c_long]
         L.oracle_pair_cost.argtypes = [vp, vp, C.c_uint32, vp, C.c_uint32, vp, vp]
         L.oracle_bpla_pairs.argtypes = [vp, vp, vp, C.c_size_t, vp, vp, vp]
+        L.oracle_nstem_pairs.argtypes = [vp, vp, vp, C.c_size_t, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -102,4 +103,14 @@ def bpla_pairs(params, x, y, xi, yi):
     out = np.zeros(len(xi))
     cx, cy = x.c(), y.c()
     lib().oracle_bpla_pairs(_p(params), _p(cx), _p(cy), len(xi), xi.ctypes.data, yi.ctypes.data, out.ctypes.data)
+    return out
+
+
+def nstem_pairs(params, x, y, xi, yi):
+    """Restated naive stem kernel; params / x / y: stem_kernel_b200.nstem.NstemParams / NstemSet."""
+    xi = np.ascontiguousarray(xi, dtype=np.uint32)
+    yi = np.ascontiguousarray(yi, dtype=np.uint32)
+    out = np.zeros(len(xi))
+    cx, cy = x.c(), y.c()
+    lib().oracle_nstem_pairs(_p(params), _p(cx), _p(cy), len(xi), xi.ctypes.data, yi.ctypes.data, out.ctypes.data)
     return out

@@ -297,3 +297,21 @@ def bpla_pairs(params, x, y, xi, yi):
                           out.ctypes.data)
     assert rc == 0
     return out
+
+
+# ---- the reference naive stem kernel (stem_kernel/stem_kernel.cpp behind oracle/ref_harness_nstem.cpp) ----
+def nstem_pairs(params, x, y, xi, yi, band=0, ali_bound=0.0):
+    """params / x / y: stem_kernel_b200.nstem.NstemParams / NstemSet."""
+    Ln = _lib("libstemk_ref_nstem.so")
+    xi = np.ascontiguousarray(xi, dtype=np.uint32)
+    yi = np.ascontiguousarray(yi, dtype=np.uint32)
+    out = np.zeros(len(xi))
+    vp = C.c_void_p
+    Ln.refnstem_pairs.argtypes = [C.c_int, C.c_int, C.c_uint, C.c_double, C.c_double, C.c_double, C.c_uint, C.c_float, C.c_float,
+                                  C.c_int, vp, C.c_char_p, vp, vp, C.c_int, vp, C.c_char_p, vp, vp, C.c_size_t, vp, vp, vp]
+    d = lambda a: a.ctypes.data if a is not None else None
+    rc = Ln.refnstem_pairs(params.bp_mode, params.use_gu, params.loop, params.gap, params.stack, params.subst, band, ali_bound,
+                           params.bp_bound, len(x), d(x.off), x.text, d(x.bp_off), d(x.bp), len(y), d(y.off), y.text,
+                           d(y.bp_off), d(y.bp), len(xi), xi.ctypes.data, yi.ctypes.data, out.ctypes.data)
+    assert rc == 0
+    return out

@@ -465,3 +465,93 @@ void oracle_bpla_pairs(const stemk_bpla_params* p, const stemk_bpla_set* X, cons
                        const uint32_t* xi, const uint32_t* yi, double* out) {
   for (size_t k = 0; k < n_pairs; ++k) out[k] = bpla_pair(p, X, xi[k], Y, yi[k]);
 }
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Naive stem kernel -- restatement of StemKernel::full_dp (stem_kernel/stem_kernel.cpp:282-351) with dp_init /
+ * dp_update (:85-111) and the base-pair classes (:353-420), statement order kept.  The reference frees the
+ * planes of column j-1 after column j (:339-344); here two columns of (Lx+1) planes per table are kept. */
+enum { NK0 = 0, NK1, NK2, NK3, NG0, NG1, NG2, NG3 };
+
+static float nstem_prob(const stemk_nstem_params* p, const char* s, size_t len, const float* tab, size_t i, size_t j) {
+  if (p->bp_mode == 1) return tab[i * len + j];
+  const char a = s[i], b = s[j];
+  int ok = (a == 'a' && b == 'u') || (a == 'u' && b == 'a') || (a == 'g' && b == 'c') || (a == 'c' && b == 'g');
+  if (p->use_gu) ok = ok || (a == 'g' && b == 'u') || (a == 'u' && b == 'g');
+  return (i + 1 + p->loop <= j && ok) ? 1.0f : 0.0f;
+}
+
+static double nstem_pair(const stemk_nstem_params* p, const stemk_nstem_set* X, uint32_t xr, const stemk_nstem_set* Y, uint32_t yr) {
+  const char* x = X->text + X->off[xr];
+  const char* y = Y->text + Y->off[yr];
+  const size_t lx = X->off[xr + 1] - X->off[xr], ly = Y->off[yr + 1] - Y->off[yr];
+  const float* tx = p->bp_mode == 1 ? X->bp + X->bp_off[xr] : NULL;
+  const float* ty = p->bp_mode == 1 ? Y->bp + Y->bp_off[yr] : NULL;
+  const double g = p->gap;
+  const size_t W = ly + 1, plane = W * W, col = (lx + 1) * plane;
+  double* mem = calloc(8 * 2 * col, sizeof(double));
+#define DP(s, i, j, k, l) mem[((size_t)(s) * 2 + ((j) & 1)) * col + (size_t)(i) * plane + (size_t)(k) * W + (l)]
+  for (size_t j = 0; j != lx + 1; ++j) {
+    for (size_t k = 0; k != W; ++k)
+      for (size_t l = 0; l != W; ++l) {
+        DP(NK0, j, j, k, l) = 1.0;
+        DP(NK1, j, j, k, l) = DP(NK2, j, j, k, l) = DP(NK3, j, j, k, l) = 0.0;
+        DP(NG0, j, j, k, l) = DP(NG1, j, j, k, l) = DP(NG2, j, j, k, l) = DP(NG3, j, j, k, l) = 0.0;
+      }
+    for (size_t l = 0; l != ly + 1; ++l) {
+      DP(NG0, j, j, l, l) = 1.0;
+      if (l == 0) continue;
+      for (size_t k = l - 1;; --k) {
+        DP(NG0, j, j, k, l) = DP(NG0, j, j, k + 1, l) * g;
+        if (k == 0) break;
+      }
+    }
+    if (j == 0) continue;
+    for (size_t i = j - 1;; --i) {
+      const float bp_ij = nstem_prob(p, x, lx, tx, i, j - 1);
+      for (int s = 0; s < 8; ++s) memset(&DP(s, i, j, 0, 0), 0, plane * sizeof(double));
+      for (size_t l = 0; l != ly + 1; ++l) {
+        DP(NK0, i, j, l, l) = 1.0;
+        DP(NG0, i, j, l, l) = DP(NG0, i + 1, j, l, l) * g;
+        if (l == 0) continue;
+        for (size_t k = l - 1;; --k) {
+          DP(NK0, i, j, k, l) = DP(NK0, i, j - 1, k, l);
+          DP(NG0, i, j, k, l) = DP(NG0, i, j - 1, k, l) * g;
+          DP(NK1, i, j, k, l) = DP(NK1, i + 1, j, k, l);
+          DP(NG1, i, j, k, l) = DP(NG1, i + 1, j, k, l) * g;
+          DP(NK2, i, j, k, l) = DP(NK2, i, j, k, l - 1);
+          DP(NG2, i, j, k, l) = DP(NG2, i, j, k, l - 1) * g;
+          DP(NK3, i, j, k, l) = DP(NK3, i, j, k + 1, l);
+          DP(NG3, i, j, k, l) = DP(NG3, i, j, k + 1, l) * g;
+          if (bp_ij > p->bp_bound) {
+            const float bp_kl = nstem_prob(p, y, ly, ty, k, l - 1);
+            if (bp_kl > p->bp_bound) {
+              if (x[i] == y[k] && x[j - 1] == y[l - 1]) {
+                DP(NK3, i, j, k, l) += DP(NG0, i + 1, j - 1, k + 1, l - 1) * p->stack * bp_ij * bp_kl;
+                DP(NG3, i, j, k, l) += DP(NG0, i + 1, j - 1, k + 1, l - 1);
+              } else {
+                DP(NK3, i, j, k, l) += DP(NG0, i + 1, j - 1, k + 1, l - 1) * p->stack * p->subst * bp_ij * bp_kl;
+              }
+            }
+          }
+          DP(NK2, i, j, k, l) += DP(NK3, i, j, k, l);
+          DP(NG2, i, j, k, l) += DP(NG3, i, j, k, l);
+          DP(NK1, i, j, k, l) += DP(NK2, i, j, k, l);
+          DP(NG1, i, j, k, l) += DP(NG2, i, j, k, l);
+          DP(NK0, i, j, k, l) += DP(NK1, i, j, k, l);
+          DP(NG0, i, j, k, l) += DP(NG1, i, j, k, l);
+          if (k == 0) break;
+        }
+      }
+      if (i == 0) break;
+    }
+  }
+  const double res = DP(NK0, 0, lx, 0, ly);
+#undef DP
+  free(mem);
+  return res;
+}
+
+void oracle_nstem_pairs(const stemk_nstem_params* p, const stemk_nstem_set* X, const stemk_nstem_set* Y, size_t n_pairs,
+                        const uint32_t* xi, const uint32_t* yi, double* out) {
+  for (size_t k = 0; k < n_pairs; ++k) out[k] = nstem_pair(p, X, xi[k], Y, yi[k]);
+}

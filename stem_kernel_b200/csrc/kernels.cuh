@@ -130,6 +130,10 @@ cudaError_t launch_normalize_square(double* matrix, uint32_t n, cudaStream_t str
 cudaError_t run_bpla(const stemk_bpla_params& p, const stemk_bpla_set& x, const stemk_bpla_set& y, size_t n_pairs,
                      const uint32_t* xi, const uint32_t* yi, double* out, int sm_count, size_t smem_optin,
                      cudaStream_t stream, std::string* err);
+// naive stem kernel (nstem.cu): host buffers in, host buffer out, synchronous on `stream`
+cudaError_t run_nstem(const stemk_nstem_params& p, const stemk_nstem_set& x, const stemk_nstem_set& y, size_t n_pairs,
+                      const uint32_t* xi, const uint32_t* yi, double* out, int sm_count, size_t smem_optin,
+                      cudaStream_t stream, std::string* err);
 cudaError_t launch_fp64_peak(double* sink, int grid, int block, int iters, cudaStream_t stream);
 
 }  // namespace stemk

@@ -739,6 +739,27 @@ int stemk_bpla_pairs(stemk_ctx* ctx, const stemk_bpla_params* params, const stem
   return STEMK_OK;
 }
 
+int stemk_nstem_pairs(stemk_ctx* ctx, const stemk_nstem_params* params, const stemk_nstem_set* x, const stemk_nstem_set* y,
+                      size_t n_pairs, const uint32_t* xi, const uint32_t* yi, double* out) {
+  if (!ctx || !params || !x || !y) return fail(ctx, STEMK_ERR_ARG, "null argument");
+  if (ctx->device == STEMK_DEVICE_NONE) return no_device(ctx);
+  if (n_pairs == 0) return STEMK_OK;
+  if (!xi || !yi || !out) return fail(ctx, STEMK_ERR_ARG, "null buffer");
+  for (const stemk_nstem_set* s : {x, y}) {
+    if (s->n_seqs && (!s->off || !s->text)) return fail(ctx, STEMK_ERR_ARG, "null set array");
+    if (params->bp_mode == 1 && s->n_seqs && (!s->bp_off || !s->bp)) return fail(ctx, STEMK_ERR_ARG, "base-pair probability tables missing");
+  }
+  if (params->bp_mode != 0 && params->bp_mode != 1) return fail(ctx, STEMK_ERR_ARG, "unknown bp_mode");
+  for (size_t k = 0; k < n_pairs; ++k)
+    if (xi[k] >= x->n_seqs || yi[k] >= y->n_seqs) return fail(ctx, STEMK_ERR_ARG, "pair index out of range");
+  CU(cudaSetDevice(ctx->device));
+  std::string err;
+  cudaError_t e = run_nstem(*params, *x, *y, n_pairs, xi, yi, out, ctx->sm_count, ctx->smem_optin, ctx->stream, &err);
+  if (e != cudaSuccess) return err.empty() ? cuda_fail(ctx, e, "naive stem kernel") : fail(ctx, STEMK_ERR_NOMEM, err);
+  ctx->launches += 1;
+  return STEMK_OK;
+}
+
 namespace {
 // operator<<(std::ostream&, double) with default flags == printf("%g"): std::to_chars(general, precision 6) produces
 // the same digits (it is specified as printf's %.6g in the C locale); non-finite values go through snprintf so

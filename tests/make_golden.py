@@ -8,6 +8,8 @@ of its own, so these files pin the oracle and the CUDA path to 
   golden_mdata.npz     the reference constructor's MData (DAG, profiles, weights) for each record
   golden_naive.npz     string_kernel/ (naive) Gram on 8 raw strings, gap parsed as float
   golden_svm.npz       40-record C1 Gram (reference) and the vendored LIBSVM's 5-fold CV targets on it
+  golden_nstem.npz     stem_kernel/ (the naive O(L^4) stem kernel, full_dp): 9 short sequences, canonical pairs with and
+                       without g-u, probability tables, a non-default parameter set; upper-triangle values
   golden_bpla.npz      bpla_kernel/ (BPLA / local-alignment kernels): 12 records (single sequences, alignments,
                        IUPAC, gaps, a length-1 and a 70-column record), their base-pairing profiles, and the
                        reference's upper-triangle values for {BP, noBP} x {sum form, Smith-Waterman}
@@ -53,6 +55,19 @@ def bpla_records():
         recs.append(dict(rows=rows, p_left=np.sqrt(a).astype(np.float32), p_right=np.sqrt(b).astype(np.float32),
                          p_unpair=np.sqrt(np.maximum(0, 1 - a - b)).astype(np.float32)))
     return recs
+
+
+def nstem_inputs():
+    """Sequences (lower case) and probability tables of the naive-stem-kernel golden file."""
+    from stem_kernel_b200 import nstem
+    recs = synth.make_config(1, 3)
+    seqs = [r["rows"][0].lower()[:34] for r in recs] + ["gggaaaccc", "a", "gcgcuuuugcgc", "gggggaaaauuuuuccccc", "acgu" * 9, "au"]
+    rng = np.random.default_rng(20260019)
+    tabs = [nstem.dense_bp(len(r["rows"][0]), r["bp"][0])[:34, :34].copy() for r in recs]
+    for s in seqs[3:]:
+        n = len(s)
+        tabs.append(np.triu(rng.uniform(0, 1, (n, n)) * (rng.uniform(0, 1, (n, n)) < 0.15), 3).astype(np.float32))
+    return seqs, tabs
 
 
 def pack_records(recs):
@@ -131,3 +146,17 @@ if __name__ == "__main__":
     g["k_custom"] = R.bpla_pairs(bpla.make_params(gap=-3.0, ext=-0.25, alpha=2.0, beta=0.3, score=np.arange(16.0).reshape(4, 4) / 4 - 1),
                                  bs, bs, xi, yi)
     np.savez_compressed(os.path.join(OUT, "golden_bpla.npz"), **g)
+
+    # ---- naive stem kernel (stem_kernel/stem_kernel.cpp via oracle/ref_harness_nstem.cpp)
+    from stem_kernel_b200 import nstem  # noqa: E402
+    seqs, tabs = nstem_inputs()
+    sa, sb = nstem.NstemSet(seqs), nstem.NstemSet(seqs, tabs)
+    xi, yi = np.triu_indices(len(seqs))
+    n = dict(seqs_json=json.dumps(seqs), tables=np.concatenate([t.reshape(-1) for t in tabs]), xi=xi.astype(np.uint32),
+             yi=yi.astype(np.uint32))
+    n["k_normal"] = R.nstem_pairs(nstem.make_params(), sa, sa, xi, yi)
+    n["k_wobble"] = R.nstem_pairs(nstem.make_params(use_gu=True), sa, sa, xi, yi)
+    n["k_table"] = R.nstem_pairs(nstem.make_params(bp_mode=1, bp_bound=0.05), sb, sb, xi, yi)
+    n["k_custom"] = R.nstem_pairs(nstem.make_params(loop=1, gap=0.6, stack=1.7, subst=0.3), sa, sa, xi, yi)
+    n["k_default_bound"] = R.nstem_pairs(nstem.make_params(bp_bound=1.0), sa, sa, xi, yi)
+    np.savez_compressed(os.path.join(OUT, "golden_nstem.npz"), **n)

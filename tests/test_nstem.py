@@ -1,0 +1,91 @@
+"""Naive stem kernel (stem_kernel/stem_kernel.cpp:282-351 full_dp, base-pair classes :353-420).
+
+CPU: the plain-C restatement against the golden values of the compiled reference, bit for bit, and against the
+reference itself on fresh inputs where oracle/_ref exists.  GPU: the CUDA kernel through the C ABI
+(stemk_nstem_pairs) against the oracle to 1e-9 relative, on the golden inputs, argument order swapped (the kernel
+stages the shorter sequence), rectangular x / y sets, a 60-nt pair, and the degenerate default bound."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, need_gpu, relerr
+from oracle import oraclebind as O
+from oracle import refbind as R
+from stem_kernel_b200 import nstem, synth
+
+TOL = 1e-9
+
+
+def golden_sets():
+    z = np.load(os.path.join(GOLDEN, "golden_nstem.npz"))
+    seqs = json.loads(str(z["seqs_json"]))
+    tabs, at = [], 0
+    for s in seqs:
+        n = len(s)
+        tabs.append(z["tables"][at:at + n * n].reshape(n, n))
+        at += n * n
+    return nstem.NstemSet(seqs), nstem.NstemSet(seqs, tabs), z
+
+
+CASES = [("k_normal", False, dict()), ("k_wobble", False, dict(use_gu=True)), ("k_table", True, dict(bp_mode=1, bp_bound=0.05)),
+         ("k_custom", False, dict(loop=1, gap=0.6, stack=1.7, subst=0.3)), ("k_default_bound", False, dict(bp_bound=1.0))]
+
+
+def test_restatement_is_bit_identical_to_the_reference_golden():
+    sa, sb, z = golden_sets()
+    for key, tab, kw in CASES:
+        s = sb if tab else sa
+        assert np.array_equal(O.nstem_pairs(nstem.make_params(**kw), s, s, z["xi"], z["yi"]), z[key]), key
+    assert np.all(z["k_default_bound"] == 1.0)          # the program's own default bound: no pair ever counts
+    assert z["k_normal"].min() >= 1.0 and z["k_normal"].max() > 1e3
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(R.REF_DIR, "libstemk_ref_nstem.so")), reason="oracle/_ref not built")
+def test_restatement_matches_the_compiled_reference_on_fresh_inputs():
+    rng = np.random.default_rng(11)
+    seqs = ["".join(rng.choice(list("acgu"), n)) for n in (1, 5, 12, 20, 27)] + ["gggcaaagccc"]
+    s = nstem.NstemSet(seqs)
+    xi, yi = np.divmod(np.arange(len(seqs) ** 2), len(seqs))
+    for kw in (dict(), dict(use_gu=True, loop=0), dict(gap=0.3, stack=2.0, subst=0.9)):
+        p = nstem.make_params(**kw)
+        assert np.array_equal(O.nstem_pairs(p, s, s, xi, yi), R.nstem_pairs(p, s, s, xi, yi))
+
+
+# ------------------------------------------------------------------------------------------------- GPU
+@pytest.mark.gpu
+def test_gpu_golden_swapped_and_rectangular():
+    need_gpu()
+    from stem_kernel_b200 import api, _lib as L
+    ctx = api.Context(L.make_params(L.STR_SIMPLE))
+    sa, sb, z = golden_sets()
+    for key, tab, kw in CASES:
+        s, p = (sb if tab else sa), nstem.make_params(**kw)
+        assert relerr(nstem.pairs(ctx, p, s, s, z["xi"], z["yi"]), z[key]) < TOL, key
+        assert relerr(nstem.pairs(ctx, p, s, s, z["yi"], z["xi"]), O.nstem_pairs(p, s, s, z["yi"], z["xi"])) < TOL, key
+    rng = np.random.default_rng(3)
+    a = nstem.NstemSet(["".join(rng.choice(list("acgu"), n)) for n in (60, 33, 7)])
+    b = nstem.NstemSet(["".join(rng.choice(list("acgu"), n)) for n in (58, 1, 40, 12)])
+    xi, yi = np.divmod(np.arange(12), 4)
+    p = nstem.make_params(use_gu=True)
+    assert relerr(nstem.pairs(ctx, p, a, b, xi, yi), O.nstem_pairs(p, a, b, xi, yi)) < TOL
+    with pytest.raises(api.StemkError, match="out of range"):
+        nstem.pairs(ctx, p, a, b, [3], [0])
+    with pytest.raises(api.StemkError, match="tables missing"):
+        nstem.pairs(ctx, nstem.make_params(bp_mode=1), a, b, [0], [0])
+
+
+@pytest.mark.gpu
+def test_gpu_config1_like_probability_tables():
+    """C1-like records (~75 nt) with their thresholded base-pair probabilities as tables: 8 records, 36 pairs."""
+    need_gpu()
+    from stem_kernel_b200 import api, _lib as L
+    ctx = api.Context(L.make_params(L.STR_SIMPLE))
+    recs = synth.make_config(1, 8, offset=40)
+    seqs = [r["rows"][0].lower() for r in recs]
+    s = nstem.NstemSet(seqs, [nstem.dense_bp(len(q), r["bp"][0], th=0.01) for q, r in zip(seqs, recs)])
+    xi, yi = np.triu_indices(len(s))
+    p = nstem.make_params(bp_mode=1, bp_bound=0.01)
+    got, want = nstem.pairs(ctx, p, s, s, xi, yi), O.nstem_pairs(p, s, s, xi, yi)
+    assert relerr(got, want) < TOL and want.max() > 1.0
