@@ -319,6 +319,37 @@ def run_b200(args, rank, world, local_rank):
                      "kernel_gcups": p2 * 1e4 / (kms * 1e-3) / 1e9,
                      "kernel_alg_tflops": 7.0 * p2 * 1e4 / (kms * 1e-3) / 1e12,
                      "e2e_pairs_per_s": p2 / wall, "e2e_note": "stemk_gram with host buffers (pair lists H2D, 32 MB matrix D2H)"}
+        # the "next" rows of SURVEY 8(f) that are built (BPLA / local-alignment kernel, naive stem kernel): one
+        # host-buffer call each on the C2 / C1 inputs, wall time (H2D and D2H inside)
+        from stem_kernel_b200 import bpla, nstem
+        rng2 = np.random.default_rng(20260002)
+        brecs = []
+        for r in recs2:
+            nb = len(r["rows"][0])
+            a_, b_ = rng2.uniform(0, 0.6, nb), rng2.uniform(0, 0.4, nb)
+            brecs.append(dict(rows=r["rows"], p_left=np.sqrt(a_), p_right=np.sqrt(b_), p_unpair=np.sqrt(np.maximum(0, 1 - a_ - b_))))
+        bset = bpla.BplaSet(brecs)
+        bxi, byi = np.triu_indices(n2)
+        bpar = bpla.make_params()
+        bpla.pairs(ctx2, bpar, bset, bset, bxi[:2000], byi[:2000])
+        t0 = time.perf_counter()
+        bpla.pairs(ctx2, bpar, bset, bset, bxi, byi)
+        bw = time.perf_counter() - t0
+        secondary["bpla"] = {"workload": "BPLAKernel (sum form, base-pairing profiles) on the C2 sequences, synthetic profiles",
+                             "pairs": p2, "e2e_pairs_per_s": p2 / bw, "e2e_gcups": p2 * 1e4 / bw / 1e9}
+        recs1 = synth.make_config(1)
+        seqs1 = [r["rows"][0].lower() for r in recs1]
+        nset = nstem.NstemSet(seqs1, [nstem.dense_bp(len(q), r["bp"][0], th=TH) for q, r in zip(seqs1, recs1)])
+        nxi, nyi = np.triu_indices(len(seqs1))
+        npar = nstem.make_params(bp_mode=1, bp_bound=TH)
+        nstem.pairs(ctx2, npar, nset, nset, nxi[:148], nyi[:148])
+        t0 = time.perf_counter()
+        nstem.pairs(ctx2, npar, nset, nset, nxi, nyi)
+        nw = time.perf_counter() - t0
+        ln1 = np.array([len(q) for q in seqs1], dtype=np.float64)
+        secondary["naive_stem"] = {"workload": "naive stem kernel (full_dp, probability tables, threshold 0.01) on the C1 records",
+                                   "pairs": len(nxi), "e2e_pairs_per_s": len(nxi) / nw,
+                                   "e2e_gcells": float(np.sum(ln1[nxi] ** 2 * ln1[nyi] ** 2) / 4.0) / nw / 1e9}
         ctx2.close()
 
     cpu = None
