@@ -31,6 +31,7 @@ struct BplaDev {            // one record set on the device
   const float* pl;
   const float* pr;
   const float* pu;
+  const uint8_t* code;     // per column: 0..3 one-hot base (count 1), 4 all-zero column, 5 general profile
 };
 
 struct BplaLaunch {
@@ -97,6 +98,7 @@ __global__ void __launch_bounds__(32 * kBplaWarps) bpla_pairs_kernel(const BplaL
     for (uint32_t i = 1; i <= lx; ++i) {
       // the x column of this row (uniform)
       float xc[4], xpl = 0.f, xpr = 0.f, xpu = 0.f;
+      const uint32_t xcode = __ldg(P.X.code + x0 + i - 1u);
 #pragma unroll
       for (int a = 0; a < 4; ++a) xc[a] = __ldg(P.X.profile + 5u * (x0 + i - 1u) + a);
       if (!no_bp) { xpl = __ldg(P.X.pl + x0 + i - 1u); xpr = __ldg(P.X.pr + x0 + i - 1u); xpu = __ldg(P.X.pu + x0 + i - 1u); }
@@ -106,10 +108,18 @@ __global__ void __launch_bounds__(32 * kBplaWarps) bpla_pairs_kernel(const BplaL
         const bool act = j <= ly;
         double m = 0.0, xv = 0.0, x2 = 0.0;
         if (act) {
-          float yc[4];
+          // one-hot columns (count exactly 1): n = 1, v = table entry, v / n = the entry bit for bit; an all-zero
+          // column gives n = 0 and the score 0 (bpla_kernel.cpp:31-44); everything else takes the general loop
+          const uint32_t ycode = __ldg(P.Y.code + y0 + j - 1u);
+          double s;
+          if (xcode < 4u && ycode < 4u) s = s_tab[xcode * 4u + ycode];
+          else if (xcode == 4u || ycode == 4u) s = 0.0;
+          else {
+            float yc[4];
 #pragma unroll
-          for (int a = 0; a < 4; ++a) yc[a] = __ldg(P.Y.profile + 5u * (y0 + j - 1u) + a);
-          double s = la_score(s_tab, xc, yc);
+            for (int a = 0; a < 4; ++a) yc[a] = __ldg(P.Y.profile + 5u * (y0 + j - 1u) + a);
+            s = la_score(s_tab, xc, yc);
+          }
           if (!no_bp) {
             const float ypl = __ldg(P.Y.pl + y0 + j - 1u), ypr = __ldg(P.Y.pr + y0 + j - 1u), ypu = __ldg(P.Y.pu + y0 + j - 1u);
             const float pair = __fadd_rn(__fmul_rn(xpr, ypr), __fmul_rn(xpl, ypl));      // bpla_kernel.cpp:58
@@ -183,12 +193,23 @@ cudaError_t run_bpla(const stemk_bpla_params& p, const stemk_bpla_set& x, const 
   BplaLaunch L;
   cudaError_t e = cudaSuccess;
   uint32_t ly_cap = 1;
+  std::vector<std::vector<uint8_t>> codes;   // host staging of the column codes, alive until the copies are done
+  codes.reserve(2);
   auto up_set = [&](const stemk_bpla_set& s, BplaDev* d, bool is_y) -> cudaError_t {
     const size_t ncol = s.n_seqs ? s.col_off[s.n_seqs] : 0;
     if (is_y) for (uint32_t r = 0; r < s.n_seqs; ++r) ly_cap = std::max(ly_cap, s.col_off[r + 1] - s.col_off[r]);
     cudaError_t q;
     if ((q = up(s.col_off, sizeof(uint32_t) * (s.n_seqs + 1), (const void**)&d->col_off)) != cudaSuccess) return q;
     if ((q = up(s.profile, sizeof(float) * 5 * ncol, (const void**)&d->profile)) != cudaSuccess) return q;
+    codes.emplace_back(ncol);
+    std::vector<uint8_t>& cd = codes.back();
+    for (size_t c = 0; c < ncol; ++c) {
+      const float* pc = s.profile + 5 * c;
+      int ones = 0, zeros = 0, which = 0;
+      for (int a = 0; a < 4; ++a) { if (pc[a] == 1.0f) { ++ones; which = a; } if (pc[a] == 0.0f) ++zeros; }
+      cd[c] = (ones == 1 && zeros == 3) ? (uint8_t)which : (zeros == 4 ? 4 : 5);
+    }
+    if ((q = up(cd.data(), ncol, (const void**)&d->code)) != cudaSuccess) return q;
     if ((q = up(s.p_left, sizeof(float) * ncol, (const void**)&d->pl)) != cudaSuccess) return q;
     if ((q = up(s.p_right, sizeof(float) * ncol, (const void**)&d->pr)) != cudaSuccess) return q;
     return up(s.p_unpair, sizeof(float) * ncol, (const void**)&d->pu);
