@@ -22,7 +22,7 @@ namespace stemk {
 
 namespace {
 
-constexpr int kNstemThreads = 256;
+constexpr int kNstemThreads = 1024;   // 32 warps: a warp streams only ~2-4 B/clk, the G0 planes need many of them
 
 struct NstemDev {
   const uint32_t* off;
@@ -112,6 +112,8 @@ __global__ void __launch_bounds__(kNstemThreads) nstem_pairs_kernel(const NstemL
       for (uint32_t i = j; i-- > 0;) {
         const float bp_ij = (i + 1u < j) ? pair_prob(P, x, lx, tx, i, j - 1u) : 0.0f;
         const bool active = bp_ij > P.bp_bound;
+        // the old plane of i is only needed by the MATCH pass of i-1: keep it when that pass will run
+        const bool keep_old = i > 0u && pair_prob(P, x, lx, tx, i - 1u, j - 1u) > P.bp_bound;
         if (active) {
           // ---- G3 (suffix recurrence along k) and the MATCH increments; thread <-> column l
           const char xa = x[i], xb = x[j - 1u];
@@ -158,7 +160,7 @@ __global__ void __launch_bounds__(kNstemThreads) nstem_pairs_kernel(const NstemL
               const double g1 = G1[at] * g + v;
               G1[at] = g1;
               const double old = g0p[at];
-              Tnew[at] = old;
+              if (keep_old) Tnew[at] = old;
               g0p[at] = old * g + g1;
             }
           }
