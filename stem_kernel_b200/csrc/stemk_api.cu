@@ -558,13 +558,14 @@ int stemk_gram(stemk_ctx* ctx, const stemk_set* train, int normalize, double* ou
                              (const double*)ctx->vals.p, n, normalize, (double*)ctx->matrix.p, ctx->stream);
   if (rc != STEMK_OK) return rc;
   const auto tg2 = now();
-  if (timing) CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
   const auto tg3 = now();
   CU(cudaMemcpyAsync(out, ctx->matrix.p, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  const auto tg4 = now();
   CU(cudaStreamSynchronize(ctx->stream));
   if (timing)
-    std::fprintf(stderr, "stemk_gram: %u records: pair list %.1f ms, enqueue %.1f ms, device %.1f ms, D2H %.1f ms\n", n, ms(tg0, tg1),
-                 ms(tg1, tg2), ms(tg2, tg3), ms(tg3, now()));
+    std::fprintf(stderr, "stemk_gram: %u records: pair list %.1f ms, enqueue %.1f ms, device %.1f ms, D2H call %.1f ms, sync %.1f ms\n", n,
+                 ms(tg0, tg1), ms(tg1, tg2), ms(tg2, tg3), ms(tg3, tg4), ms(tg4, now()));
   return STEMK_OK;
 }
 
