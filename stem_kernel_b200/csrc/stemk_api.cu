@@ -62,6 +62,8 @@ struct stemk_ctx {
   unsigned long long* d_bucket = nullptr;  // count[16] | start[16] | queue heads[16]
   int use_fast = 1;                        // STEMK_FAST=0 in the environment forces the general stem kernel
   int use_rows = 0;                        // STEMK_ROWSK=1: the experimental row-block kernel (stem_rows.cu) instead of the one-row-per-warp fast kernel
+  int use_lanes = 0;                       // STEMK_LANES=1: the lanes-are-rows kernel (stem_lanes.cu); STEMK_LANES_R forces the block height
+  int lanes_r = 0;
   int rows_tw = 4, rows_r = 0, rows_nt = 0; // STEMK_ROWS_TW / _R / _NT: warps per team, forced rows per block, team limit
   std::string err;
   // stats
@@ -178,6 +180,8 @@ int stemk_create(stemk_ctx** out, const stemk_params* params, int device) {
   make_tables(*params, &c->tables);
   if (const char* f = std::getenv("STEMK_FAST")) c->use_fast = std::atoi(f);
   if (const char* f = std::getenv("STEMK_ROWSK")) c->use_rows = std::atoi(f);
+  if (const char* f = std::getenv("STEMK_LANES")) c->use_lanes = std::atoi(f);
+  if (const char* f = std::getenv("STEMK_LANES_R")) c->lanes_r = std::atoi(f);
   if (const char* f = std::getenv("STEMK_ROWS_TW")) c->rows_tw = std::max(1, std::min(8, std::atoi(f)));
   if (const char* f = std::getenv("STEMK_ROWS_R")) c->rows_r = std::atoi(f);
   if (const char* f = std::getenv("STEMK_ROWS_NT")) c->rows_nt = std::atoi(f);
@@ -312,7 +316,8 @@ int stemk_pairs_device(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, s
     // ---- classify: trivial pairs are finished, the others go to the general kernel (bucket 0) or to the fast
     // kernel's size buckets (1..), each bucket keeping the caller's pair order
     static const uint32_t kCaps[kMaxFastBuckets] = {256, 320, 384, 448, 512, 640, 768, kFastMaxN};
-    const bool rows_mode = ctx->use_rows != 0;
+    const bool lanes_mode = ctx->use_lanes != 0;
+    const bool rows_mode = ctx->use_rows != 0 && !lanes_mode;
     const bool any_fast = ctx->use_fast && x->host.n_fast > 0 && y->host.n_fast > 0;
     StemClassify C;
     C.X = x->view; C.Y = y->view; C.xi = d_xi; C.yi = d_yi; C.n_pairs = n_pairs; C.out = stem_out;
@@ -418,8 +423,42 @@ int stemk_pairs_device(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, s
                      h[12] / (double)(h[14] ? h[14] : 1), h[13] / (double)(h[14] ? h[14] : 1), h[14]);
       }
     }
+    // ---- lanes-are-rows kernel, one launch per size bucket: the tallest row block whose tile fits next to the record
+    for (int b = 0; lanes_mode && b < C.n_caps; ++b) {
+      const uint32_t ny_cap = std::min(C.caps[b], std::max(1u, y->host.max_fastN));
+      const uint32_t lo = b ? C.caps[b - 1] : 0u;
+      uint32_t e4_cap = 4;
+      bool any = false;
+      for (const RecDev& r : y->host.rec)
+        if ((r.flags & REC_FAST) && r.N > lo && r.N <= C.caps[b]) { e4_cap = std::max(e4_cap, r.e4); any = true; }
+      if (!any) continue;
+      const size_t budget = std::min<size_t>(ctx->smem_optin, (size_t)227 * 1024) - 512;   // static shared memory
+      uint32_t R = 0;
+      for (uint32_t cand : {32u, 16u, 8u}) {
+        if (ctx->lanes_r && (uint32_t)ctx->lanes_r != cand) continue;
+        if ((size_t)(ny_cap + 1u) * (2u * cand + 1u) > 65535u) continue;   // child lists are 16-bit tile columns
+        if (stem_lanes_smem_bytes(cand, ny_cap, e4_cap, lev_cap) <= budget) { R = cand; break; }
+      }
+      if (!R) return fail(ctx, STEMK_ERR_NOMEM, "lanes stem kernel: record does not fit in shared memory");
+      const size_t smem = stem_lanes_smem_bytes(R, ny_cap, e4_cap, lev_cap);
+      const int grid = (int)std::min<size_t>((n_pairs + kLanesGroup - 1) / kLanesGroup, (size_t)ctx->sm_count);
+      const unsigned long long stride = (unsigned long long)kLanesGroup * nx_cap * ((ny_cap + 1u) & ~1u);
+      CU(ctx->scratch.reserve(sizeof(double) * stride * grid));
+      CU(ctx->rowacc.reserve(sizeof(double) * (size_t)kLanesGroup * nx_cap * grid));
+      StemLanesLaunch F;
+      F.X = x->view; F.Y = y->view; F.xi = d_xi; F.yi = d_yi; F.out = stem_out; F.order = C.order;
+      F.start = C.start; F.count = C.count; F.counter = heads + 1 + b; F.bucket = 1 + b;
+      F.scratch = (double*)ctx->scratch.p; F.scratch_stride = stride; F.rowacc = (double*)ctx->rowacc.p; F.pair_tab = ctx->d_pair_tab;
+      F.len_band = ctx->params.len_band; F.nx_cap = nx_cap; F.ny_cap = ny_cap; F.e4_cap = e4_cap; F.lev_cap = lev_cap;
+      if (std::getenv("STEMK_TIMING")) std::fprintf(stderr, "lanes bucket %d: cap %u R %u smem %zu\n", b, ny_cap, R, smem);
+      stemk_ctx::Timed tm = timed_begin(ctx, 0, st);
+      cudaError_t le = launch_stem_lanes(F, R, grid, smem, st);
+      timed_end(ctx, tm, st);
+      CU(le);
+      ctx->launches += 1;
+    }
     // ---- fast kernel, one launch per size bucket (shared memory and CTAs per SM sized for the bucket)
-    for (int b = 0; !rows_mode && b < C.n_caps; ++b) {
+    for (int b = 0; !rows_mode && !lanes_mode && b < C.n_caps; ++b) {
       const uint32_t ny_cap = std::min(C.caps[b], std::max(1u, y->host.max_fastN));
       const uint32_t e4_cap = std::max(4u, y->host.max_E4);
       const size_t budget = std::min<size_t>(ctx->smem_optin, (size_t)227 * 1024);
