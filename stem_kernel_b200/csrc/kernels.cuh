@@ -98,6 +98,7 @@ struct StemLanesLaunch {
   double* rowacc;                    // per CTA: kLanesGroup x nx_cap per-row result slots
   const double* pair_tab;
   uint32_t len_band, nx_cap, ny_cap, e4_cap, lev_cap;
+  unsigned long long* prof;          // optional (LANES_PROF builds): per-phase cycle counters of thread 0, summed over CTAs
 };
 constexpr int kRowsMaxThreads = 512;  // launch bound of the row-block kernel (128 registers per thread)
 

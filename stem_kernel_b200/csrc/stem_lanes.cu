@@ -104,6 +104,12 @@ __global__ void __launch_bounds__(32 * kLanesWarps, 1) stem_lanes_kernel(const S
   const uint32_t* __restrict__ order = P.order + P.start[P.bucket];
   unsigned long long item = 0, item_end = 0;  // the CTA's current run of queue positions
   const uint32_t tileb = sb + L.tile;
+#ifdef LANES_PROF
+  unsigned long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pt = clock64();   // thread 0: stage, A, B, C, red, blocks, levels swept, group tail
+#define PROF(k) do { const unsigned long long now_ = clock64(); pf[k] += now_ - pt; pt = now_; } while (0)
+#else
+#define PROF(k) do { } while (0)
+#endif
 
   // sweep mapping: lane = slot * R + row
   const uint32_t r_b = lane & (R - 1u), s_b = lane / R;
@@ -166,6 +172,7 @@ __global__ void __launch_bounds__(32 * kLanesWarps, 1) stem_lanes_kernel(const S
       sts_u32(sb + (L.yLmax + 4 * l), mx);
     }
 
+    PROF(0);
     for (uint32_t lvl = 0; lvl < maxlev; ++lvl) {
       __syncthreads();   // previous level's rows are in the slab; s_lo / s_cnt free
       if (tid < g) {
@@ -238,6 +245,11 @@ __global__ void __launch_bounds__(32 * kLanesWarps, 1) stem_lanes_kernel(const S
         }
 
         // ---- phase B: sweep the y DAG level by level; lane <-> row, warp <-> NS nodes of the level
+#ifdef LANES_PROF
+        __syncthreads();
+        PROF(1);
+        pf[5] += 1;
+#endif
         double racc = 0.0;
         uint32_t jbeg = lds_u32(sb + L.yLev);
         for (uint32_t ly = 0; ly < ry.nlev; ++ly) {
@@ -249,6 +261,9 @@ __global__ void __launch_bounds__(32 * kLanesWarps, 1) stem_lanes_kernel(const S
             continue;
           }
           __syncthreads();   // HQ complete (first trip); the rows of the levels below are complete
+#ifdef LANES_PROF
+          pf[6] += 1;
+#endif
           for (uint32_t jj = jbeg + warp * NS; jj < jend; jj += kLW * NS) {
             const uint32_t j = jj + s_b;
             const bool valid = j < jend;
@@ -301,6 +316,7 @@ __global__ void __launch_bounds__(32 * kLanesWarps, 1) stem_lanes_kernel(const S
           jbeg = jend;
         }
         __syncthreads();   // the block's H and HQ are complete
+        PROF(2);
 
         // ---- phase C: finished rows G0s(i,:) = up_x(i) * dn_y * (H + a_x*HQ) -> slab
         for (uint32_t it = warp; it < cnt * nchunk; it += kLW) {
@@ -317,6 +333,7 @@ __global__ void __launch_bounds__(32 * kLanesWarps, 1) stem_lanes_kernel(const S
           }
         }
         __syncthreads();   // tile free
+        PROF(3);
 
         // ---- the rows' path-weighted MATCH sums: partial sums per (warp, node slot), added in a fixed order
         sts_f64(tileb + 8u * (warp * 32u + lane), racc);
@@ -329,6 +346,7 @@ __global__ void __launch_bounds__(32 * kLanesWarps, 1) stem_lanes_kernel(const S
           rowacc0[(size_t)slB * P.nx_cap + iB] = xpaths * t;
         }
         __syncthreads();   // partial sums consumed before the next block's dummy column / phase A overwrite them
+        PROF(4);
       }
     }
 
@@ -342,7 +360,11 @@ __global__ void __launch_bounds__(32 * kLanesWarps, 1) stem_lanes_kernel(const S
       t = warp_sum_l(t);
       if (lane == 0) P.out[ps.k] = t + ps.plr * (double)ry.lr;
     }
+    PROF(7);
   }
+#ifdef LANES_PROF
+  if (tid == 0 && P.prof) for (int k = 0; k < 8; ++k) atomicAdd(P.prof + k, pf[k]);
+#endif
 }
 
 template <int R>

@@ -451,11 +451,27 @@ int stemk_pairs_device(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, s
       F.scratch = (double*)ctx->scratch.p; F.scratch_stride = stride; F.rowacc = (double*)ctx->rowacc.p; F.pair_tab = ctx->d_pair_tab;
       F.len_band = ctx->params.len_band; F.nx_cap = nx_cap; F.ny_cap = ny_cap; F.e4_cap = e4_cap; F.lev_cap = lev_cap;
       if (std::getenv("STEMK_TIMING")) std::fprintf(stderr, "lanes bucket %d: cap %u R %u smem %zu\n", b, ny_cap, R, smem);
+      F.prof = nullptr;
+      static unsigned long long* d_lprof = nullptr;
+      const bool prof = std::getenv("STEMK_PROF") != nullptr;
+      if (prof) {
+        if (!d_lprof) cudaMalloc((void**)&d_lprof, 8 * sizeof(unsigned long long));
+        cudaMemsetAsync(d_lprof, 0, 8 * sizeof(unsigned long long), st);
+        F.prof = d_lprof;
+      }
       stemk_ctx::Timed tm = timed_begin(ctx, 0, st);
       cudaError_t le = launch_stem_lanes(F, R, grid, smem, st);
       timed_end(ctx, tm, st);
       CU(le);
       ctx->launches += 1;
+      if (prof) {   // only meaningful with a -DLANES_PROF build
+        unsigned long long h[8];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, d_lprof, sizeof(h), cudaMemcpyDeviceToHost);
+        const double nb = h[5] ? (double)h[5] : 1.0;
+        std::fprintf(stderr, "lanes prof cap %u R %u: blocks %llu, y levels swept per block %.1f | cycles per block: A %.0f B %.0f C %.0f sums %.0f | "
+                     "staging %.0f tail %.0f (per block)\n", ny_cap, R, h[5], h[6] / nb, h[1] / nb, h[2] / nb, h[3] / nb, h[4] / nb, h[0] / nb, h[7] / nb);
+      }
     }
     // ---- fast kernel, one launch per size bucket (shared memory and CTAs per SM sized for the bucket)
     for (int b = 0; !rows_mode && !lanes_mode && b < C.n_caps; ++b) {
