@@ -199,6 +199,13 @@ typedef struct stemk_bpla_set {
 int stemk_bpla_pairs(stemk_ctx* ctx, const stemk_bpla_params* params, const stemk_bpla_set* x, const stemk_bpla_set* y,
                      size_t n_pairs, const uint32_t* xi, const uint32_t* yi, double* out);
 
+/* BPLAKernel<double, MData>::compute_gradients (bpla_kernel/bpla_kernel.cpp:176-402; bpla_kernel.h:30-34), the call
+ * bpla_optimizer.cpp:77,114,151,187,233,244 makes per pair: value[k] = the kernel value of the optimizer's model
+ * (BPLA_Forward :178-243 -- not the same number as operator()) and grad[4k .. 4k+3] = its partial derivatives with
+ * respect to alpha, beta, gap, ext (params->no_bp and params->sw must be 0; param vector order of :188-191). */
+int stemk_bpla_gradients(stemk_ctx* ctx, const stemk_bpla_params* params, const stemk_bpla_set* x, const stemk_bpla_set* y,
+                         size_t n_pairs, const uint32_t* xi, const uint32_t* yi, double* value, double* grad);
+
 /* ---- naive stem kernel: stem_kernel/stem_kernel.cpp:282-351 (full_dp) --------------------
  * StemKernel<double, BPMat>::operator() of the stem_kernel/ program with band 0 and no alignment constraint: the
  * O(Lx^2 Ly^2) dynamic program over all pairs of base pairs (i,j) x (k,l) on the raw (lower-case) sequences.

@@ -37,6 +37,7 @@ def lib():
         L.oracle_print.argtypes = [vp, C.c_size_t, C.c_size_t, vp, vp, C.c_long]
         L.oracle_pair_cost.argtypes = [vp, vp, C.c_uint32, vp, C.c_uint32, vp, vp]
         L.oracle_bpla_pairs.argtypes = [vp, vp, vp, C.c_size_t, vp, vp, vp]
+        L.oracle_bpla_gradients.argtypes = [vp, vp, vp, C.c_size_t, vp, vp, vp, vp]
         L.oracle_nstem_pairs.argtypes = [vp, vp, vp, C.c_size_t, vp, vp, vp]
         _lib = L
     return _lib
@@ -104,6 +105,17 @@ def bpla_pairs(params, x, y, xi, yi):
     cx, cy = x.c(), y.c()
     lib().oracle_bpla_pairs(_p(params), _p(cx), _p(cy), len(xi), xi.ctypes.data, yi.ctypes.data, out.ctypes.data)
     return out
+
+
+def bpla_gradients(params, x, y, xi, yi):
+    """Restated BPLAKernel::compute_gradients: (values [n], gradients [n, 4] = d/d{alpha, beta, gap, ext})."""
+    xi = np.ascontiguousarray(xi, dtype=np.uint32)
+    yi = np.ascontiguousarray(yi, dtype=np.uint32)
+    val, grad = np.zeros(len(xi)), np.zeros((len(xi), 4))
+    cx, cy = x.c(), y.c()
+    lib().oracle_bpla_gradients(_p(params), _p(cx), _p(cy), len(xi), xi.ctypes.data, yi.ctypes.data, val.ctypes.data,
+                                grad.ctypes.data)
+    return val, grad
 
 
 def nstem_pairs(params, x, y, xi, yi):

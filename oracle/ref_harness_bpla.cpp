@@ -45,3 +45,23 @@ extern "C" int refbpla_pairs(int noBP, int SW, double gap, double ext, double al
   for (size_t p = 0; p < n_pairs; ++p) out[p] = k(X[xi[p]], Y[yi[p]]);
   return 0;
 }
+
+// BPLAKernel::compute_gradients (bpla_kernel.cpp:387-402, static): value[p] and grad[4p..] = d/d{alpha, beta, gap, ext}
+extern "C" int refbpla_gradients(double gap, double ext, double alpha, double beta, const double* table16,
+                                 int nx, const uint32_t* row_off_x, const char* const* rows_x, const uint32_t* col_off_x,
+                                 const float* pl_x, const float* pr_x, const float* pu_x,
+                                 int ny, const uint32_t* row_off_y, const char* const* rows_y, const uint32_t* col_off_y,
+                                 const float* pl_y, const float* pr_y, const float* pu_y,
+                                 size_t n_pairs, const uint32_t* xi, const uint32_t* yi, double* value, double* grad) {
+  boost::multi_array<double, 2> table(boost::extents[4][4]);
+  for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) table[a][b] = table16[a * 4 + b];
+  std::vector<MData> X = build(nx, row_off_x, rows_x, col_off_x, pl_x, pr_x, pu_x);
+  std::vector<MData> Y = build(ny, row_off_y, rows_y, col_off_y, pl_y, pr_y, pu_y);
+  std::vector<double> param(4), d(4);
+  param[0] = alpha; param[1] = beta; param[2] = gap; param[3] = ext;
+  for (size_t p = 0; p < n_pairs; ++p) {
+    value[p] = BPLAKernel<double, MData>::compute_gradients(X[xi[p]], Y[yi[p]], table, param, d);
+    for (int k = 0; k < 4; ++k) grad[4 * p + k] = d[k];
+  }
+  return 0;
+}

@@ -299,6 +299,36 @@ def bpla_pairs(params, x, y, xi, yi):
     return out
 
 
+def bpla_gradients(params, x, y, xi, yi):
+    """BPLAKernel<double,MData>::compute_gradients of the compiled reference: (values [n], gradients [n, 4])."""
+    Lb = _lib("libstemk_ref_bpla.so")
+    xi = np.ascontiguousarray(xi, dtype=np.uint32)
+    yi = np.ascontiguousarray(yi, dtype=np.uint32)
+    val, grad = np.zeros(len(xi)), np.zeros((len(xi), 4))
+
+    def rows_of(s):
+        off = np.zeros(len(s) + 1, dtype=np.uint32)
+        flat = []
+        for k, r in enumerate(s.rows):
+            flat.extend(r)
+            off[k + 1] = len(flat)
+        return off, (C.c_char_p * max(1, len(flat)))(*[t.encode() for t in flat])
+
+    ox, rx = rows_of(x)
+    oy, ry = rows_of(y)
+    table = np.array(list(params.score), dtype=np.float64)
+    vp = C.c_void_p
+    Lb.refbpla_gradients.argtypes = [C.c_double, C.c_double, C.c_double, C.c_double, vp,
+                                     C.c_int, vp, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, C.c_size_t, vp, vp, vp, vp]
+    rc = Lb.refbpla_gradients(params.gap, params.ext, params.alpha, params.beta, table.ctypes.data,
+                              len(x), ox.ctypes.data, rx, x.col_off.ctypes.data, x.p_left.ctypes.data, x.p_right.ctypes.data,
+                              x.p_unpair.ctypes.data, len(y), oy.ctypes.data, ry, y.col_off.ctypes.data, y.p_left.ctypes.data,
+                              y.p_right.ctypes.data, y.p_unpair.ctypes.data, len(xi), xi.ctypes.data, yi.ctypes.data,
+                              val.ctypes.data, grad.ctypes.data)
+    assert rc == 0
+    return val, grad
+
+
 # ---- the reference naive stem kernel (stem_kernel/stem_kernel.cpp behind oracle/ref_harness_nstem.cpp) ----
 def nstem_pairs(params, x, y, xi, yi, band=0, ali_bound=0.0):
     """params / x / y: stem_kernel_b200.nstem.NstemParams / NstemSet."""

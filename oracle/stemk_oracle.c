@@ -466,6 +466,111 @@ void oracle_bpla_pairs(const stemk_bpla_params* p, const stemk_bpla_set* X, cons
   for (size_t k = 0; k < n_pairs; ++k) out[k] = bpla_pair(p, X, xi[k], Y, yi[k]);
 }
 
+/* BPLAKernel::compute_gradients (bpla_kernel.cpp:176-402): the forward tables (BPLA_Forward :178-243), the backward
+ * tables (BPLA_Backward :245-314) and the accumulation of the four partial derivatives d/d{alpha, beta, gap, ext}
+ * (BPLA_ForwardBackword :335-385), statement by statement.  The score is always the base-pairing-profile score
+ * (:210-212); w_pair is a float expression (the profiles are float vectors), w_unpair a double one. */
+enum { GM = 0, GIX, GIY, GLX, GLY, GRX, GRY, GN };
+
+static double bpla_grad_pair(const stemk_bpla_params* p, const stemk_bpla_set* X, uint32_t xr, const stemk_bpla_set* Y, uint32_t yr,
+                             double* d) {
+  const size_t x0 = X->col_off[xr], lx = X->col_off[xr + 1] - x0, y0 = Y->col_off[yr], ly = Y->col_off[yr + 1] - y0;
+  const size_t w = ly + 1, plane = (lx + 1) * w;
+  const double alpha = p->alpha, beta = p->beta, gap = p->gap, ext = p->ext;
+  const double beta_gap = exp(beta * gap), beta_ext = exp(beta * ext);
+  double* F = calloc(2 * GN * plane, sizeof(double));
+  double* B = F + GN * plane;
+#define FT(t, i, j) F[(size_t)(t) * plane + (size_t)(i) * w + (j)]
+#define BT(t, i, j) B[(size_t)(t) * plane + (size_t)(i) * w + (j)]
+  /* forward */
+  FT(GM, 0, 0) = 1; FT(GLX, 0, 0) = 1; FT(GLY, 0, 0) = 1;
+  for (size_t i = 1; i != lx + 1; ++i) FT(GLX, i, 0) += FT(GLX, i - 1, 0);
+  for (size_t j = 1; j != ly + 1; ++j) FT(GLY, 0, j) += FT(GLY, 0, j - 1);
+  for (size_t i = 1; i != lx + 1; ++i)
+    for (size_t j = 1; j != ly + 1; ++j) {
+      const size_t cx = x0 + i - 1, cy = y0 + j - 1;
+      const double s = alpha * (X->p_right[cx] * Y->p_right[cy] + X->p_left[cx] * Y->p_left[cy]) +
+                       X->p_unpair[cx] * Y->p_unpair[cy] * bpla_la_score(p->score, X->profile + 5 * cx, Y->profile + 5 * cy);
+      const double beta_s = exp(beta * s);
+      FT(GM, i, j) += beta_s * FT(GM, i - 1, j - 1);
+      FT(GM, i, j) += beta_s * FT(GIX, i - 1, j - 1);
+      FT(GM, i, j) += beta_s * FT(GIY, i - 1, j - 1);
+      FT(GM, i, j) += beta_s * FT(GLX, i - 1, j - 1);
+      FT(GM, i, j) += beta_s * FT(GLY, i - 1, j - 1);
+      FT(GIX, i, j) += beta_gap * FT(GM, i - 1, j);
+      FT(GIX, i, j) += beta_ext * FT(GIX, i - 1, j);
+      FT(GIY, i, j) += beta_gap * FT(GM, i, j - 1);
+      FT(GIY, i, j) += beta_gap * FT(GIX, i, j - 1);
+      FT(GIY, i, j) += beta_ext * FT(GIY, i, j - 1);
+      FT(GLX, i, j) += FT(GLX, i - 1, 0);
+      FT(GLY, i, j) += FT(GLX, i, j - 1);
+      FT(GLY, i, j) += FT(GLY, i, j - 1);
+      FT(GRX, i, j) += FT(GM, i - 1, j);
+      FT(GRX, i, j) += FT(GRX, i - 1, j);
+      FT(GRY, i, j) += FT(GM, i, j - 1);
+      FT(GRY, i, j) += FT(GRX, i, j - 1);
+      FT(GRY, i, j) += FT(GRY, i, j - 1);
+    }
+  /* backward */
+  BT(GM, lx, ly) = 1; BT(GRX, lx, ly) = 1; BT(GRY, lx, ly) = 1;
+  for (size_t i = lx; i != 0; --i)
+    for (size_t j = ly; j != 0; --j) {
+      const size_t cx = x0 + i - 1, cy = y0 + j - 1;
+      const double s = alpha * (X->p_right[cx] * Y->p_right[cy] + X->p_left[cx] * Y->p_left[cy]) +
+                       X->p_unpair[cx] * Y->p_unpair[cy] * bpla_la_score(p->score, X->profile + 5 * cx, Y->profile + 5 * cy);
+      const double beta_s = exp(beta * s);
+      BT(GM, i - 1, j - 1) += beta_s * BT(GM, i, j);
+      BT(GIX, i - 1, j - 1) += beta_s * BT(GM, i, j);
+      BT(GIY, i - 1, j - 1) += beta_s * BT(GM, i, j);
+      BT(GLX, i - 1, j - 1) += beta_s * BT(GM, i, j);
+      BT(GLY, i - 1, j - 1) += beta_s * BT(GM, i, j);
+      BT(GM, i - 1, j) += beta_gap * BT(GIX, i, j);
+      BT(GIX, i - 1, j) += beta_ext * BT(GIX, i, j);
+      BT(GM, i, j - 1) += beta_gap * BT(GIY, i, j);
+      BT(GIX, i, j - 1) += beta_gap * BT(GIY, i, j);
+      BT(GIY, i, j - 1) += beta_ext * BT(GIY, i, j);
+      BT(GLX, i - 1, 0) += BT(GLX, i, j);
+      BT(GLX, i, j - 1) += BT(GLY, i, j);
+      BT(GLY, i, j - 1) += BT(GLY, i, j);
+      BT(GM, i - 1, j) += BT(GRX, i, j);
+      BT(GRX, i - 1, j) += BT(GRX, i, j);
+      BT(GM, i, j - 1) += BT(GRY, i, j);
+      BT(GRX, i, j - 1) += BT(GRY, i, j);
+      BT(GRY, i, j - 1) += BT(GRY, i, j);
+    }
+  /* (the two border loops of BPLA_Backward :306-312 only feed its return value, which compute_gradients drops) */
+  /* forward x backward */
+  d[0] = d[1] = d[2] = d[3] = 0.0;
+  for (size_t i = 1; i != lx + 1; ++i)
+    for (size_t j = 1; j != ly + 1; ++j) {
+      const size_t cx = x0 + i - 1, cy = y0 + j - 1;
+      const double w_pair = X->p_right[cx] * Y->p_right[cy] + X->p_left[cx] * Y->p_left[cy];
+      const double w_unpair = X->p_unpair[cx] * Y->p_unpair[cy] * bpla_la_score(p->score, X->profile + 5 * cx, Y->profile + 5 * cy);
+      const double beta_s = exp(beta * (alpha * w_pair + w_unpair));
+      for (int t = GM; t <= GLY; ++t) {   /* update_alpha_beta :316-322, tables in the order M, IX, IY, LX, LY */
+        const double v = FT(t, i - 1, j - 1) * beta_s * BT(GM, i, j);
+        d[0] += beta * w_pair * v;
+        d[1] += (alpha * w_pair + w_unpair) * v;
+      }
+      double v;                           /* update_beta_gap_ext :324-331 */
+      v = FT(GM, i - 1, j) * beta_gap * BT(GIX, i, j);  d[1] += gap * v; d[2] += beta * v;
+      v = FT(GIX, i - 1, j) * beta_ext * BT(GIX, i, j); d[1] += ext * v; d[3] += beta * v;
+      v = FT(GM, i, j - 1) * beta_gap * BT(GIY, i, j);  d[1] += gap * v; d[2] += beta * v;
+      v = FT(GIX, i, j - 1) * beta_gap * BT(GIY, i, j); d[1] += gap * v; d[2] += beta * v;
+      v = FT(GIY, i, j - 1) * beta_ext * BT(GIY, i, j); d[1] += ext * v; d[3] += beta * v;
+    }
+  const double res = 1 + FT(GM, lx, ly) + FT(GRX, lx, ly) + FT(GRY, lx, ly);
+#undef FT
+#undef BT
+  free(F);
+  return res;
+}
+
+void oracle_bpla_gradients(const stemk_bpla_params* p, const stemk_bpla_set* X, const stemk_bpla_set* Y, size_t n_pairs,
+                           const uint32_t* xi, const uint32_t* yi, double* value, double* grad) {
+  for (size_t k = 0; k < n_pairs; ++k) value[k] = bpla_grad_pair(p, X, xi[k], Y, yi[k], grad + 4 * k);
+}
+
 /* ------------------------------------------------------------------------------------------------------------
  * Naive stem kernel -- restatement of StemKernel::full_dp (stem_kernel/stem_kernel.cpp:282-351) with dp_init /
  * dp_update (:85-111) and the base-pair classes (:353-420), statement order kept.  The reference frees the

@@ -20,6 +20,9 @@ void oracle_pair_cost(const stemk_params* p, const stemk_seqset_desc* X, uint32_
 /* BPLA / local-alignment kernel, bpla_kernel/bpla_kernel.cpp:16-175 */
 void oracle_bpla_pairs(const stemk_bpla_params* p, const stemk_bpla_set* X, const stemk_bpla_set* Y, size_t n_pairs,
                        const uint32_t* xi, const uint32_t* yi, double* out);
+/* BPLAKernel::compute_gradients, bpla_kernel/bpla_kernel.cpp:176-402: value[k] and grad[4k..4k+3] = d/d{alpha, beta, gap, ext} */
+void oracle_bpla_gradients(const stemk_bpla_params* p, const stemk_bpla_set* X, const stemk_bpla_set* Y, size_t n_pairs,
+                           const uint32_t* xi, const uint32_t* yi, double* value, double* grad);
 /* naive stem kernel, stem_kernel/stem_kernel.cpp:282-351 (full_dp) with the base-pair classes of :353-420 */
 void oracle_nstem_pairs(const stemk_nstem_params* p, const stemk_nstem_set* X, const stemk_nstem_set* Y, size_t n_pairs,
                         const uint32_t* xi, const uint32_t* yi, double* out);

@@ -105,6 +105,18 @@ def pairs(ctx, params, x, y, xi, yi):
     return out
 
 
+def gradients(ctx, params, x, y, xi, yi):
+    """BPLAKernel::compute_gradients(x[xi[k]], y[yi[k]], score_table, [alpha, beta, gap, ext], d) on the context's
+    device: (values [n], gradients [n, 4] = d/d{alpha, beta, gap, ext}); bpla_kernel.cpp:387-402."""
+    xi = np.ascontiguousarray(xi, dtype=np.uint32)
+    yi = np.ascontiguousarray(yi, dtype=np.uint32)
+    val, grad = np.zeros(len(xi)), np.zeros((len(xi), 4))
+    cx, cy = x.c(), y.c()
+    ctx._check(L.lib().stemk_bpla_gradients(ctx.h, C.byref(params), C.byref(cx), C.byref(cy), len(xi), xi.ctypes.data,
+                                            yi.ctypes.data, val.ctypes.data, grad.ctypes.data))
+    return val, grad
+
+
 def gram(ctx, params, s, normalize=False):
     """KernelMatrix::calculate(train, kernel, normalize) for the BPLA kernel (upper triangle evaluated, mirrored)."""
     n = len(s)

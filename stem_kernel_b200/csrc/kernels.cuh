@@ -156,8 +156,8 @@ cudaError_t launch_scatter_square(const double* vals, const uint32_t* xi, const 
 cudaError_t launch_normalize_square(double* matrix, uint32_t n, cudaStream_t stream);
 // BPLA / local-alignment kernels (bpla.cu): host buffers in, host buffer out, synchronous on `stream`
 cudaError_t run_bpla(const stemk_bpla_params& p, const stemk_bpla_set& x, const stemk_bpla_set& y, size_t n_pairs,
-                     const uint32_t* xi, const uint32_t* yi, double* out, int sm_count, size_t smem_optin,
-                     cudaStream_t stream, std::string* err);
+                     const uint32_t* xi, const uint32_t* yi, double* out, double* grad, int sm_count, size_t smem_optin,
+                     cudaStream_t stream, std::string* err);   // grad != NULL: BPLAKernel::compute_gradients, 4 doubles per pair
 // naive stem kernel (nstem.cu): host buffers in, host buffer out, synchronous on `stream`
 cudaError_t run_nstem(const stemk_nstem_params& p, const stemk_nstem_set& x, const stemk_nstem_set& y, size_t n_pairs,
                       const uint32_t* xi, const uint32_t* yi, double* out, int sm_count, size_t smem_optin,

@@ -789,8 +789,31 @@ int stemk_bpla_pairs(stemk_ctx* ctx, const stemk_bpla_params* params, const stem
     if (xi[k] >= x->n_seqs || yi[k] >= y->n_seqs) return fail(ctx, STEMK_ERR_ARG, "pair index out of range");
   CU(cudaSetDevice(ctx->device));
   std::string err;
-  cudaError_t e = run_bpla(*params, *x, *y, n_pairs, xi, yi, out, ctx->sm_count, ctx->smem_optin, ctx->stream, &err);
+  cudaError_t e = run_bpla(*params, *x, *y, n_pairs, xi, yi, out, nullptr, ctx->sm_count, ctx->smem_optin, ctx->stream, &err);
   if (e != cudaSuccess) return err.empty() ? cuda_fail(ctx, e, "BPLA kernel") : fail(ctx, STEMK_ERR_NOMEM, err);
+  ctx->launches += 1;
+  return STEMK_OK;
+}
+
+int stemk_bpla_gradients(stemk_ctx* ctx, const stemk_bpla_params* params, const stemk_bpla_set* x, const stemk_bpla_set* y,
+                         size_t n_pairs, const uint32_t* xi, const uint32_t* yi, double* value, double* grad) {
+  if (!ctx || !params || !x || !y) return fail(ctx, STEMK_ERR_ARG, "null argument");
+  if (ctx->device == STEMK_DEVICE_NONE) return no_device(ctx);
+  if (params->no_bp || params->sw)
+    return fail(ctx, STEMK_ERR_ARG, "compute_gradients is defined for the base-pairing-profile sum kernel only (no_bp = sw = 0)");
+  if (n_pairs == 0) return STEMK_OK;
+  if (!xi || !yi || !value || !grad) return fail(ctx, STEMK_ERR_ARG, "null buffer");
+  for (const stemk_bpla_set* s : {x, y}) {
+    if (s->n_seqs && (!s->col_off || !s->profile)) return fail(ctx, STEMK_ERR_ARG, "null set array");
+    if (s->n_seqs && (!s->p_left || !s->p_right || !s->p_unpair))
+      return fail(ctx, STEMK_ERR_ARG, "base-pairing profiles missing (p_left / p_right / p_unpair)");
+  }
+  for (size_t k = 0; k < n_pairs; ++k)
+    if (xi[k] >= x->n_seqs || yi[k] >= y->n_seqs) return fail(ctx, STEMK_ERR_ARG, "pair index out of range");
+  CU(cudaSetDevice(ctx->device));
+  std::string err;
+  cudaError_t e = run_bpla(*params, *x, *y, n_pairs, xi, yi, value, grad, ctx->sm_count, ctx->smem_optin, ctx->stream, &err);
+  if (e != cudaSuccess) return err.empty() ? cuda_fail(ctx, e, "BPLA gradient kernel") : fail(ctx, STEMK_ERR_NOMEM, err);
   ctx->launches += 1;
   return STEMK_OK;
 }

@@ -12,7 +12,8 @@ of its own, so these files pin the oracle and the CUDA path to 
                        without g-u, probability tables, a non-default parameter set; upper-triangle values
   golden_bpla.npz      bpla_kernel/ (BPLA / local-alignment kernels): 12 records (single sequences, alignments,
                        IUPAC, gaps, a length-1 and a 70-column record), their base-pairing profiles, and the
-                       reference's upper-triangle values for {BP, noBP} x {sum form, Smith-Waterman}
+                       reference's upper-triangle values for {BP, noBP} x {sum form, Smith-Waterman}, and
+                       compute_gradients (value + four derivatives per pair) for two parameter sets
 """
 import json
 import os
@@ -145,6 +146,10 @@ if __name__ == "__main__":
             g[f"k_nobp{no_bp}_sw{sw}"] = R.bpla_pairs(bpla.make_params(no_bp=no_bp, sw=sw), bs, bs, xi, yi)
     g["k_custom"] = R.bpla_pairs(bpla.make_params(gap=-3.0, ext=-0.25, alpha=2.0, beta=0.3, score=np.arange(16.0).reshape(4, 4) / 4 - 1),
                                  bs, bs, xi, yi)
+    # BPLAKernel::compute_gradients (bpla_kernel.cpp:387-402): values and d/d{alpha, beta, gap, ext}, default and custom parameters
+    g["grad_value"], g["grad"] = R.bpla_gradients(bpla.make_params(), bs, bs, xi, yi)
+    g["grad_value_custom"], g["grad_custom"] = R.bpla_gradients(
+        bpla.make_params(gap=-3.0, ext=-0.25, alpha=2.0, beta=0.3, score=np.arange(16.0).reshape(4, 4) / 4 - 1), bs, bs, xi, yi)
     np.savez_compressed(os.path.join(OUT, "golden_bpla.npz"), **g)
 
     # ---- naive stem kernel (stem_kernel/stem_kernel.cpp via oracle/ref_harness_nstem.cpp)

@@ -55,6 +55,43 @@ def test_restatement_matches_the_compiled_reference_on_fresh_inputs():
         assert np.array_equal(O.bpla_pairs(p, s, s, xi, yi), R.bpla_pairs(p, s, s, xi, yi))
 
 
+def test_gradient_restatement_is_bit_identical_to_the_reference_golden():
+    """BPLAKernel::compute_gradients (bpla_kernel.cpp:176-402): value and d/d{alpha, beta, gap, ext} per pair."""
+    s, z = golden_set()
+    v, g = O.bpla_gradients(bpla.make_params(), s, s, z["xi"], z["yi"])
+    assert np.array_equal(v, z["grad_value"]) and np.array_equal(g, z["grad"])
+    v, g = O.bpla_gradients(bpla.make_params(**CUSTOM), s, s, z["xi"], z["yi"])
+    assert np.array_equal(v, z["grad_value_custom"]) and np.array_equal(g, z["grad_custom"])
+
+
+def test_gradients_are_the_derivatives_of_the_value():
+    """Independent check of the oracle: central differences of compute_gradients' own value in each parameter."""
+    s, z = golden_set()
+    xi, yi = z["xi"][:20], z["yi"][:20]
+    base = dict(gap=-8.0, ext=-0.75, alpha=4.5, beta=0.11)
+    _, g = O.bpla_gradients(bpla.make_params(**base), s, s, xi, yi)
+    for k, name in enumerate(("alpha", "beta", "gap", "ext")):
+        h = 2.0 ** -12
+        lo, hi = dict(base), dict(base)
+        lo[name] -= h; hi[name] += h
+        pl, ph = bpla.make_params(**lo), bpla.make_params(**hi)     # make_params rounds to float like the reference's CLI
+        vl, _ = O.bpla_gradients(pl, s, s, xi, yi)
+        vh, _ = O.bpla_gradients(ph, s, s, xi, yi)
+        fd = (vh - vl) / (getattr(ph, name) - getattr(pl, name))
+        assert np.allclose(fd, g[:, k], rtol=1e-3, atol=1e-6 * np.abs(g).max()), name
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(R.REF_DIR, "libstemk_ref_bpla.so")), reason="oracle/_ref not built")
+def test_gradient_restatement_matches_the_compiled_reference_on_fresh_inputs():
+    recs = [dict(rows=r["rows"], bp=r["bp"]) for r in synth.make_config(1, 6, offset=4100)]
+    s = bpla.BplaSet(recs)
+    xi, yi = np.triu_indices(len(s))
+    p = bpla.make_params(gap=-5.0, ext=-0.5, alpha=3.0, beta=0.2)
+    v, g = O.bpla_gradients(p, s, s, xi, yi)
+    rv, rg = R.bpla_gradients(p, s, s, xi, yi)
+    assert np.array_equal(v, rv) and np.array_equal(g, rg)
+
+
 def test_pairing_profiles_follow_the_reference_front_end():
     """data.cpp:19-46: p_left / p_right are square roots of the summed pairing probabilities, p_unpair of the rest."""
     bp = (np.array([1, 1, 3]), np.array([8, 9, 7]), np.array([0.5, 0.25, 0.81]))
@@ -111,3 +148,40 @@ def test_gpu_gram_on_config1_and_rectangular_config3():
     for no_bp, sw in VARIANTS:
         q = bpla.make_params(no_bp=no_bp, sw=sw)
         assert relerr(bpla.pairs(ctx, q, a, b, xi, yi), O.bpla_pairs(q, a, b, xi, yi)) < TOL
+
+
+@pytest.mark.gpu
+def test_gpu_gradients_golden_edge_cases_and_long_records():
+    """stemk_bpla_gradients against the reference's golden values and the oracle: every value and every derivative
+    within 1e-9 relative (the derivative with respect to beta mixes signs, so its error is measured against the sum
+    of the other three magnitudes as well -- observed ~1e-14)."""
+    need_gpu()
+    from stem_kernel_b200 import api, _lib as L
+    ctx = api.Context(L.make_params(L.STR_SIMPLE))
+    s, z = golden_set()
+
+    def check(got, want):
+        (v, g), (wv, wg) = got, want
+        assert relerr(v, wv) < TOL
+        scale = np.maximum(np.abs(wg), 1e-3 * np.abs(wg).max(axis=1, keepdims=True))
+        assert np.max(np.abs(g - wg) / scale) < TOL
+
+    check(bpla.gradients(ctx, bpla.make_params(), s, s, z["xi"], z["yi"]), (z["grad_value"], z["grad"]))
+    check(bpla.gradients(ctx, bpla.make_params(**CUSTOM), s, s, z["xi"], z["yi"]), (z["grad_value_custom"], z["grad_custom"]))
+    rng = np.random.default_rng(6)
+    recs = []
+    for n in (1, 2, 31, 32, 33, 64, 65, 97):
+        a, b = rng.uniform(0, 0.6, n), rng.uniform(0, 0.4, n)
+        recs.append(dict(rows=["".join(rng.choice(list("acgu"), n))], p_left=np.sqrt(a), p_right=np.sqrt(b),
+                         p_unpair=np.sqrt(np.maximum(0, 1 - a - b))))
+    e = bpla.BplaSet(recs)
+    xi, yi = np.divmod(np.arange(len(e) ** 2), len(e))
+    p = bpla.make_params()
+    check(bpla.gradients(ctx, p, e, e, xi, yi), O.bpla_gradients(p, e, e, xi, yi))
+    # 150-300 nt records, x and y sets differ
+    a = bpla.BplaSet([dict(rows=r["rows"], bp=r["bp"]) for r in synth.make_config(3, 4, offset=50)])
+    b = bpla.BplaSet([dict(rows=r["rows"], bp=r["bp"]) for r in synth.make_config(3, 3, offset=90)])
+    xi, yi = np.divmod(np.arange(12), 3)
+    check(bpla.gradients(ctx, p, a, b, xi, yi), O.bpla_gradients(p, a, b, xi, yi))
+    with pytest.raises(api.StemkError, match="no_bp = sw = 0"):
+        bpla.gradients(ctx, bpla.make_params(sw=True), e, e, [0], [0])
