@@ -117,6 +117,21 @@ def gradients(ctx, params, x, y, xi, yi):
     return val, grad
 
 
+def gradient_matrices(ctx, params, s):
+    """The kernel matrix and the four gradient matrices bpla_optimizer builds from compute_gradients over all pairs
+    i <= j, mirrored (CalcMatrix, bpla_optimizer.cpp:55-123): (kmat [n, n], gmat [4, n, n])."""
+    n = len(s)
+    iu = np.triu_indices(n)
+    v, g = gradients(ctx, params, s, s, iu[0], iu[1])
+    kmat, gmat = np.zeros((n, n)), np.zeros((4, n, n))
+    kmat[iu] = v
+    kmat[(iu[1], iu[0])] = v
+    for l in range(4):
+        gmat[l][iu] = g[:, l]
+        gmat[l][(iu[1], iu[0])] = g[:, l]
+    return kmat, gmat
+
+
 def gram(ctx, params, s, normalize=False):
     """KernelMatrix::calculate(train, kernel, normalize) for the BPLA kernel (upper triangle evaluated, mirrored)."""
     n = len(s)

@@ -183,5 +183,10 @@ def test_gpu_gradients_golden_edge_cases_and_long_records():
     b = bpla.BplaSet([dict(rows=r["rows"], bp=r["bp"]) for r in synth.make_config(3, 3, offset=90)])
     xi, yi = np.divmod(np.arange(12), 3)
     check(bpla.gradients(ctx, p, a, b, xi, yi), O.bpla_gradients(p, a, b, xi, yi))
+    # the optimizer's matrices (bpla_optimizer.cpp:55-123): symmetric, diagonal = the pair (i, i)
+    km, gm = bpla.gradient_matrices(ctx, p, e)
+    wv, wg = O.bpla_gradients(p, e, e, np.arange(len(e)), np.arange(len(e)))
+    assert np.array_equal(km, km.T) and np.array_equal(gm, gm.transpose(0, 2, 1)) and relerr(np.diag(km), wv) < TOL
+    assert relerr(gm[0].diagonal(), wg[:, 0]) < TOL
     with pytest.raises(api.StemkError, match="no_bp = sw = 0"):
         bpla.gradients(ctx, bpla.make_params(sw=True), e, e, [0], [0])
