@@ -31,6 +31,7 @@ namespace {
 
 constexpr uint32_t kLG = kLanesGroup;
 constexpr uint32_t kLW = kLanesWarps;
+constexpr uint32_t kLCh = 24;   // inner pairs of a row whose slab offsets are staged in shared memory (more: read from the record)
 
 struct LanesLayout {
   uint32_t tab, yD0, yD1, yD2, yD3, yI, yC, yLev, yLmax, tile, total;
@@ -89,6 +90,10 @@ __global__ void __launch_bounds__(32 * kLanesWarps, 1) stem_lanes_kernel(const S
   __shared__ uint32_t s_g, s_maxlev;
   __shared__ LSlot s_slot[kLG];
   __shared__ uint32_t s_lo[kLG], s_cnt[kLG];    // rows of the current x level, per pair of the group
+  // the rows of the block in flight: pair of the group, row, inner pairs (first kLCh staged as slab row offsets)
+  __shared__ uint32_t s_rsl[32], s_ri[32], s_re0[32], s_rne[32];
+  __shared__ double s_rs2[32], s_ra[32], s_rup[32];
+  __shared__ __align__(16) uint32_t s_rch[32 * kLCh];
   const LanesLayout L = lanes_layout(R, P.ny_cap, P.e4_cap, P.lev_cap);
   const uint32_t sb = (uint32_t)__cvta_generic_to_shared(sm);
 
@@ -113,7 +118,12 @@ __global__ void __launch_bounds__(32 * kLanesWarps, 1) stem_lanes_kernel(const S
 
   // sweep mapping: lane = slot * R + row
   const uint32_t r_b = lane & (R - 1u), s_b = lane / R;
-  const uint32_t hb = tileb + 8u * r_b;        // H(j, r_b) at hb + JS*j, HQ at + HQO
+  // Base addresses of the sweep as opaque registers: left to itself the compiler rebuilds the whole shared-memory
+  // carve-up (constant-bank loads, S2R SR_CgaCtaId, a dozen integer instructions) inside the per-node loop.
+  auto pin = [](uint32_t v) { uint32_t o; asm volatile("mov.u32 %0, %1;" : "=r"(o) : "r"(v)); return o; };
+  const uint32_t hb = pin(tileb + 8u * r_b);   // H(j, r_b) at hb + JS*j, HQ at + HQO
+  const uint32_t aI = pin(sb + L.yI), aD0 = pin(sb + L.yD0), aD1 = pin(sb + L.yD1), aD2 = pin(sb + L.yD2);
+  const uint32_t aC = pin(sb + L.yC), aTab = pin(sb + L.tab), aLev = pin(sb + L.yLev), aLmax = pin(sb + L.yLmax);
 
   for (;;) {
     __syncthreads();  // previous group fully retired (also orders the tab fill on the first trip)
@@ -195,6 +205,22 @@ __global__ void __launch_bounds__(32 * kLanesWarps, 1) stem_lanes_kernel(const S
         const uint32_t cnt = min((uint32_t)R, total - b0);
         // the dummy column (the partial sums of the previous block aliased the tile)
         if (tid < 2u * R) sts_f64(tileb + JS * Ny + 8u * tid, 0.0);
+        // the block's rows: one thread per row fetches the row record, then one thread per (row, inner pair) its slab offset
+        if (tid < cnt) {
+          uint32_t sl, i;
+          locate(b0 + tid, &sl, &i);
+          const XNode* __restrict__ xn = X.xnode + s_slot[sl].node0 + i;
+          const double2 x0 = __ldg(reinterpret_cast<const double2*>(xn));        // {s2, a}
+          const double2 x1 = __ldg(reinterpret_cast<const double2*>(xn) + 1);    // {up, ql}
+          const uint4 x3 = __ldg(reinterpret_cast<const uint4*>(xn) + 3);        // {e0, e1, len, bcode}
+          s_rsl[tid] = sl; s_ri[tid] = i; s_re0[tid] = x3.x; s_rne[tid] = x3.y - x3.x;
+          s_rs2[tid] = x0.x; s_ra[tid] = x0.y; s_rup[tid] = x1.x;
+        }
+        __syncthreads();
+        for (uint32_t t = tid; t < cnt * kLCh; t += blockDim.x) {
+          const uint32_t r = t / kLCh, c = t % kLCh;
+          if (c < s_rne[r]) s_rch[t] = __ldg(X.cidx + s_re0[r] + c) * NYS;
+        }
 
         // ---- this lane's row of the block (sweep mapping)
         const bool live = r_b < cnt;
@@ -211,31 +237,39 @@ __global__ void __launch_bounds__(32 * kLanesWarps, 1) stem_lanes_kernel(const S
         const uint32_t blk_lo = __reduce_min_sync(0xffffffffu, len_lo);
 
         // ---- phase A: HQ(r,:) = up_y * s2_x(i) * sum over inner pairs c of G0s(c,:)
+        __syncthreads();   // s_rch complete
         const uint32_t nchunk = (Ny + 127u) >> 7;
         for (uint32_t it = warp; it < cnt * nchunk; it += kLW) {
           const uint32_t r = it % cnt, ch = it / cnt;
-          uint32_t sl, i;
-          locate(b0 + r, &sl, &i);
-          const XNode* __restrict__ xn = X.xnode + s_slot[sl].node0 + i;
-          const uint4 xi4 = __ldg(reinterpret_cast<const uint4*>(xn) + 3);
-          const uint32_t e0 = xi4.x, e1 = xi4.y;
-          const double xs2 = __ldg(&xn->s2);
-          const double* __restrict__ G0 = slab + sl * slot_stride;
+          const uint32_t ne_all = s_rne[r], nst = min(ne_all, kLCh);
+          const double xs2 = s_rs2[r];
           const uint32_t j = (ch << 7) + lane;
+          const double* __restrict__ G0 = slab + s_rsl[r] * slot_stride + j;
           const bool v0 = j < Ny, v1 = j + 32u < Ny, v2 = j + 64u < Ny, v3 = j + 96u < Ny;
           double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
-          for (uint32_t eb = e0; eb < e1; eb += 32u) {
-            const uint32_t ne = min(32u, e1 - eb);
-            uint32_t off_l = 0u;
-            if (lane < ne) off_l = __ldg(X.cidx + eb + lane) * NYS;
-#pragma unroll 4
-            for (uint32_t tt = 0; tt < ne; ++tt) {
-              const double* __restrict__ src = G0 + __shfl_sync(0xffffffffu, off_l, tt) + j;
-              if (v0) q0 += __ldcg(src);
-              if (v1) q1 += __ldcg(src + 32);
-              if (v2) q2 += __ldcg(src + 64);
-              if (v3) q3 += __ldcg(src + 96);
-            }
+          for (uint32_t c = 0; c < nst; c += 4u) {
+            // four inner pairs at a time: sixteen loads in flight per lane before the first add
+            const uint4 o4 = *reinterpret_cast<const uint4*>(&s_rch[r * kLCh + c]);
+            const bool k1 = c + 1u < nst, k2 = c + 2u < nst, k3 = c + 3u < nst;
+            const double* __restrict__ p0 = G0 + o4.x;
+            const double* __restrict__ p1 = G0 + o4.y;
+            const double* __restrict__ p2 = G0 + o4.z;
+            const double* __restrict__ p3 = G0 + o4.w;
+            const double a00 = v0 ? __ldcg(p0) : 0.0, a01 = v1 ? __ldcg(p0 + 32) : 0.0, a02 = v2 ? __ldcg(p0 + 64) : 0.0, a03 = v3 ? __ldcg(p0 + 96) : 0.0;
+            const double a10 = (k1 && v0) ? __ldcg(p1) : 0.0, a11 = (k1 && v1) ? __ldcg(p1 + 32) : 0.0, a12 = (k1 && v2) ? __ldcg(p1 + 64) : 0.0, a13 = (k1 && v3) ? __ldcg(p1 + 96) : 0.0;
+            const double a20 = (k2 && v0) ? __ldcg(p2) : 0.0, a21 = (k2 && v1) ? __ldcg(p2 + 32) : 0.0, a22 = (k2 && v2) ? __ldcg(p2 + 64) : 0.0, a23 = (k2 && v3) ? __ldcg(p2 + 96) : 0.0;
+            const double a30 = (k3 && v0) ? __ldcg(p3) : 0.0, a31 = (k3 && v1) ? __ldcg(p3 + 32) : 0.0, a32 = (k3 && v2) ? __ldcg(p3 + 64) : 0.0, a33 = (k3 && v3) ? __ldcg(p3 + 96) : 0.0;
+            q0 += a00; q1 += a01; q2 += a02; q3 += a03;
+            q0 += a10; q1 += a11; q2 += a12; q3 += a13;
+            q0 += a20; q1 += a21; q2 += a22; q3 += a23;
+            q0 += a30; q1 += a31; q2 += a32; q3 += a33;
+          }
+          for (uint32_t c = kLCh; c < ne_all; ++c) {   // rows with more inner pairs than are staged
+            const double* __restrict__ src = G0 + __ldg(X.cidx + s_re0[r] + c) * NYS;
+            if (v0) q0 += __ldcg(src);
+            if (v1) q1 += __ldcg(src + 32);
+            if (v2) q2 += __ldcg(src + 64);
+            if (v3) q3 += __ldcg(src + 96);
           }
           const uint32_t dst = tileb + HQO + 8u * r + JS * j;
           if (v0) sts_f64(dst, lds_v2f64(sb + (L.yD1 + 16u * j)).y * (xs2 * q0));
@@ -251,10 +285,10 @@ __global__ void __launch_bounds__(32 * kLanesWarps, 1) stem_lanes_kernel(const S
         pf[5] += 1;
 #endif
         double racc = 0.0;
-        uint32_t jbeg = lds_u32(sb + L.yLev);
+        uint32_t jbeg = lds_u32(aLev);
         for (uint32_t ly = 0; ly < ry.nlev; ++ly) {
-          const uint32_t jend = lds_u32(sb + (L.yLev + 4u * ly + 4u));
-          if (lds_u32(sb + (L.yLmax + 4u * ly)) < blk_lo) {
+          const uint32_t jend = lds_u32(aLev + 4u * ly + 4u);
+          if (lds_u32(aLmax + 4u * ly) < blk_lo) {
             // every row of the block is below its window on every node of this level: G1 == 0
             for (uint32_t t = jbeg * R + tid; t < jend * R; t += blockDim.x) sts_f64(tileb + JS * (t / R) + 8u * (t % R), 0.0);
             jbeg = jend;
@@ -268,7 +302,7 @@ __global__ void __launch_bounds__(32 * kLanesWarps, 1) stem_lanes_kernel(const S
             const uint32_t j = jj + s_b;
             const bool valid = j < jend;
             const uint32_t jc = valid ? j : jend - 1u;
-            const uint2 niw = lds_v2u32(sb + (L.yI + 8u * jc));
+            const uint2 niw = lds_v2u32(aI + 8u * jc);
             const uint32_t yl = niw.y >> 16;
             const bool skip = !valid || yl < len_lo;
             const bool inb = !skip && yl <= len_hi;
@@ -277,39 +311,45 @@ __global__ void __launch_bounds__(32 * kLanesWarps, 1) stem_lanes_kernel(const S
               continue;
             }
             const bool any_inb = __any_sync(0xffffffffu, inb);
-            uint32_t e = sb + L.yC + 2u * (niw.x >> 8);
+            uint32_t e = aC + 2u * (niw.x >> 8);
             const uint32_t eend = e + 8u * (niw.y & 0xffffu);
+            uint2 c4 = lds_v2u32(e);                                 // first four children (the word after a list is readable)
+            const double2 d1 = lds_v2f64(aD1 + 16u * jc);   // {up*a*s2, up}
             double S0 = 0.0, S1 = 0.0, m = 0.0;
             if (any_inb) {
+              // the node constants of a MATCH cell are requested before the gathers, not after them
+              const double2 d0 = lds_v2f64(aD0 + 16u * jc);  // {s2_y, el_y}
+              const double2 d2 = lds_v2f64(aD2 + 16u * jc);  // {paths_y, bfreq_y}
+              const double tv = lds_f64(aTab + 8u * (xbc * 16u + (niw.x & 0xffu)));
               double R0 = 0.0, R1 = 0.0;
 #pragma unroll 1
-              for (; e < eend; e += 8u) {
-                const uint2 c4 = lds_v2u32(e);
+              while (e < eend) {
+                e += 8u;
+                const uint2 nx = lds_v2u32(e);                       // next four, in flight during this round's gathers
                 const uint32_t a0 = hb + ((c4.x & 0xffffu) << 3), a1 = hb + ((c4.x >> 16) << 3);
                 const uint32_t a2 = hb + ((c4.y & 0xffffu) << 3), a3 = hb + ((c4.y >> 16) << 3);
-                S0 += lds_f64(a0); R0 += lds_f64(a0 + HQO);
-                S1 += lds_f64(a1); R1 += lds_f64(a1 + HQO);
-                S0 += lds_f64(a2); R0 += lds_f64(a2 + HQO);
-                S1 += lds_f64(a3); R1 += lds_f64(a3 + HQO);
+                const double h0 = lds_f64(a0), g0 = lds_f64(a0 + HQO), h1 = lds_f64(a1), g1 = lds_f64(a1 + HQO);
+                const double h2 = lds_f64(a2), g2 = lds_f64(a2 + HQO), h3 = lds_f64(a3), g3 = lds_f64(a3 + HQO);
+                S0 += h0; R0 += g0; S1 += h1; R1 += g1;
+                S0 += h2; R0 += g2; S1 += h3; R1 += g3;
+                c4 = nx;
               }
               if (inb) {
-                const double2 d0 = lds_v2f64(sb + (L.yD0 + 16u * jc));  // {s2_y, el_y}
-                const double2 d2 = lds_v2f64(sb + (L.yD2 + 16u * jc));  // {paths_y, bfreq_y}
-                const double vs = lds_f64(sb + (L.tab + 8u * (xbc * 16u + (niw.x & 0xffu)))) * xbf * d2.y;
+                const double vs = tv * xbf * d2.y;
                 m = vs * fma(d0.y, xql, d0.x * (R0 + R1));
                 racc = fma(d2.x, m, racc);
               }
             } else {
 #pragma unroll 1
-              for (; e < eend; e += 8u) {
-                const uint2 c4 = lds_v2u32(e);
-                S0 += lds_f64(hb + ((c4.x & 0xffffu) << 3));
-                S1 += lds_f64(hb + ((c4.x >> 16) << 3));
-                S0 += lds_f64(hb + ((c4.y & 0xffffu) << 3));
-                S1 += lds_f64(hb + ((c4.y >> 16) << 3));
+              while (e < eend) {
+                e += 8u;
+                const uint2 nx = lds_v2u32(e);
+                const double h0 = lds_f64(hb + ((c4.x & 0xffffu) << 3)), h1 = lds_f64(hb + ((c4.x >> 16) << 3));
+                const double h2 = lds_f64(hb + ((c4.y & 0xffffu) << 3)), h3 = lds_f64(hb + ((c4.y >> 16) << 3));
+                S0 += h0; S1 += h1; S0 += h2; S1 += h3;
+                c4 = nx;
               }
             }
-            const double2 d1 = lds_v2f64(sb + (L.yD1 + 16u * jc));  // {up*a*s2, up}
             const double h = skip ? 0.0 : fma(d1.x, S0 + S1, d1.y * m);   // up_y * (M + a_y*s2_y*sum)
             if (valid) sts_f64(hb + JS * jc, h);
           }
@@ -321,11 +361,8 @@ __global__ void __launch_bounds__(32 * kLanesWarps, 1) stem_lanes_kernel(const S
         // ---- phase C: finished rows G0s(i,:) = up_x(i) * dn_y * (H + a_x*HQ) -> slab
         for (uint32_t it = warp; it < cnt * nchunk; it += kLW) {
           const uint32_t r = it % cnt, ch = it / cnt;
-          uint32_t sl, i;
-          locate(b0 + r, &sl, &i);
-          const XNode* __restrict__ xc = X.xnode + s_slot[sl].node0 + i;
-          const double xa2 = __ldg(&xc->a), xup = __ldg(&xc->up);
-          double* __restrict__ g0row = slab + sl * slot_stride + (size_t)i * NYS;
+          const double xa2 = s_ra[r], xup = s_rup[r];
+          double* __restrict__ g0row = slab + s_rsl[r] * slot_stride + (size_t)s_ri[r] * NYS;
           const uint32_t jhi = min(Ny, (ch << 7) + 128u);
           for (uint32_t j = (ch << 7) + lane; j < jhi; j += 32u) {
             const uint32_t a = tileb + 8u * r + JS * j;

@@ -432,7 +432,7 @@ int stemk_pairs_device(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, s
       for (const RecDev& r : y->host.rec)
         if ((r.flags & REC_FAST) && r.N > lo && r.N <= C.caps[b]) { e4_cap = std::max(e4_cap, r.e4); any = true; }
       if (!any) continue;
-      const size_t budget = std::min<size_t>(ctx->smem_optin, (size_t)227 * 1024) - 512;   // static shared memory
+      const size_t budget = std::min<size_t>(ctx->smem_optin, (size_t)227 * 1024) - 5120;   // static shared memory (block row records, staged inner-pair offsets)
       uint32_t R = 0;
       for (uint32_t cand : {32u, 16u, 8u}) {
         if (ctx->lanes_r && (uint32_t)ctx->lanes_r != cand) continue;
