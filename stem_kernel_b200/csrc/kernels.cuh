@@ -79,7 +79,7 @@ struct StemRowsLaunch {
 #define STEMK_LANES_GROUP 8
 #endif
 #ifndef STEMK_LANES_WARPS
-#define STEMK_LANES_WARPS 24
+#define STEMK_LANES_WARPS 20
 #endif
 constexpr uint32_t kLanesGroup = STEMK_LANES_GROUP;  // pairs sharing one staged y record that a CTA runs level by level
 constexpr int kLanesWarps = STEMK_LANES_WARPS;

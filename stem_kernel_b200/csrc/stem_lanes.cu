@@ -19,8 +19,8 @@
 // synchronous:
 //   A  warp <-> (row, 128 columns), lanes <-> columns: sums of the finished pre-scaled G0 rows of the inner pairs
 //      (coalesced L2 reads of the per-pair slab), written transposed into the tile (odd column stride: no conflicts)
-//   B  y level by y level with a CTA barrier; levels in which every row of the block is below its band window
-//      (G1 == 0, length-monotone DAGs) are zero-filled without a barrier
+//   B  y level by y level on the first kLB warps with a named barrier; levels in which every row of the block is
+//      below its band window (G1 == 0, length-monotone DAGs) are zero-filled without a barrier
 //   C  warp <-> (row, 128 columns): the finished rows are scaled and written to the slab
 // A row's path-weighted MATCH sum is reduced over the warps in a fixed order, so results are reproducible run to run.
 #include "kernels.cuh"
@@ -31,6 +31,10 @@ namespace {
 
 constexpr uint32_t kLG = kLanesGroup;
 constexpr uint32_t kLW = kLanesWarps;
+#ifndef STEMK_LANES_BWARPS
+#define STEMK_LANES_BWARPS 10
+#endif
+constexpr uint32_t kLB = STEMK_LANES_BWARPS < STEMK_LANES_WARPS ? STEMK_LANES_BWARPS : STEMK_LANES_WARPS;   // warps that run the y sweep (a level has 10-40 nodes; a barrier over fewer warps is cheaper)
 constexpr uint32_t kLCh = 24;   // inner pairs of a row whose slab offsets are staged in shared memory (more: read from the record)
 
 struct LanesLayout {
@@ -285,20 +289,22 @@ __global__ void __launch_bounds__(32 * kLanesWarps, 1) stem_lanes_kernel(const S
         pf[5] += 1;
 #endif
         double racc = 0.0;
+        __syncthreads();   // HQ complete
+        if (warp < kLB) {   // the sweep runs on the first kLB warps, with its own named barrier
         uint32_t jbeg = lds_u32(aLev);
         for (uint32_t ly = 0; ly < ry.nlev; ++ly) {
           const uint32_t jend = lds_u32(aLev + 4u * ly + 4u);
           if (lds_u32(aLmax + 4u * ly) < blk_lo) {
             // every row of the block is below its window on every node of this level: G1 == 0
-            for (uint32_t t = jbeg * R + tid; t < jend * R; t += blockDim.x) sts_f64(tileb + JS * (t / R) + 8u * (t % R), 0.0);
+            for (uint32_t t = jbeg * R + tid; t < jend * R; t += 32u * kLB) sts_f64(tileb + JS * (t / R) + 8u * (t % R), 0.0);
             jbeg = jend;
             continue;
           }
-          __syncthreads();   // HQ complete (first trip); the rows of the levels below are complete
+          asm volatile("bar.sync 1, %0;" ::"n"(32 * kLB) : "memory");   // the rows of the levels below are complete
 #ifdef LANES_PROF
           pf[6] += 1;
 #endif
-          for (uint32_t jj = jbeg + warp * NS; jj < jend; jj += kLW * NS) {
+          for (uint32_t jj = jbeg + warp * NS; jj < jend; jj += kLB * NS) {
             const uint32_t j = jj + s_b;
             const bool valid = j < jend;
             const uint32_t jc = valid ? j : jend - 1u;
@@ -354,6 +360,7 @@ __global__ void __launch_bounds__(32 * kLanesWarps, 1) stem_lanes_kernel(const S
             if (valid) sts_f64(hb + JS * jc, h);
           }
           jbeg = jend;
+        }
         }
         __syncthreads();   // the block's H and HQ are complete
         PROF(2);
