@@ -9,7 +9,7 @@
 //     k(x,y) = sum_i paths_x(i) * sum_j paths_y(j) * M(i,j)  (+ plr_x * lr_y)
 //
 // Mapping.  The y record is the same for every row of every pair of a group, so the sweep over the y DAG is made
-// WARP-UNIFORM: a BLOCK of R rows (R = 32, 16 or 8, chosen per size bucket so that the tile fits) is held in shared
+// WARP-UNIFORM: a BLOCK of R rows (R = 32, 28, ... 8, the tallest whose tile fits, chosen per size bucket) is held in shared
 // memory as a tile [column j][H(0..R-1) | HQ(0..R-1) | pad]; in the sweep a lane owns a ROW of the block and a warp
 // owns 32/R NODES of the current y level: the child list of the node is read once per warp (a broadcast), the
 // gathers H[child][lane] are contiguous, there is no per-lane control flow, and one warp instruction serves 32
@@ -86,7 +86,8 @@ struct LSlot {           // one pair of the group in flight
 
 template <int R>
 __global__ void __launch_bounds__(32 * kLanesWarps, 1) stem_lanes_kernel(const StemLanesLaunch P) {
-  constexpr uint32_t NS = 32u / R;              // nodes of a y level a warp sweeps side by side
+  constexpr uint32_t NS = 32u / R;              // nodes of a y level a warp sweeps side by side (lanes >= NS*R idle: R need not divide 32)
+  constexpr uint32_t LB = NS == 1u ? kLW : kLB; // warps of the sweep: one node per warp needs them all, two or more per warp half of them
   constexpr uint32_t JS = (2u * R + 1u) * 8u;   // bytes per tile column: H[R], HQ[R], one pad double
   constexpr uint32_t HQO = 8u * R;              // HQ part of a column
   extern __shared__ __align__(16) unsigned char sm[];
@@ -121,7 +122,8 @@ __global__ void __launch_bounds__(32 * kLanesWarps, 1) stem_lanes_kernel(const S
 #endif
 
   // sweep mapping: lane = slot * R + row
-  const uint32_t r_b = lane & (R - 1u), s_b = lane / R;
+  const uint32_t r_b = lane % R, s_b = lane / R;
+  const bool lane_ok = lane < NS * R;
   // Base addresses of the sweep as opaque registers: left to itself the compiler rebuilds the whole shared-memory
   // carve-up (constant-bank loads, S2R SR_CgaCtaId, a dozen integer instructions) inside the per-node loop.
   auto pin = [](uint32_t v) { uint32_t o; asm volatile("mov.u32 %0, %1;" : "=r"(o) : "r"(v)); return o; };
@@ -227,7 +229,7 @@ __global__ void __launch_bounds__(32 * kLanesWarps, 1) stem_lanes_kernel(const S
         }
 
         // ---- this lane's row of the block (sweep mapping)
-        const bool live = r_b < cnt;
+        const bool live = lane_ok && r_b < cnt;
         uint32_t slB = 0, iB = 0;
         if (live) locate(b0 + r_b, &slB, &iB);
         const XNode* __restrict__ xr = X.xnode + s_slot[slB].node0 + iB;
@@ -290,23 +292,23 @@ __global__ void __launch_bounds__(32 * kLanesWarps, 1) stem_lanes_kernel(const S
 #endif
         double racc = 0.0;
         __syncthreads();   // HQ complete
-        if (warp < kLB) {   // the sweep runs on the first kLB warps, with its own named barrier
+        if (warp < LB) {   // the sweep runs on the first LB warps, with its own named barrier
         uint32_t jbeg = lds_u32(aLev);
         for (uint32_t ly = 0; ly < ry.nlev; ++ly) {
           const uint32_t jend = lds_u32(aLev + 4u * ly + 4u);
           if (lds_u32(aLmax + 4u * ly) < blk_lo) {
             // every row of the block is below its window on every node of this level: G1 == 0
-            for (uint32_t t = jbeg * R + tid; t < jend * R; t += 32u * kLB) sts_f64(tileb + JS * (t / R) + 8u * (t % R), 0.0);
+            for (uint32_t t = jbeg * R + tid; t < jend * R; t += 32u * LB) sts_f64(tileb + JS * (t / R) + 8u * (t % R), 0.0);
             jbeg = jend;
             continue;
           }
-          asm volatile("bar.sync 1, %0;" ::"n"(32 * kLB) : "memory");   // the rows of the levels below are complete
+          asm volatile("bar.sync 1, %0;" ::"n"(32 * LB) : "memory");   // the rows of the levels below are complete
 #ifdef LANES_PROF
           pf[6] += 1;
 #endif
-          for (uint32_t jj = jbeg + warp * NS; jj < jend; jj += kLB * NS) {
+          for (uint32_t jj = jbeg + warp * NS; jj < jend; jj += LB * NS) {
             const uint32_t j = jj + s_b;
-            const bool valid = j < jend;
+            const bool valid = lane_ok && j < jend;
             const uint32_t jc = valid ? j : jend - 1u;
             const uint2 niw = lds_v2u32(aI + 8u * jc);
             const uint32_t yl = niw.y >> 16;
@@ -427,7 +429,11 @@ size_t stem_lanes_smem_bytes(uint32_t rows, uint32_t ny_cap, uint32_t e4_cap, ui
 
 cudaError_t launch_stem_lanes(const StemLanesLaunch& p, uint32_t rows, int grid, size_t smem, cudaStream_t stream) {
   if (rows == 32) return launch_r<32>(p, grid, smem, stream);
+  if (rows == 28) return launch_r<28>(p, grid, smem, stream);
+  if (rows == 24) return launch_r<24>(p, grid, smem, stream);
+  if (rows == 20) return launch_r<20>(p, grid, smem, stream);
   if (rows == 16) return launch_r<16>(p, grid, smem, stream);
+  if (rows == 12) return launch_r<12>(p, grid, smem, stream);
   if (rows == 8) return launch_r<8>(p, grid, smem, stream);
   return cudaErrorInvalidValue;
 }
