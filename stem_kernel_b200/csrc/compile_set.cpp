@@ -16,6 +16,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <functional>
 #include <thread>
 
 #include "ribosum85_60.inc"
@@ -295,59 +296,88 @@ std::string compile_set(const stemk_seqset_desc& s, double g, int n_threads, Com
     c.prof.reserve(4 * nc); c.c16.reserve(n16); c.blk.reserve(nblk); c.cost_pd.reserve(ncost); c.cost_pb.reserve(ncost);
     c.cost_off.reserve(n + 1); c.n_nodes_all.reserve(n); c.n_edges_all.reserve(n); c.max_level_rows.reserve(n);
   }
-  for (uint32_t r = 0; r < n; ++r) {
-    RecOut& o = recs[r];
-    if (!o.err.empty()) return "record " + std::to_string(r) + ": " + o.err;
-    RecDev h = o.hdr;
-    h.node0 = (uint32_t)c.a.size();
-    h.coff0 = (uint32_t)c.coff.size();
-    h.lev0 = (uint32_t)c.lev_off.size();
-    h.boff0 = (uint32_t)c.boff.size();
-    h.col0 = (uint32_t)c.ccode.size();
-    h.c16_0 = (uint32_t)c.c16.size(); h.e4 = (uint32_t)o.c16.size();
-    h.blk0 = (uint32_t)c.blk.size(); h.nblk = (uint32_t)o.blk.size();
-    append(c.up, o.up); append(c.dn, o.dn); append(c.s2, o.s2); append(c.nodei, o.nodei);
-    append(c.c16, o.c16); append(c.blk, o.blk);
-    if (h.flags & REC_FAST) {
-      c.max_E4 = std::max(c.max_E4, h.e4); c.max_fastN = std::max(c.max_fastN, h.N); ++c.n_fast;
+  // ---- merge.  Pass 1 (serial, sizes only): record headers, the offsets that become absolute, set statistics.
+  std::vector<uint32_t> e0s(n), b0s(n);
+  {
+    size_t nn = 0, ncoff = 0, nlev = 0, nboff = 0, ncol = 0, n16 = 0, nblk = 0, ne = 0, nb = 0, ncost = 0;
+    for (uint32_t r = 0; r < n; ++r) {
+      RecOut& o = recs[r];
+      if (!o.err.empty()) return "record " + std::to_string(r) + ": " + o.err;
+      RecDev h = o.hdr;
+      h.node0 = (uint32_t)nn; h.coff0 = (uint32_t)ncoff; h.lev0 = (uint32_t)nlev; h.boff0 = (uint32_t)nboff; h.col0 = (uint32_t)ncol;
+      h.c16_0 = (uint32_t)n16; h.e4 = (uint32_t)o.c16.size();
+      h.blk0 = (uint32_t)nblk; h.nblk = (uint32_t)o.blk.size();
+      if (h.flags & REC_FAST) {
+        c.max_E4 = std::max(c.max_E4, h.e4); c.max_fastN = std::max(c.max_fastN, h.N); ++c.n_fast;
+      }
+      e0s[r] = (uint32_t)ne; b0s[r] = (uint32_t)nb;
+      if (o.pd.empty()) { o.pd.assign(1, 0.0); o.pb.assign(1, 0.0); }
+      c.cost_off.push_back(ncost);
+      c.rec[r] = h;
+      c.n_nodes_all.push_back(o.n_all);
+      c.n_edges_all.push_back(o.e_all);
+      c.max_level_rows.push_back(o.max_rows);
+      if (o.n_all) c.has_dag = true;
+      if (h.flags & REC_HAS_WEIGHT) ++c.n_weighted;
+      if (h.flags & REC_SIMPLE_COLS) ++c.n_simple_cols;
+      c.max_N = std::max(c.max_N, h.N);
+      c.max_L = std::max(c.max_L, h.L);
+      c.max_E = std::max(c.max_E, (uint32_t)o.cidx.size());
+      c.max_nlev = std::max(c.max_nlev, h.nlev);
+      nn += o.a.size(); ncoff += o.coff.size(); nlev += o.lev_off.size(); nboff += o.boff.size(); ncol += o.ccode.size();
+      n16 += o.c16.size(); nblk += o.blk.size(); ne += o.cidx.size(); nb += o.bab.size(); ncost += o.pd.size();
     }
-    // child / profile offsets become absolute so the kernels index cidx/ce/bab/bfq directly
-    const uint32_t e0 = (uint32_t)c.cidx.size(), b0 = (uint32_t)c.bab.size();
-    for (auto& v : o.coff) v += e0;
-    for (auto& v : o.boff) v += b0;
-    append(c.a, o.a); append(c.el, o.el); append(c.ql, o.ql); append(c.paths, o.paths); append(c.gapt, o.gapt);
-    append(c.bfreq, o.bfreq); append(c.len, o.len); append(c.bcode, o.bcode); append(c.coff, o.coff);
-    append(c.cidx, o.cidx); append(c.ce, o.ce); append(c.lev_off, o.lev_off); append(c.boff, o.boff);
-    append(c.bab, o.bab); append(c.bfq, o.bfq); append(c.ccode, o.ccode); append(c.cw, o.cw);
-    append(c.prof, o.prof); append(c.text, o.text); append(c.deg_all, o.deg_all);
-    if (o.pd.empty()) { o.pd.assign(1, 0.0); o.pb.assign(1, 0.0); }
-    c.cost_off.push_back(c.cost_pd.size());
-    append(c.cost_pd, o.pd); append(c.cost_pb, o.pb);
-    c.rec[r] = h;
-    c.n_nodes_all.push_back(o.n_all);
-    c.n_edges_all.push_back(o.e_all);
-    c.max_level_rows.push_back(o.max_rows);
-    if (o.n_all) c.has_dag = true;
-    if (h.flags & REC_HAS_WEIGHT) ++c.n_weighted;
-    if (h.flags & REC_SIMPLE_COLS) ++c.n_simple_cols;
-    c.max_N = std::max(c.max_N, h.N);
-    c.max_L = std::max(c.max_L, h.L);
-    c.max_E = std::max(c.max_E, (uint32_t)o.cidx.size());
-    c.max_nlev = std::max(c.max_nlev, h.nlev);
+    c.cost_off.push_back(ncost);
   }
-  c.cost_off.push_back(c.cost_pd.size());
-  // packed row records (absolute child ranges, so built after the merge)
+  // Pass 2: the arrays themselves, one group of arrays per thread (every group walks the records in order).
+  {
+    std::vector<std::function<void()>> groups;
+    groups.push_back([&]() { for (RecOut& o : recs) { append(c.a, o.a); append(c.el, o.el); append(c.ql, o.ql); append(c.paths, o.paths); append(c.gapt, o.gapt); } });
+    groups.push_back([&]() { for (RecOut& o : recs) { append(c.bfreq, o.bfreq); append(c.up, o.up); append(c.dn, o.dn); append(c.s2, o.s2); append(c.nodei, o.nodei); } });
+    groups.push_back([&]() {
+      for (uint32_t r = 0; r < n; ++r) {   // child / profile offsets become absolute so the kernels index cidx/ce/bab/bfq directly
+        RecOut& o = recs[r];
+        for (auto& v : o.coff) v += e0s[r];
+        for (auto& v : o.boff) v += b0s[r];
+        append(c.coff, o.coff); append(c.boff, o.boff); append(c.len, o.len); append(c.bcode, o.bcode); append(c.deg_all, o.deg_all);
+        append(c.lev_off, o.lev_off);
+      }
+    });
+    groups.push_back([&]() { for (RecOut& o : recs) { append(c.cidx, o.cidx); append(c.ce, o.ce); append(c.c16, o.c16); append(c.blk, o.blk); } });
+    groups.push_back([&]() { for (RecOut& o : recs) { append(c.bab, o.bab); append(c.bfq, o.bfq); append(c.ccode, o.ccode); append(c.cw, o.cw); append(c.text, o.text); } });
+    groups.push_back([&]() { for (RecOut& o : recs) { append(c.prof, o.prof); append(c.cost_pd, o.pd); append(c.cost_pb, o.pb); } });
+    if (n_threads <= 1) {
+      for (auto& g : groups) g();
+    } else {
+      std::vector<std::thread> th;
+      for (auto& g : groups) th.emplace_back(g);
+      for (auto& x : th) x.join();
+    }
+  }
+  // packed row records (absolute child ranges, so built after the merge); records are independent
   c.xnode.resize(c.a.size());
   c.yband.resize(c.a.size());
-  for (uint32_t r = 0; r < n; ++r) {
-    const RecDev& h = c.rec[r];
-    for (uint32_t k = 0; k < h.N; ++k) {
-      const uint32_t gk = h.node0 + k;
-      XNode& xn = c.xnode[gk];
-      xn.s2 = c.s2[gk]; xn.a = c.a[gk]; xn.up = c.up[gk]; xn.ql = c.ql[gk]; xn.bfreq = c.bfreq[gk]; xn.paths = c.paths[gk];
-      NodeB& nb = c.yband[gk];
-      nb.s2 = c.s2[gk]; nb.el = c.el[gk]; nb.paths = c.paths[gk]; nb.bfreq = c.bfreq[gk];
-      xn.e0 = c.coff[h.coff0 + k]; xn.e1 = c.coff[h.coff0 + k + 1]; xn.len = c.len[gk]; xn.bcode = c.bcode[gk];
+  {
+    auto pack = [&](uint32_t r_lo, uint32_t r_hi) {
+      for (uint32_t r = r_lo; r < r_hi; ++r) {
+        const RecDev& h = c.rec[r];
+        for (uint32_t k = 0; k < h.N; ++k) {
+          const uint32_t gk = h.node0 + k;
+          XNode& xn = c.xnode[gk];
+          xn.s2 = c.s2[gk]; xn.a = c.a[gk]; xn.up = c.up[gk]; xn.ql = c.ql[gk]; xn.bfreq = c.bfreq[gk]; xn.paths = c.paths[gk];
+          NodeB& nb = c.yband[gk];
+          nb.s2 = c.s2[gk]; nb.el = c.el[gk]; nb.paths = c.paths[gk]; nb.bfreq = c.bfreq[gk];
+          xn.e0 = c.coff[h.coff0 + k]; xn.e1 = c.coff[h.coff0 + k + 1]; xn.len = c.len[gk]; xn.bcode = c.bcode[gk];
+        }
+      }
+    };
+    if (n_threads <= 1) {
+      pack(0, n);
+    } else {
+      std::vector<std::thread> th;
+      for (int t = 0; t < n_threads; ++t)
+        th.emplace_back(pack, (uint32_t)((uint64_t)n * t / n_threads), (uint32_t)((uint64_t)n * (t + 1) / n_threads));
+      for (auto& x : th) x.join();
     }
   }
   if (timing) {
