@@ -394,7 +394,13 @@ def run_b200(args, rank, world, local_rank):
                      "traffic": 4.44e6 * len(mine),
                      "traffic_note": "per step, summed over the step's bucket launches like `achieved`; the per-pair DP "
                                      "table (G0 slab, ~1.2 MB) lives in L2/HBM by design, see DESIGN.md 5.1",
-                     "kernel": "stem_pairs_kernel", "kernel_ms_per_launch": kern_ms,
+                     "kernel": "stem_fast_kernel", "kernel_ms_per_launch": kern_ms,
+                     # what the kernel actually saturates (ncu capture, not live): the recursion is a gather-accumulate
+                     # through shared memory, so the instruction issue slots and the shared-memory pipe fill up long
+                     # before the FP64 pipe does
+                     "practical_bounds": {"issue_slots_busy": 0.647, "shared_memory_wavefronts_of_peak": 0.501,
+                                          "fp64_pipe_active": 0.168, "dram_throughput_of_peak": 0.182,
+                                          "source": "profiles/r01_stem_final_ncu_summary.txt (ncu --set full, 256 C3 records)"},
                      "kernel_share_of_step": kern_ms / (total_ms / args.steps),
                      "peak_source": "FP64 FMA probe run live on this GPU (stemk_fp64_peak); MEASURED_PEAKS.json has no "
                                     "fp64 entry",
