@@ -555,6 +555,9 @@ int stemk_pairs(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, size_t n
   int rc = stemk_pairs_device(ctx, x, y, n_pairs, (const uint32_t*)ctx->idx_x.p, (const uint32_t*)ctx->idx_y.p,
                               (double*)ctx->vals.p, ctx->stream);
   if (rc != STEMK_OK) return rc;
+  // wait for the kernels first: a copy into pageable memory queued behind seconds of device work was measured to cost
+  // several hundred milliseconds more than the same copy issued on an idle stream (see stemk_gram)
+  CU(cudaStreamSynchronize(ctx->stream));
   CU(cudaMemcpyAsync(out, ctx->vals.p, n_pairs * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return STEMK_OK;
