@@ -39,6 +39,7 @@ def lib():
         L.oracle_bpla_pairs.argtypes = [vp, vp, vp, C.c_size_t, vp, vp, vp]
         L.oracle_bpla_gradients.argtypes = [vp, vp, vp, C.c_size_t, vp, vp, vp, vp]
         L.oracle_nstem_pairs.argtypes = [vp, vp, vp, C.c_size_t, vp, vp, vp]
+        L.oracle_nstem_pairs_banded.argtypes = [vp, C.c_uint, vp, vp, C.c_size_t, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -125,4 +126,14 @@ def nstem_pairs(params, x, y, xi, yi):
     out = np.zeros(len(xi))
     cx, cy = x.c(), y.c()
     lib().oracle_nstem_pairs(_p(params), _p(cx), _p(cy), len(xi), xi.ctypes.data, yi.ctypes.data, out.ctypes.data)
+    return out
+
+
+def nstem_pairs_banded(params, band, x, y, xi, yi):
+    """Restated StemKernel::partial_dp with the band-only constraints (band > 0; ali_bound = 0)."""
+    xi = np.ascontiguousarray(xi, dtype=np.uint32)
+    yi = np.ascontiguousarray(yi, dtype=np.uint32)
+    out = np.zeros(len(xi))
+    cx, cy = x.c(), y.c()
+    lib().oracle_nstem_pairs_banded(_p(params), int(band), _p(cx), _p(cy), len(xi), xi.ctypes.data, yi.ctypes.data, out.ctypes.data)
     return out

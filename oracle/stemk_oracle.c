@@ -656,6 +656,129 @@ static double nstem_pair(const stemk_nstem_params* p, const stemk_nstem_set* X, 
   return res;
 }
 
+/* StemKernel::partial_dp (stem_kernel/stem_kernel.cpp:113-280) with the band-only alignment constraints of
+ * alignment_constraints (:14-83, ali_bound == 0, band > 0): row i of x may pair with columns c_low[i]..c_high[i] of y
+ * around the diagonal; cells outside a plane's window keep the plane's fill value (0, or 1 for K0 of the (j,j) planes)
+ * and the four neighbour terms fall back to the reference's "approximation" cells at the window border.  Statement
+ * order kept; the #if 0 blocks of the reference are dead code and are not restated. */
+static double nstem_pair_banded(const stemk_nstem_params* p, unsigned band, const stemk_nstem_set* X, uint32_t xr,
+                                const stemk_nstem_set* Y, uint32_t yr) {
+  const char* x = X->text + X->off[xr];
+  const char* y = Y->text + Y->off[yr];
+  const size_t lx = X->off[xr + 1] - X->off[xr], ly = Y->off[yr + 1] - Y->off[yr];
+  const float* tx = p->bp_mode == 1 ? X->bp + X->bp_off[xr] : NULL;
+  const float* ty = p->bp_mode == 1 ? Y->bp + Y->bp_off[yr] : NULL;
+  const double g = p->gap;
+  const size_t W = ly + 1, plane = W * W, col = (lx + 1) * plane;
+  double* g_pow = malloc((ly + 1) * sizeof(double));
+  g_pow[0] = 1.0;
+  for (size_t i = 1; i != ly + 1; ++i) g_pow[i] = g_pow[i - 1] * g;
+  /* alignment_constraints :77-83 */
+  size_t* c_low = malloc(2 * (lx + 1) * sizeof(size_t));
+  size_t* c_high = c_low + (lx + 1);
+  for (size_t i = 0; i != lx + 1; ++i) {
+    const unsigned j = (unsigned)((double)i / lx * ly + 0.5);
+    c_low[i] = j < band ? 0 : j - band;
+    c_high[i] = j + band > ly ? ly : j + band;
+  }
+  double* mem = calloc(8 * 2 * col, sizeof(double));
+#define DP(s, i, j, k, l) mem[((size_t)(s) * 2 + ((j) & 1)) * col + (size_t)(i) * plane + (size_t)(k) * W + (l)]
+  for (size_t j = 0; j != lx + 1; ++j) {
+    for (size_t k = 0; k != W; ++k)
+      for (size_t l = 0; l != W; ++l) {
+        DP(NK0, j, j, k, l) = 1.0;
+        DP(NK1, j, j, k, l) = DP(NK2, j, j, k, l) = DP(NK3, j, j, k, l) = 0.0;
+        DP(NG0, j, j, k, l) = DP(NG1, j, j, k, l) = DP(NG2, j, j, k, l) = DP(NG3, j, j, k, l) = 0.0;
+      }
+    for (size_t l = 0; l != ly + 1; ++l) {
+      DP(NG0, j, j, l, l) = 1.0;
+      if (l == 0) continue;
+      for (size_t k = l - 1;; --k) {
+        DP(NG0, j, j, k, l) = DP(NG0, j, j, k + 1, l) * g;
+        if (k == 0) break;
+      }
+    }
+    if (j == 0) continue;
+    for (size_t i = j - 1;; --i) {
+      const float bp_ij = nstem_prob(p, x, lx, tx, i, j - 1);
+      for (int s = 0; s < 8; ++s) memset(&DP(s, i, j, 0, 0), 0, plane * sizeof(double));
+      for (size_t l = c_low[j]; l != c_high[j] + 1; ++l) {
+        DP(NK0, i, j, l, l) = 1.0;
+        DP(NG0, i, j, l, l) = DP(NG0, i + 1, j, l, l) * g;
+        if (l == 0) continue;
+        size_t k = l - 1 < c_high[i] ? l - 1 : c_high[i];
+        if (k < c_low[i]) continue;                       /* the reference's loop condition k >= c_low[i] */
+        for (;; --k) {
+          if (l <= c_high[j - 1]) {
+            DP(NK0, i, j, k, l) = DP(NK0, i, j - 1, k, l);
+            DP(NG0, i, j, k, l) = DP(NG0, i, j - 1, k, l) * g;
+          } else {
+            DP(NK0, i, j, k, l) = DP(NK0, i, j - 1, k, c_high[j - 1]);
+            DP(NG0, i, j, k, l) = DP(NG0, i, j - 1, k, c_high[j - 1]) * g * g;
+          }
+          if (k >= c_low[i + 1]) {
+            DP(NK1, i, j, k, l) = DP(NK1, i + 1, j, k, l);
+            DP(NG1, i, j, k, l) = DP(NG1, i + 1, j, k, l) * g;
+          } else {
+            DP(NK1, i, j, k, l) = DP(NK1, i + 1, j, c_low[i + 1], l);
+            DP(NG1, i, j, k, l) = DP(NG1, i + 1, j, c_low[i + 1], l) * g * g;
+          }
+          if (l - 1 >= c_low[j] || k == l - 1) {
+            DP(NK2, i, j, k, l) = DP(NK2, i, j, k, l - 1);
+            DP(NG2, i, j, k, l) = DP(NG2, i, j, k, l - 1) * g;
+          } else {
+            DP(NK2, i, j, k, l) = 0.0;
+            DP(NG2, i, j, k, l) = 0.0;
+            for (size_t ll = k; ll != l; ++ll) {
+              DP(NK2, i, j, k, l) += DP(NK3, i, j, ll, ll);
+              DP(NG2, i, j, k, l) += DP(NG3, i, j, ll, ll) * g_pow[l - k];
+            }
+          }
+          if (k + 1 <= c_high[i]) {
+            DP(NK3, i, j, k, l) = DP(NK3, i, j, k + 1, l);
+            DP(NG3, i, j, k, l) = DP(NG3, i, j, k + 1, l) * g;
+          } else {
+            DP(NK3, i, j, k, l) = DP(NK3, i, j, l, l);
+            DP(NG3, i, j, k, l) = DP(NG3, i, j, l, l) * g_pow[l - k];
+          }
+          if (bp_ij > p->bp_bound) {
+            const float bp_kl = nstem_prob(p, y, ly, ty, k, l - 1);
+            if (bp_kl > p->bp_bound) {
+              if (x[i] == y[k] && x[j - 1] == y[l - 1]) {
+                DP(NK3, i, j, k, l) += DP(NG0, i + 1, j - 1, k + 1, l - 1) * p->stack * bp_ij * bp_kl;
+                DP(NG3, i, j, k, l) += DP(NG0, i + 1, j - 1, k + 1, l - 1);
+              } else {
+                DP(NK3, i, j, k, l) += DP(NG0, i + 1, j - 1, k + 1, l - 1) * p->stack * p->subst * bp_ij * bp_kl;
+              }
+            }
+          }
+          DP(NK2, i, j, k, l) += DP(NK3, i, j, k, l);
+          DP(NG2, i, j, k, l) += DP(NG3, i, j, k, l);
+          DP(NK1, i, j, k, l) += DP(NK2, i, j, k, l);
+          DP(NG1, i, j, k, l) += DP(NG2, i, j, k, l);
+          DP(NK0, i, j, k, l) += DP(NK1, i, j, k, l);
+          DP(NG0, i, j, k, l) += DP(NG1, i, j, k, l);
+          if (k == c_low[i]) break;
+        }
+      }
+      if (i == 0) break;
+    }
+  }
+  const double res = DP(NK0, 0, lx, 0, ly);
+#undef DP
+  free(mem);
+  free(c_low);
+  free(g_pow);
+  return res;
+}
+
+/* band == 0: full_dp; band > 0: partial_dp with the band-only constraints (stem_kernel.h:51-54 with ali_bound == 0) */
+void oracle_nstem_pairs_banded(const stemk_nstem_params* p, unsigned band, const stemk_nstem_set* X, const stemk_nstem_set* Y,
+                               size_t n_pairs, const uint32_t* xi, const uint32_t* yi, double* out) {
+  for (size_t k = 0; k < n_pairs; ++k)
+    out[k] = band > 0 ? nstem_pair_banded(p, band, X, xi[k], Y, yi[k]) : nstem_pair(p, X, xi[k], Y, yi[k]);
+}
+
 void oracle_nstem_pairs(const stemk_nstem_params* p, const stemk_nstem_set* X, const stemk_nstem_set* Y, size_t n_pairs,
                         const uint32_t* xi, const uint32_t* yi, double* out) {
   for (size_t k = 0; k < n_pairs; ++k) out[k] = nstem_pair(p, X, xi[k], Y, yi[k]);

@@ -26,6 +26,9 @@ void oracle_bpla_gradients(const stemk_bpla_params* p, const stemk_bpla_set* X, 
 /* naive stem kernel, stem_kernel/stem_kernel.cpp:282-351 (full_dp) with the base-pair classes of :353-420 */
 void oracle_nstem_pairs(const stemk_nstem_params* p, const stemk_nstem_set* X, const stemk_nstem_set* Y, size_t n_pairs,
                         const uint32_t* xi, const uint32_t* yi, double* out);
+/* band > 0: StemKernel::partial_dp with the band-only constraints (stem_kernel.cpp:14-83, 113-280); band == 0: full_dp */
+void oracle_nstem_pairs_banded(const stemk_nstem_params* p, unsigned band, const stemk_nstem_set* X, const stemk_nstem_set* Y,
+                               size_t n_pairs, const uint32_t* xi, const uint32_t* yi, double* out);
 #ifdef __cplusplus
 }
 #endif

@@ -164,4 +164,8 @@ if __name__ == "__main__":
     n["k_table"] = R.nstem_pairs(nstem.make_params(bp_mode=1, bp_bound=0.05), sb, sb, xi, yi)
     n["k_custom"] = R.nstem_pairs(nstem.make_params(loop=1, gap=0.6, stack=1.7, subst=0.3), sa, sa, xi, yi)
     n["k_default_bound"] = R.nstem_pairs(nstem.make_params(bp_bound=1.0), sa, sa, xi, yi)
+    # the banded partial_dp (stem_kernel.cpp:113-280, band-only constraints :77-83)
+    for band in (3, 8):
+        n[f"k_normal_band{band}"] = R.nstem_pairs(nstem.make_params(), sa, sa, xi, yi, band=band)
+        n[f"k_table_band{band}"] = R.nstem_pairs(nstem.make_params(bp_mode=1, bp_bound=0.05), sb, sb, xi, yi, band=band)
     np.savez_compressed(os.path.join(OUT, "golden_nstem.npz"), **n)

@@ -53,6 +53,27 @@ def test_restatement_matches_the_compiled_reference_on_fresh_inputs():
         assert np.array_equal(O.nstem_pairs(p, s, s, xi, yi), R.nstem_pairs(p, s, s, xi, yi))
 
 
+def test_banded_restatement_is_bit_identical_to_the_reference():
+    """StemKernel::partial_dp with the band-only constraints (stem_kernel.cpp:14-83, 113-280): golden values of the
+    compiled reference, and, where oracle/_ref exists, fresh inputs incl. a band wider than the sequences (= full_dp).
+    (Oracle only so far: the CUDA kernel covers full_dp)"""
+    sa, sb, z = golden_sets()
+    for band in (3, 8):
+        assert np.array_equal(O.nstem_pairs_banded(nstem.make_params(), band, sa, sa, z["xi"], z["yi"]), z[f"k_normal_band{band}"])
+        assert np.array_equal(O.nstem_pairs_banded(nstem.make_params(bp_mode=1, bp_bound=0.05), band, sb, sb, z["xi"], z["yi"]),
+                              z[f"k_table_band{band}"])
+    assert not np.array_equal(z["k_normal_band3"], z["k_normal"])
+    if os.path.exists(os.path.join(R.REF_DIR, "libstemk_ref_nstem.so")):
+        rng = np.random.default_rng(12)
+        seqs = ["".join(rng.choice(list("acgu"), n)) for n in (2, 9, 16, 23)] + ["gggcaaagccc"]
+        s = nstem.NstemSet(seqs)
+        xi, yi = np.divmod(np.arange(len(seqs) ** 2), len(seqs))
+        p = nstem.make_params(use_gu=True, loop=1)
+        for band in (1, 4, 30):
+            assert np.array_equal(O.nstem_pairs_banded(p, band, s, s, xi, yi), R.nstem_pairs(p, s, s, xi, yi, band=band))
+        assert np.array_equal(O.nstem_pairs_banded(p, 30, s, s, xi, yi), O.nstem_pairs(p, s, s, xi, yi))
+
+
 # ------------------------------------------------------------------------------------------------- GPU
 @pytest.mark.gpu
 def test_gpu_golden_swapped_and_rectangular():
