@@ -212,7 +212,7 @@ int stemk_bpla_gradients(stemk_ctx* ctx, const stemk_bpla_params* params, const 
  * bp_mode 0: canonical pairs from the text, NormalBasePair / WobbleBasePair (:353-392; use_gu selects g-u pairs);
  * bp_mode 1: prob(i,j) read from a dense row-major L x L float table per sequence (the role of the
  * ViennaRNA-backed BPMatrix class, :394-420).  Parameter defaults: stem_kernel/main.cpp:46-64 (gap 0.8, stack 1,
- * loop 3, subst 0.5).  The banded / alignment-constrained partial_dp (:113-280) is not provided. */
+ * loop 3, subst 0.5).  The banded partial_dp (:113-280) is stemk_nstem_pairs_banded below. */
 typedef struct stemk_nstem_params {
   int32_t bp_mode;
   int32_t use_gu;
@@ -232,6 +232,12 @@ typedef struct stemk_nstem_set {
 /* out[k] = k_stem_naive(x[xi[k]], y[yi[k]]) on the context's device (host buffers).  No CPU path. */
 int stemk_nstem_pairs(stemk_ctx* ctx, const stemk_nstem_params* params, const stemk_nstem_set* x, const stemk_nstem_set* y,
                       size_t n_pairs, const uint32_t* xi, const uint32_t* yi, double* out);
+
+/* The same kernel with band > 0 (stem_kernel.h:51-54: operator() takes partial_dp, stem_kernel.cpp:113-280, with the
+ * band-only alignment constraints of :77-83; the pair-HMM constraints of ali_bound > 0 are not provided): row i of x may
+ * pair with the columns of y within `band` of the diagonal.  The arguments keep their roles (the band is not symmetric). */
+int stemk_nstem_pairs_banded(stemk_ctx* ctx, const stemk_nstem_params* params, uint32_t band, const stemk_nstem_set* x,
+                             const stemk_nstem_set* y, size_t n_pairs, const uint32_t* xi, const uint32_t* yi, double* out);
 
 /* Text of kernel-matrix rows in the reference's output format -- KernelMatrix::print (kernel_matrix.cpp:756-770)
  * and Output::kernel_output (framework.cpp:190-204): one line "<label> 0:<cnt> 1:<v> 2:<v> ... \n" per row, every

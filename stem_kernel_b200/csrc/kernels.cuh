@@ -160,8 +160,8 @@ cudaError_t run_bpla(const stemk_bpla_params& p, const stemk_bpla_set& x, const 
                      cudaStream_t stream, std::string* err);   // grad != NULL: BPLAKernel::compute_gradients, 4 doubles per pair
 // naive stem kernel (nstem.cu): host buffers in, host buffer out, synchronous on `stream`
 cudaError_t run_nstem(const stemk_nstem_params& p, const stemk_nstem_set& x, const stemk_nstem_set& y, size_t n_pairs,
-                      const uint32_t* xi, const uint32_t* yi, double* out, int sm_count, size_t smem_optin,
-                      cudaStream_t stream, std::string* err);
+                      const uint32_t* xi, const uint32_t* yi, double* out, uint32_t band, int sm_count, size_t smem_optin,
+                      cudaStream_t stream, std::string* err);   // band > 0: partial_dp with the band-only constraints
 cudaError_t launch_fp64_peak(double* sink, int grid, int block, int iters, cudaStream_t stream);
 
 }  // namespace stemk

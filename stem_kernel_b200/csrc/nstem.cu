@@ -182,10 +182,144 @@ __global__ void __launch_bounds__(kNstemThreads) nstem_pairs_kernel(const NstemL
   }
 }
 
+
+// ---- StemKernel::partial_dp with the band-only constraints (stem_kernel.cpp:14-83, 113-280) ----------------------
+// Row i of x may pair with the columns c_low[i] .. c_high[i] of y (a band of half-width `band` around the diagonal,
+// :77-83), so a plane (i,j) only has cells k in [c_low[i], c_high[i]], l in [c_low[j], c_high[j]], k < l; everything
+// else keeps the plane's fill value.  At the window borders the reference substitutes "approximation" cells for the
+// missing neighbours, which breaks the prefix-sum structure the full kernel uses to drop the K tables: all eight
+// tables are kept, on band-compressed planes (window of (2 band + 2)^2 cells per table) in a per-warp global scratch
+// holding two columns j of planes.  Restated facts the kernel uses (each follows from the statements of :130-262):
+//   * the planes (j,j) are constants: K0 = 1, G0(k,l) = g^(l-k), the other six tables 0;
+//   * the diagonal cells of a plane (i,j) are K0(l,l) = 1, G0(l,l) = g^(j-i) for l in the window of j, else 0, and 0
+//     in the other six tables, so the two fall-back sums over K3/G3(ll,ll) (:203-209, :215-216) are 0;
+//   * a cell outside its plane's window reads as 0.
+// One warp per pair: pass 1, lane <-> column l, the K3/G3 suffix recurrences along k with the MATCH term; pass 2,
+// lane <-> row k, K2/G2 along l, then K1/G1 from the plane (i+1,j) and K0/G0 from the plane (i,j-1), statement order
+// and operand order of the reference kept.
+struct NstemBandLaunch {
+  NstemLaunch B;
+  uint32_t band, wcap;              // wcap = plane pitch: min(2 band + 2, ly_cap + 2)
+};
+constexpr int kNbandWarps = 4;
+enum { BK0 = 0, BK1, BK2, BK3, BG0, BG1, BG2, BG3 };
+
+__global__ void __launch_bounds__(32 * kNbandWarps) nstem_banded_kernel(const NstemBandLaunch Q) {
+  const NstemLaunch& P = Q.B;
+  extern __shared__ __align__(16) double sm[];
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t WP = Q.wcap;                                   // pitch of a compressed plane
+  const size_t tsz = (size_t)WP * WP;                            // one table of one plane
+  double* scr = P.scratch + (size_t)(blockIdx.x * kNbandWarps + warp) * P.scratch_stride;
+  const double g = P.gap;
+  const uint32_t band = Q.band;
+
+  for (;;) {
+    unsigned long long kq = 0;
+    if (lane == 0) kq = atomicAdd(P.counter, 1ull);
+    kq = __shfl_sync(0xffffffffu, kq, 0);
+    if (kq >= P.n_pairs) break;
+    const uint32_t xr = P.xi[kq], yr = P.yi[kq];
+    const uint32_t lx = P.X.off[xr + 1] - P.X.off[xr], ly = P.Y.off[yr + 1] - P.Y.off[yr];
+    const char* x = P.X.text + P.X.off[xr];
+    const char* y = P.Y.text + P.Y.off[yr];
+    const float* tx = P.bp_mode == 1 ? P.X.bp + P.X.bp_off[xr] : nullptr;
+    const float* ty = P.bp_mode == 1 ? P.Y.bp + P.Y.bp_off[yr] : nullptr;
+    if (lx == 0 || ly == 0) {                                    // K0(0,lx,0,ly) is a diagonal cell or a (j,j) plane: 1
+      if (lane == 0) P.out[kq] = 1.0;
+      continue;
+    }
+    // g^n by repeated multiplication (the chains G0(i,j,l,l) = G0(i+1,j,l,l) * g and :119-121), per warp in shared memory
+    double* gp = sm + (size_t)warp * (P.pitch + 2u);
+    __syncwarp();
+    if (lane == 0) { gp[0] = 1.0; for (uint32_t n = 1; n <= max(lx, ly); ++n) gp[n] = gp[n - 1] * g; }
+    __syncwarp();
+    auto clo = [&](uint32_t i) { const uint32_t c = (uint32_t)((double)i / (double)lx * (double)ly + 0.5); return c < band ? 0u : c - band; };
+    auto chi = [&](uint32_t i) { const uint32_t c = (uint32_t)((double)i / (double)lx * (double)ly + 0.5); return c + band > ly ? ly : c + band; };
+    // plane (i, column parity): 8 tables of WP x WP, cell (k,l) at [k - clo(i)][l - clo(j)]
+    auto tab = [&](uint32_t t, uint32_t i, uint32_t j) { return scr + (((size_t)(j & 1u) * (lx + 1u) + i) * 8u + t) * tsz; };
+    // value of table t of plane (i,j) at (k,l), for a plane that is complete (fill values, diagonals, (j,j) planes)
+    auto get = [&](uint32_t t, uint32_t i, uint32_t j, uint32_t k, uint32_t l) -> double {
+      if (i == j) return t == BK0 ? 1.0 : ((t == BG0 && k <= l) ? gp[l - k] : 0.0);
+      const uint32_t ci = clo(i), cj = clo(j);
+      if (l < cj || l > chi(j)) return 0.0;
+      if (k == l) return t == BK0 ? 1.0 : (t == BG0 ? gp[j - i] : 0.0);
+      if (k < ci || k > chi(i) || k > l) return 0.0;
+      return tab(t, i, j)[(size_t)(k - ci) * WP + (l - cj)];
+    };
+
+    for (uint32_t j = 1; j <= lx; ++j) {
+      const uint32_t cj = clo(j), hj = chi(j), hj1 = chi(j - 1u);
+      for (uint32_t i = j - 1u;; --i) {
+        const uint32_t ci = clo(i), hi = chi(i), ci1 = clo(i + 1u);
+        const float bp_ij = pair_prob(P, x, lx, tx, i, j - 1u);
+        double* T[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) T[t] = tab(t, i, j);
+        for (size_t c = lane; c < 8u * tsz; c += 32u) T[0][c] = 0.0;            // the 8 tables of a plane are contiguous
+        __syncwarp();
+        // ---- pass 1: K3 / G3 along k (descending), lane <-> l
+        for (uint32_t l = cj + lane; l <= hj; l += 32u) {
+          if (l == 0u) continue;
+          uint32_t k = min(l - 1u, hi);
+          if (k < ci) continue;
+          double k3 = 0.0, g3 = 0.0;                                               // K3 / G3 (k+1, l): 0 above the window and on the diagonal
+          for (;; --k) {
+            if (k + 1u <= hi) g3 = g3 * g;                                         // :211-213 (K3 is copied)
+            else { k3 = 0.0; g3 = 0.0; }                                           // :214-217: K3/G3(l,l) = 0
+            if (bp_ij > P.bp_bound) {                                              // :219-231
+              const float bp_kl = pair_prob(P, y, ly, ty, k, l - 1u);
+              if (bp_kl > P.bp_bound) {
+                const double g0m = get(BG0, i + 1u, j - 1u, k + 1u, l - 1u);
+                if (x[i] == y[k] && x[j - 1u] == y[l - 1u]) {
+                  k3 += g0m * P.stack * (double)bp_ij * (double)bp_kl;
+                  g3 += g0m;
+                } else {
+                  k3 += g0m * P.stack * P.subst * (double)bp_ij * (double)bp_kl;
+                }
+              }
+            }
+            T[BK3][(size_t)(k - ci) * WP + (l - cj)] = k3;
+            T[BG3][(size_t)(k - ci) * WP + (l - cj)] = g3;
+            if (k == ci) break;
+          }
+        }
+        __syncwarp();
+        // ---- pass 2: K2 / G2 along l (ascending), then K1 / G1 and K0 / G0, lane <-> k
+        for (uint32_t k = ci + lane; k <= hi; k += 32u) {
+          double k2 = 0.0, g2 = 0.0;                                               // K2 / G2 (k, l-1)
+          for (uint32_t l = max(cj, k + 1u); l <= hj; ++l) {
+            // :198-210: the left neighbour inside the window (0 on the diagonal), nothing left of the window
+            if (l - 1u >= cj) g2 = g2 * g; else { k2 = 0.0; g2 = 0.0; }
+            const size_t at = (size_t)(k - ci) * WP + (l - cj);
+            k2 += T[BK3][at];                                                      // dp_update :102-103
+            g2 += T[BG3][at];
+            double k1, g1;                                                         // :179-186
+            if (k >= ci1) { k1 = get(BK1, i + 1u, j, k, l); g1 = get(BG1, i + 1u, j, k, l) * g; }
+            else { k1 = get(BK1, i + 1u, j, ci1, l); g1 = get(BG1, i + 1u, j, ci1, l) * g * g; }
+            k1 += k2;                                                              // :104-105
+            g1 += g2;
+            double k0, g0;                                                         // :170-177
+            if (l <= hj1) { k0 = get(BK0, i, j - 1u, k, l); g0 = get(BG0, i, j - 1u, k, l) * g; }
+            else { k0 = get(BK0, i, j - 1u, k, hj1); g0 = get(BG0, i, j - 1u, k, hj1) * g * g; }
+            k0 += k1;                                                              // :106-107
+            g0 += g1;
+            T[BK2][at] = k2; T[BG2][at] = g2; T[BK1][at] = k1; T[BG1][at] = g1; T[BK0][at] = k0; T[BG0][at] = g0;
+          }
+        }
+        __syncwarp();
+        if (i == 0u) break;
+      }
+    }
+    if (lane == 0) P.out[kq] = get(BK0, 0u, lx, 0u, ly);
+    __syncwarp();
+  }
+}
+
 }  // namespace
 
 cudaError_t run_nstem(const stemk_nstem_params& p, const stemk_nstem_set& x, const stemk_nstem_set& y, size_t n_pairs,
-                      const uint32_t* xi, const uint32_t* yi, double* out, int sm_count, size_t smem_optin,
+                      const uint32_t* xi, const uint32_t* yi, double* out, uint32_t band, int sm_count, size_t smem_optin,
                       cudaStream_t stream, std::string* err) {
   std::vector<void*> to_free;
   auto up = [&](const void* h, size_t bytes, const void** d) -> cudaError_t {
@@ -199,16 +333,16 @@ cudaError_t run_nstem(const stemk_nstem_params& p, const stemk_nstem_set& x, con
     return cudaMemcpyAsync(q, h, bytes, cudaMemcpyHostToDevice, stream);
   };
   auto cleanup = [&]() { for (void* q : to_free) cudaFree(q); };
-  // x of a pair = the longer sequence, y = the shorter: caps over the pair list
+  // x of a pair = the longer sequence, y = the shorter: caps over the pair list (banded: the arguments keep their roles)
   uint32_t lx_cap = 1, ly_cap = 1;
   for (size_t k = 0; k < n_pairs; ++k) {
     const uint32_t a = x.off[xi[k] + 1] - x.off[xi[k]], b = y.off[yi[k] + 1] - y.off[yi[k]];
-    lx_cap = std::max(lx_cap, std::max(a, b));
-    ly_cap = std::max(ly_cap, std::min(a, b));
+    lx_cap = std::max(lx_cap, band ? a : std::max(a, b));
+    ly_cap = std::max(ly_cap, band ? b : std::min(a, b));
   }
   const uint32_t pitch = (ly_cap + 1u) | 1u;
   const size_t plane = (size_t)pitch * pitch;
-  const size_t smem = 2 * plane * sizeof(double);
+  const size_t smem = band ? 0 : 2 * plane * sizeof(double);
   if (smem > smem_optin) { if (err) *err = "naive stem kernel: the shorter sequence of a pair is too long for shared memory"; return cudaErrorInvalidValue; }
   NstemLaunch L;
   cudaError_t e;
@@ -230,12 +364,20 @@ cudaError_t run_nstem(const stemk_nstem_params& p, const stemk_nstem_set& x, con
   const void *dxi, *dyi;
   void *dout = nullptr, *dscr = nullptr;
   unsigned long long* dcnt = nullptr;
-  const int grid = (int)std::min<size_t>(n_pairs, (size_t)sm_count);
-  const unsigned long long stride = (unsigned long long)(lx_cap + 3u) * plane;
+  const uint32_t wcap = std::min(2u * band + 2u, ly_cap + 2u);
+  int grid = (int)std::min<size_t>(n_pairs, (size_t)sm_count);
+  unsigned long long stride = (unsigned long long)(lx_cap + 3u) * plane;
+  if (band) {   // per warp: two columns of (lx_cap + 1) planes, eight tables of wcap^2 cells each
+    stride = 2ull * (lx_cap + 1u) * 8ull * wcap * wcap;
+    const size_t budget = (size_t)8 << 30;
+    size_t ctas = std::min<size_t>((n_pairs + kNbandWarps - 1) / kNbandWarps, (size_t)sm_count * 4);
+    ctas = std::max<size_t>(1, std::min<size_t>(ctas, (size_t)(budget / (sizeof(double) * stride * kNbandWarps))));
+    grid = (int)ctas;
+  }
   if ((e = up(xi, sizeof(uint32_t) * n_pairs, &dxi)) != cudaSuccess || (e = up(yi, sizeof(uint32_t) * n_pairs, &dyi)) != cudaSuccess ||
       (e = cudaMalloc(&dout, sizeof(double) * n_pairs)) != cudaSuccess) { cleanup(); return e; }
   to_free.push_back(dout);
-  if ((e = cudaMalloc(&dscr, sizeof(double) * stride * grid)) != cudaSuccess) { cleanup(); return e; }
+  if ((e = cudaMalloc(&dscr, sizeof(double) * stride * grid * (band ? kNbandWarps : 1))) != cudaSuccess) { cleanup(); return e; }
   to_free.push_back(dscr);
   if ((e = cudaMalloc((void**)&dcnt, sizeof(unsigned long long))) != cudaSuccess) { cleanup(); return e; }
   to_free.push_back(dcnt);
@@ -244,8 +386,18 @@ cudaError_t run_nstem(const stemk_nstem_params& p, const stemk_nstem_set& x, con
   L.scratch = (double*)dscr; L.scratch_stride = stride;
   L.gap = p.gap; L.stack = p.stack; L.subst = p.subst; L.bp_bound = p.bp_bound; L.bp_mode = p.bp_mode; L.use_gu = p.use_gu;
   L.loop = p.loop; L.pitch = pitch;
-  if ((e = cudaFuncSetAttribute(nstem_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) { cleanup(); return e; }
-  nstem_pairs_kernel<<<grid, kNstemThreads, smem, stream>>>(L);
+  if (band) {
+    NstemBandLaunch BL;
+    BL.B = L; BL.band = band; BL.wcap = wcap;
+    const size_t bsmem = sizeof(double) * (pitch + 2u) * kNbandWarps;   // the powers of g, per warp (pitch >= max length + 1 of y; x below)
+    BL.B.pitch = std::max(pitch, (lx_cap + 1u) | 1u);
+    const size_t bsmem2 = sizeof(double) * (BL.B.pitch + 2u) * kNbandWarps;
+    (void)bsmem;
+    nstem_banded_kernel<<<grid, 32 * kNbandWarps, bsmem2, stream>>>(BL);
+  } else {
+    if ((e = cudaFuncSetAttribute(nstem_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) { cleanup(); return e; }
+    nstem_pairs_kernel<<<grid, kNstemThreads, smem, stream>>>(L);
+  }
   if ((e = cudaGetLastError()) != cudaSuccess) { cleanup(); return e; }
   e = cudaMemcpyAsync(out, dout, sizeof(double) * n_pairs, cudaMemcpyDeviceToHost, stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(stream);

@@ -823,8 +823,22 @@ int stemk_bpla_gradients(stemk_ctx* ctx, const stemk_bpla_params* params, const 
   return STEMK_OK;
 }
 
+static int nstem_pairs_impl(stemk_ctx* ctx, const stemk_nstem_params* params, uint32_t band, const stemk_nstem_set* x,
+                            const stemk_nstem_set* y, size_t n_pairs, const uint32_t* xi, const uint32_t* yi, double* out);
+
 int stemk_nstem_pairs(stemk_ctx* ctx, const stemk_nstem_params* params, const stemk_nstem_set* x, const stemk_nstem_set* y,
                       size_t n_pairs, const uint32_t* xi, const uint32_t* yi, double* out) {
+  return nstem_pairs_impl(ctx, params, 0, x, y, n_pairs, xi, yi, out);
+}
+
+int stemk_nstem_pairs_banded(stemk_ctx* ctx, const stemk_nstem_params* params, uint32_t band, const stemk_nstem_set* x,
+                             const stemk_nstem_set* y, size_t n_pairs, const uint32_t* xi, const uint32_t* yi, double* out) {
+  if (ctx && band == 0) return fail(ctx, STEMK_ERR_ARG, "band must be positive (band 0 is stemk_nstem_pairs)");
+  return nstem_pairs_impl(ctx, params, band, x, y, n_pairs, xi, yi, out);
+}
+
+static int nstem_pairs_impl(stemk_ctx* ctx, const stemk_nstem_params* params, uint32_t band, const stemk_nstem_set* x,
+                            const stemk_nstem_set* y, size_t n_pairs, const uint32_t* xi, const uint32_t* yi, double* out) {
   if (!ctx || !params || !x || !y) return fail(ctx, STEMK_ERR_ARG, "null argument");
   if (ctx->device == STEMK_DEVICE_NONE) return no_device(ctx);
   if (n_pairs == 0) return STEMK_OK;
@@ -838,7 +852,7 @@ int stemk_nstem_pairs(stemk_ctx* ctx, const stemk_nstem_params* params, const st
     if (xi[k] >= x->n_seqs || yi[k] >= y->n_seqs) return fail(ctx, STEMK_ERR_ARG, "pair index out of range");
   CU(cudaSetDevice(ctx->device));
   std::string err;
-  cudaError_t e = run_nstem(*params, *x, *y, n_pairs, xi, yi, out, ctx->sm_count, ctx->smem_optin, ctx->stream, &err);
+  cudaError_t e = run_nstem(*params, *x, *y, n_pairs, xi, yi, out, band, ctx->sm_count, ctx->smem_optin, ctx->stream, &err);
   if (e != cudaSuccess) return err.empty() ? cuda_fail(ctx, e, "naive stem kernel") : fail(ctx, STEMK_ERR_NOMEM, err);
   ctx->launches += 1;
   return STEMK_OK;

@@ -76,3 +76,14 @@ def pairs(ctx, params, x, y, xi, yi):
     ctx._check(L.lib().stemk_nstem_pairs(ctx.h, C.byref(params), C.byref(cx), C.byref(cy), len(xi), xi.ctypes.data,
                                          yi.ctypes.data, out.ctypes.data))
     return out
+
+
+def pairs_banded(ctx, params, band, x, y, xi, yi):
+    """StemKernel(..., band, ali_bound=0)(x[xi[k]], y[yi[k]]) with band > 0: partial_dp (stem_kernel.cpp:113-280)."""
+    xi = np.ascontiguousarray(xi, dtype=np.uint32)
+    yi = np.ascontiguousarray(yi, dtype=np.uint32)
+    out = np.zeros(len(xi))
+    cx, cy = x.c(), y.c()
+    ctx._check(L.lib().stemk_nstem_pairs_banded(ctx.h, C.byref(params), int(band), C.byref(cx), C.byref(cy), len(xi),
+                                                xi.ctypes.data, yi.ctypes.data, out.ctypes.data))
+    return out

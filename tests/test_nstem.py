@@ -110,3 +110,31 @@ def test_gpu_config1_like_probability_tables():
     p = nstem.make_params(bp_mode=1, bp_bound=0.01)
     got, want = nstem.pairs(ctx, p, s, s, xi, yi), O.nstem_pairs(p, s, s, xi, yi)
     assert relerr(got, want) < TOL and want.max() > 1.0
+
+
+@pytest.mark.gpu
+def test_gpu_banded_partial_dp():
+    """stemk_nstem_pairs_banded (partial_dp with the band-only constraints) against the reference's golden values and
+    the oracle: canonical pairs and probability tables, bands 1 ... wider than the sequences (= full_dp), x and y
+    sets of different lengths in both roles."""
+    need_gpu()
+    from stem_kernel_b200 import api, _lib as L
+    ctx = api.Context(L.make_params(L.STR_SIMPLE))
+    sa, sb, z = golden_sets()
+    errs = {}
+    for band in (3, 8):
+        errs[("normal", band)] = relerr(nstem.pairs_banded(ctx, nstem.make_params(), band, sa, sa, z["xi"], z["yi"]), z[f"k_normal_band{band}"])
+        errs[("table", band)] = relerr(nstem.pairs_banded(ctx, nstem.make_params(bp_mode=1, bp_bound=0.05), band, sb, sb, z["xi"], z["yi"]),
+                                       z[f"k_table_band{band}"])
+    rng = np.random.default_rng(13)
+    a = nstem.NstemSet(["".join(rng.choice(list("acgu"), n)) for n in (1, 7, 19, 33, 48)] + ["gggcaaagccc"])
+    b = nstem.NstemSet(["".join(rng.choice(list("acgu"), n)) for n in (2, 11, 26, 40)])
+    xi, yi = np.divmod(np.arange(len(a.seqs) * len(b.seqs)), len(b.seqs))
+    p = nstem.make_params(use_gu=True, loop=1, gap=0.7)
+    for band in (1, 5, 12, 60):
+        errs[("ab", band)] = relerr(nstem.pairs_banded(ctx, p, band, a, b, xi, yi), O.nstem_pairs_banded(p, band, a, b, xi, yi))
+        errs[("ba", band)] = relerr(nstem.pairs_banded(ctx, p, band, b, a, yi, xi), O.nstem_pairs_banded(p, band, b, a, yi, xi))
+    errs[("full", 60)] = relerr(nstem.pairs_banded(ctx, p, 60, a, b, xi, yi), O.nstem_pairs(p, a, b, xi, yi))
+    assert max(errs.values()) < TOL, errs
+    with pytest.raises(api.StemkError, match="band must be positive"):
+        nstem.pairs_banded(ctx, p, 0, a, b, xi, yi)
