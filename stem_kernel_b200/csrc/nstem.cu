@@ -389,11 +389,9 @@ cudaError_t run_nstem(const stemk_nstem_params& p, const stemk_nstem_set& x, con
   if (band) {
     NstemBandLaunch BL;
     BL.B = L; BL.band = band; BL.wcap = wcap;
-    const size_t bsmem = sizeof(double) * (pitch + 2u) * kNbandWarps;   // the powers of g, per warp (pitch >= max length + 1 of y; x below)
-    BL.B.pitch = std::max(pitch, (lx_cap + 1u) | 1u);
-    const size_t bsmem2 = sizeof(double) * (BL.B.pitch + 2u) * kNbandWarps;
-    (void)bsmem;
-    nstem_banded_kernel<<<grid, 32 * kNbandWarps, bsmem2, stream>>>(BL);
+    BL.B.pitch = std::max(pitch, (lx_cap + 1u) | 1u);                    // the powers of g, per warp: up to max(lx, ly)
+    const size_t bsmem = sizeof(double) * (BL.B.pitch + 2u) * kNbandWarps;
+    nstem_banded_kernel<<<grid, 32 * kNbandWarps, bsmem, stream>>>(BL);
   } else {
     if ((e = cudaFuncSetAttribute(nstem_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) { cleanup(); return e; }
     nstem_pairs_kernel<<<grid, kNstemThreads, smem, stream>>>(L);

@@ -149,7 +149,6 @@ int stemk_device_count(void) {
 const char* stemk_last_error(const stemk_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
 int stemk_create(stemk_ctx** out, const stemk_params* params, int device) {
-  stemk_ctx* ctx = nullptr;
   if (!out || !params) return fail(nullptr, STEMK_ERR_ARG, "null argument");
   *out = nullptr;
   if (params->kind < STEMK_SI_STEM || params->kind > STEMK_STR_NAIVE) return fail(nullptr, STEMK_ERR_ARG, "unknown kernel kind");
