@@ -1,6 +1,6 @@
 """BPLA kernel timing: C2-like set (n random 100-nt sequences) and C1-like records; error against the oracle on a sample."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from stem_kernel_b200 import synth, bpla, api, _lib as L
 from oracle import oraclebind as O

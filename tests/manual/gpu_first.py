@@ -1,6 +1,6 @@
 """First GPU contact: parity of every kernel kind against the C oracle on small sets + rough timing."""
 import sys, time, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from stem_kernel_b200 import synth, hostlib, api, _lib as L
 from oracle import oraclebind as O

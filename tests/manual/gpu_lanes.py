@@ -1,7 +1,7 @@
 """GPU check of the lanes-are-rows stem kernel (STEMK_LANES=1): whole Gram matrix against the fast kernel,
 sampled pairs against the oracle, and timing on C3-like records."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from stem_kernel_b200 import synth, hostlib, api, _lib as L
 from oracle import oraclebind as O

@@ -1,6 +1,6 @@
 """Naive stem kernel timing: n C1-like records (~75 nt) with probability tables; error against the oracle on a sample."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from stem_kernel_b200 import synth, nstem, api, _lib as L
 from oracle import oraclebind as O

@@ -1,6 +1,6 @@
 """Quick GPU check of the fast stem kernel: parity vs oracle on a few pairs + timing on C3-like records."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from stem_kernel_b200 import synth, hostlib, api, _lib as L
 from oracle import oraclebind as O
