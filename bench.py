@@ -404,6 +404,13 @@ def run_b200(args, rank, world, local_rank):
                      "kernel_share_of_step": kern_ms / (total_ms / args.steps),
                      "peak_source": "FP64 FMA probe run live on this GPU (stemk_fp64_peak); MEASURED_PEAKS.json has no "
                                     "fp64 entry",
+                     # the same kernel against the HBM roofline: its DRAM traffic (ncu capture above) over its live
+                     # launch time, against the measured copy bandwidth of MEASURED_PEAKS.json
+                     "hbm_view": {"bound": "hbm", "achieved": 4.44e6 * len(mine) / (kern_ms * 1e-3) / 1e9 if kern_ms else None,
+                                  "peak": hbm_peak, "unit": "GB/s",
+                                  "frac": (4.44e6 * len(mine) / (kern_ms * 1e-3) / 1e9 / hbm_peak) if kern_ms and hbm_peak else None,
+                                  "note": "traffic of the per-pair DP tables (not compulsory bytes); peak = measured "
+                                          "hbm_gbs of MEASURED_PEAKS.json, else the 6650 GB/s fallback"},
                      "hbm_sanity": {"set_bytes": int(set_bytes), "peak_gbs": hbm_peak,
                                     "note": "compulsory HBM traffic is << 1 B/flop on this path (SURVEY 8(d))"}},
         "cpu_baseline": cpu,
