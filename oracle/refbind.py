@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-REF_DIR = os.path.join(_HERE, "_ref")
+# STEMK_REF_VARIANT=o3 selects the courtesy build of the same sources (-O3 -march=x86-64-v3)
+REF_DIR = os.path.join(_HERE, "_ref", os.environ.get("STEMK_REF_VARIANT", ""))
 
 # kernel kinds of ref_harness.cpp (RefKind)
 SI_STEM, SU_STEM, SI_STEM_STR, SU_STEM_STR, LSU_STEM, LSU_STR, LSU_STEM_STR, STR_SUBST, STR_SIMPLE = range(9)

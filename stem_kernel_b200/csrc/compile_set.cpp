@@ -48,13 +48,13 @@ struct RecOut {  // one record's share, appended to the CompiledSet in record or
   std::vector<double> up, dn, s2;
   std::vector<NodeI> nodei;
   std::vector<uint16_t> c16;
-  std::vector<uint32_t> blk;
+  std::vector<uint32_t> blk, lperm;
   std::vector<double> pd, pb;  // work-model prefix sums over node length
-  uint32_t n_all = 0, e_all = 0, max_rows = 0;
+  uint32_t n_all = 0, e_all = 0, max_rows = 0, band_cnt = 0;
   std::string err;
 };
 
-void compile_record(const stemk_seqset_desc& s, uint32_t r, double g, RecOut* o) {
+void compile_record(const stemk_seqset_desc& s, uint32_t r, double g, uint32_t len_band, RecOut* o) {
   const uint32_t n0 = s.node_off[r], n = s.node_off[r + 1] - n0;
   const uint32_t* first = s.node_first + n0;
   const uint32_t* last = s.node_last + n0;
@@ -156,7 +156,9 @@ void compile_record(const stemk_seqset_desc& s, uint32_t r, double g, RecOut* o)
     o->lev_off[l + 1] += o->lev_off[l];
   }
   {
-    // inside a level, nodes with many inner pairs first: lanes of a warp then see similar trip counts
+    // inside a level the longest nodes first: the nodes at or above a row's length window are then a prefix of
+    // every level (stem_fast.cu stops a level at the first node below it); ties: many inner pairs first, so that
+    // neighbouring lanes see similar trip counts
     std::vector<uint32_t> nl_deg(n, 0);
     for (uint32_t u = 0; u < n; ++u)
       for (uint32_t e = eoff[u]; e < eoff[u + 1]; ++e) if (!leaf[s.edge_to[e]]) ++nl_deg[u];
@@ -164,6 +166,8 @@ void compile_record(const stemk_seqset_desc& s, uint32_t r, double g, RecOut* o)
     for (uint32_t u = 0; u < n; ++u) if (!leaf[u]) order.push_back(u);
     std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
       if (level[a] != level[b]) return level[a] < level[b];
+      const uint32_t la = last[a] - first[a], lb = last[b] - first[b];
+      if (la != lb) return la > lb;
       return nl_deg[a] > nl_deg[b];
     });
     for (uint32_t k = 0; k < order.size(); ++k) newidx[order[k]] = k;
@@ -250,6 +254,19 @@ void compile_record(const stemk_seqset_desc& s, uint32_t r, double g, RecOut* o)
       for (uint32_t r = o->lev_off[l]; r < o->lev_off[l + 1]; r += kFastRows)
         o->blk.push_back(r | (std::min(kFastRows, o->lev_off[l + 1] - r) << 16));
     if (fast) h.flags |= REC_FAST;
+    // nodes sorted by length (the band of a row is a range of this list) and the most nodes any window
+    // [l - band, l + band] holds: the size of the fast kernel's per-warp MATCH buffer
+    o->lperm.resize(N);
+    for (uint32_t k = 0; k < N; ++k) o->lperm[k] = (std::min(o->len[k], 0xffffu) << 16) | (k & 0xffffu);
+    std::sort(o->lperm.begin(), o->lperm.end());
+    if (len_band == 0) o->band_cnt = N;
+    else {
+      uint32_t lo = 0;
+      for (uint32_t hi = 0; hi < N; ++hi) {
+        while ((o->lperm[hi] >> 16) - (o->lperm[lo] >> 16) > 2 * len_band) ++lo;
+        o->band_cnt = std::max(o->band_cnt, hi - lo + 1);
+      }
+    }
   }
   o->pd.assign(max_len + 2, 0.0); o->pb.assign(max_len + 2, 0.0);
   for (uint32_t k = 0; k < N; ++k) {
@@ -264,7 +281,7 @@ void append(std::vector<T>& dst, const std::vector<T>& src) { dst.insert(dst.end
 
 }  // namespace
 
-std::string compile_set(const stemk_seqset_desc& s, double g, int n_threads, CompiledSet* out) {
+std::string compile_set(const stemk_seqset_desc& s, double g, uint32_t len_band, int n_threads, CompiledSet* out) {
   const uint32_t n = s.n_seqs;
   const bool timing = std::getenv("STEMK_TIMING") != nullptr;
   auto t0 = std::chrono::steady_clock::now();
@@ -272,11 +289,11 @@ std::string compile_set(const stemk_seqset_desc& s, double g, int n_threads, Com
   if (n_threads < 1) n_threads = 1;
   n_threads = std::min<int>(n_threads, std::max<uint32_t>(1, n / 16));
   if (n_threads <= 1) {
-    for (uint32_t r = 0; r < n; ++r) compile_record(s, r, g, &recs[r]);
+    for (uint32_t r = 0; r < n; ++r) compile_record(s, r, g, len_band, &recs[r]);
   } else {
     std::vector<std::thread> th;
     for (int t = 0; t < n_threads; ++t)
-      th.push_back(std::thread([&, t]() { for (uint32_t r = t; r < n; r += n_threads) compile_record(s, r, g, &recs[r]); }));
+      th.push_back(std::thread([&, t]() { for (uint32_t r = t; r < n; r += n_threads) compile_record(s, r, g, len_band, &recs[r]); }));
     for (auto& x : th) x.join();
   }
   auto t1 = std::chrono::steady_clock::now();
@@ -293,7 +310,7 @@ std::string compile_set(const stemk_seqset_desc& s, double g, int n_threads, Com
     c.len.reserve(nn); c.bcode.reserve(nn); c.nodei.reserve(nn); c.deg_all.reserve(nn);
     c.coff.reserve(nn + n); c.boff.reserve(nn + n); c.cidx.reserve(ne); c.ce.reserve(ne); c.lev_off.reserve(nl);
     c.bab.reserve(nb); c.bfq.reserve(nb); c.ccode.reserve(nc); c.cw.reserve(nc); c.text.reserve(nc);
-    c.prof.reserve(4 * nc); c.c16.reserve(n16); c.blk.reserve(nblk); c.cost_pd.reserve(ncost); c.cost_pb.reserve(ncost);
+    c.prof.reserve(4 * nc); c.c16.reserve(n16); c.blk.reserve(nblk); c.lperm.reserve(nn); c.cost_pd.reserve(ncost); c.cost_pb.reserve(ncost);
     c.cost_off.reserve(n + 1); c.n_nodes_all.reserve(n); c.n_edges_all.reserve(n); c.max_level_rows.reserve(n);
   }
   // ---- merge.  Pass 1 (serial, sizes only): record headers, the offsets that become absolute, set statistics.
@@ -309,6 +326,7 @@ std::string compile_set(const stemk_seqset_desc& s, double g, int n_threads, Com
       h.blk0 = (uint32_t)nblk; h.nblk = (uint32_t)o.blk.size();
       if (h.flags & REC_FAST) {
         c.max_E4 = std::max(c.max_E4, h.e4); c.max_fastN = std::max(c.max_fastN, h.N); ++c.n_fast;
+        c.max_band_cnt = std::max(c.max_band_cnt, o.band_cnt);
       }
       e0s[r] = (uint32_t)ne; b0s[r] = (uint32_t)nb;
       if (o.pd.empty()) { o.pd.assign(1, 0.0); o.pb.assign(1, 0.0); }
@@ -317,6 +335,7 @@ std::string compile_set(const stemk_seqset_desc& s, double g, int n_threads, Com
       c.n_nodes_all.push_back(o.n_all);
       c.n_edges_all.push_back(o.e_all);
       c.max_level_rows.push_back(o.max_rows);
+      c.band_cnt.push_back(o.band_cnt);
       if (o.n_all) c.has_dag = true;
       if (h.flags & REC_HAS_WEIGHT) ++c.n_weighted;
       if (h.flags & REC_SIMPLE_COLS) ++c.n_simple_cols;
@@ -343,7 +362,7 @@ std::string compile_set(const stemk_seqset_desc& s, double g, int n_threads, Com
         append(c.lev_off, o.lev_off);
       }
     });
-    groups.push_back([&]() { for (RecOut& o : recs) { append(c.cidx, o.cidx); append(c.ce, o.ce); append(c.c16, o.c16); append(c.blk, o.blk); } });
+    groups.push_back([&]() { for (RecOut& o : recs) { append(c.cidx, o.cidx); append(c.ce, o.ce); append(c.c16, o.c16); append(c.blk, o.blk); append(c.lperm, o.lperm); } });
     groups.push_back([&]() { for (RecOut& o : recs) { append(c.bab, o.bab); append(c.bfq, o.bfq); append(c.ccode, o.ccode); append(c.cw, o.cw); append(c.text, o.text); } });
     groups.push_back([&]() { for (RecOut& o : recs) { append(c.prof, o.prof); append(c.cost_pd, o.pd); append(c.cost_pb, o.pb); } });
     if (n_threads <= 1) {
@@ -356,7 +375,6 @@ std::string compile_set(const stemk_seqset_desc& s, double g, int n_threads, Com
   }
   // packed row records (absolute child ranges, so built after the merge); records are independent
   c.xnode.resize(c.a.size());
-  c.yband.resize(c.a.size());
   {
     auto pack = [&](uint32_t r_lo, uint32_t r_hi) {
       for (uint32_t r = r_lo; r < r_hi; ++r) {
@@ -365,8 +383,6 @@ std::string compile_set(const stemk_seqset_desc& s, double g, int n_threads, Com
           const uint32_t gk = h.node0 + k;
           XNode& xn = c.xnode[gk];
           xn.s2 = c.s2[gk]; xn.a = c.a[gk]; xn.up = c.up[gk]; xn.ql = c.ql[gk]; xn.bfreq = c.bfreq[gk]; xn.paths = c.paths[gk];
-          NodeB& nb = c.yband[gk];
-          nb.s2 = c.s2[gk]; nb.el = c.el[gk]; nb.paths = c.paths[gk]; nb.bfreq = c.bfreq[gk];
           xn.e0 = c.coff[h.coff0 + k]; xn.e1 = c.coff[h.coff0 + k + 1]; xn.len = c.len[gk]; xn.bcode = c.bcode[gk];
         }
       }

@@ -32,7 +32,7 @@ constexpr int kMaxFastBuckets = 8;
 #endif
 constexpr uint32_t kFastGroup = STEMK_GROUP;  // == kGroup of stem_fast.cu
 #ifndef STEMK_MAXWARPS
-#define STEMK_MAXWARPS 28
+#define STEMK_MAXWARPS 24
 #endif
 constexpr int kFastMaxWarps = STEMK_MAXWARPS;  // warps per CTA of the fast stem kernel (its launch bound)
 
@@ -52,55 +52,9 @@ struct StemFastLaunch {
   double* rowacc;                    // per CTA: kFastGroup x nx_cap per-row result slots
   const double* pair_tab;
   uint32_t len_band, nx_cap, ny_cap, e4_cap, lev_cap;
+  uint32_t band_cap;                 // entries of the per-warp MATCH buffer (>= the y set's max_band_cnt)
+  unsigned long long* prof;          // optional (FAST_PROF builds): per-phase cycle counters summed over warps
 };
-
-// row-block stem kernel (stem_rows.cu): same queue / bucket plumbing as the fast kernel
-struct StemRowsLaunch {
-  SetView X, Y;
-  const uint32_t* xi;
-  const uint32_t* yi;
-  double* out;
-  const uint32_t* order;
-  const unsigned long long* start;
-  const unsigned long long* count;
-  unsigned long long* counter;
-  int bucket;
-  double* scratch;                   // per-CTA slabs of pre-scaled G0 rows (one per pair of a group)
-  unsigned long long scratch_stride; // doubles per CTA (all slabs of the group)
-  double* rowacc;                    // per CTA: kFastGroup x nx_cap per-row result slots + 1024 partial sums
-  unsigned long long rowacc_stride;  // doubles per CTA
-  const double* pair_tab;
-  uint32_t len_band, nx_cap, ny_cap, e4_cap, ylev_cap, xlev_cap;
-  uint32_t team_warps;               // warps of a team (a team sweeps one row block)
-  unsigned long long* prof;          // optional (ROWS_PROF builds): per-phase cycle counters, 16 per launch
-};
-// lanes-are-rows stem kernel (stem_lanes.cu): same queue / bucket plumbing as the fast kernel
-#ifndef STEMK_LANES_GROUP
-#define STEMK_LANES_GROUP 8
-#endif
-#ifndef STEMK_LANES_WARPS
-#define STEMK_LANES_WARPS 20
-#endif
-constexpr uint32_t kLanesGroup = STEMK_LANES_GROUP;  // pairs sharing one staged y record that a CTA runs level by level
-constexpr int kLanesWarps = STEMK_LANES_WARPS;
-struct StemLanesLaunch {
-  SetView X, Y;
-  const uint32_t* xi;
-  const uint32_t* yi;
-  double* out;
-  const uint32_t* order;
-  const unsigned long long* start;
-  const unsigned long long* count;
-  unsigned long long* counter;
-  int bucket;
-  double* scratch;                   // per-CTA slabs of pre-scaled G0 rows (one per pair of a group)
-  unsigned long long scratch_stride; // doubles per CTA (all slabs of the group)
-  double* rowacc;                    // per CTA: kLanesGroup x nx_cap per-row result slots
-  const double* pair_tab;
-  uint32_t len_band, nx_cap, ny_cap, e4_cap, lev_cap;
-  unsigned long long* prof;          // optional (LANES_PROF builds): per-phase cycle counters of thread 0, summed over CTAs
-};
-constexpr int kRowsMaxThreads = 512;  // launch bound of the row-block kernel (128 registers per thread)
 
 struct StemClassify {
   SetView X, Y;
@@ -136,14 +90,10 @@ size_t stem_smem_bytes(uint32_t nslots, uint32_t nx_cap, uint32_t ny_cap, uint32
 int stem_warps_per_cta();
 cudaError_t launch_stem(const StemLaunch& p, int grid, size_t smem, cudaStream_t stream);
 int stem_max_ctas_per_sm(size_t smem);
-size_t stem_fast_smem_bytes(uint32_t nwarps, uint32_t nx_cap, uint32_t ny_cap, uint32_t e4_cap, uint32_t lev_cap);
+size_t stem_fast_smem_bytes(uint32_t nwarps, uint32_t nx_cap, uint32_t ny_cap, uint32_t e4_cap, uint32_t lev_cap,
+                            uint32_t band_cap);
 int stem_fast_ctas_per_sm(int nwarps, size_t smem);
 cudaError_t launch_stem_fast(const StemFastLaunch& p, int grid, int nwarps, size_t smem, cudaStream_t stream);
-size_t stem_rows_smem_bytes(uint32_t rows, uint32_t nteams, uint32_t team_warps, uint32_t nx_cap, uint32_t ny_cap,
-                            uint32_t e4_cap, uint32_t ylev_cap, uint32_t xlev_cap);
-cudaError_t launch_stem_rows(const StemRowsLaunch& p, uint32_t rows, int grid, int nteams, size_t smem, cudaStream_t stream);
-size_t stem_lanes_smem_bytes(uint32_t rows, uint32_t ny_cap, uint32_t e4_cap, uint32_t lev_cap);
-cudaError_t launch_stem_lanes(const StemLanesLaunch& p, uint32_t rows, int grid, size_t smem, cudaStream_t stream);
 cudaError_t launch_classify(const StemClassify& c, int n_buckets, unsigned long long* counters, cudaStream_t stream);
 void string_shape_for(uint32_t ly_cap, int mode, int* cw, int* tp);
 // mode: 0 plain one-hot columns, 1 weighted, 2 naive characters, 3 general (see string_kernel.cu)

@@ -4,59 +4,80 @@
 // node / edge scores score_table.cpp:56-101,162-201), for records whose skip-edge factors are separable
 // (REC_FAST, compile_set.cpp):  e(p,c) = g^(len_p-len_c-2) = s2(p) * up(c).  Rows are therefore kept PRE-SCALED,
 //     H (i,j) = up_y(j) * G1(i,j)          HQ(i,j) = up_y(j) * Q(i,j)          G0s(i,j) = up_x(i) * G0(i,j)
-// and every gather of the recurrence becomes a plain sum over 2-byte child indices:
+// and every gather of the recurrence becomes a plain sum over child offsets:
 //     Q (i,j) = s2_x(i) * sum_cx G0s(cx,j)
 //     R (i,j) = s2_y(j) * sum_cy HQ(i,cy) + el_y(j)*ql_x(i)         S(i,j) = s2_y(j) * sum_cy H(i,cy)
-//     M = in_band ? v_s*R : 0      G1 = M + a_y(j)*S      G0 = G1 + a_x(i)*Q = dn_y(j) * (H + a_x(i)*HQ)
+//     M = in_band ? v_s*R : 0      G1 = M + a_y(j)*S      G0 = G1 + a_x(i)*Q
 //     k(x,y) = sum_i paths_x(i) * sum_j paths_y(j) * M(i,j)  (+ plr_x * lr_y)
-// No FMA operand has to be fetched per edge any more, child lists are padded to multiples of four (index N is an
-// all-zero dummy column), so the inner loop is one 8-byte index load + four 8-byte gathers + four adds.
+// Child lists are padded to multiples of four (index N is an all-zero dummy column).
+//
+// The rows of a BLOCK of kFastRows x nodes of one DAG level are computed together by one warp.  MATCH
+// (stem_kernel.cpp:46-59) only exists inside the length band, ~13 % of the cells, and R only depends on the finished
+// rows of i's inner pairs -- not on the row's own sweep -- so it is taken out of the sweep and done with full lanes:
+//   A   per row, lanes <-> column pairs: q = sum of the finished pre-scaled G0 rows of i's inner pairs (coalesced
+//       16-byte reads of the per-pair slab, eight in flight per lane);  HQ(i,:) = up_y*s2_x*q goes to the block
+//       buffer, the a_x*Q part of G0s(i,:) straight to the slab
+//   B1  per row, lanes <-> the y nodes INSIDE THE BAND of i (a contiguous range of the record's length-sorted node
+//       list, found by two warp-wide searches): R gathered from the block buffer, up_y*M(i,j) kept in a small
+//       per-warp buffer, the path-weighted MATCH sum of the row accumulated here
+//   Z   the row's part of the block buffer is cleared and the band's up_y*M values are scattered into it: it is now H
+//   B2  y level by y level, lanes <-> nodes of the level, every lane carrying ALL rows of the block (the buffer is
+//       interleaved [column][row], one 16-byte load fetches a child's value for two rows):
+//       H(i,j) += up_y*a_y*s2_y * sum_cy H(i,cy) for the nodes at or above the band (G1 is identically 0 below it:
+//       length-monotone DAG); nodes of a level are sorted by length, so a level stops at the first node below the
+//       window.  The index loads, node records and address arithmetic of the sweep are shared by the rows of the
+//       block; only __syncwarp between levels
+//   C   per row, lanes <-> column pairs: slab(i,j) += up_x*dn_y*H(i,j) where H is non-zero, fence, raise the flags
+// Per row a warp holds ONE buffer row (HQ, then H) plus the band buffer, against two full rows in the first version
+// of this kernel: more rows in flight per SM.
 //
 // Mapping.  One persistent CTA per SM; launches are bucketed by the size of the staged record so that shared memory
 // is sized for the bucket, not for the largest record of the set.  A CTA takes a GROUP of up to kGroup consecutive
 // queue positions that share their y record (callers order pair lists y-major), stages that record in shared memory
 // once and runs the group's pairs concurrently: a DAG level of one x record has ~14 rows, too few to keep the CTA's
-// warps busy on its own.  Warps pull row BLOCKS of the x records -- up to kFastRows rows of one DAG level, precomputed per record --
-// from a shared-memory queue, wait on per-row flags until the rows of the block's inner pairs are published, and
-// run the block alone:
-//   A  per row, lanes <-> columns: sum of the finished pre-scaled G0 rows (coalesced L2 reads of the per-CTA slab)
-//   B  y level by y level, lanes <-> (row of the block) x (node of the level): both rows share every index load;
-//      only __syncwarp between levels
-//   C  per row, lanes <-> columns: the finished row is scaled, written to the slab, fenced, its flag raised
-// The path-weighted MATCH sum of a row goes to a per-row shared-memory slot and the slots are added in a fixed
-// order at the end of the pair, so a pair's value does not depend on which warp happened to run which row.
+// warps busy on its own.  Warps pull row blocks of the x records -- precomputed per record -- from a shared-memory
+// ticket counter, wait on per-row flags until the rows of the block's inner pairs are published, and run the block
+// alone.  The path-weighted MATCH sum of a row goes to a per-row slot and the slots are added in a fixed order at the
+// end of the pair, so a pair's value does not depend on which warp happened to run which row: results are
+// bit-reproducible run to run.
 #include "kernels.cuh"
 
 namespace stemk {
 
 namespace {
 
-#ifndef STEMK_GROUP
-#define STEMK_GROUP 6
+constexpr uint32_t kGroup = kFastGroup;  // pairs sharing one staged y record that a CTA runs concurrently
+constexpr uint32_t R = kFastRows;        // rows of a block (1, 2 or 4)
+static_assert(R == 1 || R == 2 || R == 4 || R == 8, "kFastRows must be 1, 2, 4 or 8");
+#ifndef STEMK_B2MAP
+#define STEMK_B2MAP 1
 #endif
-constexpr uint32_t kGroup = STEMK_GROUP;  // pairs sharing one staged y record that a CTA runs concurrently
+// sweep mapping: 0 = lanes <-> nodes, every lane carries all rows of the block; 1 = lanes <-> (node slot, row)
 
 struct FastLayout {
-  uint32_t tab, yD0, yD1, yD2, yD3, yI, yC, yLev, done, rows, row_bytes, total;
+  uint32_t tab, yB2, yB1a, yB1b, yUp, yDn, yC, yLev, yPerm, done, warps, mbuf_bytes, buf_bytes, warp_bytes, total;
 };
 
-// nwarps warps, each with kFastRows x (HQ row, H row)
+// per warp: the band buffer, then the block buffer [ny_cap + 1 columns (the last one is the dummy)][R rows]
 __host__ __device__ inline FastLayout fast_layout(uint32_t nwarps, uint32_t nx_cap, uint32_t ny_cap, uint32_t e4_cap,
-                                                  uint32_t lev_cap) {
+                                                  uint32_t lev_cap, uint32_t band_cap) {
   FastLayout L;
   uint32_t off = 0;
   auto take = [&](uint32_t bytes) { uint32_t at = off; off += (bytes + 15u) & ~15u; return at; };
   L.tab = take(8 * 256);
-  L.yD0 = take(16 * ny_cap);  // {s2, el}     (MATCH cells only)
-  L.yD1 = take(16 * ny_cap);  // {up*a*s2, up}
-  L.yD2 = take(16 * ny_cap);  // {paths, bfreq}
-  L.yD3 = take(8 * ny_cap);   // dn
-  L.yI = take(8 * ny_cap);    // NodeI
-  L.yC = take(2 * e4_cap);    // child lists
+  L.yB2 = take(16 * ny_cap);   // {child list offset << 8 | bcode, deg4 | len << 16, coef = up*a*s2}   (sweep)
+  L.yB1a = take(16 * ny_cap);  // {s2, el}                                                                (MATCH)
+  L.yB1b = take(16 * ny_cap);  // {bfreq*up, paths*dn}                                                    (MATCH)
+  L.yUp = take(8 * (ny_cap + 2u));  // up                                                                 (phase A)
+  L.yDn = take(8 * (ny_cap + 2u));  // dn                                                                 (phase C)
+  L.yC = take(4 * e4_cap);     // child lists as 32-bit byte offsets into the block buffer
   L.yLev = take(4 * (lev_cap + 1));
-  L.done = take(nx_cap * kGroup);        // one byte per row, per pair of the group
-  L.row_bytes = (8u * (ny_cap + 1u) + 15u) & ~15u;  // + the dummy column
-  L.rows = take(2u * kFastRows * L.row_bytes * nwarps);
+  L.yPerm = take(4 * ny_cap);  // nodes sorted by length: len << 16 | node
+  L.done = take(nx_cap * kGroup);  // one byte per row, per pair of the group
+  L.mbuf_bytes = (8u * band_cap + 15u) & ~15u;
+  L.buf_bytes = (8u * R * (ny_cap + 2u) + 15u) & ~15u;
+  L.warp_bytes = L.mbuf_bytes + L.buf_bytes;
+  L.warps = take(L.warp_bytes * nwarps);
   L.total = off;
   return L;
 }
@@ -77,23 +98,53 @@ __device__ __forceinline__ uint32_t ld_flag_f(uint32_t addr) {
 __device__ __forceinline__ double lds_f64(uint32_t a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
 __device__ __forceinline__ double2 lds_v2f64(uint32_t a) { double2 v; asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a)); return v; }
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-__device__ __forceinline__ uint2 lds_v2u32(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
-__device__ __forceinline__ NodeI lds_nodei(uint32_t a) {
-  const uint2 v = lds_v2u32(a);
-  NodeI n; n.e4_bcode = v.x; n.deg4 = (uint16_t)(v.y & 0xffffu); n.len = (uint16_t)(v.y >> 16);
-  return n;
-}
+__device__ __forceinline__ uint4 lds_v4u32(uint32_t a) { uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
 __device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
 __device__ __forceinline__ void sts_v2f64(uint32_t a, double2 v) { asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v.x), "d"(v.y) : "memory"); }
 __device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-__device__ __forceinline__ void sts_v2u32(uint32_t a, uint2 v) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(v.x), "r"(v.y) : "memory"); }
-__device__ __forceinline__ void sts_nodei(uint32_t a, NodeI n) { sts_v2u32(a, make_uint2(n.e4_bcode, (uint32_t)n.deg4 | ((uint32_t)n.len << 16))); }
+__device__ __forceinline__ void sts_v4u32(uint32_t a, uint4 v) { asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
+// Makes a value opaque to the optimiser: base addresses of the shared-memory carve-up are otherwise rematerialised
+// from the kernel parameters inside the innermost loops (a dozen integer instructions per DP cell).
+__device__ __forceinline__ uint32_t pin(uint32_t v) { asm volatile("mov.b32 %0, %0;" : "+r"(v)); return v; }
 
 struct PairSlot {        // one pair of the group in flight
   uint32_t k;            // pair number (index into xi / yi / out)
-  uint32_t N, node0, coff0, blk0, nblk;
+  uint32_t N, node0, blk0, nblk;
   double plr;
 };
+
+// number of sorted entries (len << 16 | node, ascending) whose length is below `key`; Ny <= 1024, whole warp
+__device__ __forceinline__ uint32_t count_len_below(uint32_t perm, uint32_t Ny, uint32_t key, uint32_t lane) {
+  const uint32_t step = (Ny + 31u) >> 5;  // <= 32
+  const uint32_t t1 = lane * step;
+  const uint32_t c1 = __popc(__ballot_sync(0xffffffffu, t1 < Ny && (lds_u32(perm + 4u * t1) >> 16) < key));
+  const uint32_t base = c1 ? (c1 - 1u) * step : 0u;
+  const uint32_t t2 = base + lane;
+  return base + __popc(__ballot_sync(0xffffffffu, t2 < Ny && (lds_u32(perm + 4u * t2) >> 16) < key));
+}
+
+// S[r] += the block buffer's values of four children (byte offsets c4, rows interleaved)
+__device__ __forceinline__ void gather4(uint32_t buf, uint4 c4, double (&S)[R]) {
+  if (R == 1) {
+    S[0] += (lds_f64(buf + c4.x) + lds_f64(buf + c4.y)) + (lds_f64(buf + c4.z) + lds_f64(buf + c4.w));
+  } else {
+#pragma unroll
+    for (uint32_t h = 0; h < R; h += 2u) {
+      const double2 a = lds_v2f64(buf + c4.x + 8u * h), b = lds_v2f64(buf + c4.y + 8u * h);
+      const double2 c = lds_v2f64(buf + c4.z + 8u * h), d = lds_v2f64(buf + c4.w + 8u * h);
+      S[h] += (a.x + b.x) + (c.x + d.x);
+      S[h + 1u] += (a.y + b.y) + (c.y + d.y);
+    }
+  }
+}
+
+#ifdef FAST_PROF
+#define PROF_T(v) const long long v = clock64()
+#define PROF_ADD(slot, a, b) do { if (lane == 0) prof_acc[slot] += (b) - (a); } while (0)
+#else
+#define PROF_T(v) do {} while (0)
+#define PROF_ADD(slot, a, b) do {} while (0)
+#endif
 
 __global__ void __launch_bounds__(32 * kFastMaxWarps, 1) stem_fast_kernel(const StemFastLaunch P) {
   extern __shared__ __align__(16) unsigned char sm[];
@@ -101,7 +152,7 @@ __global__ void __launch_bounds__(32 * kFastMaxWarps, 1) stem_fast_kernel(const 
   __shared__ uint32_t s_next_blk, s_g, s_maxblk;
   __shared__ PairSlot s_slot[kGroup];
   const uint32_t nwarps = blockDim.x >> 5;
-  const FastLayout L = fast_layout(nwarps, P.nx_cap, P.ny_cap, P.e4_cap, P.lev_cap);
+  const FastLayout L = fast_layout(nwarps, P.nx_cap, P.ny_cap, P.e4_cap, P.lev_cap, P.band_cap);
   const uint32_t sb = (uint32_t)__cvta_generic_to_shared(sm);  // raw 32-bit shared addresses: LDS/STS [reg+imm]
 
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -113,9 +164,17 @@ __global__ void __launch_bounds__(32 * kFastMaxWarps, 1) stem_fast_kernel(const 
   const SetView& Y = P.Y;
   const unsigned long long n_items = P.count[P.bucket];
   const uint32_t* __restrict__ order = P.order + P.start[P.bucket];
-  // this warp's rows: [r][HQ | H]
-  const uint32_t wrows = L.rows + 2u * kFastRows * L.row_bytes * warp;
+  // this warp's buffers: [band buffer | block buffer]; pinned so that they live in registers through the loops
+  const uint32_t mbuf = pin(sb + L.warps + L.warp_bytes * warp);
+  const uint32_t wbuf = pin(mbuf + L.mbuf_bytes);
+  const uint32_t yPerm = pin(sb + L.yPerm), yB2 = pin(sb + L.yB2), yC = pin(sb + L.yC), yLev = pin(sb + L.yLev);
+  const uint32_t yUp = pin(sb + L.yUp), yDn = pin(sb + L.yDn);
   unsigned long long item = 0, item_end = 0;  // the CTA's current run of queue positions
+#ifdef FAST_PROF
+  long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long prof_gwait = 0;
+  const long long prof_t00 = clock64();
+#endif
 
   for (;;) {
     __syncthreads();  // previous group fully retired (also orders the tab fill on the first trip)
@@ -131,7 +190,7 @@ __global__ void __launch_bounds__(32 * kFastMaxWarps, 1) stem_fast_kernel(const 
           const uint32_t k = order[item + g];
           const RecDev rx = X.rec[P.xi[k]];
           PairSlot ps;
-          ps.k = k; ps.N = rx.N; ps.node0 = rx.node0; ps.coff0 = rx.coff0; ps.blk0 = rx.blk0; ps.nblk = rx.nblk; ps.plr = rx.plr;
+          ps.k = k; ps.N = rx.N; ps.node0 = rx.node0; ps.blk0 = rx.blk0; ps.nblk = rx.nblk; ps.plr = rx.plr;
           s_slot[g] = ps;
           maxblk = max(maxblk, rx.nblk);
           ++g;
@@ -148,205 +207,373 @@ __global__ void __launch_bounds__(32 * kFastMaxWarps, 1) stem_fast_kernel(const 
     if (g == 0) break;
     const RecDev ry = Y.rec[P.yi[order[s_item]]];
     const uint32_t Ny = ry.N;
-    const uint32_t NYS = (Ny + 1u) & ~1u;  // row stride of the G0 slabs
+    const uint32_t NYS = (Ny + 1u) & ~1u;  // row stride of the G0 slabs (even: rows are 16-byte aligned)
     const uint32_t n_tickets = g * s_maxblk;
+    const uint32_t dmy = 8u * R * Ny;      // byte offset of the dummy column in the block buffer
 
     // ---- stage the y record, clear the row flags
     for (uint32_t j = tid; j < Ny; j += blockDim.x) {
       const uint32_t gy = ry.node0 + j;
-      const double ys2 = Y.s2[gy], yup = Y.up[gy];
-      sts_v2f64(sb + (L.yD0 + 16 * j), make_double2(ys2, Y.el[gy]));
-      sts_v2f64(sb + (L.yD1 + 16 * j), make_double2(yup * (Y.a[gy] * ys2), yup));   // H = up*a*s2 * sum(H children) (+ up*M)
-      sts_v2f64(sb + (L.yD2 + 16 * j), make_double2(Y.paths[gy], Y.bfreq[gy]));
-      sts_f64(sb + (L.yD3 + 8 * j), Y.dn[gy]);
-      sts_nodei(sb + (L.yI + 8 * j), Y.nodei[gy]);
+      const double ys2 = Y.s2[gy], yup = Y.up[gy], ydn = Y.dn[gy];
+      const NodeI ni = Y.nodei[gy];
+      const double coef = yup * (Y.a[gy] * ys2);   // H = up*a*s2 * sum(H children) (+ up*M)
+      sts_v4u32(yB2 + 16 * j, make_uint4(ni.e4_bcode, (uint32_t)ni.deg4 | ((uint32_t)ni.len << 16),
+                                         (uint32_t)__double2loint(coef), (uint32_t)__double2hiint(coef)));
+      sts_v2f64(sb + (L.yB1a + 16 * j), make_double2(ys2, Y.el[gy]));
+      sts_v2f64(sb + (L.yB1b + 16 * j), make_double2(Y.bfreq[gy] * yup, Y.paths[gy] * ydn));
+      sts_f64(yUp + 8 * j, yup);
+      sts_f64(yDn + 8 * j, ydn);
+      sts_u32(yPerm + 4 * j, Y.lperm[gy]);
     }
+    if (tid < 2u) { sts_f64(yUp + 8 * (Ny + tid), 0.0); sts_f64(yDn + 8 * (Ny + tid), 0.0); }   // read in pairs
     {
-      const uint2* __restrict__ src = reinterpret_cast<const uint2*>(Y.c16 + ry.c16_0);  // c16_0 is a multiple of 4
-      for (uint32_t e = tid; e < ry.e4 / 4u; e += blockDim.x) sts_v2u32(sb + (L.yC + 8 * e), src[e]);
+      const uint16_t* __restrict__ src = Y.c16 + ry.c16_0;
+      for (uint32_t e = tid; e < ry.e4; e += blockDim.x) sts_u32(yC + 4 * e, R * (uint32_t)src[e]);
     }
-    for (uint32_t l = tid; l <= ry.nlev; l += blockDim.x) sts_u32(sb + (L.yLev + 4 * l), Y.lev_off[ry.lev0 + l]);
+    for (uint32_t l = tid; l <= ry.nlev; l += blockDim.x) sts_u32(yLev + 4 * l, Y.lev_off[ry.lev0 + l]);
     for (uint32_t i = tid; i < (g * P.nx_cap + 3u) / 4u; i += blockDim.x) sts_u32(sb + (L.done + 4 * i), 0u);
-    // the dummy column of every row of this warp
-    if (lane < 2u * kFastRows) sts_f64(sb + (wrows + L.row_bytes * lane + 8u * Ny), 0.0);
+    // the dummy column (and the pad after it) of this warp's block buffer
+    if (lane < 2u * R) sts_f64(wbuf + dmy + 8u * lane, 0.0);
     __syncthreads();
 
     for (;;) {
       // tickets interleave the pairs of the group block by block; a pair's own blocks keep their order, which is
       // all the dependencies need (a block only waits for earlier blocks of the same pair)
+      PROF_T(t_0);
       uint32_t t = 0;
       if (lane == 0) t = atomicAdd(&s_next_blk, 1u);
       t = __shfl_sync(0xffffffffu, t, 0);
       if (t >= n_tickets) break;
+      PROF_T(t_tk);
+      PROF_ADD(7, t_0, t_tk);
       const uint32_t sl = t % g, b = t / g;
       const PairSlot ps = s_slot[sl];
       if (b >= ps.nblk) continue;
-      const uint32_t blk = kFastRows == 1u ? (b | (1u << 16)) : X.blk[ps.blk0 + b];   // one row per block: block b = row b
-      const uint32_t i0 = blk & 0xffffu, cnt = blk >> 16;  // cnt in 1..kFastRows
+      const uint32_t blk = R == 1u ? (b | (1u << 16)) : X.blk[ps.blk0 + b];   // one row per block: block b = row b
+      const uint32_t i0 = blk & 0xffffu, cnt = blk >> 16;  // cnt in 1..R
       double* __restrict__ G0 = slab + sl * slot_stride;
-      const uint32_t done = L.done + sl * P.nx_cap;
+      const uint32_t done = sb + L.done + sl * P.nx_cap;
       double* __restrict__ rowacc = P.rowacc + ((size_t)blockIdx.x * kGroup + sl) * P.nx_cap;
+      uint32_t len_lo_blk = 0xffffffffu;   // the lowest window bound over the rows of the block
 
-      // ---- phase A: HQ(r,:) = up_y * s2_x(i) * sum over inner pairs c of G0s(c,:)
-      for (uint32_t r = 0; r < cnt; ++r) {
+      for (uint32_t r = 0; r < R; ++r) {
+        const uint32_t rb = wbuf + 8u * r;   // element (r, j) of the block buffer sits at rb + 8*R*j
+        if (r >= cnt) {   // a short block
+#if STEMK_B2MAP == 0
+          for (uint32_t j = lane; j <= Ny; j += 32u) sts_f64(rb + 8u * R * j, 0.0);   // the sweep touches every row
+#endif
+          continue;
+        }
+        PROF_T(t_a0);
         const uint32_t i = i0 + r;
-        const uint32_t hq = wrows + 2u * L.row_bytes * r;
         const XNode* __restrict__ xn = X.xnode + ps.node0 + i;   // one 64-byte line, the same address for every lane
-        const uint4 xi4 = __ldg(reinterpret_cast<const uint4*>(xn) + 3);
-        const uint32_t e0 = xi4.x, e1 = xi4.y;
-        const double xs2 = __ldg(&xn->s2);
+        const double2 x01 = __ldg(reinterpret_cast<const double2*>(xn));       // {s2, a}
+        const double2 x23 = __ldg(reinterpret_cast<const double2*>(xn) + 1);   // {up, ql}
+        const double2 x45 = __ldg(reinterpret_cast<const double2*>(xn) + 2);   // {bfreq, paths}
+        const uint4 xi4 = __ldg(reinterpret_cast<const uint4*>(xn) + 3);       // {e0, e1, len, bcode}
+        const uint32_t e0 = xi4.x, e1 = xi4.y, xl = xi4.z, xbc = xi4.w;
+        const double xs2 = x01.x, pc = x23.x * x01.y;   // pc = up_x * a_x
+        double* __restrict__ g0row = G0 + (size_t)i * NYS;
+        const uint32_t len_lo = (band != 0u && xl > band) ? xl - band : 0u;
+        len_lo_blk = min(len_lo_blk, len_lo);
+
+        // ---- phase A: q = sum over inner pairs c of G0s(c,:);  HQ = up_y*s2_x*q -> buffer, up_x*a_x*s2_x*q -> slab
         for (uint32_t eb = e0; eb < e1 || eb == e0; eb += 32u) {
           const uint32_t ne = min(32u, e1 - eb);
           const bool last = eb + 32u >= e1;
-          uint32_t off_l = 0u;
-          if (lane < ne) {
-            const uint32_t c = X.cidx[eb + lane];
-            off_l = c * NYS;
-            #ifndef ABL_NO_WAIT
-            while (ld_flag_f(sb + done + c) == 0u) __nanosleep(32);
-#endif  // wait until that row is published
-          }
-          __syncwarp();
+          const bool more = eb != e0;
+          PROF_T(t_w0);
+          uint32_t c = 0u;
+          if (lane < ne) c = X.cidx[eb + lane];
+          const uint32_t off_l = c * NYS;
+          // wait until the rows of all inner pairs are published (one poll per lane and round, the whole warp sleeps)
+#ifndef ABL_NO_WAIT
+          while (!__all_sync(0xffffffffu, lane >= ne || ld_flag_f(done + c) != 0u)) __nanosleep(64);
+#endif
           __threadfence_block();  // acquire: the G0 rows behind the flags just seen
+          PROF_T(t_w1);
+          PROF_ADD(6, t_w0, t_w1);
 #ifndef STEMK_NO_PREFETCH
-          // The slabs of all CTAs together are several times the L2, so about half of these rows come from
-          // DRAM: ask for every 128-byte line of every child row at once instead of discovering the misses
-          // sixteen loads at a time.
+          // The slabs of all CTAs together are several times the L2, so part of these rows come from DRAM: ask for
+          // every 128-byte line of every child row at once instead of discovering the misses a few loads at a time.
           for (uint32_t tt = 0; tt < ne; ++tt) {
             const double* __restrict__ src = G0 + __shfl_sync(0xffffffffu, off_l, tt);
             for (uint32_t ln = lane * 16u; ln < Ny; ln += 512u) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + ln));
           }
 #endif
-          for (uint32_t jb = 0; jb < Ny; jb += 128u) {  // uniform trip count: the shuffles below need every lane
-            const uint32_t j = jb + lane;
-            const bool v0 = j < Ny, v1 = j + 32u < Ny, v2 = j + 64u < Ny, v3 = j + 96u < Ny;
-            const bool more = eb != e0;
-            double q0 = (v0 && more) ? lds_f64(sb + (hq + 8u * j)) : 0.0;
-            double q1 = (v1 && more) ? lds_f64(sb + (hq + 8u * (j + 32u))) : 0.0;
-            double q2 = (v2 && more) ? lds_f64(sb + (hq + 8u * (j + 64u))) : 0.0;
-            double q3 = (v3 && more) ? lds_f64(sb + (hq + 8u * (j + 96u))) : 0.0;
-#pragma unroll 4
-            for (uint32_t tt = 0; tt < ne; ++tt) {
-              const double* __restrict__ src = G0 + __shfl_sync(0xffffffffu, off_l, tt) + j;
-#ifndef ABL_NO_A
-              if (v0) q0 += __ldcg(src);
-              if (v1) q1 += __ldcg(src + 32);
-              if (v2) q2 += __ldcg(src + 64);
-              if (v3) q3 += __ldcg(src + 96);
+          for (uint32_t jb = 0; jb < Ny; jb += 256u) {  // uniform trip count: the shuffles below need every lane
+            const uint32_t j = jb + 2u * lane;           // this lane: columns j, j+1 of four 64-column chunks
+            const bool v0 = j < Ny, v1 = j + 64u < Ny, v2 = j + 128u < Ny, v3 = j + 192u < Ny;
+            double2 q0 = make_double2(0.0, 0.0), q1 = q0, q2 = q0, q3 = q0;
+            if (more) {
+              if (v0) { q0.x = lds_f64(rb + 8u * R * j); q0.y = lds_f64(rb + 8u * R * (j + 1u)); }
+              if (v1) { q1.x = lds_f64(rb + 8u * R * (j + 64u)); q1.y = lds_f64(rb + 8u * R * (j + 65u)); }
+              if (v2) { q2.x = lds_f64(rb + 8u * R * (j + 128u)); q2.y = lds_f64(rb + 8u * R * (j + 129u)); }
+              if (v3) { q3.x = lds_f64(rb + 8u * R * (j + 192u)); q3.y = lds_f64(rb + 8u * R * (j + 193u)); }
+            }
+            // two inner pairs x four column chunks per round: eight independent 16-byte loads in flight per lane
+#pragma unroll 1
+#ifdef ABL_NO_A
+            for (uint32_t tt = 0; tt < 0u; tt += 2u) {
 #else
-              q0 += (double)(size_t)src * 1e-300;
+            for (uint32_t tt = 0; tt < ne; tt += 2u) {
 #endif
+              const double2* __restrict__ s0 = reinterpret_cast<const double2*>(G0 + __shfl_sync(0xffffffffu, off_l, tt) + j);
+              const double2* __restrict__ s1 = reinterpret_cast<const double2*>(G0 + __shfl_sync(0xffffffffu, off_l, (tt + 1u) & 31u) + j);
+              const bool c1 = tt + 1u < ne;
+              const double2 z = make_double2(0.0, 0.0);
+              double2 t00 = z, t01 = z, t02 = z, t03 = z, t10 = z, t11 = z, t12 = z, t13 = z;
+              if (v0) t00 = __ldcg(s0);
+              if (v1) t01 = __ldcg(s0 + 32);
+              if (v2) t02 = __ldcg(s0 + 64);
+              if (v3) t03 = __ldcg(s0 + 96);
+              if (v0 && c1) t10 = __ldcg(s1);
+              if (v1 && c1) t11 = __ldcg(s1 + 32);
+              if (v2 && c1) t12 = __ldcg(s1 + 64);
+              if (v3 && c1) t13 = __ldcg(s1 + 96);
+              q0.x += t00.x + t10.x; q0.y += t00.y + t10.y;
+              q1.x += t01.x + t11.x; q1.y += t01.y + t11.y;
+              q2.x += t02.x + t12.x; q2.y += t02.y + t12.y;
+              q3.x += t03.x + t13.x; q3.y += t03.y + t13.y;
             }
-            if (last) {  // scale: HQ = up_y(j) * (s2_x * sum)
-              if (v0) q0 = lds_v2f64(sb + (L.yD1 + 16u * j)).y * (xs2 * q0);
-              if (v1) q1 = lds_v2f64(sb + (L.yD1 + 16u * (j + 32u))).y * (xs2 * q1);
-              if (v2) q2 = lds_v2f64(sb + (L.yD1 + 16u * (j + 64u))).y * (xs2 * q2);
-              if (v3) q3 = lds_v2f64(sb + (L.yD1 + 16u * (j + 96u))).y * (xs2 * q3);
+            if (last) {
+              // the second column of a pair may be the slab row's pad (j + 1 == Ny, Ny odd): its value is never used
+              if (v0) { const double2 u = lds_v2f64(yUp + 8u * j); const double sx = xs2 * q0.x, sy = xs2 * q0.y;
+                        *reinterpret_cast<double2*>(g0row + j) = make_double2(pc * sx, pc * sy); q0 = make_double2(u.x * sx, u.y * sy); }
+              if (v1) { const double2 u = lds_v2f64(yUp + 8u * (j + 64u)); const double sx = xs2 * q1.x, sy = xs2 * q1.y;
+                        *reinterpret_cast<double2*>(g0row + j + 64u) = make_double2(pc * sx, pc * sy); q1 = make_double2(u.x * sx, u.y * sy); }
+              if (v2) { const double2 u = lds_v2f64(yUp + 8u * (j + 128u)); const double sx = xs2 * q2.x, sy = xs2 * q2.y;
+                        *reinterpret_cast<double2*>(g0row + j + 128u) = make_double2(pc * sx, pc * sy); q2 = make_double2(u.x * sx, u.y * sy); }
+              if (v3) { const double2 u = lds_v2f64(yUp + 8u * (j + 192u)); const double sx = xs2 * q3.x, sy = xs2 * q3.y;
+                        *reinterpret_cast<double2*>(g0row + j + 192u) = make_double2(pc * sx, pc * sy); q3 = make_double2(u.x * sx, u.y * sy); }
             }
-            if (v0) sts_f64(sb + (hq + 8u * j), q0);
-            if (v1) sts_f64(sb + (hq + 8u * (j + 32u)), q1);
-            if (v2) sts_f64(sb + (hq + 8u * (j + 64u)), q2);
-            if (v3) sts_f64(sb + (hq + 8u * (j + 96u)), q3);
+            // (column Ny of the buffer is the dummy column: never written here)
+            if (v0) { sts_f64(rb + 8u * R * j, q0.x); if (j + 1u < Ny) sts_f64(rb + 8u * R * (j + 1u), q0.y); }
+            if (v1) { sts_f64(rb + 8u * R * (j + 64u), q1.x); if (j + 65u < Ny) sts_f64(rb + 8u * R * (j + 65u), q1.y); }
+            if (v2) { sts_f64(rb + 8u * R * (j + 128u), q2.x); if (j + 129u < Ny) sts_f64(rb + 8u * R * (j + 129u), q2.y); }
+            if (v3) { sts_f64(rb + 8u * R * (j + 192u), q3.x); if (j + 193u < Ny) sts_f64(rb + 8u * R * (j + 193u), q3.y); }
           }
           if (e1 == e0) break;
         }
-      }
-      __syncwarp();
+        __syncwarp();
+        PROF_T(t_a1);
+        PROF_ADD(1, t_a0, t_a1);
 
-      // ---- phase B: sweep the y DAG level by level; lanes <-> (row r, node slot s)
-      // rows of the block rounded up to 1, 2, 4: lane = row * nslot + slot (all compile-time for one row per warp)
-      const uint32_t rsh = kFastRows == 1u ? 0u : (cnt > 2u ? 2u : (cnt > 1u ? 1u : 0u));
-      const uint32_t nslot = 32u >> rsh;
-      const uint32_t r_raw = lane >> (5u - rsh), slot = lane & (nslot - 1u);
-      const bool live = kFastRows == 1u ? true : r_raw < cnt;
-      const uint32_t r = live ? r_raw : 0u;
-      const uint32_t gx = ps.node0 + i0 + r;
-      const XNode* __restrict__ xr = X.xnode + gx;
-      const double2 x12 = __ldg(reinterpret_cast<const double2*>(xr) + 1), x22 = __ldg(reinterpret_cast<const double2*>(xr) + 2);
-      const uint4 xr4 = __ldg(reinterpret_cast<const uint4*>(xr) + 3);
-      const double xql = x12.y, xbf = x22.x, xpaths = x22.y;
-      const uint32_t xl = xr4.z, xbc = xr4.w;
-      const uint32_t hqrow = wrows + 2u * L.row_bytes * r, hrow = hqrow + L.row_bytes;
-      // MATCH needs |len_x - len_y| <= band; below the window G1 is identically 0 (length-monotone DAG)
-      const uint32_t len_lo = (band != 0u && xl > band) ? xl - band : 0u;
-      const uint32_t len_hi = band != 0u ? xl + band : 0xffffffffu;
-      double racc = 0.0;
-      uint32_t jbeg = lds_u32(sb + (L.yLev));
-#ifdef ABL_NO_B
-      for (uint32_t ly = 0; ly < 1; ++ly) {
+        // ---- phase B1: MATCH on the y nodes inside the band of row i (a range of the length-sorted node list)
+        uint32_t lo = 0u, hi = Ny;
+        if (band != 0u) {
+          lo = xl > band ? count_len_below(yPerm, Ny, xl - band, lane) : 0u;
+          hi = count_len_below(yPerm, Ny, xl + band + 1u, lane);
+        }
+        {
+          const double xql = x23.y, xbf = x45.x;
+          const uint32_t tabx = sb + L.tab + 128u * xbc;
+          double racc = 0.0;
+#ifdef ABL_NO_B1
+          for (uint32_t tq = lo + lane; tq < lo; tq += 32u) {
 #else
-      for (uint32_t ly = 0; ly < ry.nlev; ++ly) {
+          for (uint32_t tq = lo + lane; tq < hi; tq += 32u) {
 #endif
-        const uint32_t jend = lds_u32(sb + (L.yLev + 4u * ly + 4u));
-        for (uint32_t j = jbeg + slot; live && j < jend; j += nslot) {
-          const NodeI ni = lds_nodei(sb + (L.yI + 8u * j));
-          const uint32_t yl = ni.len;
-          if (yl < len_lo) {  // G1 == 0 here and below
-            sts_f64(sb + (hrow + 8u * j), 0.0);
-            continue;
-          }
-          const bool in_band = yl <= len_hi;
-          const double2 d1 = lds_v2f64(sb + (L.yD1 + 16u * j));  // {up*a*s2, up}
-          uint32_t e = L.yC + 2u * (ni.e4_bcode >> 8);
-          const uint32_t eend = e + 8u * ni.deg4;
-          double S0 = 0.0, S1 = 0.0, m = 0.0;
-          if (in_band) {
+            const uint32_t j = lds_u32(yPerm + 4u * tq) & 0xffffu;
+            const uint4 rec = lds_v4u32(yB2 + 16u * j);
+            const double2 ya = lds_v2f64(sb + L.yB1a + 16u * j);   // {s2_y, el_y}
+            const double2 yb = lds_v2f64(sb + L.yB1b + 16u * j);   // {bfreq_y*up_y, paths_y*dn_y}
+            const double tv = lds_f64(tabx + 8u * (rec.x & 0xffu));
+            uint32_t e = yC + 4u * (rec.x >> 8);
+            const uint32_t eend = e + 16u * (rec.y & 0xffffu);
             double R0 = 0.0, R1 = 0.0;
 #pragma unroll 1
-            for (; e < eend; e += 8u) {
-              const uint2 c4 = lds_v2u32(sb + (e));
-              const uint32_t o0 = c4.x & 0xffffu, o1 = c4.x >> 16, o2 = c4.y & 0xffffu, o3 = c4.y >> 16;
-              S0 += lds_f64(sb + (hrow + o0)); R0 += lds_f64(sb + (hqrow + o0));
-              S1 += lds_f64(sb + (hrow + o1)); R1 += lds_f64(sb + (hqrow + o1));
-              S0 += lds_f64(sb + (hrow + o2)); R0 += lds_f64(sb + (hqrow + o2));
-              S1 += lds_f64(sb + (hrow + o3)); R1 += lds_f64(sb + (hqrow + o3));
+            for (; e < eend; e += 16u) {
+              const uint4 c4 = lds_v4u32(e);
+              R0 += lds_f64(rb + c4.x) + lds_f64(rb + c4.y);
+              R1 += lds_f64(rb + c4.z) + lds_f64(rb + c4.w);
             }
-            const double2 d0 = lds_v2f64(sb + (L.yD0 + 16u * j));  // {s2_y, el_y}
-            const double2 d2 = lds_v2f64(sb + (L.yD2 + 16u * j));  // {paths_y, bfreq_y}
-            const double vs = lds_f64(sb + (L.tab + 8u * (xbc * 16u + (ni.e4_bcode & 0xffu)))) * xbf * d2.y;
-            m = vs * fma(d0.y, xql, d0.x * (R0 + R1));
-            racc = fma(d2.x, m, racc);
-          } else {
-#pragma unroll 1
-            for (; e < eend; e += 8u) {
-              const uint2 c4 = lds_v2u32(sb + (e));
-              S0 += lds_f64(sb + hrow + (c4.x & 0xffffu));
-              S1 += lds_f64(sb + hrow + (c4.x >> 16));
-              S0 += lds_f64(sb + hrow + (c4.y & 0xffffu));
-              S1 += lds_f64(sb + hrow + (c4.y >> 16));
-            }
+            const double vs = tv * xbf * yb.x;
+            const double mp = vs * fma(ya.y, xql, ya.x * (R0 + R1));   // up_y * M(i,j)
+            racc = fma(yb.y, mp, racc);
+            sts_f64(mbuf + 8u * (tq - lo), mp);
           }
-          sts_f64(sb + (hrow + 8u * j), fma(d1.x, S0 + S1, d1.y * m));   // up_y * (M + a_y*s2_y*sum)
+          racc = warp_sum_all(racc);
+          if (lane == 0) rowacc[i] = x45.y * racc;   // per-row slot in global scratch (L2)
         }
-        jbeg = jend;
         __syncwarp();
+        // ---- Z: the row's part of the buffer becomes the H row: zero, then the band's up_y*M
+        for (uint32_t j = lane; j <= Ny; j += 32u) sts_f64(rb + 8u * R * j, 0.0);
+        __syncwarp();
+        for (uint32_t tq = lo + lane; tq < hi; tq += 32u)
+          sts_f64(rb + 8u * R * (lds_u32(yPerm + 4u * tq) & 0xffffu), lds_f64(mbuf + 8u * (tq - lo)));
+        __syncwarp();
+        PROF_T(t_b1);
+        PROF_ADD(2, t_a1, t_b1);
       }
-      // per-row path-weighted MATCH sum (lanes of one row are contiguous: reduce inside the half / full warp)
 
-      for (uint32_t o = nslot >> 1; o > 0u; o >>= 1) racc += __shfl_xor_sync(0xffffffffu, racc, o);
-      if (slot == 0u && live) rowacc[i0 + r] = xpaths * racc;   // per-row slot in global scratch (L2)
-
-      // ---- phase C: finished rows G0s(i,:) = up_x(i) * dn_y * (H + a_x*HQ), then publish them
-      for (uint32_t rr = 0; rr < cnt; ++rr) {
-        const uint32_t i = i0 + rr;
-        const uint32_t hq2 = wrows + 2u * L.row_bytes * rr, h2 = hq2 + L.row_bytes;
-        const XNode* __restrict__ xc = X.xnode + ps.node0 + i;
-        const double xa2 = __ldg(&xc->a), xup = __ldg(&xc->up);
-        double* __restrict__ g0row = G0 + (size_t)i * NYS;
-#ifdef ABL_NO_C
-        for (uint32_t j = lane; j < 32u; j += 32u)
+#if STEMK_B2MAP == 1
+      // ---- phase B2: sweep the y DAG level by level; lanes <-> (node slot, row of the block): the R lanes of a slot
+      // read R consecutive doubles of the interleaved buffer, and share the slot's node record and index loads
+      PROF_T(t_b2a);
+      {
+        constexpr uint32_t nslot = 32u / R;
+        const uint32_t r = lane % R, slot = lane / R;
+        const bool live = r < cnt;
+        const uint32_t xl = __ldg(&X.xnode[ps.node0 + i0 + (live ? r : 0u)].len);
+        // below the window (len_y + band < len_x) G1 is identically 0: length-monotone DAG
+        const uint32_t len_lo = (band != 0u && xl > band) ? xl - band : 0u;
+        const uint32_t rbase = wbuf + 8u * r;
+        uint32_t jbeg = lds_u32(yLev);
+#ifdef ABL_NO_B2
+        for (uint32_t ly = 0; ly < 1u; ++ly) {
 #else
-        for (uint32_t j = lane; j < Ny; j += 32u)
+        for (uint32_t ly = 0; ly < ry.nlev; ++ly) {
 #endif
-          g0row[j] = xup * (lds_f64(sb + (L.yD3 + 8u * j)) * fma(xa2, lds_f64(sb + (hq2 + 8u * j)), lds_f64(sb + (h2 + 8u * j))));
+          const uint32_t jend = lds_u32(yLev + 4u * ly + 4u);
+          for (uint32_t j = jbeg + slot; live && j < jend; j += nslot) {
+            const uint4 rec = lds_v4u32(yB2 + 16u * j);
+            if ((rec.y >> 16) < len_lo) break;   // nodes of a level are sorted by length, longest first
+            const uint32_t e = yC + 4u * (rec.x >> 8);
+            const uint32_t n4 = rec.y & 0xffffu;
+            const uint32_t hj0 = rbase + 8u * R * j;
+            const double hold = lds_f64(hj0);
+            // the first three rounds of four children are straight-line code: index loads first, then the gathers
+            // (lanes with fewer children read the all-zero dummy column), so that their latencies overlap
+            uint4 ca = make_uint4(dmy, dmy, dmy, dmy), cb = ca, cc = ca;
+            if (n4 > 0u) ca = lds_v4u32(e);
+            if (n4 > 1u) cb = lds_v4u32(e + 16u);
+            if (n4 > 2u) cc = lds_v4u32(e + 32u);
+            double S0 = lds_f64(rbase + ca.x) + lds_f64(rbase + ca.y);
+            double S1 = lds_f64(rbase + ca.z) + lds_f64(rbase + ca.w);
+            if (n4 > 1u) {
+              S0 += lds_f64(rbase + cb.x) + lds_f64(rbase + cb.y);
+              S1 += lds_f64(rbase + cb.z) + lds_f64(rbase + cb.w);
+            }
+            if (n4 > 2u) {
+              S0 += lds_f64(rbase + cc.x) + lds_f64(rbase + cc.y);
+              S1 += lds_f64(rbase + cc.z) + lds_f64(rbase + cc.w);
+#pragma unroll 1
+              for (uint32_t k = 3u; k < n4; ++k) {
+                const uint4 c4 = lds_v4u32(e + 16u * k);
+                S0 += lds_f64(rbase + c4.x) + lds_f64(rbase + c4.y);
+                S1 += lds_f64(rbase + c4.z) + lds_f64(rbase + c4.w);
+              }
+            }
+            sts_f64(hj0, fma(__hiloint2double((int)rec.w, (int)rec.z), S0 + S1, hold));   // up_y*M + up_y*a_y*s2_y*sum
+          }
+          jbeg = jend;
+          __syncwarp();
+        }
+      }
+#else
+      // ---- phase B2: sweep the y DAG level by level; lanes <-> nodes of the level, every lane carries all rows
+      PROF_T(t_b2a);
+      {
+        // below the window (len_y + band < len_x) G1 is identically 0: length-monotone DAG.  A row whose own window
+        // starts above the block's gets zeros there by itself (its buffer is zero below its window).
+        uint32_t jbeg = lds_u32(yLev);
+        for (uint32_t ly = 0; ly < ry.nlev; ++ly) {
+          const uint32_t jend = lds_u32(yLev + 4u * ly + 4u);
+          for (uint32_t jj = jbeg; jj < jend; jj += 32u) {   // uniform
+            const uint32_t j = jj + lane;
+            uint4 rec = make_uint4(0u, 0u, 0u, 0u);
+            if (j < jend) rec = lds_v4u32(yB2 + 16u * j);
+            const bool act = j < jend && (rec.y >> 16) >= len_lo_blk;   // nodes of a level: longest first
+            const uint32_t n4 = act ? (rec.y & 0xffffu) : 0u;
+            const uint32_t vote = __ballot_sync(0xffffffffu, act);
+            if (vote == 0u) break;
+            const uint32_t m = __reduce_max_sync(0xffffffffu, n4);   // rounds of four children the warp needs
+            const uint32_t e = yC + 4u * (rec.x >> 8);
+            double S[R];
+#pragma unroll
+            for (uint32_t h = 0; h < R; ++h) S[h] = 0.0;
+            const uint4 dz = make_uint4(dmy, dmy, dmy, dmy);
+            if (m != 0u) {
+              // the first three rounds are straight-line code (index loads first, then the gathers); lanes with
+              // fewer children read the all-zero dummy column
+              uint4 ca = dz, cb = dz, cc = dz;
+              if (n4 > 0u) ca = lds_v4u32(e);
+              if (m > 1u && n4 > 1u) cb = lds_v4u32(e + 16u);
+              if (m > 2u && n4 > 2u) cc = lds_v4u32(e + 32u);
+              gather4(wbuf, ca, S);
+              if (m > 1u) gather4(wbuf, cb, S);
+              if (m > 2u) gather4(wbuf, cc, S);
+              for (uint32_t k = 3u; k < m; ++k) {
+                uint4 cd = dz;
+                if (n4 > k) cd = lds_v4u32(e + 16u * k);
+                gather4(wbuf, cd, S);
+              }
+            }
+            if (act) {
+              const double coef = __hiloint2double((int)rec.w, (int)rec.z);
+              const uint32_t hj = wbuf + 8u * R * j;
+              if (R == 1) {
+                sts_f64(hj, fma(coef, S[0], lds_f64(hj)));   // up_y*M + up_y*a_y*s2_y*sum
+              } else {
+#pragma unroll
+                for (uint32_t h = 0; h < R; h += 2u) {
+                  const double2 old = lds_v2f64(hj + 8u * h);
+                  sts_v2f64(hj + 8u * h, make_double2(fma(coef, S[h], old.x), fma(coef, S[h + 1u], old.y)));
+                }
+              }
+            }
+            if (vote != 0xffffffffu) break;   // the window of this level ended inside this chunk
+          }
+          jbeg = jend;
+          __syncwarp();
+        }
+      }
+#endif
+      PROF_T(t_b2b);
+      PROF_ADD(3, t_b2a, t_b2b);
+
+      // ---- phase C: G0s(i,:) += up_x * dn_y * H(i,:), then publish the rows
+#ifdef ABL_NO_C
+      for (uint32_t rr = 0; rr < 0u; ++rr) {
+#else
+      for (uint32_t rr = 0; rr < cnt; ++rr) {
+#endif
+        const uint32_t i = i0 + rr;
+        const uint32_t rb = wbuf + 8u * rr;
+        const double xup = __ldg(&X.xnode[ps.node0 + i].up);
+        double* __restrict__ g0row = G0 + (size_t)i * NYS;
+        for (uint32_t jb = 0; jb < Ny; jb += 512u) {
+          // eight 64-column chunks per trip: every read of the slab is issued before the first use
+          const uint32_t j = jb + 2u * lane;
+          double2 hv[8], ov[8];
+          bool wv[8];
+          double2* __restrict__ gp = reinterpret_cast<double2*>(g0row + j);
+#pragma unroll
+          for (uint32_t k = 0; k < 8u; ++k) {
+            // column Ny of the buffer is the dummy column (zero), so the second element of the last pair is harmless
+            hv[k] = make_double2(0.0, 0.0);
+            if (j + 64u * k < Ny) { hv[k].x = lds_f64(rb + 8u * R * (j + 64u * k)); hv[k].y = lds_f64(rb + 8u * R * (j + 64u * k + 1u)); }
+            wv[k] = hv[k].x != 0.0 || hv[k].y != 0.0;
+          }
+#pragma unroll
+          for (uint32_t k = 0; k < 8u; ++k) { ov[k] = hv[k]; if (wv[k]) ov[k] = __ldcg(gp + 32u * k); }
+#pragma unroll
+          for (uint32_t k = 0; k < 8u; ++k)
+            if (wv[k]) {
+              const double2 d = lds_v2f64(yDn + 8u * (j + 64u * k));
+              gp[32u * k] = make_double2(fma(xup, d.x * hv[k].x, ov[k].x), fma(xup, d.y * hv[k].y, ov[k].y));
+            }
+        }
       }
       __threadfence_block();
       __syncwarp();
-      if (lane < cnt) asm volatile("st.volatile.shared.u8 [%0], %1;" ::"r"(sb + done + i0 + lane), "r"(1u) : "memory");
+      if (lane < cnt) asm volatile("st.volatile.shared.u8 [%0], %1;" ::"r"(done + i0 + lane), "r"(1u) : "memory");
+      PROF_T(t_c);
+      PROF_ADD(4, t_b2b, t_c);
+      PROF_ADD(0, t_0, t_c);
+#ifdef FAST_PROF
+      if (lane == 0) prof_acc[5] += cnt;
+#endif
     }
 
     // ---- fixed-order sum of the per-row slots, one warp per pair of the group
+    PROF_T(t_g0);
     __syncthreads();
+    PROF_T(t_g1);
+#ifdef FAST_PROF
+    if (lane == 0) prof_gwait += t_g1 - t_g0;
+#endif
     if (warp < g) {
       const PairSlot ps = s_slot[warp];
       double t = 0.0;
@@ -356,6 +583,14 @@ __global__ void __launch_bounds__(32 * kFastMaxWarps, 1) stem_fast_kernel(const 
       if (lane == 0) P.out[ps.k] = t + ps.plr * (double)ry.lr;
     }
   }
+#ifdef FAST_PROF
+  if (lane == 0 && P.prof)
+  {
+    for (int q = 0; q < 8; ++q) atomicAdd(P.prof + q, (unsigned long long)prof_acc[q]);
+    atomicAdd(P.prof + 8, (unsigned long long)prof_gwait);
+    atomicAdd(P.prof + 9, (unsigned long long)(clock64() - prof_t00));
+  }
+#endif
 }
 
 // ---- pair classification: which kernel / size bucket runs a pair -----------------------------------------
@@ -413,8 +648,9 @@ __global__ void bucket_fill_stable_kernel(const StemClassify C) {
 
 }  // namespace
 
-size_t stem_fast_smem_bytes(uint32_t nwarps, uint32_t nx_cap, uint32_t ny_cap, uint32_t e4_cap, uint32_t lev_cap) {
-  return fast_layout(nwarps, nx_cap, ny_cap, e4_cap, lev_cap).total;
+size_t stem_fast_smem_bytes(uint32_t nwarps, uint32_t nx_cap, uint32_t ny_cap, uint32_t e4_cap, uint32_t lev_cap,
+                            uint32_t band_cap) {
+  return fast_layout(nwarps, nx_cap, ny_cap, e4_cap, lev_cap, band_cap).total;
 }
 
 cudaError_t launch_stem_fast(const StemFastLaunch& p, int grid, int nwarps, size_t smem, cudaStream_t stream) {

@@ -61,10 +61,6 @@ struct stemk_ctx {
   DevBuf scratch, carry, tmp_stem, tmp_str, idx_x, idx_y, vals, matrix, order, rowacc;
   unsigned long long* d_bucket = nullptr;  // count[16] | start[16] | queue heads[16]
   int use_fast = 1;                        // STEMK_FAST=0 in the environment forces the general stem kernel
-  int use_rows = 0;                        // STEMK_ROWSK=1: the experimental row-block kernel (stem_rows.cu) instead of the one-row-per-warp fast kernel
-  int use_lanes = 0;                       // STEMK_LANES=1: the lanes-are-rows kernel (stem_lanes.cu); STEMK_LANES_R forces the block height
-  int lanes_r = 0;
-  int rows_tw = 4, rows_r = 0, rows_nt = 0; // STEMK_ROWS_TW / _R / _NT: warps per team, forced rows per block, team limit
   std::string err;
   // stats
   uint64_t launches = 0;
@@ -178,12 +174,6 @@ int stemk_create(stemk_ctx** out, const stemk_params* params, int device) {
   c->params = *params;
   make_tables(*params, &c->tables);
   if (const char* f = std::getenv("STEMK_FAST")) c->use_fast = std::atoi(f);
-  if (const char* f = std::getenv("STEMK_ROWSK")) c->use_rows = std::atoi(f);
-  if (const char* f = std::getenv("STEMK_LANES")) c->use_lanes = std::atoi(f);
-  if (const char* f = std::getenv("STEMK_LANES_R")) c->lanes_r = std::atoi(f);
-  if (const char* f = std::getenv("STEMK_ROWS_TW")) c->rows_tw = std::max(1, std::min(8, std::atoi(f)));
-  if (const char* f = std::getenv("STEMK_ROWS_R")) c->rows_r = std::atoi(f);
-  if (const char* f = std::getenv("STEMK_ROWS_NT")) c->rows_nt = std::atoi(f);
   bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaMalloc((void**)&c->d_pair_tab, sizeof(double) * 256) == cudaSuccess &&
             cudaMalloc((void**)&c->d_subst, sizeof(double) * 16) == cudaSuccess &&
@@ -226,7 +216,7 @@ int stemk_upload(stemk_ctx* ctx, const stemk_seqset_desc* desc, stemk_set** out)
   stemk_set* s = new stemk_set;
   s->device = ctx->device;
   const int n_threads = (int)std::min<unsigned>(16, std::max(1u, std::thread::hardware_concurrency()));
-  std::string err = compile_set(*desc, ctx->params.loop_gap, n_threads, &s->host);
+  std::string err = compile_set(*desc, ctx->params.loop_gap, ctx->params.len_band, n_threads, &s->host);
   if (!err.empty()) { delete s; return fail(ctx, STEMK_ERR_ARG, err); }
   const CompiledSet& h = s->host;
   if (ctx->device == STEMK_DEVICE_NONE) { *out = s; return STEMK_OK; }
@@ -238,7 +228,7 @@ int stemk_upload(stemk_ctx* ctx, const stemk_seqset_desc* desc, stemk_set** out)
                o_boff = place(off, h.boff), o_bab = place(off, h.bab), o_bfq = place(off, h.bfq),
                o_ccode = place(off, h.ccode), o_cw = place(off, h.cw), o_prof = place(off, h.prof),
                o_text = place(off, h.text), o_up = place(off, h.up), o_dn = place(off, h.dn), o_s2 = place(off, h.s2),
-               o_nodei = place(off, h.nodei), o_c16 = place(off, h.c16), o_blk = place(off, h.blk), o_xnode = place(off, h.xnode), o_yband = place(off, h.yband);
+               o_nodei = place(off, h.nodei), o_c16 = place(off, h.c16), o_blk = place(off, h.blk), o_xnode = place(off, h.xnode), o_lperm = place(off, h.lperm);
   off = (off + 255) & ~size_t(255);
   cudaError_t e = s->blob.reserve(std::max<size_t>(off, 256));
   // every array goes straight from its host vector to its place in the blob (no staging copy)
@@ -250,7 +240,7 @@ int stemk_upload(stemk_ctx* ctx, const stemk_seqset_desc* desc, stemk_set** out)
   put(o_bfreq, h.bfreq); put(o_len, h.len); put(o_bcode, h.bcode); put(o_coff, h.coff); put(o_cidx, h.cidx);
   put(o_ce, h.ce); put(o_lev, h.lev_off); put(o_boff, h.boff); put(o_bab, h.bab); put(o_bfq, h.bfq);
   put(o_ccode, h.ccode); put(o_cw, h.cw); put(o_prof, h.prof); put(o_text, h.text);
-  put(o_up, h.up); put(o_dn, h.dn); put(o_s2, h.s2); put(o_nodei, h.nodei); put(o_c16, h.c16); put(o_blk, h.blk); put(o_xnode, h.xnode); put(o_yband, h.yband);
+  put(o_up, h.up); put(o_dn, h.dn); put(o_s2, h.s2); put(o_nodei, h.nodei); put(o_c16, h.c16); put(o_blk, h.blk); put(o_xnode, h.xnode); put(o_lperm, h.lperm);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) { s->blob.release(); delete s; return cuda_fail(ctx, e, "set upload"); }
   char* b = static_cast<char*>(s->blob.p);
@@ -264,7 +254,7 @@ int stemk_upload(stemk_ctx* ctx, const stemk_seqset_desc* desc, stemk_set** out)
   v.bfq = (const double*)(b + o_bfq); v.ccode = (const uint8_t*)(b + o_ccode); v.cw = (const double*)(b + o_cw);
   v.prof = (const float*)(b + o_prof); v.text = (const uint8_t*)(b + o_text);
   v.up = (const double*)(b + o_up); v.dn = (const double*)(b + o_dn); v.s2 = (const double*)(b + o_s2);
-  v.nodei = (const NodeI*)(b + o_nodei); v.c16 = (const uint16_t*)(b + o_c16); v.blk = (const uint32_t*)(b + o_blk); v.xnode = (const XNode*)(b + o_xnode); v.yband = (const NodeB*)(b + o_yband);
+  v.nodei = (const NodeI*)(b + o_nodei); v.c16 = (const uint16_t*)(b + o_c16); v.blk = (const uint32_t*)(b + o_blk); v.xnode = (const XNode*)(b + o_xnode); v.lperm = (const uint32_t*)(b + o_lperm);
   *out = s;
   return STEMK_OK;
 }
@@ -315,8 +305,6 @@ int stemk_pairs_device(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, s
     // ---- classify: trivial pairs are finished, the others go to the general kernel (bucket 0) or to the fast
     // kernel's size buckets (1..), each bucket keeping the caller's pair order
     static const uint32_t kCaps[kMaxFastBuckets] = {256, 320, 384, 448, 512, 640, 768, kFastMaxN};
-    const bool lanes_mode = ctx->use_lanes != 0;
-    const bool rows_mode = ctx->use_rows != 0 && !lanes_mode;
     const bool any_fast = ctx->use_fast && x->host.n_fast > 0 && y->host.n_fast > 0;
     StemClassify C;
     C.X = x->view; C.Y = y->view; C.xi = d_xi; C.yi = d_yi; C.n_pairs = n_pairs; C.out = stem_out;
@@ -360,130 +348,24 @@ int stemk_pairs_device(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, s
       CU(le);
       ctx->launches += 1;
     }
-    // ---- row-block kernel, one launch per size bucket: as many teams as fit next to the staged record
-    for (int b = 0; rows_mode && b < C.n_caps; ++b) {
+    // ---- fast kernel, one launch per size bucket (shared memory and warps per CTA sized for the bucket)
+    for (int b = 0; any_fast && b < C.n_caps; ++b) {
       const uint32_t ny_cap = std::min(C.caps[b], std::max(1u, y->host.max_fastN));
       const uint32_t lo = b ? C.caps[b - 1] : 0u;
-      uint32_t e4_cap = 4;
+      uint32_t e4_cap = 4, band_cap = 1;
       bool any = false;
-      for (const RecDev& r : y->host.rec)
-        if ((r.flags & REC_FAST) && r.N > lo && r.N <= C.caps[b]) { e4_cap = std::max(e4_cap, r.e4); any = true; }
+      for (size_t r = 0; r < y->host.rec.size(); ++r) {
+        const RecDev& ry = y->host.rec[r];
+        if (!(ry.flags & REC_FAST) || ry.N <= lo || ry.N > C.caps[b]) continue;
+        e4_cap = std::max(e4_cap, ry.e4); band_cap = std::max(band_cap, y->host.band_cnt[r]); any = true;
+      }
       if (!any) continue;
-      const uint32_t xlev_cap = std::max(1u, x->host.max_nlev);
-      const size_t budget = std::min<size_t>(ctx->smem_optin, (size_t)227 * 1024) - 512;   // static shared memory
-      const uint32_t tw = (uint32_t)ctx->rows_tw;
-      auto teams_for = [&](uint32_t R) {
-        uint32_t nt = 0;
-        if ((ny_cap + 1u) * 8u * (R + 1u) > 65535u) return 0u;   // tile offsets are 16 bit
-        const uint32_t lim = std::min<uint32_t>(15u, (uint32_t)kRowsMaxThreads / (32u * tw));
-        while (nt < lim && stem_rows_smem_bytes(R, nt + 1, tw, nx_cap, ny_cap, e4_cap, lev_cap, xlev_cap) <= budget) ++nt;
-        if (ctx->rows_nt > 0) nt = std::min<uint32_t>(nt, (uint32_t)ctx->rows_nt);
-        return nt;
-      };
-      uint32_t R = 8, nt = teams_for(8);
-      if (ctx->rows_r == 4 || ctx->rows_r == 8 || ctx->rows_r == 16) { R = (uint32_t)ctx->rows_r; nt = teams_for(R); }
-      else if (nt < 2) { R = 4; nt = teams_for(4); }
-      if (nt < 1) return fail(ctx, STEMK_ERR_NOMEM, "row-block stem kernel: record does not fit in shared memory");
-      const size_t smem = stem_rows_smem_bytes(R, nt, tw, nx_cap, ny_cap, e4_cap, lev_cap, xlev_cap);
-      const int grid = (int)std::min<size_t>((n_pairs + kFastGroup - 1) / kFastGroup, (size_t)ctx->sm_count);
-      const unsigned long long stride = (unsigned long long)kFastGroup * nx_cap * ((ny_cap + 3u) & ~3u);
-      const unsigned long long ra_stride = (unsigned long long)kFastGroup * nx_cap;
-      CU(ctx->scratch.reserve(sizeof(double) * stride * grid));
-      CU(ctx->rowacc.reserve(sizeof(double) * ra_stride * grid));
-      StemRowsLaunch F;
-      F.X = x->view; F.Y = y->view; F.xi = d_xi; F.yi = d_yi; F.out = stem_out; F.order = C.order;
-      F.start = C.start; F.count = C.count; F.counter = heads + 1 + b; F.bucket = 1 + b;
-      F.scratch = (double*)ctx->scratch.p; F.scratch_stride = stride; F.rowacc = (double*)ctx->rowacc.p;
-      F.rowacc_stride = ra_stride; F.pair_tab = ctx->d_pair_tab;
-      F.len_band = ctx->params.len_band; F.nx_cap = nx_cap; F.ny_cap = ny_cap; F.e4_cap = e4_cap;
-      F.ylev_cap = lev_cap; F.xlev_cap = xlev_cap; F.team_warps = tw;
-      F.prof = nullptr;
-      static unsigned long long* d_prof = nullptr;
-      const bool prof = std::getenv("STEMK_PROF") != nullptr;
-      if (prof) {
-        if (!d_prof) cudaMalloc((void**)&d_prof, 32 * sizeof(unsigned long long));
-        cudaMemsetAsync(d_prof, 0, 32 * sizeof(unsigned long long), st);
-        F.prof = d_prof;
-      }
-      if (std::getenv("STEMK_TIMING")) std::fprintf(stderr, "rows bucket %d: cap %u R %u teams %u smem %zu\n", b, ny_cap, R, nt, smem);
-      stemk_ctx::Timed tm = timed_begin(ctx, 0, st);
-      cudaError_t le = launch_stem_rows(F, R, grid, (int)nt, smem, st);
-      timed_end(ctx, tm, st);
-      CU(le);
-      ctx->launches += 1;
-      if (prof) {
-        unsigned long long h[32];
-        cudaStreamSynchronize(st);
-        cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost);
-        const double nb = h[6] ? (double)h[6] : 1.0, nt_ = h[9] ? (double)h[9] : 1.0;
-        std::fprintf(stderr, "prof cap %u R %u teams %u: blocks %llu levels/block %.1f | per block: ticket %.0f A %.0f Await %.0f B %.0f C %.0f | "
-                     "per team: setup %.0f total %.0f cycles | per step (warp 0): votes+addr %.0f gathers+sum %.0f rest %.0f (steps/block %.1f) | per A batch: flags+TMA %.0f sum %.0f cycles (batches %llu)\n", ny_cap, R, nt, h[6], h[7] / nb, h[1] / nb, h[2] / nb, h[3] / nb, h[4] / nb,
-                     h[5] / nb, h[0] / nt_, h[8] / nt_, h[10] / (double)(h[17] ? h[17] : 1), h[11] / (double)(h[17] ? h[17] : 1), h[15] / (double)(h[17] ? h[17] : 1), h[17] / nb,
-                     h[12] / (double)(h[14] ? h[14] : 1), h[13] / (double)(h[14] ? h[14] : 1), h[14]);
-      }
-    }
-    // ---- lanes-are-rows kernel, one launch per size bucket: the tallest row block whose tile fits next to the record
-    for (int b = 0; lanes_mode && b < C.n_caps; ++b) {
-      const uint32_t ny_cap = std::min(C.caps[b], std::max(1u, y->host.max_fastN));
-      const uint32_t lo = b ? C.caps[b - 1] : 0u;
-      uint32_t e4_cap = 4;
-      bool any = false;
-      for (const RecDev& r : y->host.rec)
-        if ((r.flags & REC_FAST) && r.N > lo && r.N <= C.caps[b]) { e4_cap = std::max(e4_cap, r.e4); any = true; }
-      if (!any) continue;
-      const size_t budget = std::min<size_t>(ctx->smem_optin, (size_t)227 * 1024) - 5120;   // static shared memory (block row records, staged inner-pair offsets)
-      uint32_t R = 0;
-      for (uint32_t cand : {32u, 28u, 24u, 20u, 16u, 12u, 8u}) {
-        // block heights that do not divide 32 sweep one node per warp; measured slower than 32 / 16 / 8 on C3
-        // (319 k against 330 k pairs/s), so they are only taken when forced
-        if (ctx->lanes_r ? (uint32_t)ctx->lanes_r != cand : (32u % cand) != 0u) continue;
-        if ((size_t)(ny_cap + 1u) * (2u * cand + 1u) > 65535u) continue;   // child lists are 16-bit tile columns
-        if (stem_lanes_smem_bytes(cand, ny_cap, e4_cap, lev_cap) <= budget) { R = cand; break; }
-      }
-      if (!R) return fail(ctx, STEMK_ERR_NOMEM, "lanes stem kernel: record does not fit in shared memory");
-      const size_t smem = stem_lanes_smem_bytes(R, ny_cap, e4_cap, lev_cap);
-      const int grid = (int)std::min<size_t>((n_pairs + kLanesGroup - 1) / kLanesGroup, (size_t)ctx->sm_count);
-      const unsigned long long stride = (unsigned long long)kLanesGroup * nx_cap * ((ny_cap + 1u) & ~1u);
-      CU(ctx->scratch.reserve(sizeof(double) * stride * grid));
-      CU(ctx->rowacc.reserve(sizeof(double) * (size_t)kLanesGroup * nx_cap * grid));
-      StemLanesLaunch F;
-      F.X = x->view; F.Y = y->view; F.xi = d_xi; F.yi = d_yi; F.out = stem_out; F.order = C.order;
-      F.start = C.start; F.count = C.count; F.counter = heads + 1 + b; F.bucket = 1 + b;
-      F.scratch = (double*)ctx->scratch.p; F.scratch_stride = stride; F.rowacc = (double*)ctx->rowacc.p; F.pair_tab = ctx->d_pair_tab;
-      F.len_band = ctx->params.len_band; F.nx_cap = nx_cap; F.ny_cap = ny_cap; F.e4_cap = e4_cap; F.lev_cap = lev_cap;
-      if (std::getenv("STEMK_TIMING")) std::fprintf(stderr, "lanes bucket %d: cap %u R %u smem %zu\n", b, ny_cap, R, smem);
-      F.prof = nullptr;
-      static unsigned long long* d_lprof = nullptr;
-      const bool prof = std::getenv("STEMK_PROF") != nullptr;
-      if (prof) {
-        if (!d_lprof) cudaMalloc((void**)&d_lprof, 8 * sizeof(unsigned long long));
-        cudaMemsetAsync(d_lprof, 0, 8 * sizeof(unsigned long long), st);
-        F.prof = d_lprof;
-      }
-      stemk_ctx::Timed tm = timed_begin(ctx, 0, st);
-      cudaError_t le = launch_stem_lanes(F, R, grid, smem, st);
-      timed_end(ctx, tm, st);
-      CU(le);
-      ctx->launches += 1;
-      if (prof) {   // only meaningful with a -DLANES_PROF build
-        unsigned long long h[8];
-        cudaStreamSynchronize(st);
-        cudaMemcpy(h, d_lprof, sizeof(h), cudaMemcpyDeviceToHost);
-        const double nb = h[5] ? (double)h[5] : 1.0;
-        std::fprintf(stderr, "lanes prof cap %u R %u: blocks %llu, y levels swept per block %.1f | cycles per block: A %.0f B %.0f C %.0f sums %.0f | "
-                     "staging %.0f tail %.0f (per block)\n", ny_cap, R, h[5], h[6] / nb, h[1] / nb, h[2] / nb, h[3] / nb, h[4] / nb, h[0] / nb, h[7] / nb);
-      }
-    }
-    // ---- fast kernel, one launch per size bucket (shared memory and CTAs per SM sized for the bucket)
-    for (int b = 0; !rows_mode && !lanes_mode && b < C.n_caps; ++b) {
-      const uint32_t ny_cap = std::min(C.caps[b], std::max(1u, y->host.max_fastN));
-      const uint32_t e4_cap = std::max(4u, y->host.max_E4);
-      const size_t budget = std::min<size_t>(ctx->smem_optin, (size_t)227 * 1024);
+      const size_t budget = std::min<size_t>(ctx->smem_optin, (size_t)227 * 1024) - 256;   // static shared memory
       // one CTA per SM with as many warps as the bucket's rows leave room for
       int best_w = 0; size_t best_smem = 0;
-      for (int t = kFastMaxWarps; t >= 2; --t) if (stem_fast_smem_bytes(t, nx_cap, ny_cap, e4_cap, lev_cap) <= budget) { best_w = t; break; }
+      for (int t = kFastMaxWarps; t >= 2; --t) if (stem_fast_smem_bytes(t, nx_cap, ny_cap, e4_cap, lev_cap, band_cap) <= budget) { best_w = t; break; }
       if (!best_w) return fail(ctx, STEMK_ERR_NOMEM, "fast stem kernel: record does not fit in shared memory");
-      best_smem = stem_fast_smem_bytes(best_w, nx_cap, ny_cap, e4_cap, lev_cap);
+      best_smem = stem_fast_smem_bytes(best_w, nx_cap, ny_cap, e4_cap, lev_cap, band_cap);
       const int per_sm = stem_fast_ctas_per_sm(best_w, best_smem);
       if (per_sm < 1) return fail(ctx, STEMK_ERR_CUDA, "fast stem kernel does not fit on an SM");
       const int grid = (int)std::min<size_t>((n_pairs + kFastGroup - 1) / kFastGroup, (size_t)ctx->sm_count);
@@ -495,11 +377,30 @@ int stemk_pairs_device(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, s
       F.start = C.start; F.count = C.count; F.counter = heads + 1 + b; F.bucket = 1 + b;
       F.scratch = (double*)ctx->scratch.p; F.scratch_stride = stride; F.rowacc = (double*)ctx->rowacc.p; F.pair_tab = ctx->d_pair_tab;
       F.len_band = ctx->params.len_band; F.nx_cap = nx_cap; F.ny_cap = ny_cap; F.e4_cap = e4_cap; F.lev_cap = lev_cap;
+      F.band_cap = band_cap; F.prof = nullptr;
+#ifdef FAST_PROF
+      unsigned long long* d_prof = nullptr;
+      cudaMalloc((void**)&d_prof, 16 * sizeof(unsigned long long));
+      cudaMemsetAsync(d_prof, 0, 16 * sizeof(unsigned long long), st);
+      F.prof = d_prof;
+#endif
       stemk_ctx::Timed tm = timed_begin(ctx, 0, st);
       cudaError_t le = launch_stem_fast(F, grid, best_w, best_smem, st);
       timed_end(ctx, tm, st);
       CU(le);
       ctx->launches += 1;
+#ifdef FAST_PROF
+      {
+        unsigned long long h[16];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost);
+        cudaFree(d_prof);
+        const double nr = h[5] ? (double)h[5] : 1.0;
+        std::fprintf(stderr, "fast prof cap %u warps %d smem %zu band_cap %u: rows %llu | cycles per row: total %.0f A %.0f (flag wait %.0f) B1+Z %.0f B2 %.0f C %.0f | of all warp time: blocks %.1f%% group barrier %.1f%%\n",
+                     ny_cap, best_w, best_smem, band_cap, h[5], h[0] / nr, h[1] / nr, h[6] / nr, h[2] / nr, h[3] / nr, h[4] / nr,
+                     100.0 * h[0] / (h[9] ? (double)h[9] : 1.0), 100.0 * h[8] / (h[9] ? (double)h[9] : 1.0));
+      }
+#endif
     }
   }
   if (has_str) {

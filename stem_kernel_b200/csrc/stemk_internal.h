@@ -39,9 +39,9 @@ enum { REC_HAS_WEIGHT = 1u, REC_SIMPLE_COLS = 2u, REC_SIMPLE_BPF = 4u,
        REC_LEN_MONOTONE = 8u,  // every non-leaf child is strictly shorter than its parent (true for front-end DAGs)
        REC_FAST = 16u };       // eligible for the separable fast kernel (see compile_set.cpp)
 #ifndef STEMK_ROWS
-#define STEMK_ROWS 1
+#define STEMK_ROWS 2
 #endif
-constexpr uint32_t kFastRows = STEMK_ROWS;  // rows (1, 2 or 4) a warp of the fast stem kernel sweeps in lockstep
+constexpr uint32_t kFastRows = STEMK_ROWS;  // rows (1, 2 or 4) of one x level a warp of the fast stem kernel sweeps in lockstep
 constexpr uint32_t kFastMaxN = 1024;  // largest staged record (non-leaf nodes) of the fast stem kernel
 
 struct __attribute__((aligned(16))) XNode {   // everything the fast kernel needs about a ROW node, one 64-byte line
@@ -50,11 +50,6 @@ struct __attribute__((aligned(16))) XNode {   // everything the fast kernel need
   double bfreq, paths;  // base-pair frequency, root->node paths
   uint32_t e0, e1;      // its non-leaf children in cidx (absolute)
   uint32_t len, bcode;
-};
-
-struct __attribute__((aligned(16))) NodeB {   // what a MATCH cell needs about a COLUMN node (row-block kernel), 32 bytes
-  double s2, el;        // g^(len-2-B), sum over leaf children of the edge factor
-  double paths, bfreq;  // root->node paths, base-pair frequency
 };
 
 struct NodeI {        // integer part of a node for the fast kernel (8 bytes)
@@ -87,7 +82,7 @@ struct SetView {
   const double* s2;      // g^(len - 2 - B)
   const NodeI* nodei;
   const XNode* xnode;
-  const NodeB* yband;
+  const uint32_t* lperm; // per record: its non-leaf nodes sorted by length, len << 16 | node (the band of a row is a range of it)
   const uint16_t* c16;   // padded child lists as byte offsets into a row (8 * record-local node number), 8N = the all-zero dummy column
   const uint32_t* blk;   // row blocks: first row | count << 16
   // general base-pair profiles (alignments / IUPAC)
@@ -111,16 +106,18 @@ struct CompiledSet {
   std::vector<double> up, dn, s2;
   std::vector<NodeI> nodei;
   std::vector<XNode> xnode;
-  std::vector<NodeB> yband;
+  std::vector<uint32_t> lperm;
   std::vector<uint16_t> c16;
   std::vector<uint32_t> blk;
   uint32_t max_E4 = 0, max_fastN = 0, n_fast = 0;  // over fast-eligible records
+  uint32_t max_band_cnt = 1;                       // most nodes of one record inside any length window of 2*len_band+1 (all of them without a band)
   uint32_t n_weighted = 0, n_simple_cols = 0;      // records with per-column weights / with one-hot-or-gap columns only
   // host-only statistics for the work model and the scheduler
   std::vector<uint32_t> n_nodes_all;  // nodes incl. leaves (reference's #V)
   std::vector<uint32_t> n_edges_all;  // edges incl. leaf edges (reference's #E)
   std::vector<uint32_t> max_level_rows;
   std::vector<uint32_t> deg_all;      // per non-leaf node (level order): out-degree incl. leaf edges
+  std::vector<uint32_t> band_cnt;     // per record: most nodes inside any length window of 2*len_band+1
   // work model: per record, prefix sums over node length of the out-degrees and of the base-pair-profile sizes
   // (cost_pd[cost_off[r] + k] = sum of deg over the record's non-leaf nodes with len < k), cost_off has n+1 entries
   std::vector<uint64_t> cost_off;
@@ -129,8 +126,9 @@ struct CompiledSet {
   uint32_t max_N = 0, max_L = 0, max_E = 0, max_nlev = 0;  // non-leaf nodes / columns / non-leaf edges / levels
 };
 
-// Builds the compiled form of every record of `desc` under loop gap `g`.  Returns "" or an error.
-std::string compile_set(const stemk_seqset_desc& desc, double g, int n_threads, CompiledSet* out);
+// Builds the compiled form of every record of `desc` under loop gap `g` and length band `len_band` (0 = none).
+// Returns "" or an error.
+std::string compile_set(const stemk_seqset_desc& desc, double g, uint32_t len_band, int n_threads, CompiledSet* out);
 
 // Kernel constants derived from stemk_params on the host with libm (same exp() the reference calls).
 struct KernelTables {

@@ -187,6 +187,10 @@ class ShardedCross:
             self.recv[0].copy_(self.send)
         if self.rank != 0:
             return None, None
+        return self.finish(normalize, init)
+
+    def finish(self, normalize=False, init=0.0):
+        """Rank 0, after the gather filled self.recv: un-deal the three lists, scatter, normalise."""
         vals, off = [], 0
         for k, (_, _, a, _) in enumerate(self.lists):
             vals.append(undeal(self.recv[:, off:off + self.slabs[k]], len(a)))

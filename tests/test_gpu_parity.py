@@ -138,34 +138,6 @@ def test_fast_and_general_kernels_agree_and_fast_is_deterministic(monkeypatch):
     assert np.array_equal(gp[a[kept], b[kept]], g_fast[perm[a[kept]], perm[b[kept]]])
 
 
-@pytest.mark.parametrize("rows", ["0", "16", "12", "8"])      # 0 takes 32-row blocks for the small records
-def test_lanes_kernel_matches_the_oracle_and_the_fast_kernel(golden, rows, monkeypatch):
-    """The opt-in lanes-are-rows stem kernel (stem_lanes.cu, STEMK_LANES=1; STEMK_LANES_R forces the block height,
-    0 = the tallest that fits): golden vectors of the reference (alignments still take the general kernel), a C3
-    subset against the oracle and against the fast kernel, run-to-run identical."""
-    monkeypatch.setenv("STEMK_LANES", "1")
-    monkeypatch.setenv("STEMK_LANES_R", rows)
-    for kind, band in ((L.SU_STEM, 10), (L.SI_STEM, 0), (L.SU_STEM_STR, 10)):
-        ctx = api.Context(L.make_params(kind, len_band=band))
-        assert relerr(ctx.gram(ctx.upload(golden["flat"])), golden["z"][f"gram_k{kind}_b{band}"]) < TOL
-        ctx.close()
-    md = hostlib.build_many(synth.make_config(3, 36, offset=2300) + synth.make_config(1, 12, offset=2400), TH)
-    flat = hostlib.SeqSet(md)
-    p = L.make_params(L.SU_STEM)
-    cl = api.Context(p)
-    ds = cl.upload(flat)
-    g_lanes = cl.gram(ds)
-    assert np.array_equal(g_lanes, cl.gram(ds))
-    xi, yi = np.triu_indices(len(md))
-    pick = np.random.default_rng(3).choice(len(xi), 60, replace=False)
-    want = O.pairs(oparams(p), flat.desc(), flat.desc(), xi[pick], yi[pick])
-    assert relerr(g_lanes[xi[pick], yi[pick]], want) < TOL
-    monkeypatch.setenv("STEMK_LANES", "0")
-    cf = api.Context(p)
-    assert relerr(g_lanes, cf.gram(cf.upload(flat))) < 1e-11
-    cl.close(); cf.close()
-
-
 def test_threshold_changes_dag_density():
     """Denser DAGs (lower threshold keeps every background pair) and sparser ones (only planted stems)."""
     recs = synth.make_config(3, 6, offset=900)
