@@ -115,6 +115,21 @@ int stemk_create(stemk_ctx** ctx, const stemk_params* params, int device);
 void stemk_destroy(stemk_ctx* ctx);
 const char* stemk_last_error(const stemk_ctx* ctx); /* ctx may be NULL: last creation error */
 
+/* Context options (test and diagnostic hooks; there is no environment-variable dispatch):
+ *   STEMK_OPT_FORCE_GENERAL  1: every stem pair runs on the general kernel (stem_kernel.cu) instead of the separable
+ *                            fast path -- what alignments / IUPAC records take anyway; lets tests compare the two
+ *   STEMK_OPT_TIMING         1: stemk_upload / stemk_gram print a host-side time breakdown on stderr */
+#define STEMK_OPT_FORCE_GENERAL 1
+#define STEMK_OPT_TIMING 2
+int stemk_set_option(stemk_ctx* ctx, int option, int value);
+
+/* Threading: a context is single-threaded and has ONE call in flight -- its scratch buffers, work queues and DP
+ * slabs belong to the call.  stemk_pairs_device / stemk_assemble_device are asynchronous on the caller's stream; a
+ * call on a DIFFERENT stream than the previous one first waits (on the device) for the previous call's work.  Use one
+ * context per host thread (the kernel object is immutable, like the reference's functors, and cheap to create).
+ * Sets are bound to the device, loop gap and length band of the context that uploaded them (the derived per-record
+ * tables depend on them); using a set with another context fails with STEMK_ERR_ARG. */
+
 /* upload a flattened set (copied; derived per-record tables are built here) */
 int stemk_upload(stemk_ctx* ctx, const stemk_seqset_desc* desc, stemk_set** set);
 void stemk_set_free(stemk_ctx* ctx, stemk_set* set);
@@ -131,9 +146,11 @@ int stemk_gram(stemk_ctx* ctx, const stemk_set* train, int normalize, double* ou
 
 /* KernelMatrix::calculate(test, train, ...) and the static one-row calculate -- kernel_matrix.cpp:635-754.
  * out: n_test*n_train row-major.  sv_index (may be NULL, n_sv = 0): only those train columns are
- * computed, the others are left untouched in out.  self_out (may be NULL): k(test_i, test_i).
- * normalize != 0: out_ij /= sqrt(self_i * k(train_j,train_j)) as kernel_matrix.cpp:735-748
- * (train diagonals are computed internally). */
+ * computed AND WRITTEN, the other entries of out are left untouched (the static row calculate writes vec[sv] only,
+ * kernel_matrix.cpp:164-171; a caller that wants the zero-initialised rows of the rectangular calculate,
+ * kernel_matrix.cpp:713, clears out first).  self_out (may be NULL): k(test_i, test_i).
+ * normalize != 0: out_ij /= sqrt(self_i * k(train_j,train_j)) as kernel_matrix.cpp:735-748, applied to the written
+ * columns (train diagonals are computed internally). */
 int stemk_cross(stemk_ctx* ctx, const stemk_set* test, const stemk_set* train, const uint32_t* sv_index,
                 uint32_t n_sv, int normalize, double* out, double* self_out);
 

@@ -11,6 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CUDA_SO = os.environ.get("STEMK_SO") or os.path.join(_HERE, "csrc", "libstemk_b200.so")   # STEMK_SO: tuning builds
 
 OK, ERR_ARG, ERR_CUDA, ERR_NOMEM, ERR_STATE = 0, -1, -2, -3, -4
+OPT_FORCE_GENERAL, OPT_TIMING = 1, 2
 
 # stemk_kind
 SI_STEM, SU_STEM, SI_STEM_STR, SU_STEM_STR, LSU_STEM, LSU_STR, LSU_STEM_STR, STR_SUBST, STR_SIMPLE, STR_NAIVE = range(10)
@@ -31,7 +32,7 @@ def make_params(kind, loop_gap=0.2, beta=0.3, stack=1.3, covar=0.8, gap=0.8, alp
     return Params(kind, len_band, loop_gap, beta, stack, covar, gap, alpha, match, mismatch)
 
 
-EXPORTS = ["stemk_version", "stemk_device_count", "stemk_create", "stemk_destroy", "stemk_last_error", "stemk_upload",
+EXPORTS = ["stemk_version", "stemk_device_count", "stemk_create", "stemk_set_option", "stemk_destroy", "stemk_last_error", "stemk_upload",
            "stemk_set_free", "stemk_set_size", "stemk_set_stats", "stemk_set_device_bytes", "stemk_gram", "stemk_cross", "stemk_diag", "stemk_pairs",
            "stemk_pairs_device", "stemk_assemble_device", "stemk_pair_cost", "stemk_stats_reset", "stemk_stats_get", "stemk_fp64_peak", "stemk_format_rows", "stemk_format_values", "stemk_bpla_pairs", "stemk_bpla_gradients", "stemk_nstem_pairs", "stemk_nstem_pairs_banded"]
 
@@ -50,6 +51,7 @@ def lib():
         L.stemk_device_count.restype = C.c_int
         L.stemk_create.argtypes = [C.POINTER(vp), C.POINTER(Params), C.c_int]
         L.stemk_destroy.argtypes = [vp]
+        L.stemk_set_option.argtypes = [vp, C.c_int, C.c_int]
         L.stemk_last_error.restype = C.c_char_p
         L.stemk_last_error.argtypes = [vp]
         L.stemk_upload.argtypes = [vp, C.POINTER(SeqSetDesc), C.POINTER(vp)]

@@ -16,6 +16,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <exception>
 #include <functional>
 #include <thread>
 
@@ -69,6 +70,16 @@ void compile_record(const stemk_seqset_desc& s, uint32_t r, double g, uint32_t l
   h.L = L;
   h.n_rows = nrows;
   o->n_all = n;
+  // descriptor sanity first: everything below sizes arrays from these numbers
+  if (s.node_off[r + 1] < n0 || s.col_off[r + 1] < c0) { o->err = "record offsets not monotone"; return; }
+  if (!(nrows > 0.0f)) { o->err = "n_rows must be positive"; return; }
+  for (uint32_t u = 0; u < n; ++u) {
+    if (last[u] < first[u] || last[u] >= L) { o->err = "node positions must satisfy first <= last < sequence length"; return; }
+    if (eoff[u + 1] < eoff[u]) { o->err = "edge offsets not monotone"; return; }
+    if (boff[u + 1] < boff[u]) { o->err = "base-pair-profile offsets not monotone"; return; }
+  }
+  for (uint32_t e = n ? eoff[0] : 0; n && e < eoff[n]; ++e)
+    if (s.edge_gaps[e] > L) { o->err = "edge gap count exceeds the sequence length"; return; }
   o->e_all = n ? eoff[n] - eoff[0] : 0;
 
   // ---- columns
@@ -242,13 +253,56 @@ void compile_record(const stemk_seqset_desc& s, uint32_t r, double g, uint32_t l
       o->s2[k] = fast ? pw(l - 2 - (long)B) : 0.0;
       NodeI ni;
       ni.e4_bcode = ((uint32_t)o->c16.size() << 8) | o->bcode[k];
-      const uint32_t c0 = o->coff[k], c1 = o->coff[k + 1];
-      for (uint32_t e = c0; e < c1; ++e) o->c16.push_back((uint16_t)(8u * o->cidx[e]));   // byte offsets into a row
-      while (o->c16.size() % 4) o->c16.push_back((uint16_t)(8u * N));   // dummy column: reads 0.0
-      ni.deg4 = (uint16_t)((o->c16.size() - (ni.e4_bcode >> 8)) / 4);
+      const uint32_t deg = o->coff[k + 1] - o->coff[k];
+      ni.deg4 = (uint16_t)((deg + 3u) / 4u);
       ni.len = (uint16_t)o->len[k];
       o->nodei[k] = ni;
+      o->c16.resize(o->c16.size() + 4u * ni.deg4, (uint16_t)(8u * N));   // dummy column: reads 0.0
       if ((o->c16.size() >> 24) != 0) fast = false;
+    }
+    // Order of the children inside every padded list.  The fast kernel sweeps the nodes of a level 32/kFastRows at a
+    // time, one lane per node, and in step p every lane gathers the p-th entry of its list: the step costs as many
+    // shared-memory wavefronts as the fullest 8-byte bank.  The sum over a list is order-free, so the entries are
+    // placed greedily, step by step, on banks no other node of the group uses in that step (a pad entry -- they all
+    // read the same dummy word -- may take a child's place when the list has room left).
+    {
+      constexpr uint32_t kSlots = 32u / kFastRows;
+      std::vector<std::vector<uint32_t>> rem;
+      for (uint32_t l = 0; l < nlev; ++l)
+        for (uint32_t g0 = o->lev_off[l]; g0 < o->lev_off[l + 1]; g0 += kSlots) {
+          const uint32_t g1 = std::min(o->lev_off[l + 1], g0 + kSlots);
+          rem.assign(g1 - g0, {});
+          uint32_t steps = 0;
+          for (uint32_t k = g0; k < g1; ++k) {
+            rem[k - g0].assign(o->cidx.begin() + o->coff[k], o->cidx.begin() + o->coff[k + 1]);
+            steps = std::max<uint32_t>(steps, 4u * o->nodei[k].deg4);
+          }
+          std::vector<uint32_t> idx(g1 - g0);
+          for (uint32_t p = 0; p < steps; ++p) {
+            uint32_t used[16];   // bank -> node column holding it in this step (0xffffffff: free)
+            std::fill(used, used + 16, 0xffffffffu);
+            uint32_t m = 0;
+            for (uint32_t k = g0; k < g1; ++k) if (p < 4u * o->nodei[k].deg4) idx[m++] = k - g0;
+            std::stable_sort(idx.begin(), idx.begin() + m, [&](uint32_t a, uint32_t b) { return rem[a].size() < rem[b].size(); });
+            for (uint32_t q = 0; q < m; ++q) {
+              std::vector<uint32_t>& r = rem[idx[q]];
+              const uint32_t k = g0 + idx[q];
+              uint16_t* slot = o->c16.data() + (o->nodei[k].e4_bcode >> 8) + p;
+              if (r.empty()) continue;                                     // stays a pad entry
+              const uint32_t left = 4u * o->nodei[k].deg4 - p;              // steps left for this list, this one included
+              size_t pick = r.size();
+              for (size_t c = 0; c < r.size(); ++c)
+                if (used[r[c] & 15u] == 0xffffffffu || used[r[c] & 15u] == r[c]) { pick = c; break; }
+              if (pick == r.size()) {
+                if (r.size() < left && (used[N & 15u] == 0xffffffffu || used[N & 15u] == N)) { used[N & 15u] = N; continue; }
+                pick = 0;
+              }
+              if (used[r[pick] & 15u] == 0xffffffffu) used[r[pick] & 15u] = r[pick];
+              *slot = (uint16_t)(8u * r[pick]);
+              r.erase(r.begin() + (long)pick);
+            }
+          }
+        }
     }
     for (uint32_t l = 0; l < nlev; ++l)
       for (uint32_t r = o->lev_off[l]; r < o->lev_off[l + 1]; r += kFastRows)
@@ -281,19 +335,24 @@ void append(std::vector<T>& dst, const std::vector<T>& src) { dst.insert(dst.end
 
 }  // namespace
 
-std::string compile_set(const stemk_seqset_desc& s, double g, uint32_t len_band, int n_threads, CompiledSet* out) {
+std::string compile_set(const stemk_seqset_desc& s, double g, uint32_t len_band, int n_threads, bool timing, CompiledSet* out) {
   const uint32_t n = s.n_seqs;
-  const bool timing = std::getenv("STEMK_TIMING") != nullptr;
   auto t0 = std::chrono::steady_clock::now();
   std::vector<RecOut> recs(n);
   if (n_threads < 1) n_threads = 1;
   n_threads = std::min<int>(n_threads, std::max<uint32_t>(1, n / 16));
+  // exceptions (std::bad_alloc on a hostile descriptor) must not leave a worker thread: they become the record's error
+  auto guarded = [&](uint32_t r) {
+    try { compile_record(s, r, g, len_band, &recs[r]); }
+    catch (const std::exception& ex) { recs[r].err = std::string("exception: ") + ex.what(); }
+    catch (...) { recs[r].err = "unknown exception"; }
+  };
   if (n_threads <= 1) {
-    for (uint32_t r = 0; r < n; ++r) compile_record(s, r, g, len_band, &recs[r]);
+    for (uint32_t r = 0; r < n; ++r) guarded(r);
   } else {
     std::vector<std::thread> th;
     for (int t = 0; t < n_threads; ++t)
-      th.push_back(std::thread([&, t]() { for (uint32_t r = t; r < n; r += n_threads) compile_record(s, r, g, len_band, &recs[r]); }));
+      th.push_back(std::thread([&, t]() { for (uint32_t r = t; r < n; r += n_threads) guarded(r); }));
     for (auto& x : th) x.join();
   }
   auto t1 = std::chrono::steady_clock::now();

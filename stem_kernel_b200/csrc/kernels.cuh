@@ -104,6 +104,17 @@ cudaError_t launch_combine(int kind, double alpha, double beta, const double* st
 cudaError_t launch_scatter_square(const double* vals, const uint32_t* xi, const uint32_t* yi, unsigned long long n_pairs,
                                   double* matrix, uint32_t n, cudaStream_t stream);
 cudaError_t launch_normalize_square(double* matrix, uint32_t n, cudaStream_t stream);
+// matrix_ops.cu: work-order pair lists and the rectangular matrix, on the device
+cudaError_t launch_gram_pairs(const uint32_t* perm, const unsigned long long* off, uint32_t n, uint32_t* xi, uint32_t* yi,
+                              cudaStream_t stream);
+cudaError_t launch_cross_pairs(const uint32_t* tperm, const uint32_t* cperm, uint32_t nt, uint32_t nc, uint32_t* xi,
+                               uint32_t* yi, cudaStream_t stream);
+cudaError_t launch_scatter_cross(const double* vals, const uint32_t* xi, const uint32_t* yi, unsigned long long n_pairs,
+                                 const uint32_t* col_of, double* out, uint32_t ld, cudaStream_t stream);
+cudaError_t launch_normalize_cross(double* out, uint32_t nt, uint32_t nc, uint32_t ld, const double* selfv,
+                                   const double* diag, const uint32_t* cols, cudaStream_t stream);
+cudaError_t launch_scatter_vec(const double* vals, const uint32_t* idx, uint32_t n, double* out, cudaStream_t stream);
+cudaError_t launch_iota(uint32_t* a, uint32_t n, cudaStream_t stream);
 // BPLA / local-alignment kernels (bpla.cu): host buffers in, host buffer out, synchronous on `stream`
 cudaError_t run_bpla(const stemk_bpla_params& p, const stemk_bpla_set& x, const stemk_bpla_set& y, size_t n_pairs,
                      const uint32_t* xi, const uint32_t* yi, double* out, double* grad, int sm_count, size_t smem_optin,

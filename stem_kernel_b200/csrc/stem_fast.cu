@@ -15,21 +15,26 @@
 // (stem_kernel.cpp:46-59) only exists inside the length band, ~13 % of the cells, and R only depends on the finished
 // rows of i's inner pairs -- not on the row's own sweep -- so it is taken out of the sweep and done with full lanes:
 //   A   per row, lanes <-> column pairs: q = sum of the finished pre-scaled G0 rows of i's inner pairs (coalesced
-//       16-byte reads of the per-pair slab, eight in flight per lane);  HQ(i,:) = up_y*s2_x*q goes to the block
+//       16-byte reads of the per-pair slab, eight in flight per lane);  HQ(i,:) = up_y*s2_x*q goes to the row
 //       buffer, the a_x*Q part of G0s(i,:) straight to the slab
 //   B1  per row, lanes <-> the y nodes INSIDE THE BAND of i (a contiguous range of the record's length-sorted node
-//       list, found by two warp-wide searches): R gathered from the block buffer, up_y*M(i,j) kept in a small
+//       list, found by two warp-wide searches): R gathered from the row buffer, up_y*M(i,j) kept in a small
 //       per-warp buffer, the path-weighted MATCH sum of the row accumulated here
-//   Z   the row's part of the block buffer is cleared and the band's up_y*M values are scattered into it: it is now H
-//   B2  y level by y level, lanes <-> nodes of the level, every lane carrying ALL rows of the block (the buffer is
-//       interleaved [column][row], one 16-byte load fetches a child's value for two rows):
+//   Z   the row buffer is cleared and the band's up_y*M values are scattered into it: it is now the H row
+//   B2  y level by y level, lanes <-> (row of the block) x (node of the level):
 //       H(i,j) += up_y*a_y*s2_y * sum_cy H(i,cy) for the nodes at or above the band (G1 is identically 0 below it:
 //       length-monotone DAG); nodes of a level are sorted by length, so a level stops at the first node below the
-//       window.  The index loads, node records and address arithmetic of the sweep are shared by the rows of the
-//       block; only __syncwarp between levels
+//       window.  The rows of a block share every instruction of the sweep; only __syncwarp between levels
 //   C   per row, lanes <-> column pairs: slab(i,j) += up_x*dn_y*H(i,j) where H is non-zero, fence, raise the flags
 // Per row a warp holds ONE buffer row (HQ, then H) plus the band buffer, against two full rows in the first version
 // of this kernel: more rows in flight per SM.
+//
+// What bounds it (ncu, profiles/r02_*): the LSU data pipe -- shared-memory wavefronts of the gathers plus the
+// global wavefronts of phase A -- at ~75 % of its peak; time follows the wavefront count of a variant, not its
+// instruction count.  Hence: child lists are 16-bit byte offsets (one 8-byte index load per four children) whose
+// order is chosen at upload so that the nodes a warp sweeps together hit different banks (compile_set.cpp), rows are
+// polled with one uniform vote instead of per-lane spinning, and the row buffers are contiguous (an interleaved
+// [column][row] buffer halves the instructions of the sweep but costs more wavefronts in phases A, Z and C).
 //
 // Mapping.  One persistent CTA per SM; launches are bucketed by the size of the staged record so that shared memory
 // is sized for the bucket, not for the largest record of the set.  A CTA takes a GROUP of up to kGroup consecutive
@@ -48,17 +53,13 @@ namespace {
 
 constexpr uint32_t kGroup = kFastGroup;  // pairs sharing one staged y record that a CTA runs concurrently
 constexpr uint32_t R = kFastRows;        // rows of a block (1, 2 or 4)
-static_assert(R == 1 || R == 2 || R == 4 || R == 8, "kFastRows must be 1, 2, 4 or 8");
-#ifndef STEMK_B2MAP
-#define STEMK_B2MAP 1
-#endif
-// sweep mapping: 0 = lanes <-> nodes, every lane carries all rows of the block; 1 = lanes <-> (node slot, row)
+static_assert(R == 1 || R == 2 || R == 4, "kFastRows must be 1, 2 or 4");
 
 struct FastLayout {
-  uint32_t tab, yB2, yB1a, yB1b, yUp, yDn, yC, yLev, yPerm, done, warps, mbuf_bytes, buf_bytes, warp_bytes, total;
+  uint32_t tab, yB2, yB1a, yB1b, yUp, yDn, yC, yLev, yPerm, done, warps, mbuf_bytes, row_bytes, warp_bytes, total;
 };
 
-// per warp: the band buffer, then the block buffer [ny_cap + 1 columns (the last one is the dummy)][R rows]
+// per warp: the band buffer, then R row buffers of ny_cap + 1 columns (the last one is the all-zero dummy column)
 __host__ __device__ inline FastLayout fast_layout(uint32_t nwarps, uint32_t nx_cap, uint32_t ny_cap, uint32_t e4_cap,
                                                   uint32_t lev_cap, uint32_t band_cap) {
   FastLayout L;
@@ -70,13 +71,13 @@ __host__ __device__ inline FastLayout fast_layout(uint32_t nwarps, uint32_t nx_c
   L.yB1b = take(16 * ny_cap);  // {bfreq*up, paths*dn}                                                    (MATCH)
   L.yUp = take(8 * (ny_cap + 2u));  // up                                                                 (phase A)
   L.yDn = take(8 * (ny_cap + 2u));  // dn                                                                 (phase C)
-  L.yC = take(4 * e4_cap);     // child lists as 32-bit byte offsets into the block buffer
+  L.yC = take(2 * e4_cap);     // child lists as 16-bit byte offsets into a row buffer, padded to multiples of four
   L.yLev = take(4 * (lev_cap + 1));
   L.yPerm = take(4 * ny_cap);  // nodes sorted by length: len << 16 | node
   L.done = take(nx_cap * kGroup);  // one byte per row, per pair of the group
   L.mbuf_bytes = (8u * band_cap + 15u) & ~15u;
-  L.buf_bytes = (8u * R * (ny_cap + 2u) + 15u) & ~15u;
-  L.warp_bytes = L.mbuf_bytes + L.buf_bytes;
+  L.row_bytes = (8u * (ny_cap + 2u) + 15u) & ~15u;
+  L.warp_bytes = L.mbuf_bytes + R * L.row_bytes;
   L.warps = take(L.warp_bytes * nwarps);
   L.total = off;
   return L;
@@ -98,6 +99,7 @@ __device__ __forceinline__ uint32_t ld_flag_f(uint32_t addr) {
 __device__ __forceinline__ double lds_f64(uint32_t a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
 __device__ __forceinline__ double2 lds_v2f64(uint32_t a) { double2 v; asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a)); return v; }
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint2 lds_v2u32(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
 __device__ __forceinline__ uint4 lds_v4u32(uint32_t a) { uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
 __device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
 __device__ __forceinline__ void sts_v2f64(uint32_t a, double2 v) { asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v.x), "d"(v.y) : "memory"); }
@@ -121,21 +123,6 @@ __device__ __forceinline__ uint32_t count_len_below(uint32_t perm, uint32_t Ny, 
   const uint32_t base = c1 ? (c1 - 1u) * step : 0u;
   const uint32_t t2 = base + lane;
   return base + __popc(__ballot_sync(0xffffffffu, t2 < Ny && (lds_u32(perm + 4u * t2) >> 16) < key));
-}
-
-// S[r] += the block buffer's values of four children (byte offsets c4, rows interleaved)
-__device__ __forceinline__ void gather4(uint32_t buf, uint4 c4, double (&S)[R]) {
-  if (R == 1) {
-    S[0] += (lds_f64(buf + c4.x) + lds_f64(buf + c4.y)) + (lds_f64(buf + c4.z) + lds_f64(buf + c4.w));
-  } else {
-#pragma unroll
-    for (uint32_t h = 0; h < R; h += 2u) {
-      const double2 a = lds_v2f64(buf + c4.x + 8u * h), b = lds_v2f64(buf + c4.y + 8u * h);
-      const double2 c = lds_v2f64(buf + c4.z + 8u * h), d = lds_v2f64(buf + c4.w + 8u * h);
-      S[h] += (a.x + b.x) + (c.x + d.x);
-      S[h + 1u] += (a.y + b.y) + (c.y + d.y);
-    }
-  }
 }
 
 #ifdef FAST_PROF
@@ -164,9 +151,10 @@ __global__ void __launch_bounds__(32 * kFastMaxWarps, 1) stem_fast_kernel(const 
   const SetView& Y = P.Y;
   const unsigned long long n_items = P.count[P.bucket];
   const uint32_t* __restrict__ order = P.order + P.start[P.bucket];
-  // this warp's buffers: [band buffer | block buffer]; pinned so that they live in registers through the loops
+  // this warp's buffers: [band buffer | row 0 | row 1 ...]; pinned so that they live in registers through the loops
   const uint32_t mbuf = pin(sb + L.warps + L.warp_bytes * warp);
-  const uint32_t wbuf = pin(mbuf + L.mbuf_bytes);
+  const uint32_t wrows = pin(mbuf + L.mbuf_bytes);
+  const uint32_t row_bytes = pin(L.row_bytes);
   const uint32_t yPerm = pin(sb + L.yPerm), yB2 = pin(sb + L.yB2), yC = pin(sb + L.yC), yLev = pin(sb + L.yLev);
   const uint32_t yUp = pin(sb + L.yUp), yDn = pin(sb + L.yDn);
   unsigned long long item = 0, item_end = 0;  // the CTA's current run of queue positions
@@ -209,7 +197,6 @@ __global__ void __launch_bounds__(32 * kFastMaxWarps, 1) stem_fast_kernel(const 
     const uint32_t Ny = ry.N;
     const uint32_t NYS = (Ny + 1u) & ~1u;  // row stride of the G0 slabs (even: rows are 16-byte aligned)
     const uint32_t n_tickets = g * s_maxblk;
-    const uint32_t dmy = 8u * R * Ny;      // byte offset of the dummy column in the block buffer
 
     // ---- stage the y record, clear the row flags
     for (uint32_t j = tid; j < Ny; j += blockDim.x) {
@@ -227,13 +214,13 @@ __global__ void __launch_bounds__(32 * kFastMaxWarps, 1) stem_fast_kernel(const 
     }
     if (tid < 2u) { sts_f64(yUp + 8 * (Ny + tid), 0.0); sts_f64(yDn + 8 * (Ny + tid), 0.0); }   // read in pairs
     {
-      const uint16_t* __restrict__ src = Y.c16 + ry.c16_0;
-      for (uint32_t e = tid; e < ry.e4; e += blockDim.x) sts_u32(yC + 4 * e, R * (uint32_t)src[e]);
+      const uint2* __restrict__ src = reinterpret_cast<const uint2*>(Y.c16 + ry.c16_0);  // c16_0 is a multiple of 4
+      for (uint32_t e = tid; e < ry.e4 / 4u; e += blockDim.x) { const uint2 v = src[e]; sts_u32(yC + 8 * e, v.x); sts_u32(yC + 8 * e + 4, v.y); }
     }
     for (uint32_t l = tid; l <= ry.nlev; l += blockDim.x) sts_u32(yLev + 4 * l, Y.lev_off[ry.lev0 + l]);
     for (uint32_t i = tid; i < (g * P.nx_cap + 3u) / 4u; i += blockDim.x) sts_u32(sb + (L.done + 4 * i), 0u);
-    // the dummy column (and the pad after it) of this warp's block buffer
-    if (lane < 2u * R) sts_f64(wbuf + dmy + 8u * lane, 0.0);
+    // the dummy column (and the pad after it) of every row buffer of this warp
+    if (lane < 2u * R) sts_f64(wrows + row_bytes * (lane >> 1) + 8u * (Ny + (lane & 1u)), 0.0);
     __syncthreads();
 
     for (;;) {
@@ -254,16 +241,9 @@ __global__ void __launch_bounds__(32 * kFastMaxWarps, 1) stem_fast_kernel(const 
       double* __restrict__ G0 = slab + sl * slot_stride;
       const uint32_t done = sb + L.done + sl * P.nx_cap;
       double* __restrict__ rowacc = P.rowacc + ((size_t)blockIdx.x * kGroup + sl) * P.nx_cap;
-      uint32_t len_lo_blk = 0xffffffffu;   // the lowest window bound over the rows of the block
 
-      for (uint32_t r = 0; r < R; ++r) {
-        const uint32_t rb = wbuf + 8u * r;   // element (r, j) of the block buffer sits at rb + 8*R*j
-        if (r >= cnt) {   // a short block
-#if STEMK_B2MAP == 0
-          for (uint32_t j = lane; j <= Ny; j += 32u) sts_f64(rb + 8u * R * j, 0.0);   // the sweep touches every row
-#endif
-          continue;
-        }
+      for (uint32_t r = 0; r < cnt; ++r) {
+        const uint32_t rb = wrows + row_bytes * r;   // this row's buffer
         PROF_T(t_a0);
         const uint32_t i = i0 + r;
         const XNode* __restrict__ xn = X.xnode + ps.node0 + i;   // one 64-byte line, the same address for every lane
@@ -274,8 +254,6 @@ __global__ void __launch_bounds__(32 * kFastMaxWarps, 1) stem_fast_kernel(const 
         const uint32_t e0 = xi4.x, e1 = xi4.y, xl = xi4.z, xbc = xi4.w;
         const double xs2 = x01.x, pc = x23.x * x01.y;   // pc = up_x * a_x
         double* __restrict__ g0row = G0 + (size_t)i * NYS;
-        const uint32_t len_lo = (band != 0u && xl > band) ? xl - band : 0u;
-        len_lo_blk = min(len_lo_blk, len_lo);
 
         // ---- phase A: q = sum over inner pairs c of G0s(c,:);  HQ = up_y*s2_x*q -> buffer, up_x*a_x*s2_x*q -> slab
         for (uint32_t eb = e0; eb < e1 || eb == e0; eb += 32u) {
@@ -286,10 +264,10 @@ __global__ void __launch_bounds__(32 * kFastMaxWarps, 1) stem_fast_kernel(const 
           uint32_t c = 0u;
           if (lane < ne) c = X.cidx[eb + lane];
           const uint32_t off_l = c * NYS;
-          // wait until the rows of all inner pairs are published (one poll per lane and round, the whole warp sleeps)
-#ifndef ABL_NO_WAIT
-          while (!__all_sync(0xffffffffu, lane >= ne || ld_flag_f(done + c) != 0u)) __nanosleep(64);
-#endif
+          // wait until the rows of all inner pairs are published: one poll per lane and round, the whole warp sleeps
+          // in between, longer every time (polling is shared-memory traffic the sweeps of the other warps pay for)
+          for (uint32_t ns = 128u; !__all_sync(0xffffffffu, lane >= ne || ld_flag_f(done + c) != 0u); ns = min(2u * ns, 2048u))
+            __nanosleep(ns);
           __threadfence_block();  // acquire: the G0 rows behind the flags just seen
           PROF_T(t_w1);
           PROF_ADD(6, t_w0, t_w1);
@@ -304,20 +282,17 @@ __global__ void __launch_bounds__(32 * kFastMaxWarps, 1) stem_fast_kernel(const 
           for (uint32_t jb = 0; jb < Ny; jb += 256u) {  // uniform trip count: the shuffles below need every lane
             const uint32_t j = jb + 2u * lane;           // this lane: columns j, j+1 of four 64-column chunks
             const bool v0 = j < Ny, v1 = j + 64u < Ny, v2 = j + 128u < Ny, v3 = j + 192u < Ny;
+            const uint32_t rj = rb + 8u * j;
             double2 q0 = make_double2(0.0, 0.0), q1 = q0, q2 = q0, q3 = q0;
             if (more) {
-              if (v0) { q0.x = lds_f64(rb + 8u * R * j); q0.y = lds_f64(rb + 8u * R * (j + 1u)); }
-              if (v1) { q1.x = lds_f64(rb + 8u * R * (j + 64u)); q1.y = lds_f64(rb + 8u * R * (j + 65u)); }
-              if (v2) { q2.x = lds_f64(rb + 8u * R * (j + 128u)); q2.y = lds_f64(rb + 8u * R * (j + 129u)); }
-              if (v3) { q3.x = lds_f64(rb + 8u * R * (j + 192u)); q3.y = lds_f64(rb + 8u * R * (j + 193u)); }
+              if (v0) q0 = lds_v2f64(rj);
+              if (v1) q1 = lds_v2f64(rj + 512u);
+              if (v2) q2 = lds_v2f64(rj + 1024u);
+              if (v3) q3 = lds_v2f64(rj + 1536u);
             }
             // two inner pairs x four column chunks per round: eight independent 16-byte loads in flight per lane
 #pragma unroll 1
-#ifdef ABL_NO_A
-            for (uint32_t tt = 0; tt < 0u; tt += 2u) {
-#else
             for (uint32_t tt = 0; tt < ne; tt += 2u) {
-#endif
               const double2* __restrict__ s0 = reinterpret_cast<const double2*>(G0 + __shfl_sync(0xffffffffu, off_l, tt) + j);
               const double2* __restrict__ s1 = reinterpret_cast<const double2*>(G0 + __shfl_sync(0xffffffffu, off_l, (tt + 1u) & 31u) + j);
               const bool c1 = tt + 1u < ne;
@@ -338,20 +313,25 @@ __global__ void __launch_bounds__(32 * kFastMaxWarps, 1) stem_fast_kernel(const 
             }
             if (last) {
               // the second column of a pair may be the slab row's pad (j + 1 == Ny, Ny odd): its value is never used
+              // (yUp[Ny] = 0, so the dummy column of the buffer stays zero)
               if (v0) { const double2 u = lds_v2f64(yUp + 8u * j); const double sx = xs2 * q0.x, sy = xs2 * q0.y;
-                        *reinterpret_cast<double2*>(g0row + j) = make_double2(pc * sx, pc * sy); q0 = make_double2(u.x * sx, u.y * sy); }
+                        *reinterpret_cast<double2*>(g0row + j) = make_double2(pc * sx, pc * sy); q0 = make_double2(u.x * sx, j + 1u < Ny ? u.y * sy : 0.0); }
               if (v1) { const double2 u = lds_v2f64(yUp + 8u * (j + 64u)); const double sx = xs2 * q1.x, sy = xs2 * q1.y;
-                        *reinterpret_cast<double2*>(g0row + j + 64u) = make_double2(pc * sx, pc * sy); q1 = make_double2(u.x * sx, u.y * sy); }
+                        *reinterpret_cast<double2*>(g0row + j + 64u) = make_double2(pc * sx, pc * sy); q1 = make_double2(u.x * sx, j + 65u < Ny ? u.y * sy : 0.0); }
               if (v2) { const double2 u = lds_v2f64(yUp + 8u * (j + 128u)); const double sx = xs2 * q2.x, sy = xs2 * q2.y;
-                        *reinterpret_cast<double2*>(g0row + j + 128u) = make_double2(pc * sx, pc * sy); q2 = make_double2(u.x * sx, u.y * sy); }
+                        *reinterpret_cast<double2*>(g0row + j + 128u) = make_double2(pc * sx, pc * sy); q2 = make_double2(u.x * sx, j + 129u < Ny ? u.y * sy : 0.0); }
               if (v3) { const double2 u = lds_v2f64(yUp + 8u * (j + 192u)); const double sx = xs2 * q3.x, sy = xs2 * q3.y;
-                        *reinterpret_cast<double2*>(g0row + j + 192u) = make_double2(pc * sx, pc * sy); q3 = make_double2(u.x * sx, u.y * sy); }
+                        *reinterpret_cast<double2*>(g0row + j + 192u) = make_double2(pc * sx, pc * sy); q3 = make_double2(u.x * sx, j + 193u < Ny ? u.y * sy : 0.0); }
+            } else {   // an intermediate round: the dummy column must stay zero
+              if (j + 1u >= Ny) q0.y = 0.0;
+              if (j + 65u >= Ny) q1.y = 0.0;
+              if (j + 129u >= Ny) q2.y = 0.0;
+              if (j + 193u >= Ny) q3.y = 0.0;
             }
-            // (column Ny of the buffer is the dummy column: never written here)
-            if (v0) { sts_f64(rb + 8u * R * j, q0.x); if (j + 1u < Ny) sts_f64(rb + 8u * R * (j + 1u), q0.y); }
-            if (v1) { sts_f64(rb + 8u * R * (j + 64u), q1.x); if (j + 65u < Ny) sts_f64(rb + 8u * R * (j + 65u), q1.y); }
-            if (v2) { sts_f64(rb + 8u * R * (j + 128u), q2.x); if (j + 129u < Ny) sts_f64(rb + 8u * R * (j + 129u), q2.y); }
-            if (v3) { sts_f64(rb + 8u * R * (j + 192u), q3.x); if (j + 193u < Ny) sts_f64(rb + 8u * R * (j + 193u), q3.y); }
+            if (v0) sts_v2f64(rj, q0);
+            if (v1) sts_v2f64(rj + 512u, q1);
+            if (v2) sts_v2f64(rj + 1024u, q2);
+            if (v3) sts_v2f64(rj + 1536u, q3);
           }
           if (e1 == e0) break;
         }
@@ -369,24 +349,20 @@ __global__ void __launch_bounds__(32 * kFastMaxWarps, 1) stem_fast_kernel(const 
           const double xql = x23.y, xbf = x45.x;
           const uint32_t tabx = sb + L.tab + 128u * xbc;
           double racc = 0.0;
-#ifdef ABL_NO_B1
-          for (uint32_t tq = lo + lane; tq < lo; tq += 32u) {
-#else
           for (uint32_t tq = lo + lane; tq < hi; tq += 32u) {
-#endif
             const uint32_t j = lds_u32(yPerm + 4u * tq) & 0xffffu;
             const uint4 rec = lds_v4u32(yB2 + 16u * j);
             const double2 ya = lds_v2f64(sb + L.yB1a + 16u * j);   // {s2_y, el_y}
             const double2 yb = lds_v2f64(sb + L.yB1b + 16u * j);   // {bfreq_y*up_y, paths_y*dn_y}
             const double tv = lds_f64(tabx + 8u * (rec.x & 0xffu));
-            uint32_t e = yC + 4u * (rec.x >> 8);
-            const uint32_t eend = e + 16u * (rec.y & 0xffffu);
+            uint32_t e = yC + 2u * (rec.x >> 8);
+            const uint32_t eend = e + 8u * (rec.y & 0xffffu);
             double R0 = 0.0, R1 = 0.0;
 #pragma unroll 1
-            for (; e < eend; e += 16u) {
-              const uint4 c4 = lds_v4u32(e);
-              R0 += lds_f64(rb + c4.x) + lds_f64(rb + c4.y);
-              R1 += lds_f64(rb + c4.z) + lds_f64(rb + c4.w);
+            for (; e < eend; e += 8u) {
+              const uint2 c4 = lds_v2u32(e);
+              R0 += lds_f64(rb + (c4.x & 0xffffu)) + lds_f64(rb + (c4.x >> 16));
+              R1 += lds_f64(rb + (c4.y & 0xffffu)) + lds_f64(rb + (c4.y >> 16));
             }
             const double vs = tv * xbf * yb.x;
             const double mp = vs * fma(ya.y, xql, ya.x * (R0 + R1));   // up_y * M(i,j)
@@ -397,163 +373,79 @@ __global__ void __launch_bounds__(32 * kFastMaxWarps, 1) stem_fast_kernel(const 
           if (lane == 0) rowacc[i] = x45.y * racc;   // per-row slot in global scratch (L2)
         }
         __syncwarp();
-        // ---- Z: the row's part of the buffer becomes the H row: zero, then the band's up_y*M
-        for (uint32_t j = lane; j <= Ny; j += 32u) sts_f64(rb + 8u * R * j, 0.0);
+        // ---- Z: the row buffer becomes the H row: zero, then the band's up_y*M
+        for (uint32_t j = 2u * lane; j <= Ny; j += 64u) sts_v2f64(rb + 8u * j, make_double2(0.0, 0.0));
         __syncwarp();
         for (uint32_t tq = lo + lane; tq < hi; tq += 32u)
-          sts_f64(rb + 8u * R * (lds_u32(yPerm + 4u * tq) & 0xffffu), lds_f64(mbuf + 8u * (tq - lo)));
+          sts_f64(rb + 8u * (lds_u32(yPerm + 4u * tq) & 0xffffu), lds_f64(mbuf + 8u * (tq - lo)));
         __syncwarp();
         PROF_T(t_b1);
         PROF_ADD(2, t_a1, t_b1);
       }
 
-#if STEMK_B2MAP == 1
-      // ---- phase B2: sweep the y DAG level by level; lanes <-> (node slot, row of the block): the R lanes of a slot
-      // read R consecutive doubles of the interleaved buffer, and share the slot's node record and index loads
+      // ---- phase B2: sweep the y DAG level by level; lanes <-> (row r of the block, node slot s): the rows of the
+      // block share every instruction of the sweep
       PROF_T(t_b2a);
       {
         constexpr uint32_t nslot = 32u / R;
-        const uint32_t r = lane % R, slot = lane / R;
+        const uint32_t r = lane / nslot, slot = lane % nslot;
         const bool live = r < cnt;
         const uint32_t xl = __ldg(&X.xnode[ps.node0 + i0 + (live ? r : 0u)].len);
         // below the window (len_y + band < len_x) G1 is identically 0: length-monotone DAG
         const uint32_t len_lo = (band != 0u && xl > band) ? xl - band : 0u;
-        const uint32_t rbase = wbuf + 8u * r;
+        const uint32_t hrow = wrows + row_bytes * r;
         uint32_t jbeg = lds_u32(yLev);
-#ifdef ABL_NO_B2
-        for (uint32_t ly = 0; ly < 1u; ++ly) {
-#else
         for (uint32_t ly = 0; ly < ry.nlev; ++ly) {
-#endif
           const uint32_t jend = lds_u32(yLev + 4u * ly + 4u);
           for (uint32_t j = jbeg + slot; live && j < jend; j += nslot) {
             const uint4 rec = lds_v4u32(yB2 + 16u * j);
             if ((rec.y >> 16) < len_lo) break;   // nodes of a level are sorted by length, longest first
-            const uint32_t e = yC + 4u * (rec.x >> 8);
-            const uint32_t n4 = rec.y & 0xffffu;
-            const uint32_t hj0 = rbase + 8u * R * j;
-            const double hold = lds_f64(hj0);
-            // the first three rounds of four children are straight-line code: index loads first, then the gathers
-            // (lanes with fewer children read the all-zero dummy column), so that their latencies overlap
-            uint4 ca = make_uint4(dmy, dmy, dmy, dmy), cb = ca, cc = ca;
-            if (n4 > 0u) ca = lds_v4u32(e);
-            if (n4 > 1u) cb = lds_v4u32(e + 16u);
-            if (n4 > 2u) cc = lds_v4u32(e + 32u);
-            double S0 = lds_f64(rbase + ca.x) + lds_f64(rbase + ca.y);
-            double S1 = lds_f64(rbase + ca.z) + lds_f64(rbase + ca.w);
-            if (n4 > 1u) {
-              S0 += lds_f64(rbase + cb.x) + lds_f64(rbase + cb.y);
-              S1 += lds_f64(rbase + cb.z) + lds_f64(rbase + cb.w);
-            }
-            if (n4 > 2u) {
-              S0 += lds_f64(rbase + cc.x) + lds_f64(rbase + cc.y);
-              S1 += lds_f64(rbase + cc.z) + lds_f64(rbase + cc.w);
+            uint32_t e = yC + 2u * (rec.x >> 8);
+            const uint32_t eend = e + 8u * (rec.y & 0xffffu);
+            double S0 = 0.0, S1 = 0.0;
 #pragma unroll 1
-              for (uint32_t k = 3u; k < n4; ++k) {
-                const uint4 c4 = lds_v4u32(e + 16u * k);
-                S0 += lds_f64(rbase + c4.x) + lds_f64(rbase + c4.y);
-                S1 += lds_f64(rbase + c4.z) + lds_f64(rbase + c4.w);
-              }
+            for (; e < eend; e += 8u) {
+              const uint2 c4 = lds_v2u32(e);
+              S0 += lds_f64(hrow + (c4.x & 0xffffu)) + lds_f64(hrow + (c4.x >> 16));
+              S1 += lds_f64(hrow + (c4.y & 0xffffu)) + lds_f64(hrow + (c4.y >> 16));
             }
-            sts_f64(hj0, fma(__hiloint2double((int)rec.w, (int)rec.z), S0 + S1, hold));   // up_y*M + up_y*a_y*s2_y*sum
+            const uint32_t hj = hrow + 8u * j;
+            sts_f64(hj, fma(__hiloint2double((int)rec.w, (int)rec.z), S0 + S1, lds_f64(hj)));   // up_y*M + up_y*a_y*s2_y*sum
           }
           jbeg = jend;
           __syncwarp();
         }
       }
-#else
-      // ---- phase B2: sweep the y DAG level by level; lanes <-> nodes of the level, every lane carries all rows
-      PROF_T(t_b2a);
-      {
-        // below the window (len_y + band < len_x) G1 is identically 0: length-monotone DAG.  A row whose own window
-        // starts above the block's gets zeros there by itself (its buffer is zero below its window).
-        uint32_t jbeg = lds_u32(yLev);
-        for (uint32_t ly = 0; ly < ry.nlev; ++ly) {
-          const uint32_t jend = lds_u32(yLev + 4u * ly + 4u);
-          for (uint32_t jj = jbeg; jj < jend; jj += 32u) {   // uniform
-            const uint32_t j = jj + lane;
-            uint4 rec = make_uint4(0u, 0u, 0u, 0u);
-            if (j < jend) rec = lds_v4u32(yB2 + 16u * j);
-            const bool act = j < jend && (rec.y >> 16) >= len_lo_blk;   // nodes of a level: longest first
-            const uint32_t n4 = act ? (rec.y & 0xffffu) : 0u;
-            const uint32_t vote = __ballot_sync(0xffffffffu, act);
-            if (vote == 0u) break;
-            const uint32_t m = __reduce_max_sync(0xffffffffu, n4);   // rounds of four children the warp needs
-            const uint32_t e = yC + 4u * (rec.x >> 8);
-            double S[R];
-#pragma unroll
-            for (uint32_t h = 0; h < R; ++h) S[h] = 0.0;
-            const uint4 dz = make_uint4(dmy, dmy, dmy, dmy);
-            if (m != 0u) {
-              // the first three rounds are straight-line code (index loads first, then the gathers); lanes with
-              // fewer children read the all-zero dummy column
-              uint4 ca = dz, cb = dz, cc = dz;
-              if (n4 > 0u) ca = lds_v4u32(e);
-              if (m > 1u && n4 > 1u) cb = lds_v4u32(e + 16u);
-              if (m > 2u && n4 > 2u) cc = lds_v4u32(e + 32u);
-              gather4(wbuf, ca, S);
-              if (m > 1u) gather4(wbuf, cb, S);
-              if (m > 2u) gather4(wbuf, cc, S);
-              for (uint32_t k = 3u; k < m; ++k) {
-                uint4 cd = dz;
-                if (n4 > k) cd = lds_v4u32(e + 16u * k);
-                gather4(wbuf, cd, S);
-              }
-            }
-            if (act) {
-              const double coef = __hiloint2double((int)rec.w, (int)rec.z);
-              const uint32_t hj = wbuf + 8u * R * j;
-              if (R == 1) {
-                sts_f64(hj, fma(coef, S[0], lds_f64(hj)));   // up_y*M + up_y*a_y*s2_y*sum
-              } else {
-#pragma unroll
-                for (uint32_t h = 0; h < R; h += 2u) {
-                  const double2 old = lds_v2f64(hj + 8u * h);
-                  sts_v2f64(hj + 8u * h, make_double2(fma(coef, S[h], old.x), fma(coef, S[h + 1u], old.y)));
-                }
-              }
-            }
-            if (vote != 0xffffffffu) break;   // the window of this level ended inside this chunk
-          }
-          jbeg = jend;
-          __syncwarp();
-        }
-      }
-#endif
       PROF_T(t_b2b);
       PROF_ADD(3, t_b2a, t_b2b);
 
       // ---- phase C: G0s(i,:) += up_x * dn_y * H(i,:), then publish the rows
-#ifdef ABL_NO_C
-      for (uint32_t rr = 0; rr < 0u; ++rr) {
-#else
       for (uint32_t rr = 0; rr < cnt; ++rr) {
-#endif
         const uint32_t i = i0 + rr;
-        const uint32_t rb = wbuf + 8u * rr;
+        const uint32_t rb = wrows + row_bytes * rr;
         const double xup = __ldg(&X.xnode[ps.node0 + i].up);
         double* __restrict__ g0row = G0 + (size_t)i * NYS;
-        for (uint32_t jb = 0; jb < Ny; jb += 512u) {
-          // eight 64-column chunks per trip: every read of the slab is issued before the first use
+        for (uint32_t jb = 0; jb < Ny; jb += 256u) {
           const uint32_t j = jb + 2u * lane;
-          double2 hv[8], ov[8];
-          bool wv[8];
+          const uint32_t rj = rb + 8u * j;
+          double2 h0 = make_double2(0.0, 0.0), h1 = h0, h2 = h0, h3 = h0;
+          // column Ny of the buffer is the dummy column (zero), so the second element of the last pair is harmless
+          if (j < Ny) h0 = lds_v2f64(rj);
+          if (j + 64u < Ny) h1 = lds_v2f64(rj + 512u);
+          if (j + 128u < Ny) h2 = lds_v2f64(rj + 1024u);
+          if (j + 192u < Ny) h3 = lds_v2f64(rj + 1536u);
+          const bool w0 = h0.x != 0.0 || h0.y != 0.0, w1 = h1.x != 0.0 || h1.y != 0.0;
+          const bool w2 = h2.x != 0.0 || h2.y != 0.0, w3 = h3.x != 0.0 || h3.y != 0.0;
           double2* __restrict__ gp = reinterpret_cast<double2*>(g0row + j);
-#pragma unroll
-          for (uint32_t k = 0; k < 8u; ++k) {
-            // column Ny of the buffer is the dummy column (zero), so the second element of the last pair is harmless
-            hv[k] = make_double2(0.0, 0.0);
-            if (j + 64u * k < Ny) { hv[k].x = lds_f64(rb + 8u * R * (j + 64u * k)); hv[k].y = lds_f64(rb + 8u * R * (j + 64u * k + 1u)); }
-            wv[k] = hv[k].x != 0.0 || hv[k].y != 0.0;
-          }
-#pragma unroll
-          for (uint32_t k = 0; k < 8u; ++k) { ov[k] = hv[k]; if (wv[k]) ov[k] = __ldcg(gp + 32u * k); }
-#pragma unroll
-          for (uint32_t k = 0; k < 8u; ++k)
-            if (wv[k]) {
-              const double2 d = lds_v2f64(yDn + 8u * (j + 64u * k));
-              gp[32u * k] = make_double2(fma(xup, d.x * hv[k].x, ov[k].x), fma(xup, d.y * hv[k].y, ov[k].y));
-            }
+          double2 o0 = h0, o1 = h0, o2 = h0, o3 = h0;
+          if (w0) o0 = __ldcg(gp);
+          if (w1) o1 = __ldcg(gp + 32);
+          if (w2) o2 = __ldcg(gp + 64);
+          if (w3) o3 = __ldcg(gp + 96);
+          if (w0) { const double2 d = lds_v2f64(yDn + 8u * j); gp[0] = make_double2(fma(xup, d.x * h0.x, o0.x), fma(xup, d.y * h0.y, o0.y)); }
+          if (w1) { const double2 d = lds_v2f64(yDn + 8u * (j + 64u)); gp[32] = make_double2(fma(xup, d.x * h1.x, o1.x), fma(xup, d.y * h1.y, o1.y)); }
+          if (w2) { const double2 d = lds_v2f64(yDn + 8u * (j + 128u)); gp[64] = make_double2(fma(xup, d.x * h2.x, o2.x), fma(xup, d.y * h2.y, o2.y)); }
+          if (w3) { const double2 d = lds_v2f64(yDn + 8u * (j + 192u)); gp[96] = make_double2(fma(xup, d.x * h3.x, o3.x), fma(xup, d.y * h3.y, o3.y)); }
         }
       }
       __threadfence_block();
@@ -584,8 +476,7 @@ __global__ void __launch_bounds__(32 * kFastMaxWarps, 1) stem_fast_kernel(const 
     }
   }
 #ifdef FAST_PROF
-  if (lane == 0 && P.prof)
-  {
+  if (lane == 0 && P.prof) {
     for (int q = 0; q < 8; ++q) atomicAdd(P.prof + q, (unsigned long long)prof_acc[q]);
     atomicAdd(P.prof + 8, (unsigned long long)prof_gwait);
     atomicAdd(P.prof + 9, (unsigned long long)(clock64() - prof_t00));

@@ -46,6 +46,8 @@ struct stemk_set {
   DevBuf blob;        // every array of the view in one allocation
   SetView view;       // device pointers
   int device = 0;
+  double loop_gap = 0;      // the parameters the derived tables were built under
+  uint32_t len_band = 0;
 };
 
 struct stemk_ctx {
@@ -59,8 +61,12 @@ struct stemk_ctx {
   double* d_subst = nullptr;
   unsigned long long* d_counter = nullptr;
   DevBuf scratch, carry, tmp_stem, tmp_str, idx_x, idx_y, vals, matrix, order, rowacc;
+  DevBuf perm, offs, diag, selfv, diag_idx, diag_vals, diag_idx2, diag_vals2;
+  void* stage[2] = {nullptr, nullptr};          // pinned host staging (copy_out / copy_in)
+  cudaEvent_t stage_ev[2] = {nullptr, nullptr};
   unsigned long long* d_bucket = nullptr;  // count[16] | start[16] | queue heads[16]
-  int use_fast = 1;                        // STEMK_FAST=0 in the environment forces the general stem kernel
+  int use_fast = 1;                        // stemk_set_option(STEMK_OPT_FORCE_GENERAL, 1) routes every pair to the general stem kernel
+  int timing = 0;                          // stemk_set_option(STEMK_OPT_TIMING, 1): host-side breakdown of the calls on stderr
   std::string err;
   // stats
   uint64_t launches = 0;
@@ -103,6 +109,10 @@ int fail(stemk_ctx* c, int code, const std::string& msg) {
 int cuda_fail(stemk_ctx* c, cudaError_t e, const char* where) {
   return fail(c, STEMK_ERR_CUDA, std::string(where) + ": " + cudaGetErrorString(e));
 }
+bool set_usable(const stemk_ctx* ctx, const stemk_set* s) {
+  return s->device == ctx->device && s->loop_gap == ctx->params.loop_gap && s->len_band == ctx->params.len_band;
+}
+const char* kSetMismatch = "set was uploaded through a context with another device, loop gap or length band";
 int no_device(stemk_ctx* c) {
   return fail(c, STEMK_ERR_CUDA, "host-only context: kernel values are computed on a CUDA device only (no CPU path)");
 }
@@ -173,7 +183,6 @@ int stemk_create(stemk_ctx** out, const stemk_params* params, int device) {
   c->smem_optin = prop.sharedMemPerBlockOptin;
   c->params = *params;
   make_tables(*params, &c->tables);
-  if (const char* f = std::getenv("STEMK_FAST")) c->use_fast = std::atoi(f);
   bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaMalloc((void**)&c->d_pair_tab, sizeof(double) * 256) == cudaSuccess &&
             cudaMalloc((void**)&c->d_subst, sizeof(double) * 16) == cudaSuccess &&
@@ -191,12 +200,23 @@ int stemk_create(stemk_ctx** out, const stemk_params* params, int device) {
   return STEMK_OK;
 }
 
+int stemk_set_option(stemk_ctx* ctx, int option, int value) {
+  if (!ctx) return fail(ctx, STEMK_ERR_ARG, "null argument");
+  switch (option) {
+    case STEMK_OPT_FORCE_GENERAL: ctx->use_fast = value ? 0 : 1; return STEMK_OK;
+    case STEMK_OPT_TIMING: ctx->timing = value; return STEMK_OK;
+    default: return fail(ctx, STEMK_ERR_ARG, "unknown option");
+  }
+}
+
 void stemk_destroy(stemk_ctx* c) {
   if (!c) return;
   if (c->device == STEMK_DEVICE_NONE) { delete c; return; }
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  for (DevBuf* b : {&c->scratch, &c->carry, &c->tmp_stem, &c->tmp_str, &c->idx_x, &c->idx_y, &c->vals, &c->matrix, &c->order, &c->rowacc}) b->release();
+  for (DevBuf* b : {&c->scratch, &c->carry, &c->tmp_stem, &c->tmp_str, &c->idx_x, &c->idx_y, &c->vals, &c->matrix, &c->order, &c->rowacc,
+                    &c->perm, &c->offs, &c->diag, &c->selfv, &c->diag_idx, &c->diag_vals, &c->diag_idx2, &c->diag_vals2}) b->release();
+  for (int k = 0; k < 2; ++k) { if (c->stage[k]) cudaFreeHost(c->stage[k]); if (c->stage_ev[k]) cudaEventDestroy(c->stage_ev[k]); }
   if (c->d_pair_tab) cudaFree(c->d_pair_tab);
   if (c->d_subst) cudaFree(c->d_subst);
   if (c->d_counter) cudaFree(c->d_counter);
@@ -215,8 +235,13 @@ int stemk_upload(stemk_ctx* ctx, const stemk_seqset_desc* desc, stemk_set** out)
   if (ctx->device != STEMK_DEVICE_NONE) CU(cudaSetDevice(ctx->device));
   stemk_set* s = new stemk_set;
   s->device = ctx->device;
+  s->loop_gap = ctx->params.loop_gap;
+  s->len_band = ctx->params.len_band;
   const int n_threads = (int)std::min<unsigned>(16, std::max(1u, std::thread::hardware_concurrency()));
-  std::string err = compile_set(*desc, ctx->params.loop_gap, ctx->params.len_band, n_threads, &s->host);
+  std::string err;
+  try { err = compile_set(*desc, ctx->params.loop_gap, ctx->params.len_band, n_threads, ctx->timing != 0, &s->host); }
+  catch (const std::bad_alloc&) { delete s; return fail(ctx, STEMK_ERR_NOMEM, "out of host memory while compiling the record set"); }
+  catch (const std::exception& ex) { delete s; return fail(ctx, STEMK_ERR_ARG, std::string("record set: ") + ex.what()); }
   if (!err.empty()) { delete s; return fail(ctx, STEMK_ERR_ARG, err); }
   const CompiledSet& h = s->host;
   if (ctx->device == STEMK_DEVICE_NONE) { *out = s; return STEMK_OK; }
@@ -286,6 +311,7 @@ int stemk_pairs_device(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, s
   if (ctx->device == STEMK_DEVICE_NONE) return no_device(ctx);
   if (n_pairs == 0) return STEMK_OK;
   if (!d_xi || !d_yi || !d_out) return fail(ctx, STEMK_ERR_ARG, "null buffer");
+  if (!set_usable(ctx, x) || !set_usable(ctx, y)) return fail(ctx, STEMK_ERR_ARG, kSetMismatch);
   CU(cudaSetDevice(ctx->device));
   cudaStream_t st = stream_ ? (cudaStream_t)stream_ : ctx->stream;
   const int kind = ctx->params.kind;
@@ -438,6 +464,58 @@ int stemk_pairs_device(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, s
   return STEMK_OK;
 }
 
+// ---- host <-> device staging ------------------------------------------------------------------------------------
+// Results travel through two pinned buffers of the context: the DMA of chunk c+1 runs while the host copies chunk c
+// into the caller's (pageable) buffer; one cudaMemcpyAsync per chunk.
+namespace {
+constexpr size_t kStageBytes = (size_t)8 << 20;
+
+int stage_reserve(stemk_ctx* ctx) {
+  for (int k = 0; k < 2; ++k)
+    if (!ctx->stage[k]) {
+      CU(cudaHostAlloc(&ctx->stage[k], kStageBytes, cudaHostAllocDefault));
+      CU(cudaEventCreateWithFlags(&ctx->stage_ev[k], cudaEventDisableTiming));
+    }
+  return STEMK_OK;
+}
+
+// dst[0 .. bytes) <- device src, after everything queued on the context's stream; returns when dst is complete
+int copy_out(stemk_ctx* ctx, void* dst, const void* d_src, size_t bytes) {
+  if (bytes == 0) return STEMK_OK;
+  if (int rc = stage_reserve(ctx)) return rc;
+  const size_t n_chunks = (bytes + kStageBytes - 1) / kStageBytes;
+  for (size_t c = 0; c <= n_chunks; ++c) {
+    if (c < n_chunks) {
+      const size_t off = c * kStageBytes, sz = std::min(kStageBytes, bytes - off);
+      CU(cudaMemcpyAsync(ctx->stage[c & 1], static_cast<const char*>(d_src) + off, sz, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaEventRecord(ctx->stage_ev[c & 1], ctx->stream));
+    }
+    if (c > 0) {
+      const size_t off = (c - 1) * kStageBytes, sz = std::min(kStageBytes, bytes - off);
+      CU(cudaEventSynchronize(ctx->stage_ev[(c - 1) & 1]));
+      std::memcpy(static_cast<char*>(dst) + off, ctx->stage[(c - 1) & 1], sz);
+    }
+  }
+  return STEMK_OK;
+}
+
+// device dst <- host src through the pinned buffers (index lists of stemk_pairs)
+int copy_in(stemk_ctx* ctx, void* d_dst, const void* src, size_t bytes) {
+  if (bytes == 0) return STEMK_OK;
+  if (int rc = stage_reserve(ctx)) return rc;
+  const size_t n_chunks = (bytes + kStageBytes - 1) / kStageBytes;
+  for (size_t c = 0; c < n_chunks; ++c) {
+    const size_t off = c * kStageBytes, sz = std::min(kStageBytes, bytes - off);
+    if (c >= 2) CU(cudaEventSynchronize(ctx->stage_ev[c & 1]));   // the DMA that last read this buffer
+    std::memcpy(ctx->stage[c & 1], static_cast<const char*>(src) + off, sz);
+    CU(cudaMemcpyAsync(static_cast<char*>(d_dst) + off, ctx->stage[c & 1], sz, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaEventRecord(ctx->stage_ev[c & 1], ctx->stream));
+  }
+  return STEMK_OK;
+}
+
+}  // namespace
+
 int stemk_pairs(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, size_t n_pairs, const uint32_t* xi,
                 const uint32_t* yi, double* out) {
   if (!ctx || !x || !y) return fail(ctx, STEMK_ERR_ARG, "null argument");
@@ -450,26 +528,29 @@ int stemk_pairs(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, size_t n
   CU(ctx->idx_x.reserve(n_pairs * sizeof(uint32_t)));
   CU(ctx->idx_y.reserve(n_pairs * sizeof(uint32_t)));
   CU(ctx->vals.reserve(n_pairs * sizeof(double)));
-  CU(cudaMemcpyAsync(ctx->idx_x.p, xi, n_pairs * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(ctx->idx_y.p, yi, n_pairs * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  if (int rc = copy_in(ctx, ctx->idx_x.p, xi, n_pairs * sizeof(uint32_t))) return rc;
+  if (int rc = copy_in(ctx, ctx->idx_y.p, yi, n_pairs * sizeof(uint32_t))) return rc;
   int rc = stemk_pairs_device(ctx, x, y, n_pairs, (const uint32_t*)ctx->idx_x.p, (const uint32_t*)ctx->idx_y.p,
                               (double*)ctx->vals.p, ctx->stream);
   if (rc != STEMK_OK) return rc;
-  // wait for the kernels first: a copy into pageable memory queued behind seconds of device work was measured to cost
-  // several hundred milliseconds more than the same copy issued on an idle stream (see stemk_gram)
-  CU(cudaStreamSynchronize(ctx->stream));
-  CU(cudaMemcpyAsync(out, ctx->vals.p, n_pairs * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
-  return STEMK_OK;
+  return copy_out(ctx, out, ctx->vals.p, n_pairs * sizeof(double));
 }
 
 // -------------------------------------------------------------------------- Gram drivers
-// Rough per-pair cost used only to order the work queue (largest first).
-static inline double sched_cost(const stemk_ctx* ctx, const CompiledSet& a, uint32_t i, const CompiledSet& b, uint32_t j) {
+// Rough per-record size key used only to order the work queue (largest first).
+static inline double size_key(const stemk_ctx* ctx, const CompiledSet& a, uint32_t i) {
   double c = 0;
-  if (kind_has_stem(ctx->params.kind)) c += (double)a.n_nodes_all[i] * b.n_edges_all[j] + (double)a.n_edges_all[i] * b.n_nodes_all[j];
-  if (kind_has_string(ctx->params.kind)) c += (double)a.rec[i].L * b.rec[j].L;
+  if (kind_has_stem(ctx->params.kind)) c += 2.0 * (double)a.n_nodes_all[i] * a.n_edges_all[i];
+  if (kind_has_string(ctx->params.kind)) c += (double)a.rec[i].L * a.rec[i].L;
   return c;
+}
+static std::vector<uint32_t> size_order(const stemk_ctx* ctx, const CompiledSet& h, const uint32_t* subset, uint32_t n) {
+  std::vector<uint32_t> perm(n);
+  std::vector<double> key(n);
+  for (uint32_t i = 0; i < n; ++i) { perm[i] = i; key[i] = size_key(ctx, h, subset ? subset[i] : i); }
+  std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) { return key[a] > key[b]; });
+  if (subset) for (uint32_t& v : perm) v = subset[v];
+  return perm;
 }
 
 int stemk_gram(stemk_ctx* ctx, const stemk_set* train, int normalize, double* out) {
@@ -478,39 +559,31 @@ int stemk_gram(stemk_ctx* ctx, const stemk_set* train, int normalize, double* ou
   if (ctx->device == STEMK_DEVICE_NONE) return no_device(ctx);
   if (n == 0) return STEMK_OK;
   CU(cudaSetDevice(ctx->device));
-  const bool timing = std::getenv("STEMK_TIMING") != nullptr;
+  const bool timing = ctx->timing != 0;
   auto now = []() { return std::chrono::steady_clock::now(); };
   auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
     return std::chrono::duration<double, std::milli>(b - a).count(); };
   const auto tg0 = now();
-  // records sorted by size, big first: the queue then hands out the expensive pairs first
-  std::vector<uint32_t> perm(n);
-  std::iota(perm.begin(), perm.end(), 0u);
-  std::vector<double> size_key(n);
-  for (uint32_t i = 0; i < n; ++i) size_key[i] = sched_cost(ctx, train->host, i, train->host, i);
-  std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) { return size_key[a] > size_key[b]; });
+  // records sorted by size, big first: the queue then hands out the expensive pairs first.  The y-major pair list
+  // itself (for every record b all partners a <= b: consecutive pairs share their y record, which the stem kernel
+  // stages once per group of pairs) is written by the device from the permutation: row q owns perm[q] + 1 pairs.
+  const std::vector<uint32_t> perm = size_order(ctx, train->host, nullptr, n);
+  std::vector<unsigned long long> off(n);
+  unsigned long long acc = 0;
+  for (uint32_t q = 0; q < n; ++q) { off[q] = acc; acc += (unsigned long long)perm[q] + 1ull; }
   const size_t n_pairs = (size_t)n * (n + 1) / 2;
-  std::vector<uint32_t> xi(n_pairs), yi(n_pairs);
-  // y-major work order: for every record b (big first) all partners a <= b (big first).  The reference evaluates
-  // kernel_(train[i], train[j]) with i <= j (kernel_matrix.cpp:47-50) and the stem kernel is not symmetric in
-  // its arguments, so x = the smaller ORIGINAL index.  Consecutive pairs share their y record, which the stem
-  // kernel stages once per group of pairs.
-  size_t k = 0;
-  for (uint32_t q = 0; q < n; ++q) {
-    const uint32_t b = perm[q];
-    for (uint32_t p = 0; p < n; ++p) {
-      const uint32_t a = perm[p];
-      if (a > b) continue;
-      xi[k] = a; yi[k] = b; ++k;
-    }
-  }
-  const auto tg1 = now();
   CU(ctx->idx_x.reserve(n_pairs * sizeof(uint32_t)));
   CU(ctx->idx_y.reserve(n_pairs * sizeof(uint32_t)));
   CU(ctx->vals.reserve(n_pairs * sizeof(double)));
   CU(ctx->matrix.reserve((size_t)n * n * sizeof(double)));
-  CU(cudaMemcpyAsync(ctx->idx_x.p, xi.data(), n_pairs * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(ctx->idx_y.p, yi.data(), n_pairs * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  CU(ctx->perm.reserve(n * sizeof(uint32_t)));
+  CU(ctx->offs.reserve(n * sizeof(unsigned long long)));
+  CU(cudaMemcpyAsync(ctx->perm.p, perm.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->offs.p, off.data(), n * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+  CU(launch_gram_pairs((const uint32_t*)ctx->perm.p, (const unsigned long long*)ctx->offs.p, n, (uint32_t*)ctx->idx_x.p,
+                       (uint32_t*)ctx->idx_y.p, ctx->stream));
+  ctx->launches += 1;
+  const auto tg1 = now();
   int rc = stemk_pairs_device(ctx, train, train, n_pairs, (const uint32_t*)ctx->idx_x.p, (const uint32_t*)ctx->idx_y.p,
                               (double*)ctx->vals.p, ctx->stream);
   if (rc != STEMK_OK) return rc;
@@ -518,14 +591,13 @@ int stemk_gram(stemk_ctx* ctx, const stemk_set* train, int normalize, double* ou
                              (const double*)ctx->vals.p, n, normalize, (double*)ctx->matrix.p, ctx->stream);
   if (rc != STEMK_OK) return rc;
   const auto tg2 = now();
-  CU(cudaStreamSynchronize(ctx->stream));
+  if (timing) CU(cudaStreamSynchronize(ctx->stream));
   const auto tg3 = now();
-  CU(cudaMemcpyAsync(out, ctx->matrix.p, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  const auto tg4 = now();
-  CU(cudaStreamSynchronize(ctx->stream));
+  rc = copy_out(ctx, out, ctx->matrix.p, (size_t)n * n * sizeof(double));
+  if (rc != STEMK_OK) return rc;
   if (timing)
-    std::fprintf(stderr, "stemk_gram: %u records: pair list %.1f ms, enqueue %.1f ms, device %.1f ms, D2H call %.1f ms, sync %.1f ms\n", n,
-                 ms(tg0, tg1), ms(tg1, tg2), ms(tg2, tg3), ms(tg3, tg4), ms(tg4, now()));
+    std::fprintf(stderr, "stemk_gram: %u records: permutation + pair-list launch %.1f ms, enqueue %.1f ms, device %.1f ms, D2H through pinned staging %.1f ms\n", n,
+                 ms(tg0, tg1), ms(tg1, tg2), ms(tg2, tg3), ms(tg3, now()));
   return STEMK_OK;
 }
 
@@ -543,68 +615,106 @@ int stemk_assemble_device(stemk_ctx* ctx, size_t n_pairs, const uint32_t* d_xi, 
   return STEMK_OK;
 }
 
+// k(x_i, x_i) for i in idx (or all) into the DEVICE vector d_out[n] at the records' own positions
+static int diag_device(stemk_ctx* ctx, const stemk_set* set, const uint32_t* idx, uint32_t n_idx, double* d_out, DevBuf* d_idx,
+                       DevBuf* d_vals) {
+  const uint32_t n = (uint32_t)set->host.rec.size();
+  const uint32_t m = idx ? n_idx : n;
+  if (m == 0) return STEMK_OK;
+  CU(d_idx->reserve(m * sizeof(uint32_t)));
+  CU(d_vals->reserve(m * sizeof(double)));
+  if (idx) CU(cudaMemcpyAsync(d_idx->p, idx, m * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  else CU(launch_iota((uint32_t*)d_idx->p, m, ctx->stream));
+  int rc = stemk_pairs_device(ctx, set, set, m, (const uint32_t*)d_idx->p, (const uint32_t*)d_idx->p, (double*)d_vals->p, ctx->stream);
+  if (rc != STEMK_OK) return rc;
+  CU(launch_scatter_vec((const double*)d_vals->p, (const uint32_t*)d_idx->p, m, d_out, ctx->stream));
+  ctx->launches += 1 + (idx ? 0 : 1);
+  return STEMK_OK;
+}
+
 int stemk_diag(stemk_ctx* ctx, const stemk_set* train, const uint32_t* sv_index, uint32_t n_sv, double* out) {
   if (!ctx || !train || !out) return fail(ctx, STEMK_ERR_ARG, "null argument");
+  if (ctx->device == STEMK_DEVICE_NONE) return no_device(ctx);
   const uint32_t n = (uint32_t)train->host.rec.size();
-  std::vector<uint32_t> idx;
-  if (n_sv == 0) { idx.resize(n); std::iota(idx.begin(), idx.end(), 0u); }
-  else {
-    if (!sv_index) return fail(ctx, STEMK_ERR_ARG, "null sv_index");
-    idx.assign(sv_index, sv_index + n_sv);
-  }
-  std::vector<double> v(idx.size());
-  int rc = stemk_pairs(ctx, train, train, idx.size(), idx.data(), idx.data(), v.data());
+  if (n_sv && !sv_index) return fail(ctx, STEMK_ERR_ARG, "null sv_index");
+  for (uint32_t k = 0; k < n_sv; ++k) if (sv_index[k] >= n) return fail(ctx, STEMK_ERR_ARG, "sv_index out of range");
+  if (n == 0) return STEMK_OK;
+  CU(cudaSetDevice(ctx->device));
+  CU(ctx->diag.reserve(n * sizeof(double)));
+  int rc = diag_device(ctx, train, n_sv ? sv_index : nullptr, n_sv, (double*)ctx->diag.p, &ctx->diag_idx, &ctx->diag_vals);
   if (rc != STEMK_OK) return rc;
-  for (size_t k = 0; k < idx.size(); ++k) out[idx[k]] = v[k];
+  if (n_sv == 0) return copy_out(ctx, out, ctx->diag.p, n * sizeof(double));
+  // with an sv_index only those entries of `out` are written (KernelMatrix::diagonal, kernel_matrix.cpp:578-633)
+  std::vector<double> v(n_sv);
+  rc = copy_out(ctx, v.data(), ctx->diag_vals.p, n_sv * sizeof(double));
+  if (rc != STEMK_OK) return rc;
+  for (uint32_t k = 0; k < n_sv; ++k) out[sv_index[k]] = v[k];
   return STEMK_OK;
 }
 
 int stemk_cross(stemk_ctx* ctx, const stemk_set* test, const stemk_set* train, const uint32_t* sv_index, uint32_t n_sv,
                 int normalize, double* out, double* self_out) {
   if (!ctx || !test || !train || !out) return fail(ctx, STEMK_ERR_ARG, "null argument");
+  if (ctx->device == STEMK_DEVICE_NONE) return no_device(ctx);
   const uint32_t nt = (uint32_t)test->host.rec.size(), ns = (uint32_t)train->host.rec.size();
-  std::vector<uint32_t> cols;
-  if (n_sv == 0) { cols.resize(ns); std::iota(cols.begin(), cols.end(), 0u); }
-  else {
-    if (!sv_index) return fail(ctx, STEMK_ERR_ARG, "null sv_index");
-    cols.assign(sv_index, sv_index + n_sv);
-    for (uint32_t c : cols) if (c >= ns) return fail(ctx, STEMK_ERR_ARG, "sv_index out of range");
+  if (n_sv && !sv_index) return fail(ctx, STEMK_ERR_ARG, "null sv_index");
+  for (uint32_t k = 0; k < n_sv; ++k) if (sv_index[k] >= ns) return fail(ctx, STEMK_ERR_ARG, "sv_index out of range");
+  if (nt == 0 || ns == 0) return STEMK_OK;
+  CU(cudaSetDevice(ctx->device));
+  // rows k(train_x, test_i): the train record is the FIRST argument (kernel_matrix.cpp:159,168).  Work order: big
+  // test records first, big train records first inside each; the list is written by the device from the two
+  // permutations.  With an sv_index the device matrix is compact (nt x n_sv, column c = sv_index[c]).
+  const uint32_t nc = n_sv ? n_sv : ns;
+  const std::vector<uint32_t> tperm = size_order(ctx, test->host, nullptr, nt);
+  const std::vector<uint32_t> cperm = size_order(ctx, train->host, n_sv ? sv_index : nullptr, nc);
+  const size_t n_pairs = (size_t)nt * nc;
+  CU(ctx->idx_x.reserve(n_pairs * sizeof(uint32_t)));
+  CU(ctx->idx_y.reserve(n_pairs * sizeof(uint32_t)));
+  CU(ctx->vals.reserve(n_pairs * sizeof(double)));
+  CU(ctx->matrix.reserve(n_pairs * sizeof(double)));
+  CU(ctx->perm.reserve(((size_t)nt + nc + ns + nc) * sizeof(uint32_t)));
+  uint32_t* d_tperm = (uint32_t*)ctx->perm.p;
+  uint32_t* d_cperm = d_tperm + nt;
+  uint32_t* d_colof = d_cperm + nc;   // train record -> column of the compact matrix
+  uint32_t* d_cols = d_colof + ns;    // column of the compact matrix -> train record
+  CU(cudaMemcpyAsync(d_tperm, tperm.data(), nt * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(d_cperm, cperm.data(), nc * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  std::vector<uint32_t> colof;
+  if (n_sv) {
+    colof.assign(ns, 0u);
+    for (uint32_t c = 0; c < n_sv; ++c) colof[sv_index[c]] = c;
+    CU(cudaMemcpyAsync(d_colof, colof.data(), ns * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_cols, sv_index, n_sv * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
   }
-  // rows k(train_x, test_i): the train record is the FIRST argument (kernel_matrix.cpp:159,168)
-  const size_t n_pairs = (size_t)nt * cols.size();
-  std::vector<uint32_t> xi(n_pairs), yi(n_pairs);
-  // order: big test records first, big train records first inside each
-  std::vector<uint32_t> tperm(nt), cperm(cols.size());
-  std::iota(tperm.begin(), tperm.end(), 0u);
-  std::iota(cperm.begin(), cperm.end(), 0u);
-  std::stable_sort(tperm.begin(), tperm.end(), [&](uint32_t a, uint32_t b) {
-    return sched_cost(ctx, test->host, a, test->host, a) > sched_cost(ctx, test->host, b, test->host, b); });
-  std::stable_sort(cperm.begin(), cperm.end(), [&](uint32_t a, uint32_t b) {
-    return sched_cost(ctx, train->host, cols[a], train->host, cols[a]) > sched_cost(ctx, train->host, cols[b], train->host, cols[b]); });
-  size_t k = 0;
-  for (uint32_t t : tperm) for (uint32_t c : cperm) { xi[k] = cols[c]; yi[k] = t; ++k; }
-  std::vector<double> v(n_pairs);
-  int rc = stemk_pairs(ctx, train, test, n_pairs, xi.data(), yi.data(), v.data());
+  CU(launch_cross_pairs(d_tperm, d_cperm, nt, nc, (uint32_t*)ctx->idx_x.p, (uint32_t*)ctx->idx_y.p, ctx->stream));
+  int rc = stemk_pairs_device(ctx, train, test, n_pairs, (const uint32_t*)ctx->idx_x.p, (const uint32_t*)ctx->idx_y.p,
+                              (double*)ctx->vals.p, ctx->stream);
   if (rc != STEMK_OK) return rc;
-  for (k = 0; k < n_pairs; ++k) out[(size_t)yi[k] * ns + xi[k]] = v[k];
-  std::vector<double> selfv;
+  CU(launch_scatter_cross((const double*)ctx->vals.p, (const uint32_t*)ctx->idx_x.p, (const uint32_t*)ctx->idx_y.p, n_pairs,
+                          n_sv ? d_colof : nullptr, (double*)ctx->matrix.p, nc, ctx->stream));
+  ctx->launches += 2;
   if (self_out || normalize) {
-    std::vector<uint32_t> id(nt);
-    std::iota(id.begin(), id.end(), 0u);
-    selfv.resize(nt);
-    rc = stemk_pairs(ctx, test, test, nt, id.data(), id.data(), selfv.data());
+    CU(ctx->selfv.reserve(nt * sizeof(double)));
+    rc = diag_device(ctx, test, nullptr, 0, (double*)ctx->selfv.p, &ctx->diag_idx, &ctx->diag_vals);
     if (rc != STEMK_OK) return rc;
-    if (self_out) std::memcpy(self_out, selfv.data(), nt * sizeof(double));
   }
   if (normalize) {
-    // kernel_matrix.cpp:735-748 over every column; columns outside sv_index keep a zero diagonal
-    // exactly like App::predict's diag vector (framework.h:188-189,282-286), i.e. they turn into NaN/inf
-    std::vector<double> diag(ns, 0.0);
-    rc = stemk_diag(ctx, train, n_sv ? cols.data() : nullptr, n_sv ? (uint32_t)cols.size() : 0, diag.data());
+    // kernel_matrix.cpp:735-748: out_ij /= sqrt(self_i * k(train_j, train_j)); with an sv_index only its columns exist
+    CU(ctx->diag.reserve(ns * sizeof(double)));
+    rc = diag_device(ctx, train, n_sv ? sv_index : nullptr, n_sv, (double*)ctx->diag.p, &ctx->diag_idx2, &ctx->diag_vals2);
     if (rc != STEMK_OK) return rc;
-    for (uint32_t i = 0; i < nt; ++i)
-      for (uint32_t j = 0; j < ns; ++j) out[(size_t)i * ns + j] /= std::sqrt(selfv[i] * diag[j]);
+    CU(launch_normalize_cross((double*)ctx->matrix.p, nt, nc, nc, (const double*)ctx->selfv.p, (const double*)ctx->diag.p,
+                              n_sv ? d_cols : nullptr, ctx->stream));
+    ctx->launches += 1;
   }
+  if (self_out) { rc = copy_out(ctx, self_out, ctx->selfv.p, nt * sizeof(double)); if (rc != STEMK_OK) return rc; }
+  if (n_sv == 0) return copy_out(ctx, out, ctx->matrix.p, n_pairs * sizeof(double));
+  // with an sv_index only those columns of `out` are written (static row calculate, kernel_matrix.cpp:635-697)
+  std::vector<double> v(n_pairs);
+  rc = copy_out(ctx, v.data(), ctx->matrix.p, n_pairs * sizeof(double));
+  if (rc != STEMK_OK) return rc;
+  for (uint32_t i = 0; i < nt; ++i)
+    for (uint32_t c = 0; c < n_sv; ++c) out[(size_t)i * ns + sv_index[c]] = v[(size_t)i * n_sv + c];
   return STEMK_OK;
 }
 

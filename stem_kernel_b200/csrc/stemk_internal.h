@@ -128,7 +128,7 @@ struct CompiledSet {
 
 // Builds the compiled form of every record of `desc` under loop gap `g` and length band `len_band` (0 = none).
 // Returns "" or an error.
-std::string compile_set(const stemk_seqset_desc& desc, double g, uint32_t len_band, int n_threads, CompiledSet* out);
+std::string compile_set(const stemk_seqset_desc& desc, double g, uint32_t len_band, int n_threads, bool timing, CompiledSet* out);
 
 // Kernel constants derived from stemk_params on the host with libm (same exp() the reference calls).
 struct KernelTables {

@@ -33,13 +33,12 @@ def _gpu():
 @pytest.mark.parametrize("kind", range(9))
 @pytest.mark.parametrize("band", [10, 0])
 @pytest.mark.parametrize("fast", ["1", "0"])
-def test_golden_gram(golden, kind, band, fast, monkeypatch):
+def test_golden_gram(golden, kind, band, fast):
     """fast=1: single-sequence records take the separable fast stem kernel, alignments the general one;
-    fast=0 forces the general kernel for every pair (STEMK_FAST is read when the context is created)."""
+    fast=0 forces the general kernel for every pair (stemk_set_option(STEMK_OPT_FORCE_GENERAL))."""
     if fast == "0" and kind in (L.STR_SUBST, L.STR_SIMPLE, L.LSU_STR):
         pytest.skip("no stem part")
-    monkeypatch.setenv("STEMK_FAST", fast)
-    ctx = api.Context(L.make_params(kind, len_band=band))
+    ctx = api.Context(L.make_params(kind, len_band=band)).set_option(L.OPT_FORCE_GENERAL, fast == "0")
     got = ctx.gram(ctx.upload(golden["flat"]))
     assert relerr(got, golden["z"][f"gram_k{kind}_b{band}"]) < TOL
     assert np.array_equal(got, got.T)
@@ -118,14 +117,12 @@ def test_loop_gap_range(g):
         assert relerr(ctx.gram(ctx.upload(flat)), O.gram(oparams(p), flat.desc(), False)) < TOL
 
 
-def test_fast_and_general_kernels_agree_and_fast_is_deterministic(monkeypatch):
+def test_fast_and_general_kernels_agree_and_fast_is_deterministic():
     recs = synth.make_config(3, 40, offset=2100)
     md = hostlib.build_many(recs, TH)
     p = L.make_params(L.SU_STEM)
-    monkeypatch.setenv("STEMK_FAST", "0")
-    cg = api.Context(p)
+    cg = api.Context(p).set_option(L.OPT_FORCE_GENERAL, 1)
     g_general = cg.gram(cg.upload(md))
-    monkeypatch.setenv("STEMK_FAST", "1")
     cf = api.Context(p)
     ds = cf.upload(md)
     g_fast = cf.gram(ds)

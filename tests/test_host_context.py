@@ -42,3 +42,25 @@ def test_upload_rejects_malformed_records():
     ctx = api.Context(L.make_params(L.SU_STEM), device=-1)
     with pytest.raises(api.StemkError, match="children before parents"):
         ctx.upload([bad])
+
+
+@pytest.mark.parametrize("case,msg", [("last_before_first", "first <= last"), ("last_outside", "first <= last"),
+                                      ("huge_gaps", "gap count"), ("no_rows", "n_rows")])
+def test_upload_validates_the_descriptor(case, msg):
+    """Hostile descriptors are refused with STEMK_ERR_ARG instead of sizing arrays from wrapped-around numbers
+    (ADVICE round 1): node_last < node_first, positions outside the sequence, absurd gap counts, n_rows = 0."""
+    f = dict(first=[2, 1], last=[2, 8], weight=[1.0, 1.0], edge_off=[0, 0, 1], edge_to=[0], edge_gaps=[6],
+             edge_w=[1.0], bpf_off=[0, 0, 1], bpf_a=[0], bpf_b=[3], bpf_f=[1.0], root=[1],
+             profile=np.zeros((10, 5), np.float32), n_seqs=1.0, seq_weight=[])
+    ctx = api.Context(L.make_params(L.SU_STEM), device=-1)
+    ctx.upload([hostlib.MData.from_arrays(f, "a" * 10)])          # the well-formed record is accepted
+    if case == "last_before_first":
+        f["last"] = [2, 0]
+    elif case == "last_outside":
+        f["last"] = [2, 10]
+    elif case == "huge_gaps":
+        f["edge_gaps"] = [4000000000]
+    else:
+        f["n_seqs"] = 0.0
+    with pytest.raises(api.StemkError, match=msg):
+        ctx.upload([hostlib.MData.from_arrays(f, "a" * 10)])
