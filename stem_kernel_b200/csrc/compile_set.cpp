@@ -184,6 +184,21 @@ void compile_record(const stemk_seqset_desc& s, uint32_t r, double g, uint32_t l
     for (uint32_t k = 0; k < order.size(); ++k) newidx[order[k]] = k;
   }
   const uint32_t N = (uint32_t)order.size();
+  {
+    // Levels are cut into SUB-LEVELS of at most 32/kFastRows nodes (still a valid children-first partition): the
+    // fast kernel then has at most one node per lane and step of its column sweep, and row blocks never straddle
+    // one.  sub1 = the first sub-level whose nodes have inner pairs (everything before it is level 0).
+    constexpr uint32_t kSlots = 32u / kFastRows;
+    std::vector<uint32_t> sub(1, 0u);
+    uint32_t sub1 = 0;
+    for (uint32_t l = 0; l < nlev; ++l) {
+      for (uint32_t g0 = o->lev_off[l]; g0 < o->lev_off[l + 1]; g0 += kSlots) sub.push_back(std::min(o->lev_off[l + 1], g0 + kSlots));
+      if (l == 0) sub1 = (uint32_t)sub.size() - 1u;
+    }
+    o->lev_off.swap(sub);
+    nlev = (uint32_t)o->lev_off.size() - 1u;
+    h.sub1 = sub1;
+  }
   h.N = N; h.nlev = nlev;
   o->a.resize(N); o->el.resize(N); o->ql.resize(N); o->paths.resize(N); o->gapt.resize(N); o->bfreq.resize(N);
   o->len.resize(N); o->bcode.resize(N); o->coff.assign(N + 1, 0); o->boff.assign(N + 1, 0);

@@ -35,6 +35,10 @@ constexpr uint32_t kFastGroup = STEMK_GROUP;  // == kGroup of stem_fast.cu
 #define STEMK_MAXWARPS 24
 #endif
 constexpr int kFastMaxWarps = STEMK_MAXWARPS;  // warps per CTA of the fast stem kernel (its launch bound)
+#ifndef STEMK_REGWARPS
+#define STEMK_REGWARPS 20
+#endif
+constexpr int kFastRegWarps = STEMK_REGWARPS;  // ... of its variants that keep a whole row in registers in phase A (102 registers per thread)
 
 // fast (separable) stem kernel: runs the pairs order[start[bucket] .. + count[bucket])
 struct StemFastLaunch {
@@ -92,7 +96,8 @@ cudaError_t launch_stem(const StemLaunch& p, int grid, size_t smem, cudaStream_t
 int stem_max_ctas_per_sm(size_t smem);
 size_t stem_fast_smem_bytes(uint32_t nwarps, uint32_t nx_cap, uint32_t ny_cap, uint32_t e4_cap, uint32_t lev_cap,
                             uint32_t band_cap);
-int stem_fast_ctas_per_sm(int nwarps, size_t smem);
+int stem_fast_ctas_per_sm(uint32_t ny_cap, int nwarps, size_t smem);
+int stem_fast_max_warps(uint32_t ny_cap);   // launch bound of the variant that serves staged records of up to ny_cap nodes
 cudaError_t launch_stem_fast(const StemFastLaunch& p, int grid, int nwarps, size_t smem, cudaStream_t stream);
 cudaError_t launch_classify(const StemClassify& c, int n_buckets, unsigned long long* counters, cudaStream_t stream);
 void string_shape_for(uint32_t ly_cap, int mode, int* cw, int* tp);

@@ -53,6 +53,13 @@ namespace {
 
 constexpr uint32_t kGroup = kFastGroup;  // pairs sharing one staged y record that a CTA runs concurrently
 constexpr uint32_t R = kFastRows;        // rows of a block (1, 2 or 4)
+#ifndef STEMK_POLL_NS0
+#define STEMK_POLL_NS0 128
+#endif
+#ifndef STEMK_POLL_NSMAX
+#define STEMK_POLL_NSMAX 2048
+#endif
+constexpr uint32_t kPollNs0 = STEMK_POLL_NS0, kPollNsMax = STEMK_POLL_NSMAX;   // sleep between two polls of the row flags: first, longest
 static_assert(R == 1 || R == 2 || R == 4, "kFastRows must be 1, 2 or 4");
 
 struct FastLayout {
@@ -72,7 +79,7 @@ __host__ __device__ inline FastLayout fast_layout(uint32_t nwarps, uint32_t nx_c
   L.yUp = take(8 * (ny_cap + 2u));  // up                                                                 (phase A)
   L.yDn = take(8 * (ny_cap + 2u));  // dn                                                                 (phase C)
   L.yC = take(2 * e4_cap);     // child lists as 16-bit byte offsets into a row buffer, padded to multiples of four
-  L.yLev = take(4 * (lev_cap + 1));
+  L.yLev = take(8 * (lev_cap + 1));   // per sub-level {first node, end}: one 8-byte broadcast load per step of the sweep
   L.yPerm = take(4 * ny_cap);  // nodes sorted by length: len << 16 | node
   L.done = take(nx_cap * kGroup);  // one byte per row, per pair of the group
   L.mbuf_bytes = (8u * band_cap + 15u) & ~15u;
@@ -109,6 +116,27 @@ __device__ __forceinline__ void sts_v4u32(uint32_t a, uint4 v) { asm volatile("s
 // from the kernel parameters inside the innermost loops (a dozen integer instructions per DP cell).
 __device__ __forceinline__ uint32_t pin(uint32_t v) { asm volatile("mov.b32 %0, %0;" : "+r"(v)); return v; }
 
+// The slabs of all CTAs together are several times the L2, so about half of the finished rows a parent row sums have
+// gone back to DRAM by the time it needs them.  Ask the L2 for all of them up front instead of discovering the misses a
+// few loads at a time: one bulk prefetch per inner pair, issued by the lane that holds its row offset.  It goes
+// through the TMA unit, not through the load/store pipe -- the prefetch.global.L2 loop this replaces cost one
+// tag wavefront per 128-byte line, an eighth of all the load/store wavefronts of the kernel.
+__device__ __forceinline__ void prefetch_rows(const double* G0, uint32_t off_l, bool mine, uint32_t NYS, uint32_t Ny,
+                                              uint32_t lane, uint32_t ne) {
+#if defined(STEMK_NO_PREFETCH)
+  (void)G0; (void)off_l; (void)mine; (void)NYS; (void)Ny; (void)lane; (void)ne;
+#elif defined(STEMK_LSU_PREFETCH)
+  (void)mine; (void)NYS;
+  for (uint32_t tt = 0; tt < ne; ++tt) {
+    const double* __restrict__ src = G0 + __shfl_sync(0xffffffffu, off_l, tt);
+    for (uint32_t ln = lane * 16u; ln < Ny; ln += 512u) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + ln));
+  }
+#else
+  (void)Ny; (void)lane; (void)ne;
+  if (mine) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(G0 + off_l), "r"(8u * NYS) : "memory");
+#endif
+}
+
 struct PairSlot {        // one pair of the group in flight
   uint32_t k;            // pair number (index into xi / yi / out)
   uint32_t N, node0, blk0, nblk;
@@ -133,7 +161,10 @@ __device__ __forceinline__ uint32_t count_len_below(uint32_t perm, uint32_t Ny, 
 #define PROF_ADD(slot, a, b) do {} while (0)
 #endif
 
-__global__ void __launch_bounds__(32 * kFastMaxWarps, 1) stem_fast_kernel(const StemFastLaunch P) {
+// NCH > 0: the staged record has at most 64*NCH nodes and phase A keeps the whole row in registers (NCH 16-byte
+// accumulators per lane); NCH = 0: any size up to kFastMaxN, phase A walks the row in blocks of 256 columns.
+template <int NCH>
+__global__ void __launch_bounds__(32 * (NCH > 0 ? kFastRegWarps : kFastMaxWarps), 1) stem_fast_kernel(const StemFastLaunch P) {
   extern __shared__ __align__(16) unsigned char sm[];
   __shared__ unsigned long long s_item;
   __shared__ uint32_t s_next_blk, s_g, s_maxblk;
@@ -217,7 +248,7 @@ __global__ void __launch_bounds__(32 * kFastMaxWarps, 1) stem_fast_kernel(const 
       const uint2* __restrict__ src = reinterpret_cast<const uint2*>(Y.c16 + ry.c16_0);  // c16_0 is a multiple of 4
       for (uint32_t e = tid; e < ry.e4 / 4u; e += blockDim.x) { const uint2 v = src[e]; sts_u32(yC + 8 * e, v.x); sts_u32(yC + 8 * e + 4, v.y); }
     }
-    for (uint32_t l = tid; l <= ry.nlev; l += blockDim.x) sts_u32(yLev + 4 * l, Y.lev_off[ry.lev0 + l]);
+    for (uint32_t l = tid; l < ry.nlev; l += blockDim.x) { sts_u32(yLev + 8 * l, Y.lev_off[ry.lev0 + l]); sts_u32(yLev + 8 * l + 4, Y.lev_off[ry.lev0 + l + 1]); }
     for (uint32_t i = tid; i < (g * P.nx_cap + 3u) / 4u; i += blockDim.x) sts_u32(sb + (L.done + 4 * i), 0u);
     // the dummy column (and the pad after it) of every row buffer of this warp
     if (lane < 2u * R) sts_f64(wrows + row_bytes * (lane >> 1) + 8u * (Ny + (lane & 1u)), 0.0);
@@ -231,8 +262,6 @@ __global__ void __launch_bounds__(32 * kFastMaxWarps, 1) stem_fast_kernel(const 
       if (lane == 0) t = atomicAdd(&s_next_blk, 1u);
       t = __shfl_sync(0xffffffffu, t, 0);
       if (t >= n_tickets) break;
-      PROF_T(t_tk);
-      PROF_ADD(7, t_0, t_tk);
       const uint32_t sl = t % g, b = t / g;
       const PairSlot ps = s_slot[sl];
       if (b >= ps.nblk) continue;
@@ -256,84 +285,133 @@ __global__ void __launch_bounds__(32 * kFastMaxWarps, 1) stem_fast_kernel(const 
         double* __restrict__ g0row = G0 + (size_t)i * NYS;
 
         // ---- phase A: q = sum over inner pairs c of G0s(c,:);  HQ = up_y*s2_x*q -> buffer, up_x*a_x*s2_x*q -> slab
-        for (uint32_t eb = e0; eb < e1 || eb == e0; eb += 32u) {
-          const uint32_t ne = min(32u, e1 - eb);
-          const bool last = eb + 32u >= e1;
-          const bool more = eb != e0;
-          PROF_T(t_w0);
-          uint32_t c = 0u;
-          if (lane < ne) c = X.cidx[eb + lane];
-          const uint32_t off_l = c * NYS;
-          // wait until the rows of all inner pairs are published: one poll per lane and round, the whole warp sleeps
-          // in between, longer every time (polling is shared-memory traffic the sweeps of the other warps pay for)
-          for (uint32_t ns = 128u; !__all_sync(0xffffffffu, lane >= ne || ld_flag_f(done + c) != 0u); ns = min(2u * ns, 2048u))
-            __nanosleep(ns);
-          __threadfence_block();  // acquire: the G0 rows behind the flags just seen
-          PROF_T(t_w1);
-          PROF_ADD(6, t_w0, t_w1);
-#ifndef STEMK_NO_PREFETCH
-          // The slabs of all CTAs together are several times the L2, so part of these rows come from DRAM: ask for
-          // every 128-byte line of every child row at once instead of discovering the misses a few loads at a time.
-          for (uint32_t tt = 0; tt < ne; ++tt) {
-            const double* __restrict__ src = G0 + __shfl_sync(0xffffffffu, off_l, tt);
-            for (uint32_t ln = lane * 16u; ln < Ny; ln += 512u) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + ln));
-          }
-#endif
-          for (uint32_t jb = 0; jb < Ny; jb += 256u) {  // uniform trip count: the shuffles below need every lane
-            const uint32_t j = jb + 2u * lane;           // this lane: columns j, j+1 of four 64-column chunks
-            const bool v0 = j < Ny, v1 = j + 64u < Ny, v2 = j + 128u < Ny, v3 = j + 192u < Ny;
-            const uint32_t rj = rb + 8u * j;
-            double2 q0 = make_double2(0.0, 0.0), q1 = q0, q2 = q0, q3 = q0;
-            if (more) {
-              if (v0) q0 = lds_v2f64(rj);
-              if (v1) q1 = lds_v2f64(rj + 512u);
-              if (v2) q2 = lds_v2f64(rj + 1024u);
-              if (v3) q3 = lds_v2f64(rj + 1536u);
-            }
-            // two inner pairs x four column chunks per round: eight independent 16-byte loads in flight per lane
+        if constexpr (NCH > 0) {
+          // the whole row lives in registers: lane <-> columns 2*lane, 2*lane+1 of each of the NCH 64-column chunks;
+          // CPR inner pairs per round, i.e. CPR*NCH independent 16-byte loads in flight per lane
+          constexpr int CPR = NCH <= 4 ? 3 : (NCH <= 6 ? 2 : 1);
+          const uint32_t j = 2u * lane;
+          double2 q[NCH];
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) q[c] = make_double2(0.0, 0.0);
+          for (uint32_t eb = e0; eb < e1; eb += 32u) {
+            const uint32_t ne = min(32u, e1 - eb);
+            PROF_T(t_w0);
+            uint32_t c = 0u;
+            if (lane < ne) c = X.cidx[eb + lane];
+            const uint32_t off_l = c * NYS;
+            for (uint32_t ns = kPollNs0; !__all_sync(0xffffffffu, lane >= ne || ld_flag_f(done + c) != 0u); ns = min(2u * ns, kPollNsMax))
+              __nanosleep(ns);
+            __threadfence_block();  // acquire: the G0 rows behind the flags just seen
+            PROF_T(t_w1);
+            PROF_ADD(6, t_w0, t_w1);
+            prefetch_rows(G0, off_l, lane < ne, NYS, Ny, lane, ne);
 #pragma unroll 1
-            for (uint32_t tt = 0; tt < ne; tt += 2u) {
-              const double2* __restrict__ s0 = reinterpret_cast<const double2*>(G0 + __shfl_sync(0xffffffffu, off_l, tt) + j);
-              const double2* __restrict__ s1 = reinterpret_cast<const double2*>(G0 + __shfl_sync(0xffffffffu, off_l, (tt + 1u) & 31u) + j);
-              const bool c1 = tt + 1u < ne;
-              const double2 z = make_double2(0.0, 0.0);
-              double2 t00 = z, t01 = z, t02 = z, t03 = z, t10 = z, t11 = z, t12 = z, t13 = z;
-              if (v0) t00 = __ldcg(s0);
-              if (v1) t01 = __ldcg(s0 + 32);
-              if (v2) t02 = __ldcg(s0 + 64);
-              if (v3) t03 = __ldcg(s0 + 96);
-              if (v0 && c1) t10 = __ldcg(s1);
-              if (v1 && c1) t11 = __ldcg(s1 + 32);
-              if (v2 && c1) t12 = __ldcg(s1 + 64);
-              if (v3 && c1) t13 = __ldcg(s1 + 96);
-              q0.x += t00.x + t10.x; q0.y += t00.y + t10.y;
-              q1.x += t01.x + t11.x; q1.y += t01.y + t11.y;
-              q2.x += t02.x + t12.x; q2.y += t02.y + t12.y;
-              q3.x += t03.x + t13.x; q3.y += t03.y + t13.y;
+            for (uint32_t tt = 0; tt < ne; tt += CPR) {
+              double2 t[CPR][NCH];
+#pragma unroll
+              for (int k = 0; k < CPR; ++k) {
+                const bool ck = tt + k < ne;
+                const double2* __restrict__ sk = reinterpret_cast<const double2*>(G0 + __shfl_sync(0xffffffffu, off_l, (tt + k) & 31u) + j);
+#pragma unroll
+                for (int cc = 0; cc < NCH; ++cc) {
+                  t[k][cc] = make_double2(0.0, 0.0);
+                  if (ck && j + 64u * cc < Ny) t[k][cc] = __ldcg(sk + 32 * cc);
+                }
+              }
+#pragma unroll
+              for (int cc = 0; cc < NCH; ++cc) {
+                double sx = t[0][cc].x, sy = t[0][cc].y;
+#pragma unroll
+                for (int k = 1; k < CPR; ++k) { sx += t[k][cc].x; sy += t[k][cc].y; }
+                q[cc].x += sx; q[cc].y += sy;
+              }
             }
-            if (last) {
-              // the second column of a pair may be the slab row's pad (j + 1 == Ny, Ny odd): its value is never used
-              // (yUp[Ny] = 0, so the dummy column of the buffer stays zero)
-              if (v0) { const double2 u = lds_v2f64(yUp + 8u * j); const double sx = xs2 * q0.x, sy = xs2 * q0.y;
-                        *reinterpret_cast<double2*>(g0row + j) = make_double2(pc * sx, pc * sy); q0 = make_double2(u.x * sx, j + 1u < Ny ? u.y * sy : 0.0); }
-              if (v1) { const double2 u = lds_v2f64(yUp + 8u * (j + 64u)); const double sx = xs2 * q1.x, sy = xs2 * q1.y;
-                        *reinterpret_cast<double2*>(g0row + j + 64u) = make_double2(pc * sx, pc * sy); q1 = make_double2(u.x * sx, j + 65u < Ny ? u.y * sy : 0.0); }
-              if (v2) { const double2 u = lds_v2f64(yUp + 8u * (j + 128u)); const double sx = xs2 * q2.x, sy = xs2 * q2.y;
-                        *reinterpret_cast<double2*>(g0row + j + 128u) = make_double2(pc * sx, pc * sy); q2 = make_double2(u.x * sx, j + 129u < Ny ? u.y * sy : 0.0); }
-              if (v3) { const double2 u = lds_v2f64(yUp + 8u * (j + 192u)); const double sx = xs2 * q3.x, sy = xs2 * q3.y;
-                        *reinterpret_cast<double2*>(g0row + j + 192u) = make_double2(pc * sx, pc * sy); q3 = make_double2(u.x * sx, j + 193u < Ny ? u.y * sy : 0.0); }
-            } else {   // an intermediate round: the dummy column must stay zero
-              if (j + 1u >= Ny) q0.y = 0.0;
-              if (j + 65u >= Ny) q1.y = 0.0;
-              if (j + 129u >= Ny) q2.y = 0.0;
-              if (j + 193u >= Ny) q3.y = 0.0;
-            }
-            if (v0) sts_v2f64(rj, q0);
-            if (v1) sts_v2f64(rj + 512u, q1);
-            if (v2) sts_v2f64(rj + 1024u, q2);
-            if (v3) sts_v2f64(rj + 1536u, q3);
           }
-          if (e1 == e0) break;
+          // the second column of a pair may be the slab row's pad (j + 1 == Ny, Ny odd): its value is never used, and
+          // the buffer's dummy column must stay zero
+#pragma unroll
+          for (int cc = 0; cc < NCH; ++cc) {
+            const uint32_t jc = j + 64u * cc;
+            if (jc < Ny) {
+              const double2 u = lds_v2f64(yUp + 8u * jc);
+              const double sx = xs2 * q[cc].x, sy = xs2 * q[cc].y;
+              *reinterpret_cast<double2*>(g0row + jc) = make_double2(pc * sx, pc * sy);
+              sts_v2f64(rb + 8u * jc, make_double2(u.x * sx, jc + 1u < Ny ? u.y * sy : 0.0));
+            }
+          }
+        } else {
+        for (uint32_t eb = e0; eb < e1 || eb == e0; eb += 32u) {
+            const uint32_t ne = min(32u, e1 - eb);
+            const bool last = eb + 32u >= e1;
+            const bool more = eb != e0;
+            PROF_T(t_w0);
+            uint32_t c = 0u;
+            if (lane < ne) c = X.cidx[eb + lane];
+            const uint32_t off_l = c * NYS;
+            // wait until the rows of all inner pairs are published: one poll per lane and round, the whole warp sleeps
+            // in between, longer every time (polling is shared-memory traffic the sweeps of the other warps pay for)
+            for (uint32_t ns = kPollNs0; !__all_sync(0xffffffffu, lane >= ne || ld_flag_f(done + c) != 0u); ns = min(2u * ns, kPollNsMax))
+              __nanosleep(ns);
+            __threadfence_block();  // acquire: the G0 rows behind the flags just seen
+            PROF_T(t_w1);
+            PROF_ADD(6, t_w0, t_w1);
+            prefetch_rows(G0, off_l, lane < ne, NYS, Ny, lane, ne);
+            for (uint32_t jb = 0; jb < Ny; jb += 256u) {  // uniform trip count: the shuffles below need every lane
+              const uint32_t j = jb + 2u * lane;           // this lane: columns j, j+1 of four 64-column chunks
+              const bool v0 = j < Ny, v1 = j + 64u < Ny, v2 = j + 128u < Ny, v3 = j + 192u < Ny;
+              const uint32_t rj = rb + 8u * j;
+              double2 q0 = make_double2(0.0, 0.0), q1 = q0, q2 = q0, q3 = q0;
+              if (more) {
+                if (v0) q0 = lds_v2f64(rj);
+                if (v1) q1 = lds_v2f64(rj + 512u);
+                if (v2) q2 = lds_v2f64(rj + 1024u);
+                if (v3) q3 = lds_v2f64(rj + 1536u);
+              }
+              // two inner pairs x four column chunks per round: eight independent 16-byte loads in flight per lane
+#pragma unroll 1
+              for (uint32_t tt = 0; tt < ne; tt += 2u) {
+                const double2* __restrict__ s0 = reinterpret_cast<const double2*>(G0 + __shfl_sync(0xffffffffu, off_l, tt) + j);
+                const double2* __restrict__ s1 = reinterpret_cast<const double2*>(G0 + __shfl_sync(0xffffffffu, off_l, (tt + 1u) & 31u) + j);
+                const bool c1 = tt + 1u < ne;
+                const double2 z = make_double2(0.0, 0.0);
+                double2 t00 = z, t01 = z, t02 = z, t03 = z, t10 = z, t11 = z, t12 = z, t13 = z;
+                if (v0) t00 = __ldcg(s0);
+                if (v1) t01 = __ldcg(s0 + 32);
+                if (v2) t02 = __ldcg(s0 + 64);
+                if (v3) t03 = __ldcg(s0 + 96);
+                if (v0 && c1) t10 = __ldcg(s1);
+                if (v1 && c1) t11 = __ldcg(s1 + 32);
+                if (v2 && c1) t12 = __ldcg(s1 + 64);
+                if (v3 && c1) t13 = __ldcg(s1 + 96);
+                q0.x += t00.x + t10.x; q0.y += t00.y + t10.y;
+                q1.x += t01.x + t11.x; q1.y += t01.y + t11.y;
+                q2.x += t02.x + t12.x; q2.y += t02.y + t12.y;
+                q3.x += t03.x + t13.x; q3.y += t03.y + t13.y;
+              }
+              if (last) {
+                // the second column of a pair may be the slab row's pad (j + 1 == Ny, Ny odd): its value is never used
+                // (yUp[Ny] = 0, so the dummy column of the buffer stays zero)
+                if (v0) { const double2 u = lds_v2f64(yUp + 8u * j); const double sx = xs2 * q0.x, sy = xs2 * q0.y;
+                          *reinterpret_cast<double2*>(g0row + j) = make_double2(pc * sx, pc * sy); q0 = make_double2(u.x * sx, j + 1u < Ny ? u.y * sy : 0.0); }
+                if (v1) { const double2 u = lds_v2f64(yUp + 8u * (j + 64u)); const double sx = xs2 * q1.x, sy = xs2 * q1.y;
+                          *reinterpret_cast<double2*>(g0row + j + 64u) = make_double2(pc * sx, pc * sy); q1 = make_double2(u.x * sx, j + 65u < Ny ? u.y * sy : 0.0); }
+                if (v2) { const double2 u = lds_v2f64(yUp + 8u * (j + 128u)); const double sx = xs2 * q2.x, sy = xs2 * q2.y;
+                          *reinterpret_cast<double2*>(g0row + j + 128u) = make_double2(pc * sx, pc * sy); q2 = make_double2(u.x * sx, j + 129u < Ny ? u.y * sy : 0.0); }
+                if (v3) { const double2 u = lds_v2f64(yUp + 8u * (j + 192u)); const double sx = xs2 * q3.x, sy = xs2 * q3.y;
+                          *reinterpret_cast<double2*>(g0row + j + 192u) = make_double2(pc * sx, pc * sy); q3 = make_double2(u.x * sx, j + 193u < Ny ? u.y * sy : 0.0); }
+              } else {   // an intermediate round: the dummy column must stay zero
+                if (j + 1u >= Ny) q0.y = 0.0;
+                if (j + 65u >= Ny) q1.y = 0.0;
+                if (j + 129u >= Ny) q2.y = 0.0;
+                if (j + 193u >= Ny) q3.y = 0.0;
+              }
+              if (v0) sts_v2f64(rj, q0);
+              if (v1) sts_v2f64(rj + 512u, q1);
+              if (v2) sts_v2f64(rj + 1024u, q2);
+              if (v3) sts_v2f64(rj + 1536u, q3);
+            }
+            if (e1 == e0) break;
+          }
         }
         __syncwarp();
         PROF_T(t_a1);
@@ -394,26 +472,42 @@ __global__ void __launch_bounds__(32 * kFastMaxWarps, 1) stem_fast_kernel(const 
         // below the window (len_y + band < len_x) G1 is identically 0: length-monotone DAG
         const uint32_t len_lo = (band != 0u && xl > band) ? xl - band : 0u;
         const uint32_t hrow = wrows + row_bytes * r;
-        uint32_t jbeg = lds_u32(yLev);
-        for (uint32_t ly = 0; ly < ry.nlev; ++ly) {
-          const uint32_t jend = lds_u32(yLev + 4u * ly + 4u);
-          for (uint32_t j = jbeg + slot; live && j < jend; j += nslot) {
-            const uint4 rec = lds_v4u32(yB2 + 16u * j);
-            if ((rec.y >> 16) < len_lo) break;   // nodes of a level are sorted by length, longest first
-            uint32_t e = yC + 2u * (rec.x >> 8);
-            const uint32_t eend = e + 8u * (rec.y & 0xffffu);
-            double S0 = 0.0, S1 = 0.0;
+        // Only the sub-levels that hold a node at or above the window of one of the block's rows are visited: their
+        // nodes are sorted by length, so the first node decides.  Lanes <-> sub-levels find them 32 at a time (one
+        // ballot); the sub-levels before ry.sub1 hold the nodes without inner pairs and have nothing to add.
+        uint32_t lo_blk = live ? len_lo : 0xffffffffu;
+#pragma unroll
+        for (uint32_t o = 16u; o >= nslot; o >>= 1) lo_blk = min(lo_blk, __shfl_xor_sync(0xffffffffu, lo_blk, o));
+        const uint32_t nlev = ry.nlev;
+        for (uint32_t base = ry.sub1 & ~31u; base < nlev; base += 32u) {
+          const uint32_t sl0 = base + lane;
+          bool act = sl0 >= ry.sub1 && sl0 < nlev;
+          if (act) act = (lds_u32(yB2 + 16u * lds_u32(yLev + 8u * sl0) + 4u) >> 16) >= lo_blk;
+          uint32_t mask = __ballot_sync(0xffffffffu, act);
+          while (mask != 0u) {
+            const uint32_t sl = base + (uint32_t)__ffs((int)mask) - 1u;
+            mask &= mask - 1u;
+            const uint2 jj = lds_v2u32(yLev + 8u * sl);
+            const uint32_t j = jj.x + slot;
+            if (live && j < jj.y) {
+              const uint4 rec = lds_v4u32(yB2 + 16u * j);
+              if ((rec.y >> 16) >= len_lo) {   // below the window G1 is identically 0
+                uint32_t e = yC + 2u * (rec.x >> 8);
+                const uint32_t eend = e + 8u * (rec.y & 0xffffu);
+                const uint32_t hj = hrow + 8u * j;
+                const double hv = lds_f64(hj);
+                double S0 = 0.0, S1 = 0.0;
 #pragma unroll 1
-            for (; e < eend; e += 8u) {
-              const uint2 c4 = lds_v2u32(e);
-              S0 += lds_f64(hrow + (c4.x & 0xffffu)) + lds_f64(hrow + (c4.x >> 16));
-              S1 += lds_f64(hrow + (c4.y & 0xffffu)) + lds_f64(hrow + (c4.y >> 16));
+                for (; e < eend; e += 8u) {
+                  const uint2 c4 = lds_v2u32(e);
+                  S0 += lds_f64(hrow + (c4.x & 0xffffu)) + lds_f64(hrow + (c4.x >> 16));
+                  S1 += lds_f64(hrow + (c4.y & 0xffffu)) + lds_f64(hrow + (c4.y >> 16));
+                }
+                sts_f64(hj, fma(__hiloint2double((int)rec.w, (int)rec.z), S0 + S1, hv));   // up_y*M + up_y*a_y*s2_y*sum
+              }
             }
-            const uint32_t hj = hrow + 8u * j;
-            sts_f64(hj, fma(__hiloint2double((int)rec.w, (int)rec.z), S0 + S1, lds_f64(hj)));   // up_y*M + up_y*a_y*s2_y*sum
+            __syncwarp();
           }
-          jbeg = jend;
-          __syncwarp();
         }
       }
       PROF_T(t_b2b);
@@ -544,20 +638,36 @@ size_t stem_fast_smem_bytes(uint32_t nwarps, uint32_t nx_cap, uint32_t ny_cap, u
   return fast_layout(nwarps, nx_cap, ny_cap, e4_cap, lev_cap, band_cap).total;
 }
 
+// kernel variant for a bucket: the register-resident phase A where the staged record fits 64*NCH columns
+using FastKernelFn = void (*)(StemFastLaunch);
+static FastKernelFn fast_kernel_for(uint32_t ny_cap) {
+  const uint32_t nch = (ny_cap + 63u) / 64u;
+  if (nch <= 4) return stem_fast_kernel<4>;
+  if (nch == 5) return stem_fast_kernel<5>;
+  if (nch == 6) return stem_fast_kernel<6>;
+  if (nch == 7) return stem_fast_kernel<7>;
+  if (nch == 8) return stem_fast_kernel<8>;
+  return stem_fast_kernel<0>;
+}
+
+int stem_fast_max_warps(uint32_t ny_cap) { return (ny_cap + 63u) / 64u <= 8u ? kFastRegWarps : kFastMaxWarps; }
+
 cudaError_t launch_stem_fast(const StemFastLaunch& p, int grid, int nwarps, size_t smem, cudaStream_t stream) {
-  cudaError_t e = cudaFuncSetAttribute(stem_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const FastKernelFn fn = fast_kernel_for(p.ny_cap);
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  stem_fast_kernel<<<grid, nwarps * 32, smem, stream>>>(p);
+  fn<<<grid, nwarps * 32, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
-int stem_fast_ctas_per_sm(int nwarps, size_t smem) {
+int stem_fast_ctas_per_sm(uint32_t ny_cap, int nwarps, size_t smem) {
+  const FastKernelFn fn = fast_kernel_for(ny_cap);
   int n = 0;
-  if (cudaFuncSetAttribute(stem_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+  if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, stem_fast_kernel, nwarps * 32, smem) != cudaSuccess) {
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, nwarps * 32, smem) != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }

@@ -389,10 +389,10 @@ int stemk_pairs_device(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, s
       const size_t budget = std::min<size_t>(ctx->smem_optin, (size_t)227 * 1024) - 256;   // static shared memory
       // one CTA per SM with as many warps as the bucket's rows leave room for
       int best_w = 0; size_t best_smem = 0;
-      for (int t = kFastMaxWarps; t >= 2; --t) if (stem_fast_smem_bytes(t, nx_cap, ny_cap, e4_cap, lev_cap, band_cap) <= budget) { best_w = t; break; }
+      for (int t = stem_fast_max_warps(ny_cap); t >= 2; --t) if (stem_fast_smem_bytes(t, nx_cap, ny_cap, e4_cap, lev_cap, band_cap) <= budget) { best_w = t; break; }
       if (!best_w) return fail(ctx, STEMK_ERR_NOMEM, "fast stem kernel: record does not fit in shared memory");
       best_smem = stem_fast_smem_bytes(best_w, nx_cap, ny_cap, e4_cap, lev_cap, band_cap);
-      const int per_sm = stem_fast_ctas_per_sm(best_w, best_smem);
+      const int per_sm = stem_fast_ctas_per_sm(ny_cap, best_w, best_smem);
       if (per_sm < 1) return fail(ctx, STEMK_ERR_CUDA, "fast stem kernel does not fit on an SM");
       const int grid = (int)std::min<size_t>((n_pairs + kFastGroup - 1) / kFastGroup, (size_t)ctx->sm_count);
       const unsigned long long stride = (unsigned long long)kFastGroup * nx_cap * ((ny_cap + 1u) & ~1u);

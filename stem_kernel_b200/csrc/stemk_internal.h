@@ -18,7 +18,7 @@ namespace stemk {
 // ------------------------------------------------------------------------------------------
 struct RecDev {
   uint32_t N;       // non-leaf nodes
-  uint32_t nlev;    // levels
+  uint32_t nlev;    // sub-levels: DAG levels cut into runs of at most 32/kFastRows nodes (compile_set.cpp)
   uint32_t node0;   // offset of this record in the per-node arrays
   uint32_t coff0;   // offset of its N+1 child offsets in `coff`
   uint32_t lev0;    // offset of its nlev+1 level offsets in `lev_off`
@@ -34,6 +34,8 @@ struct RecDev {
   uint32_t e4;      // entries of those lists (every node's list padded to a multiple of 4 with index N)
   uint32_t blk0;    // offset of its row blocks in `blk`
   uint32_t nblk;    // row blocks (<= kFastRows rows of one level each)
+  uint32_t sub1;    // first sub-level whose nodes have inner pairs (the sub-levels before it are DAG level 0)
+  uint32_t pad_;
 };
 enum { REC_HAS_WEIGHT = 1u, REC_SIMPLE_COLS = 2u, REC_SIMPLE_BPF = 4u,
        REC_LEN_MONOTONE = 8u,  // every non-leaf child is strictly shorter than its parent (true for front-end DAGs)
