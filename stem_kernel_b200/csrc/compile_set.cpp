@@ -257,7 +257,7 @@ void compile_record(const stemk_seqset_desc& s, uint32_t r, double g, uint32_t l
     pos[0] = neg[0] = 1.0;
     const double ginv = 1.0 / g;
     for (uint32_t k = 1; k <= span; ++k) { pos[k] = pos[k - 1] * g; neg[k] = neg[k - 1] * ginv; }
-    auto in_range = [](double v) { return std::isfinite(v) && std::fabs(v) > 1e-140 && std::fabs(v) < 1e140; };
+    auto in_range = [](double v) { return std::isfinite(v) && std::fabs(v) > 1e-125 && std::fabs(v) < 1e125; };
     if (!in_range(pos[span]) || !in_range(neg[span])) fast = false;
     auto pw = [&](long k) { return k >= 0 ? pos[(size_t)k] : neg[(size_t)(-k)]; };
     o->up.resize(N); o->dn.resize(N); o->s2.resize(N); o->nodei.resize(N);

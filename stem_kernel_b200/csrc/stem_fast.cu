@@ -53,17 +53,21 @@ namespace {
 
 constexpr uint32_t kGroup = kFastGroup;  // pairs sharing one staged y record that a CTA runs concurrently
 constexpr uint32_t R = kFastRows;        // rows of a block (1, 2 or 4)
+#ifndef STEMK_A_TWO_PASS
+#define STEMK_A_TWO_PASS 0
+#endif
 #ifndef STEMK_POLL_NS0
 #define STEMK_POLL_NS0 128
 #endif
 #ifndef STEMK_POLL_NSMAX
 #define STEMK_POLL_NSMAX 2048
 #endif
+constexpr uint32_t kBandRegs = 128;      // MATCH values of a row kept in registers (four per lane) instead of the per-warp band buffer
 constexpr uint32_t kPollNs0 = STEMK_POLL_NS0, kPollNsMax = STEMK_POLL_NSMAX;   // sleep between two polls of the row flags: first, longest
 static_assert(R == 1 || R == 2 || R == 4, "kFastRows must be 1, 2 or 4");
 
 struct FastLayout {
-  uint32_t tab, yB2, yB1a, yB1b, yUp, yDn, yC, yLev, yPerm, done, warps, mbuf_bytes, row_bytes, warp_bytes, total;
+  uint32_t tab, yB2, yB1a, yB1b, yC, yLev, yPerm, done, warps, mbuf_bytes, row_bytes, warp_bytes, total;
 };
 
 // per warp: the band buffer, then R row buffers of ny_cap + 1 columns (the last one is the all-zero dummy column)
@@ -74,15 +78,13 @@ __host__ __device__ inline FastLayout fast_layout(uint32_t nwarps, uint32_t nx_c
   auto take = [&](uint32_t bytes) { uint32_t at = off; off += (bytes + 15u) & ~15u; return at; };
   L.tab = take(8 * 256);
   L.yB2 = take(16 * ny_cap);   // {child list offset << 8 | bcode, deg4 | len << 16, coef = up*a*s2}   (sweep)
-  L.yB1a = take(16 * ny_cap);  // {s2, el}                                                                (MATCH)
-  L.yB1b = take(16 * ny_cap);  // {bfreq*up, paths*dn}                                                    (MATCH)
-  L.yUp = take(8 * (ny_cap + 2u));  // up                                                                 (phase A)
-  L.yDn = take(8 * (ny_cap + 2u));  // dn                                                                 (phase C)
+  L.yB1a = take(16 * ny_cap);  // {s2*bfreq*up, el*bfreq*up}                                              (MATCH)
+  L.yB1b = take(16 * ny_cap);  // {paths*dn, the two integer words of the sweep record}                   (MATCH)
   L.yC = take(2 * e4_cap);     // child lists as 16-bit byte offsets into a row buffer, padded to multiples of four
   L.yLev = take(8 * (lev_cap + 1));   // per sub-level {first node, end}: one 8-byte broadcast load per step of the sweep
   L.yPerm = take(4 * ny_cap);  // nodes sorted by length: len << 16 | node
   L.done = take(nx_cap * kGroup);  // one byte per row, per pair of the group
-  L.mbuf_bytes = (8u * band_cap + 15u) & ~15u;
+  L.mbuf_bytes = band_cap > kBandRegs ? ((8u * band_cap + 15u) & ~15u) : 0u;   // bands of up to kBandRegs nodes stay in registers
   L.row_bytes = (8u * (ny_cap + 2u) + 15u) & ~15u;
   L.warp_bytes = L.mbuf_bytes + R * L.row_bytes;
   L.warps = take(L.warp_bytes * nwarps);
@@ -187,7 +189,6 @@ __global__ void __launch_bounds__(32 * (NCH > 0 ? kFastRegWarps : kFastMaxWarps)
   const uint32_t wrows = pin(mbuf + L.mbuf_bytes);
   const uint32_t row_bytes = pin(L.row_bytes);
   const uint32_t yPerm = pin(sb + L.yPerm), yB2 = pin(sb + L.yB2), yC = pin(sb + L.yC), yLev = pin(sb + L.yLev);
-  const uint32_t yUp = pin(sb + L.yUp), yDn = pin(sb + L.yDn);
   unsigned long long item = 0, item_end = 0;  // the CTA's current run of queue positions
 #ifdef FAST_PROF
   long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -237,13 +238,11 @@ __global__ void __launch_bounds__(32 * (NCH > 0 ? kFastRegWarps : kFastMaxWarps)
       const double coef = yup * (Y.a[gy] * ys2);   // H = up*a*s2 * sum(H children) (+ up*M)
       sts_v4u32(yB2 + 16 * j, make_uint4(ni.e4_bcode, (uint32_t)ni.deg4 | ((uint32_t)ni.len << 16),
                                          (uint32_t)__double2loint(coef), (uint32_t)__double2hiint(coef)));
-      sts_v2f64(sb + (L.yB1a + 16 * j), make_double2(ys2, Y.el[gy]));
-      sts_v2f64(sb + (L.yB1b + 16 * j), make_double2(Y.bfreq[gy] * yup, Y.paths[gy] * ydn));
-      sts_f64(yUp + 8 * j, yup);
-      sts_f64(yDn + 8 * j, ydn);
+      const double bfu = Y.bfreq[gy] * yup;
+      sts_v2f64(sb + (L.yB1a + 16 * j), make_double2(ys2 * bfu, Y.el[gy] * bfu));
+      sts_v2f64(sb + (L.yB1b + 16 * j), make_double2(Y.paths[gy] * ydn, __hiloint2double((int)((uint32_t)ni.deg4 | ((uint32_t)ni.len << 16)), (int)ni.e4_bcode)));
       sts_u32(yPerm + 4 * j, Y.lperm[gy]);
     }
-    if (tid < 2u) { sts_f64(yUp + 8 * (Ny + tid), 0.0); sts_f64(yDn + 8 * (Ny + tid), 0.0); }   // read in pairs
     {
       const uint2* __restrict__ src = reinterpret_cast<const uint2*>(Y.c16 + ry.c16_0);  // c16_0 is a multiple of 4
       for (uint32_t e = tid; e < ry.e4 / 4u; e += blockDim.x) { const uint2 v = src[e]; sts_u32(yC + 8 * e, v.x); sts_u32(yC + 8 * e + 4, v.y); }
@@ -286,57 +285,64 @@ __global__ void __launch_bounds__(32 * (NCH > 0 ? kFastRegWarps : kFastMaxWarps)
 
         // ---- phase A: q = sum over inner pairs c of G0s(c,:);  HQ = up_y*s2_x*q -> buffer, up_x*a_x*s2_x*q -> slab
         if constexpr (NCH > 0) {
-          // the whole row lives in registers: lane <-> columns 2*lane, 2*lane+1 of each of the NCH 64-column chunks;
-          // CPR inner pairs per round, i.e. CPR*NCH independent 16-byte loads in flight per lane
-          constexpr int CPR = NCH <= 4 ? 3 : (NCH <= 6 ? 2 : 1);
+          // The row lives in registers: lane <-> columns 2*lane, 2*lane+1 of each 64-column chunk; CPR inner pairs
+          // x W chunks = 7 to 12 independent 16-byte loads are in flight per lane in every round.
+          constexpr int W = STEMK_A_TWO_PASS && NCH > 6 ? (NCH + 1) / 2 : NCH;   // two passes measured slower (-6 %): off
+          constexpr int CPR = W <= 4 ? 3 : (W <= 6 ? 2 : 1);
           const uint32_t j = 2u * lane;
-          double2 q[NCH];
 #pragma unroll
-          for (int c = 0; c < NCH; ++c) q[c] = make_double2(0.0, 0.0);
-          for (uint32_t eb = e0; eb < e1; eb += 32u) {
-            const uint32_t ne = min(32u, e1 - eb);
-            PROF_T(t_w0);
-            uint32_t c = 0u;
-            if (lane < ne) c = X.cidx[eb + lane];
-            const uint32_t off_l = c * NYS;
-            for (uint32_t ns = kPollNs0; !__all_sync(0xffffffffu, lane >= ne || ld_flag_f(done + c) != 0u); ns = min(2u * ns, kPollNsMax))
-              __nanosleep(ns);
-            __threadfence_block();  // acquire: the G0 rows behind the flags just seen
-            PROF_T(t_w1);
-            PROF_ADD(6, t_w0, t_w1);
-            prefetch_rows(G0, off_l, lane < ne, NYS, Ny, lane, ne);
+          for (int c0 = 0; c0 < NCH; c0 += W) {
+            double2 q[W];
+#pragma unroll
+            for (int c = 0; c < W; ++c) q[c] = make_double2(0.0, 0.0);
+            for (uint32_t eb = e0; eb < e1; eb += 32u) {
+              const uint32_t ne = min(32u, e1 - eb);
+              uint32_t c = 0u;
+              if (lane < ne) c = X.cidx[eb + lane];
+              const uint32_t off_l = c * NYS;
+              if (c0 == 0) {
+                // wait until the rows of all inner pairs are published: one poll per lane and round, the whole warp
+                // sleeps in between, longer every time
+                PROF_T(t_w0);
+                for (uint32_t ns = kPollNs0; !__all_sync(0xffffffffu, lane >= ne || ld_flag_f(done + c) != 0u); ns = min(2u * ns, kPollNsMax))
+                  __nanosleep(ns);
+                __threadfence_block();  // acquire: the G0 rows behind the flags just seen
+                PROF_T(t_w1);
+                PROF_ADD(6, t_w0, t_w1);
+                prefetch_rows(G0, off_l, lane < ne, NYS, Ny, lane, ne);
+              }
 #pragma unroll 1
-            for (uint32_t tt = 0; tt < ne; tt += CPR) {
-              double2 t[CPR][NCH];
+              for (uint32_t tt = 0; tt < ne; tt += CPR) {
+                double2 t[CPR][W];
 #pragma unroll
-              for (int k = 0; k < CPR; ++k) {
-                const bool ck = tt + k < ne;
-                const double2* __restrict__ sk = reinterpret_cast<const double2*>(G0 + __shfl_sync(0xffffffffu, off_l, (tt + k) & 31u) + j);
+                for (int k = 0; k < CPR; ++k) {
+                  const bool ck = tt + k < ne;
+                  const double2* __restrict__ sk = reinterpret_cast<const double2*>(G0 + __shfl_sync(0xffffffffu, off_l, (tt + k) & 31u) + j);
 #pragma unroll
-                for (int cc = 0; cc < NCH; ++cc) {
-                  t[k][cc] = make_double2(0.0, 0.0);
-                  if (ck && j + 64u * cc < Ny) t[k][cc] = __ldcg(sk + 32 * cc);
+                  for (int cc = 0; cc < W; ++cc) {
+                    t[k][cc] = make_double2(0.0, 0.0);
+                    if (c0 + cc < NCH && ck && j + 64u * (c0 + cc) < Ny) t[k][cc] = __ldcg(sk + 32 * (c0 + cc));
+                  }
+                }
+#pragma unroll
+                for (int cc = 0; cc < W; ++cc) {
+                  double sx = t[0][cc].x, sy = t[0][cc].y;
+#pragma unroll
+                  for (int k = 1; k < CPR; ++k) { sx += t[k][cc].x; sy += t[k][cc].y; }
+                  q[cc].x += sx; q[cc].y += sy;
                 }
               }
-#pragma unroll
-              for (int cc = 0; cc < NCH; ++cc) {
-                double sx = t[0][cc].x, sy = t[0][cc].y;
-#pragma unroll
-                for (int k = 1; k < CPR; ++k) { sx += t[k][cc].x; sy += t[k][cc].y; }
-                q[cc].x += sx; q[cc].y += sy;
-              }
             }
-          }
-          // the second column of a pair may be the slab row's pad (j + 1 == Ny, Ny odd): its value is never used, and
-          // the buffer's dummy column must stay zero
+            // the second column of a pair may be the slab row's pad (j + 1 == Ny, Ny odd): its value is never used, and
+            // the buffer's dummy column must stay zero
 #pragma unroll
-          for (int cc = 0; cc < NCH; ++cc) {
-            const uint32_t jc = j + 64u * cc;
-            if (jc < Ny) {
-              const double2 u = lds_v2f64(yUp + 8u * jc);
-              const double sx = xs2 * q[cc].x, sy = xs2 * q[cc].y;
-              *reinterpret_cast<double2*>(g0row + jc) = make_double2(pc * sx, pc * sy);
-              sts_v2f64(rb + 8u * jc, make_double2(u.x * sx, jc + 1u < Ny ? u.y * sy : 0.0));
+            for (int cc = 0; cc < W; ++cc) {
+              const uint32_t jc = j + 64u * (c0 + cc);
+              if (c0 + cc < NCH && jc < Ny) {
+                const double sx = xs2 * q[cc].x, sy = xs2 * q[cc].y;   // HQ: the slab rows carry up_y already
+                *reinterpret_cast<double2*>(g0row + jc) = make_double2(pc * sx, pc * sy);
+                sts_v2f64(rb + 8u * jc, make_double2(sx, jc + 1u < Ny ? sy : 0.0));
+              }
             }
           }
         } else {
@@ -390,15 +396,15 @@ __global__ void __launch_bounds__(32 * (NCH > 0 ? kFastRegWarps : kFastMaxWarps)
               }
               if (last) {
                 // the second column of a pair may be the slab row's pad (j + 1 == Ny, Ny odd): its value is never used
-                // (yUp[Ny] = 0, so the dummy column of the buffer stays zero)
-                if (v0) { const double2 u = lds_v2f64(yUp + 8u * j); const double sx = xs2 * q0.x, sy = xs2 * q0.y;
-                          *reinterpret_cast<double2*>(g0row + j) = make_double2(pc * sx, pc * sy); q0 = make_double2(u.x * sx, j + 1u < Ny ? u.y * sy : 0.0); }
-                if (v1) { const double2 u = lds_v2f64(yUp + 8u * (j + 64u)); const double sx = xs2 * q1.x, sy = xs2 * q1.y;
-                          *reinterpret_cast<double2*>(g0row + j + 64u) = make_double2(pc * sx, pc * sy); q1 = make_double2(u.x * sx, j + 65u < Ny ? u.y * sy : 0.0); }
-                if (v2) { const double2 u = lds_v2f64(yUp + 8u * (j + 128u)); const double sx = xs2 * q2.x, sy = xs2 * q2.y;
-                          *reinterpret_cast<double2*>(g0row + j + 128u) = make_double2(pc * sx, pc * sy); q2 = make_double2(u.x * sx, j + 129u < Ny ? u.y * sy : 0.0); }
-                if (v3) { const double2 u = lds_v2f64(yUp + 8u * (j + 192u)); const double sx = xs2 * q3.x, sy = xs2 * q3.y;
-                          *reinterpret_cast<double2*>(g0row + j + 192u) = make_double2(pc * sx, pc * sy); q3 = make_double2(u.x * sx, j + 193u < Ny ? u.y * sy : 0.0); }
+                // (and the dummy column of the buffer must stay zero)
+                if (v0) { const double sx = xs2 * q0.x, sy = xs2 * q0.y;
+                        *reinterpret_cast<double2*>(g0row + j) = make_double2(pc * sx, pc * sy); q0 = make_double2(sx, j + 1u < Ny ? sy : 0.0); }
+                if (v1) { const double sx = xs2 * q1.x, sy = xs2 * q1.y;
+                        *reinterpret_cast<double2*>(g0row + j + 64u) = make_double2(pc * sx, pc * sy); q1 = make_double2(sx, j + 65u < Ny ? sy : 0.0); }
+                if (v2) { const double sx = xs2 * q2.x, sy = xs2 * q2.y;
+                        *reinterpret_cast<double2*>(g0row + j + 128u) = make_double2(pc * sx, pc * sy); q2 = make_double2(sx, j + 129u < Ny ? sy : 0.0); }
+                if (v3) { const double sx = xs2 * q3.x, sy = xs2 * q3.y;
+                        *reinterpret_cast<double2*>(g0row + j + 192u) = make_double2(pc * sx, pc * sy); q3 = make_double2(sx, j + 193u < Ny ? sy : 0.0); }
               } else {   // an intermediate round: the dummy column must stay zero
                 if (j + 1u >= Ny) q0.y = 0.0;
                 if (j + 65u >= Ny) q1.y = 0.0;
@@ -426,15 +432,16 @@ __global__ void __launch_bounds__(32 * (NCH > 0 ? kFastRegWarps : kFastMaxWarps)
         {
           const double xql = x23.y, xbf = x45.x;
           const uint32_t tabx = sb + L.tab + 128u * xbc;
+          const uint32_t yB1a = sb + L.yB1a, yB1b = sb + L.yB1b;
           double racc = 0.0;
-          for (uint32_t tq = lo + lane; tq < hi; tq += 32u) {
-            const uint32_t j = lds_u32(yPerm + 4u * tq) & 0xffffu;
-            const uint4 rec = lds_v4u32(yB2 + 16u * j);
-            const double2 ya = lds_v2f64(sb + L.yB1a + 16u * j);   // {s2_y, el_y}
-            const double2 yb = lds_v2f64(sb + L.yB1b + 16u * j);   // {bfreq_y*up_y, paths_y*dn_y}
-            const double tv = lds_f64(tabx + 8u * (rec.x & 0xffu));
-            uint32_t e = yC + 2u * (rec.x >> 8);
-            const uint32_t eend = e + 8u * (rec.y & 0xffffu);
+          // up_y * M(i,j) of one band node: R gathered from the row buffer (HQ)
+          auto match = [&](uint32_t j) -> double {
+            const double2 ya = lds_v2f64(yB1a + 16u * j);   // {s2_y*bfreq_y*up_y, el_y*bfreq_y*up_y}
+            const double2 yb = lds_v2f64(yB1b + 16u * j);   // {paths_y*dn_y, record words}
+            const uint32_t rx = (uint32_t)__double2loint(yb.y), ry2 = (uint32_t)__double2hiint(yb.y);
+            const double tv = lds_f64(tabx + 8u * (rx & 0xffu));
+            uint32_t e = yC + 2u * (rx >> 8);
+            const uint32_t eend = e + 8u * (ry2 & 0xffffu);
             double R0 = 0.0, R1 = 0.0;
 #pragma unroll 1
             for (; e < eend; e += 8u) {
@@ -442,20 +449,37 @@ __global__ void __launch_bounds__(32 * (NCH > 0 ? kFastRegWarps : kFastMaxWarps)
               R0 += lds_f64(rb + (c4.x & 0xffffu)) + lds_f64(rb + (c4.x >> 16));
               R1 += lds_f64(rb + (c4.y & 0xffffu)) + lds_f64(rb + (c4.y >> 16));
             }
-            const double vs = tv * xbf * yb.x;
-            const double mp = vs * fma(ya.y, xql, ya.x * (R0 + R1));   // up_y * M(i,j)
-            racc = fma(yb.y, mp, racc);
-            sts_f64(mbuf + 8u * (tq - lo), mp);
+            const double mp = (tv * xbf) * fma(ya.y, xql, ya.x * (R0 + R1));
+            racc = fma(yb.x, mp, racc);
+            return mp;
+          };
+          if (P.band_cap <= kBandRegs) {
+            // the band's values wait in registers while the buffer is cleared: no trip through shared memory
+            uint32_t jr[4];
+            double mr[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t tq = lo + lane + 32u * k;
+              jr[k] = 0xffffffffu; mr[k] = 0.0;
+              if (tq < hi) { jr[k] = lds_u32(yPerm + 4u * tq) & 0xffffu; mr[k] = match(jr[k]); }
+            }
+            __syncwarp();
+            // ---- Z: the row buffer becomes the H row: zero, then the band's up_y*M
+            for (uint32_t j = 2u * lane; j <= Ny; j += 64u) sts_v2f64(rb + 8u * j, make_double2(0.0, 0.0));
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (jr[k] != 0xffffffffu) sts_f64(rb + 8u * jr[k], mr[k]);
+          } else {
+            for (uint32_t tq = lo + lane; tq < hi; tq += 32u) sts_f64(mbuf + 8u * (tq - lo), match(lds_u32(yPerm + 4u * tq) & 0xffffu));
+            __syncwarp();
+            for (uint32_t j = 2u * lane; j <= Ny; j += 64u) sts_v2f64(rb + 8u * j, make_double2(0.0, 0.0));
+            __syncwarp();
+            for (uint32_t tq = lo + lane; tq < hi; tq += 32u)
+              sts_f64(rb + 8u * (lds_u32(yPerm + 4u * tq) & 0xffffu), lds_f64(mbuf + 8u * (tq - lo)));
           }
           racc = warp_sum_all(racc);
           if (lane == 0) rowacc[i] = x45.y * racc;   // per-row slot in global scratch (L2)
         }
-        __syncwarp();
-        // ---- Z: the row buffer becomes the H row: zero, then the band's up_y*M
-        for (uint32_t j = 2u * lane; j <= Ny; j += 64u) sts_v2f64(rb + 8u * j, make_double2(0.0, 0.0));
-        __syncwarp();
-        for (uint32_t tq = lo + lane; tq < hi; tq += 32u)
-          sts_f64(rb + 8u * (lds_u32(yPerm + 4u * tq) & 0xffffu), lds_f64(mbuf + 8u * (tq - lo)));
         __syncwarp();
         PROF_T(t_b1);
         PROF_ADD(2, t_a1, t_b1);
@@ -536,10 +560,10 @@ __global__ void __launch_bounds__(32 * (NCH > 0 ? kFastRegWarps : kFastMaxWarps)
           if (w1) o1 = __ldcg(gp + 32);
           if (w2) o2 = __ldcg(gp + 64);
           if (w3) o3 = __ldcg(gp + 96);
-          if (w0) { const double2 d = lds_v2f64(yDn + 8u * j); gp[0] = make_double2(fma(xup, d.x * h0.x, o0.x), fma(xup, d.y * h0.y, o0.y)); }
-          if (w1) { const double2 d = lds_v2f64(yDn + 8u * (j + 64u)); gp[32] = make_double2(fma(xup, d.x * h1.x, o1.x), fma(xup, d.y * h1.y, o1.y)); }
-          if (w2) { const double2 d = lds_v2f64(yDn + 8u * (j + 128u)); gp[64] = make_double2(fma(xup, d.x * h2.x, o2.x), fma(xup, d.y * h2.y, o2.y)); }
-          if (w3) { const double2 d = lds_v2f64(yDn + 8u * (j + 192u)); gp[96] = make_double2(fma(xup, d.x * h3.x, o3.x), fma(xup, d.y * h3.y, o3.y)); }
+          if (w0) gp[0] = make_double2(fma(xup, h0.x, o0.x), fma(xup, h0.y, o0.y));
+          if (w1) gp[32] = make_double2(fma(xup, h1.x, o1.x), fma(xup, h1.y, o1.y));
+          if (w2) gp[64] = make_double2(fma(xup, h2.x, o2.x), fma(xup, h2.y, o2.y));
+          if (w3) gp[96] = make_double2(fma(xup, h3.x, o3.x), fma(xup, h3.y, o3.y));
         }
       }
       __threadfence_block();
