@@ -487,14 +487,23 @@ def run_b200(args, rank, world, local_rank):
     desc = flat.desc()
     desc_t = flat_t.desc() if flat_t else None
     e2e_ms, e2e_upload_ms = [], []
+    e2e_pinned = None
     mine_lists = [sharded.deal(len(l[2]), rank, world) for l in lists]
     for it in range(1 + args.steps):                       # first pass is a warm-up of the host path
         barrier()
         t0 = time.perf_counter()
         h, ht = C.c_void_p(), C.c_void_p()
-        ctx._check(L.lib().stemk_upload(ctx.h, C.byref(desc), C.byref(h)))
-        if desc_t is not None:
-            ctx._check(L.lib().stemk_upload(ctx.h, C.byref(desc_t), C.byref(ht)))
+        if world == 1:
+            ctx._check(L.lib().stemk_upload(ctx.h, C.byref(desc), C.byref(h)))
+            if desc_t is not None:
+                ctx._check(L.lib().stemk_upload(ctx.h, C.byref(desc_t), C.byref(ht)))
+        else:
+            # the records are compiled ONCE, on rank 0; the compiled sets reach the other GPUs with one NCCL broadcast each
+            e2e_sets = [sharded.broadcast_set(ctx, ctx.upload(flat) if rank == 0 else None)]
+            h = e2e_sets[0].h
+            if flat_t:
+                e2e_sets.append(sharded.broadcast_set(ctx, ctx.upload(flat_t) if rank == 0 else None))
+                ht = e2e_sets[1].h
         t_up = time.perf_counter() - t0
         if world == 1 and W["square"]:
             out = np.empty((n, n))
@@ -524,12 +533,20 @@ def run_b200(args, rank, world, local_rank):
                         m = be.assemble(sg.xi_all, sg.yi_all, sharded.undeal(sg.recv, n_pairs), n, True)
                     else:
                         m = sc.finish(normalize=True)[0]
-                    out = m.cpu().numpy()
+                    if e2e_pinned is None or e2e_pinned.shape != m.shape:
+                        e2e_pinned = torch.empty(m.shape, dtype=torch.float64, pin_memory=True)
+                    e2e_pinned.copy_(m, non_blocking=True)
+                    torch.cuda.current_stream(dev).synchronize()
+                    out = e2e_pinned.numpy()
                 else:
                     dist.gather(drv.send, None, dst=0)
-        L.lib().stemk_set_free(ctx.h, h)
-        if ht:
-            L.lib().stemk_set_free(ctx.h, ht)
+        if world == 1:
+            L.lib().stemk_set_free(ctx.h, h)
+            if ht:
+                L.lib().stemk_set_free(ctx.h, ht)
+        else:
+            for s_ in e2e_sets:
+                s_.free()
         barrier()
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
@@ -543,7 +560,7 @@ def run_b200(args, rank, world, local_rank):
         h2d = set_bytes + (8 * n_pairs if W["square"] else 0)        # records (+ the two uint32 index lists the caller's side builds)
         d2h = 8 * n * n if W["square"] else 8 * (nt * n + nt)
     else:
-        h2d = set_bytes + 8 * my_pairs + 8 * my_pairs                  # records, index lists, values back up for the gather
+        h2d = (set_bytes if rank == 0 else 0) + 8 * my_pairs + 8 * my_pairs   # records (rank 0 only: the other ranks get them over NVLink), index lists, values back up for the gather
         d2h = 8 * my_pairs + ((8 * n * n if W["square"] else 8 * nt * n) if rank == 0 else 0)
 
     if rank != 0:
@@ -640,7 +657,7 @@ def run_b200(args, rank, world, local_rank):
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": float(np.mean(e2e_ms)), "upload_ms_per_step": float(np.mean(e2e_upload_ms)),
                 "path": ("stemk_upload + " + ("stemk_gram" if W["square"] else "stemk_cross") + " with host buffers") if world == 1 else
-                        "stemk_upload + stemk_pairs with host buffers per rank, NCCL gather, device assemble, D2H"},
+                        "stemk_upload on rank 0 + one NCCL broadcast of the compiled set, stemk_pairs with host buffers per rank, NCCL gather, device assemble, pinned D2H"},
         "gpu_launches": int(st["launches"]),
         "gpu_launches_per_step": launches_per_step,
         "roofline": roof,

@@ -140,6 +140,28 @@ void stemk_set_stats(const stemk_set* set, uint32_t* n_nodes, uint32_t* n_edges,
 /* Bytes of device memory the uploaded set occupies (= host->device bytes copied by stemk_upload). */
 uint64_t stemk_set_device_bytes(const stemk_set* set);
 
+/* ---- several devices (the reference's MPI path, kernel_matrix.cpp:186-262, 495-526, 560-571, a device per rank) --
+ * One context per device, all created with the same parameters.
+ *   stemk_set_clone     copies an uploaded set to the device of `ctx`, device to device (NVLink when the devices are
+ *                       peers): no second host compile, no second host->device copy.  Record headers and statistics
+ *                       are shared with the source set; either set may be freed first.
+ *   stemk_upload_multi  stemk_upload on ctxs[0] + stemk_set_clone onto ctxs[1..n_ctx): sets[d] lives on ctxs[d]'s device.
+ *   stemk_gram_multi    KernelMatrix::calculate(train, kernel, normalize) over n_ctx devices driven by ONE host thread:
+ *                       the y-major pair order is dealt round-robin, every device evaluates its share on its own stream,
+ *                       device 0 gathers the shares over peer copies, assembles and normalises.  out: n*n row-major,
+ *                       the same values as stemk_gram on one device.  Errors of device d > 0 are reported through
+ *                       stemk_last_error(ctxs[0]).
+ *   stemk_set_export / stemk_set_import  the same for one PROCESS per device (torchrun, MPI): the set as one byte
+ *                       string in a caller-provided DEVICE buffer of stemk_set_export_bytes(set) bytes, to be moved
+ *                       with the caller's collective (one NCCL broadcast) and turned back into a set on the receiving
+ *                       device.  The byte layout is private to the library version that wrote it. */
+int stemk_set_clone(stemk_ctx* ctx, const stemk_set* src, stemk_set** set);
+int stemk_upload_multi(stemk_ctx* const* ctxs, int n_ctx, const stemk_seqset_desc* desc, stemk_set** sets);
+int stemk_gram_multi(stemk_ctx* const* ctxs, const stemk_set* const* sets, int n_ctx, int normalize, double* out);
+uint64_t stemk_set_export_bytes(const stemk_set* set);
+int stemk_set_export(stemk_ctx* ctx, const stemk_set* set, void* d_dst, void* stream);
+int stemk_set_import(stemk_ctx* ctx, const void* d_src, uint64_t bytes, stemk_set** set);
+
 /* KernelMatrix::calculate(train, kernel, normalize) -- kernel_matrix.cpp:485-575.
  * out: n*n row-major, both triangles.  normalize: K_ij /= sqrt(K_ii K_jj), K_ii = 1. */
 int stemk_gram(stemk_ctx* ctx, const stemk_set* train, int normalize, double* out);

@@ -120,6 +120,9 @@ class DeviceSet:
     def __init__(self, ctx, mdatas):
         self.ctx = ctx
         self.h = C.c_void_p()
+        if mdatas is None:      # adopted handle (clone / import)
+            self.n = 0
+            return
         if isinstance(mdatas, SeqSet):
             flat = mdatas
         else:
@@ -127,6 +130,33 @@ class DeviceSet:
         desc = flat.desc()
         ctx._check(L.lib().stemk_upload(ctx.h, C.byref(desc), C.byref(self.h)))
         self.n = len(flat)
+
+    @classmethod
+    def _adopt(cls, ctx, handle):
+        s = cls(ctx, None)
+        s.h = handle
+        s.n = int(L.lib().stemk_set_size(handle))
+        return s
+
+    def clone_to(self, ctx):
+        """stemk_set_clone: the same set on the device of another context (device-to-device copy, no recompilation)."""
+        h = C.c_void_p()
+        ctx._check(L.lib().stemk_set_clone(ctx.h, self.h, C.byref(h)))
+        return DeviceSet._adopt(ctx, h)
+
+    def export_bytes(self):
+        return int(L.lib().stemk_set_export_bytes(self.h))
+
+    def export_to(self, d_ptr, stream=None):
+        """stemk_set_export into a DEVICE buffer of export_bytes() bytes (e.g. a torch uint8 tensor's data_ptr())."""
+        self.ctx._check(L.lib().stemk_set_export(self.ctx.h, self.h, d_ptr, stream))
+
+    @classmethod
+    def import_from(cls, ctx, d_ptr, nbytes):
+        """stemk_set_import: a set exported on another rank, after the caller's broadcast brought its bytes here."""
+        h = C.c_void_p()
+        ctx._check(L.lib().stemk_set_import(ctx.h, d_ptr, nbytes, C.byref(h)))
+        return cls._adopt(ctx, h)
 
     def __len__(self):
         return self.n
@@ -150,6 +180,26 @@ class DeviceSet:
             self.free()
         except Exception:
             pass
+
+
+def upload_multi(ctxs, mdatas):
+    """stemk_upload_multi: compile once, one set per context/device (sets[d] on ctxs[d])."""
+    flat = mdatas if isinstance(mdatas, SeqSet) else SeqSet(mdatas)
+    desc = flat.desc()
+    hc = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+    hs = (C.c_void_p * len(ctxs))()
+    ctxs[0]._check(L.lib().stemk_upload_multi(hc, len(ctxs), C.byref(desc), hs))
+    return [DeviceSet._adopt(c, C.c_void_p(h)) for c, h in zip(ctxs, hs)]
+
+
+def gram_multi(ctxs, sets, normalize=False):
+    """stemk_gram_multi: one Gram matrix over the devices of `ctxs` (one host thread, one context per device)."""
+    n = len(sets[0])
+    out = np.zeros((n, n))
+    hc = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+    hs = (C.c_void_p * len(ctxs))(*[s.h for s in sets])
+    ctxs[0]._check(L.lib().stemk_gram_multi(hc, hs, len(ctxs), int(normalize), out.ctypes.data))
+    return out
 
 
 # ---------------------------------------------------------------- kernel classes (def_kernel.h)

@@ -120,6 +120,10 @@ cudaError_t launch_normalize_cross(double* out, uint32_t nt, uint32_t nc, uint32
                                    const double* diag, const uint32_t* cols, cudaStream_t stream);
 cudaError_t launch_scatter_vec(const double* vals, const uint32_t* idx, uint32_t n, double* out, cudaStream_t stream);
 cudaError_t launch_iota(uint32_t* a, uint32_t n, cudaStream_t stream);
+cudaError_t launch_deal_pairs(const uint32_t* xi, const uint32_t* yi, unsigned long long n_pairs, uint32_t rank, uint32_t world,
+                              uint32_t* out_x, uint32_t* out_y, cudaStream_t stream);
+cudaError_t launch_undeal(const double* gathered, unsigned long long per, uint32_t world, unsigned long long n_pairs,
+                          double* vals, cudaStream_t stream);
 // BPLA / local-alignment kernels (bpla.cu): host buffers in, host buffer out, synchronous on `stream`
 cudaError_t run_bpla(const stemk_bpla_params& p, const stemk_bpla_set& x, const stemk_bpla_set& y, size_t n_pairs,
                      const uint32_t* xi, const uint32_t* yi, double* out, double* grad, int sm_count, size_t smem_optin,

@@ -76,6 +76,24 @@ __global__ void scatter_vec_kernel(const double* __restrict__ vals, const uint32
   if (k < n) out[idx[k]] = vals[k];
 }
 
+// Multi-device Gram matrix: device r of W owns positions r, r + W, ... of the global pair order
+__global__ void deal_pairs_kernel(const uint32_t* __restrict__ xi, const uint32_t* __restrict__ yi, unsigned long long n_pairs,
+                                  uint32_t rank, uint32_t world, uint32_t* __restrict__ out_x, uint32_t* __restrict__ out_y) {
+  const unsigned long long m = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  const unsigned long long k = m * world + rank;
+  if (k >= n_pairs) return;
+  out_x[m] = xi[k];
+  out_y[m] = yi[k];
+}
+
+// ... and the gathered values [world][per] go back into the global order: position k sits at [k % world][k / world]
+__global__ void undeal_kernel(const double* __restrict__ gathered, unsigned long long per, uint32_t world,
+                              unsigned long long n_pairs, double* __restrict__ vals) {
+  const unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  if (k >= n_pairs) return;
+  vals[k] = gathered[(k % world) * per + k / world];
+}
+
 __global__ void iota_kernel(uint32_t* __restrict__ a, uint32_t n) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k < n) a[k] = k;
@@ -116,6 +134,21 @@ cudaError_t launch_normalize_cross(double* out, uint32_t nt, uint32_t nc, uint32
 cudaError_t launch_scatter_vec(const double* vals, const uint32_t* idx, uint32_t n, double* out, cudaStream_t stream) {
   if (n == 0) return cudaSuccess;
   scatter_vec_kernel<<<(n + 255) / 256, 256, 0, stream>>>(vals, idx, n, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_deal_pairs(const uint32_t* xi, const uint32_t* yi, unsigned long long n_pairs, uint32_t rank, uint32_t world,
+                              uint32_t* out_x, uint32_t* out_y, cudaStream_t stream) {
+  const unsigned long long mine = n_pairs > rank ? (n_pairs - rank + world - 1) / world : 0;
+  if (mine == 0) return cudaSuccess;
+  deal_pairs_kernel<<<(unsigned)((mine + 255) / 256), 256, 0, stream>>>(xi, yi, n_pairs, rank, world, out_x, out_y);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_undeal(const double* gathered, unsigned long long per, uint32_t world, unsigned long long n_pairs,
+                          double* vals, cudaStream_t stream) {
+  if (n_pairs == 0) return cudaSuccess;
+  undeal_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, stream>>>(gathered, per, world, n_pairs, vals);
   return cudaGetLastError();
 }
 

@@ -17,6 +17,8 @@
 #include <thread>
 #include <vector>
 
+#include <memory>
+
 #include "kernels.cuh"
 
 using namespace stemk;
@@ -41,13 +43,21 @@ struct DevBuf {
 
 }  // namespace
 
+constexpr int kBlobArrays = 28;
+
 struct stemk_set {
-  CompiledSet host;   // kept for the work model and the scheduler
+  // host-side record headers and statistics (work model, scheduler, launch shapes); shared between the copies of a
+  // set on several devices (stemk_set_clone), immutable after the upload
+  std::shared_ptr<CompiledSet> hostp;
+  CompiledSet& host;
   DevBuf blob;        // every array of the view in one allocation
   SetView view;       // device pointers
   int device = 0;
   double loop_gap = 0;      // the parameters the derived tables were built under
   uint32_t len_band = 0;
+  size_t lay[kBlobArrays] = {};   // offset of every array of the view inside the blob (same order as make_view)
+  stemk_set() : hostp(std::make_shared<CompiledSet>()), host(*hostp) {}
+  explicit stemk_set(std::shared_ptr<CompiledSet> h) : hostp(std::move(h)), host(*hostp) {}
 };
 
 struct stemk_ctx {
@@ -62,6 +72,8 @@ struct stemk_ctx {
   unsigned long long* d_counter = nullptr;
   DevBuf scratch, carry, tmp_stem, tmp_str, idx_x, idx_y, vals, matrix, order, rowacc;
   DevBuf perm, offs, diag, selfv, diag_idx, diag_vals, diag_idx2, diag_vals2;
+  DevBuf deal_x, deal_y, gathered, undealt;     // stemk_gram_multi: this device's share of the pair list; on device 0 the gather
+  cudaEvent_t multi_ev = nullptr;
   void* stage[2] = {nullptr, nullptr};          // pinned host staging (copy_out / copy_in)
   cudaEvent_t stage_ev[2] = {nullptr, nullptr};
   unsigned long long* d_bucket = nullptr;  // count[16] | start[16] | queue heads[16]
@@ -215,7 +227,9 @@ void stemk_destroy(stemk_ctx* c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (DevBuf* b : {&c->scratch, &c->carry, &c->tmp_stem, &c->tmp_str, &c->idx_x, &c->idx_y, &c->vals, &c->matrix, &c->order, &c->rowacc,
-                    &c->perm, &c->offs, &c->diag, &c->selfv, &c->diag_idx, &c->diag_vals, &c->diag_idx2, &c->diag_vals2}) b->release();
+                    &c->perm, &c->offs, &c->diag, &c->selfv, &c->diag_idx, &c->diag_vals, &c->diag_idx2, &c->diag_vals2,
+                    &c->deal_x, &c->deal_y, &c->gathered, &c->undealt}) b->release();
+  if (c->multi_ev) cudaEventDestroy(c->multi_ev);
   for (int k = 0; k < 2; ++k) { if (c->stage[k]) cudaFreeHost(c->stage[k]); if (c->stage_ev[k]) cudaEventDestroy(c->stage_ev[k]); }
   if (c->d_pair_tab) cudaFree(c->d_pair_tab);
   if (c->d_subst) cudaFree(c->d_subst);
@@ -228,6 +242,38 @@ void stemk_destroy(stemk_ctx* c) {
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
+
+namespace {
+
+// device pointers of a set from its blob and the array offsets recorded at upload
+void make_view(stemk_set* s) {
+  char* b = static_cast<char*>(s->blob.p);
+  const size_t* o = s->lay;
+  SetView& v = s->view;
+  v.n_recs = (uint32_t)s->host.rec.size();
+  v.rec = (const RecDev*)(b + o[0]); v.a = (const double*)(b + o[1]); v.el = (const double*)(b + o[2]);
+  v.ql = (const double*)(b + o[3]); v.paths = (const double*)(b + o[4]); v.gapt = (const double*)(b + o[5]);
+  v.bfreq = (const double*)(b + o[6]); v.len = (const uint32_t*)(b + o[7]); v.bcode = (const uint8_t*)(b + o[8]);
+  v.coff = (const uint32_t*)(b + o[9]); v.cidx = (const uint32_t*)(b + o[10]); v.ce = (const double*)(b + o[11]);
+  v.lev_off = (const uint32_t*)(b + o[12]); v.boff = (const uint32_t*)(b + o[13]); v.bab = (const uint8_t*)(b + o[14]);
+  v.bfq = (const double*)(b + o[15]); v.ccode = (const uint8_t*)(b + o[16]); v.cw = (const double*)(b + o[17]);
+  v.prof = (const float*)(b + o[18]); v.text = (const uint8_t*)(b + o[19]);
+  v.up = (const double*)(b + o[20]); v.dn = (const double*)(b + o[21]); v.s2 = (const double*)(b + o[22]);
+  v.nodei = (const NodeI*)(b + o[23]); v.c16 = (const uint16_t*)(b + o[24]); v.blk = (const uint32_t*)(b + o[25]);
+  v.xnode = (const XNode*)(b + o[26]); v.lperm = (const uint32_t*)(b + o[27]);
+}
+
+// After the upload the host keeps the record headers and what the work model (stemk_pair_cost), the scheduler and the
+// launch shapes read; the per-node / per-edge arrays that only existed to be copied to the device are released
+// (about 100 KB per 150-300 nt record).
+void drop_upload_arrays(CompiledSet* h) {
+  auto drop = [](auto& v) { std::remove_reference_t<decltype(v)>().swap(v); };
+  drop(h->a); drop(h->el); drop(h->ql); drop(h->paths); drop(h->gapt); drop(h->bfreq); drop(h->ce); drop(h->bfq); drop(h->cw);
+  drop(h->coff); drop(h->cidx); drop(h->lev_off); drop(h->bcode); drop(h->bab); drop(h->ccode); drop(h->prof);
+  drop(h->up); drop(h->dn); drop(h->s2); drop(h->nodei); drop(h->xnode); drop(h->lperm); drop(h->c16); drop(h->blk);
+}
+
+}  // namespace
 
 int stemk_upload(stemk_ctx* ctx, const stemk_seqset_desc* desc, stemk_set** out) {
   if (!ctx || !desc || !out) return fail(ctx, STEMK_ERR_ARG, "null argument");
@@ -246,14 +292,14 @@ int stemk_upload(stemk_ctx* ctx, const stemk_seqset_desc* desc, stemk_set** out)
   const CompiledSet& h = s->host;
   if (ctx->device == STEMK_DEVICE_NONE) { *out = s; return STEMK_OK; }
   size_t off = 0;
-  const size_t o_rec = place(off, h.rec), o_a = place(off, h.a), o_el = place(off, h.el), o_ql = place(off, h.ql),
-               o_paths = place(off, h.paths), o_gapt = place(off, h.gapt), o_bfreq = place(off, h.bfreq),
-               o_len = place(off, h.len), o_bcode = place(off, h.bcode), o_coff = place(off, h.coff),
-               o_cidx = place(off, h.cidx), o_ce = place(off, h.ce), o_lev = place(off, h.lev_off),
-               o_boff = place(off, h.boff), o_bab = place(off, h.bab), o_bfq = place(off, h.bfq),
-               o_ccode = place(off, h.ccode), o_cw = place(off, h.cw), o_prof = place(off, h.prof),
-               o_text = place(off, h.text), o_up = place(off, h.up), o_dn = place(off, h.dn), o_s2 = place(off, h.s2),
-               o_nodei = place(off, h.nodei), o_c16 = place(off, h.c16), o_blk = place(off, h.blk), o_xnode = place(off, h.xnode), o_lperm = place(off, h.lperm);
+  size_t* o = s->lay;
+  o[0] = place(off, h.rec); o[1] = place(off, h.a); o[2] = place(off, h.el); o[3] = place(off, h.ql);
+  o[4] = place(off, h.paths); o[5] = place(off, h.gapt); o[6] = place(off, h.bfreq); o[7] = place(off, h.len);
+  o[8] = place(off, h.bcode); o[9] = place(off, h.coff); o[10] = place(off, h.cidx); o[11] = place(off, h.ce);
+  o[12] = place(off, h.lev_off); o[13] = place(off, h.boff); o[14] = place(off, h.bab); o[15] = place(off, h.bfq);
+  o[16] = place(off, h.ccode); o[17] = place(off, h.cw); o[18] = place(off, h.prof); o[19] = place(off, h.text);
+  o[20] = place(off, h.up); o[21] = place(off, h.dn); o[22] = place(off, h.s2); o[23] = place(off, h.nodei);
+  o[24] = place(off, h.c16); o[25] = place(off, h.blk); o[26] = place(off, h.xnode); o[27] = place(off, h.lperm);
   off = (off + 255) & ~size_t(255);
   cudaError_t e = s->blob.reserve(std::max<size_t>(off, 256));
   // every array goes straight from its host vector to its place in the blob (no staging copy)
@@ -261,25 +307,16 @@ int stemk_upload(stemk_ctx* ctx, const stemk_seqset_desc* desc, stemk_set** out)
     if (e == cudaSuccess && !v.empty())
       e = cudaMemcpyAsync(static_cast<char*>(s->blob.p) + at, v.data(), v.size() * sizeof(v[0]), cudaMemcpyHostToDevice, ctx->stream);
   };
-  put(o_rec, h.rec); put(o_a, h.a); put(o_el, h.el); put(o_ql, h.ql); put(o_paths, h.paths); put(o_gapt, h.gapt);
-  put(o_bfreq, h.bfreq); put(o_len, h.len); put(o_bcode, h.bcode); put(o_coff, h.coff); put(o_cidx, h.cidx);
-  put(o_ce, h.ce); put(o_lev, h.lev_off); put(o_boff, h.boff); put(o_bab, h.bab); put(o_bfq, h.bfq);
-  put(o_ccode, h.ccode); put(o_cw, h.cw); put(o_prof, h.prof); put(o_text, h.text);
-  put(o_up, h.up); put(o_dn, h.dn); put(o_s2, h.s2); put(o_nodei, h.nodei); put(o_c16, h.c16); put(o_blk, h.blk); put(o_xnode, h.xnode); put(o_lperm, h.lperm);
+  put(o[0], h.rec); put(o[1], h.a); put(o[2], h.el); put(o[3], h.ql); put(o[4], h.paths); put(o[5], h.gapt);
+  put(o[6], h.bfreq); put(o[7], h.len); put(o[8], h.bcode); put(o[9], h.coff); put(o[10], h.cidx);
+  put(o[11], h.ce); put(o[12], h.lev_off); put(o[13], h.boff); put(o[14], h.bab); put(o[15], h.bfq);
+  put(o[16], h.ccode); put(o[17], h.cw); put(o[18], h.prof); put(o[19], h.text);
+  put(o[20], h.up); put(o[21], h.dn); put(o[22], h.s2); put(o[23], h.nodei); put(o[24], h.c16); put(o[25], h.blk);
+  put(o[26], h.xnode); put(o[27], h.lperm);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) { s->blob.release(); delete s; return cuda_fail(ctx, e, "set upload"); }
-  char* b = static_cast<char*>(s->blob.p);
-  SetView& v = s->view;
-  v.n_recs = (uint32_t)h.rec.size();
-  v.rec = (const RecDev*)(b + o_rec); v.a = (const double*)(b + o_a); v.el = (const double*)(b + o_el);
-  v.ql = (const double*)(b + o_ql); v.paths = (const double*)(b + o_paths); v.gapt = (const double*)(b + o_gapt);
-  v.bfreq = (const double*)(b + o_bfreq); v.len = (const uint32_t*)(b + o_len); v.bcode = (const uint8_t*)(b + o_bcode);
-  v.coff = (const uint32_t*)(b + o_coff); v.cidx = (const uint32_t*)(b + o_cidx); v.ce = (const double*)(b + o_ce);
-  v.lev_off = (const uint32_t*)(b + o_lev); v.boff = (const uint32_t*)(b + o_boff); v.bab = (const uint8_t*)(b + o_bab);
-  v.bfq = (const double*)(b + o_bfq); v.ccode = (const uint8_t*)(b + o_ccode); v.cw = (const double*)(b + o_cw);
-  v.prof = (const float*)(b + o_prof); v.text = (const uint8_t*)(b + o_text);
-  v.up = (const double*)(b + o_up); v.dn = (const double*)(b + o_dn); v.s2 = (const double*)(b + o_s2);
-  v.nodei = (const NodeI*)(b + o_nodei); v.c16 = (const uint16_t*)(b + o_c16); v.blk = (const uint32_t*)(b + o_blk); v.xnode = (const XNode*)(b + o_xnode); v.lperm = (const uint32_t*)(b + o_lperm);
+  make_view(s);
+  drop_upload_arrays(&s->host);
   *out = s;
   return STEMK_OK;
 }
@@ -289,6 +326,144 @@ void stemk_set_free(stemk_ctx* ctx, stemk_set* s) {
   if (ctx && ctx->device != STEMK_DEVICE_NONE) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
   s->blob.release();
   delete s;
+}
+
+// ---- one set on several devices -----------------------------------------------------------------------------
+int stemk_set_clone(stemk_ctx* ctx, const stemk_set* src, stemk_set** out) {
+  if (!ctx || !src || !out) return fail(ctx, STEMK_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (ctx->device == STEMK_DEVICE_NONE || src->device == STEMK_DEVICE_NONE) return no_device(ctx);
+  if (src->loop_gap != ctx->params.loop_gap || src->len_band != ctx->params.len_band)
+    return fail(ctx, STEMK_ERR_ARG, "stemk_set_clone: the destination context has another loop gap or length band");
+  CU(cudaSetDevice(ctx->device));
+  stemk_set* s = new stemk_set(src->hostp);   // record headers and statistics are shared, not copied
+  s->device = ctx->device; s->loop_gap = src->loop_gap; s->len_band = src->len_band;
+  std::memcpy(s->lay, src->lay, sizeof(s->lay));
+  cudaError_t e = s->blob.reserve(std::max<size_t>(src->blob.bytes, 256));
+  // device to device: over NVLink when the two devices are peers, staged by the driver otherwise
+  if (e == cudaSuccess) e = cudaMemcpyPeerAsync(s->blob.p, ctx->device, src->blob.p, src->device, src->blob.bytes, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) { s->blob.release(); delete s; return cuda_fail(ctx, e, "stemk_set_clone"); }
+  make_view(s);
+  *out = s;
+  return STEMK_OK;
+}
+
+int stemk_upload_multi(stemk_ctx* const* ctxs, int n_ctx, const stemk_seqset_desc* desc, stemk_set** sets) {
+  if (!ctxs || n_ctx < 1 || !desc || !sets) return fail(n_ctx > 0 && ctxs ? ctxs[0] : nullptr, STEMK_ERR_ARG, "null argument");
+  for (int d = 0; d < n_ctx; ++d) sets[d] = nullptr;
+  int rc = stemk_upload(ctxs[0], desc, &sets[0]);   // the records are compiled once ...
+  for (int d = 1; rc == STEMK_OK && d < n_ctx; ++d) {
+    rc = stemk_set_clone(ctxs[d], sets[0], &sets[d]);   // ... and reach the other devices device-to-device
+    if (rc != STEMK_OK) fail(ctxs[0], rc, std::string("device ") + std::to_string(d) + ": " + stemk_last_error(ctxs[d]));
+  }
+  if (rc != STEMK_OK) for (int d = 0; d < n_ctx; ++d) { stemk_set_free(ctxs[d], sets[d]); sets[d] = nullptr; }
+  return rc;
+}
+
+// A set as one byte string -- [header | host-side record headers and statistics | device blob] -- written into a
+// DEVICE buffer, so that a multi-process driver can broadcast it (NCCL) instead of compiling the records once per
+// rank.  Layout private to this library version.
+}  // extern "C" (templates below)
+namespace {
+constexpr uint64_t kExportMagic = 0x53544d4b53455432ull;   // "STMKSET2"
+struct ExportHeader {
+  uint64_t magic, meta_bytes, blob_bytes;
+  double loop_gap;
+  uint32_t len_band, n_recs;
+  uint64_t lay[kBlobArrays];
+  uint32_t max_E4, max_fastN, n_fast, max_band_cnt, n_weighted, n_simple_cols, has_dag, max_N, max_L, max_E, max_nlev, pad_;
+  uint64_t cnt[12];   // element counts of the meta arrays, in the order of meta_arrays()
+};
+template <class F>
+void meta_arrays(CompiledSet& h, F&& f) {   // every host array that outlives the upload
+  f(0, h.rec); f(1, h.n_nodes_all); f(2, h.n_edges_all); f(3, h.max_level_rows); f(4, h.band_cnt); f(5, h.deg_all);
+  f(6, h.len); f(7, h.boff); f(8, h.text); f(9, h.cost_off); f(10, h.cost_pd); f(11, h.cost_pb);
+}
+size_t round256(size_t v) { return (v + 255) & ~size_t(255); }
+}  // namespace
+extern "C" {
+
+uint64_t stemk_set_export_bytes(const stemk_set* s) {
+  if (!s || s->device == STEMK_DEVICE_NONE) return 0;
+  size_t meta = 0;
+  meta_arrays(const_cast<CompiledSet&>(s->host), [&](int, auto& v) { meta += round256(v.size() * sizeof(v[0])); });
+  return round256(sizeof(ExportHeader)) + meta + round256(s->blob.bytes);
+}
+
+int stemk_set_export(stemk_ctx* ctx, const stemk_set* s, void* d_dst, void* stream_) {
+  if (!ctx || !s || !d_dst) return fail(ctx, STEMK_ERR_ARG, "null argument");
+  if (ctx->device == STEMK_DEVICE_NONE) return no_device(ctx);
+  if (!set_usable(ctx, s)) return fail(ctx, STEMK_ERR_ARG, kSetMismatch);
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = stream_ ? (cudaStream_t)stream_ : ctx->stream;
+  const CompiledSet& h = s->host;
+  ExportHeader hd;
+  std::memset(&hd, 0, sizeof(hd));
+  hd.magic = kExportMagic; hd.blob_bytes = s->blob.bytes; hd.loop_gap = s->loop_gap; hd.len_band = s->len_band;
+  hd.n_recs = (uint32_t)h.rec.size();
+  for (int k = 0; k < kBlobArrays; ++k) hd.lay[k] = s->lay[k];
+  hd.max_E4 = h.max_E4; hd.max_fastN = h.max_fastN; hd.n_fast = h.n_fast; hd.max_band_cnt = h.max_band_cnt;
+  hd.n_weighted = h.n_weighted; hd.n_simple_cols = h.n_simple_cols; hd.has_dag = h.has_dag ? 1u : 0u;
+  hd.max_N = h.max_N; hd.max_L = h.max_L; hd.max_E = h.max_E; hd.max_nlev = h.max_nlev;
+  size_t meta = 0;
+  meta_arrays(s->host, [&](int k, auto& v) { hd.cnt[k] = v.size(); meta += round256(v.size() * sizeof(v[0])); });
+  hd.meta_bytes = meta;
+  char* dst = static_cast<char*>(d_dst);
+  // the header and the host arrays are pageable: the copies below return when the source has been read
+  CU(cudaMemcpyAsync(dst, &hd, sizeof(hd), cudaMemcpyHostToDevice, st));
+  size_t at = round256(sizeof(ExportHeader));
+  cudaError_t e = cudaSuccess;
+  meta_arrays(s->host, [&](int, auto& v) {
+    if (e == cudaSuccess && !v.empty()) e = cudaMemcpyAsync(dst + at, v.data(), v.size() * sizeof(v[0]), cudaMemcpyHostToDevice, st);
+    at += round256(v.size() * sizeof(v[0]));
+  });
+  CU(e);
+  CU(cudaMemcpyAsync(dst + at, s->blob.p, s->blob.bytes, cudaMemcpyDeviceToDevice, st));
+  CU(cudaStreamSynchronize(st));
+  return STEMK_OK;
+}
+
+int stemk_set_import(stemk_ctx* ctx, const void* d_src, uint64_t bytes, stemk_set** out) {
+  if (!ctx || !d_src || !out) return fail(ctx, STEMK_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (ctx->device == STEMK_DEVICE_NONE) return no_device(ctx);
+  if (bytes < sizeof(ExportHeader)) return fail(ctx, STEMK_ERR_ARG, "stemk_set_import: buffer too small");
+  CU(cudaSetDevice(ctx->device));
+  const char* src = static_cast<const char*>(d_src);
+  ExportHeader hd;
+  CU(cudaMemcpyAsync(&hd, src, sizeof(hd), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (hd.magic != kExportMagic) return fail(ctx, STEMK_ERR_ARG, "stemk_set_import: not a set exported by this library version");
+  if (round256(sizeof(ExportHeader)) + hd.meta_bytes + round256(hd.blob_bytes) > bytes)
+    return fail(ctx, STEMK_ERR_ARG, "stemk_set_import: truncated buffer");
+  if (hd.loop_gap != ctx->params.loop_gap || hd.len_band != ctx->params.len_band)
+    return fail(ctx, STEMK_ERR_ARG, "stemk_set_import: the set was compiled under another loop gap or length band");
+  stemk_set* s = new stemk_set;
+  s->device = ctx->device; s->loop_gap = hd.loop_gap; s->len_band = hd.len_band;
+  for (int k = 0; k < kBlobArrays; ++k) s->lay[k] = (size_t)hd.lay[k];
+  CompiledSet& h = s->host;
+  h.max_E4 = hd.max_E4; h.max_fastN = hd.max_fastN; h.n_fast = hd.n_fast; h.max_band_cnt = hd.max_band_cnt;
+  h.n_weighted = hd.n_weighted; h.n_simple_cols = hd.n_simple_cols; h.has_dag = hd.has_dag != 0;
+  h.max_N = hd.max_N; h.max_L = hd.max_L; h.max_E = hd.max_E; h.max_nlev = hd.max_nlev;
+  size_t at = round256(sizeof(ExportHeader));
+  cudaError_t e = cudaSuccess;
+  try {
+    meta_arrays(h, [&](int k, auto& v) {
+      v.resize((size_t)hd.cnt[k]);
+      if (e == cudaSuccess && !v.empty()) e = cudaMemcpyAsync(v.data(), src + at, v.size() * sizeof(v[0]), cudaMemcpyDeviceToHost, ctx->stream);
+      at += round256(v.size() * sizeof(v[0]));
+    });
+  } catch (const std::bad_alloc&) { delete s; return fail(ctx, STEMK_ERR_NOMEM, "stemk_set_import: out of host memory"); }
+  if (e == cudaSuccess && at != round256(sizeof(ExportHeader)) + hd.meta_bytes) { delete s; return fail(ctx, STEMK_ERR_ARG, "stemk_set_import: inconsistent header"); }
+  if (e == cudaSuccess) e = s->blob.reserve(std::max<size_t>((size_t)hd.blob_bytes, 256));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(s->blob.p, src + at, (size_t)hd.blob_bytes, cudaMemcpyDeviceToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) { s->blob.release(); delete s; return cuda_fail(ctx, e, "stemk_set_import"); }
+  if (h.rec.size() != hd.n_recs) { s->blob.release(); delete s; return fail(ctx, STEMK_ERR_ARG, "stemk_set_import: inconsistent header"); }
+  make_view(s);
+  *out = s;
+  return STEMK_OK;
 }
 
 uint32_t stemk_set_size(const stemk_set* s) { return s ? (uint32_t)s->host.rec.size() : 0; }
@@ -599,6 +774,85 @@ int stemk_gram(stemk_ctx* ctx, const stemk_set* train, int normalize, double* ou
     std::fprintf(stderr, "stemk_gram: %u records: permutation + pair-list launch %.1f ms, enqueue %.1f ms, device %.1f ms, D2H through pinned staging %.1f ms\n", n,
                  ms(tg0, tg1), ms(tg1, tg2), ms(tg2, tg3), ms(tg3, now()));
   return STEMK_OK;
+}
+
+// KernelMatrix::calculate over several devices of ONE process: the reference's MPI path (CalcTrainMatrix with
+// `cnt % size == rank`, kernel_matrix.cpp:186-262; Ssend/Recv of every rank's values to rank 0, :495-526; normalisation
+// of the gathered matrix, :560-571) with a device in the place of a rank.  One global y-major pair order, position k
+// goes to device k % n_ctx (neighbouring pairs cost nearly the same: balanced to a fraction of a percent, and every
+// device still runs its expensive pairs first); every device evaluates its share through stemk_pairs_device on its own
+// stream, device 0 pulls the shares over NVLink (cudaMemcpyPeerAsync behind an event of the producing stream), puts
+// them back into the global order, scatters with the mirror and normalises.
+int stemk_gram_multi(stemk_ctx* const* ctxs, const stemk_set* const* sets, int n_ctx, int normalize, double* out) {
+  stemk_ctx* ctx = (ctxs && n_ctx > 0) ? ctxs[0] : nullptr;
+  if (!ctx || !sets || !out) return fail(ctx, STEMK_ERR_ARG, "null argument");
+  for (int d = 0; d < n_ctx; ++d) {
+    if (!ctxs[d] || !sets[d]) return fail(ctx, STEMK_ERR_ARG, "null context or set");
+    if (ctxs[d]->device == STEMK_DEVICE_NONE) return no_device(ctx);
+    if (!set_usable(ctxs[d], sets[d])) return fail(ctx, STEMK_ERR_ARG, kSetMismatch);
+    if (sets[d]->host.rec.size() != sets[0]->host.rec.size() || std::memcmp(&ctxs[d]->params, &ctx->params, sizeof(stemk_params)) != 0)
+      return fail(ctx, STEMK_ERR_ARG, "stemk_gram_multi: the contexts must share their kernel parameters and the sets their records");
+    for (int q = 0; q < d; ++q) if (ctxs[q]->device == ctxs[d]->device) return fail(ctx, STEMK_ERR_ARG, "stemk_gram_multi: one context per device");
+  }
+  if (n_ctx == 1) return stemk_gram(ctx, sets[0], normalize, out);
+  const uint32_t n = (uint32_t)sets[0]->host.rec.size();
+  if (n == 0) return STEMK_OK;
+  const uint32_t W = (uint32_t)n_ctx;
+  const std::vector<uint32_t> perm = size_order(ctx, sets[0]->host, nullptr, n);
+  std::vector<unsigned long long> off(n);
+  unsigned long long acc = 0;
+  for (uint32_t q = 0; q < n; ++q) { off[q] = acc; acc += (unsigned long long)perm[q] + 1ull; }
+  const size_t n_pairs = (size_t)n * (n + 1) / 2;
+  const size_t per = (n_pairs + W - 1) / W;
+  auto dfail = [&](int d, int rc) { if (d > 0) fail(ctx, rc, std::string("device ") + std::to_string(d) + ": " + stemk_last_error(ctxs[d])); return rc; };
+  // ---- every device: the pair list from the permutation, its share of it, the values
+  for (uint32_t d = 0; d < W; ++d) {
+    stemk_ctx* c = ctxs[d];
+    const size_t mine = n_pairs > d ? (n_pairs - d + W - 1) / W : 0;
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e == cudaSuccess && !c->multi_ev) e = cudaEventCreateWithFlags(&c->multi_ev, cudaEventDisableTiming);
+    for (auto [buf, bytes] : {std::pair<DevBuf*, size_t>{&c->idx_x, n_pairs * sizeof(uint32_t)}, {&c->idx_y, n_pairs * sizeof(uint32_t)},
+                              {&c->deal_x, per * sizeof(uint32_t)}, {&c->deal_y, per * sizeof(uint32_t)}, {&c->vals, per * sizeof(double)},
+                              {&c->perm, n * sizeof(uint32_t)}, {&c->offs, n * sizeof(unsigned long long)}})
+      if (e == cudaSuccess) e = buf->reserve(bytes);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->perm.p, perm.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->offs.p, off.data(), n * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = launch_gram_pairs((const uint32_t*)c->perm.p, (const unsigned long long*)c->offs.p, n, (uint32_t*)c->idx_x.p, (uint32_t*)c->idx_y.p, c->stream);
+    if (e == cudaSuccess) e = launch_deal_pairs((const uint32_t*)c->idx_x.p, (const uint32_t*)c->idx_y.p, n_pairs, d, W, (uint32_t*)c->deal_x.p, (uint32_t*)c->deal_y.p, c->stream);
+    if (e != cudaSuccess) return dfail((int)d, cuda_fail(c, e, "stemk_gram_multi"));
+    c->launches += 2;
+    if (mine) {
+      const int rc = stemk_pairs_device(c, sets[d], sets[d], mine, (const uint32_t*)c->deal_x.p, (const uint32_t*)c->deal_y.p, (double*)c->vals.p, c->stream);
+      if (rc != STEMK_OK) return dfail((int)d, rc);
+    }
+    e = cudaEventRecord(c->multi_ev, c->stream);
+    if (e != cudaSuccess) return dfail((int)d, cuda_fail(c, e, "stemk_gram_multi"));
+  }
+  // ---- device 0: gather, un-deal, assemble
+  CU(cudaSetDevice(ctx->device));
+  CU(ctx->gathered.reserve(per * W * sizeof(double)));
+  CU(ctx->undealt.reserve(n_pairs * sizeof(double)));
+  CU(ctx->matrix.reserve((size_t)n * n * sizeof(double)));
+  for (uint32_t d = 0; d < W; ++d) {
+    const size_t mine = n_pairs > d ? (n_pairs - d + W - 1) / W : 0;
+    if (!mine) continue;
+    if (d > 0) {
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, ctx->device, ctxs[d]->device) == cudaSuccess && can) {
+        const cudaError_t pe = cudaDeviceEnablePeerAccess(ctxs[d]->device, 0);
+        if (pe != cudaSuccess) cudaGetLastError();   // already enabled
+      }
+      CU(cudaStreamWaitEvent(ctx->stream, ctxs[d]->multi_ev, 0));
+    }
+    CU(cudaMemcpyPeerAsync(static_cast<double*>(ctx->gathered.p) + (size_t)d * per, ctx->device, ctxs[d]->vals.p, ctxs[d]->device,
+                           mine * sizeof(double), ctx->stream));
+  }
+  CU(launch_undeal((const double*)ctx->gathered.p, per, W, n_pairs, (double*)ctx->undealt.p, ctx->stream));
+  ctx->launches += 1;
+  int rc = stemk_assemble_device(ctx, n_pairs, (const uint32_t*)ctx->idx_x.p, (const uint32_t*)ctx->idx_y.p,
+                                 (const double*)ctx->undealt.p, n, normalize, (double*)ctx->matrix.p, ctx->stream);
+  if (rc != STEMK_OK) return rc;
+  return copy_out(ctx, out, ctx->matrix.p, (size_t)n * n * sizeof(double));
 }
 
 int stemk_assemble_device(stemk_ctx* ctx, size_t n_pairs, const uint32_t* d_xi, const uint32_t* d_yi,

@@ -258,6 +258,24 @@ class GpuBackend:
         return self.matrix
 
 
+def broadcast_set(ctx, dset, src=0, group=None):
+    """One compiled set on every rank: rank `src` passes its uploaded DeviceSet, the others None.  The records are
+    compiled once (stemk_upload on `src`); the compiled set travels as ONE device-to-device broadcast (NCCL over
+    NVLink) of stemk_set_export's byte string and becomes a set again through stemk_set_import -- instead of one
+    host compile and one host->device copy per rank."""
+    from .api import DeviceSet
+    rank = dist.get_rank(group)
+    dev = torch.device("cuda", ctx.device)
+    nbytes = torch.tensor([dset.export_bytes() if rank == src else 0], dtype=torch.int64, device=dev)
+    dist.broadcast(nbytes, src, group=group)
+    buf = torch.empty(int(nbytes.item()), dtype=torch.uint8, device=dev)
+    if rank == src:
+        dset.export_to(buf.data_ptr())          # returns when the bytes are in `buf`
+    dist.broadcast(buf, src, group=group)
+    torch.cuda.current_stream(dev).synchronize()
+    return dset if rank == src else DeviceSet.import_from(ctx, buf.data_ptr(), buf.numel())
+
+
 def record_keys(dset, stem=True, string=False):
     """Per-record size key of the work order (cost of the record against itself)."""
     v, e, length = dset.stats()
