@@ -39,8 +39,20 @@ def _lib(name):
     return _libs[name]
 
 
+# which build of the reference harness lib() hands out: "libstemk_ref.so" (the checker proper) or
+# "libstemk_ref_binding.so" (the same translation units + the KernelMatrix binding of INTEGRATION.md linked against the
+# product library; tests/test_ref_binding.py switches to it with use_library()).  MData / kernel handles belong to the
+# library that made them.
+_DEFAULT = "libstemk_ref.so"
+
+
+def use_library(name):
+    global _DEFAULT
+    _DEFAULT = name
+
+
 def lib():
-    L = _lib("libstemk_ref.so")
+    L = _lib(_DEFAULT)
     if getattr(L, "_typed", False):
         return L
     vp, ci, cu, cd, cf = C.c_void_p, C.c_int, C.c_uint, C.c_double, C.c_float
@@ -69,6 +81,13 @@ def lib():
     L.ref_diag.argtypes = [vp, ci, P(vp), vp, ci, cu, vp]
     L.ref_pairs_timed.restype = cd
     L.ref_pairs_timed.argtypes = [vp, ci, P(vp), ci, vp, vp, cu, vp]
+    if hasattr(L, "refbind_gram"):   # the compiled INTEGRATION.md binding (oracle/ref_binding_test.cpp)
+        L.refbind_gram.restype = ci
+        L.refbind_gram.argtypes = [vp, ci, P(vp), vp, ci, ci, vp, vp, C.c_long, P(C.c_long), vp, C.c_long]
+        L.refbind_cross.restype = ci
+        L.refbind_cross.argtypes = [vp, ci, P(vp), ci, P(vp), ci, ci, ci, vp, vp, vp, C.c_long]
+        L.refbind_diag.restype = ci
+        L.refbind_diag.argtypes = [vp, ci, P(vp), vp, ci, ci, vp, vp, C.c_long]
     L._typed = True
     return L
 
@@ -199,6 +218,38 @@ class RefKernel:
         sv = np.ascontiguousarray(sv_index, dtype=np.uint32)
         secs = lib().ref_diag(self.h, len(train), self._hs(train), sv.ctypes.data, len(sv), n_th, out.ctypes.data)
         return out, secs
+
+    # ---- the same KernelMatrix members through the compiled binding (GpuBound<K>, oracle/ref_binding_test.cpp)
+    @staticmethod
+    def _bound(rc, err):
+        if rc != 0:
+            raise RuntimeError("reference-side binding: " + err.value.decode(errors="replace"))
+
+    def bound_gram(self, ds, normalize=False, labels=None, device=0):
+        n = len(ds)
+        out = np.zeros((n, n))
+        lab = np.ascontiguousarray(labels, dtype=np.int32) if labels is not None else None
+        text = C.create_string_buffer(64 + n * (n + 2) * 24)
+        tl, err = C.c_long(0), C.create_string_buffer(512)
+        self._bound(lib().refbind_gram(self.h, n, self._hs(ds), lab.ctypes.data if lab is not None else None, int(normalize),
+                                       device, out.ctypes.data, text, len(text), C.byref(tl), err, len(err)), err)
+        return out, text.raw[:tl.value].decode()
+
+    def bound_cross(self, test, train, norm_test=False, normalize=False, device=0):
+        out = np.zeros((len(test), len(train)))
+        selfv = np.zeros(len(test))
+        err = C.create_string_buffer(512)
+        self._bound(lib().refbind_cross(self.h, len(test), self._hs(test), len(train), self._hs(train), int(norm_test),
+                                        int(normalize), device, out.ctypes.data, selfv.ctypes.data, err, len(err)), err)
+        return out, selfv
+
+    def bound_diag(self, train, sv_index=(), device=0, init=0.0):
+        out = np.full(len(train), init, dtype=np.float64)
+        sv = np.ascontiguousarray(sv_index, dtype=np.uint32)
+        err = C.create_string_buffer(512)
+        self._bound(lib().refbind_diag(self.h, len(train), self._hs(train), sv.ctypes.data, len(sv), device, out.ctypes.data,
+                                       err, len(err)), err)
+        return out
 
     def pairs_timed(self, ds, pi, pj, n_th=1):
         pi = np.ascontiguousarray(pi, dtype=np.int32)
