@@ -130,6 +130,14 @@ int stemk_set_option(stemk_ctx* ctx, int option, int value);
  * Sets are bound to the device, loop gap and length band of the context that uploaded them (the derived per-record
  * tables depend on them); using a set with another context fails with STEMK_ERR_ARG. */
 
+/* Limits (records outside them fail the call with STEMK_ERR_NOMEM and a message naming the record; there is no CPU
+ * path to fall back to): the fast stem kernel takes records of up to 1024 non-leaf DAG nodes whose gap powers
+ * g^(len/2) stay within 1e-125 .. 1e125 (about 360 nt of pair span at g = 0.2) with unit edge weights, single-entry
+ * base-pair profiles and no gap columns under a node -- every record the reference's front end makes from one
+ * sequence; everything else (alignments, IUPAC codes, hand-made DAGs) runs on the general stem kernel, which stages
+ * the second record of a pair in shared memory: about 1000 non-leaf nodes / 8000 inner edges per record.  The string
+ * kernels have no length limit. */
+
 /* upload a flattened set (copied; derived per-record tables are built here) */
 int stemk_upload(stemk_ctx* ctx, const stemk_seqset_desc* desc, stemk_set** set);
 void stemk_set_free(stemk_ctx* ctx, stemk_set* set);

@@ -16,6 +16,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <exception>
 #include <functional>
 #include <thread>
@@ -53,6 +54,12 @@ struct RecOut {  // one record's share, appended to the CompiledSet in record or
   std::vector<double> pd, pb;  // work-model prefix sums over node length
   uint32_t n_all = 0, e_all = 0, max_rows = 0, band_cnt = 0;
   std::string err;
+  void swap_arrays(RecOut& o) {   // takes over (and with a fresh object: releases) o's arrays
+    a.swap(o.a); el.swap(o.el); ql.swap(o.ql); paths.swap(o.paths); gapt.swap(o.gapt); bfreq.swap(o.bfreq); ce.swap(o.ce); bfq.swap(o.bfq);
+    cw.swap(o.cw); len.swap(o.len); coff.swap(o.coff); cidx.swap(o.cidx); lev_off.swap(o.lev_off); boff.swap(o.boff); bcode.swap(o.bcode);
+    bab.swap(o.bab); ccode.swap(o.ccode); text.swap(o.text); prof.swap(o.prof); deg_all.swap(o.deg_all); up.swap(o.up); dn.swap(o.dn);
+    s2.swap(o.s2); nodei.swap(o.nodei); c16.swap(o.c16); blk.swap(o.blk); lperm.swap(o.lperm); pd.swap(o.pd); pb.swap(o.pb);
+  }
 };
 
 void compile_record(const stemk_seqset_desc& s, uint32_t r, double g, uint32_t len_band, RecOut* o) {
@@ -350,7 +357,8 @@ void append(std::vector<T>& dst, const std::vector<T>& src) { dst.insert(dst.end
 
 }  // namespace
 
-std::string compile_set(const stemk_seqset_desc& s, double g, uint32_t len_band, int n_threads, bool timing, CompiledSet* out) {
+std::string compile_set(const stemk_seqset_desc& s, double g, uint32_t len_band, int n_threads, bool timing, CompiledSet* out,
+                        const std::function<char*(size_t)>& sink) {
   const uint32_t n = s.n_seqs;
   auto t0 = std::chrono::steady_clock::now();
   std::vector<RecOut> recs(n);
@@ -374,99 +382,103 @@ std::string compile_set(const stemk_seqset_desc& s, double g, uint32_t len_band,
   CompiledSet& c = *out;
   c = CompiledSet();
   c.rec.resize(n);
-  {  // one allocation per array instead of growth by doubling
-    size_t nn = 0, ne = 0, nl = 0, nb = 0, nc = 0, n16 = 0, nblk = 0, ncost = 0;
-    for (const RecOut& o : recs) {
-      nn += o.a.size(); ne += o.cidx.size(); nl += o.lev_off.size(); nb += o.bab.size(); nc += o.ccode.size();
-      n16 += o.c16.size(); nblk += o.blk.size(); ncost += std::max<size_t>(1, o.pd.size());
-    }
-    for (auto* v : {&c.a, &c.el, &c.ql, &c.paths, &c.gapt, &c.bfreq, &c.up, &c.dn, &c.s2}) v->reserve(nn);
-    c.len.reserve(nn); c.bcode.reserve(nn); c.nodei.reserve(nn); c.deg_all.reserve(nn);
-    c.coff.reserve(nn + n); c.boff.reserve(nn + n); c.cidx.reserve(ne); c.ce.reserve(ne); c.lev_off.reserve(nl);
-    c.bab.reserve(nb); c.bfq.reserve(nb); c.ccode.reserve(nc); c.cw.reserve(nc); c.text.reserve(nc);
-    c.prof.reserve(4 * nc); c.c16.reserve(n16); c.blk.reserve(nblk); c.lperm.reserve(nn); c.cost_pd.reserve(ncost); c.cost_pb.reserve(ncost);
-    c.cost_off.reserve(n + 1); c.n_nodes_all.reserve(n); c.n_edges_all.reserve(n); c.max_level_rows.reserve(n);
-  }
   // ---- merge.  Pass 1 (serial, sizes only): record headers, the offsets that become absolute, set statistics.
   std::vector<uint32_t> e0s(n), b0s(n);
-  {
-    size_t nn = 0, ncoff = 0, nlev = 0, nboff = 0, ncol = 0, n16 = 0, nblk = 0, ne = 0, nb = 0, ncost = 0;
-    for (uint32_t r = 0; r < n; ++r) {
-      RecOut& o = recs[r];
-      if (!o.err.empty()) return "record " + std::to_string(r) + ": " + o.err;
-      RecDev h = o.hdr;
-      h.node0 = (uint32_t)nn; h.coff0 = (uint32_t)ncoff; h.lev0 = (uint32_t)nlev; h.boff0 = (uint32_t)nboff; h.col0 = (uint32_t)ncol;
-      h.c16_0 = (uint32_t)n16; h.e4 = (uint32_t)o.c16.size();
-      h.blk0 = (uint32_t)nblk; h.nblk = (uint32_t)o.blk.size();
-      if (h.flags & REC_FAST) {
-        c.max_E4 = std::max(c.max_E4, h.e4); c.max_fastN = std::max(c.max_fastN, h.N); ++c.n_fast;
-        c.max_band_cnt = std::max(c.max_band_cnt, o.band_cnt);
-      }
-      e0s[r] = (uint32_t)ne; b0s[r] = (uint32_t)nb;
-      if (o.pd.empty()) { o.pd.assign(1, 0.0); o.pb.assign(1, 0.0); }
-      c.cost_off.push_back(ncost);
-      c.rec[r] = h;
-      c.n_nodes_all.push_back(o.n_all);
-      c.n_edges_all.push_back(o.e_all);
-      c.max_level_rows.push_back(o.max_rows);
-      c.band_cnt.push_back(o.band_cnt);
-      if (o.n_all) c.has_dag = true;
-      if (h.flags & REC_HAS_WEIGHT) ++c.n_weighted;
-      if (h.flags & REC_SIMPLE_COLS) ++c.n_simple_cols;
-      c.max_N = std::max(c.max_N, h.N);
-      c.max_L = std::max(c.max_L, h.L);
-      c.max_E = std::max(c.max_E, (uint32_t)o.cidx.size());
-      c.max_nlev = std::max(c.max_nlev, h.nlev);
-      nn += o.a.size(); ncoff += o.coff.size(); nlev += o.lev_off.size(); nboff += o.boff.size(); ncol += o.ccode.size();
-      n16 += o.c16.size(); nblk += o.blk.size(); ne += o.cidx.size(); nb += o.bab.size(); ncost += o.pd.size();
+  size_t nn = 0, ncoff = 0, nlev = 0, nboff = 0, ncol = 0, n16 = 0, nblk = 0, ne = 0, nb = 0, ncost = 0;
+  c.cost_off.reserve(n + 1); c.n_nodes_all.reserve(n); c.n_edges_all.reserve(n); c.max_level_rows.reserve(n); c.band_cnt.reserve(n);
+  for (uint32_t r = 0; r < n; ++r) {
+    RecOut& o = recs[r];
+    if (!o.err.empty()) return "record " + std::to_string(r) + ": " + o.err;
+    RecDev h = o.hdr;
+    h.node0 = (uint32_t)nn; h.coff0 = (uint32_t)ncoff; h.lev0 = (uint32_t)nlev; h.boff0 = (uint32_t)nboff; h.col0 = (uint32_t)ncol;
+    h.c16_0 = (uint32_t)n16; h.e4 = (uint32_t)o.c16.size();
+    h.blk0 = (uint32_t)nblk; h.nblk = (uint32_t)o.blk.size();
+    if (h.flags & REC_FAST) {
+      c.max_E4 = std::max(c.max_E4, h.e4); c.max_fastN = std::max(c.max_fastN, h.N); ++c.n_fast;
+      c.max_band_cnt = std::max(c.max_band_cnt, o.band_cnt);
     }
+    e0s[r] = (uint32_t)ne; b0s[r] = (uint32_t)nb;
+    if (o.pd.empty()) { o.pd.assign(1, 0.0); o.pb.assign(1, 0.0); }
     c.cost_off.push_back(ncost);
+    c.rec[r] = h;
+    c.n_nodes_all.push_back(o.n_all);
+    c.n_edges_all.push_back(o.e_all);
+    c.max_level_rows.push_back(o.max_rows);
+    c.band_cnt.push_back(o.band_cnt);
+    if (o.n_all) c.has_dag = true;
+    if (h.flags & REC_HAS_WEIGHT) ++c.n_weighted;
+    if (h.flags & REC_SIMPLE_COLS) ++c.n_simple_cols;
+    c.max_N = std::max(c.max_N, h.N);
+    c.max_L = std::max(c.max_L, h.L);
+    c.max_E = std::max(c.max_E, (uint32_t)o.cidx.size());
+    c.max_nlev = std::max(c.max_nlev, h.nlev);
+    nn += o.a.size(); ncoff += o.coff.size(); nlev += o.lev_off.size(); nboff += o.boff.size(); ncol += o.ccode.size();
+    n16 += o.c16.size(); nblk += o.blk.size(); ne += o.cidx.size(); nb += o.bab.size(); ncost += o.pd.size();
   }
-  // Pass 2: the arrays themselves, one group of arrays per thread (every group walks the records in order).
+  c.cost_off.push_back(ncost);
+  // what the host keeps (work model, scheduler, launch shapes)
+  c.len.resize(nn); c.deg_all.resize(nn); c.boff.resize(nboff); c.text.resize(ncol); c.cost_pd.resize(ncost); c.cost_pb.resize(ncost);
+  // ---- the device image: every array of the SetView at its place in ONE buffer (the order of stemk_api.cu's
+  // make_view), 256-byte aligned; with no sink (host-only context) only the host arrays are filled
+  enum { A_REC, A_A, A_EL, A_QL, A_PATHS, A_GAPT, A_BFREQ, A_LEN, A_BCODE, A_COFF, A_CIDX, A_CE, A_LEV, A_BOFF, A_BAB, A_BFQ,
+         A_CCODE, A_CW, A_PROF, A_TEXT, A_UP, A_DN, A_S2, A_NODEI, A_C16, A_BLK, A_XNODE, A_LPERM, A_COUNT };
+  static_assert(A_COUNT == kBlobArrays, "blob layout");
+  size_t off = 0;
+  auto place = [&](size_t bytes) { off = (off + 255) & ~size_t(255); const size_t at = off; off += bytes; return at; };
+  size_t* L = c.blob_lay;
+  L[A_REC] = place(n * sizeof(RecDev));
+  L[A_A] = place(nn * 8); L[A_EL] = place(nn * 8); L[A_QL] = place(nn * 8); L[A_PATHS] = place(nn * 8); L[A_GAPT] = place(nn * 8);
+  L[A_BFREQ] = place(nn * 8); L[A_LEN] = place(nn * 4); L[A_BCODE] = place(nn); L[A_COFF] = place(ncoff * 4);
+  L[A_CIDX] = place(ne * 4); L[A_CE] = place(ne * 8); L[A_LEV] = place(nlev * 4); L[A_BOFF] = place(nboff * 4);
+  L[A_BAB] = place(nb); L[A_BFQ] = place(nb * 8); L[A_CCODE] = place(ncol); L[A_CW] = place(ncol * 8);
+  L[A_PROF] = place(ncol * 4 * 4); L[A_TEXT] = place(ncol); L[A_UP] = place(nn * 8); L[A_DN] = place(nn * 8); L[A_S2] = place(nn * 8);
+  L[A_NODEI] = place(nn * sizeof(NodeI)); L[A_C16] = place(n16 * 2); L[A_BLK] = place(nblk * 4);
+  L[A_XNODE] = place(nn * sizeof(XNode)); L[A_LPERM] = place(nn * 4);
+  c.blob_bytes = (off + 255) & ~size_t(255);
+  char* blob = sink ? sink(c.blob_bytes) : nullptr;
+  if (sink && !blob) return "out of memory for the compiled set";
+  // Pass 2: the arrays themselves, records in parallel (each thread a contiguous range of records).
   {
-    std::vector<std::function<void()>> groups;
-    groups.push_back([&]() { for (RecOut& o : recs) { append(c.a, o.a); append(c.el, o.el); append(c.ql, o.ql); append(c.paths, o.paths); append(c.gapt, o.gapt); } });
-    groups.push_back([&]() { for (RecOut& o : recs) { append(c.bfreq, o.bfreq); append(c.up, o.up); append(c.dn, o.dn); append(c.s2, o.s2); append(c.nodei, o.nodei); } });
-    groups.push_back([&]() {
-      for (uint32_t r = 0; r < n; ++r) {   // child / profile offsets become absolute so the kernels index cidx/ce/bab/bfq directly
+    auto copy = [&](int which, size_t elem_off, const auto& v) {
+      if (blob && !v.empty()) std::memcpy(blob + L[which] + elem_off * sizeof(v[0]), v.data(), v.size() * sizeof(v[0]));
+    };
+    auto fill = [&](uint32_t r_lo, uint32_t r_hi) {
+      for (uint32_t r = r_lo; r < r_hi; ++r) {
         RecOut& o = recs[r];
+        const RecDev& h = c.rec[r];
+        // child / profile offsets become absolute so the kernels index cidx/ce/bab/bfq directly
         for (auto& v : o.coff) v += e0s[r];
         for (auto& v : o.boff) v += b0s[r];
-        append(c.coff, o.coff); append(c.boff, o.boff); append(c.len, o.len); append(c.bcode, o.bcode); append(c.deg_all, o.deg_all);
-        append(c.lev_off, o.lev_off);
-      }
-    });
-    groups.push_back([&]() { for (RecOut& o : recs) { append(c.cidx, o.cidx); append(c.ce, o.ce); append(c.c16, o.c16); append(c.blk, o.blk); append(c.lperm, o.lperm); } });
-    groups.push_back([&]() { for (RecOut& o : recs) { append(c.bab, o.bab); append(c.bfq, o.bfq); append(c.ccode, o.ccode); append(c.cw, o.cw); append(c.text, o.text); } });
-    groups.push_back([&]() { for (RecOut& o : recs) { append(c.prof, o.prof); append(c.cost_pd, o.pd); append(c.cost_pb, o.pb); } });
-    if (n_threads <= 1) {
-      for (auto& g : groups) g();
-    } else {
-      std::vector<std::thread> th;
-      for (auto& g : groups) th.emplace_back(g);
-      for (auto& x : th) x.join();
-    }
-  }
-  // packed row records (absolute child ranges, so built after the merge); records are independent
-  c.xnode.resize(c.a.size());
-  {
-    auto pack = [&](uint32_t r_lo, uint32_t r_hi) {
-      for (uint32_t r = r_lo; r < r_hi; ++r) {
-        const RecDev& h = c.rec[r];
-        for (uint32_t k = 0; k < h.N; ++k) {
-          const uint32_t gk = h.node0 + k;
-          XNode& xn = c.xnode[gk];
-          xn.s2 = c.s2[gk]; xn.a = c.a[gk]; xn.up = c.up[gk]; xn.ql = c.ql[gk]; xn.bfreq = c.bfreq[gk]; xn.paths = c.paths[gk];
-          xn.e0 = c.coff[h.coff0 + k]; xn.e1 = c.coff[h.coff0 + k + 1]; xn.len = c.len[gk]; xn.bcode = c.bcode[gk];
+        copy(A_A, h.node0, o.a); copy(A_EL, h.node0, o.el); copy(A_QL, h.node0, o.ql); copy(A_PATHS, h.node0, o.paths);
+        copy(A_GAPT, h.node0, o.gapt); copy(A_BFREQ, h.node0, o.bfreq); copy(A_LEN, h.node0, o.len); copy(A_BCODE, h.node0, o.bcode);
+        copy(A_COFF, h.coff0, o.coff); copy(A_CIDX, e0s[r], o.cidx); copy(A_CE, e0s[r], o.ce); copy(A_LEV, h.lev0, o.lev_off);
+        copy(A_BOFF, h.boff0, o.boff); copy(A_BAB, b0s[r], o.bab); copy(A_BFQ, b0s[r], o.bfq); copy(A_CCODE, h.col0, o.ccode);
+        copy(A_CW, h.col0, o.cw); copy(A_PROF, (size_t)4 * h.col0, o.prof); copy(A_TEXT, h.col0, o.text);
+        copy(A_UP, h.node0, o.up); copy(A_DN, h.node0, o.dn); copy(A_S2, h.node0, o.s2); copy(A_NODEI, h.node0, o.nodei);
+        copy(A_C16, h.c16_0, o.c16); copy(A_BLK, h.blk0, o.blk); copy(A_LPERM, h.node0, o.lperm);
+        if (blob) {   // packed row records (absolute child ranges)
+          XNode* xn = reinterpret_cast<XNode*>(blob + L[A_XNODE]) + h.node0;
+          for (uint32_t k = 0; k < h.N; ++k) {
+            xn[k].s2 = o.s2[k]; xn[k].a = o.a[k]; xn[k].up = o.up[k]; xn[k].ql = o.ql[k]; xn[k].bfreq = o.bfreq[k]; xn[k].paths = o.paths[k];
+            xn[k].e0 = o.coff[k]; xn[k].e1 = o.coff[k + 1]; xn[k].len = o.len[k]; xn[k].bcode = o.bcode[k];
+          }
         }
+        std::copy(o.len.begin(), o.len.end(), c.len.begin() + h.node0);
+        std::copy(o.deg_all.begin(), o.deg_all.end(), c.deg_all.begin() + h.node0);
+        std::copy(o.boff.begin(), o.boff.end(), c.boff.begin() + h.boff0);
+        std::copy(o.text.begin(), o.text.end(), c.text.begin() + h.col0);
+        std::copy(o.pd.begin(), o.pd.end(), c.cost_pd.begin() + (long)c.cost_off[r]);
+        std::copy(o.pb.begin(), o.pb.end(), c.cost_pb.begin() + (long)c.cost_off[r]);
+        RecOut().swap_arrays(o);   // the record's share is in place: give its memory back early
       }
     };
+    if (blob) std::memcpy(blob + L[A_REC], c.rec.data(), n * sizeof(RecDev));
     if (n_threads <= 1) {
-      pack(0, n);
+      fill(0, n);
     } else {
       std::vector<std::thread> th;
       for (int t = 0; t < n_threads; ++t)
-        th.emplace_back(pack, (uint32_t)((uint64_t)n * t / n_threads), (uint32_t)((uint64_t)n * (t + 1) / n_threads));
+        th.emplace_back(fill, (uint32_t)((uint64_t)n * t / n_threads), (uint32_t)((uint64_t)n * (t + 1) / n_threads));
       for (auto& x : th) x.join();
     }
   }

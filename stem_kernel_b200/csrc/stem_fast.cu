@@ -2,39 +2,39 @@
 //
 // Same restated recurrence as stem_kernel.cu (StemKernel<ST,D>::operator(), stem_kernel_lite/stem_kernel.cpp:14-95;
 // node / edge scores score_table.cpp:56-101,162-201), for records whose skip-edge factors are separable
-// (REC_FAST, compile_set.cpp):  e(p,c) = g^(len_p-len_c-2) = s2(p) * up(c).  Rows are therefore kept PRE-SCALED,
-//     H (i,j) = up_y(j) * G1(i,j)          HQ(i,j) = up_y(j) * Q(i,j)          G0s(i,j) = up_x(i) * G0(i,j)
-// and every gather of the recurrence becomes a plain sum over child offsets:
-//     Q (i,j) = s2_x(i) * sum_cx G0s(cx,j)
-//     R (i,j) = s2_y(j) * sum_cy HQ(i,cy) + el_y(j)*ql_x(i)         S(i,j) = s2_y(j) * sum_cy H(i,cy)
-//     M = in_band ? v_s*R : 0      G1 = M + a_y(j)*S      G0 = G1 + a_x(i)*Q
+// (REC_FAST, compile_set.cpp):  e(p,c) = g^(len_p-len_c-2) = s2(p) * up(c).  Everything is kept PRE-SCALED,
+//     H (i,j) = up_y(j) * G1(i,j)        HQ(i,j) = up_y(j) * Q(i,j)        G0ss(i,j) = up_x(i) * up_y(j) * G0(i,j)
+// so that every gather of the recurrence is a plain sum over child offsets and no phase multiplies per column:
+//     HQ(i,j) = s2_x(i) * sum_cx G0ss(cx,j)
+//     R (i,j) = s2_y(j) * sum_cy HQ(i,cy)/up_y(j) ...   in the scaled form:  up_y*M = v_s*bfreq_y*up_y*(s2_y*sum_cy HQ(i,cy) + el_y*ql_x)
+//     H (i,j) = up_y*M(i,j) + up_y*a_y*s2_y * sum_cy H(i,cy)             (M only inside the length band)
+//     G0ss(i,j) = up_x(i) * (H(i,j) + a_x(i)*HQ(i,j))
 //     k(x,y) = sum_i paths_x(i) * sum_j paths_y(j) * M(i,j)  (+ plr_x * lr_y)
 // Child lists are padded to multiples of four (index N is an all-zero dummy column).
 //
-// The rows of a BLOCK of kFastRows x nodes of one DAG level are computed together by one warp.  MATCH
-// (stem_kernel.cpp:46-59) only exists inside the length band, ~13 % of the cells, and R only depends on the finished
-// rows of i's inner pairs -- not on the row's own sweep -- so it is taken out of the sweep and done with full lanes:
-//   A   per row, lanes <-> column pairs: q = sum of the finished pre-scaled G0 rows of i's inner pairs (coalesced
-//       16-byte reads of the per-pair slab, eight in flight per lane);  HQ(i,:) = up_y*s2_x*q goes to the row
-//       buffer, the a_x*Q part of G0s(i,:) straight to the slab
+// A warp computes a BLOCK of kFastRows = 2 rows of one x sub-level.  MATCH (stem_kernel.cpp:46-59) only exists inside
+// the length band, ~13 % of the cells, and R only depends on the finished rows of i's inner pairs -- not on the row's
+// own sweep -- so it is taken out of the sweep and done with full lanes:
+//   A   per row, lanes <-> column pairs: q = sum of the finished G0ss rows of i's inner pairs.  The rows of a pair live
+//       in a per-pair slab in global memory (L2); one TMA bulk prefetch per inner pair asks the L2 for the whole row,
+//       then coalesced 16-byte reads, the row accumulated in REGISTERS (template on the row width: 7-12 independent
+//       loads in flight per lane);  HQ(i,:) = s2_x*q goes to the row buffer, up_x*a_x*HQ straight to the slab
 //   B1  per row, lanes <-> the y nodes INSIDE THE BAND of i (a contiguous range of the record's length-sorted node
-//       list, found by two warp-wide searches): R gathered from the row buffer, up_y*M(i,j) kept in a small
-//       per-warp buffer, the path-weighted MATCH sum of the row accumulated here
-//   Z   the row buffer is cleared and the band's up_y*M values are scattered into it: it is now the H row
-//   B2  y level by y level, lanes <-> (row of the block) x (node of the level):
-//       H(i,j) += up_y*a_y*s2_y * sum_cy H(i,cy) for the nodes at or above the band (G1 is identically 0 below it:
-//       length-monotone DAG); nodes of a level are sorted by length, so a level stops at the first node below the
-//       window.  The rows of a block share every instruction of the sweep; only __syncwarp between levels
-//   C   per row, lanes <-> column pairs: slab(i,j) += up_x*dn_y*H(i,j) where H is non-zero, fence, raise the flags
-// Per row a warp holds ONE buffer row (HQ, then H) plus the band buffer, against two full rows in the first version
-// of this kernel: more rows in flight per SM.
+//       list, found by two warp-wide searches): R gathered from the row buffer, up_y*M(i,j) kept in registers, the
+//       path-weighted MATCH sum of the row accumulated here
+//   Z   the row buffer is cleared and the band's up_y*M values are dropped into it: it is now the H row
+//   B2  y sub-level by sub-level (at most 16 nodes, sorted by length), lanes <-> (row of the block) x (node):
+//       H(i,j) += coef_j * sum_cy H(i,cy) for the nodes at or above the band (G1 is identically 0 below it:
+//       length-monotone DAG).  Only the sub-levels that hold such a node are visited (one ballot per 32 sub-levels)
+//   C   per row, lanes <-> column pairs: slab(i,j) += up_x*H(i,j) where H is non-zero, fence, raise the flags
 //
-// What bounds it (ncu, profiles/r02_*): the LSU data pipe -- shared-memory wavefronts of the gathers plus the
-// global wavefronts of phase A -- at ~75 % of its peak; time follows the wavefront count of a variant, not its
-// instruction count.  Hence: child lists are 16-bit byte offsets (one 8-byte index load per four children) whose
-// order is chosen at upload so that the nodes a warp sweeps together hit different banks (compile_set.cpp), rows are
-// polled with one uniform vote instead of per-lane spinning, and the row buffers are contiguous (an interleaved
-// [column][row] buffer halves the instructions of the sweep but costs more wavefronts in phases A, Z and C).
+// What bounds it (ncu, profiles/r02_*): the LSU data pipe -- shared-memory wavefronts of the gathers (two thirds of
+// them in B2) plus the global wavefronts of phases A and C -- at 66-70 % of its peak; time follows the wavefront count
+// of a variant, not its instruction count, its warps (16 to 24 give the same throughput) or the latency of a phase.
+// Hence: child lists are 16-bit byte offsets (one 8-byte index load per four children) whose order is chosen at upload
+// so that the nodes a warp sweeps together hit different banks (compile_set.cpp), rows are polled with one uniform
+// vote, the prefetch goes through the TMA unit (a prefetch.global.L2 per line cost an eighth of all wavefronts), no
+// phase loads a per-column scale factor, and the band's values never take a round trip through shared memory.
 //
 // Mapping.  One persistent CTA per SM; launches are bucketed by the size of the staged record so that shared memory
 // is sized for the bucket, not for the largest record of the set.  A CTA takes a GROUP of up to kGroup consecutive
@@ -44,7 +44,8 @@
 // ticket counter, wait on per-row flags until the rows of the block's inner pairs are published, and run the block
 // alone.  The path-weighted MATCH sum of a row goes to a per-row slot and the slots are added in a fixed order at the
 // end of the pair, so a pair's value does not depend on which warp happened to run which row: results are
-// bit-reproducible run to run.
+// bit-reproducible run to run and independent of the pair's position in a list (which is what makes the multi-device
+// matrices of stemk_gram_multi bit-identical to the single-device ones).
 #include "kernels.cuh"
 
 namespace stemk {

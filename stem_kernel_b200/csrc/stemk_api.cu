@@ -43,8 +43,6 @@ struct DevBuf {
 
 }  // namespace
 
-constexpr int kBlobArrays = 28;
-
 struct stemk_set {
   // host-side record headers and statistics (work model, scheduler, launch shapes); shared between the copies of a
   // set on several devices (stemk_set_clone), immutable after the upload
@@ -74,6 +72,10 @@ struct stemk_ctx {
   DevBuf perm, offs, diag, selfv, diag_idx, diag_vals, diag_idx2, diag_vals2;
   DevBuf deal_x, deal_y, gathered, undealt;     // stemk_gram_multi: this device's share of the pair list; on device 0 the gather
   cudaEvent_t multi_ev = nullptr;
+  void* upload_stage = nullptr;                 // pinned host image of the set being uploaded (kept for the next upload)
+  size_t upload_stage_bytes = 0;
+  cudaStream_t last_stream = nullptr;           // stream of the previous device-side call (scratch, queues and slabs are per context)
+  cudaEvent_t order_ev = nullptr;
   void* stage[2] = {nullptr, nullptr};          // pinned host staging (copy_out / copy_in)
   cudaEvent_t stage_ev[2] = {nullptr, nullptr};
   unsigned long long* d_bucket = nullptr;  // count[16] | start[16] | queue heads[16]
@@ -112,6 +114,23 @@ void timed_end(stemk_ctx* c, stemk_ctx::Timed t, cudaStream_t st) {
   cudaEventRecord(t.b, st);
   c->pending.push_back(t);
   if (c->pending.size() >= 256) timed_resolve(c);
+}
+
+// The context's scratch buffers, work queues and DP slabs belong to ONE call at a time.  When a device-side call
+// arrives on another stream than the previous one, the new stream first waits (on the device) for everything the
+// previous stream was given, so two calls never share those buffers in flight.
+cudaError_t order_after_previous(stemk_ctx* c, cudaStream_t st) {
+  if (c->last_stream && c->last_stream != st) {
+    if (!c->order_ev) { cudaError_t e = cudaEventCreateWithFlags(&c->order_ev, cudaEventDisableTiming); if (e != cudaSuccess) return e; }
+    if (cudaEventRecord(c->order_ev, c->last_stream) == cudaSuccess) {
+      const cudaError_t e = cudaStreamWaitEvent(st, c->order_ev, 0);
+      if (e != cudaSuccess) return e;
+    } else {
+      cudaGetLastError();                       // the caller destroyed that stream: its work was synchronised by then
+    }
+  }
+  c->last_stream = st;
+  return cudaSuccess;
 }
 
 int fail(stemk_ctx* c, int code, const std::string& msg) {
@@ -230,6 +249,8 @@ void stemk_destroy(stemk_ctx* c) {
                     &c->perm, &c->offs, &c->diag, &c->selfv, &c->diag_idx, &c->diag_vals, &c->diag_idx2, &c->diag_vals2,
                     &c->deal_x, &c->deal_y, &c->gathered, &c->undealt}) b->release();
   if (c->multi_ev) cudaEventDestroy(c->multi_ev);
+  if (c->order_ev) cudaEventDestroy(c->order_ev);
+  if (c->upload_stage) cudaFreeHost(c->upload_stage);
   for (int k = 0; k < 2; ++k) { if (c->stage[k]) cudaFreeHost(c->stage[k]); if (c->stage_ev[k]) cudaEventDestroy(c->stage_ev[k]); }
   if (c->d_pair_tab) cudaFree(c->d_pair_tab);
   if (c->d_subst) cudaFree(c->d_subst);
@@ -263,60 +284,52 @@ void make_view(stemk_set* s) {
   v.xnode = (const XNode*)(b + o[26]); v.lperm = (const uint32_t*)(b + o[27]);
 }
 
-// After the upload the host keeps the record headers and what the work model (stemk_pair_cost), the scheduler and the
-// launch shapes read; the per-node / per-edge arrays that only existed to be copied to the device are released
-// (about 100 KB per 150-300 nt record).
-void drop_upload_arrays(CompiledSet* h) {
-  auto drop = [](auto& v) { std::remove_reference_t<decltype(v)>().swap(v); };
-  drop(h->a); drop(h->el); drop(h->ql); drop(h->paths); drop(h->gapt); drop(h->bfreq); drop(h->ce); drop(h->bfq); drop(h->cw);
-  drop(h->coff); drop(h->cidx); drop(h->lev_off); drop(h->bcode); drop(h->bab); drop(h->ccode); drop(h->prof);
-  drop(h->up); drop(h->dn); drop(h->s2); drop(h->nodei); drop(h->xnode); drop(h->lperm); drop(h->c16); drop(h->blk);
-}
-
 }  // namespace
 
 int stemk_upload(stemk_ctx* ctx, const stemk_seqset_desc* desc, stemk_set** out) {
   if (!ctx || !desc || !out) return fail(ctx, STEMK_ERR_ARG, "null argument");
   *out = nullptr;
-  if (ctx->device != STEMK_DEVICE_NONE) CU(cudaSetDevice(ctx->device));
+  const bool on_device = ctx->device != STEMK_DEVICE_NONE;
+  if (on_device) CU(cudaSetDevice(ctx->device));
   stemk_set* s = new stemk_set;
   s->device = ctx->device;
   s->loop_gap = ctx->params.loop_gap;
   s->len_band = ctx->params.len_band;
   const int n_threads = (int)std::min<unsigned>(16, std::max(1u, std::thread::hardware_concurrency()));
+  // The records are compiled in parallel and written straight into ONE pinned host image of the device blob (kept
+  // by the context for the next upload), which then goes to the device with a single copy.
+  cudaError_t stage_err = cudaSuccess;
+  std::function<char*(size_t)> sink;
+  if (on_device) sink = [&](size_t bytes) -> char* {
+    if (bytes > ctx->upload_stage_bytes) {
+      if (ctx->upload_stage) cudaFreeHost(ctx->upload_stage);
+      ctx->upload_stage = nullptr; ctx->upload_stage_bytes = 0;
+      stage_err = cudaHostAlloc(&ctx->upload_stage, bytes + bytes / 8, cudaHostAllocDefault);
+      if (stage_err != cudaSuccess) { cudaGetLastError(); ctx->upload_stage = nullptr; return nullptr; }
+      ctx->upload_stage_bytes = bytes + bytes / 8;
+    }
+    return static_cast<char*>(ctx->upload_stage);
+  };
   std::string err;
-  try { err = compile_set(*desc, ctx->params.loop_gap, ctx->params.len_band, n_threads, ctx->timing != 0, &s->host); }
+  const auto t0 = std::chrono::steady_clock::now();
+  try { err = compile_set(*desc, ctx->params.loop_gap, ctx->params.len_band, n_threads, ctx->timing != 0, &s->host, sink); }
   catch (const std::bad_alloc&) { delete s; return fail(ctx, STEMK_ERR_NOMEM, "out of host memory while compiling the record set"); }
   catch (const std::exception& ex) { delete s; return fail(ctx, STEMK_ERR_ARG, std::string("record set: ") + ex.what()); }
+  if (stage_err != cudaSuccess) { delete s; return cuda_fail(ctx, stage_err, "pinned staging for the set upload"); }
   if (!err.empty()) { delete s; return fail(ctx, STEMK_ERR_ARG, err); }
+  if (!on_device) { *out = s; return STEMK_OK; }
   const CompiledSet& h = s->host;
-  if (ctx->device == STEMK_DEVICE_NONE) { *out = s; return STEMK_OK; }
-  size_t off = 0;
-  size_t* o = s->lay;
-  o[0] = place(off, h.rec); o[1] = place(off, h.a); o[2] = place(off, h.el); o[3] = place(off, h.ql);
-  o[4] = place(off, h.paths); o[5] = place(off, h.gapt); o[6] = place(off, h.bfreq); o[7] = place(off, h.len);
-  o[8] = place(off, h.bcode); o[9] = place(off, h.coff); o[10] = place(off, h.cidx); o[11] = place(off, h.ce);
-  o[12] = place(off, h.lev_off); o[13] = place(off, h.boff); o[14] = place(off, h.bab); o[15] = place(off, h.bfq);
-  o[16] = place(off, h.ccode); o[17] = place(off, h.cw); o[18] = place(off, h.prof); o[19] = place(off, h.text);
-  o[20] = place(off, h.up); o[21] = place(off, h.dn); o[22] = place(off, h.s2); o[23] = place(off, h.nodei);
-  o[24] = place(off, h.c16); o[25] = place(off, h.blk); o[26] = place(off, h.xnode); o[27] = place(off, h.lperm);
-  off = (off + 255) & ~size_t(255);
-  cudaError_t e = s->blob.reserve(std::max<size_t>(off, 256));
-  // every array goes straight from its host vector to its place in the blob (no staging copy)
-  auto put = [&](size_t at, const auto& v) {
-    if (e == cudaSuccess && !v.empty())
-      e = cudaMemcpyAsync(static_cast<char*>(s->blob.p) + at, v.data(), v.size() * sizeof(v[0]), cudaMemcpyHostToDevice, ctx->stream);
-  };
-  put(o[0], h.rec); put(o[1], h.a); put(o[2], h.el); put(o[3], h.ql); put(o[4], h.paths); put(o[5], h.gapt);
-  put(o[6], h.bfreq); put(o[7], h.len); put(o[8], h.bcode); put(o[9], h.coff); put(o[10], h.cidx);
-  put(o[11], h.ce); put(o[12], h.lev_off); put(o[13], h.boff); put(o[14], h.bab); put(o[15], h.bfq);
-  put(o[16], h.ccode); put(o[17], h.cw); put(o[18], h.prof); put(o[19], h.text);
-  put(o[20], h.up); put(o[21], h.dn); put(o[22], h.s2); put(o[23], h.nodei); put(o[24], h.c16); put(o[25], h.blk);
-  put(o[26], h.xnode); put(o[27], h.lperm);
+  for (int k = 0; k < kBlobArrays; ++k) s->lay[k] = h.blob_lay[k];
+  const auto t1 = std::chrono::steady_clock::now();
+  cudaError_t e = s->blob.reserve(std::max<size_t>(h.blob_bytes, 256));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(s->blob.p, ctx->upload_stage, h.blob_bytes, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) { s->blob.release(); delete s; return cuda_fail(ctx, e, "set upload"); }
+  if (ctx->timing)
+    std::fprintf(stderr, "stemk_upload: compile %.1f ms, device allocation + one copy of %.1f MB %.1f ms\n",
+                 std::chrono::duration<double, std::milli>(t1 - t0).count(), h.blob_bytes / 1e6,
+                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
   make_view(s);
-  drop_upload_arrays(&s->host);
   *out = s;
   return STEMK_OK;
 }
@@ -489,6 +502,7 @@ int stemk_pairs_device(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, s
   if (!set_usable(ctx, x) || !set_usable(ctx, y)) return fail(ctx, STEMK_ERR_ARG, kSetMismatch);
   CU(cudaSetDevice(ctx->device));
   cudaStream_t st = stream_ ? (cudaStream_t)stream_ : ctx->stream;
+  CU(order_after_previous(ctx, st));
   const int kind = ctx->params.kind;
   const bool has_stem = kind_has_stem(kind), has_str = kind_has_string(kind);
   const bool combine = (has_stem && has_str) || kind == STEMK_LSU_STEM || kind == STEMK_LSU_STR;
@@ -530,7 +544,14 @@ int stemk_pairs_device(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, s
       const uint32_t ny_cap = std::max(1u, y->host.max_N);
       uint32_t nslots; size_t smem;
       stem_config(ctx, x->host, y->host, &nslots, &smem);
-      if (!nslots) return fail(ctx, STEMK_ERR_NOMEM, "a record has too many DAG nodes to stage in shared memory");
+      if (!nslots) {
+        uint32_t worst = 0;
+        for (uint32_t r = 0; r < y->host.rec.size(); ++r) if (y->host.rec[r].N > y->host.rec[worst].N) worst = r;
+        return fail(ctx, STEMK_ERR_NOMEM, "general stem kernel: record " + std::to_string(worst) + " of the second set has " +
+                    std::to_string(y->host.rec[worst].N) + " non-leaf DAG nodes and " + std::to_string(y->host.max_E) +
+                    " inner edges, more than one CTA can stage in shared memory (56 B per node + 16 B per edge + two row buffers "
+                    "in 227 KB: about 1000 nodes); see the limits section of include/stemk.h");
+      }
       int per_sm = stem_max_ctas_per_sm(smem);
       if (per_sm < 1) return fail(ctx, STEMK_ERR_CUDA, "stem kernel does not fit on an SM");
       per_sm = std::min(per_sm, 4);
@@ -863,6 +884,7 @@ int stemk_assemble_device(stemk_ctx* ctx, size_t n_pairs, const uint32_t* d_xi, 
   if (!d_matrix || (n_pairs && (!d_xi || !d_yi || !d_vals))) return fail(ctx, STEMK_ERR_ARG, "null buffer");
   CU(cudaSetDevice(ctx->device));
   cudaStream_t st = stream_ ? (cudaStream_t)stream_ : ctx->stream;
+  CU(order_after_previous(ctx, st));
   CU(launch_scatter_square(d_vals, d_xi, d_yi, n_pairs, d_matrix, n, st));
   ctx->launches += 1;
   if (normalize) { CU(launch_normalize_square(d_matrix, n, st)); ctx->launches += 2; }

@@ -2,6 +2,7 @@
 // compiler (compile_set.cpp), the CUDA kernels and the C ABI (stemk_api.cu).
 #pragma once
 #include <cstdint>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -98,19 +99,17 @@ struct SetView {
   const uint8_t* text;   // raw characters
 };
 
-// Host-side result of compiling a descriptor: one byte blob + the view's offsets.
+constexpr int kBlobArrays = 28;   // arrays of a SetView
+
+// Host-side result of compiling a descriptor: the record headers and what the work model, the scheduler and the
+// launch shapes read.  The per-node / per-edge arrays themselves only exist in the device image, which compile_set
+// writes straight into the buffer its sink hands out (blob_lay = where each array of the SetView sits in it).
 struct CompiledSet {
   std::vector<RecDev> rec;
-  std::vector<double> a, el, ql, paths, gapt, bfreq, ce, bfq, cw;
-  std::vector<uint32_t> len, coff, cidx, lev_off, boff;
-  std::vector<uint8_t> bcode, bab, ccode, text;
-  std::vector<float> prof;
-  std::vector<double> up, dn, s2;
-  std::vector<NodeI> nodei;
-  std::vector<XNode> xnode;
-  std::vector<uint32_t> lperm;
-  std::vector<uint16_t> c16;
-  std::vector<uint32_t> blk;
+  std::vector<uint32_t> len, boff;   // per non-leaf node: last - first; base-pair-profile offsets (absolute)
+  std::vector<uint8_t> text;         // raw characters per column
+  size_t blob_lay[kBlobArrays] = {};
+  size_t blob_bytes = 0;
   uint32_t max_E4 = 0, max_fastN = 0, n_fast = 0;  // over fast-eligible records
   uint32_t max_band_cnt = 1;                       // most nodes of one record inside any length window of 2*len_band+1 (all of them without a band)
   uint32_t n_weighted = 0, n_simple_cols = 0;      // records with per-column weights / with one-hot-or-gap columns only
@@ -130,7 +129,9 @@ struct CompiledSet {
 
 // Builds the compiled form of every record of `desc` under loop gap `g` and length band `len_band` (0 = none).
 // Returns "" or an error.
-std::string compile_set(const stemk_seqset_desc& desc, double g, uint32_t len_band, int n_threads, bool timing, CompiledSet* out);
+// `sink(bytes)` returns the buffer the device image is written into (NULL sink: host arrays only).
+std::string compile_set(const stemk_seqset_desc& desc, double g, uint32_t len_band, int n_threads, bool timing, CompiledSet* out,
+                        const std::function<char*(size_t)>& sink);
 
 // Kernel constants derived from stemk_params on the host with libm (same exp() the reference calls).
 struct KernelTables {
