@@ -121,7 +121,6 @@ const char* stemk_last_error(const stemk_ctx* ctx); /* ctx may be NULL: last cre
  *   STEMK_OPT_TIMING         1: stemk_upload / stemk_gram print a host-side time breakdown on stderr */
 #define STEMK_OPT_FORCE_GENERAL 1
 #define STEMK_OPT_TIMING 2
-#define STEMK_OPT_TILE_SWEEP 3   /* 0: the fast stem kernel sweeps the two rows of a warp's own block (stem_fast.cu) everywhere; 1 (default): 16-row tiles (stem_tile.cu) where they fit -- same values to rounding, lets tests compare the two */
 int stemk_set_option(stemk_ctx* ctx, int option, int value);
 
 /* Threading: a context is single-threaded and has ONE call in flight -- its scratch buffers, work queues and DP

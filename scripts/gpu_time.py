@@ -6,7 +6,6 @@ from stem_kernel_b200 import synth, hostlib, api, _lib as L
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 600
 md = hostlib.build_many(synth.make_config(3, n))
 ctx = api.Context(L.make_params(L.SU_STEM)); ds = ctx.upload(md)
-if os.environ.get('STEMK_TILE'): ctx.set_option(L.OPT_TILE_SWEEP, int(os.environ['STEMK_TILE']))
 ctx.gram(ds)
 ctx.stats_reset(); G = ctx.gram(ds); st = ctx.stats()
 npairs = n * (n + 1) // 2

@@ -99,10 +99,6 @@ size_t stem_fast_smem_bytes(uint32_t nwarps, uint32_t nx_cap, uint32_t ny_cap, u
 int stem_fast_ctas_per_sm(uint32_t ny_cap, int nwarps, size_t smem);
 int stem_fast_max_warps(uint32_t ny_cap);   // launch bound of the variant that serves staged records of up to ny_cap nodes
 cudaError_t launch_stem_fast(const StemFastLaunch& p, int grid, int nwarps, size_t smem, cudaStream_t stream);
-// stem_tile.cu: the same kernel with the column sweep on 16-row tiles (staged records of up to 384 nodes, bands of up to 128)
-bool stem_tile_serves(uint32_t ny_cap, uint32_t band_cap);
-size_t stem_tile_smem_bytes(uint32_t nwarps, uint32_t nx_cap, uint32_t ny_cap, uint32_t e4_cap, uint32_t lev_cap);
-cudaError_t launch_stem_tile(const StemFastLaunch& p, int grid, int nwarps, size_t smem, cudaStream_t stream);
 cudaError_t launch_classify(const StemClassify& c, int n_buckets, unsigned long long* counters, cudaStream_t stream);
 void string_shape_for(uint32_t ly_cap, int mode, int* cw, int* tp);
 // mode: 0 plain one-hot columns, 1 weighted, 2 naive characters, 3 general (see string_kernel.cu)

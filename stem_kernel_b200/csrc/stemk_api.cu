@@ -16,7 +16,6 @@
 #include <string>
 #include <thread>
 #include <vector>
-#include <unistd.h>
 
 #include <memory>
 
@@ -24,9 +23,6 @@
 
 using namespace stemk;
 
-#ifndef STEMK_TILE_DEFAULT
-#define STEMK_TILE_DEFAULT 1
-#endif
 
 namespace {
 
@@ -85,7 +81,6 @@ struct stemk_ctx {
   cudaEvent_t stage_ev[2] = {nullptr, nullptr};
   unsigned long long* d_bucket = nullptr;  // count[16] | start[16] | queue heads[16]
   int use_fast = 1;                        // stemk_set_option(STEMK_OPT_FORCE_GENERAL, 1) routes every pair to the general stem kernel
-  int use_tile = STEMK_TILE_DEFAULT;       // stemk_set_option(STEMK_OPT_TILE_SWEEP, 0/1): the tile variant of the fast stem kernel
   int timing = 0;                          // stemk_set_option(STEMK_OPT_TIMING, 1): host-side breakdown of the calls on stderr
   std::string err;
   // stats
@@ -242,7 +237,6 @@ int stemk_set_option(stemk_ctx* ctx, int option, int value) {
   switch (option) {
     case STEMK_OPT_FORCE_GENERAL: ctx->use_fast = value ? 0 : 1; return STEMK_OK;
     case STEMK_OPT_TIMING: ctx->timing = value; return STEMK_OK;
-    case STEMK_OPT_TILE_SWEEP: ctx->use_tile = value ? 1 : 0; return STEMK_OK;
     default: return fail(ctx, STEMK_ERR_ARG, "unknown option");
   }
 }
@@ -589,22 +583,14 @@ int stemk_pairs_device(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, s
         e4_cap = std::max(e4_cap, ry.e4); band_cap = std::max(band_cap, y->host.band_cnt[r]); any = true;
       }
       if (!any) continue;
-      const size_t budget = std::min<size_t>(ctx->smem_optin, (size_t)227 * 1024) - 2048;   // static shared memory
+      const size_t budget = std::min<size_t>(ctx->smem_optin, (size_t)227 * 1024) - 256;   // static shared memory
       // one CTA per SM with as many warps as the bucket's rows leave room for
       int best_w = 0; size_t best_smem = 0;
-      // the tile variant (column sweep on 16-row tiles) where its tiles fit next to at least 16 row workers
-      bool tile = ctx->use_tile && stem_tile_serves(ny_cap, band_cap);
-      if (tile) {
-        for (int t = stem_fast_max_warps(ny_cap); t >= 16; --t) if (stem_tile_smem_bytes(t, nx_cap, ny_cap, e4_cap, lev_cap) <= budget) { best_w = t; break; }
-        if (best_w) best_smem = stem_tile_smem_bytes(best_w, nx_cap, ny_cap, e4_cap, lev_cap); else tile = false;
-      }
-      if (!tile) {
-        for (int t = stem_fast_max_warps(ny_cap); t >= 2; --t) if (stem_fast_smem_bytes(t, nx_cap, ny_cap, e4_cap, lev_cap, band_cap) <= budget) { best_w = t; break; }
-        if (!best_w) return fail(ctx, STEMK_ERR_NOMEM, "fast stem kernel: record does not fit in shared memory");
-        best_smem = stem_fast_smem_bytes(best_w, nx_cap, ny_cap, e4_cap, lev_cap, band_cap);
-        const int per_sm = stem_fast_ctas_per_sm(ny_cap, best_w, best_smem);
-        if (per_sm < 1) return fail(ctx, STEMK_ERR_CUDA, "fast stem kernel does not fit on an SM");
-      }
+      for (int t = stem_fast_max_warps(ny_cap); t >= 2; --t) if (stem_fast_smem_bytes(t, nx_cap, ny_cap, e4_cap, lev_cap, band_cap) <= budget) { best_w = t; break; }
+      if (!best_w) return fail(ctx, STEMK_ERR_NOMEM, "fast stem kernel: record does not fit in shared memory");
+      best_smem = stem_fast_smem_bytes(best_w, nx_cap, ny_cap, e4_cap, lev_cap, band_cap);
+      const int per_sm = stem_fast_ctas_per_sm(ny_cap, best_w, best_smem);
+      if (per_sm < 1) return fail(ctx, STEMK_ERR_CUDA, "fast stem kernel does not fit on an SM");
       const int grid = (int)std::min<size_t>((n_pairs + kFastGroup - 1) / kFastGroup, (size_t)ctx->sm_count);
       const unsigned long long stride = (unsigned long long)kFastGroup * nx_cap * ((ny_cap + 1u) & ~1u);
       CU(ctx->scratch.reserve(sizeof(double) * stride * grid));
@@ -615,60 +601,17 @@ int stemk_pairs_device(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, s
       F.scratch = (double*)ctx->scratch.p; F.scratch_stride = stride; F.rowacc = (double*)ctx->rowacc.p; F.pair_tab = ctx->d_pair_tab;
       F.len_band = ctx->params.len_band; F.nx_cap = nx_cap; F.ny_cap = ny_cap; F.e4_cap = e4_cap; F.lev_cap = lev_cap;
       F.band_cap = band_cap; F.prof = nullptr;
-#ifdef TILE_DEBUG
-      unsigned long long* d_dbg = nullptr;
-      cudaMalloc((void**)&d_dbg, 256 * sizeof(unsigned long long));
-      cudaMemsetAsync(d_dbg, 0, 256 * sizeof(unsigned long long), st);
-      F.prof = d_dbg;
-#endif
 #ifdef FAST_PROF
       unsigned long long* d_prof = nullptr;
       cudaMalloc((void**)&d_prof, 16 * sizeof(unsigned long long));
       cudaMemsetAsync(d_prof, 0, 16 * sizeof(unsigned long long), st);
       F.prof = d_prof;
 #endif
-#ifdef TILE_DEBUG
-      std::fprintf(stderr, "launch cap %u tile %d warps %d smem %zu grid %d band_cap %u e4_cap %u lev_cap %u nx_cap %u\n", ny_cap, (int)tile, best_w, best_smem, grid, band_cap, e4_cap, lev_cap, nx_cap);
-#endif
       stemk_ctx::Timed tm = timed_begin(ctx, 0, st);
-      cudaError_t le = tile ? launch_stem_tile(F, grid, best_w, best_smem, st) : launch_stem_fast(F, grid, best_w, best_smem, st);
+      cudaError_t le = launch_stem_fast(F, grid, best_w, best_smem, st);
       timed_end(ctx, tm, st);
       CU(le);
       ctx->launches += 1;
-#ifdef TILE_DEBUG
-      {
-        unsigned long long h[32];
-        if (tile) {   // peek at CTA 0's per-warp progress markers while the kernel runs
-          cudaStream_t peek; cudaStreamCreateWithFlags(&peek, cudaStreamNonBlocking);
-          for (int round = 0; round < 2; ++round) {
-            std::this_thread::sleep_for(std::chrono::milliseconds(round ? 2000 : 500));
-            if (cudaStreamQuery(st) == cudaSuccess) break;
-            unsigned long long g[256];
-            cudaMemcpyAsync(g, d_dbg, sizeof(g), cudaMemcpyDeviceToHost, peek);
-            cudaStreamSynchronize(peek);
-            std::fprintf(stderr, "  still running after %s: CTA 0\n", round ? "2.5 s" : "0.5 s");
-            for (int w = 0; w < 20; ++w)
-              std::fprintf(stderr, "   warp %2d at %08llx rows_done %llu hint %llu cur_fill %llu lock %llu next_blk %llu | t0 st %llu gr %llu rd %llu dn %llu dd %llu | t1 st %llu gr %llu rd %llu dn %llu\n", w, g[32 + w],
-                           g[64 + w] & 0xffff, (g[64 + w] >> 16) & 0xffff, (g[64 + w] >> 32) & 0xff, (g[64 + w] >> 40) & 0xf, g[64 + w] >> 44,
-                           g[96 + w] & 15, (g[96 + w] >> 4) & 255, (g[96 + w] >> 12) & 255, (g[96 + w] >> 20) & 255, (g[96 + w] >> 28) & 255,
-                           (g[96 + w] >> 36) & 15, (g[96 + w] >> 40) & 255, (g[96 + w] >> 48) & 255, (g[96 + w] >> 56) & 255);
-            if (round) { std::fflush(stderr); _exit(3); }
-          }
-        }
-        const cudaError_t se = cudaStreamSynchronize(st);
-        std::fprintf(stderr, "  finished: %s\n", cudaGetErrorString(se));
-        cudaMemcpy(h, d_dbg, sizeof(h), cudaMemcpyDeviceToHost);
-        cudaFree(d_dbg);
-        if (h[0]) {
-          std::fprintf(stderr, "TILE WATCHDOG cap %u tile %d: %llu CTAs stuck; first: where %llu warp %llu a %llu b %llu rows_done %llu/%llu hint %llu cur_fill %llu lock %llu next_blk %llu cta %llu\n",
-                       ny_cap, (int)tile, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9], h[16], h[17]);
-          for (int t = 0; t < 2; ++t)
-            std::fprintf(stderr, "  tile %d: state %llu granted %llu ready %llu drain_next %llu drained %llu lo %llu\n", t, h[10 + 3 * t], h[11 + 3 * t] & 255, (h[11 + 3 * t] >> 8) & 255,
-                         (h[11 + 3 * t] >> 16) & 255, (h[11 + 3 * t] >> 24) & 255, h[12 + 3 * t]);
-          for (int q = 0; q < 12; ++q) std::fprintf(stderr, "  warp %2d at %08llx   warp %2d at %08llx\n", 2 * q, h[18 + q] & 0xffffffffull, 2 * q + 1, h[18 + q] >> 32);
-        }
-      }
-#endif
 #ifdef FAST_PROF
       {
         unsigned long long h[16];
