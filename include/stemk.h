@@ -286,6 +286,15 @@ int stemk_nstem_pairs(stemk_ctx* ctx, const stemk_nstem_params* params, const st
 int stemk_nstem_pairs_banded(stemk_ctx* ctx, const stemk_nstem_params* params, uint32_t band, const stemk_nstem_set* x,
                              const stemk_nstem_set* y, size_t n_pairs, const uint32_t* xi, const uint32_t* yi, double* out);
 
+/* The same partial_dp under caller-supplied alignment constraints -- what StemKernel::alignment_constraints
+ * (stem_kernel/stem_kernel.cpp:14-67) produces from the pair-HMM posteriors when ali_bound > 0, optionally narrowed by
+ * the band (:57-66): row i (0..lx) of x[xi[k]] may pair with columns c_low[win_off[k] + i] .. c_high[win_off[k] + i]
+ * of y[yi[k]].  win_off has n_pairs + 1 entries, every pair owns lx + 1 of each array, c_low <= c_high <= ly.  The
+ * pair HMM itself (phmm.cpp) stays CPU code in front of this call. */
+int stemk_nstem_pairs_windows(stemk_ctx* ctx, const stemk_nstem_params* params, const stemk_nstem_set* x, const stemk_nstem_set* y,
+                              size_t n_pairs, const uint32_t* xi, const uint32_t* yi, const uint32_t* win_off,
+                              const uint32_t* c_low, const uint32_t* c_high, double* out);
+
 /* Text of kernel-matrix rows in the reference's output format -- KernelMatrix::print (kernel_matrix.cpp:756-770)
  * and Output::kernel_output (framework.cpp:190-204): one line "<label> 0:<cnt> 1:<v> 2:<v> ... \n" per row, every
  * value printed like operator<<(std::ostream&, double) with default flags ("%g").  m: n_rows x n_cols with row

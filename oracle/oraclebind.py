@@ -40,6 +40,7 @@ def lib():
         L.oracle_bpla_gradients.argtypes = [vp, vp, vp, C.c_size_t, vp, vp, vp, vp]
         L.oracle_nstem_pairs.argtypes = [vp, vp, vp, C.c_size_t, vp, vp, vp]
         L.oracle_nstem_pairs_banded.argtypes = [vp, C.c_uint, vp, vp, C.c_size_t, vp, vp, vp]
+        L.oracle_nstem_pairs_windows.argtypes = [vp, vp, vp, C.c_size_t, vp, vp, vp, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -136,4 +137,17 @@ def nstem_pairs_banded(params, band, x, y, xi, yi):
     out = np.zeros(len(xi))
     cx, cy = x.c(), y.c()
     lib().oracle_nstem_pairs_banded(_p(params), int(band), _p(cx), _p(cy), len(xi), xi.ctypes.data, yi.ctypes.data, out.ctypes.data)
+    return out
+
+
+def nstem_pairs_windows(params, x, y, xi, yi, windows):
+    """Restated partial_dp under caller-supplied per-row windows; windows[k] = (c_low, c_high), lx + 1 entries each."""
+    from stem_kernel_b200.nstem import pack_windows
+    xi = np.ascontiguousarray(xi, dtype=np.uint32)
+    yi = np.ascontiguousarray(yi, dtype=np.uint32)
+    off, lo, hi = pack_windows(windows)
+    out = np.zeros(len(xi))
+    cx, cy = x.c(), y.c()
+    lib().oracle_nstem_pairs_windows(_p(params), _p(cx), _p(cy), len(xi), xi.ctypes.data, yi.ctypes.data, off.ctypes.data,
+                                     lo.ctypes.data, hi.ctypes.data, out.ctypes.data)
     return out

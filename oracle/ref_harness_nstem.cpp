@@ -22,6 +22,28 @@ struct TableBP {   // prob(i, j) of a registered sequence object: dense row-majo
 }  // namespace
 template class StemKernel<double, TableBP>;
 
+// alignment_constraints is private; an explicit instantiation may name it legally (same device as ref_harness.cpp's gap table)
+namespace {
+typedef void (StemKernel<double, NormalBasePair>::*ConstraintsFn)(const std::string&, const std::string&, std::vector<uint>&,
+                                                                   std::vector<uint>&) const;
+template <class Tag, typename Tag::type M>
+struct Expose { friend typename Tag::type expose(Tag) { return M; } };
+struct ConstraintsTag { typedef ConstraintsFn type; friend type expose(ConstraintsTag); };
+template struct Expose<ConstraintsTag, &StemKernel<double, NormalBasePair>::alignment_constraints>;
+}  // namespace
+
+// c_low / c_high (lx + 1 entries each) of StemKernel::alignment_constraints for one pair (stem_kernel.cpp:14-83): the
+// pair-HMM constraints when ali_bound > 0 (narrowed by the band, :57-66), the band alone otherwise
+extern "C" int refnstem_windows(unsigned band, float ali_bound, const char* x, unsigned lx, const char* y, unsigned ly,
+                                uint32_t* c_low, uint32_t* c_high) {
+  const std::string X(x, x + lx), Y(y, y + ly);
+  StemKernel<double, NormalBasePair> k(false, 3, 0.5, 1.0, 0.5, band, ali_bound, 1.0f);   // only band / ali_bound matter here
+  std::vector<uint> lo, hi;
+  (k.*expose(ConstraintsTag()))(X, Y, lo, hi);
+  for (unsigned i = 0; i <= lx; ++i) { c_low[i] = lo[i]; c_high[i] = hi[i]; }
+  return 0;
+}
+
 extern "C" int refnstem_pairs(int bp_mode, int use_gu, unsigned loop, double gap, double stack, double subst, unsigned band,
                               float ali_bound, float bp_bound,
                               int nx, const uint32_t* off_x, const char* text_x, const uint64_t* bp_off_x, const float* bp_x,

@@ -397,3 +397,15 @@ def nstem_pairs(params, x, y, xi, yi, band=0, ali_bound=0.0):
                            d(y.bp_off), d(y.bp), len(xi), xi.ctypes.data, yi.ctypes.data, out.ctypes.data)
     assert rc == 0
     return out
+
+
+def nstem_windows(x_seq, y_seq, band=0, ali_bound=0.0):
+    """(c_low, c_high), lx + 1 entries each: StemKernel::alignment_constraints of the reference (stem_kernel.cpp:14-83) --
+    the pair-HMM constraints when ali_bound > 0 (narrowed by the band), the band alone otherwise."""
+    Ln = _lib("libstemk_ref_nstem.so")
+    Ln.refnstem_windows.argtypes = [C.c_uint, C.c_float, C.c_char_p, C.c_uint, C.c_char_p, C.c_uint, C.c_void_p, C.c_void_p]
+    xs, ys = x_seq.lower().encode(), y_seq.lower().encode()
+    lo, hi = np.zeros(len(xs) + 1, dtype=np.uint32), np.zeros(len(xs) + 1, dtype=np.uint32)
+    rc = Ln.refnstem_windows(int(band), float(ali_bound), xs, len(xs), ys, len(ys), lo.ctypes.data, hi.ctypes.data)
+    assert rc == 0
+    return lo, hi

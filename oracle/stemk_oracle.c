@@ -662,7 +662,7 @@ static double nstem_pair(const stemk_nstem_params* p, const stemk_nstem_set* X, 
  * and the four neighbour terms fall back to the reference's "approximation" cells at the window border.  Statement
  * order kept; the #if 0 blocks of the reference are dead code and are not restated. */
 static double nstem_pair_banded(const stemk_nstem_params* p, unsigned band, const stemk_nstem_set* X, uint32_t xr,
-                                const stemk_nstem_set* Y, uint32_t yr) {
+                                const stemk_nstem_set* Y, uint32_t yr, const uint32_t* win_low, const uint32_t* win_high) {
   const char* x = X->text + X->off[xr];
   const char* y = Y->text + Y->off[yr];
   const size_t lx = X->off[xr + 1] - X->off[xr], ly = Y->off[yr + 1] - Y->off[yr];
@@ -677,6 +677,7 @@ static double nstem_pair_banded(const stemk_nstem_params* p, unsigned band, cons
   size_t* c_low = malloc(2 * (lx + 1) * sizeof(size_t));
   size_t* c_high = c_low + (lx + 1);
   for (size_t i = 0; i != lx + 1; ++i) {
+    if (win_low) { c_low[i] = win_low[i]; c_high[i] = win_high[i]; continue; }   /* the caller's constraints (:25-67) */
     const unsigned j = (unsigned)((double)i / lx * ly + 0.5);
     c_low[i] = j < band ? 0 : j - band;
     c_high[i] = j + band > ly ? ly : j + band;
@@ -776,7 +777,15 @@ static double nstem_pair_banded(const stemk_nstem_params* p, unsigned band, cons
 void oracle_nstem_pairs_banded(const stemk_nstem_params* p, unsigned band, const stemk_nstem_set* X, const stemk_nstem_set* Y,
                                size_t n_pairs, const uint32_t* xi, const uint32_t* yi, double* out) {
   for (size_t k = 0; k < n_pairs; ++k)
-    out[k] = band > 0 ? nstem_pair_banded(p, band, X, xi[k], Y, yi[k]) : nstem_pair(p, X, xi[k], Y, yi[k]);
+    out[k] = band > 0 ? nstem_pair_banded(p, band, X, xi[k], Y, yi[k], NULL, NULL) : nstem_pair(p, X, xi[k], Y, yi[k]);
+}
+
+/* partial_dp under caller-supplied per-row windows (the c_low / c_high of alignment_constraints, stem_kernel.cpp:14-67) */
+void oracle_nstem_pairs_windows(const stemk_nstem_params* p, const stemk_nstem_set* X, const stemk_nstem_set* Y, size_t n_pairs,
+                                const uint32_t* xi, const uint32_t* yi, const uint32_t* win_off, const uint32_t* c_low,
+                                const uint32_t* c_high, double* out) {
+  for (size_t k = 0; k < n_pairs; ++k)
+    out[k] = nstem_pair_banded(p, 1, X, xi[k], Y, yi[k], c_low + win_off[k], c_high + win_off[k]);
 }
 
 void oracle_nstem_pairs(const stemk_nstem_params* p, const stemk_nstem_set* X, const stemk_nstem_set* Y, size_t n_pairs,

@@ -29,6 +29,10 @@ void oracle_nstem_pairs(const stemk_nstem_params* p, const stemk_nstem_set* X, c
 /* band > 0: StemKernel::partial_dp with the band-only constraints (stem_kernel.cpp:14-83, 113-280); band == 0: full_dp */
 void oracle_nstem_pairs_banded(const stemk_nstem_params* p, unsigned band, const stemk_nstem_set* X, const stemk_nstem_set* Y,
                                size_t n_pairs, const uint32_t* xi, const uint32_t* yi, double* out);
+/* partial_dp under caller-supplied per-row windows: the c_low / c_high of alignment_constraints (stem_kernel.cpp:14-67) */
+void oracle_nstem_pairs_windows(const stemk_nstem_params* p, const stemk_nstem_set* X, const stemk_nstem_set* Y, size_t n_pairs,
+                                const uint32_t* xi, const uint32_t* yi, const uint32_t* win_off, const uint32_t* c_low,
+                                const uint32_t* c_high, double* out);
 #ifdef __cplusplus
 }
 #endif

@@ -34,7 +34,7 @@ def make_params(kind, loop_gap=0.2, beta=0.3, stack=1.3, covar=0.8, gap=0.8, alp
 
 EXPORTS = ["stemk_version", "stemk_device_count", "stemk_create", "stemk_set_option", "stemk_destroy", "stemk_last_error", "stemk_upload",
            "stemk_set_free", "stemk_set_size", "stemk_set_stats", "stemk_set_device_bytes", "stemk_gram", "stemk_cross", "stemk_diag", "stemk_pairs",
-           "stemk_pairs_device", "stemk_assemble_device", "stemk_pair_cost", "stemk_stats_reset", "stemk_stats_get", "stemk_fp64_peak", "stemk_format_rows", "stemk_format_values", "stemk_bpla_pairs", "stemk_bpla_gradients", "stemk_nstem_pairs", "stemk_nstem_pairs_banded",
+           "stemk_pairs_device", "stemk_assemble_device", "stemk_pair_cost", "stemk_stats_reset", "stemk_stats_get", "stemk_fp64_peak", "stemk_format_rows", "stemk_format_values", "stemk_bpla_pairs", "stemk_bpla_gradients", "stemk_nstem_pairs", "stemk_nstem_pairs_banded", "stemk_nstem_pairs_windows",
            "stemk_set_clone", "stemk_upload_multi", "stemk_gram_multi", "stemk_set_export_bytes", "stemk_set_export", "stemk_set_import"]
 
 _lib = None
@@ -78,6 +78,7 @@ def lib():
         L.stemk_bpla_gradients.argtypes = [vp, vp, vp, vp, sz, vp, vp, vp, vp]
         L.stemk_nstem_pairs.argtypes = [vp, vp, vp, vp, sz, vp, vp, vp]
         L.stemk_nstem_pairs_banded.argtypes = [vp, vp, C.c_uint32, vp, vp, sz, vp, vp, vp]
+        L.stemk_nstem_pairs_windows.argtypes = [vp, vp, vp, vp, sz, vp, vp, vp, vp, vp, vp]
         L.stemk_set_clone.argtypes = [vp, vp, C.POINTER(vp)]
         L.stemk_upload_multi.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(SeqSetDesc), C.POINTER(vp)]
         L.stemk_gram_multi.argtypes = [C.POINTER(vp), C.POINTER(vp), C.c_int, C.c_int, vp]

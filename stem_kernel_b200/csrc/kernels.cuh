@@ -131,7 +131,8 @@ cudaError_t run_bpla(const stemk_bpla_params& p, const stemk_bpla_set& x, const 
 // naive stem kernel (nstem.cu): host buffers in, host buffer out, synchronous on `stream`
 cudaError_t run_nstem(const stemk_nstem_params& p, const stemk_nstem_set& x, const stemk_nstem_set& y, size_t n_pairs,
                       const uint32_t* xi, const uint32_t* yi, double* out, uint32_t band, int sm_count, size_t smem_optin,
-                      cudaStream_t stream, std::string* err);   // band > 0: partial_dp with the band-only constraints
+                      cudaStream_t stream, std::string* err,   // band > 0: partial_dp with the band-only constraints
+                      const uint32_t* win_off = nullptr, const uint32_t* c_low = nullptr, const uint32_t* c_high = nullptr);   // or the caller's per-row windows
 cudaError_t launch_fp64_peak(double* sink, int grid, int block, int iters, cudaStream_t stream);
 
 }  // namespace stemk

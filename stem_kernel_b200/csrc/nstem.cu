@@ -199,7 +199,12 @@ __global__ void __launch_bounds__(kNstemThreads) nstem_pairs_kernel(const NstemL
 // and operand order of the reference kept.
 struct NstemBandLaunch {
   NstemLaunch B;
-  uint32_t band, wcap;              // wcap = plane pitch: min(2 band + 2, ly_cap + 2)
+  uint32_t band, wcap;              // wcap = plane pitch: min(2 band + 2, ly_cap + 2), or the widest caller window + 2
+  // caller-supplied constraints instead of the band (alignment_constraints with ali_bound > 0, stem_kernel.cpp:25-67):
+  // pair k owns entries win_off[k] .. win_off[k] + lx of c_low / c_high (row i of x pairs with columns c_low..c_high of y)
+  const uint32_t* win_off;
+  const uint32_t* c_low;
+  const uint32_t* c_high;
 };
 constexpr int kNbandWarps = 4;
 enum { BK0 = 0, BK1, BK2, BK3, BG0, BG1, BG2, BG3 };
@@ -234,8 +239,10 @@ __global__ void __launch_bounds__(32 * kNbandWarps) nstem_banded_kernel(const Ns
     __syncwarp();
     if (lane == 0) { gp[0] = 1.0; for (uint32_t n = 1; n <= max(lx, ly); ++n) gp[n] = gp[n - 1] * g; }
     __syncwarp();
-    auto clo = [&](uint32_t i) { const uint32_t c = (uint32_t)((double)i / (double)lx * (double)ly + 0.5); return c < band ? 0u : c - band; };
-    auto chi = [&](uint32_t i) { const uint32_t c = (uint32_t)((double)i / (double)lx * (double)ly + 0.5); return c + band > ly ? ly : c + band; };
+    const uint32_t* wl = Q.win_off ? Q.c_low + Q.win_off[kq] : nullptr;
+    const uint32_t* wh = Q.win_off ? Q.c_high + Q.win_off[kq] : nullptr;
+    auto clo = [&](uint32_t i) { if (wl) return __ldg(wl + i); const uint32_t c = (uint32_t)((double)i / (double)lx * (double)ly + 0.5); return c < band ? 0u : c - band; };
+    auto chi = [&](uint32_t i) { if (wh) return __ldg(wh + i); const uint32_t c = (uint32_t)((double)i / (double)lx * (double)ly + 0.5); return c + band > ly ? ly : c + band; };
     // plane (i, column parity): 8 tables of WP x WP, cell (k,l) at [k - clo(i)][l - clo(j)]
     auto tab = [&](uint32_t t, uint32_t i, uint32_t j) { return scr + (((size_t)(j & 1u) * (lx + 1u) + i) * 8u + t) * tsz; };
     // value of table t of plane (i,j) at (k,l), for a plane that is complete (fill values, diagonals, (j,j) planes)
@@ -320,7 +327,9 @@ __global__ void __launch_bounds__(32 * kNbandWarps) nstem_banded_kernel(const Ns
 
 cudaError_t run_nstem(const stemk_nstem_params& p, const stemk_nstem_set& x, const stemk_nstem_set& y, size_t n_pairs,
                       const uint32_t* xi, const uint32_t* yi, double* out, uint32_t band, int sm_count, size_t smem_optin,
-                      cudaStream_t stream, std::string* err) {
+                      cudaStream_t stream, std::string* err, const uint32_t* win_off, const uint32_t* c_low, const uint32_t* c_high) {
+  const bool windows = win_off != nullptr;
+  if (windows) band = 1;   // the banded kernel, its windows read from the caller's arrays
   std::vector<void*> to_free;
   auto up = [&](const void* h, size_t bytes, const void** d) -> cudaError_t {
     *d = nullptr;
@@ -364,7 +373,16 @@ cudaError_t run_nstem(const stemk_nstem_params& p, const stemk_nstem_set& x, con
   const void *dxi, *dyi;
   void *dout = nullptr, *dscr = nullptr;
   unsigned long long* dcnt = nullptr;
-  const uint32_t wcap = std::min(2u * band + 2u, ly_cap + 2u);
+  uint32_t wcap = std::min(2u * band + 2u, ly_cap + 2u);
+  const void *d_woff = nullptr, *d_clo = nullptr, *d_chi = nullptr;
+  if (windows) {
+    uint32_t widest = 0;
+    const size_t n_win = win_off[n_pairs];
+    for (size_t q = 0; q < n_win; ++q) widest = std::max(widest, c_high[q] >= c_low[q] ? c_high[q] - c_low[q] : 0u);
+    wcap = std::min(widest + 2u, ly_cap + 2u);
+    if ((e = up(win_off, sizeof(uint32_t) * (n_pairs + 1), &d_woff)) != cudaSuccess || (e = up(c_low, sizeof(uint32_t) * n_win, &d_clo)) != cudaSuccess ||
+        (e = up(c_high, sizeof(uint32_t) * n_win, &d_chi)) != cudaSuccess) { cleanup(); return e; }
+  }
   int grid = (int)std::min<size_t>(n_pairs, (size_t)sm_count);
   unsigned long long stride = (unsigned long long)(lx_cap + 3u) * plane;
   if (band) {   // per warp: two columns of (lx_cap + 1) planes, eight tables of wcap^2 cells each
@@ -389,6 +407,7 @@ cudaError_t run_nstem(const stemk_nstem_params& p, const stemk_nstem_set& x, con
   if (band) {
     NstemBandLaunch BL;
     BL.B = L; BL.band = band; BL.wcap = wcap;
+    BL.win_off = (const uint32_t*)d_woff; BL.c_low = (const uint32_t*)d_clo; BL.c_high = (const uint32_t*)d_chi;
     BL.B.pitch = std::max(pitch, (lx_cap + 1u) | 1u);                    // the powers of g, per warp: up to max(lx, ly)
     const size_t bsmem = sizeof(double) * (BL.B.pitch + 2u) * kNbandWarps;
     nstem_banded_kernel<<<grid, 32 * kNbandWarps, bsmem, stream>>>(BL);

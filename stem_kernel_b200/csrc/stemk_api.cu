@@ -1111,21 +1111,30 @@ int stemk_bpla_gradients(stemk_ctx* ctx, const stemk_bpla_params* params, const 
 }
 
 static int nstem_pairs_impl(stemk_ctx* ctx, const stemk_nstem_params* params, uint32_t band, const stemk_nstem_set* x,
-                            const stemk_nstem_set* y, size_t n_pairs, const uint32_t* xi, const uint32_t* yi, double* out);
+                            const stemk_nstem_set* y, size_t n_pairs, const uint32_t* xi, const uint32_t* yi, double* out,
+                            const uint32_t* win_off, const uint32_t* c_low, const uint32_t* c_high);
 
 int stemk_nstem_pairs(stemk_ctx* ctx, const stemk_nstem_params* params, const stemk_nstem_set* x, const stemk_nstem_set* y,
                       size_t n_pairs, const uint32_t* xi, const uint32_t* yi, double* out) {
-  return nstem_pairs_impl(ctx, params, 0, x, y, n_pairs, xi, yi, out);
+  return nstem_pairs_impl(ctx, params, 0, x, y, n_pairs, xi, yi, out, nullptr, nullptr, nullptr);
 }
 
 int stemk_nstem_pairs_banded(stemk_ctx* ctx, const stemk_nstem_params* params, uint32_t band, const stemk_nstem_set* x,
                              const stemk_nstem_set* y, size_t n_pairs, const uint32_t* xi, const uint32_t* yi, double* out) {
   if (ctx && band == 0) return fail(ctx, STEMK_ERR_ARG, "band must be positive (band 0 is stemk_nstem_pairs)");
-  return nstem_pairs_impl(ctx, params, band, x, y, n_pairs, xi, yi, out);
+  return nstem_pairs_impl(ctx, params, band, x, y, n_pairs, xi, yi, out, nullptr, nullptr, nullptr);
+}
+
+int stemk_nstem_pairs_windows(stemk_ctx* ctx, const stemk_nstem_params* params, const stemk_nstem_set* x, const stemk_nstem_set* y,
+                              size_t n_pairs, const uint32_t* xi, const uint32_t* yi, const uint32_t* win_off, const uint32_t* c_low,
+                              const uint32_t* c_high, double* out) {
+  if (ctx && (!win_off || !c_low || !c_high)) return fail(ctx, STEMK_ERR_ARG, "null window array");
+  return nstem_pairs_impl(ctx, params, 1, x, y, n_pairs, xi, yi, out, win_off, c_low, c_high);
 }
 
 static int nstem_pairs_impl(stemk_ctx* ctx, const stemk_nstem_params* params, uint32_t band, const stemk_nstem_set* x,
-                            const stemk_nstem_set* y, size_t n_pairs, const uint32_t* xi, const uint32_t* yi, double* out) {
+                            const stemk_nstem_set* y, size_t n_pairs, const uint32_t* xi, const uint32_t* yi, double* out,
+                            const uint32_t* win_off, const uint32_t* c_low, const uint32_t* c_high) {
   if (!ctx || !params || !x || !y) return fail(ctx, STEMK_ERR_ARG, "null argument");
   if (ctx->device == STEMK_DEVICE_NONE) return no_device(ctx);
   if (n_pairs == 0) return STEMK_OK;
@@ -1139,7 +1148,15 @@ static int nstem_pairs_impl(stemk_ctx* ctx, const stemk_nstem_params* params, ui
     if (xi[k] >= x->n_seqs || yi[k] >= y->n_seqs) return fail(ctx, STEMK_ERR_ARG, "pair index out of range");
   CU(cudaSetDevice(ctx->device));
   std::string err;
-  cudaError_t e = run_nstem(*params, *x, *y, n_pairs, xi, yi, out, band, ctx->sm_count, ctx->smem_optin, ctx->stream, &err);
+  if (win_off) {   // windows: one entry per row 0..lx of every pair, inside the second sequence
+    for (size_t k = 0; k < n_pairs; ++k) {
+      const uint32_t lx = x->off[xi[k] + 1] - x->off[xi[k]], ly = y->off[yi[k] + 1] - y->off[yi[k]];
+      if (win_off[k + 1] < win_off[k] || win_off[k + 1] - win_off[k] != lx + 1u) return fail(ctx, STEMK_ERR_ARG, "window arrays: a pair needs lx + 1 entries");
+      for (uint32_t q = win_off[k]; q < win_off[k + 1]; ++q)
+        if (c_low[q] > c_high[q] || c_high[q] > ly) return fail(ctx, STEMK_ERR_ARG, "window arrays: need c_low <= c_high <= ly");
+    }
+  }
+  cudaError_t e = run_nstem(*params, *x, *y, n_pairs, xi, yi, out, band, ctx->sm_count, ctx->smem_optin, ctx->stream, &err, win_off, c_low, c_high);
   if (e != cudaSuccess) return err.empty() ? cuda_fail(ctx, e, "naive stem kernel") : fail(ctx, STEMK_ERR_NOMEM, err);
   ctx->launches += 1;
   return STEMK_OK;

@@ -87,3 +87,25 @@ def pairs_banded(ctx, params, band, x, y, xi, yi):
     ctx._check(L.lib().stemk_nstem_pairs_banded(ctx.h, C.byref(params), int(band), C.byref(cx), C.byref(cy), len(xi),
                                                 xi.ctypes.data, yi.ctypes.data, out.ctypes.data))
     return out
+
+
+def pack_windows(windows):
+    """[(c_low, c_high)] per pair (arrays of lx + 1 entries) -> (win_off, c_low, c_high) as the C ABI takes them."""
+    off = np.zeros(len(windows) + 1, dtype=np.uint32)
+    off[1:] = np.cumsum([len(w[0]) for w in windows])
+    lo = np.ascontiguousarray(np.concatenate([np.asarray(w[0]) for w in windows]) if windows else np.zeros(0), dtype=np.uint32)
+    hi = np.ascontiguousarray(np.concatenate([np.asarray(w[1]) for w in windows]) if windows else np.zeros(0), dtype=np.uint32)
+    return off, lo, hi
+
+
+def pairs_windows(ctx, params, x, y, xi, yi, windows):
+    """partial_dp under caller-supplied per-row constraints (the c_low / c_high of StemKernel::alignment_constraints with
+    ali_bound > 0, stem_kernel.cpp:14-67): windows[k] = (c_low, c_high) of pair k, lx + 1 entries each."""
+    xi = np.ascontiguousarray(xi, dtype=np.uint32)
+    yi = np.ascontiguousarray(yi, dtype=np.uint32)
+    off, lo, hi = pack_windows(windows)
+    out = np.zeros(len(xi))
+    cx, cy = x.c(), y.c()
+    ctx._check(L.lib().stemk_nstem_pairs_windows(ctx.h, C.byref(params), C.byref(cx), C.byref(cy), len(xi), xi.ctypes.data,
+                                                 yi.ctypes.data, off.ctypes.data, lo.ctypes.data, hi.ctypes.data, out.ctypes.data))
+    return out

@@ -8,7 +8,7 @@ of its own, so these files pin the oracle and the CUDA path to 
   golden_mdata.npz     the reference constructor's MData (DAG, profiles, weights) for each record
   golden_naive.npz     string_kernel/ (naive) Gram on 8 raw strings, gap parsed as float
   golden_svm.npz       40-record C1 Gram (reference) and the vendored LIBSVM's 5-fold CV targets on it
-  golden_nstem.npz     stem_kernel/ (the naive O(L^4) stem kernel, full_dp): 9 short sequences, canonical pairs with and
+  golden_nstem.npz     stem_kernel/ (the naive O(L^4) stem kernel, full_dp, banded partial_dp, partial_dp under pair-HMM windows): 9 short sequences, canonical pairs with and
                        without g-u, probability tables, a non-default parameter set; upper-triangle values
   golden_bpla.npz      bpla_kernel/ (BPLA / local-alignment kernels): 12 records (single sequences, alignments,
                        IUPAC, gaps, a length-1 and a 70-column record), their base-pairing profiles, and the
@@ -168,4 +168,12 @@ if __name__ == "__main__":
     for band in (3, 8):
         n[f"k_normal_band{band}"] = R.nstem_pairs(nstem.make_params(), sa, sa, xi, yi, band=band)
         n[f"k_table_band{band}"] = R.nstem_pairs(nstem.make_params(bp_mode=1, bp_bound=0.05), sb, sb, xi, yi, band=band)
+    # partial_dp under the pair-HMM constraints of ali_bound > 0 (alignment_constraints, stem_kernel.cpp:14-67; phmm.cpp),
+    # alone and narrowed by a band (:57-66): the reference's own windows (c_low / c_high per row) and its values
+    for tag, band, ab in (("ali", 0, 0.3), ("ali_band4", 4, 0.3)):
+        wins = [R.nstem_windows(seqs[a], seqs[b], band=band, ali_bound=ab) for a, b in zip(xi, yi)]
+        n[f"win_low_{tag}"] = np.concatenate([w[0] for w in wins])
+        n[f"win_high_{tag}"] = np.concatenate([w[1] for w in wins])
+        n[f"k_normal_{tag}"] = R.nstem_pairs(nstem.make_params(), sa, sa, xi, yi, band=band, ali_bound=ab)
+        n[f"k_table_{tag}"] = R.nstem_pairs(nstem.make_params(bp_mode=1, bp_bound=0.05), sb, sb, xi, yi, band=band, ali_bound=ab)
     np.savez_compressed(os.path.join(OUT, "golden_nstem.npz"), **n)

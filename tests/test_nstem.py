@@ -138,3 +138,80 @@ def test_gpu_banded_partial_dp():
     assert max(errs.values()) < TOL, errs
     with pytest.raises(api.StemkError, match="band must be positive"):
         nstem.pairs_banded(ctx, p, 0, a, b, xi, yi)
+
+
+def golden_windows(z, tag, sa):
+    """The reference's own c_low / c_high (alignment_constraints, stem_kernel.cpp:14-67) per golden pair."""
+    wins, at = [], 0
+    for a in z["xi"]:
+        n = len(sa.seqs[int(a)]) + 1
+        wins.append((z[f"win_low_{tag}"][at:at + n], z[f"win_high_{tag}"][at:at + n]))
+        at += n
+    return wins
+
+
+def test_window_restatement_is_bit_identical_to_the_reference_with_pair_hmm_constraints():
+    """partial_dp under the constraints of ali_bound > 0 (pair-HMM posteriors, phmm.cpp; alone and narrowed by a band,
+    stem_kernel.cpp:25-67): the restatement fed the reference's own windows gives the reference's values bit for bit."""
+    sa, sb, z = golden_sets()
+    for tag in ("ali", "ali_band4"):
+        wins = golden_windows(z, tag, sa)
+        assert max(int((h - l).max()) for l, h in wins) > 8          # wider than any band tested: unaligned stretches
+        assert np.array_equal(O.nstem_pairs_windows(nstem.make_params(), sa, sa, z["xi"], z["yi"], wins), z[f"k_normal_{tag}"])
+        assert np.array_equal(O.nstem_pairs_windows(nstem.make_params(bp_mode=1, bp_bound=0.05), sb, sb, z["xi"], z["yi"], wins),
+                              z[f"k_table_{tag}"])
+    # the band-only windows through the same entry give the banded values
+    band = 3
+    wins = []
+    for a, b in zip(z["xi"], z["yi"]):
+        lx, ly = len(sa.seqs[int(a)]), len(sa.seqs[int(b)])
+        c = (np.arange(lx + 1) / lx * ly + 0.5).astype(np.uint32)
+        wins.append((np.where(c < band, 0, c - band), np.minimum(c + band, ly)))
+    assert np.array_equal(O.nstem_pairs_windows(nstem.make_params(), sa, sa, z["xi"], z["yi"], wins), z["k_normal_band3"])
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(R.REF_DIR, "libstemk_ref_nstem.so")), reason="oracle/_ref not built")
+def test_window_restatement_matches_the_compiled_reference_on_fresh_inputs():
+    rng = np.random.default_rng(23)
+    seqs = ["".join(rng.choice(list("acgu"), n)) for n in (9, 14, 21, 26)] + ["gggcaaagccc", "gggcuaaagcccu"]
+    s = nstem.NstemSet(seqs)
+    xi, yi = np.divmod(np.arange(len(seqs) ** 2), len(seqs))
+    for band, ab in ((0, 0.2), (2, 0.5), (5, 0.05)):
+        wins = [R.nstem_windows(seqs[a], seqs[b], band=band, ali_bound=ab) for a, b in zip(xi, yi)]
+        p = nstem.make_params(use_gu=True)
+        assert np.array_equal(O.nstem_pairs_windows(p, s, s, xi, yi, wins), R.nstem_pairs(p, s, s, xi, yi, band=band, ali_bound=ab))
+
+
+@pytest.mark.gpu
+def test_gpu_windows_match_the_reference_golden_and_the_oracle():
+    """stemk_nstem_pairs_windows: the device kernel under the reference's pair-HMM windows."""
+    need_gpu()
+    from stem_kernel_b200 import _lib as L
+    from stem_kernel_b200 import api
+    sa, sb, z = golden_sets()
+    ctx = api.Context(L.make_params(L.STR_SIMPLE), device=0)
+    for tag in ("ali", "ali_band4"):
+        wins = golden_windows(z, tag, sa)
+        got = nstem.pairs_windows(ctx, nstem.make_params(), sa, sa, z["xi"], z["yi"], wins)
+        assert relerr(got, z[f"k_normal_{tag}"]) < TOL
+        got = nstem.pairs_windows(ctx, nstem.make_params(bp_mode=1, bp_bound=0.05), sb, sb, z["xi"], z["yi"], wins)
+        assert relerr(got, z[f"k_table_{tag}"]) < TOL
+    # fresh sequences, arbitrary monotone windows (not produced by any band): against the oracle
+    rng = np.random.default_rng(5)
+    seqs = ["".join(rng.choice(list("acgu"), n)) for n in (11, 17, 24, 30)]
+    s = nstem.NstemSet(seqs)
+    xi, yi = np.divmod(np.arange(len(seqs) ** 2), len(seqs))
+    wins = []
+    for a, b in zip(xi, yi):
+        lx, ly = len(seqs[a]), len(seqs[b])
+        c = (np.arange(lx + 1) / lx * ly + 0.5).astype(np.int64)
+        w = rng.integers(1, 7, size=lx + 1)
+        lo = np.maximum.accumulate(np.clip(c - w, 0, ly))
+        hi = np.maximum.accumulate(np.maximum(np.clip(c + w[::-1], 0, ly), lo))
+        wins.append((lo.astype(np.uint32), hi.astype(np.uint32)))
+    p = nstem.make_params(use_gu=True, gap=0.6)
+    assert relerr(nstem.pairs_windows(ctx, p, s, s, xi, yi, wins), O.nstem_pairs_windows(p, s, s, xi, yi, wins)) < TOL
+    # malformed windows are refused
+    bad = [(w[0][:-1], w[1][:-1]) for w in wins]
+    with pytest.raises(api.StemkError):
+        nstem.pairs_windows(ctx, p, s, s, xi, yi, bad)
