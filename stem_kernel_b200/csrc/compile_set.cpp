@@ -19,7 +19,6 @@
 #include <cstring>
 #include <exception>
 #include <functional>
-#include <queue>
 #include <thread>
 
 #include "ribosum85_60.inc"
@@ -52,7 +51,6 @@ struct RecOut {  // one record's share, appended to the CompiledSet in record or
   std::vector<NodeI> nodei;
   std::vector<uint16_t> c16;
   std::vector<uint32_t> blk, lperm;
-  std::vector<uint16_t> slot, waitrow;   // slab row of a node; the row whose completion frees that slab row (0xffff: fresh)
   std::vector<double> pd, pb;  // work-model prefix sums over node length
   uint32_t n_all = 0, e_all = 0, max_rows = 0, band_cnt = 0;
   std::string err;
@@ -61,7 +59,6 @@ struct RecOut {  // one record's share, appended to the CompiledSet in record or
     cw.swap(o.cw); len.swap(o.len); coff.swap(o.coff); cidx.swap(o.cidx); lev_off.swap(o.lev_off); boff.swap(o.boff); bcode.swap(o.bcode);
     bab.swap(o.bab); ccode.swap(o.ccode); text.swap(o.text); prof.swap(o.prof); deg_all.swap(o.deg_all); up.swap(o.up); dn.swap(o.dn);
     s2.swap(o.s2); nodei.swap(o.nodei); c16.swap(o.c16); blk.swap(o.blk); lperm.swap(o.lperm); pd.swap(o.pd); pb.swap(o.pb);
-    slot.swap(o.slot); waitrow.swap(o.waitrow);
   }
 };
 
@@ -347,40 +344,6 @@ void compile_record(const stemk_seqset_desc& s, uint32_t r, double g, uint32_t l
       }
     }
   }
-  // ---- slab rows (the reference's DPTable row pool: dptable.h:10-74, rows freed after a node's last parent,
-  // max_pa, stem_kernel.cpp:79-85).  The fast kernel keeps row i of its per-pair G0 table in slab row slot[i].  A slab
-  // row is handed on, in row order, once its owner's last parent lies more than kSlabMargin rows back (rows complete
-  // out of order, the margin keeps the reuse off the critical path); the new owner still waits at run time until every
-  // row up to that last parent is published (waitrow), so the static assignment is safe under any schedule.  A pair then
-  // touches ~60 % of its Nx x Ny table's addresses instead of all of them.  cidx carries the child's slab row in its
-  // upper half.
-  {
-    constexpr uint32_t kSlabMargin = 32;
-    o->slot.assign(N, 0); o->waitrow.assign(N, 0xffffu);
-    uint32_t n_slots = 0;
-    if (N < 0xffffu) {
-      std::vector<uint32_t> maxpa(N);
-      for (uint32_t k = 0; k < N; ++k) maxpa[k] = k;
-      for (uint32_t k = 0; k < N; ++k)
-        for (uint32_t e = o->coff[k]; e < o->coff[k + 1]; ++e) maxpa[o->cidx[e]] = std::max(maxpa[o->cidx[e]], k);
-      std::priority_queue<std::pair<uint32_t, uint32_t>, std::vector<std::pair<uint32_t, uint32_t>>, std::greater<std::pair<uint32_t, uint32_t>>> freed;
-      for (uint32_t i = 0; i < N; ++i) {
-        if (!freed.empty() && freed.top().first + kSlabMargin < i) {
-          o->slot[i] = (uint16_t)freed.top().second; o->waitrow[i] = (uint16_t)freed.top().first;
-          freed.pop();
-        } else {
-          o->slot[i] = (uint16_t)n_slots++;
-        }
-        freed.push({maxpa[i], o->slot[i]});
-      }
-      for (uint32_t k = 0; k < N; ++k)
-        for (uint32_t e = o->coff[k]; e < o->coff[k + 1]; ++e) o->cidx[e] |= (uint32_t)o->slot[o->cidx[e]] << 16;
-    } else {
-      for (uint32_t k = 0; k < N; ++k) o->slot[k] = (uint16_t)k;   // never staged by a stem kernel anyway
-      n_slots = N;
-    }
-    h.n_slots = n_slots;
-  }
   o->pd.assign(max_len + 2, 0.0); o->pb.assign(max_len + 2, 0.0);
   for (uint32_t k = 0; k < N; ++k) {
     o->pd[o->len[k] + 1] += o->deg_all[k];
@@ -497,8 +460,7 @@ std::string compile_set(const stemk_seqset_desc& s, double g, uint32_t len_band,
           XNode* xn = reinterpret_cast<XNode*>(blob + L[A_XNODE]) + h.node0;
           for (uint32_t k = 0; k < h.N; ++k) {
             xn[k].s2 = o.s2[k]; xn[k].a = o.a[k]; xn[k].up = o.up[k]; xn[k].ql = o.ql[k]; xn[k].bfreq = o.bfreq[k]; xn[k].paths = o.paths[k];
-            xn[k].e0 = o.coff[k]; xn[k].e1 = o.coff[k + 1];
-            xn[k].len = o.len[k] | ((uint32_t)o.waitrow[k] << 16); xn[k].bcode = o.bcode[k] | ((uint32_t)o.slot[k] << 8);
+            xn[k].e0 = o.coff[k]; xn[k].e1 = o.coff[k + 1]; xn[k].len = o.len[k]; xn[k].bcode = o.bcode[k];
           }
         }
         std::copy(o.len.begin(), o.len.end(), c.len.begin() + h.node0);
@@ -522,9 +484,6 @@ std::string compile_set(const stemk_seqset_desc& s, double g, uint32_t len_band,
   }
   if (timing) {
     auto t2 = std::chrono::steady_clock::now();
-    double rows = 0, slots = 0;
-    for (const RecDev& h : c.rec) { rows += h.N; slots += h.n_slots; }
-    std::fprintf(stderr, "compile_set: slab rows after recycling %.0f of %.0f (%.1f %%)\n", slots, rows, rows ? 100.0 * slots / rows : 0.0);
     std::fprintf(stderr, "compile_set: %u records, per-record %.1f ms (%d threads), merge %.1f ms\n", n,
                  std::chrono::duration<double, std::milli>(t1 - t0).count(), n_threads,
                  std::chrono::duration<double, std::milli>(t2 - t1).count());

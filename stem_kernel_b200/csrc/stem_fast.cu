@@ -110,7 +110,6 @@ __global__ void __launch_bounds__(32 * (NCH > 0 ? kFastRegWarps : kFastMaxWarps)
   __shared__ unsigned long long s_item;
   __shared__ uint32_t s_next_blk, s_g, s_maxblk;
   __shared__ PairSlot s_slot[kGroup];
-  __shared__ uint32_t s_wm[kGroup];   // per pair of the group: every row below this index is published (the row pool's release mark)
   const uint32_t nwarps = blockDim.x >> 5;
   const FastLayout L = fast_layout(nwarps, P.nx_cap, P.ny_cap, P.e4_cap, P.lev_cap, P.band_cap);
   const uint32_t sb = (uint32_t)__cvta_generic_to_shared(sm);  // raw 32-bit shared addresses: LDS/STS [reg+imm]
@@ -161,7 +160,6 @@ __global__ void __launch_bounds__(32 * (NCH > 0 ? kFastRegWarps : kFastMaxWarps)
       }
       s_g = g;
       s_next_blk = 0;
-      for (uint32_t q = 0; q < kGroup; ++q) s_wm[q] = 0;
     }
     __syncthreads();
     const uint32_t g = s_g;
@@ -220,17 +218,9 @@ __global__ void __launch_bounds__(32 * (NCH > 0 ? kFastRegWarps : kFastMaxWarps)
         const double2 x23 = __ldg(reinterpret_cast<const double2*>(xn) + 1);   // {up, ql}
         const double2 x45 = __ldg(reinterpret_cast<const double2*>(xn) + 2);   // {bfreq, paths}
         const uint4 xi4 = __ldg(reinterpret_cast<const uint4*>(xn) + 3);       // {e0, e1, len, bcode}
-        const uint32_t e0 = xi4.x, e1 = xi4.y, xl = xi4.z & 0xffffu, xbc = xi4.w & 0xffu;
+        const uint32_t e0 = xi4.x, e1 = xi4.y, xl = xi4.z, xbc = xi4.w;
         const double xs2 = x01.x, pc = x23.x * x01.y;   // pc = up_x * a_x
-        // The row pool (dptable.h:10-74): row i lives in slab row `xi4.w >> 8`, which an earlier row owned until its
-        // last parent was done.  The assignment is static (compile_set.cpp); what is checked here is that every row up
-        // to that last parent (xi4.z >> 16) is published before this row overwrites the slab row.
-        double* __restrict__ g0row = G0 + (size_t)(xi4.w >> 8) * NYS;
-        {
-          const uint32_t waitrow = xi4.z >> 16;
-          if (waitrow != 0xffffu)
-            for (uint32_t ns = kPollNs0; *(volatile uint32_t*)&s_wm[sl] <= waitrow; ns = min(2u * ns, kPollNsMax)) __nanosleep(ns);
-        }
+        double* __restrict__ g0row = G0 + (size_t)i * NYS;
 
         // ---- phase A: q = sum over inner pairs c of G0s(c,:);  HQ = up_y*s2_x*q -> buffer, up_x*a_x*s2_x*q -> slab
         if constexpr (NCH > 0) {
@@ -248,8 +238,7 @@ __global__ void __launch_bounds__(32 * (NCH > 0 ? kFastRegWarps : kFastMaxWarps)
               const uint32_t ne = min(32u, e1 - eb);
               uint32_t c = 0u;
               if (lane < ne) c = X.cidx[eb + lane];
-              const uint32_t off_l = (c >> 16) * NYS;   // the child's slab row
-              c &= 0xffffu;                             // the child's row: its flag
+              const uint32_t off_l = c * NYS;
               if (c0 == 0) {
                 // wait until the rows of all inner pairs are published: one poll per lane and round, the whole warp
                 // sleeps in between, longer every time
@@ -303,8 +292,7 @@ __global__ void __launch_bounds__(32 * (NCH > 0 ? kFastRegWarps : kFastMaxWarps)
             PROF_T(t_w0);
             uint32_t c = 0u;
             if (lane < ne) c = X.cidx[eb + lane];
-            const uint32_t off_l = (c >> 16) * NYS;   // the child's slab row
-            c &= 0xffffu;                             // the child's row: its flag
+            const uint32_t off_l = c * NYS;
             // wait until the rows of all inner pairs are published: one poll per lane and round, the whole warp sleeps
             // in between, longer every time (polling is shared-memory traffic the sweeps of the other warps pay for)
             for (uint32_t ns = kPollNs0; !__all_sync(0xffffffffu, lane >= ne || ld_flag_f(done + c) != 0u); ns = min(2u * ns, kPollNsMax))
@@ -443,7 +431,7 @@ __global__ void __launch_bounds__(32 * (NCH > 0 ? kFastRegWarps : kFastMaxWarps)
         constexpr uint32_t nslot = 32u / R;
         const uint32_t r = lane / nslot, slot = lane % nslot;
         const bool live = r < cnt;
-        const uint32_t xl = __ldg(&X.xnode[ps.node0 + i0 + (live ? r : 0u)].len) & 0xffffu;
+        const uint32_t xl = __ldg(&X.xnode[ps.node0 + i0 + (live ? r : 0u)].len);
         // below the window (len_y + band < len_x) G1 is identically 0: length-monotone DAG
         const uint32_t len_lo = (band != 0u && xl > band) ? xl - band : 0u;
         const uint32_t hrow = wrows + row_bytes * r;
@@ -493,7 +481,7 @@ __global__ void __launch_bounds__(32 * (NCH > 0 ? kFastRegWarps : kFastMaxWarps)
         const uint32_t i = i0 + rr;
         const uint32_t rb = wrows + row_bytes * rr;
         const double xup = __ldg(&X.xnode[ps.node0 + i].up);
-        double* __restrict__ g0row = G0 + (size_t)(__ldg(&X.xnode[ps.node0 + i].bcode) >> 8) * NYS;
+        double* __restrict__ g0row = G0 + (size_t)i * NYS;
         for (uint32_t jb = 0; jb < Ny; jb += 256u) {
           const uint32_t j = jb + 2u * lane;
           const uint32_t rj = rb + 8u * j;
@@ -520,13 +508,6 @@ __global__ void __launch_bounds__(32 * (NCH > 0 ? kFastRegWarps : kFastMaxWarps)
       __threadfence_block();
       __syncwarp();
       if (lane < cnt) asm volatile("st.volatile.shared.u8 [%0], %1;" ::"r"(done + i0 + lane), "r"(1u) : "memory");
-      __syncwarp();
-      if (lane == 0) {   // move the pair's release mark over every row that is published by now
-        uint32_t w = *(volatile uint32_t*)&s_wm[sl];
-        const uint32_t w0 = w;
-        while (w < ps.N && ld_flag_f(done + w) != 0u) ++w;
-        if (w != w0) atomicMax(&s_wm[sl], w);
-      }
       PROF_T(t_c);
       PROF_ADD(4, t_b2b, t_c);
       PROF_ADD(0, t_0, t_c);

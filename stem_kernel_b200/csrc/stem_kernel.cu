@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_pairs_kernel(const StemL
     }
     for (uint32_t e = tid; e < Ey; e += kStemThreads) {
       EdgeRec er;
-      er.ce = Y.ce[ye0 + e]; er.off = (Y.cidx[ye0 + e] & 0xffffu) * 8u; er.pad = 0;
+      er.ce = Y.ce[ye0 + e]; er.off = Y.cidx[ye0 + e] * 8u; er.pad = 0;
       SM(EdgeRec, L.yE + 16 * e) = er;
     }
     for (uint32_t l = tid; l <= ry.nlev; l += kStemThreads) SM(uint32_t, L.yLev + 4 * l) = Y.lev_off[ry.lev0 + l];
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_pairs_kernel(const StemL
           double ce_l = 0.0;
           uint32_t off_l = 0u;
           if (lane < ne) {
-            const uint32_t c = X.cidx[eb + lane] & 0xffffu;
+            const uint32_t c = X.cidx[eb + lane];
             ce_l = X.ce[eb + lane];
             off_l = c * NYS;
             while (ld_flag(sm, L.done + 4u * c) == 0u) __nanosleep(40);  // wait until that row is finished

@@ -592,10 +592,7 @@ int stemk_pairs_device(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, s
       const int per_sm = stem_fast_ctas_per_sm(ny_cap, best_w, best_smem);
       if (per_sm < 1) return fail(ctx, STEMK_ERR_CUDA, "fast stem kernel does not fit on an SM");
       const int grid = (int)std::min<size_t>((n_pairs + kFastGroup - 1) / kFastGroup, (size_t)ctx->sm_count);
-      // a pair's G0 table needs as many slab rows as its x record's row pool (rows recycled after their last parent)
-      uint32_t slot_cap = 1;
-      for (const RecDev& rx : x->host.rec) if (rx.flags & REC_FAST) slot_cap = std::max(slot_cap, rx.n_slots);
-      const unsigned long long stride = (unsigned long long)kFastGroup * slot_cap * ((ny_cap + 1u) & ~1u);
+      const unsigned long long stride = (unsigned long long)kFastGroup * nx_cap * ((ny_cap + 1u) & ~1u);
       CU(ctx->scratch.reserve(sizeof(double) * stride * grid));
       CU(ctx->rowacc.reserve(sizeof(double) * (size_t)kFastGroup * nx_cap * grid));
       StemFastLaunch F;

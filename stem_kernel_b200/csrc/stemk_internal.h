@@ -36,7 +36,7 @@ struct RecDev {
   uint32_t blk0;    // offset of its row blocks in `blk`
   uint32_t nblk;    // row blocks (<= kFastRows rows of one level each)
   uint32_t sub1;    // first sub-level whose nodes have inner pairs (the sub-levels before it are DAG level 0)
-  uint32_t n_slots; // slab rows the fast kernel's G0 table of this record needs (rows recycled after their last parent)
+  uint32_t pad_;
 };
 enum { REC_HAS_WEIGHT = 1u, REC_SIMPLE_COLS = 2u, REC_SIMPLE_BPF = 4u,
        REC_LEN_MONOTONE = 8u,  // every non-leaf child is strictly shorter than its parent (true for front-end DAGs)
@@ -52,7 +52,7 @@ struct __attribute__((aligned(16))) XNode {   // everything the fast kernel need
   double up, ql;        // g^(B-len), sum_children e*G0(child, leaf column)
   double bfreq, paths;  // base-pair frequency, root->node paths
   uint32_t e0, e1;      // its non-leaf children in cidx (absolute)
-  uint32_t len, bcode;  // len | waitrow << 16 (the row that must be published before this node's slab row may be written, 0xffff: none); bcode | slab row << 8
+  uint32_t len, bcode;
 };
 
 struct NodeI {        // integer part of a node for the fast kernel (8 bytes)
@@ -76,7 +76,7 @@ struct SetView {
   const uint8_t* bcode;  // a*4+b for a single-entry profile, 0xFF otherwise
   // children (non-leaf only), CSR local to the record
   const uint32_t* coff;  // [sum(N+1)]
-  const uint32_t* cidx;  // child, in the record's level numbering (low 16 bits) | the child's slab row << 16
+  const uint32_t* cidx;  // child, in the record's level numbering
   const double* ce;      // g^gaps * edge weight
   const uint32_t* lev_off;
   // separable fast path: e(j,c) = g^(len_j - len_c - 2) = s2[j] * up[c]; dn = 1/up (as its own power)
