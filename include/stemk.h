@@ -118,9 +118,12 @@ const char* stemk_last_error(const stemk_ctx* ctx); /* ctx may be NULL: last cre
 /* Context options (test and diagnostic hooks; there is no environment-variable dispatch):
  *   STEMK_OPT_FORCE_GENERAL  1: every stem pair runs on the general kernel (stem_kernel.cu) instead of the separable
  *                            fast path -- what alignments / IUPAC records take anyway; lets tests compare the two
- *   STEMK_OPT_TIMING         1: stemk_upload / stemk_gram print a host-side time breakdown on stderr */
+ *   STEMK_OPT_TIMING         1: stemk_upload / stemk_gram print a host-side time breakdown on stderr
+ *   STEMK_OPT_FORCE_UNSTAGED 1: the pairs of the general kernel all run on its unstaged variant (the one that takes
+ *                            records of any size); lets tests cover it with small records */
 #define STEMK_OPT_FORCE_GENERAL 1
 #define STEMK_OPT_TIMING 2
+#define STEMK_OPT_FORCE_UNSTAGED 3
 int stemk_set_option(stemk_ctx* ctx, int option, int value);
 
 /* Threading: a context is single-threaded and has ONE call in flight -- its scratch buffers, work queues and DP
@@ -130,13 +133,14 @@ int stemk_set_option(stemk_ctx* ctx, int option, int value);
  * Sets are bound to the device, loop gap and length band of the context that uploaded them (the derived per-record
  * tables depend on them); using a set with another context fails with STEMK_ERR_ARG. */
 
-/* Limits (records outside them fail the call with STEMK_ERR_NOMEM and a message naming the record; there is no CPU
- * path to fall back to): the fast stem kernel takes records of up to 1024 non-leaf DAG nodes whose gap powers
- * g^(len/2) stay within 1e-125 .. 1e125 (about 360 nt of pair span at g = 0.2) with unit edge weights, single-entry
- * base-pair profiles and no gap columns under a node -- every record the reference's front end makes from one
- * sequence; everything else (alignments, IUPAC codes, hand-made DAGs) runs on the general stem kernel, which stages
- * the second record of a pair in shared memory: about 1000 non-leaf nodes / 8000 inner edges per record.  The string
- * kernels have no length limit. */
+/* Record sizes.  The stem kernels take records of ANY size, like the reference's operator(): the fast stem kernel
+ * runs records of up to 1024 non-leaf DAG nodes whose gap powers g^(len/2) stay within 1e-125 .. 1e125 (about 360 nt of
+ * pair span at g = 0.2) with unit edge weights, single-entry base-pair profiles and no gap columns under a node --
+ * every record the reference's front end makes from one sequence; everything else (alignments, IUPAC codes, hand-made
+ * DAGs, longer records) runs on the general stem kernel, which stages the second record of a pair in shared memory
+ * (up to about 1000 non-leaf nodes / 8000 inner edges), and pairs with a larger record run on its unstaged variant,
+ * which keeps everything in global memory (slower per pair; bounded only by device memory: 8 B x nodes_x x nodes_y of
+ * scratch per pair in flight).  The string kernels have no length limit. */
 
 /* upload a flattened set (copied; derived per-record tables are built here) */
 int stemk_upload(stemk_ctx* ctx, const stemk_seqset_desc* desc, stemk_set** set);

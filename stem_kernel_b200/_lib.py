@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CUDA_SO = os.environ.get("STEMK_SO") or os.path.join(_HERE, "csrc", "libstemk_b200.so")   # STEMK_SO: tuning builds
 
 OK, ERR_ARG, ERR_CUDA, ERR_NOMEM, ERR_STATE = 0, -1, -2, -3, -4
-OPT_FORCE_GENERAL, OPT_TIMING = 1, 2
+OPT_FORCE_GENERAL, OPT_TIMING, OPT_FORCE_UNSTAGED = 1, 2, 3
 
 # stemk_kind
 SI_STEM, SU_STEM, SI_STEM_STR, SU_STEM_STR, LSU_STEM, LSU_STR, LSU_STEM_STR, STR_SUBST, STR_SIMPLE, STR_NAIVE = range(10)

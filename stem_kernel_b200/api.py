@@ -37,7 +37,7 @@ class Context:
             raise StemkError(f"stemk error {rc}: {L.lib().stemk_last_error(self.h).decode()}")
 
     def set_option(self, option, value=1):
-        """stemk_set_option: L.OPT_FORCE_GENERAL (general stem kernel for every pair), L.OPT_TIMING."""
+        """stemk_set_option: L.OPT_FORCE_GENERAL (general stem kernel for every pair), L.OPT_FORCE_UNSTAGED (its any-size variant), L.OPT_TIMING."""
         self._check(L.lib().stemk_set_option(self.h, int(option), int(value)))
         return self
 

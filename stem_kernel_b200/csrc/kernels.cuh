@@ -72,6 +72,27 @@ struct StemClassify {
   uint32_t caps[kMaxFastBuckets];    // staged-record size limit of fast bucket b (bucket number 1+b)
   int n_caps;
   int allow_fast;
+  // pairs of the general kernel whose records do not fit its shared-memory carve-up (x rows > gen_nx, y nodes > gen_ny
+  // or y inner edges > gen_ey) go to bucket `big_bucket` (the unstaged kernel); big_bucket < 0: no such bucket
+  int big_bucket;
+  uint32_t gen_nx, gen_ny, gen_ey;
+};
+
+// unstaged general stem kernel: runs the pairs order[start[bucket] .. + count[bucket]) with nothing in shared memory
+struct StemBigLaunch {
+  SetView X, Y;
+  const uint32_t* xi;
+  const uint32_t* yi;
+  double* out;
+  const uint32_t* order;
+  const unsigned long long* start;   // [n_buckets] device
+  const unsigned long long* count;   // [n_buckets] device
+  unsigned long long* counter;       // this bucket's work-queue head (zeroed by the classifier)
+  int bucket;
+  double* scratch;                   // per CTA: G0 slab nx_cap x ny_pitch | per warp a Q row and a G1 row | nx_cap row flags
+  unsigned long long scratch_stride; // doubles per CTA (stem_unstaged_scratch_doubles)
+  const double* pair_tab;
+  uint32_t len_band, nx_cap, ny_cap;
 };
 
 struct StringLaunch {
@@ -94,6 +115,8 @@ size_t stem_smem_bytes(uint32_t nslots, uint32_t nx_cap, uint32_t ny_cap, uint32
 int stem_warps_per_cta();
 cudaError_t launch_stem(const StemLaunch& p, int grid, size_t smem, cudaStream_t stream);
 int stem_max_ctas_per_sm(size_t smem);
+unsigned long long stem_unstaged_scratch_doubles(uint32_t nx_cap, uint32_t ny_cap);
+cudaError_t launch_stem_unstaged(const StemBigLaunch& p, int grid, cudaStream_t stream);
 size_t stem_fast_smem_bytes(uint32_t nwarps, uint32_t nx_cap, uint32_t ny_cap, uint32_t e4_cap, uint32_t lev_cap,
                             uint32_t band_cap);
 int stem_fast_ctas_per_sm(uint32_t ny_cap, int nwarps, size_t smem);

@@ -542,12 +542,17 @@ __global__ void __launch_bounds__(32 * (NCH > 0 ? kFastRegWarps : kFastMaxWarps)
 }
 
 // ---- pair classification: which kernel / size bucket runs a pair -----------------------------------------
-// bucket 0 = general kernel; 1 + b = fast kernel with shared memory sized for bucket b; trivial pairs (an empty DAG
-// on either side) are finished here.
+// bucket 0 = general kernel; 1 + b = fast kernel with shared memory sized for bucket b; big_bucket = the unstaged
+// general kernel (records of any size); trivial pairs (an empty DAG on either side) are finished here.
 __device__ __forceinline__ int pair_bucket(const StemClassify& C, const RecDev& rx, const RecDev& ry) {
   if (rx.N == 0 || ry.N == 0) return -1;
-  if (!C.allow_fast || !(rx.flags & REC_FAST) || !(ry.flags & REC_FAST)) return 0;
-  for (int b = 0; b < C.n_caps; ++b) if (ry.N <= C.caps[b]) return 1 + b;
+  if (C.allow_fast && (rx.flags & REC_FAST) && (ry.flags & REC_FAST))
+    for (int b = 0; b < C.n_caps; ++b) if (ry.N <= C.caps[b]) return 1 + b;
+  // general kernel; records its shared-memory carve-up cannot hold go to the unstaged kernel
+  if (C.big_bucket >= 0) {
+    const uint32_t ey = C.Y.coff[ry.coff0 + ry.N] - C.Y.coff[ry.coff0];
+    if (rx.N > C.gen_nx || ry.N > C.gen_ny || ey > C.gen_ey) return C.big_bucket;
+  }
   return 0;
 }
 

@@ -286,7 +286,177 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_pairs_kernel(const StemL
 #undef SM
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The same recurrence with NOTHING staged: records of any size (the reference's operator() has no size limit).
+// The y record is read where the upload put it (global memory through L1/L2), every warp's Q and G1 rows and the row
+// flags live in the CTA's global scratch next to the G0 slab.  Same dataflow -- a warp takes the next row, waits for
+// the rows of its inner pairs, runs phases A, B, C alone -- and the same arithmetic per cell as stem_pairs_kernel
+// (the two y-edge sums are kept in one accumulator instead of two).  Only the pairs the classifier finds too large
+// for the staged kernel's shared-memory carve-up run here (bucket StemClassify::big_bucket).
+struct UnstagedLayout { unsigned long long pitch, rows, flags, total; };
+__host__ __device__ inline UnstagedLayout unstaged_layout(uint32_t nx_cap, uint32_t ny_cap) {
+  UnstagedLayout U;
+  U.pitch = ((unsigned long long)ny_cap + 1ull) & ~1ull;
+  U.rows = (unsigned long long)nx_cap * U.pitch;
+  U.flags = U.rows + 2ull * kStemWarps * U.pitch;
+  U.total = U.flags + ((unsigned long long)nx_cap + 1ull) / 2ull;
+  U.total = (U.total + 1ull) & ~1ull;
+  return U;
+}
+
+__global__ void __launch_bounds__(kStemThreads, 1) stem_pairs_unstaged_kernel(const StemBigLaunch P) {
+  __shared__ double s_tab[256];
+  __shared__ double s_red[kStemWarps];
+  __shared__ unsigned long long s_pair;
+  __shared__ uint32_t s_next_row;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const uint32_t band = P.len_band;
+  const unsigned long long n_items = P.count[P.bucket];
+  const uint32_t* __restrict__ order = P.order + P.start[P.bucket];
+  for (uint32_t t = tid; t < 256; t += kStemThreads) s_tab[t] = P.pair_tab[t];
+  const UnstagedLayout U = unstaged_layout(P.nx_cap, P.ny_cap);
+  double* __restrict__ base = P.scratch + (size_t)blockIdx.x * P.scratch_stride;
+  double* __restrict__ G0 = base;
+  double* qrow = base + U.rows + 2ull * warp * U.pitch;   // this warp's Q row; its G1 row follows
+  double* g1row = qrow + U.pitch;
+  volatile uint32_t* done = reinterpret_cast<volatile uint32_t*>(base + U.flags);
+  const SetView& X = P.X;
+  const SetView& Y = P.Y;
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) { s_pair = atomicAdd(P.counter, 1ull); s_next_row = 0; }
+    __syncthreads();
+    if (s_pair >= n_items) break;
+    const unsigned long long k = order[s_pair];
+    const RecDev rx = X.rec[P.xi[k]];
+    const RecDev ry = Y.rec[P.yi[k]];
+    const uint32_t Nx = rx.N, Ny = ry.N;
+    const double extra = rx.plr * (double)ry.lr;
+    if (Nx == 0 || Ny == 0) {
+      if (tid == 0) P.out[k] = extra;
+      continue;
+    }
+    const unsigned long long NYS = ((unsigned long long)Ny + 1ull) & ~1ull;
+    for (uint32_t i = tid; i < Nx; i += kStemThreads) done[i] = 0u;
+    __threadfence_block();
+    __syncthreads();
+
+    const uint32_t* __restrict__ xcoff = X.coff + rx.coff0;
+    const uint32_t* __restrict__ ycoff = Y.coff + ry.coff0;
+    const uint32_t* __restrict__ ylev = Y.lev_off + ry.lev0;
+    const bool simple_bpf = (rx.flags & REC_SIMPLE_BPF) && (ry.flags & REC_SIMPLE_BPF);
+    const bool skip_short = band != 0u && (ry.flags & REC_LEN_MONOTONE);
+    double acc = 0.0;
+
+    for (;;) {
+      uint32_t i = 0;
+      if (lane == 0) i = atomicAdd(&s_next_row, 1u);
+      i = __shfl_sync(0xffffffffu, i, 0);
+      if (i >= Nx) break;
+      const uint32_t gx = rx.node0 + i;
+      const uint32_t e0 = xcoff[i], e1 = xcoff[i + 1];
+      const double xa = X.a[gx], xql = X.ql[gx], xpath = X.paths[gx], xbf = X.bfreq[gx], xgap = X.gapt[gx];
+      const uint32_t xl = X.len[gx], xbc = X.bcode[gx];
+
+      // ---- phase A: Q(i,:) = sum over inner pairs c of e * G0(c,:)
+      for (uint32_t eb = e0; eb < e1 || eb == e0; eb += 32u) {
+        const uint32_t ne = min(32u, e1 - eb);
+        double ce_l = 0.0;
+        unsigned long long off_l = 0ull;
+        if (lane < ne) {
+          const uint32_t c = X.cidx[eb + lane];
+          ce_l = X.ce[eb + lane];
+          off_l = (unsigned long long)c * NYS;
+          while (done[c] == 0u) __nanosleep(100);   // wait until that row is finished
+        }
+        __syncwarp();
+        __threadfence_block();   // acquire: the G0 rows behind the flags just seen
+        for (uint32_t jb = 0; jb < Ny; jb += 32u) {   // uniform trip count: the shuffles below need every lane
+          const uint32_t j = jb + lane;
+          const bool one = j < Ny;
+          double q = (one && eb != e0) ? __ldcg(qrow + j) : 0.0;
+          for (uint32_t t = 0; t < ne; ++t) {
+            const double ce = __shfl_sync(0xffffffffu, ce_l, t);
+            const unsigned long long off = __shfl_sync(0xffffffffu, off_l, t);
+            if (one) q = fma(ce, __ldcg(G0 + off + j), q);
+          }
+          if (one) qrow[j] = q;
+        }
+        if (e1 == e0) break;
+      }
+      __syncwarp();
+
+      // ---- phase B: sweep the y DAG level by level, lanes <-> nodes of the level
+      double racc = 0.0;
+      uint32_t jbeg = ylev[0];
+      for (uint32_t ly = 0; ly < ry.nlev; ++ly) {
+        const uint32_t jend = ylev[ly + 1];
+        for (uint32_t j = jbeg + lane; j < jend; j += 32u) {
+          const uint32_t gy = ry.node0 + j;
+          const uint32_t yl = Y.len[gy];
+          if (skip_short && yl + band < xl) {   // G1 == 0 here and below (see the header)
+            g1row[j] = 0.0;
+            continue;
+          }
+          const uint32_t dl = xl > yl ? xl - yl : yl - xl;
+          const bool in_band = (band == 0u) || (dl <= band);
+          const double ya = Y.a[gy];
+          uint32_t e = ycoff[j];
+          const uint32_t eend = ycoff[j + 1];
+          double S = 0.0, m = 0.0;
+          if (in_band) {
+            double vs;
+            if (simple_bpf) vs = s_tab[xbc * 16u + Y.bcode[gy]] * xbf * Y.bfreq[gy];
+            else vs = node_match_general(X.boff + rx.boff0 + i, X.bab, X.bfq, Y.boff + ry.boff0 + j, Y.bab, Y.bfq, s_tab);
+            vs = fma(ya, xgap, vs);
+            vs = fma(xa, Y.gapt[gy], vs);
+            double R = 0.0;
+            for (; e < eend; ++e) {
+              const uint32_t c = Y.cidx[e];
+              const double ce = Y.ce[e];
+              S = fma(ce, __ldcg(g1row + c), S);
+              R = fma(ce, __ldcg(qrow + c), R);
+            }
+            m = vs * fma(Y.el[gy], xql, R);
+            racc = fma(Y.paths[gy], m, racc);
+          } else {
+            for (; e < eend; ++e) S = fma(Y.ce[e], __ldcg(g1row + Y.cidx[e]), S);
+          }
+          g1row[j] = fma(ya, S, m);
+        }
+        jbeg = jend;
+        __syncwarp();
+      }
+      acc = fma(xpath, racc, acc);
+
+      // ---- phase C: finished row G0(i,:) = G1 + a_x * Q, then publish it
+      double* __restrict__ g0row = G0 + (unsigned long long)i * NYS;
+      for (uint32_t j = lane; j < Ny; j += 32u) g0row[j] = fma(xa, __ldcg(qrow + j), __ldcg(g1row + j));
+      __threadfence_block();
+      __syncwarp();
+      if (lane == 0) done[i] = 1u;
+    }
+
+    acc = warp_sum(acc);
+    if (lane == 0) s_red[warp] = acc;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int w = 0; w < kStemWarps; ++w) t += s_red[w];
+      P.out[k] = t + extra;
+    }
+  }
+}
+
 }  // namespace
+
+unsigned long long stem_unstaged_scratch_doubles(uint32_t nx_cap, uint32_t ny_cap) { return unstaged_layout(nx_cap, ny_cap).total; }
+
+cudaError_t launch_stem_unstaged(const StemBigLaunch& p, int grid, cudaStream_t stream) {
+  stem_pairs_unstaged_kernel<<<grid, kStemThreads, 0, stream>>>(p);
+  return cudaGetLastError();
+}
 
 size_t stem_smem_bytes(uint32_t nslots, uint32_t nx_cap, uint32_t ny_cap, uint32_t ey_cap, uint32_t lev_cap) {
   return stem_layout(nslots, nx_cap, ny_cap, ey_cap, lev_cap).total;

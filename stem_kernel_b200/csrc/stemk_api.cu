@@ -69,7 +69,7 @@ struct stemk_ctx {
   double* d_pair_tab = nullptr;
   double* d_subst = nullptr;
   unsigned long long* d_counter = nullptr;
-  DevBuf scratch, carry, tmp_stem, tmp_str, idx_x, idx_y, vals, matrix, order, rowacc;
+  DevBuf scratch, scratch_big, carry, tmp_stem, tmp_str, idx_x, idx_y, vals, matrix, order, rowacc;
   DevBuf perm, offs, diag, selfv, diag_idx, diag_vals, diag_idx2, diag_vals2;
   DevBuf deal_x, deal_y, gathered, undealt;     // stemk_gram_multi: this device's share of the pair list; on device 0 the gather
   cudaEvent_t multi_ev = nullptr;
@@ -81,6 +81,7 @@ struct stemk_ctx {
   cudaEvent_t stage_ev[2] = {nullptr, nullptr};
   unsigned long long* d_bucket = nullptr;  // count[16] | start[16] | queue heads[16]
   int use_fast = 1;                        // stemk_set_option(STEMK_OPT_FORCE_GENERAL, 1) routes every pair to the general stem kernel
+  int force_unstaged = 0;                  // stemk_set_option(STEMK_OPT_FORCE_UNSTAGED, 1): the general kernel's pairs all run unstaged
   int timing = 0;                          // stemk_set_option(STEMK_OPT_TIMING, 1): host-side breakdown of the calls on stderr
   std::string err;
   // stats
@@ -163,14 +164,18 @@ size_t place(size_t& off, const std::vector<T>& v) {
 }
 
 // number of row slots (warps with private Q/G1 rows) and shared memory for a launch of x set against y set
-void stem_config(const stemk_ctx* ctx, const CompiledSet& xs, const CompiledSet& ys, uint32_t* nslots, size_t* smem) {
-  const uint32_t nx = std::max(1u, xs.max_N), ny = std::max(1u, ys.max_N), ey = std::max(1u, ys.max_E), lv = std::max(1u, ys.max_nlev);
+void stem_config(const stemk_ctx* ctx, uint32_t nx, uint32_t ny, uint32_t ey, uint32_t lv, uint32_t* nslots, size_t* smem) {
   const size_t budget = std::min<size_t>(ctx->smem_optin, (size_t)226 * 1024);
   uint32_t best = 0;
   for (uint32_t w = (uint32_t)stem_warps_per_cta(); w >= 1; --w) if (stem_smem_bytes(w, nx, ny, ey, lv) <= budget) { best = w; break; }
   *nslots = best;
   *smem = best ? stem_smem_bytes(best, nx, ny, ey, lv) : 0;
 }
+
+// Records the staged general kernel takes when the largest records of a set do not fit its shared-memory carve-up with
+// at least kGenMinSlots row slots: 56 B per node + 16 B per inner edge + 4 B per x row + two rows of 8 B per node and
+// slot leave 8 slots at these sizes.  Larger records run on the unstaged kernel.
+constexpr uint32_t kGenMinSlots = 4, kGenCapNx = 2048, kGenCapNy = 640, kGenCapEy = 5120;
 
 }  // namespace
 
@@ -236,6 +241,7 @@ int stemk_set_option(stemk_ctx* ctx, int option, int value) {
   if (!ctx) return fail(ctx, STEMK_ERR_ARG, "null argument");
   switch (option) {
     case STEMK_OPT_FORCE_GENERAL: ctx->use_fast = value ? 0 : 1; return STEMK_OK;
+    case STEMK_OPT_FORCE_UNSTAGED: ctx->force_unstaged = value ? 1 : 0; return STEMK_OK;
     case STEMK_OPT_TIMING: ctx->timing = value; return STEMK_OK;
     default: return fail(ctx, STEMK_ERR_ARG, "unknown option");
   }
@@ -246,7 +252,7 @@ void stemk_destroy(stemk_ctx* c) {
   if (c->device == STEMK_DEVICE_NONE) { delete c; return; }
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  for (DevBuf* b : {&c->scratch, &c->carry, &c->tmp_stem, &c->tmp_str, &c->idx_x, &c->idx_y, &c->vals, &c->matrix, &c->order, &c->rowacc,
+  for (DevBuf* b : {&c->scratch, &c->scratch_big, &c->carry, &c->tmp_stem, &c->tmp_str, &c->idx_x, &c->idx_y, &c->vals, &c->matrix, &c->order, &c->rowacc,
                     &c->perm, &c->offs, &c->diag, &c->selfv, &c->diag_idx, &c->diag_vals, &c->diag_idx2, &c->diag_vals2,
                     &c->deal_x, &c->deal_y, &c->gathered, &c->undealt}) b->release();
   if (c->multi_ev) cudaEventDestroy(c->multi_ev);
@@ -515,11 +521,9 @@ int stemk_pairs_device(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, s
   }
 
   if (has_stem) {
-    const uint32_t nx_cap = std::max(1u, x->host.max_N);
-    const uint32_t lev_cap = std::max(1u, y->host.max_nlev);
     if (n_pairs > 0xffffffffull) return fail(ctx, STEMK_ERR_ARG, "more than 2^32 pairs in one call");
-    // ---- classify: trivial pairs are finished, the others go to the general kernel (bucket 0) or to the fast
-    // kernel's size buckets (1..), each bucket keeping the caller's pair order
+    // ---- classify: trivial pairs are finished, the others go to the general kernel (bucket 0), to the fast
+    // kernel's size buckets (1..) or to the unstaged kernel (last bucket), each bucket keeping the caller's pair order
     static const uint32_t kCaps[kMaxFastBuckets] = {256, 320, 384, 448, 512, 640, 768, kFastMaxN};
     const bool any_fast = ctx->use_fast && x->host.n_fast > 0 && y->host.n_fast > 0;
     StemClassify C;
@@ -532,45 +536,79 @@ int stemk_pairs_device(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, s
         C.caps[C.n_caps++] = kCaps[b];
         if (kCaps[b] >= y->host.max_fastN) break;
       }
+    // general kernel: needed unless every record with a DAG is fast-eligible.  Its shared-memory carve-up is sized for
+    // the largest records of the two sets; when those leave fewer than kGenMinSlots row slots it is sized for
+    // kGenCap* instead and the pairs with a larger record run on the unstaged kernel.
+    auto n_dag = [](const CompiledSet& h) { uint32_t n = 0; for (const RecDev& r : h.rec) n += r.N > 0; return n; };
+    const bool need_general = !any_fast || x->host.n_fast < n_dag(x->host) || y->host.n_fast < n_dag(y->host);
+    uint32_t gen_nx = std::max(1u, x->host.max_N), gen_ny = std::max(1u, y->host.max_N), gen_ey = std::max(1u, y->host.max_E);
+    uint32_t gen_lv = std::max(1u, y->host.max_nlev), nslots = 0;
+    size_t gen_smem = 0;
+    C.big_bucket = -1; C.gen_nx = C.gen_ny = C.gen_ey = 0xffffffffu;
+    bool run_staged = need_general;
+    if (need_general) {
+      stem_config(ctx, gen_nx, gen_ny, gen_ey, gen_lv, &nslots, &gen_smem);
+      if (nslots < kGenMinSlots || ctx->force_unstaged) {
+        C.big_bucket = 1 + C.n_caps;
+        if (ctx->force_unstaged) { C.gen_nx = C.gen_ny = C.gen_ey = 0; run_staged = false; }
+        else {
+          gen_nx = std::min(gen_nx, kGenCapNx); gen_ny = std::min(gen_ny, kGenCapNy); gen_ey = std::min(gen_ey, kGenCapEy);
+          gen_lv = std::min(gen_lv, gen_ny);   // a record has at most one sub-level per node
+          C.gen_nx = gen_nx; C.gen_ny = gen_ny; C.gen_ey = gen_ey;
+          stem_config(ctx, gen_nx, gen_ny, gen_ey, gen_lv, &nslots, &gen_smem);
+          if (!nslots) return fail(ctx, STEMK_ERR_CUDA, "general stem kernel does not fit in shared memory");
+        }
+      }
+    }
     CU(ctx->order.reserve(n_pairs * sizeof(uint32_t)));
     C.order = (uint32_t*)ctx->order.p;
-    const int n_buckets = 1 + C.n_caps;
+    const int n_buckets = 1 + C.n_caps + (C.big_bucket >= 0 ? 1 : 0);
     CU(launch_classify(C, n_buckets, heads, st));
     ctx->launches += 3;
 
-    // ---- general kernel: needed unless every record with a DAG is fast-eligible
-    auto n_dag = [](const CompiledSet& h) { uint32_t n = 0; for (const RecDev& r : h.rec) n += r.N > 0; return n; };
-    const bool need_general = !any_fast || x->host.n_fast < n_dag(x->host) || y->host.n_fast < n_dag(y->host);
-    if (need_general) {
-      const uint32_t ny_cap = std::max(1u, y->host.max_N);
-      uint32_t nslots; size_t smem;
-      stem_config(ctx, x->host, y->host, &nslots, &smem);
-      if (!nslots) {
-        uint32_t worst = 0;
-        for (uint32_t r = 0; r < y->host.rec.size(); ++r) if (y->host.rec[r].N > y->host.rec[worst].N) worst = r;
-        return fail(ctx, STEMK_ERR_NOMEM, "general stem kernel: record " + std::to_string(worst) + " of the second set has " +
-                    std::to_string(y->host.rec[worst].N) + " non-leaf DAG nodes and " + std::to_string(y->host.max_E) +
-                    " inner edges, more than one CTA can stage in shared memory (56 B per node + 16 B per edge + two row buffers "
-                    "in 227 KB: about 1000 nodes); see the limits section of include/stemk.h");
-      }
-      int per_sm = stem_max_ctas_per_sm(smem);
+    if (run_staged) {
+      int per_sm = stem_max_ctas_per_sm(gen_smem);
       if (per_sm < 1) return fail(ctx, STEMK_ERR_CUDA, "stem kernel does not fit on an SM");
       per_sm = std::min(per_sm, 4);
-      const int grid = (int)std::min<size_t>(n_pairs, (size_t)ctx->sm_count * per_sm);
-      const unsigned long long stride = (unsigned long long)nx_cap * ((ny_cap + 1u) & ~1u);
+      const unsigned long long stride = (unsigned long long)gen_nx * ((gen_ny + 1u) & ~1u);
+      // the G0 slabs of all resident CTAs: at most ~4 GB
+      const size_t by_mem = std::max<size_t>(1, ((size_t)4 << 30) / (sizeof(double) * (size_t)stride));
+      const int grid = (int)std::min(std::min<size_t>(n_pairs, (size_t)ctx->sm_count * per_sm), by_mem);
       CU(ctx->scratch.reserve(sizeof(double) * stride * grid));
       StemLaunch L;
       L.X = x->view; L.Y = y->view; L.xi = d_xi; L.yi = d_yi; L.n_pairs = n_pairs; L.out = stem_out;
       L.counter = heads + 0; L.scratch = (double*)ctx->scratch.p; L.scratch_stride = stride;
-      L.pair_tab = ctx->d_pair_tab; L.len_band = ctx->params.len_band; L.nslots = nslots; L.nx_cap = nx_cap; L.ny_cap = ny_cap;
-      L.ey_cap = std::max(1u, y->host.max_E); L.lev_cap = lev_cap;
+      L.pair_tab = ctx->d_pair_tab; L.len_band = ctx->params.len_band; L.nslots = nslots; L.nx_cap = gen_nx; L.ny_cap = gen_ny;
+      L.ey_cap = gen_ey; L.lev_cap = gen_lv;
       L.order = C.order; L.n_items_dev = C.count + 0;
       stemk_ctx::Timed tm = timed_begin(ctx, 0, st);
-      cudaError_t le = launch_stem(L, grid, smem, st);
+      cudaError_t le = launch_stem(L, grid, gen_smem, st);
       timed_end(ctx, tm, st);
       CU(le);
       ctx->launches += 1;
     }
+    if (C.big_bucket >= 0) {
+      // unstaged kernel: one CTA per pair in flight, everything in the CTA's global scratch (sized for the largest
+      // records of the two sets); as many CTAs as ~4 GB of scratch allow, at most one per SM
+      const uint32_t bx = std::max(1u, x->host.max_N), by = std::max(1u, y->host.max_N);
+      const unsigned long long stride = stem_unstaged_scratch_doubles(bx, by);
+      const size_t by_mem = std::max<size_t>(1, ((size_t)4 << 30) / (sizeof(double) * (size_t)stride));
+      const int grid = (int)std::min(std::min<size_t>(n_pairs, (size_t)ctx->sm_count), by_mem);
+      CU(ctx->scratch_big.reserve(sizeof(double) * stride * grid));
+      StemBigLaunch B;
+      B.X = x->view; B.Y = y->view; B.xi = d_xi; B.yi = d_yi; B.out = stem_out; B.order = C.order;
+      B.start = C.start; B.count = C.count; B.counter = heads + C.big_bucket; B.bucket = C.big_bucket;
+      B.scratch = (double*)ctx->scratch_big.p; B.scratch_stride = stride; B.pair_tab = ctx->d_pair_tab;
+      B.len_band = ctx->params.len_band; B.nx_cap = bx; B.ny_cap = by;
+      stemk_ctx::Timed tm = timed_begin(ctx, 0, st);
+      cudaError_t le = launch_stem_unstaged(B, grid, st);
+      timed_end(ctx, tm, st);
+      CU(le);
+      ctx->launches += 1;
+    }
+    // the fast kernel only ever sees fast-eligible records: its row flags, slabs and level table are sized for those
+    const uint32_t nx_cap = std::max(1u, x->host.max_fastN);
+    const uint32_t lev_cap = std::max(1u, std::min(y->host.max_nlev, std::max(1u, y->host.max_fastN)));
     // ---- fast kernel, one launch per size bucket (shared memory and warps per CTA sized for the bucket)
     for (int b = 0; any_fast && b < C.n_caps; ++b) {
       const uint32_t ny_cap = std::min(C.caps[b], std::max(1u, y->host.max_fastN));

@@ -45,6 +45,43 @@ def test_golden_gram(golden, kind, band, fast):
     ctx.close()
 
 
+@pytest.mark.parametrize("band", [10, 0])
+def test_golden_gram_unstaged_kernel(golden, band):
+    """The any-size variant of the general stem kernel (nothing staged in shared memory) on the golden records:
+    STEMK_OPT_FORCE_UNSTAGED sends every pair of the general kernel to it."""
+    ctx = api.Context(L.make_params(L.SU_STEM_STR, len_band=band))
+    ctx.set_option(L.OPT_FORCE_GENERAL, True).set_option(L.OPT_FORCE_UNSTAGED, True)
+    got = ctx.gram(ctx.upload(golden["flat"]))
+    assert relerr(got, golden["z"][f"gram_k{L.SU_STEM_STR}_b{band}"]) < TOL
+    ctx.close()
+
+
+@pytest.mark.parametrize("band", [10, 0])
+def test_records_of_any_size(band):
+    """Records beyond every shared-memory limit (700-1500 nt: 1 200-2 400 non-leaf DAG nodes, 7 000-16 000 inner edges)
+    next to ordinary ones and an alignment: the reference's operator() has no size limit; the
+    classifier sends the pairs with a large record to the unstaged kernel, the others stay where they were."""
+    recs = [synth.ncrna_like(777, i, 700, 900) for i in range(2)] + [synth.ncrna_like(778, 0, 1200, 1500)]
+    recs += synth.make_config(3, 4, offset=50) + [synth.alignment_like(5, 1, n_rows=3, L=70)]
+    flat = hostlib.SeqSet([hostlib.MData.from_record(r, TH) for r in recs])
+    p = L.make_params(L.SU_STEM, len_band=band)
+    ctx = api.Context(p)
+    ds = ctx.upload(flat)
+    want = O.gram(oparams(p), flat.desc(), False)
+    assert relerr(ctx.gram(ds), want) < TOL
+    # rectangular, large records on either side (the oracle's own rectangular matrix: the stem kernel is not symmetric
+    # in its arguments and a row is kernel(train_j, test_i), kernel_matrix.cpp:164-171)
+    smallf = hostlib.SeqSet([hostlib.MData.from_record(r, TH) for r in recs[3:]])
+    small = ctx.upload(smallf)
+    m, sv = ctx.cross(small, ds)
+    wm, wsv = O.cross(oparams(p), smallf.desc(), flat.desc())
+    assert relerr(m, wm) < TOL and relerr(sv, wsv) < TOL
+    m, sv = ctx.cross(ds, small)
+    wm, wsv = O.cross(oparams(p), flat.desc(), smallf.desc())
+    assert relerr(m, wm) < TOL and relerr(sv, wsv) < TOL
+    ctx.close()
+
+
 def test_golden_normalised_text_is_byte_identical(golden):
     z = golden["z"]
     ctx = api.Context(L.make_params(L.SU_STEM_STR))
