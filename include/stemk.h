@@ -299,6 +299,58 @@ int stemk_nstem_pairs_windows(stemk_ctx* ctx, const stemk_nstem_params* params, 
                               size_t n_pairs, const uint32_t* xi, const uint32_t* yi, const uint32_t* win_off,
                               const uint32_t* c_low, const uint32_t* c_high, double* out);
 
+/* ---- Front end: base-pair probabilities -------------------------------------------------------
+ * Replaces the per-sequence ViennaRNA call of the reference's front end -- fold / init_pf_fold / pf_fold and the copy
+ * bp(i,j) = pr[iindx[i]-j] under a process-wide mutex (common/bpmatrix.cpp:141-177) -- by a batched McCaskill
+ * partition function on the device: one CTA per sequence, inside and outside recursions swept diagonal by diagonal.
+ * ViennaRNA is an external, unversioned dependency that is absent from this image, so the ENERGY MODEL IS AN INPUT:
+ * a nearest-neighbour loop model in the shape of the Vienna 1.8 pf_fold recursions with dangles on both sides of
+ * every multiloop / exterior stem (-d2): stacking, hairpin / bulge / interior initiation by size (logarithmic
+ * extrapolation beyond 30), terminal mismatches, asymmetry (Ninio) term, terminal A-U / G-U penalty, linear
+ * multiloop.  Not modelled: the tabulated 1x1 / 2x1 / 2x2 interior loops and special tri/tetraloop bonuses (they take
+ * the generic formulas), no_closingGU, noLonelyPairs, alifold.  PARITY WITH ViennaRNA IS UNPINNED: the checker is
+ * this repo's own CPU restatement (oracle/stemk_fold_oracle.c), itself checked against an exhaustive enumeration of
+ * all secondary structures of short sequences.
+ *
+ * Pair types: 1 CG, 2 GC, 3 GU, 4 UG, 5 AU, 6 UA (0 = cannot pair); base codes 1 A, 2 C, 3 G, 4 U (0 = anything else:
+ * never pairs).  Energies in kcal/mol.  Pairs need at least 3 unpaired bases between them; interior loops have at most
+ * 30 unpaired bases. */
+typedef struct stemk_fold_model {
+  double temperature;          /* degrees Celsius: kT = (temperature + 273.15) * 1.98717e-3 kcal/mol */
+  double pf_scale;             /* per-nucleotide scaling of the partition function (Vienna::pf_scale); <= 0: Vienna's
+                                  default exp(-(-185 + (temperature - 37) * 7.27) / (1000 kT)) */
+  int32_t no_gu;               /* Vienna::noGU */
+  int32_t pad_;
+  double stack[8][8];          /* [type(i,j)][reversed type of the inner pair] like Vienna's stack37 */
+  double hairpin[31], bulge[31], interior[31];   /* initiation by loop size; sizes > 30: [30] + lxc * ln(size / 30) */
+  double lxc;
+  double mismatch_h[8][5][5];  /* hairpin terminal mismatch [type][base after i][base before j] (loops of > 3) */
+  double mismatch_i[8][5][5];  /* interior-loop terminal mismatch, both ends */
+  double dangle5[8][5], dangle3[8][5];   /* [type][neighbouring base]; applied on both sides wherever a neighbour exists */
+  double ninio, max_ninio;     /* asymmetry: min(max_ninio, |u1 - u2| * ninio) */
+  double terminal_au;          /* pair types > 2 closing a bulge of > 1, a hairpin of 3 or an exterior stem */
+  double ml_closing, ml_intern[8], ml_base;
+} stemk_fold_model;
+
+/* A stand-in parameter set so that tests, the benchmark and the front end have something to fold with: stacking,
+ * initiation and multiloop terms of Turner-1999 magnitude, synthetic mismatch / dangle tables.  NOT a published
+ * parameter file; real parameters are the caller's. */
+void stemk_fold_model_default(stemk_fold_model* model);
+
+/* Base-pair probabilities of n_seqs sequences: sequence k is text[seq_off[k] .. seq_off[k+1]) (case-insensitive acgu/t;
+ * anything else never pairs).  The result stays in the context until the next call: *n_pairs_total = number of pairs
+ * (i < j, 1-based like BPMatrix) with probability >= cutoff over all sequences (cutoff <= 0: every pair with a
+ * non-zero probability).  ensemble (optional, [n_seqs]): -kT ln Z in kcal/mol.  dense (optional): for every sequence
+ * an (L+1) x (L+1) row-major table with dense[i*(L+1)+j] = P(i,j) for 1 <= i < j <= L, 0 elsewhere -- the layout of
+ * BPMatrix::table_ as the reference reads it -- concatenated in sequence order. */
+int stemk_fold_bpp(stemk_ctx* ctx, const stemk_fold_model* model, uint32_t n_seqs, const uint64_t* seq_off, const char* text,
+                   double cutoff, uint64_t* n_pairs_total, double* ensemble, double* dense);
+/* The pair lists of the last stemk_fold_bpp: pair_off[n_seqs + 1], then bi / bj / bp of *n_pairs_total entries, per
+ * sequence in ascending (i, j) -- the sparse per-row lists the front end (host/frontend.cpp: Profiler + DAGBuilder)
+ * consumes -- and unpaired (optional, one entry per character of text): max(0, 1 - sum_j P(i,j)) over ALL pairs, not
+ * only the listed ones (Profiler's nbp_, stem_kernel_lite/data.cpp:94-123). */
+int stemk_fold_fetch(stemk_ctx* ctx, uint64_t* pair_off, uint32_t* bi, uint32_t* bj, double* bp, double* unpaired);
+
 /* Text of kernel-matrix rows in the reference's output format -- KernelMatrix::print (kernel_matrix.cpp:756-770)
  * and Output::kernel_output (framework.cpp:190-204): one line "<label> 0:<cnt> 1:<v> 2:<v> ... \n" per row, every
  * value printed like operator<<(std::ostream&, double) with default flags ("%g").  m: n_rows x n_cols with row

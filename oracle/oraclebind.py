@@ -41,6 +41,10 @@ def lib():
         L.oracle_nstem_pairs.argtypes = [vp, vp, vp, C.c_size_t, vp, vp, vp]
         L.oracle_nstem_pairs_banded.argtypes = [vp, C.c_uint, vp, vp, C.c_size_t, vp, vp, vp]
         L.oracle_nstem_pairs_windows.argtypes = [vp, vp, vp, C.c_size_t, vp, vp, vp, vp, vp, vp]
+        L.oracle_fold_bpp.argtypes = [vp, C.c_char_p, C.c_uint32, vp, vp, vp]
+        L.oracle_fold_model_default.argtypes = [vp]
+        L.oracle_fold_default_scale.restype = C.c_double
+        L.oracle_fold_default_scale.argtypes = [C.c_double]
         _lib = L
     return _lib
 
@@ -151,3 +155,32 @@ def nstem_pairs_windows(params, x, y, xi, yi, windows):
     lib().oracle_nstem_pairs_windows(_p(params), _p(cx), _p(cy), len(xi), xi.ctypes.data, yi.ctypes.data, off.ctypes.data,
                                      lo.ctypes.data, hi.ctypes.data, out.ctypes.data)
     return out
+
+
+class FoldModel(C.Structure):
+    """stemk_fold_model of include/stemk.h."""
+    _fields_ = [("temperature", C.c_double), ("pf_scale", C.c_double), ("no_gu", C.c_int32), ("pad_", C.c_int32),
+                ("stack", C.c_double * 8 * 8), ("hairpin", C.c_double * 31), ("bulge", C.c_double * 31),
+                ("interior", C.c_double * 31), ("lxc", C.c_double), ("mismatch_h", C.c_double * 5 * 5 * 8),
+                ("mismatch_i", C.c_double * 5 * 5 * 8), ("dangle5", C.c_double * 5 * 8), ("dangle3", C.c_double * 5 * 8),
+                ("ninio", C.c_double), ("max_ninio", C.c_double), ("terminal_au", C.c_double), ("ml_closing", C.c_double),
+                ("ml_intern", C.c_double * 8), ("ml_base", C.c_double)]
+
+
+def fold_model_default():
+    m = FoldModel()
+    lib().oracle_fold_model_default(_p(m))
+    return m
+
+
+def fold_bpp(model, seq):
+    """(dense (L+1)x(L+1) table with P(i,j) at [i,j], 1-based i<j; ensemble free energy; unpaired[L]) of one sequence
+    (oracle/stemk_fold_oracle.c: McCaskill restated; parity with ViennaRNA unpinned)."""
+    n = len(seq)
+    dense = np.zeros((n + 1, n + 1))
+    unp = np.zeros(n)
+    ens = C.c_double(0.0)
+    rc = lib().oracle_fold_bpp(_p(model), seq.encode(), n, dense.ctypes.data, _p(ens), unp.ctypes.data)
+    if rc != 0:
+        raise FloatingPointError("partition function out of range under this pf_scale")
+    return dense, ens.value, unp

@@ -35,7 +35,8 @@ def make_params(kind, loop_gap=0.2, beta=0.3, stack=1.3, covar=0.8, gap=0.8, alp
 EXPORTS = ["stemk_version", "stemk_device_count", "stemk_create", "stemk_set_option", "stemk_destroy", "stemk_last_error", "stemk_upload",
            "stemk_set_free", "stemk_set_size", "stemk_set_stats", "stemk_set_device_bytes", "stemk_gram", "stemk_cross", "stemk_diag", "stemk_pairs",
            "stemk_pairs_device", "stemk_assemble_device", "stemk_pair_cost", "stemk_stats_reset", "stemk_stats_get", "stemk_fp64_peak", "stemk_format_rows", "stemk_format_values", "stemk_bpla_pairs", "stemk_bpla_gradients", "stemk_nstem_pairs", "stemk_nstem_pairs_banded", "stemk_nstem_pairs_windows",
-           "stemk_set_clone", "stemk_upload_multi", "stemk_gram_multi", "stemk_set_export_bytes", "stemk_set_export", "stemk_set_import"]
+           "stemk_set_clone", "stemk_upload_multi", "stemk_gram_multi", "stemk_set_export_bytes", "stemk_set_export", "stemk_set_import",
+           "stemk_fold_model_default", "stemk_fold_bpp", "stemk_fold_fetch"]
 
 _lib = None
 
@@ -88,5 +89,8 @@ def lib():
         L.stemk_set_import.argtypes = [vp, vp, C.c_uint64, C.POINTER(vp)]
         L.stemk_format_values.restype = sz
         L.stemk_format_values.argtypes = [vp, sz, vp, sz]
+        L.stemk_fold_model_default.argtypes = [vp]
+        L.stemk_fold_bpp.argtypes = [vp, vp, u32, vp, C.c_char_p, C.c_double, C.POINTER(C.c_uint64), vp, vp]
+        L.stemk_fold_fetch.argtypes = [vp, vp, vp, vp, vp, vp]
         _lib = L
     return _lib

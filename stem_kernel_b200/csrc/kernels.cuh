@@ -156,6 +156,14 @@ cudaError_t run_nstem(const stemk_nstem_params& p, const stemk_nstem_set& x, con
                       const uint32_t* xi, const uint32_t* yi, double* out, uint32_t band, int sm_count, size_t smem_optin,
                       cudaStream_t stream, std::string* err,   // band > 0: partial_dp with the band-only constraints
                       const uint32_t* win_off = nullptr, const uint32_t* c_low = nullptr, const uint32_t* c_high = nullptr);   // or the caller's per-row windows
+// base-pair probabilities (fold.cu): host buffers in, host vectors out, synchronous on `stream`
+struct FoldResult {
+  std::vector<uint64_t> pair_off;     // [n_seqs + 1]
+  std::vector<uint32_t> bi, bj;       // 1-based, i < j, per sequence in ascending (i, j)
+  std::vector<double> bp, unpaired, ensemble, dense;
+};
+cudaError_t run_fold(const stemk_fold_model& m, uint32_t n_seqs, const uint64_t* seq_off, const char* text, double cutoff,
+                     bool want_dense, int sm_count, cudaStream_t stream, FoldResult* res, std::string* err);
 cudaError_t launch_fp64_peak(double* sink, int grid, int block, int iters, cudaStream_t stream);
 
 }  // namespace stemk

@@ -81,6 +81,8 @@ struct stemk_ctx {
   cudaEvent_t stage_ev[2] = {nullptr, nullptr};
   unsigned long long* d_bucket = nullptr;  // count[16] | start[16] | queue heads[16]
   int use_fast = 1;                        // stemk_set_option(STEMK_OPT_FORCE_GENERAL, 1) routes every pair to the general stem kernel
+  FoldResult fold;                         // result of the last stemk_fold_bpp
+  uint32_t fold_n = 0;
   int force_unstaged = 0;                  // stemk_set_option(STEMK_OPT_FORCE_UNSTAGED, 1): the general kernel's pairs all run unstaged
   int timing = 0;                          // stemk_set_option(STEMK_OPT_TIMING, 1): host-side breakdown of the calls on stderr
   std::string err;
@@ -1211,6 +1213,75 @@ inline char* put_g(char* p, double v) {
 }
 inline char* put_u(char* p, uint32_t v) { return std::to_chars(p, p + 12, v).ptr; }
 }  // namespace
+
+// -------------------------------------------------------------------------- base-pair probabilities (front end)
+void stemk_fold_model_default(stemk_fold_model* m) {
+  if (!m) return;
+  static const double stack[6][6] = {{-2.4, -3.3, -2.1, -1.4, -2.1, -2.1}, {-3.3, -3.4, -2.5, -1.5, -2.2, -2.4},
+                                     {-2.1, -2.5, 1.3, -0.5, -1.4, -1.3},  {-1.4, -1.5, -0.5, 0.3, -0.6, -1.0},
+                                     {-2.1, -2.2, -1.4, -0.6, -1.1, -0.9}, {-2.1, -2.4, -1.3, -1.0, -0.9, -1.3}};
+  static const double hp[31] = {99, 99, 99, 5.7, 5.6, 5.6, 5.4, 5.9, 5.6, 6.4, 6.5, 6.6, 6.7, 6.78, 6.86, 6.94,
+                                7.01, 7.07, 7.13, 7.19, 7.25, 7.3, 7.35, 7.4, 7.44, 7.49, 7.53, 7.57, 7.61, 7.65, 7.69};
+  static const double bl[31] = {99, 3.8, 2.8, 3.2, 3.6, 4.0, 4.4, 4.59, 4.7, 4.8, 4.9, 5.0, 5.1, 5.2, 5.3, 5.4,
+                                5.5, 5.6, 5.7, 5.8, 5.9, 6.0, 6.1, 6.2, 6.3, 6.4, 6.5, 6.6, 6.7, 6.8, 6.9};
+  static const double il[31] = {99, 99, 4.1, 5.1, 1.7, 1.8, 2.0, 2.2, 2.3, 2.4, 2.5, 2.6, 2.7, 2.8, 2.9, 3.0,
+                                3.1, 3.2, 3.3, 3.4, 3.5, 3.6, 3.7, 3.8, 3.9, 4.0, 4.1, 4.2, 4.3, 4.4, 4.5};
+  std::memset(m, 0, sizeof(*m));
+  m->temperature = 37.0;
+  m->pf_scale = -1.0;
+  for (int a = 1; a <= 6; ++a) for (int b = 1; b <= 6; ++b) m->stack[a][b] = stack[a - 1][b - 1];
+  for (int u = 0; u <= 30; ++u) { m->hairpin[u] = hp[u]; m->bulge[u] = bl[u]; m->interior[u] = il[u]; }
+  m->lxc = 1.07856;
+  for (int t = 1; t <= 6; ++t)
+    for (int a = 0; a < 5; ++a) {
+      for (int b = 0; b < 5; ++b) {
+        m->mismatch_h[t][a][b] = -(0.3 + 0.1 * ((t + 2 * a + 3 * b) % 9));
+        m->mismatch_i[t][a][b] = -(0.1 * ((2 * t + a + 4 * b) % 8)) + (t > 2 ? 0.7 : 0.0);
+      }
+      m->dangle5[t][a] = a ? -(0.1 + 0.05 * ((t + 3 * a) % 6)) : 0.0;
+      m->dangle3[t][a] = a ? -(0.2 + 0.1 * ((2 * t + a) % 7)) : 0.0;
+    }
+  m->ninio = 0.5; m->max_ninio = 3.0;
+  m->terminal_au = 0.5;
+  m->ml_closing = 3.4;
+  for (int t = 0; t < 8; ++t) m->ml_intern[t] = 0.4 + (t > 2 ? 0.5 : 0.0);
+  m->ml_base = 0.0;
+}
+
+int stemk_fold_bpp(stemk_ctx* ctx, const stemk_fold_model* model, uint32_t n_seqs, const uint64_t* seq_off, const char* text,
+                   double cutoff, uint64_t* n_pairs_total, double* ensemble, double* dense) {
+  if (!ctx || !model || (n_seqs && (!seq_off || (!text && seq_off[n_seqs])))) return fail(ctx, STEMK_ERR_ARG, "null argument");
+  if (ctx->device == STEMK_DEVICE_NONE) return no_device(ctx);
+  if (!(model->temperature > -273.0) || !std::isfinite(model->temperature)) return fail(ctx, STEMK_ERR_ARG, "fold model: temperature");
+  CU(cudaSetDevice(ctx->device));
+  std::string err;
+  ctx->fold_n = 0;
+  cudaError_t e;
+  try { e = run_fold(*model, n_seqs, seq_off, text, cutoff, dense != nullptr, ctx->sm_count, ctx->stream, &ctx->fold, &err); }
+  catch (const std::bad_alloc&) { return fail(ctx, STEMK_ERR_NOMEM, "stemk_fold_bpp: out of host memory"); }
+  if (e != cudaSuccess) {
+    if (err.empty()) return cuda_fail(ctx, e, "base-pair probability kernel");
+    return fail(ctx, e == cudaErrorMemoryAllocation ? STEMK_ERR_NOMEM : STEMK_ERR_ARG, err);
+  }
+  ctx->fold_n = n_seqs;
+  ctx->launches += 1;
+  if (n_pairs_total) *n_pairs_total = ctx->fold.pair_off.empty() ? 0 : ctx->fold.pair_off.back();
+  if (ensemble) std::copy(ctx->fold.ensemble.begin(), ctx->fold.ensemble.end(), ensemble);
+  if (dense) { std::copy(ctx->fold.dense.begin(), ctx->fold.dense.end(), dense); ctx->fold.dense.clear(); ctx->fold.dense.shrink_to_fit(); }
+  return STEMK_OK;
+}
+
+int stemk_fold_fetch(stemk_ctx* ctx, uint64_t* pair_off, uint32_t* bi, uint32_t* bj, double* bp, double* unpaired) {
+  if (!ctx) return fail(ctx, STEMK_ERR_ARG, "null argument");
+  const FoldResult& r = ctx->fold;
+  if (r.pair_off.size() != (size_t)ctx->fold_n + 1) return fail(ctx, STEMK_ERR_ARG, "stemk_fold_fetch: no result (call stemk_fold_bpp first)");
+  if (pair_off) std::copy(r.pair_off.begin(), r.pair_off.end(), pair_off);
+  if (bi) std::copy(r.bi.begin(), r.bi.end(), bi);
+  if (bj) std::copy(r.bj.begin(), r.bj.end(), bj);
+  if (bp) std::copy(r.bp.begin(), r.bp.end(), bp);
+  if (unpaired) std::copy(r.unpaired.begin(), r.unpaired.end(), unpaired);
+  return STEMK_OK;
+}
 
 size_t stemk_format_rows(const double* m, uint32_t n_rows, uint32_t n_cols, size_t ld, const char* const* labels,
                          uint32_t first_cnt, int n_threads, char* out, size_t cap) {
