@@ -729,6 +729,31 @@ def secondary_figures(local_rank):
     secondary["naive_stem"] = {"workload": "naive stem kernel (full_dp, probability tables, threshold 0.01) on the C1 records",
                                "pairs": len(nxi), "e2e_pairs_per_s": len(nxi) / nw,
                                "e2e_gcells": float(np.sum(ln1[nxi] ** 2 * ln1[nyi] ** 2) / 4.0) / nw / 1e9}
+    # base-pair probabilities of the C3 sequences on the device (stemk_fold_bpp, host buffers in and
+    # out); beside it the oracle restatement of the same recursions on one host core (the reference serialises its
+    # ViennaRNA calls under a mutex, common/bpmatrix.cpp:152-155).  Parity with ViennaRNA itself is unpinned.
+    from stem_kernel_b200 import fold
+    from oracle import oraclebind as O
+    seqs3 = [r["rows"][0] for r in synth.make_config(3)]
+    fm = fold.default_model()
+    folder = fold.Folder(ctx2)
+    folder.bpp(seqs3[:64], fm, cutoff=TH / 10)
+    t0 = time.perf_counter()
+    fr = folder.bpp(seqs3, fm, cutoff=TH / 10)
+    fw = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    worst = 0.0
+    for k in range(0, len(seqs3), len(seqs3) // 8):
+        want = O.fold_bpp(fm, seqs3[k])[0]
+        i_, j_, p_ = fr.pairs[k]
+        worst = max(worst, float(np.max(np.abs(p_ - want[i_, j_]) / want[i_, j_])) if len(p_) else 0.0)
+    ow = (time.perf_counter() - t0) / 8
+    nt3 = float(sum(len(q) for q in seqs3))
+    secondary["fold"] = {"workload": "McCaskill base-pair probabilities of the C3 sequences (150-300 nt), stand-in loop model, cut-off 0.001",
+                         "sequences": len(seqs3), "kernel_ms": fr.kernel_ms, "kernel_seqs_per_s": len(seqs3) / (fr.kernel_ms * 1e-3),
+                         "e2e_seqs_per_s": len(seqs3) / fw, "e2e_nt_per_s": nt3 / fw,
+                         "cpu_port_seqs_per_s_1core": 1.0 / ow, "parity_max_rel_err_8_sequences": worst,
+                         "parity": "unpinned against ViennaRNA (absent); device = oracle restatement"}
     ctx2.close()
     return secondary
 

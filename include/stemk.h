@@ -350,6 +350,8 @@ int stemk_fold_bpp(stemk_ctx* ctx, const stemk_fold_model* model, uint32_t n_seq
  * consumes -- and unpaired (optional, one entry per character of text): max(0, 1 - sum_j P(i,j)) over ALL pairs, not
  * only the listed ones (Profiler's nbp_, stem_kernel_lite/data.cpp:94-123). */
 int stemk_fold_fetch(stemk_ctx* ctx, uint64_t* pair_off, uint32_t* bi, uint32_t* bj, double* bp, double* unpaired);
+/* Device time (ms, CUDA events on the context's stream) of the kernel of the last stemk_fold_bpp. */
+double stemk_fold_last_ms(const stemk_ctx* ctx);
 
 /* Text of kernel-matrix rows in the reference's output format -- KernelMatrix::print (kernel_matrix.cpp:756-770)
  * and Output::kernel_output (framework.cpp:190-204): one line "<label> 0:<cnt> 1:<v> 2:<v> ... \n" per row, every

@@ -11,7 +11,7 @@ with fold.Folder() as f:
     f.bpp(seqs[:64], m, cutoff=1e-3)
     for cut in (1e-2, 1e-4):
         t = time.time(); r = f.bpp(seqs, m, cutoff=cut); dt = time.time() - t
-        print(f"n={n} cutoff={cut} {dt*1e3:.1f} ms  {n/dt:.0f} seq/s  pairs listed {sum(len(p[0]) for p in r.pairs)}", flush=True)
+        print(f"n={n} cutoff={cut} call {dt*1e3:.1f} ms ({n/dt:.0f} seq/s), kernel {r.kernel_ms:.1f} ms ({n/r.kernel_ms*1e3:.0f} seq/s)  pairs listed {sum(len(p[0]) for p in r.pairs)}", flush=True)
 if len(sys.argv) > 2:
     from oracle import oraclebind as O
     t = time.time()

@@ -36,7 +36,7 @@ EXPORTS = ["stemk_version", "stemk_device_count", "stemk_create", "stemk_set_opt
            "stemk_set_free", "stemk_set_size", "stemk_set_stats", "stemk_set_device_bytes", "stemk_gram", "stemk_cross", "stemk_diag", "stemk_pairs",
            "stemk_pairs_device", "stemk_assemble_device", "stemk_pair_cost", "stemk_stats_reset", "stemk_stats_get", "stemk_fp64_peak", "stemk_format_rows", "stemk_format_values", "stemk_bpla_pairs", "stemk_bpla_gradients", "stemk_nstem_pairs", "stemk_nstem_pairs_banded", "stemk_nstem_pairs_windows",
            "stemk_set_clone", "stemk_upload_multi", "stemk_gram_multi", "stemk_set_export_bytes", "stemk_set_export", "stemk_set_import",
-           "stemk_fold_model_default", "stemk_fold_bpp", "stemk_fold_fetch"]
+           "stemk_fold_model_default", "stemk_fold_bpp", "stemk_fold_fetch", "stemk_fold_last_ms"]
 
 _lib = None
 
@@ -92,5 +92,7 @@ def lib():
         L.stemk_fold_model_default.argtypes = [vp]
         L.stemk_fold_bpp.argtypes = [vp, vp, u32, vp, C.c_char_p, C.c_double, C.POINTER(C.c_uint64), vp, vp]
         L.stemk_fold_fetch.argtypes = [vp, vp, vp, vp, vp, vp]
+        L.stemk_fold_last_ms.restype = C.c_double
+        L.stemk_fold_last_ms.argtypes = [vp]
         _lib = L
     return _lib

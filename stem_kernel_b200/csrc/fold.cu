@@ -36,12 +36,18 @@
 
 #include "kernels.cuh"
 
+#ifndef FOLD_THREADS
+#define FOLD_THREADS 256
+#endif
+#ifndef FOLD_CTAS
+#define FOLD_CTAS 4
+#endif
+
 namespace stemk {
 
 namespace {
 
-constexpr int kTurn = 3, kMaxLoop = 30, kFoldThreads = 512, kFoldWarps = kFoldThreads / 32;
-constexpr int kCombos = (kMaxLoop + 1) * (kMaxLoop + 2) / 2;   // (u1, u2) with u1 + u2 <= 30
+constexpr int kTurn = 3, kMaxLoop = 30, kFoldThreads = FOLD_THREADS, kFoldWarps = kFoldThreads / 32;
 constexpr int kTables = 10;
 
 struct FoldTab {          // Boltzmann factors of the model; *S = with the scaling of the loop's own nucleotides
@@ -98,22 +104,68 @@ __device__ __forceinline__ double warp_sum_f(double v) {
   return v;
 }
 
-// (i,j) of type `type` closes, (k,l) of type tkl is the inner pair; S = base codes (1-based)
-__device__ __forceinline__ double il_weight(const FoldTab& T, const uint8_t* S, int i, int j, int k, int l, int type, int tkl) {
-  const int u1 = k - i - 1, u2 = j - l - 1, t2 = d_rtype(tkl);
-  if (u1 == 0 && u2 == 0) return T.stackS[type][t2];
-  if (u1 == 0 || u2 == 0) {
-    const int u = u1 + u2;
-    return T.bulgeS[u] * (u == 1 ? T.stackB[type][t2] : T.tau[type] * T.tau[t2]);
+// a pair of type `type` closes the loop, a pair of type tkl is the inner pair; mm_close / mm_inner = the interior-loop mismatch
+// factors of the two pairs, mmI[type][S[i+1]][S[j-1]] and mmI[rtype(tkl)][S[l+1]][S[k-1]]
+__device__ __forceinline__ double il_weight(const FoldTab& T, int u1, int u2, int type, int tkl, double mm_close, double mm_inner) {
+  const int t2 = d_rtype(tkl);
+  if (u1 != 0 && u2 != 0) {
+    const int d = u1 > u2 ? u1 - u2 : u2 - u1;
+    return T.interiorS[u1 + u2] * T.ninioB[d] * (mm_close * mm_inner);
   }
-  const int d = u1 > u2 ? u1 - u2 : u2 - u1;
-  return T.interiorS[u1 + u2] * T.ninioB[d] * T.mmI[type][S[i + 1]][S[j - 1]] * T.mmI[t2][S[l + 1]][S[k - 1]];
+  const int u = u1 + u2;
+  if (u == 0) return T.stackS[type][t2];
+  return T.bulgeS[u] * (u == 1 ? T.stackB[type][t2] : T.tau[type] * T.tau[t2]);
 }
 
-__global__ void __launch_bounds__(kFoldThreads, 2) fold_kernel(const FoldLaunch P) {
+// Sum over the interior loops (stacks and bulges included) of one cell.
+// OUTSIDE = false: (i,j) closes, tab = Qb of the inner pair (k,l) = (i+1+u1, j-1-u2);
+// OUTSIDE = true:  (i,j) is the inner pair, tab = Ob of the closing pair (p,q) = (i-1-u1, j+1+u2).
+// Lanes <-> u2, one row (k or p) of the tables per step, so that a step reads <= 31 CONSECUTIVE pair types and table
+// entries: with lanes over arbitrary (u1, u2) combinations every load touched 32 different lines and the kernel was
+// bound by the L1 tag stage (profiles/r02_fold_ncu_summary.txt).  kIlUnroll rows are taken at a time: all their pair
+// types are asked for first, then all their table entries (the two loads of a row depend on each other).
+#ifndef FOLD_UNROLL
+#define FOLD_UNROLL 4
+#endif
+constexpr int kIlUnroll = FOLD_UNROLL;
+template <bool OUTSIDE>
+__device__ __forceinline__ double interior_sum(const FoldTab& T, const uint8_t* S, const uint8_t* __restrict__ ty,
+                                               const double* __restrict__ tab, int W, int n, int i, int j, int type, int lane) {
+  double acc = 0.0;
+  const double mm_ij = T.mmI[OUTSIDE ? d_rtype(type) : type][S[OUTSIDE ? j + 1 : i + 1]][S[OUTSIDE ? i - 1 : j - 1]];   // this cell's own mismatch factor
+  const int u1_end = min(kMaxLoop, OUTSIDE ? i - 2 : j - i - 3 - kTurn);   // last u1 with a row inside the sequence / a pair that can close
+  const int u2 = lane;
+  const int b = OUTSIDE ? j + 1 + u2 : j - 1 - u2;
+  for (int u0 = 0; u0 <= u1_end; u0 += kIlUnroll) {
+    uint32_t at[kIlUnroll];
+    uint8_t tp[kIlUnroll];
+    double v[kIlUnroll];
+#pragma unroll
+    for (int u = 0; u < kIlUnroll; ++u) {
+      const int u1 = u0 + u;
+      const int a = OUTSIDE ? i - 1 - u1 : i + 1 + u1;
+      const bool ok = u1 <= u1_end && u2 <= kMaxLoop - u1 && (OUTSIDE ? b <= n : b - a > kTurn);
+      at[u] = (uint32_t)(a * W + b);
+      tp[u] = ok ? ty[at[u]] : (uint8_t)0;
+    }
+#pragma unroll
+    for (int u = 0; u < kIlUnroll; ++u) v[u] = tp[u] ? tab[at[u]] : 0.0;
+#pragma unroll
+    for (int u = 0; u < kIlUnroll; ++u)
+      if (tp[u]) {
+        const int u1 = u0 + u;
+        const int a = OUTSIDE ? i - 1 - u1 : i + 1 + u1;
+        // il_weight(closing type, inner type, closing pair's mismatch factor, inner pair's)
+        acc += v[u] * (OUTSIDE ? il_weight(T, u1, u2, tp[u], type, T.mmI[tp[u]][S[a + 1]][S[b - 1]], mm_ij)
+                               : il_weight(T, u1, u2, type, tp[u], mm_ij, T.mmI[d_rtype(tp[u])][S[b + 1]][S[a - 1]]));
+      }
+  }
+  return acc;
+}
+
+__global__ void __launch_bounds__(kFoldThreads, FOLD_CTAS) fold_kernel(const FoldLaunch P) {
   extern __shared__ __align__(16) unsigned char dyn[];   // base codes of the sequence in flight: cap bytes
   __shared__ FoldTab T;
-  __shared__ uint16_t s_combo[kCombos];
   __shared__ unsigned long long s_seq, s_base;
   __shared__ uint32_t s_wsum[kFoldWarps];
   __shared__ uint32_t s_run;
@@ -123,11 +175,6 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_kernel(const FoldLaunch 
     const double* src = reinterpret_cast<const double*>(P.tab);
     double* dst = reinterpret_cast<double*>(&T);
     for (int t = tid; t < (int)(sizeof(FoldTab) / sizeof(double)); t += kFoldThreads) dst[t] = src[t];
-    for (int t = tid; t < kCombos; t += kFoldThreads) {   // t -> (u1, u2), u1-major
-      int u1 = 0, rest = t;
-      while (rest > kMaxLoop - u1) { rest -= kMaxLoop - u1 + 1; ++u1; }
-      s_combo[t] = (uint16_t)((u1 << 8) | rest);
-    }
   }
   const size_t cap2 = (size_t)P.cap * P.cap;
   double* base = P.scratch + (size_t)blockIdx.x * P.scratch_stride;
@@ -179,16 +226,7 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_kernel(const FoldLaunch 
         const int type = ty[IX(i, j)];
         double qb = 0.0;
         if (type) {
-          double acc = 0.0;
-          // interior loops, stacks and bulges: lanes over (u1, u2)
-          for (int c = lane; c < kCombos; c += 32) {
-            const int u1 = s_combo[c] >> 8, u2 = s_combo[c] & 0xff;
-            const int k = i + 1 + u1, l = j - 1 - u2;
-            if (l - k > kTurn) {
-              const int tkl = ty[IX(k, l)];
-              if (tkl) acc += Qb[IX(k, l)] * il_weight(T, S, i, j, k, l, type, tkl);
-            }
-          }
+          double acc = interior_sum<false>(T, S, ty, Qb, W, n, i, j, type, lane);
           // multiloop: sum_k Qm(i+1,k-1) Qm1(k,j-1)
           double ml = 0.0;
           const double* qm_row = Qm + IX(i + 1, 0);
@@ -236,15 +274,7 @@ __global__ void __launch_bounds__(kFoldThreads, 2) fold_kernel(const FoldLaunch 
         const int j = i + d;
         const int type = d > kTurn ? ty[IX(i, j)] : 0;
         if (type) {
-          double acc = 0.0;
-          for (int c = lane; c < kCombos; c += 32) {
-            const int u1 = s_combo[c] >> 8, u2 = s_combo[c] & 0xff;
-            const int p = i - 1 - u1, q = j + 1 + u2;
-            if (p >= 1 && q <= n) {
-              const int tpq = ty[IX(p, q)];
-              if (tpq) acc += Ob[IX(p, q)] * il_weight(T, S, p, q, i, j, tpq, type);
-            }
-          }
+          double acc = interior_sum<true>(T, S, ty, Ob, W, n, i, j, type, lane);
           double ml = 0.0;
           const double* qmt = QmT + IX(i - 1, 0);   // QmT[i-1][p+1] = Qm(p+1, i-1)
           const double* at = AT + IX(j, 0);
@@ -352,7 +382,8 @@ uint8_t base_code(char c) {
 }  // namespace
 
 cudaError_t run_fold(const stemk_fold_model& m, uint32_t n_seqs, const uint64_t* seq_off, const char* text, double cutoff,
-                     bool want_dense, int sm_count, cudaStream_t stream, FoldResult* res, std::string* err) {
+                     bool want_dense, int sm_count, cudaStream_t stream, FoldResult* res, std::string* err, void** scratch_p,
+                     size_t* scratch_bytes) {
   res->pair_off.assign((size_t)n_seqs + 1, 0);
   res->bi.clear(); res->bj.clear(); res->bp.clear(); res->unpaired.clear(); res->ensemble.assign(n_seqs, 0.0); res->dense.clear();
   if (n_seqs == 0) return cudaSuccess;
@@ -430,14 +461,22 @@ cudaError_t run_fold(const stemk_fold_model& m, uint32_t n_seqs, const uint64_t*
   void *d_tab, *d_hp, *d_sp, *d_up, *d_codes, *d_off, *d_order, *d_cnt, *d_start, *d_count, *d_i, *d_j, *d_p, *d_unp, *d_ens, *d_status,
       *d_scratch, *d_dense = nullptr, *d_doff = nullptr;
   const unsigned long long stride = ((unsigned long long)kTables * cap * cap + ((unsigned long long)cap * cap + 7) / 8 + 1) & ~1ull;
-  int grid = (int)std::min<uint64_t>(n_seqs, (uint64_t)sm_count * 2);
+  int grid = (int)std::min<uint64_t>(n_seqs, (uint64_t)sm_count * FOLD_CTAS);
   grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)grid, ((uint64_t)8 << 30) / (stride * sizeof(double))));
   bool ok = upload(&d_tab, &T, sizeof(T)) && upload(&d_hp, hpS.data(), hpS.size() * 8) && upload(&d_sp, sp.data(), sp.size() * 8) &&
             upload(&d_up, up.data(), up.size() * 8) && upload(&d_codes, codes.data(), codes.size()) &&
             upload(&d_off, seq_off, ((size_t)n_seqs + 1) * 8) && upload(&d_order, order.data(), (size_t)n_seqs * 4) &&
             dalloc(&d_cnt, 16) && dalloc(&d_start, (size_t)n_seqs * 8) && dalloc(&d_count, (size_t)n_seqs * 4) &&
             dalloc(&d_i, out_cap * 4) && dalloc(&d_j, out_cap * 4) && dalloc(&d_p, out_cap * 8) && dalloc(&d_unp, n_chars * 8) &&
-            dalloc(&d_ens, (size_t)n_seqs * 8) && dalloc(&d_status, (size_t)n_seqs * 4) && dalloc(&d_scratch, stride * sizeof(double) * grid);
+            dalloc(&d_ens, (size_t)n_seqs * 8) && dalloc(&d_status, (size_t)n_seqs * 4);
+  if (ok && *scratch_bytes < stride * sizeof(double) * grid) {   // the DP tables of the sequences in flight: kept by the context
+    if (*scratch_p) cudaFree(*scratch_p);
+    *scratch_p = nullptr; *scratch_bytes = 0;
+    e = cudaMalloc(scratch_p, stride * sizeof(double) * grid);
+    ok = e == cudaSuccess;
+    if (ok) *scratch_bytes = stride * sizeof(double) * grid;
+  }
+  d_scratch = *scratch_p;
   if (ok && want_dense) ok = dalloc(&d_dense, dense_total * 8) && upload(&d_doff, dense_off.data(), (size_t)n_seqs * 8);
   if (ok) { e = cudaMemsetAsync(d_cnt, 0, 16, stream); ok = e == cudaSuccess; }
   if (!ok) { cleanup(); if (err && e == cudaErrorMemoryAllocation) *err = "base-pair probabilities: out of device memory (split the batch or raise the cut-off)"; return e; }
@@ -449,8 +488,12 @@ cudaError_t run_fold(const stemk_fold_model& m, uint32_t n_seqs, const uint64_t*
   L.out_p = (double*)d_p; L.unpaired = (double*)d_unp; L.ensemble = (double*)d_ens; L.status = (int*)d_status;
   L.dense = (double*)d_dense; L.dense_off = (const uint64_t*)d_doff;
   const size_t smem = ((size_t)cap + 15) & ~(size_t)15;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEventCreate(&ev0); cudaEventCreate(&ev1);
+  cudaEventRecord(ev0, stream);
   fold_kernel<<<grid, kFoldThreads, smem, stream>>>(L);
   e = cudaGetLastError();
+  cudaEventRecord(ev1, stream);
   // ---- results back to the host, pair lists put in sequence order
   std::vector<uint64_t> start(n_seqs);
   std::vector<uint32_t> count(n_seqs);
@@ -468,6 +511,9 @@ cudaError_t run_fold(const stemk_fold_model& m, uint32_t n_seqs, const uint64_t*
     e = cudaMemcpyAsync(res->dense.data(), d_dense, dense_total * 8, cudaMemcpyDeviceToHost, stream);
   }
   if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  res->kernel_ms = 0.0;
+  if (e == cudaSuccess) { float ms = 0; if (cudaEventElapsedTime(&ms, ev0, ev1) == cudaSuccess) res->kernel_ms = ms; }
+  cudaEventDestroy(ev0); cudaEventDestroy(ev1);
   if (e != cudaSuccess) { cleanup(); return e; }
   const uint64_t total = cnt[1];
   std::vector<uint32_t> ti(total), tj(total);

@@ -161,9 +161,11 @@ struct FoldResult {
   std::vector<uint64_t> pair_off;     // [n_seqs + 1]
   std::vector<uint32_t> bi, bj;       // 1-based, i < j, per sequence in ascending (i, j)
   std::vector<double> bp, unpaired, ensemble, dense;
+  double kernel_ms = 0;               // device time of the fold kernel (CUDA events on the launching stream)
 };
 cudaError_t run_fold(const stemk_fold_model& m, uint32_t n_seqs, const uint64_t* seq_off, const char* text, double cutoff,
-                     bool want_dense, int sm_count, cudaStream_t stream, FoldResult* res, std::string* err);
+                     bool want_dense, int sm_count, cudaStream_t stream, FoldResult* res, std::string* err, void** scratch_p,
+                     size_t* scratch_bytes);   // *scratch_p: device buffer the caller keeps between calls (grown here)
 cudaError_t launch_fp64_peak(double* sink, int grid, int block, int iters, cudaStream_t stream);
 
 }  // namespace stemk

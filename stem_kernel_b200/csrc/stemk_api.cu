@@ -69,7 +69,7 @@ struct stemk_ctx {
   double* d_pair_tab = nullptr;
   double* d_subst = nullptr;
   unsigned long long* d_counter = nullptr;
-  DevBuf scratch, scratch_big, carry, tmp_stem, tmp_str, idx_x, idx_y, vals, matrix, order, rowacc;
+  DevBuf scratch, scratch_big, fold_scratch, carry, tmp_stem, tmp_str, idx_x, idx_y, vals, matrix, order, rowacc;
   DevBuf perm, offs, diag, selfv, diag_idx, diag_vals, diag_idx2, diag_vals2;
   DevBuf deal_x, deal_y, gathered, undealt;     // stemk_gram_multi: this device's share of the pair list; on device 0 the gather
   cudaEvent_t multi_ev = nullptr;
@@ -88,7 +88,7 @@ struct stemk_ctx {
   std::string err;
   // stats
   uint64_t launches = 0;
-  double stem_ms = 0, string_ms = 0;
+  double stem_ms = 0, string_ms = 0, fold_ms = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // launch timings are resolved lazily (stemk_stats_get) so that the launch path never blocks the host
   struct Timed { cudaEvent_t a, b; int which; };
@@ -254,7 +254,7 @@ void stemk_destroy(stemk_ctx* c) {
   if (c->device == STEMK_DEVICE_NONE) { delete c; return; }
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  for (DevBuf* b : {&c->scratch, &c->scratch_big, &c->carry, &c->tmp_stem, &c->tmp_str, &c->idx_x, &c->idx_y, &c->vals, &c->matrix, &c->order, &c->rowacc,
+  for (DevBuf* b : {&c->scratch, &c->scratch_big, &c->fold_scratch, &c->carry, &c->tmp_stem, &c->tmp_str, &c->idx_x, &c->idx_y, &c->vals, &c->matrix, &c->order, &c->rowacc,
                     &c->perm, &c->offs, &c->diag, &c->selfv, &c->diag_idx, &c->diag_vals, &c->diag_idx2, &c->diag_vals2,
                     &c->deal_x, &c->deal_y, &c->gathered, &c->undealt}) b->release();
   if (c->multi_ev) cudaEventDestroy(c->multi_ev);
@@ -1257,7 +1257,9 @@ int stemk_fold_bpp(stemk_ctx* ctx, const stemk_fold_model* model, uint32_t n_seq
   std::string err;
   ctx->fold_n = 0;
   cudaError_t e;
-  try { e = run_fold(*model, n_seqs, seq_off, text, cutoff, dense != nullptr, ctx->sm_count, ctx->stream, &ctx->fold, &err); }
+  const auto t0 = std::chrono::steady_clock::now();
+  try { e = run_fold(*model, n_seqs, seq_off, text, cutoff, dense != nullptr, ctx->sm_count, ctx->stream, &ctx->fold, &err,
+                     &ctx->fold_scratch.p, &ctx->fold_scratch.bytes); }
   catch (const std::bad_alloc&) { return fail(ctx, STEMK_ERR_NOMEM, "stemk_fold_bpp: out of host memory"); }
   if (e != cudaSuccess) {
     if (err.empty()) return cuda_fail(ctx, e, "base-pair probability kernel");
@@ -1265,11 +1267,17 @@ int stemk_fold_bpp(stemk_ctx* ctx, const stemk_fold_model* model, uint32_t n_seq
   }
   ctx->fold_n = n_seqs;
   ctx->launches += 1;
+  ctx->fold_ms += ctx->fold.kernel_ms;
+  if (ctx->timing)
+    std::fprintf(stderr, "stemk_fold_bpp: %u sequences, kernel %.1f ms, call %.1f ms\n", n_seqs, ctx->fold.kernel_ms,
+                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
   if (n_pairs_total) *n_pairs_total = ctx->fold.pair_off.empty() ? 0 : ctx->fold.pair_off.back();
   if (ensemble) std::copy(ctx->fold.ensemble.begin(), ctx->fold.ensemble.end(), ensemble);
   if (dense) { std::copy(ctx->fold.dense.begin(), ctx->fold.dense.end(), dense); ctx->fold.dense.clear(); ctx->fold.dense.shrink_to_fit(); }
   return STEMK_OK;
 }
+
+double stemk_fold_last_ms(const stemk_ctx* ctx) { return ctx ? ctx->fold.kernel_ms : 0.0; }
 
 int stemk_fold_fetch(stemk_ctx* ctx, uint64_t* pair_off, uint32_t* bi, uint32_t* bj, double* bp, double* unpaired) {
   if (!ctx) return fail(ctx, STEMK_ERR_ARG, "null argument");

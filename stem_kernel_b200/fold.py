@@ -33,8 +33,8 @@ class FoldResult:
     """pairs[k] = (i, j, p) arrays of sequence k (1-based, i < j, ascending (i, j)); unpaired[k] = per-position
     max(0, 1 - sum_j P); ensemble[k] = -kT ln Z; dense[k] = (L+1) x (L+1) table when asked for."""
 
-    def __init__(self, pairs, unpaired, ensemble, dense):
-        self.pairs, self.unpaired, self.ensemble, self.dense = pairs, unpaired, ensemble, dense
+    def __init__(self, pairs, unpaired, ensemble, dense, kernel_ms=0.0):
+        self.pairs, self.unpaired, self.ensemble, self.dense, self.kernel_ms = pairs, unpaired, ensemble, dense, kernel_ms
 
 
 class Folder:
@@ -83,7 +83,7 @@ class Folder:
                 w = int(lens[k]) + 1
                 dl.append(dn[dpos:dpos + w * w].reshape(w, w))
                 dpos += w * w
-        return FoldResult(pairs, unpaired, ens, dl if dense else None)
+        return FoldResult(pairs, unpaired, ens, dl if dense else None, float(lib.stemk_fold_last_ms(self.ctx.h)))
 
 
 __all__ = ["FoldModel", "FoldResult", "Folder", "default_model", "StemkError"]
