@@ -31,6 +31,7 @@
 // compacted per sequence in ascending (i,j) with a block-wide scan into one output range reserved by a single atomic.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <numeric>
 
@@ -41,6 +42,14 @@
 #endif
 #ifndef FOLD_CTAS
 #define FOLD_CTAS 4
+#endif
+
+#ifdef FOLD_PROF
+#define FP_T(v) const long long v = clock64()
+#define FP_ADD(slot, a, b) do { if (lane == 0) fprof[slot] += (b) - (a); } while (0)
+#else
+#define FP_T(v) do {} while (0)
+#define FP_ADD(slot, a, b) do {} while (0)
 #endif
 
 namespace stemk {
@@ -83,6 +92,7 @@ struct FoldLaunch {
   double* unpaired;           // concatenated like codes
   double* ensemble;           // [n_seqs]
   int* status;                // [n_seqs] 1: partition function out of range
+  unsigned long long* prof;   // FOLD_PROF builds: per-phase cycle counters summed over warps
   double* dense;              // optional
   const uint64_t* dense_off;  // [n_seqs]
 };
@@ -122,8 +132,8 @@ __device__ __forceinline__ double il_weight(const FoldTab& T, int u1, int u2, in
 // OUTSIDE = true:  (i,j) is the inner pair, tab = Ob of the closing pair (p,q) = (i-1-u1, j+1+u2).
 // Lanes <-> u2, one row (k or p) of the tables per step, so that a step reads <= 31 CONSECUTIVE pair types and table
 // entries: with lanes over arbitrary (u1, u2) combinations every load touched 32 different lines and the kernel was
-// bound by the L1 tag stage (profiles/r02_fold_ncu_summary.txt).  kIlUnroll rows are taken at a time: all their pair
-// types are asked for first, then all their table entries (the two loads of a row depend on each other).
+// bound by the L1 tag stage (profiles/r02_fold_ncu_summary.txt).  kIlUnroll rows are taken at a time (one round trip to
+// L2 / DRAM per step: the kernel is bound by the latency of these chains, not by a pipe).
 #ifndef FOLD_UNROLL
 #define FOLD_UNROLL 4
 #endif
@@ -137,19 +147,19 @@ __device__ __forceinline__ double interior_sum(const FoldTab& T, const uint8_t* 
   const int u2 = lane;
   const int b = OUTSIDE ? j + 1 + u2 : j - 1 - u2;
   for (int u0 = 0; u0 <= u1_end; u0 += kIlUnroll) {
-    uint32_t at[kIlUnroll];
     uint8_t tp[kIlUnroll];
     double v[kIlUnroll];
+    // the pair type and the table entry of a combination are asked for TOGETHER (the entry of a non-pair is 0: the
+    // tables are cleared per sequence and only pairs are ever written), one round trip per kIlUnroll rows instead of two
 #pragma unroll
     for (int u = 0; u < kIlUnroll; ++u) {
       const int u1 = u0 + u;
       const int a = OUTSIDE ? i - 1 - u1 : i + 1 + u1;
       const bool ok = u1 <= u1_end && u2 <= kMaxLoop - u1 && (OUTSIDE ? b <= n : b - a > kTurn);
-      at[u] = (uint32_t)(a * W + b);
-      tp[u] = ok ? ty[at[u]] : (uint8_t)0;
+      const uint32_t at = (uint32_t)(a * W + b);
+      tp[u] = ok ? ty[at] : (uint8_t)0;
+      v[u] = ok ? tab[at] : 0.0;
     }
-#pragma unroll
-    for (int u = 0; u < kIlUnroll; ++u) v[u] = tp[u] ? tab[at[u]] : 0.0;
 #pragma unroll
     for (int u = 0; u < kIlUnroll; ++u)
       if (tp[u]) {
@@ -176,6 +186,10 @@ __global__ void __launch_bounds__(kFoldThreads, FOLD_CTAS) fold_kernel(const Fol
     double* dst = reinterpret_cast<double*>(&T);
     for (int t = tid; t < (int)(sizeof(FoldTab) / sizeof(double)); t += kFoldThreads) dst[t] = src[t];
   }
+#ifdef FOLD_PROF
+  long long fprof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  const long long fp_t00 = clock64();
+#endif
   const size_t cap2 = (size_t)P.cap * P.cap;
   double* base = P.scratch + (size_t)blockIdx.x * P.scratch_stride;
   const double* __restrict__ sp = P.sp;
@@ -186,6 +200,7 @@ __global__ void __launch_bounds__(kFoldThreads, FOLD_CTAS) fold_kernel(const Fol
     if (tid == 0) s_seq = atomicAdd(P.counter, 1ull);
     __syncthreads();
     if (s_seq >= P.n_seqs) break;
+    FP_T(t_s0);
     const uint32_t sid = P.order[s_seq];
     const uint64_t c0 = P.seq_off[sid];
     const int n = (int)(P.seq_off[sid + 1] - c0);
@@ -219,14 +234,20 @@ __global__ void __launch_bounds__(kFoldThreads, FOLD_CTAS) fold_kernel(const Fol
     }
     __syncthreads();
 
+    FP_T(t_s1);
+    FP_ADD(0, t_s0, t_s1);
     // ---------------------------------------------------------------- inside
     for (int d = kTurn + 1; d < n; ++d) {
+      FP_T(t_d0);
       for (int i = 1 + warp; i + d <= n; i += kFoldWarps) {
         const int j = i + d;
+        FP_T(t_c0);
         const int type = ty[IX(i, j)];
         double qb = 0.0;
         if (type) {
           double acc = interior_sum<false>(T, S, ty, Qb, W, n, i, j, type, lane);
+          FP_T(t_c1);
+          FP_ADD(1, t_c0, t_c1);
           // multiloop: sum_k Qm(i+1,k-1) Qm1(k,j-1)
           double ml = 0.0;
           const double* qm_row = Qm + IX(i + 1, 0);
@@ -237,7 +258,10 @@ __global__ void __launch_bounds__(kFoldThreads, FOLD_CTAS) fold_kernel(const Fol
           qb = warp_sum_f(acc);
           const int u = d - 1;
           qb += P.hpS[u] * (u == 3 ? T.tau[type] : T.mmH[type][S[i + 1]][S[j - 1]]);
+          FP_T(t_c2);
+          FP_ADD(2, t_c1, t_c2);
         }
+        FP_T(t_c3);
         double dang = 1.0;
         if (type) dang = (i > 1 ? T.d5[type][S[i - 1]] : 1.0) * (j < n ? T.d3[type][S[j + 1]] : 1.0);
         const double qm1 = Qm1T[IX(j - 1, i)] * T.u1 + (type ? qb * T.mlintern[type] * dang : 0.0);
@@ -262,9 +286,19 @@ __global__ void __launch_bounds__(kFoldThreads, FOLD_CTAS) fold_kernel(const Fol
           QmT[IX(j, i)] = sm;
           Q[IX(i, j)] = sq;
         }
+        FP_T(t_c4);
+        FP_ADD(3, t_c3, t_c4);
+#ifdef FOLD_PROF
+        if (lane == 0) { fprof[8] += 1; if (type) fprof[9] += 1; }
+#endif
       }
+      FP_T(t_d1);
       __syncthreads();
+      FP_T(t_d2);
+      FP_ADD(4, t_d0, t_d1);
+      FP_ADD(5, t_d1, t_d2);
     }
+    FP_T(t_o0);
     const double Z = n > 0 ? Q[IX(1, n)] : 1.0;
     const bool bad = !(Z > 0.0) || isinf(Z) || isnan(Z);
 
@@ -310,6 +344,8 @@ __global__ void __launch_bounds__(kFoldThreads, FOLD_CTAS) fold_kernel(const Fol
       __syncthreads();
     }
 
+    FP_T(t_o1);
+    FP_ADD(6, t_o0, t_o1);
     // ---------------------------------------------------------------- probabilities, per-position sums, pair lists
     const double invZ = bad ? 0.0 : 1.0 / Z;
     for (size_t t = tid; t < W2; t += kFoldThreads) Ob[t] = ty[t] ? Qb[t] * Ob[t] * invZ : 0.0;   // Ob becomes P
@@ -365,8 +401,16 @@ __global__ void __launch_bounds__(kFoldThreads, FOLD_CTAS) fold_kernel(const Fol
       __syncthreads();
       if (tid == 0) s_run += total;
     }
+    FP_T(t_o2);
+    FP_ADD(7, t_o1, t_o2);
 #undef IX
   }
+#ifdef FOLD_PROF
+  if (lane == 0 && P.prof) {
+    for (int q = 0; q < 10; ++q) atomicAdd(P.prof + q, (unsigned long long)fprof[q]);
+    atomicAdd(P.prof + 10, (unsigned long long)(clock64() - fp_t00));
+  }
+#endif
 }
 
 uint8_t base_code(char c) {
@@ -487,6 +531,12 @@ cudaError_t run_fold(const stemk_fold_model& m, uint32_t n_seqs, const uint64_t*
   L.out_start = (uint64_t*)d_start; L.out_count = (uint32_t*)d_count; L.out_i = (uint32_t*)d_i; L.out_j = (uint32_t*)d_j;
   L.out_p = (double*)d_p; L.unpaired = (double*)d_unp; L.ensemble = (double*)d_ens; L.status = (int*)d_status;
   L.dense = (double*)d_dense; L.dense_off = (const uint64_t*)d_doff;
+#ifdef FOLD_PROF
+  unsigned long long* d_prof = nullptr;
+  cudaMalloc((void**)&d_prof, 16 * sizeof(unsigned long long));
+  cudaMemsetAsync(d_prof, 0, 16 * sizeof(unsigned long long), stream);
+  L.prof = d_prof;
+#endif
   const size_t smem = ((size_t)cap + 15) & ~(size_t)15;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEventCreate(&ev0); cudaEventCreate(&ev1);
@@ -514,6 +564,17 @@ cudaError_t run_fold(const stemk_fold_model& m, uint32_t n_seqs, const uint64_t*
   res->kernel_ms = 0.0;
   if (e == cudaSuccess) { float ms = 0; if (cudaEventElapsedTime(&ms, ev0, ev1) == cudaSuccess) res->kernel_ms = ms; }
   cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+#ifdef FOLD_PROF
+  {
+    unsigned long long h[16];
+    cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(d_prof);
+    const double tot = h[10] ? (double)h[10] : 1.0, cells = h[8] ? (double)h[8] : 1.0, pc = h[9] ? (double)h[9] : 1.0;
+    std::fprintf(stderr, "fold prof: grid %d x %d threads, %u seqs | of all warp time: setup %.1f%% inside cells %.1f%% inside barrier %.1f%% outside %.1f%% output %.1f%% | inside, cycles per cell: interior %.0f (per pair cell) ml+hairpin %.0f (per pair cell) Qm/Q sums %.0f (per cell); cells %.0f of which pairs %.0f\n",
+                 grid, kFoldThreads, n_seqs, 100.0 * h[0] / tot, 100.0 * h[4] / tot, 100.0 * h[5] / tot, 100.0 * h[6] / tot, 100.0 * h[7] / tot,
+                 h[1] / pc, h[2] / pc, h[3] / cells, cells, pc);
+  }
+#endif
   if (e != cudaSuccess) { cleanup(); return e; }
   const uint64_t total = cnt[1];
   std::vector<uint32_t> ti(total), tj(total);
