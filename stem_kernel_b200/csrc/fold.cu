@@ -179,6 +179,7 @@ __global__ void __launch_bounds__(kFoldThreads, FOLD_CTAS) fold_kernel(const Fol
   __shared__ unsigned long long s_seq, s_base;
   __shared__ uint32_t s_wsum[kFoldWarps];
   __shared__ uint32_t s_run;
+  __shared__ int s_cell[2];   // next cell of the running diagonal (two counters, alternating: the other one is reset under the barrier)
   uint8_t* S = dyn;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   {
@@ -234,15 +235,24 @@ __global__ void __launch_bounds__(kFoldThreads, FOLD_CTAS) fold_kernel(const Fol
     }
     __syncthreads();
 
+    if (tid == 0) { s_cell[0] = 0; s_cell[1] = 0; }
+    __syncthreads();
     FP_T(t_s1);
     FP_ADD(0, t_s0, t_s1);
     // ---------------------------------------------------------------- inside
     for (int d = kTurn + 1; d < n; ++d) {
       FP_T(t_d0);
-      for (int i = 1 + warp; i + d <= n; i += kFoldWarps) {
+      if (tid == 0) s_cell[(d + 1) & 1] = 0;
+      // cells are drawn from a counter: a pair cell costs ~4x a cell that is no pair, a static deal leaves warps idle
+      for (;;) {
+        int i = 0;
+        if (lane == 0) i = 1 + atomicAdd(&s_cell[d & 1], 1);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i + d > n) break;
         const int j = i + d;
         FP_T(t_c0);
         const int type = ty[IX(i, j)];
+        const double qm1_prev = Qm1T[IX(j - 1, i)], qq_prev = QqT[IX(j - 1, i)];   // asked for before the sums below need them
         double qb = 0.0;
         if (type) {
           double acc = interior_sum<false>(T, S, ty, Qb, W, n, i, j, type, lane);
@@ -252,6 +262,7 @@ __global__ void __launch_bounds__(kFoldThreads, FOLD_CTAS) fold_kernel(const Fol
           double ml = 0.0;
           const double* qm_row = Qm + IX(i + 1, 0);
           const double* qm1_row = Qm1T + IX(j - 1, 0);
+#pragma unroll 4
           for (int k = i + 2 + lane; k <= j - 1; k += 32) ml += qm_row[k - 1] * qm1_row[k];
           const int tt = d_rtype(type);
           acc += ml * (T.mlclosingS * T.mlintern[tt] * T.d3[tt][S[i + 1]] * T.d5[tt][S[j - 1]]);
@@ -264,14 +275,15 @@ __global__ void __launch_bounds__(kFoldThreads, FOLD_CTAS) fold_kernel(const Fol
         FP_T(t_c3);
         double dang = 1.0;
         if (type) dang = (i > 1 ? T.d5[type][S[i - 1]] : 1.0) * (j < n ? T.d3[type][S[j + 1]] : 1.0);
-        const double qm1 = Qm1T[IX(j - 1, i)] * T.u1 + (type ? qb * T.mlintern[type] * dang : 0.0);
-        const double qq = QqT[IX(j - 1, i)] * T.s1 + (type ? qb * T.tau[type] * dang : 0.0);
+        const double qm1 = qm1_prev * T.u1 + (type ? qb * T.mlintern[type] * dang : 0.0);
+        const double qq = qq_prev * T.s1 + (type ? qb * T.tau[type] * dang : 0.0);
         // Qm, Q: the k = i terms are this cell's own Qm1 / Qq
         double sm = 0.0, sq = 0.0;
         const double* qmi = Qm + IX(i, 0);
         const double* qi = Q + IX(i, 0);
         const double* qm1j = Qm1T + IX(j, 0);
         const double* qqj = QqT + IX(j, 0);
+#pragma unroll 4
         for (int k = i + 1 + lane; k <= j; k += 32) {
           sm += (up[k - i] + qmi[k - 1]) * qm1j[k];
           sq += qi[k - 1] * qqj[k];
@@ -303,8 +315,15 @@ __global__ void __launch_bounds__(kFoldThreads, FOLD_CTAS) fold_kernel(const Fol
     const bool bad = !(Z > 0.0) || isinf(Z) || isnan(Z);
 
     // ---------------------------------------------------------------- outside
+    if (tid == 0) { s_cell[0] = 0; s_cell[1] = 0; }
+    __syncthreads();
     for (int d = n - 1; d >= 1 && !bad; --d) {
-      for (int i = 1 + warp; i + d <= n; i += kFoldWarps) {
+      if (tid == 0) s_cell[(d + 1) & 1] = 0;
+      for (;;) {
+        int i = 0;
+        if (lane == 0) i = 1 + atomicAdd(&s_cell[d & 1], 1);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i + d > n) break;
         const int j = i + d;
         const int type = d > kTurn ? ty[IX(i, j)] : 0;
         if (type) {
@@ -313,6 +332,7 @@ __global__ void __launch_bounds__(kFoldThreads, FOLD_CTAS) fold_kernel(const Fol
           const double* qmt = QmT + IX(i - 1, 0);   // QmT[i-1][p+1] = Qm(p+1, i-1)
           const double* at = AT + IX(j, 0);
           const double* bt = BT + IX(j, 0);
+#pragma unroll 4
           for (int p = 1 + lane; p < i; p += 32) ml += qmt[p + 1] * at[p] + up[i - p - 1] * bt[p];
           const double dang = (i > 1 ? T.d5[type][S[i - 1]] : 1.0) * (j < n ? T.d3[type][S[j + 1]] : 1.0);
           acc += ml * (T.mlintern[type] * dang);
@@ -328,6 +348,7 @@ __global__ void __launch_bounds__(kFoldThreads, FOLD_CTAS) fold_kernel(const Fol
           double a = 0.0, b = 0.0;
           const double* wrow = Wc + IX(i, 0);
           const double* qmr = Qm + IX(j + 1, 0);
+#pragma unroll 4
           for (int q = j + 1 + lane; q <= n; q += 32) {
             const double w = wrow[q];
             if (w != 0.0) {
