@@ -64,3 +64,21 @@ def test_upload_validates_the_descriptor(case, msg):
         f["n_seqs"] = 0.0
     with pytest.raises(api.StemkError, match=msg):
         ctx.upload([hostlib.MData.from_arrays(f, "a" * 10)])
+
+
+def test_fold_has_no_cpu_path_and_checks_its_arguments():
+    """stemk_fold_bpp computes on a CUDA device only; a host-only context refuses, null arguments are STEMK_ERR_ARG."""
+    import ctypes as C
+    from stem_kernel_b200 import fold
+    ctx = api.Context(L.make_params(L.SU_STEM), device=-1)
+    with pytest.raises(api.StemkError, match="no CPU path"):
+        fold.Folder(ctx).bpp(["gggaaaccc"])
+    lib = L.lib()
+    total = C.c_uint64(0)
+    assert lib.stemk_fold_bpp(ctx.h, None, 0, None, None, 0.0, C.byref(total), None, None) == L.ERR_ARG
+    assert lib.stemk_fold_fetch(ctx.h, None, None, None, None, None) == L.ERR_ARG        # nothing to fetch yet
+    m = fold.default_model()
+    assert m.temperature == 37.0 and m.stack[1][2] == -3.3 and m.hairpin[3] == 5.7 and m.ml_closing == 3.4
+    # the stand-in parameter set of the product and the checker's restatement of it are the same numbers
+    mo = O.fold_model_default()
+    assert bytes(m) == bytes(mo)
