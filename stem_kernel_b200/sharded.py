@@ -285,3 +285,31 @@ def record_keys(dset, stem=True, string=False):
     if string:
         k += length.astype(np.float64) ** 2
     return k
+
+
+# ----------------------------------------------------------------------------------------------- front end
+class ShardedFold:
+    """Base-pair probabilities of a batch of sequences over the ranks (the front end's McCaskill, fold.py / fold.cu).
+
+    Sequences are independent: the batch is put in ONE global order, longest first (cost ~ L^3), dealt round-robin --
+    rank r owns positions r, r+W, ... -- every rank folds its share on its own GPU and the pair lists travel to rank 0
+    in one gather of objects (they are ragged).  No data-path collective besides that gather.  `fold_fn(seqs)` returns
+    one (i, j, p) triple of arrays per sequence: fold.Folder(...).bpp(...).pairs on the GPUs, the oracle in the CPU
+    test."""
+
+    def __init__(self, lengths, rank, world):
+        self.rank, self.world = rank, world
+        self.order = np.argsort(-np.asarray(lengths, dtype=np.int64), kind="stable")
+        self.mine = self.order[rank::world]
+
+    def run(self, seqs, fold_fn):
+        part = fold_fn([seqs[k] for k in self.mine])
+        gathered = [None] * self.world if self.rank == 0 else None
+        dist.gather_object([(int(k), tuple(np.asarray(a) for a in p)) for k, p in zip(self.mine, part)], gathered, dst=0)
+        if self.rank != 0:
+            return None
+        out = [None] * len(seqs)
+        for share in gathered:
+            for k, p in share:
+                out[k] = p
+        return out

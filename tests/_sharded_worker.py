@@ -43,6 +43,30 @@ def main():
             np.fill_diagonal(m, 1.0)
         return torch.from_numpy(m)
 
+    if len(sys.argv) > 5 and sys.argv[5] == "fold":
+        # front end: base-pair probabilities of a ragged batch, the oracle as arithmetic
+        seqs = [r["rows"][0] for r in recs if len(r["rows"]) == 1][:9] + ["", "gggaaaccc"]
+        fm = O.fold_model_default()
+
+        def fold_fn(part):
+            res = []
+            for q in part:
+                d = O.fold_bpp(fm, q)[0]
+                i, j = np.nonzero(d >= 0.01)
+                res.append((i, j, d[i, j]))
+            return res
+
+        got = sharded.ShardedFold([len(q) for q in seqs], rank, world).run(seqs, fold_fn)
+        assert (got is None) == (rank != 0)
+        if rank == 0:
+            want = fold_fn(seqs)
+            assert len(got) == len(want)
+            for g, w in zip(got, want):
+                assert all(np.array_equal(a, b) for a, b in zip(g, w))
+            np.save(out, np.array([len(g[0]) for g in got]))
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     if len(sys.argv) > 5 and sys.argv[5] == "cross":
         # rectangular: the first 11 golden records are the training set, the rest the test set, 7 sv columns
         n_tr = 11

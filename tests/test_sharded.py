@@ -101,3 +101,16 @@ def test_world_size_2_gloo_rectangular_matches_the_oracle(tmp_path):
     assert np.array_equal(got[:, :11], want, equal_nan=True) and np.array_equal(got[:, 11], want_self)
     others = np.setdiff1d(np.arange(11), cols)
     assert not np.isfinite(got[:, others]).any()
+
+
+def test_world_size_2_gloo_sharded_fold(tmp_path):
+    """ShardedFold: a ragged batch of sequences dealt longest-first over two ranks, pair lists gathered on rank 0 in
+    the caller's order, equal to the one-process result (the worker compares them; arithmetic = the oracle)."""
+    port, out = _free_port(), str(tmp_path / "fold.npy")
+    worker = os.path.join(ROOT, "tests", "_sharded_worker.py")
+    procs = [subprocess.Popen([sys.executable, worker, str(r), "2", str(port), out, "fold"], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT) for r in range(2)]
+    logs = [p.communicate(timeout=240)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(logs)
+    counts = np.load(out)
+    assert len(counts) == 11 and counts[-2] == 0 and counts.sum() > 0
