@@ -81,7 +81,7 @@ struct FoldLaunch {
   uint32_t n_seqs, cap;       // cap = longest sequence + 2
   int no_gu;
   double cutoff;
-  double* scratch;            // per CTA: kTables tables of cap^2 doubles, then cap^2 pair-type bytes
+  double* scratch;            // per CTA: kTables tables of cap^2 doubles
   unsigned long long scratch_stride;   // doubles per CTA
   unsigned long long* counter;         // [0] next sequence, [1] output cursor
   uint64_t* out_start;        // [n_seqs] first entry of the sequence's pairs in out_*
@@ -130,45 +130,48 @@ __device__ __forceinline__ double il_weight(const FoldTab& T, int u1, int u2, in
 // Sum over the interior loops (stacks and bulges included) of one cell.
 // OUTSIDE = false: (i,j) closes, tab = Qb of the inner pair (k,l) = (i+1+u1, j-1-u2);
 // OUTSIDE = true:  (i,j) is the inner pair, tab = Ob of the closing pair (p,q) = (i-1-u1, j+1+u2).
-// Lanes <-> u2, one row (k or p) of the tables per step, so that a step reads <= 31 CONSECUTIVE pair types and table
-// entries: with lanes over arbitrary (u1, u2) combinations every load touched 32 different lines and the kernel was
-// bound by the L1 tag stage (profiles/r02_fold_ncu_summary.txt).  kIlUnroll rows are taken at a time (one round trip to
-// L2 / DRAM per step: the kernel is bound by the latency of these chains, not by a pipe).
-#ifndef FOLD_UNROLL
-#define FOLD_UNROLL 4
+// Only ~1/4 of the 496 (u1, u2) combinations are pairs inside the sequence, and the owning warp's instruction stream is
+// what bounds the kernel, so the combinations are COMPACTED first: kIlRows rows at a time, lanes <-> u2
+// decide from the staged sequence alone (5x5 pair-type table, no global load) which combinations exist, one ballot per
+// row puts their codes densely into the warp's staging bytes, and the table entries are then fetched and weighted with
+// every lane busy -- consecutive lanes mostly read consecutive entries of a row.
+#ifndef FOLD_ROWS
+#define FOLD_ROWS 8
 #endif
-constexpr int kIlUnroll = FOLD_UNROLL;
+constexpr int kIlRows = FOLD_ROWS;   // <= 8: a code is (row << 5) | u2 in one byte
 template <bool OUTSIDE>
-__device__ __forceinline__ double interior_sum(const FoldTab& T, const uint8_t* S, const uint8_t* __restrict__ ty,
+__device__ __forceinline__ double interior_sum(const FoldTab& T, const uint8_t* S, const uint8_t* s_pt, uint8_t* stage,
                                                const double* __restrict__ tab, int W, int n, int i, int j, int type, int lane) {
   double acc = 0.0;
   const double mm_ij = T.mmI[OUTSIDE ? d_rtype(type) : type][S[OUTSIDE ? j + 1 : i + 1]][S[OUTSIDE ? i - 1 : j - 1]];   // this cell's own mismatch factor
   const int u1_end = min(kMaxLoop, OUTSIDE ? i - 2 : j - i - 3 - kTurn);   // last u1 with a row inside the sequence / a pair that can close
-  const int u2 = lane;
-  const int b = OUTSIDE ? j + 1 + u2 : j - 1 - u2;
-  for (int u0 = 0; u0 <= u1_end; u0 += kIlUnroll) {
-    uint8_t tp[kIlUnroll];
-    double v[kIlUnroll];
-    // the pair type and the table entry of a combination are asked for TOGETHER (the entry of a non-pair is 0: the
-    // tables are cleared per sequence and only pairs are ever written), one round trip per kIlUnroll rows instead of two
+  const int b = OUTSIDE ? j + 1 + lane : j - 1 - lane;
+  const int sb = (OUTSIDE ? b <= n : b >= 1) ? S[b] : 0;   // code 0 never pairs
+  const uint32_t lt = (1u << lane) - 1u;
+  for (int u0 = 0; u0 <= u1_end; u0 += kIlRows) {
+    uint32_t total = 0;
 #pragma unroll
-    for (int u = 0; u < kIlUnroll; ++u) {
-      const int u1 = u0 + u;
+    for (int r = 0; r < kIlRows; ++r) {
+      const int u1 = u0 + r;
       const int a = OUTSIDE ? i - 1 - u1 : i + 1 + u1;
-      const bool ok = u1 <= u1_end && u2 <= kMaxLoop - u1 && (OUTSIDE ? b <= n : b - a > kTurn);
-      const uint32_t at = (uint32_t)(a * W + b);
-      tp[u] = ok ? ty[at] : (uint8_t)0;
-      v[u] = ok ? tab[at] : 0.0;
+      bool ok = u1 <= u1_end && lane <= kMaxLoop - u1 && (OUTSIDE || b - a > kTurn);
+      if (ok) ok = s_pt[S[a] * 5 + sb] != 0;
+      const uint32_t m = __ballot_sync(0xffffffffu, ok);
+      if (ok) stage[total + __popc(m & lt)] = (uint8_t)((r << 5) | lane);
+      total += __popc(m);
     }
-#pragma unroll
-    for (int u = 0; u < kIlUnroll; ++u)
-      if (tp[u]) {
-        const int u1 = u0 + u;
-        const int a = OUTSIDE ? i - 1 - u1 : i + 1 + u1;
-        // il_weight(closing type, inner type, closing pair's mismatch factor, inner pair's)
-        acc += v[u] * (OUTSIDE ? il_weight(T, u1, u2, tp[u], type, T.mmI[tp[u]][S[a + 1]][S[b - 1]], mm_ij)
-                               : il_weight(T, u1, u2, type, tp[u], mm_ij, T.mmI[d_rtype(tp[u])][S[b + 1]][S[a - 1]]));
-      }
+    __syncwarp();
+    for (uint32_t t = lane; t < total; t += 32u) {
+      const int code = stage[t];
+      const int u1 = u0 + (code >> 5), u2 = code & 31;
+      const int a = OUTSIDE ? i - 1 - u1 : i + 1 + u1, bb = OUTSIDE ? j + 1 + u2 : j - 1 - u2;
+      const int tp = s_pt[S[a] * 5 + S[bb]];
+      const double v = tab[(size_t)a * W + bb];
+      // il_weight(closing type, inner type, closing pair's mismatch factor, inner pair's)
+      acc += v * (OUTSIDE ? il_weight(T, u1, u2, tp, type, T.mmI[tp][S[a + 1]][S[bb - 1]], mm_ij)
+                          : il_weight(T, u1, u2, type, tp, mm_ij, T.mmI[d_rtype(tp)][S[bb + 1]][S[a - 1]]));
+    }
+    __syncwarp();   // the staging bytes are reused by the next rows
   }
   return acc;
 }
@@ -179,6 +182,8 @@ __global__ void __launch_bounds__(kFoldThreads, FOLD_CTAS) fold_kernel(const Fol
   __shared__ unsigned long long s_seq, s_base;
   __shared__ uint32_t s_wsum[kFoldWarps];
   __shared__ uint32_t s_run;
+  __shared__ uint8_t s_pt[32];                        // pair type by (code of i) * 5 + (code of j)
+  __shared__ uint8_t s_stage[kFoldWarps][256];        // per warp: codes of the interior-loop combinations that exist
   __shared__ int s_cell[2];   // next cell of the running diagonal (two counters, alternating: the other one is reset under the barrier)
   uint8_t* S = dyn;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -186,6 +191,7 @@ __global__ void __launch_bounds__(kFoldThreads, FOLD_CTAS) fold_kernel(const Fol
     const double* src = reinterpret_cast<const double*>(P.tab);
     double* dst = reinterpret_cast<double*>(&T);
     for (int t = tid; t < (int)(sizeof(FoldTab) / sizeof(double)); t += kFoldThreads) dst[t] = src[t];
+    if (tid < 32) s_pt[tid] = tid < 25 ? (uint8_t)d_pair_type(tid / 5, tid % 5, P.no_gu) : (uint8_t)0;
   }
 #ifdef FOLD_PROF
   long long fprof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -218,8 +224,8 @@ __global__ void __launch_bounds__(kFoldThreads, FOLD_CTAS) fold_kernel(const Fol
     double* Wc = base + 7 * cap2;
     double* AT = base + 8 * cap2;
     double* BT = base + 9 * cap2;
-    uint8_t* ty = reinterpret_cast<uint8_t*>(base + (size_t)kTables * cap2);
 #define IX(a, b) ((size_t)(a) * W + (size_t)(b))
+#define PT(a, b) ((b) - (a) > kTurn ? (int)s_pt[S[a] * 5 + S[b]] : 0)   /* pair type of (a,b), 1 <= a, b <= n */
 
     for (int t = tid; t < W; t += kFoldThreads) S[t] = (t >= 1 && t <= n) ? P.codes[c0 + t - 1] : (uint8_t)0;
     for (int tb = 0; tb < kTables; ++tb) {
@@ -227,14 +233,11 @@ __global__ void __launch_bounds__(kFoldThreads, FOLD_CTAS) fold_kernel(const Fol
       for (size_t t = tid; t < W2; t += kFoldThreads) q[t] = 0.0;
     }
     __syncthreads();
-    for (size_t t = tid; t < W2; t += kFoldThreads) {
-      const int i = (int)(t / W), j = (int)(t % W);
-      ty[t] = (i >= 1 && j <= n && j - i > kTurn) ? (uint8_t)d_pair_type(S[i], S[j], P.no_gu) : (uint8_t)0;
-      // spans without a pair: only the exterior table is non-zero; Q(i,i-1) = 1 is the empty interval
-      if (i >= 1 && i <= n + 1 && j >= i - 1 && j <= n && j - i <= kTurn) Q[t] = sp[j - i + 1];
+    // spans without a pair: only the exterior table is non-zero; Q(i,i-1) = 1 is the empty interval
+    for (int t = tid; t < (n + 1) * (kTurn + 2); t += kFoldThreads) {
+      const int i = 1 + t / (kTurn + 2), j = i - 1 + t % (kTurn + 2);
+      if (j <= n) Q[IX(i, j)] = sp[j - i + 1];
     }
-    __syncthreads();
-
     if (tid == 0) { s_cell[0] = 0; s_cell[1] = 0; }
     __syncthreads();
     FP_T(t_s1);
@@ -251,11 +254,11 @@ __global__ void __launch_bounds__(kFoldThreads, FOLD_CTAS) fold_kernel(const Fol
         if (i + d > n) break;
         const int j = i + d;
         FP_T(t_c0);
-        const int type = ty[IX(i, j)];
+        const int type = PT(i, j);
         const double qm1_prev = Qm1T[IX(j - 1, i)], qq_prev = QqT[IX(j - 1, i)];   // asked for before the sums below need them
         double qb = 0.0;
         if (type) {
-          double acc = interior_sum<false>(T, S, ty, Qb, W, n, i, j, type, lane);
+          double acc = interior_sum<false>(T, S, s_pt, s_stage[warp], Qb, W, n, i, j, type, lane);
           FP_T(t_c1);
           FP_ADD(1, t_c0, t_c1);
           // multiloop: sum_k Qm(i+1,k-1) Qm1(k,j-1)
@@ -325,9 +328,9 @@ __global__ void __launch_bounds__(kFoldThreads, FOLD_CTAS) fold_kernel(const Fol
         i = __shfl_sync(0xffffffffu, i, 0);
         if (i + d > n) break;
         const int j = i + d;
-        const int type = d > kTurn ? ty[IX(i, j)] : 0;
+        const int type = PT(i, j);
         if (type) {
-          double acc = interior_sum<true>(T, S, ty, Ob, W, n, i, j, type, lane);
+          double acc = interior_sum<true>(T, S, s_pt, s_stage[warp], Ob, W, n, i, j, type, lane);
           double ml = 0.0;
           const double* qmt = QmT + IX(i - 1, 0);   // QmT[i-1][p+1] = Qm(p+1, i-1)
           const double* at = AT + IX(j, 0);
@@ -369,7 +372,10 @@ __global__ void __launch_bounds__(kFoldThreads, FOLD_CTAS) fold_kernel(const Fol
     FP_ADD(6, t_o0, t_o1);
     // ---------------------------------------------------------------- probabilities, per-position sums, pair lists
     const double invZ = bad ? 0.0 : 1.0 / Z;
-    for (size_t t = tid; t < W2; t += kFoldThreads) Ob[t] = ty[t] ? Qb[t] * Ob[t] * invZ : 0.0;   // Ob becomes P
+    for (size_t t = tid; t < W2; t += kFoldThreads) {   // Ob becomes P
+      const int i = (int)(t / W), j = (int)(t % W);
+      Ob[t] = (i >= 1 && j <= n && PT(i, j)) ? Qb[t] * Ob[t] * invZ : 0.0;
+    }
     __syncthreads();
     for (int t = 1 + tid; t <= n; t += kFoldThreads) {
       double s = 0.0;
@@ -425,6 +431,7 @@ __global__ void __launch_bounds__(kFoldThreads, FOLD_CTAS) fold_kernel(const Fol
     FP_T(t_o2);
     FP_ADD(7, t_o1, t_o2);
 #undef IX
+#undef PT
   }
 #ifdef FOLD_PROF
   if (lane == 0 && P.prof) {
@@ -525,7 +532,7 @@ cudaError_t run_fold(const stemk_fold_model& m, uint32_t n_seqs, const uint64_t*
   std::memset(&L, 0, sizeof(L));
   void *d_tab, *d_hp, *d_sp, *d_up, *d_codes, *d_off, *d_order, *d_cnt, *d_start, *d_count, *d_i, *d_j, *d_p, *d_unp, *d_ens, *d_status,
       *d_scratch, *d_dense = nullptr, *d_doff = nullptr;
-  const unsigned long long stride = ((unsigned long long)kTables * cap * cap + ((unsigned long long)cap * cap + 7) / 8 + 1) & ~1ull;
+  const unsigned long long stride = ((unsigned long long)kTables * cap * cap + 1) & ~1ull;
   int grid = (int)std::min<uint64_t>(n_seqs, (uint64_t)sm_count * FOLD_CTAS);
   grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)grid, ((uint64_t)8 << 30) / (stride * sizeof(double))));
   bool ok = upload(&d_tab, &T, sizeof(T)) && upload(&d_hp, hpS.data(), hpS.size() * 8) && upload(&d_sp, sp.data(), sp.size() * 8) &&
