@@ -79,9 +79,10 @@ struct FoldLaunch {
   const uint64_t* seq_off;    // [n_seqs + 1]
   const uint32_t* order;      // sequences, longest first
   uint32_t n_seqs, cap;       // cap = longest sequence + 2
+  uint32_t pb_shared;         // byte offset of the pairable-column bits in dynamic shared memory, 0: they live in the scratch
   int no_gu;
   double cutoff;
-  double* scratch;            // per CTA: kTables tables of cap^2 doubles
+  double* scratch;            // per CTA: kTables tables of cap^2 doubles, then cap rows of pairable-column bits
   unsigned long long scratch_stride;   // doubles per CTA
   unsigned long long* counter;         // [0] next sequence, [1] output cursor
   uint64_t* out_start;        // [n_seqs] first entry of the sequence's pairs in out_*
@@ -131,48 +132,51 @@ __device__ __forceinline__ double il_weight(const FoldTab& T, int u1, int u2, in
 // OUTSIDE = false: (i,j) closes, tab = Qb of the inner pair (k,l) = (i+1+u1, j-1-u2);
 // OUTSIDE = true:  (i,j) is the inner pair, tab = Ob of the closing pair (p,q) = (i-1-u1, j+1+u2).
 // Only ~1/4 of the 496 (u1, u2) combinations are pairs inside the sequence, and the owning warp's instruction stream is
-// what bounds the kernel, so the combinations are COMPACTED first: kIlRows rows at a time, lanes <-> u2
-// decide from the staged sequence alone (5x5 pair-type table, no global load) which combinations exist, one ballot per
-// row puts their codes densely into the warp's staging bytes, and the table entries are then fetched and weighted with
-// every lane busy -- consecutive lanes mostly read consecutive entries of a row.
-#ifndef FOLD_ROWS
-#define FOLD_ROWS 8
-#endif
-constexpr int kIlRows = FOLD_ROWS;   // <= 8: a code is (row << 5) | u2 in one byte
+// what bounds the kernel, so the combinations that exist are found WITHOUT touching the others: the
+// sequence's pairable columns are a bit vector per row (pb, built once per sequence; bit l + 32 of row a = (a,l) can
+// pair), lane <-> row u1 cuts its 31-column window out of it with one funnel shift, a warp scan of the popcounts gives
+// every row its place in the warp's staging area, each lane writes the codes of its set bits there, and the table
+// entries are then fetched and weighted with every lane busy -- consecutive lanes mostly read consecutive entries of a
+// row.
 template <bool OUTSIDE>
-__device__ __forceinline__ double interior_sum(const FoldTab& T, const uint8_t* S, const uint8_t* s_pt, uint8_t* stage,
-                                               const double* __restrict__ tab, int W, int n, int i, int j, int type, int lane) {
+__device__ __forceinline__ double interior_sum(const FoldTab& T, const uint8_t* S, const uint8_t* s_pt, const uint32_t* pb, int pbw,
+                                               uint16_t* stage, const double* __restrict__ tab, int W, int n, int i, int j, int type,
+                                               int lane) {
   double acc = 0.0;
   const double mm_ij = T.mmI[OUTSIDE ? d_rtype(type) : type][S[OUTSIDE ? j + 1 : i + 1]][S[OUTSIDE ? i - 1 : j - 1]];   // this cell's own mismatch factor
   const int u1_end = min(kMaxLoop, OUTSIDE ? i - 2 : j - i - 3 - kTurn);   // last u1 with a row inside the sequence / a pair that can close
-  const int b = OUTSIDE ? j + 1 + lane : j - 1 - lane;
-  const int sb = (OUTSIDE ? b <= n : b >= 1) ? S[b] : 0;   // code 0 never pairs
-  const uint32_t lt = (1u << lane) - 1u;
-  for (int u0 = 0; u0 <= u1_end; u0 += kIlRows) {
-    uint32_t total = 0;
-#pragma unroll
-    for (int r = 0; r < kIlRows; ++r) {
-      const int u1 = u0 + r;
-      const int a = OUTSIDE ? i - 1 - u1 : i + 1 + u1;
-      bool ok = u1 <= u1_end && lane <= kMaxLoop - u1 && (OUTSIDE || b - a > kTurn);
-      if (ok) ok = s_pt[S[a] * 5 + sb] != 0;
-      const uint32_t m = __ballot_sync(0xffffffffu, ok);
-      if (ok) stage[total + __popc(m & lt)] = (uint8_t)((r << 5) | lane);
-      total += __popc(m);
-    }
-    __syncwarp();
-    for (uint32_t t = lane; t < total; t += 32u) {
-      const int code = stage[t];
-      const int u1 = u0 + (code >> 5), u2 = code & 31;
-      const int a = OUTSIDE ? i - 1 - u1 : i + 1 + u1, bb = OUTSIDE ? j + 1 + u2 : j - 1 - u2;
-      const int tp = s_pt[S[a] * 5 + S[bb]];
-      const double v = tab[(size_t)a * W + bb];
-      // il_weight(closing type, inner type, closing pair's mismatch factor, inner pair's)
-      acc += v * (OUTSIDE ? il_weight(T, u1, u2, tp, type, T.mmI[tp][S[a + 1]][S[bb - 1]], mm_ij)
-                          : il_weight(T, u1, u2, type, tp, mm_ij, T.mmI[d_rtype(tp)][S[bb + 1]][S[a - 1]]));
-    }
-    __syncwarp();   // the staging bytes are reused by the next rows
+  // this lane's row: its pairable columns inside the window, bit q <-> u2 = q (outside) or 30 - q (inside)
+  uint32_t x = 0;
+  if (lane <= u1_end) {
+    const int a = OUTSIDE ? i - 1 - lane : i + 1 + lane;
+    const int lo = (OUTSIDE ? j + 1 : j - 1 - kMaxLoop) + 32;
+    const uint32_t* row = pb + (size_t)a * pbw + (lo >> 5);
+    x = __funnelshift_r(row[0], row[1], lo & 31) & 0x7fffffffu;
+    x &= OUTSIDE ? (0x7fffffffu >> lane) : ~((1u << lane) - 1u);   // u2 <= 30 - u1
   }
+  const int cnt = __popc(x);
+  int at = cnt;   // inclusive scan of the rows' counts
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, at, o); if (lane >= o) at += v; }
+  const int total = __shfl_sync(0xffffffffu, at, 31);
+  at -= cnt;
+  while (x) {
+    const int q = __ffs((int)x) - 1;
+    x &= x - 1u;
+    stage[at++] = (uint16_t)((lane << 5) | (OUTSIDE ? q : kMaxLoop - q));
+  }
+  __syncwarp();
+  for (int t = lane; t < total; t += 32) {
+    const int code = stage[t];
+    const int u1 = code >> 5, u2 = code & 31;
+    const int a = OUTSIDE ? i - 1 - u1 : i + 1 + u1, bb = OUTSIDE ? j + 1 + u2 : j - 1 - u2;
+    const int tp = s_pt[S[a] * 5 + S[bb]];
+    const double v = tab[(size_t)a * W + bb];
+    // il_weight(closing type, inner type, closing pair's mismatch factor, inner pair's)
+    acc += v * (OUTSIDE ? il_weight(T, u1, u2, tp, type, T.mmI[tp][S[a + 1]][S[bb - 1]], mm_ij)
+                        : il_weight(T, u1, u2, type, tp, mm_ij, T.mmI[d_rtype(tp)][S[bb + 1]][S[a - 1]]));
+  }
+  __syncwarp();   // the staging area is reused by the warp's next cell
   return acc;
 }
 
@@ -183,7 +187,7 @@ __global__ void __launch_bounds__(kFoldThreads, FOLD_CTAS) fold_kernel(const Fol
   __shared__ uint32_t s_wsum[kFoldWarps];
   __shared__ uint32_t s_run;
   __shared__ uint8_t s_pt[32];                        // pair type by (code of i) * 5 + (code of j)
-  __shared__ uint8_t s_stage[kFoldWarps][256];        // per warp: codes of the interior-loop combinations that exist
+  __shared__ uint16_t s_stage[kFoldWarps][512];       // per warp: codes (u1 << 5 | u2) of the interior-loop combinations that exist
   __shared__ int s_cell[2];   // next cell of the running diagonal (two counters, alternating: the other one is reset under the barrier)
   uint8_t* S = dyn;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -228,11 +232,25 @@ __global__ void __launch_bounds__(kFoldThreads, FOLD_CTAS) fold_kernel(const Fol
 #define PT(a, b) ((b) - (a) > kTurn ? (int)s_pt[S[a] * 5 + S[b]] : 0)   /* pair type of (a,b), 1 <= a, b <= n */
 
     for (int t = tid; t < W; t += kFoldThreads) S[t] = (t >= 1 && t <= n) ? P.codes[c0 + t - 1] : (uint8_t)0;
+    // pairable columns of every row as bits (bit l + 32 of row a: (a,l) can pair, l - a > 3): in shared memory when the
+    // launch reserved room for the longest sequence (P.pb_shared), in the CTA's scratch otherwise
+    const int pbw = (n + 33) / 32 + 2;   // a window starts at most at bit n + 33 and spans two words
+    uint32_t* pb = P.pb_shared ? reinterpret_cast<uint32_t*>(dyn + P.pb_shared) : reinterpret_cast<uint32_t*>(base + (size_t)kTables * cap2);
     for (int tb = 0; tb < kTables; ++tb) {
       double* q = base + (size_t)tb * cap2;
       for (size_t t = tid; t < W2; t += kFoldThreads) q[t] = 0.0;
     }
     __syncthreads();
+    for (int t = tid; t < W * pbw; t += kFoldThreads) {
+      const int a = t / pbw, w = t % pbw;
+      uint32_t bits = 0;
+      if (a >= 1 && a <= n)
+        for (int q = 0; q < 32; ++q) {
+          const int l = 32 * w + q - 32;
+          if (l <= n && l - a > kTurn && s_pt[S[a] * 5 + S[l]]) bits |= 1u << q;
+        }
+      pb[t] = bits;
+    }
     // spans without a pair: only the exterior table is non-zero; Q(i,i-1) = 1 is the empty interval
     for (int t = tid; t < (n + 1) * (kTurn + 2); t += kFoldThreads) {
       const int i = 1 + t / (kTurn + 2), j = i - 1 + t % (kTurn + 2);
@@ -258,7 +276,7 @@ __global__ void __launch_bounds__(kFoldThreads, FOLD_CTAS) fold_kernel(const Fol
         const double qm1_prev = Qm1T[IX(j - 1, i)], qq_prev = QqT[IX(j - 1, i)];   // asked for before the sums below need them
         double qb = 0.0;
         if (type) {
-          double acc = interior_sum<false>(T, S, s_pt, s_stage[warp], Qb, W, n, i, j, type, lane);
+          double acc = interior_sum<false>(T, S, s_pt, pb, pbw, s_stage[warp], Qb, W, n, i, j, type, lane);
           FP_T(t_c1);
           FP_ADD(1, t_c0, t_c1);
           // multiloop: sum_k Qm(i+1,k-1) Qm1(k,j-1)
@@ -330,7 +348,7 @@ __global__ void __launch_bounds__(kFoldThreads, FOLD_CTAS) fold_kernel(const Fol
         const int j = i + d;
         const int type = PT(i, j);
         if (type) {
-          double acc = interior_sum<true>(T, S, s_pt, s_stage[warp], Ob, W, n, i, j, type, lane);
+          double acc = interior_sum<true>(T, S, s_pt, pb, pbw, s_stage[warp], Ob, W, n, i, j, type, lane);
           double ml = 0.0;
           const double* qmt = QmT + IX(i - 1, 0);   // QmT[i-1][p+1] = Qm(p+1, i-1)
           const double* at = AT + IX(j, 0);
@@ -353,12 +371,9 @@ __global__ void __launch_bounds__(kFoldThreads, FOLD_CTAS) fold_kernel(const Fol
           const double* qmr = Qm + IX(j + 1, 0);
 #pragma unroll 4
           for (int q = j + 1 + lane; q <= n; q += 32) {
-            const double w = wrow[q];
-            if (w != 0.0) {
-              const double qm = qmr[q - 1];
-              a += w * (up[q - j - 1] + qm);
-              b += w * qm;
-            }
+            const double w = wrow[q], qm = qmr[q - 1];   // both asked for at once: W is mostly 0, but a dependent load costs a round trip
+            a += w * (up[q - j - 1] + qm);
+            b += w * qm;
           }
           a = warp_sum_f(a);
           b = warp_sum_f(b);
@@ -532,7 +547,9 @@ cudaError_t run_fold(const stemk_fold_model& m, uint32_t n_seqs, const uint64_t*
   std::memset(&L, 0, sizeof(L));
   void *d_tab, *d_hp, *d_sp, *d_up, *d_codes, *d_off, *d_order, *d_cnt, *d_start, *d_count, *d_i, *d_j, *d_p, *d_unp, *d_ens, *d_status,
       *d_scratch, *d_dense = nullptr, *d_doff = nullptr;
-  const unsigned long long stride = ((unsigned long long)kTables * cap * cap + 1) & ~1ull;
+  const uint32_t pbw_cap = (max_len + 33) / 32 + 2;
+  const size_t pb_bytes = (size_t)cap * pbw_cap * 4;
+  const unsigned long long stride = ((unsigned long long)kTables * cap * cap + (pb_bytes + 7) / 8 + 1) & ~1ull;
   int grid = (int)std::min<uint64_t>(n_seqs, (uint64_t)sm_count * FOLD_CTAS);
   grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)grid, ((uint64_t)8 << 30) / (stride * sizeof(double))));
   bool ok = upload(&d_tab, &T, sizeof(T)) && upload(&d_hp, hpS.data(), hpS.size() * 8) && upload(&d_sp, sp.data(), sp.size() * 8) &&
@@ -565,10 +582,13 @@ cudaError_t run_fold(const stemk_fold_model& m, uint32_t n_seqs, const uint64_t*
   cudaMemsetAsync(d_prof, 0, 16 * sizeof(unsigned long long), stream);
   L.prof = d_prof;
 #endif
-  const size_t smem = ((size_t)cap + 15) & ~(size_t)15;
+  size_t smem = ((size_t)cap + 15) & ~(size_t)15;
+  L.pb_shared = 0;
+  if (pb_bytes <= 40 * 1024) { L.pb_shared = (uint32_t)smem; smem += pb_bytes; }   // longer sequences: the bits stay in the scratch (L1/L2)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEventCreate(&ev0); cudaEventCreate(&ev1);
   cudaEventRecord(ev0, stream);
+  cudaFuncSetAttribute(fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   fold_kernel<<<grid, kFoldThreads, smem, stream>>>(L);
   e = cudaGetLastError();
   cudaEventRecord(ev1, stream);
