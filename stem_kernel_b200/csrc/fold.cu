@@ -37,12 +37,6 @@
 
 #include "kernels.cuh"
 
-#ifndef FOLD_THREADS
-#define FOLD_THREADS 256
-#endif
-#ifndef FOLD_CTAS
-#define FOLD_CTAS 4
-#endif
 
 #ifdef FOLD_PROF
 #define FP_T(v) const long long v = clock64()
@@ -56,7 +50,7 @@ namespace stemk {
 
 namespace {
 
-constexpr int kTurn = 3, kMaxLoop = 30, kFoldThreads = FOLD_THREADS, kFoldWarps = kFoldThreads / 32;
+constexpr int kTurn = 3, kMaxLoop = 30;
 constexpr int kTables = 10;
 
 struct FoldTab {          // Boltzmann factors of the model; *S = with the scaling of the loop's own nucleotides
@@ -180,7 +174,12 @@ __device__ __forceinline__ double interior_sum(const FoldTab& T, const uint8_t* 
   return acc;
 }
 
-__global__ void __launch_bounds__(kFoldThreads, FOLD_CTAS) fold_kernel(const FoldLaunch P) {
+// THREADS x CTAS: 1024 x 1 for sequences of 128 nt and more -- the fewer sequences an SM has in flight, the more of
+// their tables the L2 holds (256 x 4: 108 ms, 512 x 2: 103 ms, 1024 x 1: 96 ms per 2 000 sequences of 150-300 nt) --
+// and 256 x 4 for short ones, whose diagonals cannot feed 32 warps.
+template <int kFoldThreads, int kFoldCtas>
+__global__ void __launch_bounds__(kFoldThreads, kFoldCtas) fold_kernel(const FoldLaunch P) {
+  constexpr int kFoldWarps = kFoldThreads / 32;
   extern __shared__ __align__(16) unsigned char dyn[];   // base codes of the sequence in flight: cap bytes
   __shared__ FoldTab T;
   __shared__ unsigned long long s_seq, s_base;
@@ -550,7 +549,10 @@ cudaError_t run_fold(const stemk_fold_model& m, uint32_t n_seqs, const uint64_t*
   const uint32_t pbw_cap = (max_len + 33) / 32 + 2;
   const size_t pb_bytes = (size_t)cap * pbw_cap * 4;
   const unsigned long long stride = ((unsigned long long)kTables * cap * cap + (pb_bytes + 7) / 8 + 1) & ~1ull;
-  int grid = (int)std::min<uint64_t>(n_seqs, (uint64_t)sm_count * FOLD_CTAS);
+  const bool big_cta = max_len >= 128;
+  const int fold_threads = big_cta ? 1024 : 256, fold_ctas = big_cta ? 1 : 4;
+  (void)fold_threads;
+  int grid = (int)std::min<uint64_t>(n_seqs, (uint64_t)sm_count * fold_ctas);
   grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)grid, ((uint64_t)8 << 30) / (stride * sizeof(double))));
   bool ok = upload(&d_tab, &T, sizeof(T)) && upload(&d_hp, hpS.data(), hpS.size() * 8) && upload(&d_sp, sp.data(), sp.size() * 8) &&
             upload(&d_up, up.data(), up.size() * 8) && upload(&d_codes, codes.data(), codes.size()) &&
@@ -588,8 +590,13 @@ cudaError_t run_fold(const stemk_fold_model& m, uint32_t n_seqs, const uint64_t*
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEventCreate(&ev0); cudaEventCreate(&ev1);
   cudaEventRecord(ev0, stream);
-  cudaFuncSetAttribute(fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  fold_kernel<<<grid, kFoldThreads, smem, stream>>>(L);
+  if (big_cta) {
+    cudaFuncSetAttribute(fold_kernel<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    fold_kernel<1024, 1><<<grid, 1024, smem, stream>>>(L);
+  } else {
+    cudaFuncSetAttribute(fold_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    fold_kernel<256, 4><<<grid, 256, smem, stream>>>(L);
+  }
   e = cudaGetLastError();
   cudaEventRecord(ev1, stream);
   // ---- results back to the host, pair lists put in sequence order
@@ -619,7 +626,7 @@ cudaError_t run_fold(const stemk_fold_model& m, uint32_t n_seqs, const uint64_t*
     cudaFree(d_prof);
     const double tot = h[10] ? (double)h[10] : 1.0, cells = h[8] ? (double)h[8] : 1.0, pc = h[9] ? (double)h[9] : 1.0;
     std::fprintf(stderr, "fold prof: grid %d x %d threads, %u seqs | of all warp time: setup %.1f%% inside cells %.1f%% inside barrier %.1f%% outside %.1f%% output %.1f%% | inside, cycles per cell: interior %.0f (per pair cell) ml+hairpin %.0f (per pair cell) Qm/Q sums %.0f (per cell); cells %.0f of which pairs %.0f\n",
-                 grid, kFoldThreads, n_seqs, 100.0 * h[0] / tot, 100.0 * h[4] / tot, 100.0 * h[5] / tot, 100.0 * h[6] / tot, 100.0 * h[7] / tot,
+                 grid, fold_threads, n_seqs, 100.0 * h[0] / tot, 100.0 * h[4] / tot, 100.0 * h[5] / tot, 100.0 * h[6] / tot, 100.0 * h[7] / tot,
                  h[1] / pc, h[2] / pc, h[3] / cells, cells, pc);
   }
 #endif
