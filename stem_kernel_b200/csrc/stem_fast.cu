@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(32 * (NCH > 0 ? kFastRegWarps : kFastMaxWarps)
           hi = count_len_below(yPerm, Ny, xl + band + 1u, lane);
         }
         {
-          const double xql = x23.y, xbf = x45.x;
+          const double xql = x23.y, xbf = x45.x, xup = x23.x;   // the H row is kept pre-scaled by up_x: the sweep is linear
           const uint32_t tabx = sb + L.tab + 128u * xbc;
           const uint32_t yB1a = sb + L.yB1a, yB1b = sb + L.yB1b;
           double racc = 0.0;
@@ -407,14 +407,14 @@ __global__ void __launch_bounds__(32 * (NCH > 0 ? kFastRegWarps : kFastMaxWarps)
             for (uint32_t j = 2u * lane; j <= Ny; j += 64u) sts_v2f64(rb + 8u * j, make_double2(0.0, 0.0));
             __syncwarp();
 #pragma unroll
-            for (int k = 0; k < 4; ++k) if (jr[k] != 0xffffffffu) sts_f64(rb + 8u * jr[k], mr[k]);
+            for (int k = 0; k < 4; ++k) if (jr[k] != 0xffffffffu) sts_f64(rb + 8u * jr[k], xup * mr[k]);
           } else {
             for (uint32_t tq = lo + lane; tq < hi; tq += 32u) sts_f64(mbuf + 8u * (tq - lo), match(lds_u32(yPerm + 4u * tq) & 0xffffu));
             __syncwarp();
             for (uint32_t j = 2u * lane; j <= Ny; j += 64u) sts_v2f64(rb + 8u * j, make_double2(0.0, 0.0));
             __syncwarp();
             for (uint32_t tq = lo + lane; tq < hi; tq += 32u)
-              sts_f64(rb + 8u * (lds_u32(yPerm + 4u * tq) & 0xffffu), lds_f64(mbuf + 8u * (tq - lo)));
+              sts_f64(rb + 8u * (lds_u32(yPerm + 4u * tq) & 0xffffu), xup * lds_f64(mbuf + 8u * (tq - lo)));
           }
           racc = warp_sum_all(racc);
           if (lane == 0) rowacc[i] = x45.y * racc;   // per-row slot in global scratch (L2)
@@ -476,34 +476,18 @@ __global__ void __launch_bounds__(32 * (NCH > 0 ? kFastRegWarps : kFastMaxWarps)
       PROF_T(t_b2b);
       PROF_ADD(3, t_b2a, t_b2b);
 
-      // ---- phase C: G0s(i,:) += up_x * dn_y * H(i,:), then publish the rows
-      for (uint32_t rr = 0; rr < cnt; ++rr) {
-        const uint32_t i = i0 + rr;
-        const uint32_t rb = wrows + row_bytes * rr;
-        const double xup = __ldg(&X.xnode[ps.node0 + i].up);
-        double* __restrict__ g0row = G0 + (size_t)i * NYS;
-        for (uint32_t jb = 0; jb < Ny; jb += 256u) {
-          const uint32_t j = jb + 2u * lane;
-          const uint32_t rj = rb + 8u * j;
-          double2 h0 = make_double2(0.0, 0.0), h1 = h0, h2 = h0, h3 = h0;
-          // column Ny of the buffer is the dummy column (zero), so the second element of the last pair is harmless
-          if (j < Ny) h0 = lds_v2f64(rj);
-          if (j + 64u < Ny) h1 = lds_v2f64(rj + 512u);
-          if (j + 128u < Ny) h2 = lds_v2f64(rj + 1024u);
-          if (j + 192u < Ny) h3 = lds_v2f64(rj + 1536u);
-          const bool w0 = h0.x != 0.0 || h0.y != 0.0, w1 = h1.x != 0.0 || h1.y != 0.0;
-          const bool w2 = h2.x != 0.0 || h2.y != 0.0, w3 = h3.x != 0.0 || h3.y != 0.0;
-          double2* __restrict__ gp = reinterpret_cast<double2*>(g0row + j);
-          double2 o0 = h0, o1 = h0, o2 = h0, o3 = h0;
-          if (w0) o0 = __ldcg(gp);
-          if (w1) o1 = __ldcg(gp + 32);
-          if (w2) o2 = __ldcg(gp + 64);
-          if (w3) o3 = __ldcg(gp + 96);
-          if (w0) gp[0] = make_double2(fma(xup, h0.x, o0.x), fma(xup, h0.y, o0.y));
-          if (w1) gp[32] = make_double2(fma(xup, h1.x, o1.x), fma(xup, h1.y, o1.y));
-          if (w2) gp[64] = make_double2(fma(xup, h2.x, o2.x), fma(xup, h2.y, o2.y));
-          if (w3) gp[96] = make_double2(fma(xup, h3.x, o3.x), fma(xup, h3.y, o3.y));
-        }
+      // ---- phase C: G0ss(i,:) += up_x * H(i,:), then publish the rows.  The buffers hold up_x * H already (B1 scales the
+      // band values, the sweep is linear), so a row is ADDED to its slab row by the TMA unit -- one bulk reduce-add from
+      // shared to global memory per row, no load/store wavefronts (reading the buffer, reading and writing the slab row
+      // was an eighth of the kernel's wavefronts).  One add per element onto the value phase A stored: deterministic.
+      asm volatile("fence.proxy.async;" ::: "memory");   // this lane's writes (buffer: sweep; slab: phase A) before the async proxy
+      __syncwarp();
+      if (lane == 0) {
+        for (uint32_t rr = 0; rr < cnt; ++rr)
+          asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;"
+                       ::"l"(__cvta_generic_to_global(G0 + (size_t)(i0 + rr) * NYS)), "r"(wrows + row_bytes * rr), "r"(8u * NYS) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the adds are performed: the rows may be published, the buffers reused
       }
       __threadfence_block();
       __syncwarp();
