@@ -26,7 +26,8 @@
 //   B2  y sub-level by sub-level (at most 16 nodes, sorted by length), lanes <-> (row of the block) x (node):
 //       H(i,j) += coef_j * sum_cy H(i,cy) for the nodes at or above the band (G1 is identically 0 below it:
 //       length-monotone DAG).  Only the sub-levels that hold such a node are visited (one ballot per 32 sub-levels)
-//   C   per row, lanes <-> column pairs: slab(i,j) += up_x*H(i,j) where H is non-zero, fence, raise the flags
+//   C   the buffers hold up_x*H (B1 scales the band values by up_x, the sweep is linear): a row is added to its slab row
+//       by the TMA unit (one cp.reduce.async.bulk .add.f64 per row, no load/store wavefronts), then the flags are raised
 //
 // What bounds it (ncu, profiles/r02_*): the LSU data pipe -- shared-memory wavefronts of the gathers (two thirds of
 // them in B2) plus the global wavefronts of phases A and C -- at 66-70 % of its peak; time follows the wavefront count
