@@ -1,4 +1,4 @@
-"""Timing of stemk_fold_bpp on n C3-like sequences (150-300 nt), with the oracle restatement timed on a few of them."""
+"""Timing of stemk_fold_bpp on n C3-like sequences (150-300 nt): kernel and host-buffer call (STEMK_SO selects a tuning build)."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -12,8 +12,3 @@ with fold.Folder() as f:
     for cut in (1e-2, 1e-4):
         t = time.time(); r = f.bpp(seqs, m, cutoff=cut); dt = time.time() - t
         print(f"n={n} cutoff={cut} call {dt*1e3:.1f} ms ({n/dt:.0f} seq/s), kernel {r.kernel_ms:.1f} ms ({n/r.kernel_ms*1e3:.0f} seq/s)  pairs listed {sum(len(p[0]) for p in r.pairs)}", flush=True)
-if len(sys.argv) > 2:
-    from oracle import oraclebind as O
-    t = time.time()
-    for s in seqs[:8]: O.fold_bpp(m, s)
-    print(f"oracle (1 core): {(time.time()-t)/8*1e3:.1f} ms per sequence")
