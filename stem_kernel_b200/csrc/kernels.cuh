@@ -28,7 +28,7 @@ struct StemLaunch {
 
 constexpr int kMaxFastBuckets = 8;
 #ifndef STEMK_GROUP
-#define STEMK_GROUP 6
+#define STEMK_GROUP 8
 #endif
 constexpr uint32_t kFastGroup = STEMK_GROUP;  // == kGroup of stem_fast.cu
 #ifndef STEMK_MAXWARPS
