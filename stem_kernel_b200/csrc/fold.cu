@@ -528,7 +528,8 @@ cudaError_t run_fold(const stemk_fold_model& m, uint32_t n_seqs, const uint64_t*
   }
 
   std::vector<void*> to_free;
-  auto cleanup = [&]() { for (void* q : to_free) cudaFree(q); };
+  auto cleanup = [&]() { for (void* q : to_free) cudaFree(q); to_free.clear(); };
+  struct Guard { decltype(cleanup)& f; ~Guard() { f(); } } guard{cleanup};   // also on a host-side std::bad_alloc below
   cudaError_t e = cudaSuccess;
   auto dalloc = [&](void** d, size_t bytes) -> bool {
     *d = nullptr;
