@@ -801,6 +801,7 @@ int stemk_gram(stemk_ctx* ctx, const stemk_set* train, int normalize, double* ou
   auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
     return std::chrono::duration<double, std::milli>(b - a).count(); };
   const auto tg0 = now();
+  if (timing) cudaEventRecord(ctx->ev0, ctx->stream);
   // records sorted by size, big first: the queue then hands out the expensive pairs first.  The y-major pair list
   // itself (for every record b all partners a <= b: consecutive pairs share their y record, which the stem kernel
   // stages once per group of pairs) is written by the device from the permutation: row q owns perm[q] + 1 pairs.
@@ -828,13 +829,18 @@ int stemk_gram(stemk_ctx* ctx, const stemk_set* train, int normalize, double* ou
                              (const double*)ctx->vals.p, n, normalize, (double*)ctx->matrix.p, ctx->stream);
   if (rc != STEMK_OK) return rc;
   const auto tg2 = now();
-  if (timing) CU(cudaStreamSynchronize(ctx->stream));
+  float span_ms = 0.0f;
+  if (timing) {
+    cudaEventRecord(ctx->ev1, ctx->stream);
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&span_ms, ctx->ev0, ctx->ev1);
+  }
   const auto tg3 = now();
   rc = copy_out(ctx, out, ctx->matrix.p, (size_t)n * n * sizeof(double));
   if (rc != STEMK_OK) return rc;
   if (timing)
-    std::fprintf(stderr, "stemk_gram: %u records: permutation + pair-list launch %.1f ms, enqueue %.1f ms, device %.1f ms, D2H through pinned staging %.1f ms\n", n,
-                 ms(tg0, tg1), ms(tg1, tg2), ms(tg2, tg3), ms(tg3, now()));
+    std::fprintf(stderr, "stemk_gram: %u records: permutation + pair-list launch %.1f ms, enqueue %.1f ms, device %.1f ms (span of the call's work on the stream %.1f ms), D2H through pinned staging %.1f ms\n", n,
+                 ms(tg0, tg1), ms(tg1, tg2), ms(tg2, tg3), (double)span_ms, ms(tg3, now()));
   return STEMK_OK;
 }
 
