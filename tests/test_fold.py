@@ -107,6 +107,32 @@ def enumerate_bpp(m, seq):
     return P / Z, -kT * math.log(Z), count
 
 
+def random_model(seed, temperature=25.0):
+    """A loop model with every table entry drawn at random (seeded): a swapped index or a transposed table in any of
+    the three implementations (enumeration here, oracle, CUDA) shows up as a mismatch."""
+    rng = np.random.default_rng(seed)
+    m = O.fold_model_default()
+    m.temperature = temperature
+    for t in range(1, 7):
+        for u in range(1, 7):
+            m.stack[t][u] = float(rng.uniform(-3.5, 0.5))
+        m.ml_intern[t] = float(rng.uniform(0.0, 1.0))
+        for a in range(5):
+            m.dangle5[t][a] = float(rng.uniform(-0.8, 0.0))
+            m.dangle3[t][a] = float(rng.uniform(-0.8, 0.0))
+            for b in range(5):
+                m.mismatch_h[t][a][b] = float(rng.uniform(-1.5, 0.0))
+                m.mismatch_i[t][a][b] = float(rng.uniform(-1.0, 0.7))
+    for u in range(31):
+        m.hairpin[u] = float(rng.uniform(3.0, 7.0))
+        m.bulge[u] = float(rng.uniform(2.0, 6.0))
+        m.interior[u] = float(rng.uniform(1.0, 5.0))
+    m.ninio, m.max_ninio = float(rng.uniform(0.2, 0.8)), float(rng.uniform(1.0, 3.0))
+    m.terminal_au = float(rng.uniform(0.0, 1.0))
+    m.ml_closing, m.ml_base = float(rng.uniform(1.0, 4.0)), float(rng.uniform(0.0, 0.3))
+    return m
+
+
 SHORT = ["gggaaaccc", "gcgcuuuugcgc", "ggaaacgaaacgcc", "gggaaauccgaaaggaaaccc"[:18], "gacuuagguuaccgagucu"[:17],
          "gugucgaaagacgaaaguc"[:18], "ggnaaaccc", "aaaaaaaa", "gcgaugcuuagc", "ggcgaaagccgaaaggc",
          # 7 481 / 11 029 / 13 043 / 42 860 structures: interior loops, bulges and multiloops with several branch layouts
@@ -122,6 +148,15 @@ def test_oracle_equals_exhaustive_enumeration(seq):
     assert np.allclose(got, want, rtol=1e-10, atol=1e-13), (seq, count)
     assert abs(gens - ens) < 1e-9
     assert np.allclose(unp, np.maximum(0.0, 1.0 - want[1:, 1:].sum(0) - want[1:, 1:].sum(1)), atol=1e-12)
+
+
+@pytest.mark.parametrize("seq", ["gggcgcaagcgcgcaagcgccc", "gcgguuagcgcaaugcgcuagc", "gacuuagguuaccgagu", "ggugcgaaagcaugcgaaagcacc"])
+@pytest.mark.parametrize("seed", [1, 2])
+def test_oracle_equals_exhaustive_enumeration_random_model(seq, seed):
+    m = random_model(seed)
+    want, ens, _ = enumerate_bpp(m, seq)
+    got, gens, _ = O.fold_bpp(m, seq)
+    assert np.allclose(got, want, rtol=1e-10, atol=1e-13) and abs(gens - ens) < 1e-9
 
 
 def test_enumeration_covers_multiloops():
@@ -186,6 +221,13 @@ def test_device_fold_equals_oracle():
             got[i, j] = True
             assert np.all(got[sure]) and not np.any(got & ~maybe)
             assert np.all(np.diff(i * (len(s) + 1) + j) > 0)
+        # a model with random tables at another temperature
+        rm = random_model(7, temperature=30.0)
+        rm2 = fold.FoldModel.from_buffer_copy(rm)
+        res = f.bpp(seqs[-6:], rm2, cutoff=0.0, dense=True)
+        for k, s in enumerate(seqs[-6:]):
+            want, ens, _ = O.fold_bpp(rm, s)
+            assert relerr(res.dense[k], want) < 1e-9 and abs(res.ensemble[k] - ens) <= 1e-9 * max(1.0, abs(ens))
         # scaling and the no-GU switch
         m.pf_scale = 1.1
         m.no_gu = 1
