@@ -246,7 +246,9 @@ typedef struct stemk_bpla_set {
 } stemk_bpla_set;
 
 /* out[k] = k_bpla(x[xi[k]], y[yi[k]]) on the context's device (host buffers; the two sets are copied to the
- * device by the call).  The context's own kernel kind is irrelevant here.  No CPU path. */
+ * device by the call).  The context's own kernel kind is irrelevant here.  No CPU path.  Length limit: a warp keeps
+ * one row of the five tables in shared memory (64 B per column of the second sequence, 4 warps per CTA): second
+ * sequences of up to about 900 columns; longer ones fail the call with STEMK_ERR_NOMEM. */
 int stemk_bpla_pairs(stemk_ctx* ctx, const stemk_bpla_params* params, const stemk_bpla_set* x, const stemk_bpla_set* y,
                      size_t n_pairs, const uint32_t* xi, const uint32_t* yi, double* out);
 
@@ -280,7 +282,9 @@ typedef struct stemk_nstem_set {
   const float* bp;
 } stemk_nstem_set;
 
-/* out[k] = k_stem_naive(x[xi[k]], y[yi[k]]) on the context's device (host buffers).  No CPU path. */
+/* out[k] = k_stem_naive(x[xi[k]], y[yi[k]]) on the context's device (host buffers).  No CPU path.  Length limit: two
+ * planes of the SHORTER sequence of a pair live in shared memory (16 B x (L+2)^2: about 115 characters); as in the
+ * reference this O(Lx^2 Ly^2) kernel is for short sequences.  Longer pairs fail the call with STEMK_ERR_NOMEM. */
 int stemk_nstem_pairs(stemk_ctx* ctx, const stemk_nstem_params* params, const stemk_nstem_set* x, const stemk_nstem_set* y,
                       size_t n_pairs, const uint32_t* xi, const uint32_t* yi, double* out);
 
