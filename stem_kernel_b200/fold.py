@@ -86,4 +86,21 @@ class Folder:
         return FoldResult(pairs, unpaired, ens, dl if dense else None, float(lib.stemk_fold_last_ms(self.ctx.h)))
 
 
-__all__ = ["FoldModel", "FoldResult", "Folder", "default_model", "StemkError"]
+def build_mdata(seqs, th=0.01, model=None, cutoff=0.0, folder=None, n_threads=None):
+    """The reference's Data(const IS&, float th, ...) constructor for a batch of single sequences (data.cpp:324-345) with
+    the device in the place of ViennaRNA: base-pair probabilities of all sequences in one stemk_fold_bpp call, then
+    Profiler + DAGBuilder on the host threads (hostlib.build_many).  cutoff: pairs below it are not handed to the front
+    end (0 keeps every pair, like the dense BPMatrix the reference reads; any value below th gives the same DAG)."""
+    from . import hostlib
+    own = folder is None
+    folder = folder if folder is not None else Folder()
+    try:
+        res = folder.bpp(seqs, model, cutoff=cutoff)
+    finally:
+        if own:
+            folder.close()
+    recs = [dict(rows=[s], bp=[res.pairs[k]], label=1) for k, s in enumerate(seqs)]
+    return hostlib.build_many(recs, th, n_threads)
+
+
+__all__ = ["FoldModel", "FoldResult", "Folder", "build_mdata", "default_model", "StemkError"]

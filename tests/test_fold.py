@@ -264,10 +264,10 @@ def test_fold_feeds_the_front_end_and_the_kernel():
     m = fold.default_model()
     with fold.Folder() as f:
         res = f.bpp(seqs, m, cutoff=0.0)
-    md_dev, md_cpu = [], []
+    md_dev, md_cpu = fold.build_mdata(seqs, 0.01, m), []
     for k, s in enumerate(seqs):
         i, j, p = res.pairs[k]
-        md_dev.append(hostlib.MData.from_record(dict(rows=[s], bp=[(i, j, p)], label=1), 0.01))
+        assert hostlib.MData.from_record(dict(rows=[s], bp=[(i, j, p)], label=1), 0.01).sizes() == md_dev[k].sizes()
         want = O.fold_bpp(m, s)[0]
         wi, wj = np.nonzero(want)
         md_cpu.append(hostlib.MData.from_record(dict(rows=[s], bp=[(wi, wj, want[wi, wj])], label=1), 0.01))
