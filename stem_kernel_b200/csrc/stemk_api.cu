@@ -69,6 +69,7 @@ struct stemk_ctx {
   double* d_pair_tab = nullptr;
   double* d_subst = nullptr;
   unsigned long long* d_counter = nullptr;
+  DevBuf blob_cache;                           // device image of the last freed set, handed to the next stemk_upload that fits
   DevBuf scratch, scratch_big, fold_scratch, carry, tmp_stem, tmp_str, idx_x, idx_y, vals, matrix, order, rowacc;
   DevBuf perm, offs, diag, selfv, diag_idx, diag_vals, diag_idx2, diag_vals2;
   DevBuf deal_x, deal_y, gathered, undealt;     // stemk_gram_multi: this device's share of the pair list; on device 0 the gather
@@ -254,7 +255,7 @@ void stemk_destroy(stemk_ctx* c) {
   if (c->device == STEMK_DEVICE_NONE) { delete c; return; }
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  for (DevBuf* b : {&c->scratch, &c->scratch_big, &c->fold_scratch, &c->carry, &c->tmp_stem, &c->tmp_str, &c->idx_x, &c->idx_y, &c->vals, &c->matrix, &c->order, &c->rowacc,
+  for (DevBuf* b : {&c->blob_cache, &c->scratch, &c->scratch_big, &c->fold_scratch, &c->carry, &c->tmp_stem, &c->tmp_str, &c->idx_x, &c->idx_y, &c->vals, &c->matrix, &c->order, &c->rowacc,
                     &c->perm, &c->offs, &c->diag, &c->selfv, &c->diag_idx, &c->diag_vals, &c->diag_idx2, &c->diag_vals2,
                     &c->deal_x, &c->deal_y, &c->gathered, &c->undealt}) b->release();
   if (c->multi_ev) cudaEventDestroy(c->multi_ev);
@@ -330,7 +331,14 @@ int stemk_upload(stemk_ctx* ctx, const stemk_seqset_desc* desc, stemk_set** out)
   const CompiledSet& h = s->host;
   for (int k = 0; k < kBlobArrays; ++k) s->lay[k] = h.blob_lay[k];
   const auto t1 = std::chrono::steady_clock::now();
-  cudaError_t e = s->blob.reserve(std::max<size_t>(h.blob_bytes, 256));
+  // A caller that uploads a set per call (upload, gram, free, ...) would otherwise allocate and free ~100 KB per record
+  // of device memory every time; the image of the last freed set is kept and reused when it fits without waste.
+  const size_t need = std::max<size_t>(h.blob_bytes, 256);
+  if (ctx->blob_cache.p && ctx->blob_cache.bytes >= need && ctx->blob_cache.bytes <= need + need / 4) {
+    s->blob = ctx->blob_cache;
+    ctx->blob_cache = DevBuf();
+  }
+  cudaError_t e = s->blob.reserve(need);
   if (e == cudaSuccess) e = cudaMemcpyAsync(s->blob.p, ctx->upload_stage, h.blob_bytes, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) { s->blob.release(); delete s; return cuda_fail(ctx, e, "set upload"); }
@@ -346,6 +354,11 @@ int stemk_upload(stemk_ctx* ctx, const stemk_seqset_desc* desc, stemk_set** out)
 void stemk_set_free(stemk_ctx* ctx, stemk_set* s) {
   if (!s) return;
   if (ctx && ctx->device != STEMK_DEVICE_NONE) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+  if (ctx && ctx->device != STEMK_DEVICE_NONE && s->device == ctx->device && s->blob.p && s->blob.bytes > ctx->blob_cache.bytes) {
+    ctx->blob_cache.release();          // keep the larger of the two images for the next upload
+    ctx->blob_cache = s->blob;
+    s->blob = DevBuf();
+  }
   s->blob.release();
   delete s;
 }
@@ -499,7 +512,7 @@ void stemk_set_stats(const stemk_set* s, uint32_t* n_nodes, uint32_t* n_edges, u
   }
 }
 
-uint64_t stemk_set_device_bytes(const stemk_set* s) { return s ? (uint64_t)s->blob.bytes : 0; }
+uint64_t stemk_set_device_bytes(const stemk_set* s) { return s && s->blob.p ? (uint64_t)std::max<size_t>(s->host.blob_bytes, 256) : 0; }
 
 // -------------------------------------------------------------------------- pair evaluator
 int stemk_pairs_device(stemk_ctx* ctx, const stemk_set* x, const stemk_set* y, size_t n_pairs, const uint32_t* d_xi,
